@@ -1,0 +1,160 @@
+"""Pins the oracle (oracle/frad_oracle.py, oracle/rs.py) against vectors produced by the
+unmodified reference (oracle/make_golden.py -> tests/golden/*.npz) and public KATs."""
+import zlib
+
+import numpy as np
+import pytest
+
+from oracle import frad_oracle as O
+from oracle import rs as R
+
+
+# ---------------------------------------------------------------- public known-answer vectors
+def test_crc_check_values(g_crc):
+    assert O.crc16_arc(b"123456789") == 0xBB3D == int(g_crc["crc16_check"][0])
+    assert O.crc32(b"123456789") == 0xCBF43926 == O.crc32_table(b"123456789")
+
+
+def test_rs_kats():
+    d = bytes.fromhex("40d2754776173206272696c6c69670ec")
+    assert R.encode_msg(d, 10)[16:].hex() == "bc2a90136bafeffd4be0"
+    assert bytes(R.RSCodec(10).encode(b"hello world")) == b"hello world\xed%T\xc4\xfd\xfd\x89\xf3\xa8\xaa"
+
+
+def test_rs_correction_limits():
+    rng = np.random.default_rng(0)
+    for k, nsym in ((96, 24), (17, 24), (200, 55), (1, 2)):
+        msg = rng.integers(0, 256, k, dtype=np.uint8).tobytes()
+        cw = R.encode_msg(msg, nsym)
+        t = nsym // 2
+        for ne in {0, 1, t}:
+            w = bytearray(cw)
+            for p in rng.choice(len(w), size=min(ne, len(w)), replace=False):
+                w[p] ^= int(rng.integers(1, 256))
+            got, nfix = R.correct_word(bytes(w), nsym)
+            assert got == msg and nfix == min(ne, len(w))
+    msg = rng.integers(0, 256, 96, dtype=np.uint8).tobytes()
+    w = bytearray(R.encode_msg(msg, 24))
+    for p in rng.choice(120, size=30, replace=False):
+        w[p] ^= int(rng.integers(1, 256))
+    with pytest.raises(R.ReedSolomonError):
+        R.correct_word(bytes(w), 24)
+
+
+def test_crc_golden(g_crc):
+    for n in (0, 1, 9, 255, 4096, 20488):
+        b = g_crc[f"crc_in_{n}"].tobytes()
+        assert O.crc16_arc(b) == int(g_crc[f"crc16_{n}"][0])
+        assert O.crc32(b) == int(g_crc[f"crc32_{n}"][0]) == O.crc32_table(b)
+
+
+def test_ecc_golden(g_crc):
+    for key in g_crc.files:
+        if not key.startswith("ecc_in_"):
+            continue
+        _, _, n, ds, cs = key.split("_")
+        enc = O.ecc_encode(g_crc[key].tobytes(), int(ds), int(cs))
+        assert enc == g_crc[f"ecc_out_{n}_{ds}_{cs}"].tobytes()
+        assert O.ecc_decode(enc, int(ds), int(cs), True) == g_crc[key].tobytes()
+        assert O.ecc_decode(enc, int(ds), int(cs), False) == g_crc[key].tobytes()
+
+
+# ---------------------------------------------------------------- profile 0
+@pytest.mark.parametrize("bits", [12, 16, 24, 32, 48, 64])
+@pytest.mark.parametrize("le", [0, 1])
+def test_p0_golden(g_p0, bits, le):
+    fr = g_p0["pcm_f32"]
+    pay = b"".join(O.p0_analogue(f, bits, 48000, bool(le))[0] for f in fr)
+    assert pay == g_p0[f"pay_f32_b{bits}_le{le}"].tobytes()
+    per = len(pay) // len(fr)
+    dec = np.stack([O.p0_digital(pay[i * per:(i + 1) * per], O.P0_DEPTHS.index(bits), 2, bool(le)) for i in range(len(fr))])
+    assert np.array_equal(dec, g_p0[f"dec_f32_b{bits}_le{le}"])
+
+
+def test_p0_golden_f64_and_ragged(g_p0):
+    fr = g_p0["pcm_f32"].astype(np.float64)
+    for bits in (16, 32, 64):
+        pay = b"".join(O.p0_analogue(f, bits, 48000, False)[0] for f in fr)
+        assert pay == g_p0[f"pay_f64_b{bits}_le0"].tobytes()
+    for key in g_p0.files:
+        if not key.startswith("rag_in_"):
+            continue
+        _, _, n, c = key.split("_")
+        x = g_p0[key]
+        pay = O.p0_analogue(x, 32, 44100, False)[0]
+        assert pay == g_p0[f"rag_pay_{n}_{c}"].tobytes()
+        assert np.array_equal(O.p0_digital(pay, 3, int(c), False), g_p0[f"rag_dec_{n}_{c}"])
+        pay = O.p0_analogue(x.astype(np.float64), 64, 44100, True)[0]
+        assert pay == g_p0[f"rag_pay64_{n}_{c}"].tobytes()
+        assert np.array_equal(O.p0_digital(pay, 5, int(c), True), g_p0[f"rag_dec64_{n}_{c}"])
+
+
+def test_p0_edge_golden(g_p0):
+    pay = O.p0_analogue(g_p0["odd12_in"], 12, 48000, False)[0]
+    assert pay == g_p0["odd12_pay"].tobytes()
+    assert np.array_equal(O.p0_digital(pay, 0, 1, False), g_p0["odd12_dec"])
+    pay, idx, _, _ = O.p0_analogue(g_p0["bump_in"], 16, 48000, False)
+    assert idx == int(g_p0["bump_idx"][0]) and pay == g_p0["bump_pay"].tobytes()
+    assert np.array_equal(O.p0_digital(g_p0["scrub_pay"].tobytes(), 3, 2, False), g_p0["scrub_dec"])
+
+
+def test_dct_definition():
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((300, 1))
+    assert np.allclose(O.dct2_forward(x)[0], O.dct2_direct_f64(x[:, 0]), atol=1e-14)
+
+
+# ---------------------------------------------------------------- profile 1
+P1_CASES = ["s48", "s48f64", "s96c8", "s44n1280", "s8n128", "s96n128", "s32n7168", "s48rag"]
+
+
+@pytest.mark.parametrize("name", P1_CASES)
+def test_p1_golden(g_p1, name):
+    sr, c, n, bits, ll = g_p1[f"{name}_meta"]
+    sr, c, n, bits = int(sr), int(c), int(n), int(bits)
+    fr = g_p1[f"{name}_pcm"]
+    for i, f in enumerate(fr):
+        q, tq, nn, b2, sr2 = O.p1_analogue_ints(f, bits, sr, float(ll))
+        assert np.array_equal(q, g_p1[f"{name}_q"][i])
+        assert np.array_equal(tq, g_p1[f"{name}_tq"][i])
+        pay = O.p1_pack(q, tq)
+        if i == 0:
+            assert pay == g_p1[f"{name}_pay0"].tobytes()
+        dec = O.p1_digital(pay, O.P1_DEPTHS.index(b2), c, sr2, nn)
+        assert np.array_equal(dec, g_p1[f"{name}_dec"][i])
+
+
+def test_p1_tools_golden(g_p1):
+    thr = O.p1_thresholds(g_p1["tool_spec"], 48000, 0.55)
+    assert np.array_equal(thr, g_p1["tool_thr"])
+    assert np.array_equal(O.p1_divisors(thr, 2048, 48000), g_p1["tool_div"])
+    assert O.golomb_encode(g_p1["gol_in"]) == g_p1["gol_out"].tobytes()
+    assert np.array_equal(O.golomb_decode(g_p1["gol_out"].tobytes()), g_p1["gol_in"])
+    assert O.golomb_encode(np.zeros(17, dtype=int)) == g_p1["gol_zero_out"].tobytes()
+    assert O.golomb_encode(np.array([], dtype=int)) == b"\x00"
+    q, tq, *_ = O.p1_analogue_ints(np.zeros((2048, 2), np.float32), 16, 48000, 0.55)
+    assert np.array_equal(q, g_p1["zero_q"]) and np.array_equal(tq, g_p1["zero_tq"])
+
+
+# ---------------------------------------------------------------- profile 2
+@pytest.mark.parametrize("name", ["s48", "s96c8", "s44n640"])
+def test_p2_golden(g_p2, name):
+    sr, c, n, bits, ll = g_p2[f"{name}_meta"]
+    sr, c, n, bits = int(sr), int(c), int(n), int(bits)
+    engaged = 0
+    for i, f in enumerate(g_p2[f"{name}_pcm"]):
+        q, tq, lpc, nn, b2, sr2 = O.p2_analogue_ints(f, bits, sr, float(ll))
+        assert np.array_equal(q, g_p2[f"{name}_q"][i])
+        assert np.array_equal(tq, g_p2[f"{name}_tq"][i])
+        assert np.array_equal(lpc, g_p2[f"{name}_lpc"][i])
+        engaged += int(np.any(lpc))
+        dec = O.p2_digital(O.p2_pack(q, tq, lpc), O.P2_DEPTHS.index(b2), c, sr2, nn)
+        assert np.array_equal(dec, g_p2[f"{name}_dec"][i])
+    if name == "s48":
+        assert engaged > 0, "golden set must exercise TNS"
+
+
+def test_p2_tools_golden(g_p2):
+    res, aq = O.tns_analysis(g_p2["tool_x"])
+    assert np.array_equal(aq, g_p2["tool_aq"]) and np.array_equal(res, g_p2["tool_res"])
+    assert np.array_equal(O.tns_synthesis(res, aq), g_p2["tool_syn"])
