@@ -1,0 +1,336 @@
+"""ctypes binding of libfradb200.so (include/fradb200.h) -- the only way the package reaches the GPU.
+
+There is deliberately no CPU fallback: if the shared library is missing, or no CUDA device can be
+opened, importing is fine but creating a :class:`Context` raises :class:`FradError`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libfradb200.so")
+
+F32, F64, S8, S16, S32, S64, U8, U16, U32, U64, F16 = range(11)
+PREC_REF, PREC_F32, PREC_F64 = 0, 1, 2
+NBANDS, LPC_LEN = 27, 13
+
+_NP2CODE = {
+    np.dtype("<f4"): F32, np.dtype("<f8"): F64, np.dtype("i1"): S8, np.dtype("<i2"): S16, np.dtype("<i4"): S32,
+    np.dtype("<i8"): S64, np.dtype("u1"): U8, np.dtype("<u2"): U16, np.dtype("<u4"): U32, np.dtype("<u8"): U64,
+    np.dtype("<f2"): F16,
+}
+
+
+class FradError(RuntimeError):
+    pass
+
+
+def dtype_code(dt) -> int:
+    dt = np.dtype(dt)
+    if dt.byteorder == ">":
+        raise FradError("big-endian PCM must be byte-swapped before it reaches the device")
+    try:
+        return _NP2CODE[dt.newbyteorder("<") if dt.itemsize > 1 else dt]
+    except KeyError:
+        raise FradError(f"unsupported PCM dtype {dt}") from None
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def lib():
+    """Load libfradb200.so once; raises FradError when it has not been built."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(_LIB_PATH):
+            raise FradError(f"{_LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "(there is no CPU fallback)")
+        L = C.CDLL(_LIB_PATH)
+        vp, i32, i64, u32, sz, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_uint32, C.c_size_t, C.c_double
+        sig = {
+            "frad_ctx_create": (i32, [i32, C.POINTER(vp)]),
+            "frad_ctx_destroy": (None, [vp]),
+            "frad_last_error": (C.c_char_p, [vp]),
+            "frad_sync": (i32, [vp]),
+            "frad_stream": (vp, [vp]),
+            "frad_device_count": (i32, []),
+            "frad_sm_count": (i32, [vp]),
+            "frad_kernel_launches": (C.c_uint64, [vp]),
+            "frad_host_alloc": (vp, [vp, sz]),
+            "frad_host_free": (None, [vp, vp]),
+            "frad_dev_alloc": (vp, [vp, sz]),
+            "frad_dev_free": (None, [vp, vp]),
+            "frad_h2d": (i32, [vp, vp, vp, sz]),
+            "frad_d2h": (i32, [vp, vp, vp, sz]),
+            "frad_memset_dev": (i32, [vp, vp, i32, sz]),
+            "frad_event_record": (i32, [vp, i32]),
+            "frad_event_elapsed_ms": (i32, [vp, i32, i32, C.POINTER(C.c_float)]),
+            "frad_p0_payload_bytes": (sz, [i32, i32, i32]),
+            "frad_p0_encode_dev": (i32, [vp, vp, i32, i64, i32, i32, i32, i32, i32, i32, vp, sz, vp]),
+            "frad_p0_decode_dev": (i32, [vp, vp, sz, i32, i32, i32, i32, i32, i32, vp, i32]),
+            "frad_p0_encode": (i32, [vp, vp, i32, i64, i32, i32, i32, i32, i32, i32, vp, sz, vp, vp]),
+            "frad_p0_decode": (i32, [vp, vp, sz, i32, i32, i32, i32, i32, i32, vp, i32]),
+            "frad_p1_encode_dev": (i32, [vp, vp, i32, i64, i32, i32, i32, i32, i32, dbl, i32, vp, vp, vp]),
+            "frad_p1_decode_dev": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, i32]),
+            "frad_p1_encode": (i32, [vp, vp, i32, i64, i32, i32, i32, i32, i32, dbl, i32, vp, vp, vp]),
+            "frad_p1_decode": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, i32]),
+            "frad_crc32_dev": (i32, [vp, vp, vp, vp, sz, u32, i32, vp]),
+            "frad_crc16_dev": (i32, [vp, vp, vp, vp, sz, u32, i32, vp]),
+            "frad_crc32": (i32, [vp, vp, vp, vp, sz, u32, i32, sz, vp]),
+            "frad_crc16": (i32, [vp, vp, vp, vp, sz, u32, i32, sz, vp]),
+            "frad_rs_encoded_len": (sz, [sz, i32, i32]),
+            "frad_rs_decoded_len": (sz, [sz, i32, i32]),
+            "frad_rs_encode_dev": (i32, [vp, vp, vp, vp, sz, u32, i32, i32, i32, vp, vp, sz]),
+            "frad_rs_decode_dev": (i32, [vp, vp, vp, vp, sz, u32, i32, i32, i32, i32, vp, vp, sz, vp, vp]),
+            "frad_rs_encode": (i32, [vp, vp, vp, vp, sz, u32, i32, sz, i32, i32, vp, vp, sz, sz]),
+            "frad_rs_decode": (i32, [vp, vp, vp, vp, sz, u32, i32, sz, i32, i32, i32, vp, vp, sz, sz, vp, vp]),
+        }
+        optional = {
+            "frad_golomb_sizes_dev": (i32, [vp, vp, i32, i32, vp, vp]),
+            "frad_golomb_pack_dev": (i32, [vp, vp, i32, i32, vp, vp, vp]),
+            "frad_golomb_unpack_dev": (i32, [vp, vp, vp, vp, i32, i32, vp, vp]),
+        }
+        for name, (res, args) in sig.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        for name, (res, args) in optional.items():
+            if hasattr(L, name):
+                fn = getattr(L, name)
+                fn.restype, fn.argtypes = res, args
+        _lib = L
+        return _lib
+
+
+EXPORTS = [
+    "frad_ctx_create", "frad_ctx_destroy", "frad_last_error", "frad_sync", "frad_stream", "frad_device_count",
+    "frad_sm_count", "frad_kernel_launches", "frad_host_alloc", "frad_host_free", "frad_dev_alloc", "frad_dev_free",
+    "frad_h2d", "frad_d2h", "frad_memset_dev", "frad_event_record", "frad_event_elapsed_ms",
+    "frad_p0_payload_bytes", "frad_p0_encode_dev", "frad_p0_decode_dev", "frad_p0_encode", "frad_p0_decode",
+    "frad_p1_encode_dev", "frad_p1_decode_dev", "frad_p1_encode", "frad_p1_decode",
+    "frad_crc32_dev", "frad_crc16_dev", "frad_crc32", "frad_crc16",
+    "frad_rs_encoded_len", "frad_rs_decoded_len", "frad_rs_encode_dev", "frad_rs_decode_dev",
+    "frad_rs_encode", "frad_rs_decode",
+]
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return a   # already an integer device address
+
+
+class DeviceBuffer:
+    """A device allocation owned by a Context (freed with the context or by .free())."""
+
+    def __init__(self, ctx: "Context", nbytes: int):
+        self.ctx, self.nbytes = ctx, int(nbytes)
+        self.ptr = lib().frad_dev_alloc(ctx.handle, self.nbytes)
+        if not self.ptr:
+            raise FradError(ctx.last_error())
+
+    def free(self):
+        if self.ptr:
+            lib().frad_dev_free(self.ctx.handle, self.ptr)
+            self.ptr = None
+
+    def __int__(self):
+        return self.ptr
+
+
+class Context:
+    """One per GPU / host thread.  Not thread-safe; distinct contexts are independent."""
+
+    def __init__(self, device: int = 0):
+        L = lib()
+        h = C.c_void_p()
+        rc = L.frad_ctx_create(int(device), C.byref(h))
+        if rc != 0:
+            raise FradError(f"frad_ctx_create({device}) failed ({rc}): {L.frad_last_error(None).decode()} "
+                            "-- this package has no CPU fallback")
+        self.handle = h
+        self.device = device
+        self._pinned = []
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def close(self):
+        if self.handle:
+            for p in self._pinned:
+                lib().frad_host_free(self.handle, p)
+            self._pinned = []
+            lib().frad_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def last_error(self) -> str:
+        return lib().frad_last_error(self.handle).decode()
+
+    def check(self, rc: int):
+        if rc != 0:
+            raise FradError(f"libfradb200 error {rc}: {self.last_error()}")
+
+    def sync(self):
+        self.check(lib().frad_sync(self.handle))
+
+    @property
+    def sm_count(self) -> int:
+        return lib().frad_sm_count(self.handle)
+
+    @property
+    def launches(self) -> int:
+        return int(lib().frad_kernel_launches(self.handle))
+
+    def pinned(self, shape, dtype) -> np.ndarray:
+        """numpy array backed by page-locked host memory (freed with the context)."""
+        dt = np.dtype(dtype)
+        n = int(np.prod(shape)) * dt.itemsize
+        p = lib().frad_host_alloc(self.handle, max(n, 1))
+        if not p:
+            raise FradError(self.last_error())
+        self._pinned.append(p)
+        buf = (C.c_char * max(n, 1)).from_address(p)
+        return np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+
+    def dev(self, nbytes: int) -> DeviceBuffer:
+        return DeviceBuffer(self, nbytes)
+
+    def h2d(self, dst, src: np.ndarray):
+        src = np.ascontiguousarray(src)
+        self.check(lib().frad_h2d(self.handle, int(dst), src.ctypes.data, src.nbytes))
+        return src   # keep alive until sync
+
+    def d2h(self, dst: np.ndarray, src, nbytes=None):
+        self.check(lib().frad_d2h(self.handle, dst.ctypes.data, int(src), dst.nbytes if nbytes is None else nbytes))
+
+    def event(self, slot: int):
+        self.check(lib().frad_event_record(self.handle, slot))
+
+    def elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_float()
+        self.check(lib().frad_event_elapsed_ms(self.handle, a, b, C.byref(ms)))
+        return float(ms.value)
+
+    # -- profile 0 ---------------------------------------------------------------------------
+    def p0_encode(self, pcm: np.ndarray, nframes: int, n: int, hop: int, bits: int, little_endian: bool,
+                  prec: int = PREC_REF, want_crc: bool = True):
+        """pcm: [samples, C] host array.  Returns (payload uint8 [B, nbytes], peak f64 [B], crc32 u32 [B] or None)."""
+        pcm = np.ascontiguousarray(pcm)
+        ch = pcm.shape[1]
+        nbytes = lib().frad_p0_payload_bytes(n, ch, bits)
+        payload = np.empty((nframes, nbytes), np.uint8)
+        peak = np.zeros(nframes, np.float64)
+        crc = np.zeros(nframes, np.uint32) if want_crc else None
+        self.check(lib().frad_p0_encode(self.handle, pcm.ctypes.data, dtype_code(pcm.dtype), hop, nframes, n, ch, bits,
+                                         int(little_endian), prec, payload.ctypes.data, nbytes, peak.ctypes.data,
+                                         _ptr(crc)))
+        return payload, peak, crc
+
+    def p0_decode(self, payload: np.ndarray, nframes: int, n: int, ch: int, bits: int, little_endian: bool,
+                  prec: int = PREC_REF, out_dtype=np.float64) -> np.ndarray:
+        payload = np.ascontiguousarray(payload, dtype=np.uint8).reshape(nframes, -1)
+        out = np.empty((nframes, n, ch), out_dtype)
+        self.check(lib().frad_p0_decode(self.handle, payload.ctypes.data, payload.shape[1], nframes, n, ch, bits,
+                                         int(little_endian), prec, out.ctypes.data, dtype_code(out.dtype)))
+        return out
+
+    # -- profiles 1 / 2 ------------------------------------------------------------------------
+    def p1_encode(self, pcm: np.ndarray, nframes: int, n: int, hop: int, bits: int, srate: int, loss_level: float,
+                  prec: int = PREC_REF, profile: int = 1):
+        pcm = np.ascontiguousarray(pcm)
+        ch = pcm.shape[1]
+        q = np.empty((nframes, n * ch), np.int32)
+        tq = np.empty((nframes, NBANDS * ch), np.int32)
+        lpc = np.empty((nframes, LPC_LEN * ch), np.int32) if profile == 2 else None
+        self.check(lib().frad_p1_encode(self.handle, pcm.ctypes.data, dtype_code(pcm.dtype), hop, nframes, n, ch, bits,
+                                         srate, float(loss_level), prec, q.ctypes.data, tq.ctypes.data, _ptr(lpc)))
+        return q, tq, lpc
+
+    def p1_decode(self, q: np.ndarray, tq: np.ndarray, lpc, nframes: int, n: int, ch: int, bits: int, srate: int,
+                  prec: int = PREC_REF, out_dtype=np.float64) -> np.ndarray:
+        q = np.ascontiguousarray(q, dtype=np.int32)
+        tq = np.ascontiguousarray(tq, dtype=np.int32)
+        if lpc is not None:
+            lpc = np.ascontiguousarray(lpc, dtype=np.int32)
+        out = np.empty((nframes, n, ch), out_dtype)
+        self.check(lib().frad_p1_decode(self.handle, q.ctypes.data, tq.ctypes.data, _ptr(lpc), nframes, n, ch, bits,
+                                         srate, prec, out.ctypes.data, dtype_code(out.dtype)))
+        return out
+
+    # -- CRC / RS over host byte strings ---------------------------------------------------------
+    @staticmethod
+    def _index(chunks):
+        lens = np.fromiter((len(c) for c in chunks), dtype=np.uint32, count=len(chunks))
+        offs = np.zeros(len(chunks), np.uint64)
+        if len(chunks) > 1:
+            np.cumsum(((lens[:-1].astype(np.uint64) + 15) // 16) * 16, out=offs[1:])   # keep messages 16-byte aligned
+        total = int(offs[-1] + lens[-1]) if len(chunks) else 0
+        buf = np.zeros(max(total, 1), np.uint8)
+        for c, o in zip(chunks, offs):
+            buf[int(o):int(o) + len(c)] = np.frombuffer(c, np.uint8)
+        return buf, offs, lens, total
+
+    def crc_many(self, chunks, bits32: bool) -> np.ndarray:
+        """CRC-32 (bits32) or CRC-16/ARC of every byte string in ``chunks``."""
+        if not chunks:
+            return np.zeros(0, np.uint32)
+        buf, offs, lens, total = self._index(chunks)
+        out = np.zeros(len(chunks), np.uint32)
+        fn = lib().frad_crc32 if bits32 else lib().frad_crc16
+        self.check(fn(self.handle, buf.ctypes.data, offs.ctypes.data, lens.ctypes.data, 0, 0, len(chunks), total,
+                      out.ctypes.data))
+        return out
+
+    def rs_encode_many(self, chunks, dsize: int, csize: int):
+        if not chunks:
+            return []
+        buf, offs, lens, total = self._index(chunks)
+        olens = np.array([lib().frad_rs_encoded_len(int(n), dsize, csize) for n in lens], np.uint64)
+        ooffs = np.zeros(len(chunks), np.uint64)
+        if len(chunks) > 1:
+            np.cumsum(((olens[:-1] + 15) // 16) * 16, out=ooffs[1:])
+        ototal = int(ooffs[-1] + olens[-1])
+        out = np.zeros(max(ototal, 1), np.uint8)
+        self.check(lib().frad_rs_encode(self.handle, buf.ctypes.data, offs.ctypes.data, lens.ctypes.data, 0, 0,
+                                         len(chunks), total, dsize, csize, out.ctypes.data, ooffs.ctypes.data, 0, ototal))
+        return [out[int(o):int(o + n)].tobytes() for o, n in zip(ooffs, olens)]
+
+    def rs_decode_many(self, chunks, dsize: int, csize: int, repair: bool):
+        """Returns (list of data byte strings, failed codewords per message, corrected bytes per message)."""
+        if not chunks:
+            return [], np.zeros(0, np.int32), np.zeros(0, np.int32)
+        buf, offs, lens, total = self._index(chunks)
+        olens = np.array([lib().frad_rs_decoded_len(int(n), dsize, csize) for n in lens], np.uint64)
+        ooffs = np.zeros(len(chunks), np.uint64)
+        if len(chunks) > 1:
+            np.cumsum(((olens[:-1] + 15) // 16) * 16, out=ooffs[1:])
+        ototal = int(ooffs[-1] + olens[-1])
+        out = np.zeros(max(ototal, 1), np.uint8)
+        status = np.zeros(len(chunks), np.int32)
+        fixed = np.zeros(len(chunks), np.int32)
+        self.check(lib().frad_rs_decode(self.handle, buf.ctypes.data, offs.ctypes.data, lens.ctypes.data, 0, 0,
+                                         len(chunks), total, dsize, csize, int(bool(repair)), out.ctypes.data,
+                                         ooffs.ctypes.data, 0, ototal, status.ctypes.data, fixed.ctypes.data))
+        return [out[int(o):int(o + n)].tobytes() for o, n in zip(ooffs, olens)], status, fixed
+
+
+_default = {}
+
+
+def default_context(device: int = 0) -> Context:
+    """Process-wide context per device, created on first use (raises FradError without a GPU)."""
+    ctx = _default.get(device)
+    if ctx is None:
+        ctx = _default[device] = Context(device)
+    return ctx

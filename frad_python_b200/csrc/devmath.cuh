@@ -1,0 +1,192 @@
+// Device helpers shared by the transform kernels: complex arithmetic, small DFTs, PCM sample
+// conversion, profile-0 value packing.
+#pragma once
+#include <cuda_fp16.h>
+#include <cstdint>
+#include "../../include/fradb200.h"
+
+template <typename T> struct vec2;
+template <> struct vec2<float> { typedef float2 type; };
+template <> struct vec2<double> { typedef double2 type; };
+
+template <typename T> __device__ __forceinline__ typename vec2<T>::type mk2(T x, T y) {
+  typename vec2<T>::type r; r.x = x; r.y = y; return r;
+}
+template <typename V> __device__ __forceinline__ V cmul(V a, V b) {
+  V r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r;
+}
+template <typename V> __device__ __forceinline__ V cadd(V a, V b) { V r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
+template <typename V> __device__ __forceinline__ V csub(V a, V b) { V r; r.x = a.x - b.x; r.y = a.y - b.y; return r; }
+template <typename V> __device__ __forceinline__ V cconj(V a) { a.y = -a.y; return a; }
+// multiply by -i (forward) or +i (inverse)
+template <bool INV, typename V> __device__ __forceinline__ V mul_mi(V a) {
+  V r;
+  if (INV) { r.x = -a.y; r.y = a.x; } else { r.x = a.y; r.y = -a.x; }
+  return r;
+}
+
+// ---- small DFTs, natural order in place; forward kernel exp(-2 pi i pq/R), inverse conjugated ----
+template <typename T, int R, bool INV> struct small_dft;
+
+template <typename T, bool INV> struct small_dft<T, 2, INV> {
+  typedef typename vec2<T>::type V;
+  static __device__ __forceinline__ void run(V* v) {
+    V a = v[0], b = v[1];
+    v[0] = cadd(a, b); v[1] = csub(a, b);
+  }
+};
+template <typename T, bool INV> struct small_dft<T, 4, INV> {
+  typedef typename vec2<T>::type V;
+  static __device__ __forceinline__ void run(V* v) {
+    V s02 = cadd(v[0], v[2]), d02 = csub(v[0], v[2]);
+    V s13 = cadd(v[1], v[3]), d13 = mul_mi<INV>(csub(v[1], v[3]));
+    v[0] = cadd(s02, s13); v[2] = csub(s02, s13);
+    v[1] = cadd(d02, d13); v[3] = csub(d02, d13);
+  }
+};
+template <int R> struct odd_roots;
+template <> struct odd_roots<3> {
+  static __device__ __forceinline__ double c(int i) { const double t[3] = {1.0, -0.5, -0.5}; return t[i]; }
+  static __device__ __forceinline__ double s(int i) { const double t[3] = {0.0, 0.8660254037844386, -0.8660254037844386}; return t[i]; }
+};
+template <> struct odd_roots<5> {
+  static __device__ __forceinline__ double c(int i) {
+    const double t[5] = {1.0, 0.30901699437494745, -0.8090169943749475, -0.8090169943749475, 0.30901699437494745}; return t[i]; }
+  static __device__ __forceinline__ double s(int i) {
+    const double t[5] = {0.0, 0.9510565162951535, 0.5877852522924731, -0.5877852522924731, -0.9510565162951535}; return t[i]; }
+};
+template <> struct odd_roots<7> {
+  static __device__ __forceinline__ double c(int i) {
+    const double t[7] = {1.0, 0.6234898018587336, -0.2225209339563144, -0.9009688679024191,
+                         -0.9009688679024191, -0.2225209339563144, 0.6234898018587336}; return t[i]; }
+  static __device__ __forceinline__ double s(int i) {
+    const double t[7] = {0.0, 0.7818314824680298, 0.9749279121818236, 0.4338837391175581,
+                         -0.4338837391175581, -0.9749279121818236, -0.7818314824680298}; return t[i]; }
+};
+// odd radix: y[p] = a_p -+ i b_p with a_p = v0 + sum_q cos(2 pi pq/R)(v_q + v_{R-q}), b_p = sum_q sin(2 pi pq/R)(v_q - v_{R-q})
+template <typename T, int R, bool INV> struct small_dft {
+  typedef typename vec2<T>::type V;
+  static __device__ __forceinline__ void run(V* v) {
+    constexpr int H = (R - 1) / 2;
+    V sp[H], sm[H];
+#pragma unroll
+    for (int q = 1; q <= H; q++) { sp[q - 1] = cadd(v[q], v[R - q]); sm[q - 1] = csub(v[q], v[R - q]); }
+    V y0 = v[0];
+#pragma unroll
+    for (int q = 0; q < H; q++) y0 = cadd(y0, sp[q]);
+    V out[R];
+    out[0] = y0;
+#pragma unroll
+    for (int p = 1; p <= H; p++) {
+      V a = v[0];
+      V b = mk2<T>(T(0), T(0));
+#pragma unroll
+      for (int q = 1; q <= H; q++) {
+        const T cc = (T)odd_roots<R>::c((p * q) % R);
+        const T ss = (T)odd_roots<R>::s((p * q) % R);
+        a.x += cc * sp[q - 1].x; a.y += cc * sp[q - 1].y;
+        b.x += ss * sm[q - 1].x; b.y += ss * sm[q - 1].y;
+      }
+      // forward: y[p] = a - i b ; y[R-p] = a + i b   (inverse swaps)
+      V mib = mul_mi<INV>(b);
+      out[p] = cadd(a, mib);
+      out[R - p] = csub(a, mib);
+    }
+#pragma unroll
+    for (int i = 0; i < R; i++) v[i] = out[i];
+  }
+};
+
+// ---- PCM sample formats (backend/pcmformat.py:34-62) ------------------------------------------
+template <typename T> __device__ __forceinline__ T load_pcm(const void* p, int dt, int64_t i) {
+  switch (dt) {
+    case FRAD_F32: return (T)((const float*)p)[i];
+    case FRAD_F64: return (T)((const double*)p)[i];
+    case FRAD_F16: return (T)__half2float(((const __half*)p)[i]);
+    case FRAD_S8:  return (T)((double)((const int8_t*)p)[i] / 128.0);
+    case FRAD_S16: return (T)((double)((const int16_t*)p)[i] / 32768.0);
+    case FRAD_S32: return (T)((double)((const int32_t*)p)[i] / 2147483648.0);
+    case FRAD_S64: return (T)((double)((const long long*)p)[i] / 9223372036854775808.0);
+    case FRAD_U8:  return (T)((double)((const uint8_t*)p)[i] / 128.0 - 1.0);
+    case FRAD_U16: return (T)((double)((const uint16_t*)p)[i] / 32768.0 - 1.0);
+    case FRAD_U32: return (T)((double)((const uint32_t*)p)[i] / 2147483648.0 - 1.0);
+    case FRAD_U64: return (T)((double)((const unsigned long long*)p)[i] / 9223372036854775808.0 - 1.0);
+    default: return T(0);
+  }
+}
+
+template <typename T> __device__ __forceinline__ void store_pcm(void* p, int dt, int64_t i, T v) {
+  if (dt == FRAD_F64) ((double*)p)[i] = (double)v;
+  else ((float*)p)[i] = (float)v;
+}
+
+// ---- profile-0 value <-> bytes (profile0.py:28-42, 51-66) -------------------------------------
+__device__ __forceinline__ uint16_t f2h_bits(float x) { return __half_as_ushort(__float2half_rn(x)); }
+__device__ __forceinline__ uint16_t f2h_bits(double x) { return __half_as_ushort(__double2half(x)); }
+__device__ __forceinline__ uint32_t f2f_bits(float x) { return __float_as_uint(x); }
+__device__ __forceinline__ uint32_t f2f_bits(double x) { return __float_as_uint(__double2float_rn(x)); }
+__device__ __forceinline__ uint64_t f2d_bits(float x) { return (uint64_t)__double_as_longlong((double)x); }
+__device__ __forceinline__ uint64_t f2d_bits(double x) { return (uint64_t)__double_as_longlong(x); }
+
+// writes the `bits/8`-byte image of value x at dst (bits in {16,24,32,48,64})
+template <typename T> __device__ __forceinline__ void p0_store_value(uint8_t* dst, T x, int bits, bool le) {
+  if (bits == 32 || bits == 24) {
+    uint32_t u = f2f_bits(x);
+    if (bits == 32) {
+      if (!le) u = __byte_perm(u, 0, 0x0123);
+      if ((((uintptr_t)dst) & 3) == 0) *(uint32_t*)dst = u;
+      else { dst[0] = u; dst[1] = u >> 8; dst[2] = u >> 16; dst[3] = u >> 24; }
+    } else {
+      if (!le) { dst[0] = u >> 24; dst[1] = u >> 16; dst[2] = u >> 8; }   // top three bytes, MSB first
+      else { dst[0] = u >> 8; dst[1] = u >> 16; dst[2] = u >> 24; }       // drop the LSB, keep LE order
+    }
+  } else if (bits == 64 || bits == 48) {
+    uint64_t u = f2d_bits(x);
+    if (bits == 64) {
+      if (!le) {
+        uint32_t lo = (uint32_t)u, hi = (uint32_t)(u >> 32);
+        u = ((uint64_t)__byte_perm(lo, 0, 0x0123) << 32) | __byte_perm(hi, 0, 0x0123);
+      }
+      if ((((uintptr_t)dst) & 7) == 0) *(uint64_t*)dst = u;
+      else { for (int i = 0; i < 8; i++) dst[i] = (uint8_t)(u >> (8 * i)); }
+    } else {
+      if (!le) { for (int i = 0; i < 6; i++) dst[i] = (uint8_t)(u >> (56 - 8 * i)); }
+      else { for (int i = 0; i < 6; i++) dst[i] = (uint8_t)(u >> (16 + 8 * i)); }
+    }
+  } else {  // 16
+    uint16_t h = f2h_bits(x);
+    if (!le) h = (uint16_t)((h >> 8) | (h << 8));
+    if ((((uintptr_t)dst) & 1) == 0) *(uint16_t*)dst = h;
+    else { dst[0] = (uint8_t)h; dst[1] = (uint8_t)(h >> 8); }
+  }
+}
+
+// reads one value; NaN / Inf become 0 (profile0.py:66)
+__device__ __forceinline__ double p0_load_value(const uint8_t* src, int bits, bool le) {
+  double v;
+  if (bits == 32 || bits == 24) {
+    uint32_t u;
+    if (bits == 32) {
+      u = (uint32_t)src[0] | ((uint32_t)src[1] << 8) | ((uint32_t)src[2] << 16) | ((uint32_t)src[3] << 24);
+      if (!le) u = __byte_perm(u, 0, 0x0123);
+    } else {
+      if (!le) u = ((uint32_t)src[0] << 24) | ((uint32_t)src[1] << 16) | ((uint32_t)src[2] << 8);
+      else u = ((uint32_t)src[0] << 8) | ((uint32_t)src[1] << 16) | ((uint32_t)src[2] << 24);
+    }
+    v = (double)__uint_as_float(u);
+  } else if (bits == 64 || bits == 48) {
+    uint64_t u = 0;
+    if (bits == 64) {
+      if (!le) { for (int i = 0; i < 8; i++) u = (u << 8) | src[i]; }
+      else { for (int i = 0; i < 8; i++) u |= (uint64_t)src[i] << (8 * i); }
+    } else {
+      if (!le) { for (int i = 0; i < 6; i++) u |= (uint64_t)src[i] << (56 - 8 * i); }
+      else { for (int i = 0; i < 6; i++) u |= (uint64_t)src[i] << (16 + 8 * i); }
+    }
+    v = __longlong_as_double((long long)u);
+  } else {
+    uint16_t h = le ? (uint16_t)(src[0] | (src[1] << 8)) : (uint16_t)((src[0] << 8) | src[1]);
+    v = (double)__half2float(__ushort_as_half(h));
+  }
+  return isfinite(v) ? v : 0.0;
+}

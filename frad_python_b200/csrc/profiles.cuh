@@ -1,0 +1,419 @@
+// Profile pro/epilogues fused around the transforms (device code shared by transform.cu and
+// dct2048.cu).  A "sequence" is one channel of one frame; X is its spectrum in shared or global
+// memory, type T (float or double).
+//
+// Restates (relative to src/libfrad/): fourier/profile0.py:24-42,51-66 (packing, overflow peak,
+// NaN scrub); fourier/tools/p1tools.py:15-44 (band edges, masking thresholds, divisor ramps, power-law
+// quantiser); fourier/profile1.py:26-40,65-74; fourier/tools/p2tools.py:8-111 and
+// fourier/profile2.py:32,85 (TNS).
+#pragma once
+#include "devmath.cuh"
+
+struct band_table {
+  int edge[FRAD_NBANDS + 1];   // unclipped bin edges, Python round() of N/(srate/2)*Hz
+  double ath[FRAD_NBANDS];     // min(absolute hearing threshold at band centre, 1)
+  double log_base;             // ln(e/2)
+  double base;                 // e/2
+};
+
+struct band_work {             // per-CTA shared scratch
+  double thr[FRAD_NBANDS + 1];
+  double step[FRAD_NBANDS + 1];
+  double sum[FRAD_NBANDS + 1];
+  int lo[FRAD_NBANDS + 1];
+  double red[33];
+  double r[FRAD_LPC_LEN + 3];
+  double a[FRAD_LPC_LEN + 3];
+  int aq[FRAD_LPC_LEN + 3];
+  int flag;
+  int pad_;
+};
+
+struct enc_params {
+  const void* pcm; int pcm_dtype; int64_t hop;
+  int B, N, C, profile, bits, le, fast_ok;
+  // profile 0
+  uint8_t* payload; size_t payload_stride; double* peak; uint16_t* half_scratch;
+  // profiles 1 / 2
+  double scale, loss; const band_table* bt; int32_t* q; int32_t* tq; int32_t* lpc;
+  void* gscratch; double* tns_scratch;
+};
+
+struct dec_params {
+  int B, N, C, profile, bits, le, fast_ok;
+  const uint8_t* payload; size_t payload_stride; const uint16_t* half_scratch;
+  double scale; const band_table* bt; const int32_t* q; const int32_t* tq; const int32_t* lpc;
+  void* pcm; int pcm_dtype;
+  void* gscratch; double* tns_scratch;
+};
+
+// ---- block reductions (all threads get the result) ---------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[w] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int i = 0; i < nw; i++) t += red[i];
+  return t;
+}
+__device__ __forceinline__ double block_max(double v, double* red) {
+  v = warp_max(v);
+  const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[w] = v;
+  __syncthreads();
+  double t = red[0];
+  for (int i = 1; i < nw; i++) t = fmax(t, red[i]);
+  return t;
+}
+
+// ---- profile 0 ---------------------------------------------------------------------------------
+template <typename T>
+__device__ void p0_epilogue(const enc_params& P, const T* X, int N, int b, int c, band_work* bw) {
+  const int C = P.C, bits = P.bits;
+  const bool le = P.le != 0;
+  uint8_t* frame = P.payload + (size_t)b * P.payload_stride;
+  double mx = 0.0;
+  for (int k = threadIdx.x; k < N; k += blockDim.x) {
+    const T v = X[k];
+    mx = fmax(mx, fabs((double)v));
+    const size_t vi = (size_t)k * C + c;
+    if (bits == 12) P.half_scratch[(size_t)b * N * C + vi] = (uint16_t)(f2h_bits(v) >> 4);
+    else p0_store_value<T>(frame + vi * (size_t)(bits >> 3), v, bits, le);
+  }
+  if (P.peak) {
+    mx = block_max(mx, bw->red);
+    if (threadIdx.x == 0) atomicMax((unsigned long long*)&P.peak[b], (unsigned long long)__double_as_longlong(mx));
+  }
+}
+
+template <typename T>
+__device__ void p0_prologue(const dec_params& P, T* X, int N, int b, int c) {
+  const int C = P.C, bits = P.bits;
+  const bool le = P.le != 0;
+  const uint8_t* frame = P.payload + (size_t)b * P.payload_stride;
+  for (int k = threadIdx.x; k < N; k += blockDim.x) {
+    const size_t vi = (size_t)k * C + c;
+    double v;
+    if (bits == 12) {
+      v = (double)__half2float(__ushort_as_half(P.half_scratch[(size_t)b * N * C + vi]));
+      if (!isfinite(v)) v = 0.0;
+    } else {
+      v = p0_load_value(frame + vi * (size_t)(bits >> 3), bits, le);
+    }
+    X[k] = (T)v;
+  }
+}
+
+// ---- profile 1 helpers -------------------------------------------------------------------------
+// |y|^0.75 with <= 1 ulp error: sqrt(|y| * sqrt(|y|))
+__device__ __forceinline__ double pow075(double a) { return sqrt(a * sqrt(a)); }
+
+// divisor ramp value for bin k (p1tools.py:35-41): linspace(t[b], t[b+1], len, endpoint=False)
+__device__ __forceinline__ double ramp_value(const band_work* bw, int k) {
+  if (k >= bw->lo[FRAD_NBANDS - 1]) return 0.0;    // bins past the start of the last band stay 0
+  int b = 0;
+#pragma unroll 1
+  for (int s = 16; s > 0; s >>= 1) { if (b + s <= FRAD_NBANDS - 2 && bw->lo[b + s] <= k) b += s; }
+  // lo[b] <= k < lo[b+1]
+  return __dadd_rn(__dmul_rn((double)(k - bw->lo[b]), bw->step[b]), bw->thr[b]);
+}
+
+__device__ __forceinline__ void ramp_setup(band_work* bw, const band_table* bt, int N) {
+  const int t = threadIdx.x;
+  if (t < FRAD_NBANDS - 1) {
+    const int n = bw->lo[t + 1] - bw->lo[t];
+    bw->step[t] = (n > 0) ? (bw->thr[t + 1] - bw->thr[t]) / (double)n : 0.0;
+  }
+}
+
+__device__ __forceinline__ int32_t sat_i32(double v) {
+  if (!(v == v)) return INT32_MIN;
+  if (v >= 2147483647.0) return INT32_MAX;
+  if (v <= -2147483648.0) return INT32_MIN;
+  return (int32_t)v;
+}
+
+// numpy pairwise summation order for short vectors (n < 128), used where the reference sums tiny arrays
+__device__ __forceinline__ double np_sum_small(const double* a, int n) {
+  if (n < 8) { double r = 0.0; for (int i = 0; i < n; i++) r = __dadd_rn(r, a[i]); return r; }
+  double r[8];
+  for (int j = 0; j < 8; j++) r[j] = a[j];
+  int i = 8;
+  for (; i < n - (n % 8); i += 8) for (int j = 0; j < 8; j++) r[j] = __dadd_rn(r[j], a[i + j]);
+  double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                         __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+  for (; i < n; i++) res = __dadd_rn(res, a[i]);
+  return res;
+}
+
+// ---- TNS (p2tools.py) --------------------------------------------------------------------------
+// x: masked spectrum (double, N), work: N doubles.  On return bw->flag != 0 means the residual in
+// `work` replaces x and bw->aq holds the quantised LPC; otherwise x stands and aq is all zero.
+__device__ void tns_analysis_block(const double* x, double* work, int N, band_work* bw) {
+  const int t = threadIdx.x;
+  if (t < FRAD_LPC_LEN) bw->aq[t] = 0;
+  if (t == 0) bw->flag = 0;
+  __syncthreads();
+  if (N < 2 * (FRAD_LPC_LEN - 1)) return;
+  double sl = 0.0, sa = 0.0, se = 0.0, sx = 0.0;
+  for (int n = t; n < N; n += blockDim.x) {
+    const double v = x[n], m = fabs(v);
+    sl += log(m + 1e-10); sa += m; se += v * v; sx += v;
+  }
+  sl = block_sum(sl, bw->red); sa = block_sum(sa, bw->red); se = block_sum(se, bw->red); sx = block_sum(sx, bw->red);
+  const double geo = exp(sl / N), arith = sa / N;
+  if (!(geo / (arith + 1e-10) < 0.5)) return;          // lpc_cond, p2tools.py:108-111
+  if (se < 1e-10) return;
+  // autocorrelation of the mean-removed, unit-norm signal (p2tools.py:8-15)
+  const double mean = sx / N;
+  double ss = 0.0;
+  for (int n = t; n < N; n += blockDim.x) { const double s = x[n] - mean; work[n] = s; ss += s * s; }
+  ss = block_sum(ss, bw->red);
+  const double nrm = sqrt(ss);
+  const double inv_applied = (nrm > 1e-6) ? 1.0 : 0.0;
+  __syncthreads();
+  if (inv_applied != 0.0) { for (int n = t; n < N; n += blockDim.x) work[n] = work[n] / nrm; }
+  __syncthreads();
+  double acc[FRAD_LPC_LEN];
+#pragma unroll
+  for (int l = 0; l < FRAD_LPC_LEN; l++) acc[l] = 0.0;
+  for (int n = t; n < N; n += blockDim.x) {
+    const double s0 = work[n];
+#pragma unroll
+    for (int l = 0; l < FRAD_LPC_LEN; l++) if (n + l < N) acc[l] += s0 * work[n + l];
+  }
+#pragma unroll
+  for (int l = 0; l < FRAD_LPC_LEN; l++) {
+    const double v = block_sum(acc[l], bw->red);
+    if (t == 0) { const double wl = 0.01 * l; bw->r[l] = v * exp(-0.5 * (wl * wl)); }
+  }
+  __syncthreads();
+  if (t == 0) {
+    // Levinson-Durbin (p2tools.py:17-34)
+    double a[FRAD_LPC_LEN], tmp[FRAD_LPC_LEN], prod[FRAD_LPC_LEN];
+    for (int i = 0; i < FRAD_LPC_LEN; i++) a[i] = 0.0;
+    a[0] = 1.0;
+    double err = bw->r[0];
+    if (err > 1e-10) {
+      for (int i = 1; i < FRAD_LPC_LEN; i++) {
+        for (int j = 0; j < i; j++) prod[j] = __dmul_rn(a[j], bw->r[i - j]);
+        double k = -np_sum_small(prod, i) / err;
+        if (fabs(k) >= 0.96) k = (k > 0.0) ? 0.96 : -0.96;
+        for (int j = 0; j < FRAD_LPC_LEN; j++) tmp[j] = a[j];
+        a[i] = k;
+        for (int j = 1; j < i; j++) a[j] = __dadd_rn(a[j], __dmul_rn(k, tmp[i - j]));
+        err = __dmul_rn(err, __dsub_rn(1.0, __dmul_rn(k, k)));
+        if (err <= 1e-12) break;
+      }
+    }
+    for (int j = 0; j < FRAD_LPC_LEN - 1; j++) prod[j] = fabs(a[j + 1]);
+    int ok = !(np_sum_small(prod, FRAD_LPC_LEN - 1) < 0.01);
+    int any = 0;
+    if (ok) {
+      bw->aq[0] = 0;
+      for (int j = 1; j < FRAD_LPC_LEN; j++) {
+        double v = a[j] * 15.0;
+        v = fmin(fmax(v, -15.0), 14.0);
+        const int qv = (int)rint(v);
+        bw->aq[j] = qv; any |= (qv != 0);
+      }
+    }
+    if (ok && any) {
+      bw->a[0] = 1.0;
+      for (int j = 1; j < FRAD_LPC_LEN; j++) bw->a[j] = (double)bw->aq[j] / 15.0;
+      bw->flag = 1;
+    } else {
+      for (int j = 0; j < FRAD_LPC_LEN; j++) bw->aq[j] = 0;
+    }
+  }
+  __syncthreads();
+  if (!bw->flag) return;
+  // FIR residual, lfilter(lpc_deq, [1], x): b0 x[n] + (b1 x[n-1] + (... + b12 x[n-12]))
+  double mxv = 0.0, sr = 0.0;
+  int bad = 0;
+  for (int n = t; n < N; n += blockDim.x) {
+    double a12 = 0.0;
+    bool first = true;
+#pragma unroll
+    for (int i = FRAD_LPC_LEN - 1; i >= 1; i--) {
+      if (n - i >= 0) {
+        const double p = __dmul_rn(bw->a[i], x[n - i]);
+        a12 = first ? p : __dadd_rn(a12, p);
+        first = false;
+      }
+    }
+    const double y = first ? __dmul_rn(bw->a[0], x[n]) : __dadd_rn(a12, __dmul_rn(bw->a[0], x[n]));
+    work[n] = y;
+    if (!isfinite(y)) bad = 1;
+    mxv = fmax(mxv, fabs(y));
+    sr += y;
+  }
+  mxv = block_max(mxv, bw->red);
+  const double badsum = block_sum((double)bad, bw->red);
+  sr = block_sum(sr, bw->red);
+  int accept = !(badsum > 0.0 || mxv > 1e6);
+  // prediction gain (p2tools.py:57-70)
+  const double mo = sx / N, mr = sr / N;
+  double eo = 0.0, er = 0.0;
+  for (int n = t; n < N; n += blockDim.x) {
+    const double d0 = x[n] - mo, d1 = work[n] - mr;
+    eo += d0 * d0; er += d1 * d1;
+  }
+  eo = block_sum(eo, bw->red); er = block_sum(er, bw->red);
+  double gain = 0.0;
+  if (!(eo < 1e-10 || er < 1e-10 || er >= eo)) gain = 20.0 * log10(eo / er);
+  if (gain < 0.030102999566398118) accept = 0;       // log10(2) / 10
+  __syncthreads();
+  if (t == 0 && !accept) { bw->flag = 0; for (int j = 0; j < FRAD_LPC_LEN; j++) bw->aq[j] = 0; }
+  __syncthreads();
+}
+
+// all-pole synthesis lfilter([1], a, x) by one thread, scipy's transposed direct form II order.
+// x: N doubles (input), y: N doubles (output).  Returns through bw->flag whether y is usable.
+__device__ void tns_synthesis_block(const double* x, double* y, int N, band_work* bw) {
+  if (threadIdx.x == 0) {
+    double z[FRAD_LPC_LEN];
+    for (int i = 0; i < FRAD_LPC_LEN; i++) z[i] = 0.0;
+    double mx = 0.0; int bad = 0;
+    for (int n = 0; n < N; n++) {
+      const double xn = x[n];
+      const double yn = __dadd_rn(z[0], xn);
+#pragma unroll
+      for (int i = 0; i < FRAD_LPC_LEN - 2; i++) z[i] = __dsub_rn(__dadd_rn(z[i + 1], __dmul_rn(xn, 0.0)), __dmul_rn(yn, bw->a[i + 1]));
+      z[FRAD_LPC_LEN - 2] = __dsub_rn(__dmul_rn(xn, 0.0), __dmul_rn(yn, bw->a[FRAD_LPC_LEN - 1]));
+      y[n] = yn;
+      if (!isfinite(yn)) bad = 1;
+      mx = fmax(mx, fabs(yn));
+    }
+    bw->flag = !(bad || mx > 1e6);
+  }
+  __syncthreads();
+}
+
+// ---- profile 1 / 2 encode epilogue --------------------------------------------------------------
+template <typename T>
+__device__ void p1_epilogue(const enc_params& P, const T* X, int N, int b, int c, band_work* bw, int cta) {
+  const band_table* bt = P.bt;
+  const int t = threadIdx.x, C = P.C;
+  if (t <= FRAD_NBANDS) { const int e = bt->edge[t]; bw->lo[t] = (e < N) ? e : N; }
+  __syncthreads();
+  // band energies of the scaled spectrum (p1tools.py:22,32)
+  const int w = t >> 5, lane = t & 31, nw = blockDim.x >> 5;
+  for (int band = w; band < FRAD_NBANDS; band += nw) {
+    double s = 0.0;
+    for (int k = bw->lo[band] + lane; k < bw->lo[band + 1]; k += 32) { const double v = (double)X[k] * P.scale; s += v * v; }
+    s = warp_sum(s);
+    if (lane == 0) bw->sum[band] = s;
+  }
+  __syncthreads();
+  if (t < FRAD_NBANDS) {
+    const int n = bw->lo[t + 1] - bw->lo[t];
+    double thr = 0.0;
+    if (n > 0) {
+      const double level = pow(sqrt(bw->sum[t] / (double)n), 0.8);
+      thr = fmax(level, bt->ath[t]) * P.loss;
+    }
+    bw->thr[t] = thr;
+  }
+  __syncthreads();
+  if (t == 0) {   // the reference stops at the first empty band, leaving zeros (p1tools.py:23)
+    bool dead = false;
+    for (int i = 0; i < FRAD_NBANDS; i++) {
+      if (bw->lo[i + 1] - bw->lo[i] <= 0) dead = true;
+      if (dead) bw->thr[i] = 0.0;
+    }
+    bw->thr[FRAD_NBANDS] = 0.0;
+  }
+  __syncthreads();
+  if (t < FRAD_NBANDS) {
+    // profile1.py:38-40: round(dequant(ln(max(thr,1)) / ln(e/2)))
+    const double v = log(fmax(bw->thr[t], 1.0)) / bt->log_base;
+    const double d = (v > 0.0) ? pow(v, 1.0 / 0.75) : 0.0;
+    P.tq[((size_t)b * FRAD_NBANDS + t) * C + c] = sat_i32(rint(d));
+  }
+  ramp_setup(bw, bt, N);
+  __syncthreads();
+  int32_t* qrow = P.q + (size_t)b * N * C;
+  if (P.profile == 1) {
+    for (int k = t; k < N; k += blockDim.x) {
+      const double div = ramp_value(bw, k);
+      double y = (div == 0.0) ? 0.0 : ((double)X[k] / div) * P.scale;
+      const double m = pow075(fabs(y));
+      qrow[(size_t)k * C + c] = sat_i32(rint(copysign(m, y)));
+    }
+    return;
+  }
+  // profile 2: TNS over the masked spectrum (profile2.py:32)
+  double* masked = P.tns_scratch + (size_t)cta * 2 * N;
+  double* work = masked + N;
+  for (int k = t; k < N; k += blockDim.x) {
+    const double div = ramp_value(bw, k);
+    masked[k] = (div == 0.0) ? 0.0 : (double)X[k] / div;
+  }
+  __syncthreads();
+  tns_analysis_block(masked, work, N, bw);
+  const double* src = bw->flag ? work : masked;
+  if (t < FRAD_LPC_LEN) P.lpc[((size_t)b * FRAD_LPC_LEN + t) * C + c] = bw->aq[t];
+  for (int k = t; k < N; k += blockDim.x) {
+    const double y = src[k] * P.scale;
+    qrow[(size_t)k * C + c] = sat_i32(rint(copysign(pow075(fabs(y)), y)));
+  }
+}
+
+// ---- profile 1 / 2 decode prologue --------------------------------------------------------------
+template <typename T>
+__device__ void p1_prologue(const dec_params& P, T* X, int N, int b, int c, band_work* bw, int cta) {
+  const band_table* bt = P.bt;
+  const int t = threadIdx.x, C = P.C;
+  if (t <= FRAD_NBANDS) { const int e = bt->edge[t]; bw->lo[t] = (e < N) ? e : N; }
+  if (t < FRAD_NBANDS) {
+    // profile1.py:66: (e/2) ** (sign(tq) |tq|^0.75)
+    const double v = (double)P.tq[((size_t)b * FRAD_NBANDS + t) * C + c];
+    const double e = copysign(pow(fabs(v), 0.75), v);
+    bw->thr[t] = (v == 0.0) ? 1.0 : pow(bt->base, e);
+  }
+  if (t == 0) bw->thr[FRAD_NBANDS] = 0.0;
+  __syncthreads();
+  ramp_setup(bw, bt, N);
+  __syncthreads();
+  const int32_t* qrow = P.q + (size_t)b * N * C;
+  if (P.profile == 1) {
+    for (int k = t; k < N; k += blockDim.x) {
+      const double qv = (double)qrow[(size_t)k * C + c];
+      const double coef = copysign(pow(fabs(qv), 1.0 / 0.75), qv) / P.scale;    // profile1.py:65
+      X[k] = (T)(coef * ramp_value(bw, k));
+    }
+    return;
+  }
+  double* coef = P.tns_scratch + (size_t)cta * 2 * N;
+  double* synth = coef + N;
+  for (int k = t; k < N; k += blockDim.x) {
+    const double qv = (double)qrow[(size_t)k * C + c];
+    coef[k] = copysign(pow(fabs(qv), 1.0 / 0.75), qv) / P.scale;
+  }
+  if (t < FRAD_LPC_LEN) bw->aq[t] = P.lpc[((size_t)b * FRAD_LPC_LEN + t) * C + c];
+  __syncthreads();
+  int any = 0;
+  for (int i = 0; i < FRAD_LPC_LEN; i++) any |= (bw->aq[i] != 0);      // np.all(lpc_quant == 0), p2tools.py:98
+  const double* src = coef;
+  if (any) {
+    if (t < FRAD_LPC_LEN) bw->a[t] = (t == 0) ? 1.0 : (double)bw->aq[t] / 15.0;
+    __syncthreads();
+    tns_synthesis_block(coef, synth, N, bw);
+    if (bw->flag) src = synth;
+  }
+  for (int k = t; k < N; k += blockDim.x) X[k] = (T)(src[k] * ramp_value(bw, k));
+}

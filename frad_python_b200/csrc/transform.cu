@@ -1,0 +1,646 @@
+// Generic-size transform path: one CTA per (frame, channel) sequence, persistent grid.
+//
+// Covers every even frame length whose half factors into {2,3,5,7} (all 32 compact sizes of
+// fourier/profiles.py:14-23 and most lossless sizes) with a shared-memory Stockham FFT, and every
+// other length with a direct O(N^2) cosine sum.  The profile pro/epilogues (profile-0 packing,
+// profile-1/2 masking + quantisation, TNS) are fused into the same kernel.  The N = 2048 fast path
+// lives in dct2048.cu and reuses the device functions declared here.
+//
+// Reference lines restated (relative to src/libfrad/): fourier/profile0.py:14-69,
+// fourier/profile1.py:15-77, fourier/profile2.py:15-91, fourier/tools/p1tools.py:15-44,
+// fourier/tools/p2tools.py:8-111.
+#include <cmath>
+#include "plan.cuh"
+#include "devmath.cuh"
+#include "profiles.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// plans
+// ------------------------------------------------------------------------------------------------
+static bool factor_half(int M, int* radix, int* npass) {
+  int n = 0, m = M;
+  while (m % 4 == 0) { radix[n++] = 4; m /= 4; }
+  while (m % 2 == 0) { radix[n++] = 2; m /= 2; }
+  while (m % 3 == 0) { radix[n++] = 3; m /= 3; }
+  while (m % 5 == 0) { radix[n++] = 5; m /= 5; }
+  while (m % 7 == 0) { radix[n++] = 7; m /= 7; }
+  *npass = n;
+  return m == 1 && n <= FRAD_MAX_RADIX_PASSES;
+}
+
+template <typename T>
+static void* upload_cpx(frad_ctx* ctx, const std::vector<long double>& re, const std::vector<long double>& im) {
+  size_t n = re.size();
+  std::vector<T> h(2 * n);
+  for (size_t i = 0; i < n; i++) { h[2 * i] = (T)re[i]; h[2 * i + 1] = (T)im[i]; }
+  void* d = nullptr;
+  if (cudaMalloc(&d, 2 * n * sizeof(T)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  // tables are uploaded synchronously once per (N, precision); not on the timed path
+  if (cudaMemcpy(d, h.data(), 2 * n * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return nullptr; }
+  return d;
+}
+
+// exact-octant evaluation of exp(i * pi * num / den)
+static void unit_root(long long num, long long den, long double* c, long double* s) {
+  const long double PI = 3.14159265358979323846264338327950288L;
+  long long period = 2 * den;
+  num %= period; if (num < 0) num += period;
+  // reduce to [0, den/2] using symmetries so that cosl/sinl see small arguments
+  int quad = (int)((2 * num) / den);           // 0..3 quarter turns of pi/2
+  long long r = 2 * num - (long long)quad * den;  // angle = quad*pi/2 + r*pi/(2 den), r in [0, den)
+  long double a = PI * (long double)r / (2.0L * (long double)den);
+  long double cc = cosl(a), ss = sinl(a);
+  switch (quad & 3) {
+    case 0: *c = cc; *s = ss; break;
+    case 1: *c = -ss; *s = cc; break;
+    case 2: *c = -cc; *s = -ss; break;
+    default: *c = ss; *s = -cc; break;
+  }
+}
+
+void frad_plan_free(frad_plan* p) {
+  if (!p) return;
+  cudaFree(p->tw); cudaFree(p->cf); cudaFree(p->df); cudaFree(p->ci); cudaFree(p->ei); cudaFree(p->ct);
+  delete p;
+}
+
+template <typename T>
+static bool build_tables(frad_ctx* ctx, frad_plan* p) {
+  const int N = p->N, M = p->M;
+  std::vector<long double> re(M), im(M);
+  for (int t = 0; t < M; t++) { unit_root(-2LL * t, M, &re[t], &im[t]); }
+  p->tw = upload_cpx<T>(ctx, re, im);
+  re.resize(M + 1); im.resize(M + 1);
+  std::vector<long double> re2(M + 1), im2(M + 1);
+  for (int k = 0; k <= M; k++) {
+    unit_root(-(long long)k, 2LL * N, &re[k], &im[k]);          // exp(-i pi k / 2N)
+    unit_root(-5LL * k, 2LL * N, &re2[k], &im2[k]);             // * exp(-2 pi i k / N) = exp(-i pi 5k / 2N)
+    re[k] /= N; im[k] /= N; re2[k] /= N; im2[k] /= N;
+  }
+  p->cf = upload_cpx<T>(ctx, re, im);
+  p->df = upload_cpx<T>(ctx, re2, im2);
+  for (int k = 0; k <= M; k++) {
+    unit_root((long long)k, 2LL * N, &re[k], &im[k]);           // exp(+i pi k / 2N)
+    unit_root(4LL * k, 2LL * N, &re2[k], &im2[k]);              // exp(+2 pi i k / N)
+  }
+  p->ci = upload_cpx<T>(ctx, re, im);
+  p->ei = upload_cpx<T>(ctx, re2, im2);
+  return p->tw && p->cf && p->df && p->ci && p->ei;
+}
+
+frad_plan* frad_get_plan(frad_ctx* ctx, int N, int prec) {
+  uint64_t key = (uint64_t)(uint32_t)N | ((uint64_t)prec << 40);
+  auto it = ctx->plans.find(key);
+  if (it != ctx->plans.end()) return it->second;
+  frad_plan* p = new frad_plan();
+  p->N = N; p->M = N / 2; p->prec = prec;
+  bool ok = true;
+  if ((N & 1) || N < 4 || !factor_half(p->M, p->radix, &p->npass)) {
+    p->direct = 1;
+    std::vector<double> h((size_t)4 * N);
+    for (long long q = 0; q < 4LL * N; q++) { long double c, s; unit_root(q, 2LL * N, &c, &s); h[q] = (double)c; }
+    if (cudaMalloc(&p->ct, h.size() * sizeof(double)) != cudaSuccess ||
+        cudaMemcpy(p->ct, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) ok = false;
+  } else {
+    ok = (prec == FRAD_PREC_F32) ? build_tables<float>(ctx, p) : build_tables<double>(ctx, p);
+  }
+  if (!ok) {
+    cudaGetLastError();
+    frad_plan_free(p);
+    frad_fail(ctx, FRAD_E_NOMEM, "plan table allocation failed");
+    return nullptr;
+  }
+  ctx->plans[key] = p;
+  return p;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FFT passes in shared memory (Stockham autosort, out of place)
+// ------------------------------------------------------------------------------------------------
+template <typename T, int R, bool INV>
+__device__ __forceinline__ void fft_pass(const typename vec2<T>::type* __restrict__ in, typename vec2<T>::type* __restrict__ out,
+                                         int M, int Ns, const typename vec2<T>::type* __restrict__ tw) {
+  typedef typename vec2<T>::type V;
+  const int L = M / R;
+  const int tstep = M / (Ns * R);
+  for (int j = threadIdx.x; j < L; j += blockDim.x) {
+    const int k = j % Ns;
+    V v[R];
+#pragma unroll
+    for (int i = 0; i < R; i++) v[i] = in[j + i * L];
+    if (Ns > 1) {
+#pragma unroll
+      for (int i = 1; i < R; i++) {
+        V w = tw[(size_t)i * k * tstep];
+        if (INV) w.y = -w.y;
+        v[i] = cmul(v[i], w);
+      }
+    }
+    small_dft<T, R, INV>::run(v);
+    const int base = (j - k) * R + k;
+#pragma unroll
+    for (int i = 0; i < R; i++) out[base + i * Ns] = v[i];
+  }
+}
+
+// runs all passes; returns the buffer that holds the result
+template <typename T, bool INV>
+__device__ typename vec2<T>::type* fft_run(typename vec2<T>::type* a, typename vec2<T>::type* b, const plan_dev& pl) {
+  typedef typename vec2<T>::type V;
+  const V* tw = (const V*)pl.tw;
+  int Ns = 1;
+  for (int p = 0; p < pl.npass; p++) {
+    const int R = pl.radix[p];
+    switch (R) {
+      case 4: fft_pass<T, 4, INV>(a, b, pl.M, Ns, tw); break;
+      case 2: fft_pass<T, 2, INV>(a, b, pl.M, Ns, tw); break;
+      case 3: fft_pass<T, 3, INV>(a, b, pl.M, Ns, tw); break;
+      case 5: fft_pass<T, 5, INV>(a, b, pl.M, Ns, tw); break;
+      default: fft_pass<T, 7, INV>(a, b, pl.M, Ns, tw); break;
+    }
+    Ns *= R;
+    __syncthreads();
+    V* t = a; a = b; b = t;
+  }
+  return a;
+}
+
+// Makhoul index: position j of the reordered sequence v reads sample n
+__device__ __forceinline__ int makhoul_src(int j, int N) { return (j < (N + 1) / 2) ? 2 * j : 2 * (N - 1 - j) + 1; }
+
+// ------------------------------------------------------------------------------------------------
+// forward: PCM sequence -> X[0..N) in shared/global buffer (type T)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ T* forward_sequence(const enc_params& P, const plan_dev& pl, int b, int c,
+                               typename vec2<T>::type* bufA, typename vec2<T>::type* bufB) {
+  typedef typename vec2<T>::type V;
+  const int N = pl.N, M = pl.M, C = P.C;
+  const int64_t base = (int64_t)b * P.hop;
+  for (int m = threadIdx.x; m < M; m += blockDim.x) {
+    const int n0 = makhoul_src(2 * m, N), n1 = makhoul_src(2 * m + 1, N);
+    T x0 = load_pcm<T>(P.pcm, P.pcm_dtype, (base + n0) * C + c);
+    T x1 = load_pcm<T>(P.pcm, P.pcm_dtype, (base + n1) * C + c);
+    bufA[m] = mk2<T>(x0, x1);
+  }
+  __syncthreads();
+  V* Z = fft_run<T, false>(bufA, bufB, pl);
+  V* O = (Z == bufA) ? bufB : bufA;
+  T* X = (T*)O;
+  const V* cf = (const V*)pl.cf;
+  const V* df = (const V*)pl.df;
+  for (int k = threadIdx.x; k <= M / 2; k += blockDim.x) {
+    const int km = M - k;
+    V zk = Z[k], zm = cconj(Z[km % M]);
+    V A = mk2<T>(T(0.5) * (zk.x + zm.x), T(0.5) * (zk.y + zm.y));
+    V D = csub(zk, zm);                       // B = D / (2i) = (D.y - i D.x) / 2
+    V Bv = mk2<T>(T(0.5) * D.y, T(-0.5) * D.x);
+    V y = cadd(cmul(cf[k], A), cmul(df[k], Bv));
+    V y2 = cadd(cmul(cf[km], cconj(A)), cmul(df[km], cconj(Bv)));
+    X[k] = y.x;
+    if (k >= 1) X[N - k] = -y.y;
+    X[km] = y2.x;                             // km == M for k == 0
+    if (k >= 1) X[N - km] = -y2.y;
+  }
+  __syncthreads();
+  return X;
+}
+
+// direct O(N^2) forward for awkward lengths; x staged in xs (double), result to X (double)
+__device__ void forward_direct(const enc_params& P, const plan_dev& pl, int b, int c, double* xs, double* X) {
+  const int N = pl.N, C = P.C;
+  const int64_t base = (int64_t)b * P.hop;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) xs[n] = load_pcm<double>(P.pcm, P.pcm_dtype, (base + n) * C + c);
+  __syncthreads();
+  const long long period = 4LL * N;
+  for (int k = threadIdx.x; k < N; k += blockDim.x) {
+    double acc = 0.0;
+    long long ph = k % period;               // k*(2n+1) mod 4N, advanced by 2k per sample
+    const long long step = (2LL * k) % period;
+    for (int n = 0; n < N; n++) {
+      acc += xs[n] * pl.ct[ph];
+      ph += step; if (ph >= period) ph -= period;
+    }
+    X[k] = acc / N;
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+// inverse: X[0..N) (type T, in bufA viewed as T*) -> PCM
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ void inverse_sequence(const dec_params& P, const plan_dev& pl, int b, int c,
+                                 typename vec2<T>::type* bufA, typename vec2<T>::type* bufB) {
+  typedef typename vec2<T>::type V;
+  const int N = pl.N, M = pl.M, C = P.C;
+  const T* X = (const T*)bufA;
+  const V* ci = (const V*)pl.ci;
+  const V* ei = (const V*)pl.ei;
+  for (int k = threadIdx.x; k <= M / 2; k += blockDim.x) {
+    const int km = M - k;
+    // V_k = (X[k] - i X[N-k]) * ci[k], with X[N] := 0
+    V vk = cmul(mk2<T>(X[k], (k == 0) ? T(0) : -X[N - k]), ci[k]);
+    V vm = cmul(mk2<T>(X[km], (k == 0) ? -T(0) * X[0] : -X[N - km]), ci[km]);
+    if (k == 0) vm = cmul(mk2<T>(X[M], -X[M]), ci[M]);      // N - M == M
+    V vmc = cconj(vm), vkc = cconj(vk);
+    // Z[k] = (V_k + conj V_{M-k}) + i e_k (V_k - conj V_{M-k})
+    V s = cadd(vk, vmc), d = cmul(ei[k], csub(vk, vmc));
+    bufB[k] = mk2<T>(s.x - d.y, s.y + d.x);
+    if (k >= 1 && km < M) {
+      V s2 = cadd(vm, vkc), d2 = cmul(ei[km], csub(vm, vkc));
+      bufB[km] = mk2<T>(s2.x - d2.y, s2.y + d2.x);
+    }
+  }
+  __syncthreads();
+  V* z = fft_run<T, true>(bufB, bufA, pl);
+  const int64_t base = (int64_t)b * N;
+  for (int m = threadIdx.x; m < M; m += blockDim.x) {
+    V v = z[m];
+    const int n0 = makhoul_src(2 * m, N), n1 = makhoul_src(2 * m + 1, N);
+    store_pcm<T>(P.pcm, P.pcm_dtype, (base + n0) * C + c, v.x);
+    store_pcm<T>(P.pcm, P.pcm_dtype, (base + n1) * C + c, v.y);
+  }
+  __syncthreads();
+}
+
+__device__ void inverse_direct(const dec_params& P, const plan_dev& pl, int b, int c, const double* X) {
+  const int N = pl.N, C = P.C;
+  const long long period = 4LL * N;
+  const int64_t base = (int64_t)b * N;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    double acc = 0.0;
+    const long long step = (2LL * n + 1) % period;
+    long long ph = step % period;             // k*(2n+1) mod 4N for k = 1
+    for (int k = 1; k < N; k++) {
+      acc += X[k] * pl.ct[ph];
+      ph += step; if (ph >= period) ph -= period;
+    }
+    store_pcm<double>(P.pcm, P.pcm_dtype, (base + n) * C + c, X[0] + 2.0 * acc);
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(1024) seq_encode_kernel(enc_params P, plan_dev pl, int b_in_smem) {
+  typedef typename vec2<T>::type V;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  band_work* bw = (band_work*)smem_raw;
+  V* bufA = (V*)(smem_raw + sizeof(band_work));
+  V* bufB = b_in_smem ? bufA + pl.M : ((V*)P.gscratch) + (size_t)blockIdx.x * pl.M;
+  const int nseq = P.B * P.C;
+  for (int s = blockIdx.x; s < nseq; s += gridDim.x) {
+    const int b = s / P.C, c = s % P.C;
+    T* X = forward_sequence<T>(P, pl, b, c, bufA, bufB);
+    if (P.profile == 0) p0_epilogue<T>(P, X, pl.N, b, c, bw);
+    else p1_epilogue<T>(P, X, pl.N, b, c, bw, blockIdx.x);
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) seq_encode_direct_kernel(enc_params P, plan_dev pl) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  band_work* bw = (band_work*)smem_raw;
+  double* xs = (double*)P.gscratch + (size_t)blockIdx.x * 2 * pl.N;
+  double* X = xs + pl.N;
+  const int nseq = P.B * P.C;
+  for (int s = blockIdx.x; s < nseq; s += gridDim.x) {
+    const int b = s / P.C, c = s % P.C;
+    forward_direct(P, pl, b, c, xs, X);
+    if (P.profile == 0) p0_epilogue<double>(P, X, pl.N, b, c, bw);
+    else p1_epilogue<double>(P, X, pl.N, b, c, bw, blockIdx.x);
+    __syncthreads();
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024) seq_decode_kernel(dec_params P, plan_dev pl, int b_in_smem) {
+  typedef typename vec2<T>::type V;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  band_work* bw = (band_work*)smem_raw;
+  V* bufA = (V*)(smem_raw + sizeof(band_work));
+  V* bufB = b_in_smem ? bufA + pl.M : ((V*)P.gscratch) + (size_t)blockIdx.x * pl.M;
+  const int nseq = P.B * P.C;
+  for (int s = blockIdx.x; s < nseq; s += gridDim.x) {
+    const int b = s / P.C, c = s % P.C;
+    T* X = (T*)bufA;
+    if (P.profile == 0) p0_prologue<T>(P, X, pl.N, b, c);
+    else p1_prologue<T>(P, X, pl.N, b, c, bw, blockIdx.x);
+    __syncthreads();
+    inverse_sequence<T>(P, pl, b, c, bufA, bufB);
+  }
+}
+
+__global__ void __launch_bounds__(256) seq_decode_direct_kernel(dec_params P, plan_dev pl) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  band_work* bw = (band_work*)smem_raw;
+  double* X = (double*)P.gscratch + (size_t)blockIdx.x * pl.N;
+  const int nseq = P.B * P.C;
+  for (int s = blockIdx.x; s < nseq; s += gridDim.x) {
+    const int b = s / P.C, c = s % P.C;
+    if (P.profile == 0) p0_prologue<double>(P, X, pl.N, b, c);
+    else p1_prologue<double>(P, X, pl.N, b, c, bw, blockIdx.x);
+    __syncthreads();
+    inverse_direct(P, pl, b, c, X);
+  }
+}
+
+// 12-bit packing helpers (profile0.py:37-41, 54-58): 16-bit scratch <-> nibble-packed payload
+__global__ void pack12_kernel(const uint16_t* __restrict__ half_top12, size_t nvals, int B, uint8_t* payload, size_t stride) {
+  const size_t npairs = (nvals + 1) / 2;
+  const size_t total = npairs * (size_t)B;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / npairs, p = i % npairs;
+    const uint16_t* src = half_top12 + b * nvals;
+    uint32_t a = src[2 * p];
+    const bool has_b = (2 * p + 1) < nvals;
+    uint32_t bb = has_b ? src[2 * p + 1] : 0;
+    uint8_t* dst = payload + b * stride + 3 * p;
+    dst[0] = (uint8_t)(a >> 4);
+    dst[1] = (uint8_t)(((a & 0xF) << 4) | (bb >> 8));
+    if (has_b) dst[2] = (uint8_t)bb;
+  }
+}
+
+__global__ void unpack12_kernel(const uint8_t* __restrict__ payload, size_t stride, size_t nvals, int B, uint16_t* half_bits) {
+  const size_t total = nvals * (size_t)B;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / nvals, v = i % nvals;
+    const uint8_t* src = payload + b * stride + 3 * (v / 2);
+    uint32_t t;
+    if ((v & 1) == 0) t = ((uint32_t)src[0] << 4) | (src[1] >> 4);
+    else t = (((uint32_t)src[1] & 0xF) << 8) | src[2];
+    half_bits[i] = (uint16_t)(t << 4);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------------
+static int pick_threads(int M) {
+  int t = (M + 3) / 4;
+  t = ((t + 31) / 32) * 32;
+  if (t < 64) t = 64;
+  if (t > 1024) t = 1024;
+  return t;
+}
+
+struct launch_cfg { int threads, grid, b_in_smem; size_t smem; size_t gscratch; };
+
+template <typename T>
+static int configure(frad_ctx* ctx, const frad_plan* pl, int nseq, const void* kernel, launch_cfg* cfg) {
+  const size_t one = (size_t)pl->M * 2 * sizeof(T);
+  const size_t fixed = sizeof(band_work);
+  const size_t limit = ctx->smem_optin;
+  cfg->threads = pick_threads(pl->M);
+  if (fixed + 2 * one <= limit) { cfg->b_in_smem = 1; cfg->smem = fixed + 2 * one; }
+  else if (fixed + one <= limit) { cfg->b_in_smem = 0; cfg->smem = fixed + one; }
+  else return frad_fail(ctx, FRAD_E_UNSUPPORTED, "frame too long for the shared-memory transform");
+  FRAD_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg->smem));
+  int per_sm = 0;
+  FRAD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, cfg->threads, cfg->smem));
+  if (per_sm < 1) per_sm = 1;
+  long long g = (long long)per_sm * ctx->sm_count;
+  cfg->grid = (int)((nseq < g) ? nseq : g);
+  if (cfg->grid < 1) cfg->grid = 1;
+  cfg->gscratch = cfg->b_in_smem ? 0 : (size_t)cfg->grid * one;
+  return FRAD_OK;
+}
+
+static int resolve_prec_fwd(int prec, int pcm_dtype) {
+  if (prec == FRAD_PREC_F32 || prec == FRAD_PREC_F64) return prec;
+  return (pcm_dtype == FRAD_F32 || pcm_dtype == FRAD_F16) ? FRAD_PREC_F32 : FRAD_PREC_F64;
+}
+static int resolve_prec_inv(int prec) { return (prec == FRAD_PREC_F32) ? FRAD_PREC_F32 : FRAD_PREC_F64; }
+
+int frad_launch_encode_2048(frad_ctx* ctx, const enc_params& P, const frad_plan* pl, int prec);   // dct2048.cu
+int frad_launch_decode_2048(frad_ctx* ctx, const dec_params& P, const frad_plan* pl, int prec);
+
+static int launch_encode(frad_ctx* ctx, enc_params& P, int prec) {
+  if (P.B <= 0) return FRAD_OK;
+  frad_plan* pl = frad_get_plan(ctx, P.N, prec);
+  if (!pl) return FRAD_E_NOMEM;
+  const int nseq = P.B * P.C;
+  if (P.profile == 2) {   // TNS work arrays: masked + residual per resident CTA
+    // sized below once the grid is known
+  }
+  if (pl->direct) {
+    int per_sm = 4;
+    int grid = per_sm * ctx->sm_count; if (grid > nseq) grid = nseq;
+    size_t need = (size_t)grid * (2 * P.N) * sizeof(double);
+    size_t tns = (P.profile == 2) ? (size_t)grid * 2 * P.N * sizeof(double) : 0;
+    char* g = (char*)frad_scratch(ctx, 0, need + tns);
+    if (!g) return FRAD_E_NOMEM;
+    P.gscratch = g; P.tns_scratch = (double*)(g + need);
+    seq_encode_direct_kernel<<<grid, 256, sizeof(band_work), ctx->stream>>>(P, plan_view(pl));
+    FRAD_LAUNCH_CHECK(ctx);
+    return FRAD_OK;
+  }
+#ifdef FRAD_HAVE_FAST2048
+  if (P.N == 2048 && P.fast_ok) return frad_launch_encode_2048(ctx, P, pl, prec);
+#endif
+  launch_cfg cfg;
+  const void* k = (prec == FRAD_PREC_F32) ? (const void*)seq_encode_kernel<float> : (const void*)seq_encode_kernel<double>;
+  int rc = (prec == FRAD_PREC_F32) ? configure<float>(ctx, pl, nseq, k, &cfg) : configure<double>(ctx, pl, nseq, k, &cfg);
+  if (rc) return rc;
+  size_t tns = (P.profile == 2) ? (size_t)cfg.grid * 2 * P.N * sizeof(double) : 0;
+  if (cfg.gscratch + tns) {
+    char* g = (char*)frad_scratch(ctx, 0, cfg.gscratch + tns);
+    if (!g) return FRAD_E_NOMEM;
+    P.gscratch = g; P.tns_scratch = (double*)(g + cfg.gscratch);
+  }
+  if (prec == FRAD_PREC_F32) seq_encode_kernel<float><<<cfg.grid, cfg.threads, cfg.smem, ctx->stream>>>(P, plan_view(pl), cfg.b_in_smem);
+  else seq_encode_kernel<double><<<cfg.grid, cfg.threads, cfg.smem, ctx->stream>>>(P, plan_view(pl), cfg.b_in_smem);
+  FRAD_LAUNCH_CHECK(ctx);
+  return FRAD_OK;
+}
+
+static int launch_decode(frad_ctx* ctx, dec_params& P, int prec) {
+  if (P.B <= 0) return FRAD_OK;
+  frad_plan* pl = frad_get_plan(ctx, P.N, prec);
+  if (!pl) return FRAD_E_NOMEM;
+  const int nseq = P.B * P.C;
+  if (pl->direct) {
+    int grid = 4 * ctx->sm_count; if (grid > nseq) grid = nseq;
+    size_t need = (size_t)grid * P.N * sizeof(double);
+    size_t tns = (P.profile == 2) ? (size_t)grid * P.N * sizeof(double) : 0;
+    char* g = (char*)frad_scratch(ctx, 0, need + tns);
+    if (!g) return FRAD_E_NOMEM;
+    P.gscratch = g; P.tns_scratch = (double*)(g + need);
+    seq_decode_direct_kernel<<<grid, 256, sizeof(band_work), ctx->stream>>>(P, plan_view(pl));
+    FRAD_LAUNCH_CHECK(ctx);
+    return FRAD_OK;
+  }
+#ifdef FRAD_HAVE_FAST2048
+  if (P.N == 2048 && P.fast_ok) return frad_launch_decode_2048(ctx, P, pl, prec);
+#endif
+  launch_cfg cfg;
+  const void* k = (prec == FRAD_PREC_F32) ? (const void*)seq_decode_kernel<float> : (const void*)seq_decode_kernel<double>;
+  int rc = (prec == FRAD_PREC_F32) ? configure<float>(ctx, pl, nseq, k, &cfg) : configure<double>(ctx, pl, nseq, k, &cfg);
+  if (rc) return rc;
+  size_t tns = (P.profile == 2) ? (size_t)cfg.grid * P.N * sizeof(double) : 0;
+  if (cfg.gscratch + tns) {
+    char* g = (char*)frad_scratch(ctx, 0, cfg.gscratch + tns);
+    if (!g) return FRAD_E_NOMEM;
+    P.gscratch = g; P.tns_scratch = (double*)(g + cfg.gscratch);
+  }
+  if (prec == FRAD_PREC_F32) seq_decode_kernel<float><<<cfg.grid, cfg.threads, cfg.smem, ctx->stream>>>(P, plan_view(pl), cfg.b_in_smem);
+  else seq_decode_kernel<double><<<cfg.grid, cfg.threads, cfg.smem, ctx->stream>>>(P, plan_view(pl), cfg.b_in_smem);
+  FRAD_LAUNCH_CHECK(ctx);
+  return FRAD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: profile 0
+// ------------------------------------------------------------------------------------------------
+static bool p0_bits_ok(int bits) { return bits == 12 || bits == 16 || bits == 24 || bits == 32 || bits == 48 || bits == 64; }
+
+extern "C" size_t frad_p0_payload_bytes(int N, int C, int bits) {
+  size_t nv = (size_t)N * (size_t)C;
+  if (bits == 12) return (nv * 3 + 1) / 2;
+  return nv * (size_t)(bits / 8);
+}
+
+extern "C" int frad_p0_encode_dev(frad_ctx* ctx, const void* pcm, int pcm_dtype, int64_t hop, int B, int N, int C,
+                                  int bits, int little_endian, int prec,
+                                  uint8_t* payload, size_t payload_stride, double* peak) {
+  if (!ctx) return FRAD_E_ARG;
+  if (B < 0 || N < 1 || C < 1 || !p0_bits_ok(bits) || !frad_dtype_size(pcm_dtype) || !pcm || !payload)
+    return frad_fail(ctx, FRAD_E_ARG, "frad_p0_encode_dev: bad argument");
+  if (payload_stride < frad_p0_payload_bytes(N, C, bits)) return frad_fail(ctx, FRAD_E_ARG, "payload_stride too small");
+  FRAD_CUDA(ctx, cudaSetDevice(ctx->device));
+  enc_params P = {};
+  P.pcm = pcm; P.pcm_dtype = pcm_dtype; P.hop = hop; P.B = B; P.N = N; P.C = C;
+  P.profile = 0; P.bits = bits; P.le = (little_endian && bits % 8 == 0) ? 1 : 0;
+  P.payload = payload; P.payload_stride = payload_stride; P.peak = peak;
+  P.fast_ok = 1;
+  const size_t nvals = (size_t)N * C;
+  if (bits == 12) {
+    P.half_scratch = (uint16_t*)frad_scratch(ctx, 1, nvals * (size_t)B * sizeof(uint16_t));
+    if (!P.half_scratch) return FRAD_E_NOMEM;
+  }
+  if (peak) FRAD_CUDA(ctx, cudaMemsetAsync(peak, 0, sizeof(double) * (size_t)B, ctx->stream));
+  int rc = launch_encode(ctx, P, resolve_prec_fwd(prec, pcm_dtype));
+  if (rc) return rc;
+  if (bits == 12 && B > 0) {
+    size_t total = ((nvals + 1) / 2) * (size_t)B;
+    int grid = (int)((total + 255) / 256); if (grid > ctx->sm_count * 16) grid = ctx->sm_count * 16;
+    pack12_kernel<<<grid, 256, 0, ctx->stream>>>(P.half_scratch, nvals, B, payload, payload_stride);
+    FRAD_LAUNCH_CHECK(ctx);
+  }
+  return FRAD_OK;
+}
+
+extern "C" int frad_p0_decode_dev(frad_ctx* ctx, const uint8_t* payload, size_t payload_stride, int B, int N, int C,
+                                  int bits, int little_endian, int prec, void* pcm, int pcm_dtype) {
+  if (!ctx) return FRAD_E_ARG;
+  if (B < 0 || N < 1 || C < 1 || !p0_bits_ok(bits) || !pcm || !payload || (pcm_dtype != FRAD_F64 && pcm_dtype != FRAD_F32))
+    return frad_fail(ctx, FRAD_E_ARG, "frad_p0_decode_dev: bad argument");
+  if (payload_stride < frad_p0_payload_bytes(N, C, bits)) return frad_fail(ctx, FRAD_E_ARG, "payload_stride too small");
+  FRAD_CUDA(ctx, cudaSetDevice(ctx->device));
+  dec_params P = {};
+  P.B = B; P.N = N; P.C = C; P.profile = 0; P.bits = bits; P.le = (little_endian && bits % 8 == 0) ? 1 : 0;
+  P.payload = payload; P.payload_stride = payload_stride; P.pcm = pcm; P.pcm_dtype = pcm_dtype;
+  P.fast_ok = 1;
+  const size_t nvals = (size_t)N * C;
+  if (bits == 12 && B > 0) {
+    uint16_t* hs = (uint16_t*)frad_scratch(ctx, 1, nvals * (size_t)B * sizeof(uint16_t));
+    if (!hs) return FRAD_E_NOMEM;
+    size_t total = nvals * (size_t)B;
+    int grid = (int)((total + 255) / 256); if (grid > ctx->sm_count * 16) grid = ctx->sm_count * 16;
+    unpack12_kernel<<<grid, 256, 0, ctx->stream>>>(payload, payload_stride, nvals, B, hs);
+    FRAD_LAUNCH_CHECK(ctx);
+    P.half_scratch = hs;
+  }
+  return launch_decode(ctx, P, resolve_prec_inv(prec));
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI: profiles 1 and 2
+// ------------------------------------------------------------------------------------------------
+static const int k_compact_srates[12] = {96000, 88200, 64000, 48000, 44100, 32000, 24000, 22050, 16000, 12000, 11025, 8000};
+static bool compact_size_ok(int N) {
+  for (int s = 0; s < 8; s++) for (int b = 128; b <= 224; b += 32) if (N == (b << s)) return true;
+  return false;
+}
+static bool compact_srate_ok(int sr) { for (int i = 0; i < 12; i++) if (k_compact_srates[i] == sr) return true; return false; }
+
+static const band_table* get_band_table(frad_ctx* ctx, int N, int srate) {
+  uint64_t key = (uint64_t)(uint32_t)N | ((uint64_t)(uint32_t)srate << 32);
+  auto it = ctx->band_tables.find(key);
+  if (it != ctx->band_tables.end()) return (const band_table*)it->second;
+  static const double hz[28] = {0, 200, 400, 600, 800, 1000, 1200, 1400, 1600, 2000, 2400, 2800, 3200, 4000, 4800, 5600,
+                                6800, 8000, 9600, 12000, 15600, 20000, 24000, 28800, 34400, 40800, 48000, 4294967295.0};
+  band_table h;
+  for (int i = 0; i < 28; i++) {
+    // p1tools.py:16  round(dlen/(srate/2)*Hz), half-to-even
+    double v = (double)N / ((double)srate / 2.0) * hz[i];
+    double r = nearbyint(v);
+    h.edge[i] = (r > 2147483647.0) ? 2147483647 : (int)r;
+  }
+  for (int b = 0; b < FRAD_NBANDS; b++) {
+    // p1tools.py:25-30
+    double f = (hz[b] + hz[b + 1]) / 2.0 / 1000.0;
+    double e = (3.64 * pow(f, -0.8) - 6.5 * exp(-0.6 * pow(f - 3.3, 2.0)) + 1e-3 * pow(f, 4.0)) / 20.0;
+    double ath = pow(10.0, e);
+    h.ath[b] = (ath < 1.0) ? ath : 1.0;
+  }
+  h.log_base = log(M_E / 2.0);      // np.log(np.e / 2)
+  h.base = M_E / 2.0;
+  void* d = nullptr;
+  if (cudaMalloc(&d, sizeof(band_table)) != cudaSuccess ||
+      cudaMemcpy(d, &h, sizeof(band_table), cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaGetLastError();
+    frad_fail(ctx, FRAD_E_NOMEM, "band table allocation failed");
+    return nullptr;
+  }
+  ctx->band_tables[key] = d;
+  return (const band_table*)d;
+}
+
+static bool p12_bits_ok(int bits, bool p2) {
+  static const int d1[7] = {8, 12, 16, 24, 32, 48, 64}, d2[7] = {8, 10, 12, 14, 16, 20, 24};
+  for (int i = 0; i < 7; i++) if ((p2 ? d2[i] : d1[i]) == bits) return true;
+  return false;
+}
+
+extern "C" int frad_p1_encode_dev(frad_ctx* ctx, const void* pcm, int pcm_dtype, int64_t hop, int B, int N, int C,
+                                  int bits, int srate, double loss_level, int prec,
+                                  int32_t* q, int32_t* tq, int32_t* lpc) {
+  if (!ctx) return FRAD_E_ARG;
+  if (B < 0 || C < 1 || !pcm || !q || !tq || !frad_dtype_size(pcm_dtype) || !compact_size_ok(N) ||
+      !compact_srate_ok(srate) || !p12_bits_ok(bits, lpc != nullptr))
+    return frad_fail(ctx, FRAD_E_ARG, "frad_p1_encode_dev: bad argument");
+  FRAD_CUDA(ctx, cudaSetDevice(ctx->device));
+  enc_params P = {};
+  P.pcm = pcm; P.pcm_dtype = pcm_dtype; P.hop = hop; P.B = B; P.N = N; P.C = C;
+  P.profile = lpc ? 2 : 1; P.bits = bits;
+  P.scale = ldexp(1.0, bits - 1);
+  loss_level = fabs(loss_level); if (loss_level < 0.125) loss_level = 0.125;    // profile1.py:20
+  P.loss = loss_level;
+  P.bt = get_band_table(ctx, N, srate);
+  if (!P.bt) return FRAD_E_NOMEM;
+  P.q = q; P.tq = tq; P.lpc = lpc;
+  P.fast_ok = 1;
+  return launch_encode(ctx, P, resolve_prec_fwd(prec, pcm_dtype));
+}
+
+extern "C" int frad_p1_decode_dev(frad_ctx* ctx, const int32_t* q, const int32_t* tq, const int32_t* lpc,
+                                  int B, int N, int C, int bits, int srate, int prec, void* pcm, int pcm_dtype) {
+  if (!ctx) return FRAD_E_ARG;
+  if (B < 0 || C < 1 || !pcm || !q || !tq || !compact_size_ok(N) || !compact_srate_ok(srate) ||
+      !p12_bits_ok(bits, lpc != nullptr) || (pcm_dtype != FRAD_F64 && pcm_dtype != FRAD_F32))
+    return frad_fail(ctx, FRAD_E_ARG, "frad_p1_decode_dev: bad argument");
+  FRAD_CUDA(ctx, cudaSetDevice(ctx->device));
+  dec_params P = {};
+  P.B = B; P.N = N; P.C = C; P.profile = lpc ? 2 : 1; P.bits = bits;
+  P.scale = ldexp(1.0, bits - 1);
+  P.bt = get_band_table(ctx, N, srate);
+  if (!P.bt) return FRAD_E_NOMEM;
+  P.q = q; P.tq = tq; P.lpc = lpc; P.pcm = pcm; P.pcm_dtype = pcm_dtype;
+  P.fast_ok = 1;
+  return launch_decode(ctx, P, resolve_prec_inv(prec));
+}

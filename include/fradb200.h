@@ -1,0 +1,152 @@
+/* fradb200 -- C ABI of the B200-native FrAD hot path (libfradb200.so).
+ *
+ * Drop-in boundary for the numeric seams of H4n-uL/FrAD_Python (paths relative to the
+ * reference's src/libfrad/):
+ *   fourier/profile0.py:14,46   analogue / digital   -> frad_p0_encode*, frad_p0_decode*
+ *   fourier/profile1.py:15,54   analogue / digital   -> frad_p1_encode*, frad_p1_decode*  (numeric part;
+ *   fourier/profile2.py:15,58   analogue / digital   -> frad_p2_encode*, frad_p2_decode*   Golomb via frad_golomb_*,
+ *                                                                                          deflate stays on the host)
+ *   tools/ecc.py:6,14           encode / decode      -> frad_rs_encode*, frad_rs_decode*
+ *   tools/asfh.py:4,69 (zlib.crc32), common.py:6 (crc16_ansi) -> frad_crc32*, frad_crc16*
+ *
+ * Conventions: every function returns 0 on success or a negative FRAD_E_* code; the text is
+ * available from frad_last_error().  No exceptions or exit() cross the ABI.  The caller owns all
+ * buffers.  A context is bound to one GPU and one CUDA stream and is NOT thread-safe; distinct
+ * contexts are independent (one per GPU / host thread).  There is no CPU fallback: without a
+ * usable CUDA device frad_ctx_create fails.
+ *
+ * "*_dev" entry points take DEVICE pointers and only enqueue work on the context's stream
+ * (results valid after frad_sync).  The entry points without the suffix take HOST pointers
+ * (ideally from frad_host_alloc, i.e. pinned), copy in, run, copy out and synchronise.
+ *
+ * Layouts (all C-contiguous):
+ *   pcm        [..][C]   interleaved samples; frame b starts at sample b*hop (hop == N without overlap)
+ *   p0 payload [B][stride] bytes, value index k*C + c, N*C*bits/8 bytes used per frame (12 bit: ceil(1.5*N*C))
+ *   q          [B][N*C]  int32, index k*C + c          (profile1.py:34-36)
+ *   tq         [B][27*C] int32, index band*C + c       (profile1.py:38-40)
+ *   lpc        [B][13*C] int32, index i*C + c          (profile2.py:46)
+ */
+#ifndef FRADB200_H
+#define FRADB200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct frad_ctx frad_ctx;
+
+enum {
+  FRAD_OK = 0,
+  FRAD_E_CUDA = -1,      /* CUDA runtime error (see frad_last_error) */
+  FRAD_E_ARG = -2,       /* invalid argument */
+  FRAD_E_NOMEM = -3,     /* device / pinned allocation failed */
+  FRAD_E_UNSUPPORTED = -4
+};
+
+/* sample formats of PCM buffers (src/libfrad/backend/pcmformat.py:4-62); little-endian host order */
+enum {
+  FRAD_F32 = 0, FRAD_F64 = 1,
+  FRAD_S8 = 2, FRAD_S16 = 3, FRAD_S32 = 4, FRAD_S64 = 5,
+  FRAD_U8 = 6, FRAD_U16 = 7, FRAD_U32 = 8, FRAD_U64 = 9,
+  FRAD_F16 = 10
+};
+
+/* compute precision of the transform: FRAD_PREC_REF follows the reference:
+ * forward = f32 for f16/f32 PCM, f64 otherwise; inverse = f64. */
+enum { FRAD_PREC_REF = 0, FRAD_PREC_F32 = 1, FRAD_PREC_F64 = 2 };
+
+#define FRAD_NBANDS 27
+#define FRAD_LPC_LEN 13
+
+/* ---- context, memory, stream --------------------------------------------------------------- */
+int  frad_ctx_create(int device, frad_ctx** out);
+void frad_ctx_destroy(frad_ctx* ctx);
+const char* frad_last_error(frad_ctx* ctx);      /* ctx may be NULL: last creation error */
+int  frad_sync(frad_ctx* ctx);
+void* frad_stream(frad_ctx* ctx);                /* the cudaStream_t work is enqueued on */
+int  frad_device_count(void);
+int  frad_sm_count(frad_ctx* ctx);
+uint64_t frad_kernel_launches(frad_ctx* ctx);    /* kernels launched through this ctx so far */
+
+void* frad_host_alloc(frad_ctx* ctx, size_t bytes);   /* pinned host memory, NULL on failure */
+void  frad_host_free(frad_ctx* ctx, void* p);
+void* frad_dev_alloc(frad_ctx* ctx, size_t bytes);    /* device memory, NULL on failure */
+void  frad_dev_free(frad_ctx* ctx, void* p);
+int  frad_h2d(frad_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);   /* async on the stream */
+int  frad_d2h(frad_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);   /* async on the stream */
+int  frad_memset_dev(frad_ctx* ctx, void* dst_dev, int value, size_t bytes);
+
+/* CUDA-event timing on the context's stream: record returns a slot id in [0, 64) */
+int  frad_event_record(frad_ctx* ctx, int slot);
+int  frad_event_elapsed_ms(frad_ctx* ctx, int slot_start, int slot_stop, float* ms);
+
+/* ---- profile 0: DCT archive (profile0.py) -------------------------------------------------- */
+/* peak[b] receives max|X| of frame b (as double) so the caller can apply the depth bump of
+ * profile0.py:24-26; payload bytes are already produced for the requested depth. */
+size_t frad_p0_payload_bytes(int N, int C, int bits);
+int frad_p0_encode_dev(frad_ctx* ctx, const void* pcm, int pcm_dtype, int64_t hop, int B, int N, int C,
+                       int bits, int little_endian, int prec,
+                       uint8_t* payload, size_t payload_stride, double* peak);
+int frad_p0_decode_dev(frad_ctx* ctx, const uint8_t* payload, size_t payload_stride, int B, int N, int C,
+                       int bits, int little_endian, int prec,
+                       void* pcm, int pcm_dtype);     /* pcm_dtype: FRAD_F64 (reference) or FRAD_F32 */
+int frad_p0_encode(frad_ctx* ctx, const void* pcm, int pcm_dtype, int64_t hop, int B, int N, int C,
+                   int bits, int little_endian, int prec,
+                   uint8_t* payload, size_t payload_stride, double* peak, uint32_t* crc32 /* may be NULL */);
+int frad_p0_decode(frad_ctx* ctx, const uint8_t* payload, size_t payload_stride, int B, int N, int C,
+                   int bits, int little_endian, int prec, void* pcm, int pcm_dtype);
+
+/* ---- profile 1 / 2: psychoacoustic quantisation (profile1.py, profile2.py, p1tools, p2tools) - */
+/* N must be one of the 32 compact frame sizes; srate one of the 12 compact rates; the caller pads
+ * short frames with zeros (profile1.py:19).  lpc == NULL selects profile 1, otherwise profile 2. */
+int frad_p1_encode_dev(frad_ctx* ctx, const void* pcm, int pcm_dtype, int64_t hop, int B, int N, int C,
+                       int bits, int srate, double loss_level, int prec,
+                       int32_t* q, int32_t* tq, int32_t* lpc);
+int frad_p1_decode_dev(frad_ctx* ctx, const int32_t* q, const int32_t* tq, const int32_t* lpc,
+                       int B, int N, int C, int bits, int srate, int prec, void* pcm, int pcm_dtype);
+int frad_p1_encode(frad_ctx* ctx, const void* pcm, int pcm_dtype, int64_t hop, int B, int N, int C,
+                   int bits, int srate, double loss_level, int prec,
+                   int32_t* q, int32_t* tq, int32_t* lpc);
+int frad_p1_decode(frad_ctx* ctx, const int32_t* q, const int32_t* tq, const int32_t* lpc,
+                   int B, int N, int C, int bits, int srate, int prec, void* pcm, int pcm_dtype);
+
+/* ---- CRC (zlib.crc32 / crc16_ansi) ---------------------------------------------------------- */
+/* Message i is buf[off[i] .. off[i]+len[i]); off == NULL means i*stride, len == NULL means ulen. */
+int frad_crc32_dev(frad_ctx* ctx, const uint8_t* buf, const uint64_t* off, const uint32_t* len,
+                   size_t stride, uint32_t ulen, int B, uint32_t* out);
+int frad_crc16_dev(frad_ctx* ctx, const uint8_t* buf, const uint64_t* off, const uint32_t* len,
+                   size_t stride, uint32_t ulen, int B, uint32_t* out);
+int frad_crc32(frad_ctx* ctx, const uint8_t* buf, const uint64_t* off, const uint32_t* len,
+               size_t stride, uint32_t ulen, int B, size_t total_bytes, uint32_t* out);
+int frad_crc16(frad_ctx* ctx, const uint8_t* buf, const uint64_t* off, const uint32_t* len,
+               size_t stride, uint32_t ulen, int B, size_t total_bytes, uint32_t* out);
+
+/* ---- Reed-Solomon ECC (tools/ecc.py; GF(2^8) 0x11D, alpha = 2, fcr = 0) ----------------------- */
+/* Message i (len[i] bytes at off[i]) is split into dsize-byte chunks; each becomes chunk || csize
+ * parity bytes at out + out_off[i].  Encoded length = len + ceil(len/dsize)*csize. */
+size_t frad_rs_encoded_len(size_t len, int dsize, int csize);
+size_t frad_rs_decoded_len(size_t len, int dsize, int csize);
+int frad_rs_encode_dev(frad_ctx* ctx, const uint8_t* buf, const uint64_t* off, const uint32_t* len,
+                       size_t stride, uint32_t ulen, int B, int dsize, int csize,
+                       uint8_t* out, const uint64_t* out_off, size_t out_stride);
+/* repair != 0: correct up to csize/2 byte errors per codeword, otherwise zero-fill the chunk
+ * (ecc.py:19-22); repair == 0: strip parity only (ecc.py:23).
+ * status (may be NULL) [B]: number of codewords zero-filled in message i (0 = all recovered);
+ * fixed (may be NULL) [B]: total corrected byte errors in message i. */
+int frad_rs_decode_dev(frad_ctx* ctx, const uint8_t* buf, const uint64_t* off, const uint32_t* len,
+                       size_t stride, uint32_t ulen, int B, int dsize, int csize, int repair,
+                       uint8_t* out, const uint64_t* out_off, size_t out_stride,
+                       int32_t* status, int32_t* fixed);
+int frad_rs_encode(frad_ctx* ctx, const uint8_t* buf, const uint64_t* off, const uint32_t* len,
+                   size_t stride, uint32_t ulen, int B, size_t total_bytes, int dsize, int csize,
+                   uint8_t* out, const uint64_t* out_off, size_t out_stride, size_t out_total_bytes);
+int frad_rs_decode(frad_ctx* ctx, const uint8_t* buf, const uint64_t* off, const uint32_t* len,
+                   size_t stride, uint32_t ulen, int B, size_t total_bytes, int dsize, int csize, int repair,
+                   uint8_t* out, const uint64_t* out_off, size_t out_stride, size_t out_total_bytes,
+                   int32_t* status, int32_t* fixed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRADB200_H */

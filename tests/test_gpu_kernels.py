@@ -1,0 +1,216 @@
+"""GPU parity tests: the CUDA path (through the C ABI, frad_python_b200._abi.Context) against the
+CPU oracle and the golden vectors produced by the reference.  Run on the B200 box (-m gpu)."""
+import numpy as np
+import pytest
+
+from oracle import frad_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+LOSS0 = 1.25 ** 0 / 19 + 0.5
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from frad_python_b200 import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def values(payload: bytes, bits: int, le: bool):
+    return O.p0_unpack(payload, bits, le)
+
+
+# Tolerances (stated): the forward DCT of f32 PCM is computed in f32 like SciPy does; two different
+# f32 FFT factorisations differ by a few f32 ulps of the frame peak.  For |x| <= 1 the coefficients
+# are <= 1, so 4e-7 absolute (about 3 ulp at 1.0) bounds the difference; f64 paths agree to ~1e-15.
+TOL_F32 = 4e-7
+TOL_F64 = 2e-15
+
+
+@pytest.mark.parametrize("bits", [12, 16, 24, 32, 48, 64])
+@pytest.mark.parametrize("le", [False, True])
+def test_p0_encode_golden(ctx, g_p0, bits, le):
+    fr = g_p0["pcm_f32"]
+    nb, n, c = fr.shape
+    pay, peak, crc = ctx.p0_encode(fr.reshape(-1, c), nb, n, n, bits, le)
+    ref = g_p0[f"pay_f32_b{bits}_le{int(le)}"].tobytes()
+    assert pay.size == len(ref)
+    got, want = values(pay.tobytes(), bits, le), values(ref, bits, le)
+    tol = {12: 2e-3, 16: 1.3e-4}.get(bits, TOL_F32)      # 12/16-bit: one step of the f16 grid below 0.25
+    assert np.max(np.abs(got - want)) <= tol
+    if bits in (12, 16):                                  # the f16 grid hides f32 noise: almost all equal
+        assert np.mean(got != want) < 2e-3
+    assert [int(x) for x in crc] == [O.crc32(pay[i].tobytes()) for i in range(nb)]
+    for i in range(nb):
+        assert abs(peak[i] - np.max(np.abs(O.dct2_forward(fr[i])))) < 1e-6
+
+
+@pytest.mark.parametrize("bits", [12, 16, 24, 32, 48, 64])
+@pytest.mark.parametrize("le", [False, True])
+def test_p0_decode_golden(ctx, g_p0, bits, le):
+    ref_pay = g_p0[f"pay_f32_b{bits}_le{int(le)}"]
+    want = g_p0[f"dec_f32_b{bits}_le{int(le)}"]
+    nb, n, c = want.shape
+    out = ctx.p0_decode(ref_pay.reshape(nb, -1), nb, n, c, bits, le)
+    assert out.dtype == np.float64
+    assert np.max(np.abs(out - want)) <= 4e-15       # f64 inverse: a few ulp of the +-1 signal
+
+
+def test_p0_encode_f64_golden(ctx, g_p0):
+    fr = g_p0["pcm_f32"].astype(np.float64)
+    nb, n, c = fr.shape
+    for bits in (16, 32, 64):
+        pay, _, _ = ctx.p0_encode(fr.reshape(-1, c), nb, n, n, bits, False)
+        ref = g_p0[f"pay_f64_b{bits}_le0"].tobytes()
+        got, want = values(pay.tobytes(), bits, False), values(ref, bits, False)
+        tol = {16: 1.3e-4, 32: 6e-8, 64: TOL_F64}[bits]
+        assert np.max(np.abs(got - want)) <= tol
+        if bits == 32:
+            assert np.mean(got != want) < 1e-3   # f64 transform, f32 storage: equal except rounding ties
+
+
+def test_p0_ragged_and_generic_sizes(ctx, g_p0):
+    for key in g_p0.files:
+        if not key.startswith("rag_in_"):
+            continue
+        _, _, n, c = key.split("_")
+        n, c = int(n), int(c)
+        x = g_p0[key]
+        pay, _, crc = ctx.p0_encode(x, 1, n, n, 32, False)
+        want = values(g_p0[f"rag_pay_{n}_{c}"].tobytes(), 32, False)
+        got = values(pay.tobytes(), 32, False)
+        assert np.max(np.abs(got - want)) <= 1e-6, (n, c)
+        assert int(crc[0]) == O.crc32(pay.tobytes())
+        out = ctx.p0_decode(g_p0[f"rag_pay_{n}_{c}"].reshape(1, -1), 1, n, c, 32, False)
+        assert np.max(np.abs(out[0] - g_p0[f"rag_dec_{n}_{c}"])) <= 1e-13 * max(1, n), (n, c)
+        pay64, _, _ = ctx.p0_encode(x.astype(np.float64), 1, n, n, 64, True)
+        want = values(g_p0[f"rag_pay64_{n}_{c}"].tobytes(), 64, True)
+        assert np.max(np.abs(values(pay64.tobytes(), 64, True) - want)) <= 1e-14, (n, c)
+        out = ctx.p0_decode(g_p0[f"rag_pay64_{n}_{c}"].reshape(1, -1), 1, n, c, 64, True)
+        assert np.max(np.abs(out[0] - g_p0[f"rag_dec64_{n}_{c}"])) <= 1e-13 * max(1, n), (n, c)
+
+
+def test_p0_edges(ctx, g_p0):
+    x = g_p0["odd12_in"]
+    pay, _, _ = ctx.p0_encode(x, 1, 5, 5, 12, False)
+    assert pay.size == g_p0["odd12_pay"].size
+    assert np.max(np.abs(values(pay.tobytes(), 12, False) - values(g_p0["odd12_pay"].tobytes(), 12, False))) < 2e-3
+    out = ctx.p0_decode(g_p0["odd12_pay"].reshape(1, -1), 1, 5, 1, 12, False)
+    assert np.max(np.abs(out[0] - g_p0["odd12_dec"])) < 1e-15
+    # overflow peak lets the host apply the depth bump (profile0.py:24-26)
+    big = g_p0["bump_in"]
+    _, peak, _ = ctx.p0_encode(big, 1, 256, 256, 16, False)
+    assert peak[0] > np.finfo("f2").max
+    # NaN / Inf scrub
+    out = ctx.p0_decode(g_p0["scrub_pay"].reshape(1, -1), 1, 4, 2, 32, False)
+    assert np.max(np.abs(out[0] - g_p0["scrub_dec"])) < 1e-15
+
+
+P1_CASES = ["s48", "s48f64", "s96c8", "s44n1280", "s8n128", "s96n128", "s32n7168", "s48rag"]
+
+
+@pytest.mark.parametrize("name", P1_CASES)
+def test_p1_golden(ctx, g_p1, name):
+    sr, c, n, bits, ll = g_p1[f"{name}_meta"]
+    sr, c, n, bits = int(sr), int(c), int(n), int(bits)
+    fr = g_p1[f"{name}_pcm"]
+    nb = len(fr)
+    nn = O.samples_min_ge(n)
+    pcm = np.zeros((nb, nn, c), fr.dtype)
+    pcm[:, :n] = fr
+    q, tq, _ = ctx.p1_encode(pcm.reshape(-1, c), nb, nn, nn, bits, sr, float(ll))
+    gq, gtq = g_p1[f"{name}_q"], g_p1[f"{name}_tq"]
+    # stated bound: quantised integers bit-exact except <= 1 step at rounding boundaries,
+    # at most 1e-4 of the coefficients (f32 transform) and 1e-3 of the few threshold integers
+    assert np.max(np.abs(q.astype(np.int64) - gq)) <= 1
+    assert np.mean(q != gq) <= 1e-4 + 1.0 / q.size
+    assert np.max(np.abs(tq.astype(np.int64) - gtq)) <= 1
+    assert np.mean(tq != gtq) <= 1e-3 + 1.0 / tq.size
+    out = ctx.p1_decode(gq, gtq, None, nb, nn, c, bits, sr)
+    want = g_p1[f"{name}_dec"]
+    assert np.max(np.abs(out - want)) <= 1e-12 * max(1.0, np.max(np.abs(want)))
+
+
+def test_p1_silence(ctx, g_p1):
+    z = np.zeros((2048, 2), np.float32)
+    q, tq, _ = ctx.p1_encode(z, 1, 2048, 2048, 16, 48000, 0.55)
+    assert np.array_equal(q[0], g_p1["zero_q"]) and np.array_equal(tq[0], g_p1["zero_tq"])
+    out = ctx.p1_decode(q, tq, None, 1, 2048, 2, 16, 48000)
+    assert np.array_equal(out[0], g_p1["zero_dec"])
+
+
+def test_p1_overlapped_frames(ctx):
+    """hop < N: frames are read in place from the contiguous PCM (encoder.py:47-50 overlap)."""
+    pcm = O.synth_pcm(0.5, 48000, 2, seed=9)
+    hop, n = 1920, 2048
+    nb = (len(pcm) - n) // hop + 1
+    q, tq, _ = ctx.p1_encode(pcm, nb, n, hop, 16, 48000, LOSS0)
+    bad = 0
+    for i in range(nb):
+        oq, otq, *_ = O.p1_analogue_ints(pcm[i * hop:i * hop + n], 16, 48000, LOSS0)
+        assert np.max(np.abs(q[i] - oq)) <= 1 and np.array_equal(tq[i], otq)
+        bad += int(np.sum(q[i] != oq))
+    assert bad <= 1e-4 * nb * n * 2 + 1
+
+
+@pytest.mark.parametrize("name", ["s48", "s96c8", "s44n640"])
+def test_p2_golden(ctx, g_p2, name):
+    sr, c, n, bits, ll = g_p2[f"{name}_meta"]
+    sr, c, n, bits = int(sr), int(c), int(n), int(bits)
+    fr = g_p2[f"{name}_pcm"]
+    nb = len(fr)
+    q, tq, lpc = ctx.p1_encode(fr.reshape(-1, c), nb, n, n, bits, sr, float(ll), profile=2)
+    gq, gtq, gl = g_p2[f"{name}_q"], g_p2[f"{name}_tq"], g_p2[f"{name}_lpc"]
+    assert np.array_equal(lpc, gl)
+    assert np.max(np.abs(q.astype(np.int64) - gq)) <= 1
+    assert np.mean(q != gq) <= 1e-4 + 1.0 / q.size
+    assert np.max(np.abs(tq.astype(np.int64) - gtq)) <= 1
+    out = ctx.p1_decode(gq, gtq, gl, nb, n, c, bits, sr)
+    want = g_p2[f"{name}_dec"]
+    assert np.max(np.abs(out - want)) <= 1e-11 * max(1.0, np.max(np.abs(want)))
+
+
+def test_crc_golden_and_random(ctx, g_crc):
+    msgs = [g_crc[f"crc_in_{n}"].tobytes() for n in (0, 1, 9, 255, 4096, 20488)] + [b"123456789"]
+    rng = np.random.default_rng(1)
+    msgs += [rng.integers(0, 256, int(n), dtype=np.uint8).tobytes() for n in rng.integers(1, 70000, 40)]
+    c32 = ctx.crc_many(msgs, True)
+    c16 = ctx.crc_many(msgs, False)
+    assert [int(x) for x in c32] == [O.crc32(m) for m in msgs]
+    assert [int(x) for x in c16] == [O.crc16_arc(m) for m in msgs]
+    assert int(c32[6]) == 0xCBF43926 and int(c16[6]) == 0xBB3D
+
+
+def test_rs_encode_golden(ctx, g_crc):
+    for key in g_crc.files:
+        if not key.startswith("ecc_in_"):
+            continue
+        _, _, n, ds, cs = key.split("_")
+        enc = ctx.rs_encode_many([g_crc[key].tobytes()], int(ds), int(cs))[0]
+        assert enc == g_crc[f"ecc_out_{n}_{ds}_{cs}"].tobytes(), key
+    assert ctx.rs_encode_many([b"hello world"], 245, 10)[0] == b"hello world\xed%T\xc4\xfd\xfd\x89\xf3\xa8\xaa"
+
+
+def test_rs_repair_matches_oracle(ctx):
+    rng = np.random.default_rng(2)
+    for ds, cs in ((96, 24), (128, 20), (200, 55), (10, 7)):
+        bad = []
+        for i in range(24):
+            m = rng.integers(0, 256, int(rng.integers(1, 3000)), dtype=np.uint8).tobytes()
+            e = bytearray(O.ecc_encode(m, ds, cs))
+            block = ds + cs
+            for cw in range(0, len(e), block):
+                u = rng.random()
+                hi = min(cw + block, len(e))
+                ne = 0 if u < 0.4 else int(rng.integers(1, cs // 2 + 1)) if u < 0.8 else int(rng.integers(cs // 2 + 1, cs + 3))
+                for p in rng.choice(hi - cw, size=min(ne, hi - cw), replace=False):
+                    e[cw + p] ^= int(rng.integers(1, 256))
+            bad.append(bytes(e))
+        got, status, fixed = ctx.rs_decode_many(bad, ds, cs, True)
+        for g, b in zip(got, bad):
+            assert g == O.ecc_decode(b, ds, cs, True)
+        got, _, _ = ctx.rs_decode_many(bad, ds, cs, False)
+        for g, b in zip(got, bad):
+            assert g == O.ecc_decode(b, ds, cs, False)
