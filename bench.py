@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py -- FrAD hot-path throughput on B200 (contract in the task statement, section 4).
+
+Workload (BASELINE.json configs[1]): profile-1 lossy encode+decode of 10 min of synthetic 48 kHz
+stereo f32 PCM, frame 2048, overlap 1/16 (hop 1920), 16-bit scale, loss level 0 -> 15 000 frames.
+One "step" = one encode pass (PCM -> quantised integers q/tq) + one decode pass (q/tq -> PCM) over
+the whole clip.  Metric: encode+decode MSamples/s (scalar PCM values = samples x channels).
+
+  value     device-resident (inputs already in HBM), CUDA events on the library's stream
+  e2e       same work through the host-pointer C ABI (pinned host buffers, H2D/D2H inside the region)
+  roofline  dominant kernel: algorithmic bytes / event time vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the oracle port of the reference NumPy/SciPy path on a bounded sample, 1 core
+
+`--impl reference` times the oracle port (the reference cannot travel / be compiled: it is Python,
+see DESIGN.md) on all host cores.  N > 1: one process per GPU (torchrun), frames sharded by
+contiguous range, no collective on the data path; weak scaling (each rank encodes its own clip).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SRATE, CH, N, HOP, BITS = 48000, 2, 2048, 1920, 16
+LOSS = 1.25 ** 0 / 19 + 0.5
+SECONDS = 600
+NFRAMES = SECONDS * SRATE // HOP            # 15 000
+NBANDS = 27
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_pcm(seed):
+    """Synthetic PCM of SURVEY 8(d): built from a 10 s tile to keep generation fast."""
+    from oracle.frad_oracle import synth_pcm
+    tile = synth_pcm(10.0, SRATE, CH, seed)
+    need = (NFRAMES - 1) * HOP + N
+    reps = -(-need // len(tile))
+    return np.ascontiguousarray(np.tile(tile, (reps, 1))[:need])
+
+
+class ClockSampler:
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        # median of the upper half = clocks while the GPU was busy (idle samples sit at the bottom)
+        busy = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": (busy[len(busy) // 2] if busy else None), "sm_max_mhz": (max(mx) if mx else None),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_sample(frames_pcm):
+    """Oracle port of the reference path for a list of frames: ints out, PCM back.  Returns seconds."""
+    from oracle import frad_oracle as O
+    t0 = time.perf_counter()
+    for f in frames_pcm:
+        q, tq, n, b, sr = O.p1_analogue_ints(f, BITS, SRATE, LOSS)
+        O.p1_digital_ints(q, tq, b, CH, sr, n)
+    return time.perf_counter() - t0
+
+
+def _cpu_worker(args):
+    seed, start, count = args
+    from oracle.frad_oracle import synth_pcm
+    pcm = synth_pcm((count * HOP + N) / SRATE + 0.01, SRATE, CH, seed + start)
+    frames = [pcm[i * HOP:i * HOP + N] for i in range(count)]
+    return cpu_sample(frames)
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the oracle port (kind "port") on all host cores, bounded sample per step."""
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    per_core = 120                      # frames per core per step (~1 s of CPU each)
+    sample_frames = per_core * cores
+    ctxmp = mp.get_context("fork")
+    times = []
+    with ctxmp.Pool(cores) as pool:
+        for step in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            pool.map(_cpu_worker, [(1000 * step, c * per_core, per_core) for c in range(cores)])
+            dt = time.perf_counter() - t0
+            if step >= args.warmup:
+                times.append(dt)
+    total = sum(times)
+    scal = sample_frames * N * CH * len(times)
+    val = scal / total / 1e6
+    line = {
+        "impl": "reference", "metric": "encode+decode MSamples/s (profile 1, 48 kHz stereo)", "value": val,
+        "unit": "MSamples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 forward / f64 inverse", "data": "synthetic",
+        "x_realtime": val * 1e6 / (SRATE * CH),
+        "config": workload_config(sample_frames),
+        "cpu_baseline": {"value": val, "unit": "MSamples/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample_frames} frames of the workload per step ({per_core} per core), "
+                                   "oracle port of profile1 analogue/digital without Golomb/deflate"},
+        "e2e": {"value": val, "unit": "MSamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(frames):
+    return {"workload": "configs[1]: profile 1 encode+decode, 10 min 48 kHz stereo f32, N=2048, hop=1920, 16-bit, "
+                        "loss level 0 (hot path: PCM <-> quantised ints; Golomb/deflate excluded)",
+            "frames": frames, "channels": CH, "frame_size": N, "hop": HOP, "srate": SRATE,
+            "cache": "inputs (230 MB PCM / 246 MB ints) larger than the 126 MB L2"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--frames", type=int, default=NFRAMES)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import ctypes as C
+    from frad_python_b200 import Context, _abi
+    L = _abi.lib()
+    ctx = Context(local)
+    B = args.frames
+    pcm_host = make_pcm(1 + rank)[: (B - 1) * HOP + N]
+    nscal = B * HOP * CH if B == NFRAMES else B * HOP * CH          # scalar PCM values consumed per pass
+    ncoef = B * N * CH
+
+    # ---- device-resident leg -----------------------------------------------------------------
+    d_pcm = ctx.dev(pcm_host.nbytes)
+    d_q = ctx.dev(ncoef * 4)
+    d_tq = ctx.dev(B * NBANDS * CH * 4)
+    d_out = ctx.dev(ncoef * 8)
+    ctx.h2d(d_pcm, pcm_host)
+    ctx.sync()
+
+    def enc():
+        ctx.check(L.frad_p1_encode_dev(ctx.handle, d_pcm.ptr, _abi.F32, HOP, B, N, CH, BITS, SRATE, LOSS, _abi.PREC_REF,
+                                       d_q.ptr, d_tq.ptr, None))
+
+    def dec():
+        ctx.check(L.frad_p1_decode_dev(ctx.handle, d_q.ptr, d_tq.ptr, None, B, N, CH, BITS, SRATE, _abi.PREC_REF,
+                                       d_out.ptr, _abi.F64))
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            dist.barrier()
+        ctx.sync()
+
+    for _ in range(max(args.warmup, 3)):
+        enc(); dec()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = ctx.launches
+    t_enc = t_dec = 0.0
+    ctx.event(0)
+    for _ in range(args.steps):
+        ctx.event(2); enc(); ctx.event(3); dec(); ctx.event(4)
+        ctx.sync()
+        t_enc += ctx.elapsed_ms(2, 3)
+        t_dec += ctx.elapsed_ms(3, 4)
+    ctx.event(1)
+    barrier()
+    total_ms = ctx.elapsed_ms(0, 1)
+    launches = ctx.launches - launches0
+
+    # ---- end-to-end leg: host buffers through the C ABI ------------------------------------------
+    h_pcm = ctx.pinned(pcm_host.shape, np.float32); h_pcm[...] = pcm_host
+    h_q = ctx.pinned((B, N * CH), np.int32)
+    h_tq = ctx.pinned((B, NBANDS * CH), np.int32)
+    h_out = ctx.pinned((B, N, CH), np.float64)
+
+    def e2e_step():
+        ctx.check(L.frad_p1_encode(ctx.handle, h_pcm.ctypes.data, _abi.F32, HOP, B, N, CH, BITS, SRATE, LOSS,
+                                   _abi.PREC_REF, h_q.ctypes.data, h_tq.ctypes.data, None))
+        ctx.check(L.frad_p1_decode(ctx.handle, h_q.ctypes.data, h_tq.ctypes.data, None, B, N, CH, BITS, SRATE,
+                                   _abi.PREC_REF, h_out.ctypes.data, _abi.F64))
+
+    e2e_step()
+    barrier()
+    e2e_steps = max(2, min(args.steps, 5))
+    ctx.event(5)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    ctx.event(6)
+    barrier()
+    e2e_ms = max(ctx.elapsed_ms(5, 6), 1e3 * (time.perf_counter() - t0))
+    launches += 0
+    clocks = sampler.stop()
+
+    # sanity: the e2e result must be real data (decoded audio close to the input)
+    err = float(np.max(np.abs(h_out[1, :HOP].astype(np.float64) - pcm_host[HOP:2 * HOP])))
+
+    if dist is not None:
+        import torch
+        t = torch.tensor([total_ms, e2e_ms, t_enc, t_dec], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_ms, t_enc, t_dec = [float(x) for x in t.tolist()]
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    ms_per_step = total_ms / args.steps
+    value = world * nscal / (ms_per_step * 1e-3) / 1e6
+    e2e_val = world * nscal / (e2e_ms / e2e_steps * 1e-3) / 1e6
+    hbm, how = peaks()
+    enc_ms, dec_ms = t_enc / args.steps, t_dec / args.steps
+    k_enc = {"kernel": "seq_encode_kernel<float> (profile-1 forward DCT + masking + quantiser)",
+             "bytes": ncoef * 8.0, "ms": enc_ms}
+    k_dec = {"kernel": "seq_decode_kernel<double> (profile-1 dequantiser + inverse DCT, f64 PCM out)",
+             "bytes": ncoef * 12.0, "ms": dec_ms}
+    dom = k_dec if dec_ms >= enc_ms else k_enc
+    for k in (k_enc, k_dec):
+        k["gbs"] = k["bytes"] / (k["ms"] * 1e-3) / 1e9
+        k["frac"] = k["gbs"] / hbm
+    line = {
+        "metric": "encode+decode MSamples/s (profile 1, 48 kHz stereo)", "value": value, "unit": "MSamples/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 forward / f64 inverse", "data": "synthetic",
+        "x_realtime": value * 1e6 / (SRATE * CH),
+        "config": workload_config(B),
+        "e2e": {"value": e2e_val, "unit": "MSamples/s",
+                "h2d_bytes_per_step": int(h_pcm.nbytes + h_q.nbytes + h_tq.nbytes),
+                "d2h_bytes_per_step": int(h_q.nbytes + h_tq.nbytes + h_out.nbytes),
+                "x_realtime": e2e_val * 1e6 / (SRATE * CH), "roundtrip_max_abs_err": err},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": dom["gbs"], "peak": hbm, "unit": "GB/s", "frac": dom["frac"],
+                     "traffic": None, "kernel": dom["kernel"], "peak_source": how,
+                     "algorithmic_bytes_per_launch": dom["bytes"], "launch_ms": dom["ms"]},
+        "kernels": [k_enc, k_dec],
+    }
+    if not args.no_cpu and world == 1:
+        from oracle.frad_oracle import synth_pcm  # noqa: F401
+        nsample = 1500
+        frames = [pcm_host[i * HOP:i * HOP + N] for i in range(nsample)]
+        dt = cpu_sample(frames)
+        line["cpu_baseline"] = {"value": nsample * N * CH / dt / 1e6, "unit": "MSamples/s", "cores": 1, "kind": "port",
+                                "sample": f"first {nsample} frames of the workload, oracle port of profile1 "
+                                          "analogue/digital (NumPy/SciPy, per frame like the reference), "
+                                          "without Golomb/deflate"}
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
