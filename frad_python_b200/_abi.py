@@ -16,6 +16,7 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "lib
 F32, F64, S8, S16, S32, S64, U8, U16, U32, U64, F16 = range(11)
 PREC_REF, PREC_F32, PREC_F64 = 0, 1, 2
 NBANDS, LPC_LEN = 27, 13
+OPT_FORCE_GENERIC, OPT_EXACT_QUANT = 1, 2
 
 _NP2CODE = {
     np.dtype("<f4"): F32, np.dtype("<f8"): F64, np.dtype("i1"): S8, np.dtype("<i2"): S16, np.dtype("<i4"): S32,
@@ -62,6 +63,7 @@ def lib():
             "frad_device_count": (i32, []),
             "frad_sm_count": (i32, [vp]),
             "frad_kernel_launches": (C.c_uint64, [vp]),
+            "frad_set_option": (i32, [vp, i32, i32]),
             "frad_host_alloc": (vp, [vp, sz]),
             "frad_host_free": (None, [vp, vp]),
             "frad_dev_alloc": (vp, [vp, sz]),
@@ -109,7 +111,7 @@ def lib():
 
 EXPORTS = [
     "frad_ctx_create", "frad_ctx_destroy", "frad_last_error", "frad_sync", "frad_stream", "frad_device_count",
-    "frad_sm_count", "frad_kernel_launches", "frad_host_alloc", "frad_host_free", "frad_dev_alloc", "frad_dev_free",
+    "frad_sm_count", "frad_kernel_launches", "frad_set_option", "frad_host_alloc", "frad_host_free", "frad_dev_alloc", "frad_dev_free",
     "frad_h2d", "frad_d2h", "frad_memset_dev", "frad_event_record", "frad_event_elapsed_ms",
     "frad_p0_payload_bytes", "frad_p0_encode_dev", "frad_p0_decode_dev", "frad_p0_encode", "frad_p0_decode",
     "frad_p1_encode_dev", "frad_p1_decode_dev", "frad_p1_encode", "frad_p1_decode",
@@ -183,6 +185,9 @@ class Context:
 
     def sync(self):
         self.check(lib().frad_sync(self.handle))
+
+    def set_option(self, option: int, value: int):
+        self.check(lib().frad_set_option(self.handle, option, value))
 
     @property
     def sm_count(self) -> int:

@@ -30,6 +30,8 @@ struct frad_ctx {
   std::map<uint64_t, void*> band_tables;     // key: N | srate<<32
   void* crc_tables = nullptr;                // device CRC tables (crc.cu)
   void* dequant_table = nullptr;             // |q|^(4/3) for small |q| (p1 decode)
+  int opt_force_generic = 0;                 // FRAD_OPT_FORCE_GENERIC: bypass the N = 2048 fast path (tests)
+  int opt_exact_quant = 0;                   // FRAD_OPT_EXACT_QUANT: always take the f64 quantiser branch (tests)
 };
 
 static inline int frad_fail(frad_ctx* ctx, int code, const char* what, const char* detail = nullptr) {

@@ -141,3 +141,12 @@ void* frad_scratch(frad_ctx* ctx, int slot, size_t bytes) {
   ctx->scratch_cap[slot] = cap;
   return p;
 }
+
+extern "C" int frad_set_option(frad_ctx* ctx, int option, int value) {
+  if (!ctx) return FRAD_E_ARG;
+  switch (option) {
+    case FRAD_OPT_FORCE_GENERIC: ctx->opt_force_generic = value; return FRAD_OK;
+    case FRAD_OPT_EXACT_QUANT: ctx->opt_exact_quant = value; return FRAD_OK;
+    default: return frad_fail(ctx, FRAD_E_ARG, "unknown option");
+  }
+}

@@ -1,0 +1,113 @@
+// Register-resident 32-point complex FFT (radix 4 x 8) and the warp-level 1024-point FFT built
+// from two of them (one shared-memory exchange, no block barrier).  All register indices are
+// compile-time constants after unrolling.
+#pragma once
+#include "devmath.cuh"
+
+// exp(-2 pi i t / 32): cos / sin tables; folded to immediates after unrolling
+__device__ __forceinline__ double w32_cos(int t) {
+  const double c[32] = {
+      1.0, 0.9807852804032304, 0.9238795325112867, 0.8314696123025452, 0.7071067811865476,
+      0.5555702330196023, 0.38268343236508984, 0.19509032201612833, 0.0, -0.1950903220161282,
+      -0.3826834323650897, -0.555570233019602, -0.7071067811865475, -0.8314696123025453,
+      -0.9238795325112867, -0.9807852804032304, -1.0, -0.9807852804032304, -0.9238795325112868,
+      -0.8314696123025455, -0.7071067811865477, -0.5555702330196022, -0.38268343236509034,
+      -0.19509032201612866, 0.0, 0.1950903220161283, 0.38268343236509, 0.5555702330196018,
+      0.7071067811865474, 0.8314696123025452, 0.9238795325112865, 0.9807852804032303};
+  return c[t & 31];
+}
+__device__ __forceinline__ double w32_sin(int t) {   // sin(2 pi t / 32) (positive angle)
+  const double s[32] = {
+      0.0, 0.19509032201612825, 0.3826834323650898, 0.5555702330196022, 0.7071067811865475,
+      0.8314696123025452, 0.9238795325112867, 0.9807852804032304, 1.0, 0.9807852804032304,
+      0.9238795325112867, 0.8314696123025455, 0.7071067811865476, 0.5555702330196022, 0.3826834323650899,
+      0.1950903220161286, 0.0, -0.19509032201612836, -0.38268343236508967, -0.555570233019602,
+      -0.7071067811865475, -0.8314696123025452, -0.9238795325112865, -0.9807852804032303, -1.0,
+      -0.9807852804032304, -0.9238795325112866, -0.8314696123025455, -0.7071067811865477,
+      -0.5555702330196022, -0.3826834323650904, -0.19509032201612872};
+  return s[t & 31];
+}
+
+// v *= exp(-+ 2 pi i t / 32), t compile-time after unrolling
+template <typename T, bool INV, typename V>
+__device__ __forceinline__ V mul_w32(V v, int t) {
+  t &= 31;
+  if (t == 0) return v;
+  if (t == 8) return mul_mi<INV>(v);                  // -i (forward) / +i (inverse)
+  if (t == 16) { v.x = -v.x; v.y = -v.y; return v; }
+  if (t == 24) return mul_mi<!INV>(v);
+  const T c = (T)w32_cos(t);
+  const T s = (T)(INV ? w32_sin(t) : -w32_sin(t));
+  V r;
+  r.x = v.x * c - v.y * s;
+  r.y = v.x * s + v.y * c;
+  return r;
+}
+
+template <typename T, bool INV, typename V>
+__device__ __forceinline__ void fft4_inplace(V& a, V& b, V& c, V& d) {
+  V s0 = cadd(a, c), s1 = csub(a, c), s2 = cadd(b, d), s3 = mul_mi<INV>(csub(b, d));
+  a = cadd(s0, s2); c = csub(s0, s2); b = cadd(s1, s3); d = csub(s1, s3);
+}
+
+// 8-point DFT in place; output index of position p is perm8(p) = (p >> 2) + 2 * (p & 3)
+template <typename T, bool INV, typename V>
+__device__ __forceinline__ void fft8_perm(V* v) {
+#pragma unroll
+  for (int n2 = 0; n2 < 4; n2++) {
+    V a = v[n2], b = v[n2 + 4];
+    v[n2] = cadd(a, b);
+    v[n2 + 4] = mul_w32<T, INV>(csub(a, b), 4 * n2);   // W8^{n2}
+  }
+  fft4_inplace<T, INV>(v[0], v[1], v[2], v[3]);
+  fft4_inplace<T, INV>(v[4], v[5], v[6], v[7]);
+}
+
+__host__ __device__ constexpr int perm8(int p) { return (p >> 2) + 2 * (p & 3); }
+// position P of fft32_perm's output holds frequency index perm32(P)
+__host__ __device__ constexpr int perm32(int P) { return (P >> 3) + 4 * perm8(P & 7); }
+// position that holds frequency index o
+__host__ __device__ constexpr int inv32(int o) { return 8 * (o & 3) + 4 * ((o >> 2) & 1) + (o >> 3); }
+
+// 32-point DFT in place, natural input order, permuted output (see perm32)
+template <typename T, bool INV, typename V>
+__device__ __forceinline__ void fft32_perm(V* v) {
+#pragma unroll
+  for (int n2 = 0; n2 < 8; n2++) {
+    fft4_inplace<T, INV>(v[n2], v[n2 + 8], v[n2 + 16], v[n2 + 24]);
+#pragma unroll
+    for (int k1 = 1; k1 < 4; k1++) v[8 * k1 + n2] = mul_w32<T, INV>(v[8 * k1 + n2], n2 * k1);
+  }
+#pragma unroll
+  for (int k1 = 0; k1 < 4; k1++) fft8_perm<T, INV>(v + 8 * k1);
+}
+
+// padded complex index inside a per-warp exchange buffer: one pad element per 32
+__device__ __forceinline__ int padc(int a) { return a + (a >> 5); }
+
+// Warp-level 1024-point FFT.  In: v[i] = z[lane + 32 i].  Out: v[o] = Z[lane + 32 o].
+// buf: this warp's exchange buffer (>= 1056 complex).  tw32: table [i][lane] = exp(-2 pi i * i * lane / 1024).
+template <typename T, bool INV>
+__device__ __forceinline__ void fft1024_warp(typename vec2<T>::type* v, typename vec2<T>::type* buf, int lane,
+                                             const typename vec2<T>::type* __restrict__ tw32) {
+  typedef typename vec2<T>::type V;
+  fft32_perm<T, INV>(v);
+#pragma unroll
+  for (int P = 0; P < 32; P++) buf[33 * lane + perm32(P)] = v[P];
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 32; i++) v[i] = buf[lane + 33 * i];
+  __syncwarp();
+#pragma unroll
+  for (int i = 1; i < 32; i++) {
+    V w = __ldg(&tw32[i * 32 + lane]);
+    if (INV) w.y = -w.y;
+    v[i] = cmul(v[i], w);
+  }
+  fft32_perm<T, INV>(v);
+  V t[32];
+#pragma unroll
+  for (int o = 0; o < 32; o++) t[o] = v[inv32(o)];
+#pragma unroll
+  for (int o = 0; o < 32; o++) v[o] = t[o];
+}

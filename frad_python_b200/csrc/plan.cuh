@@ -19,6 +19,7 @@ struct frad_plan {
   int npass = 0;
   int radix[FRAD_MAX_RADIX_PASSES] = {};
   void *tw = nullptr, *cf = nullptr, *df = nullptr, *ci = nullptr, *ei = nullptr;
+  void* tw32 = nullptr;  // N == 2048 only: [i][lane] = exp(-2 pi i * i * lane / 1024) for the 32 x 32 warp FFT
   double* ct = nullptr;
 };
 

@@ -162,7 +162,7 @@ __device__ __forceinline__ double np_sum_small(const double* a, int n) {
 // ---- TNS (p2tools.py) --------------------------------------------------------------------------
 // x: masked spectrum (double, N), work: N doubles.  On return bw->flag != 0 means the residual in
 // `work` replaces x and bw->aq holds the quantised LPC; otherwise x stands and aq is all zero.
-__device__ void tns_analysis_block(const double* x, double* work, int N, band_work* bw) {
+static __device__ void tns_analysis_block(const double* x, double* work, int N, band_work* bw) {
   const int t = threadIdx.x;
   if (t < FRAD_LPC_LEN) bw->aq[t] = 0;
   if (t == 0) bw->flag = 0;
@@ -283,7 +283,7 @@ __device__ void tns_analysis_block(const double* x, double* work, int N, band_wo
 
 // all-pole synthesis lfilter([1], a, x) by one thread, scipy's transposed direct form II order.
 // x: N doubles (input), y: N doubles (output).  Returns through bw->flag whether y is usable.
-__device__ void tns_synthesis_block(const double* x, double* y, int N, band_work* bw) {
+static __device__ void tns_synthesis_block(const double* x, double* y, int N, band_work* bw) {
   if (threadIdx.x == 0) {
     double z[FRAD_LPC_LEN];
     for (int i = 0; i < FRAD_LPC_LEN; i++) z[i] = 0.0;

@@ -60,7 +60,7 @@ static void unit_root(long long num, long long den, long double* c, long double*
 
 void frad_plan_free(frad_plan* p) {
   if (!p) return;
-  cudaFree(p->tw); cudaFree(p->cf); cudaFree(p->df); cudaFree(p->ci); cudaFree(p->ei); cudaFree(p->ct);
+  cudaFree(p->tw); cudaFree(p->cf); cudaFree(p->df); cudaFree(p->ci); cudaFree(p->ei); cudaFree(p->ct); cudaFree(p->tw32);
   delete p;
 }
 
@@ -85,6 +85,12 @@ static bool build_tables(frad_ctx* ctx, frad_plan* p) {
   }
   p->ci = upload_cpx<T>(ctx, re, im);
   p->ei = upload_cpx<T>(ctx, re2, im2);
+  if (N == 2048) {
+    re.resize(1024); im.resize(1024);
+    for (int i = 0; i < 32; i++) for (int l = 0; l < 32; l++) unit_root(-2LL * i * l, 1024, &re[i * 32 + l], &im[i * 32 + l]);
+    p->tw32 = upload_cpx<T>(ctx, re, im);
+    if (!p->tw32) return false;
+  }
   return p->tw && p->cf && p->df && p->ci && p->ei;
 }
 
@@ -416,8 +422,10 @@ static int resolve_prec_fwd(int prec, int pcm_dtype) {
 }
 static int resolve_prec_inv(int prec) { return (prec == FRAD_PREC_F32) ? FRAD_PREC_F32 : FRAD_PREC_F64; }
 
-int frad_launch_encode_2048(frad_ctx* ctx, const enc_params& P, const frad_plan* pl, int prec);   // dct2048.cu
+int frad_launch_encode_2048(frad_ctx* ctx, const enc_params& P, const frad_plan* pl, int prec, int force_exact);   // dct2048.cu
 int frad_launch_decode_2048(frad_ctx* ctx, const dec_params& P, const frad_plan* pl, int prec);
+bool frad_fast2048_encode_ok(const enc_params& P, int prec);
+bool frad_fast2048_decode_ok(const dec_params& P, int prec);
 
 static int launch_encode(frad_ctx* ctx, enc_params& P, int prec) {
   if (P.B <= 0) return FRAD_OK;
@@ -440,7 +448,7 @@ static int launch_encode(frad_ctx* ctx, enc_params& P, int prec) {
     return FRAD_OK;
   }
 #ifdef FRAD_HAVE_FAST2048
-  if (P.N == 2048 && P.fast_ok) return frad_launch_encode_2048(ctx, P, pl, prec);
+  if (!ctx->opt_force_generic && frad_fast2048_encode_ok(P, prec)) return frad_launch_encode_2048(ctx, P, pl, prec, ctx->opt_exact_quant);
 #endif
   launch_cfg cfg;
   const void* k = (prec == FRAD_PREC_F32) ? (const void*)seq_encode_kernel<float> : (const void*)seq_encode_kernel<double>;
@@ -475,7 +483,7 @@ static int launch_decode(frad_ctx* ctx, dec_params& P, int prec) {
     return FRAD_OK;
   }
 #ifdef FRAD_HAVE_FAST2048
-  if (P.N == 2048 && P.fast_ok) return frad_launch_decode_2048(ctx, P, pl, prec);
+  if (!ctx->opt_force_generic && frad_fast2048_decode_ok(P, prec)) return frad_launch_decode_2048(ctx, P, pl, prec);
 #endif
   launch_cfg cfg;
   const void* k = (prec == FRAD_PREC_F32) ? (const void*)seq_decode_kernel<float> : (const void*)seq_decode_kernel<double>;

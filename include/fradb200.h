@@ -69,6 +69,11 @@ int  frad_device_count(void);
 int  frad_sm_count(frad_ctx* ctx);
 uint64_t frad_kernel_launches(frad_ctx* ctx);    /* kernels launched through this ctx so far */
 
+/* test / diagnostic switches (default 0): results must not depend on them beyond the stated tolerances */
+enum { FRAD_OPT_FORCE_GENERIC = 1,   /* bypass the N = 2048 fast kernels */
+       FRAD_OPT_EXACT_QUANT = 2 };   /* profile-1 quantiser: always evaluate the f64 formula */
+int  frad_set_option(frad_ctx* ctx, int option, int value);
+
 void* frad_host_alloc(frad_ctx* ctx, size_t bytes);   /* pinned host memory, NULL on failure */
 void  frad_host_free(frad_ctx* ctx, void* p);
 void* frad_dev_alloc(frad_ctx* ctx, size_t bytes);    /* device memory, NULL on failure */

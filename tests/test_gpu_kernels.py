@@ -214,3 +214,56 @@ def test_rs_repair_matches_oracle(ctx):
         got, _, _ = ctx.rs_decode_many(bad, ds, cs, False)
         for g, b in zip(got, bad):
             assert g == O.ecc_decode(b, ds, cs, False)
+
+
+def test_fast2048_quantiser_exact_branch_consistency(ctx):
+    """The f32 fast branch of the N=2048 quantiser must give exactly the integers of the f64 formula."""
+    from frad_python_b200 import _abi
+    pcm = O.synth_pcm(1.0, 48000, 2, seed=21)
+    nb = (len(pcm) - 2048) // 1920 + 1
+    for bits, loss in ((16, LOSS0), (24, 0.125), (8, 3.0)):
+        q1, tq1, _ = ctx.p1_encode(pcm, nb, 2048, 1920, bits, 48000, loss)
+        ctx.set_option(_abi.OPT_EXACT_QUANT, 1)
+        try:
+            q2, tq2, _ = ctx.p1_encode(pcm, nb, 2048, 1920, bits, 48000, loss)
+        finally:
+            ctx.set_option(_abi.OPT_EXACT_QUANT, 0)
+        assert np.array_equal(q1, q2) and np.array_equal(tq1, tq2)
+
+
+def test_fast2048_matches_generic_path(ctx):
+    """N=2048 fast kernels vs the generic shared-memory kernels (different FFT factorisation)."""
+    from frad_python_b200 import _abi
+    for c in (1, 2, 3, 8):
+        pcm = O.synth_pcm(0.3, 48000, c, seed=30 + c)
+        nb = len(pcm) // 2048
+        res = {}
+        for mode in (0, 1):
+            ctx.set_option(_abi.OPT_FORCE_GENERIC, mode)
+            try:
+                pay, peak, crc = ctx.p0_encode(pcm, nb, 2048, 2048, 32, False)
+                q, tq, _ = ctx.p1_encode(pcm, nb, 2048, 2048, 16, 48000, LOSS0)
+                dec0 = ctx.p0_decode(pay, nb, 2048, c, 32, False)
+                dec1 = ctx.p1_decode(q, tq, None, nb, 2048, c, 16, 48000)
+                dec1f = ctx.p1_decode(q, tq, None, nb, 2048, c, 16, 48000, prec=_abi.PREC_F32)
+                res[mode] = (values(pay.tobytes(), 32, False), peak, q, tq, dec0, dec1, dec1f, pay)
+            finally:
+                ctx.set_option(_abi.OPT_FORCE_GENERIC, 0)
+        a, b = res[0], res[1]
+        assert np.max(np.abs(a[0] - b[0])) <= TOL_F32
+        assert np.max(np.abs(a[1] - b[1])) <= 1e-6
+        assert np.max(np.abs(a[2] - b[2])) <= 1 and np.mean(a[2] != b[2]) <= 1e-4 + 1.0 / a[2].size
+        assert np.max(np.abs(a[3] - b[3])) <= 1
+        # decode of identical inputs: fast f64 kernel vs generic f64 kernel
+        dec0g = None
+        assert np.max(np.abs(a[5] - ctx.p1_decode(a[2], a[3], None, nb, 2048, c, 16, 48000))) == 0.0
+        ctx.set_option(_abi.OPT_FORCE_GENERIC, 1)
+        try:
+            ref0 = ctx.p0_decode(a[7], nb, 2048, c, 32, False)
+            ref1 = ctx.p1_decode(a[2], a[3], None, nb, 2048, c, 16, 48000)
+        finally:
+            ctx.set_option(_abi.OPT_FORCE_GENERIC, 0)
+        assert np.max(np.abs(a[4] - ref0)) <= 1e-14
+        assert np.max(np.abs(a[5] - ref1)) <= 1e-13
+        # f32 inverse (fast mode): stated tolerance 1 LSB at 16 bit = 3.05e-5; measured ~1e-6
+        assert np.max(np.abs(a[6] - ref1)) <= 3e-6
