@@ -8,8 +8,10 @@
 //   encode  PCM f32 -> DCT-II -> profile 0: big/little-endian f32 payload + per-frame peak
 //                             -> profile 1: band energies (register partials + transposed warp
 //                                reduction), thresholds, divisor ramps, power-law quantiser (f32 fast
-//                                path with an exact f64 re-evaluation next to rounding boundaries)
+//                                branch with an exact f64 re-evaluation next to rounding boundaries)
 //   decode  payload / quantised ints -> dequantise -> DCT-III -> PCM (f64 or f32 out)
+// The real-FFT split and the DCT twiddles are applied pairwise (k, M-k): one pair yields
+// X[k], X[N-k], X[M-k], X[M+k] from two complex multiplies (see DESIGN.md "Transform").
 // Reference lines: fourier/profile0.py:21-30,63-69; fourier/profile1.py:21-40,65-77;
 // fourier/tools/p1tools.py:18-44.
 #include "plan.cuh"
@@ -20,16 +22,17 @@ namespace {
 
 constexpr int FN = 2048, FM = 1024, FW = 8;          // frame, half, warps per CTA
 constexpr int SEQ_CPX = 1056;                        // padded complex slots per warp buffer
+constexpr int DQ_TAB = 1024;                         // f32 dequantiser table entries (|q| < DQ_TAB)
+constexpr int DQ_TAB64 = 4096;                       // f64 table (global memory)
+#define FRAD_RSQRT2 0.70710678118654752440
 
-__device__ __forceinline__ int zword(int n) {        // word index (in units of T) of sample n inside the z layout
+__device__ __forceinline__ int zword(int n) {        // word index (units of T) of sample n inside the z layout
   const int nn = (n & 1) ? (2 * FN - 1 - n) : n;
   return 2 * padc(nn >> 2) + ((nn >> 1) & 1);
 }
 __device__ __forceinline__ int swz(int n) { return (n & ~31) | ((n + (n >> 5)) & 31); }
 
-template <typename T> __device__ __forceinline__ T shfl_t(T v, int src);
-template <> __device__ __forceinline__ float shfl_t<float>(float v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-template <> __device__ __forceinline__ double shfl_t<double>(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+template <typename T> __device__ __forceinline__ T shfl_t(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
 // 32 per-lane partial sums (index = band) -> lane b holds the warp total of band b.  31 shuffles.
 __device__ __forceinline__ float transpose_reduce32(float* part, int lane) {
@@ -56,40 +59,70 @@ __host__ __device__ inline tile_map make_tiles(int B, int C) {
   return t;
 }
 
+struct smem_tail {
+  int lo[FRAD_NBANDS + 1];
+  double thr[FW][FRAD_NBANDS + 1];
+  float dq[DQ_TAB];                                   // decode only: |q|^(4/3) / scale
+};
+
+// ---- cooperative staging helpers ----------------------------------------------------------------
+// Frame words (32-bit) are interleaved [i][c]; word e = i*C + c goes to / comes from per-sequence
+// buffer (f*C + c) at word position POS(i).  CT == 2 is unrolled with linear addressing.
+template <int CT, int STRIDE_WORDS, typename POS>
+__device__ __forceinline__ void scatter_frame(const uint4* __restrict__ src, uint32_t* seq_base, int C, int f, int tid, POS pos) {
+  const int words = FN * C;
+  if (CT == 2) {
+#pragma unroll
+    for (int it = 0; it < FN * 2 / 4 / (FW * 32); it++) {
+      const int e4 = tid + it * FW * 32;
+      const uint4 x = __ldg(src + e4);
+      uint32_t* s0 = seq_base + (size_t)(f * 2) * STRIDE_WORDS;
+      uint32_t* s1 = s0 + STRIDE_WORDS;
+      const int p0 = pos(2 * e4), p1 = pos(2 * e4 + 1);
+      s0[p0] = x.x; s1[p0] = x.y; s0[p1] = x.z; s1[p1] = x.w;
+    }
+  } else {
+    for (int e4 = tid; e4 < words / 4; e4 += FW * 32) {
+      const uint4 x = __ldg(src + e4);
+      const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int e = 4 * e4 + j;
+        const int i = e / C, c = e - i * C;
+        (seq_base + (size_t)(f * C + c) * STRIDE_WORDS)[pos(i)] = xs[j];
+      }
+    }
+  }
+}
+
+template <int CT, int STRIDE_WORDS, typename W, typename O, typename POS, typename CVT>
+__device__ __forceinline__ void gather4(const W* seq_base, int C, int f, int e4, POS pos, CVT cvt, O* o4) {
+  if (CT == 2) {
+    const W* s0 = seq_base + (size_t)(f * 2) * STRIDE_WORDS;
+    const W* s1 = s0 + STRIDE_WORDS;
+    const int p0 = pos(2 * e4), p1 = pos(2 * e4 + 1);
+    o4[0] = cvt(s0[p0]); o4[1] = cvt(s1[p0]); o4[2] = cvt(s0[p1]); o4[3] = cvt(s1[p1]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int e = 4 * e4 + j;
+      const int i = e / C, c = e - i * C;
+      o4[j] = cvt((seq_base + (size_t)(f * C + c) * STRIDE_WORDS)[pos(i)]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // encode
 // ------------------------------------------------------------------------------------------------
-struct enc_smem_tail {
-  int lo[FRAD_NBANDS + 1];
-  double thr[FW][FRAD_NBANDS + 1];
-};
-
-// quantiser for one coefficient: rint(sign(x) |x * scale / div|^0.75), exact w.r.t. the f64 formula
-__device__ __forceinline__ int quant_one(float x, float a, float nb, float t0f, float t1f, float invn, float scalef,
-                                         double t0, double step, double scale, bool force_exact) {
-  // ramp value as a convex combination (no cancellation): (t0 (n - j) + t1 j) / n
-  const float divf = (t0f * nb + t1f * a) * invn;
-  const float y = fabsf(x) * scalef * __frcp_rn(divf);
-  float s, v;
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(y));
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(v) : "f"(y * s));
-  const float big = v + 12582912.0f;                 // round-to-nearest-even to an integer for v < 2^22
-  const float r = big - 12582912.0f;
-  const float dist = fabsf(v - r);
-  const bool fast_ok = (dist < 0.5f - (8e-7f * v + 1e-7f)) && (v < 2.0e6f) && (divf > 0.0f) && !force_exact;
-  int m;
-  if (fast_ok) {
-    m = __float_as_int(big) - 0x4B400000;
-  } else {
-    const double div = __dadd_rn(__dmul_rn((double)a, step), t0);       // np.linspace: j * step + start
-    double rr = 0.0;
-    if (div != 0.0) {
-      const double yy = fabs(((double)x / div) * scale);
-      rr = rint(sqrt(yy * sqrt(yy)));
-    }
-    m = (rr >= 2147483647.0) ? 2147483647 : (int)rr;
-    if (!(rr == rr)) m = 0;
-  }
+// exact quantiser of one coefficient (the f64 formula of profile1.py:31-36 with np.linspace's ramp)
+__device__ __noinline__ int quant_exact(float x, int j, double t0, double step, double scale) {
+  const double div = __dadd_rn(__dmul_rn((double)j, step), t0);
+  if (div == 0.0) return 0;
+  const double yy = fabs(((double)x / div) * scale);
+  const double rr = rint(sqrt(yy * sqrt(yy)));
+  if (!(rr == rr)) return 0;
+  const int m = (rr >= 2147483647.0) ? 2147483647 : (int)rr;
   return (x < 0.0f) ? -m : m;
 }
 
@@ -98,34 +131,23 @@ __global__ void __launch_bounds__(FW * 32, 2) enc2048_kernel(enc_params P, plan_
                                                              int force_exact) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* seq_all = (float2*)smem_raw;
-  enc_smem_tail* tail = (enc_smem_tail*)(smem_raw + (size_t)FW * SEQ_CPX * sizeof(float2));
+  smem_tail* tail = (smem_tail*)(smem_raw + (size_t)FW * SEQ_CPX * sizeof(float2));
   const int C = CT ? CT : P.C;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const tile_map tm = make_tiles(P.B, C);
   const float* pcm = (const float*)P.pcm;
-  const float2* cf = (const float2*)pl.cf;
-  const float2* df = (const float2*)pl.df;
+  const float2* cfh = (const float2*)pl.cfh;
+  const float2* dfh = (const float2*)pl.dfh;
   if (PROFILE == 1 && tid <= FRAD_NBANDS) { const int e = P.bt->edge[tid]; tail->lo[tid] = (e < FN) ? e : FN; }
-  const int words_per_frame = FN * C;                     // 32-bit words of input and of output per frame
+  const int words_per_frame = FN * C;
 
   for (int tile = blockIdx.x; tile < tm.ntiles; tile += gridDim.x) {
     const int b0 = tile * tm.fpc;
     const int nf = min(tm.fpc, P.B - b0);
     __syncthreads();                                      // previous tile fully stored before restaging
-    // ---- cooperative, coalesced load of nf frames; scatter into the per-sequence z layout ----
-    for (int f = 0; f < nf; f++) {
-      const float4* src = (const float4*)(pcm + (size_t)(b0 + f) * P.hop * C);
-      for (int e4 = tid; e4 < words_per_frame / 4; e4 += FW * 32) {
-        const float4 x = __ldg(src + e4);
-        const float xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int e = 4 * e4 + j;
-          const int n = e / C, c = e - n * C;
-          ((float*)(seq_all + (size_t)(f * C + c) * SEQ_CPX))[zword(n)] = xs[j];
-        }
-      }
-    }
+    for (int f = 0; f < nf; f++)
+      scatter_frame<CT, SEQ_CPX * 2>((const uint4*)(pcm + (size_t)(b0 + f) * P.hop * C), (uint32_t*)seq_all, C, f, tid,
+                                     [](int n) { return zword(n); });
     __syncthreads();
     if (w < nf * C) {
       const int f = w / C, c = w - f * C, b = b0 + f;
@@ -136,39 +158,36 @@ __global__ void __launch_bounds__(FW * 32, 2) enc2048_kernel(enc_params P, plan_
       for (int i = 0; i < 32; i++) v[i] = buf[lane + 33 * i];
       __syncwarp();
       fft1024_warp<float, false>(v, buf, lane, tw32);
-      // ---- real-FFT split + DCT post-twiddle: X[k], X[N-k] for k = lane + 32 o ----
+      // ---- pairwise real-FFT split + DCT twiddle: (k, M-k) -> X[k], X[N-k], X[M-k], X[M+k] ----
       const int partner = (32 - lane) & 31;
+      const bool swap_out = (PROFILE == 0) && !P.le;
       float mx = 0.0f;
+      auto emit = [&](int k, float val) {
+        if (PROFILE == 0) {
+          mx = fmaxf(mx, fabsf(val));
+          if (swap_out) val = __uint_as_float(__byte_perm(__float_as_uint(val), 0, 0x0123));
+        }
+        X[k] = val;
+      };
+      auto do_pair = [&](int k, float2 zk, float2 zm, bool first) {      // zm = conj(Z[M-k])
+        const float2 A = cadd(zk, zm), D = csub(zk, zm);
+        const float2 Bv = make_float2(D.y, -D.x);
+        const float2 Pk = cmul(__ldg(cfh + k), A), Qk = cmul(__ldg(dfh + k), Bv);
+        const float2 y = cadd(Pk, Qk), t = csub(Pk, Qk);
+        emit(k, y.x);
+        if (!first) emit(FN - k, -y.y);
+        emit(FM - k, (t.x - t.y) * (float)FRAD_RSQRT2);
+        if (!first) emit(FM + k, (t.x + t.y) * (float)FRAD_RSQRT2);
+      };
 #pragma unroll
-      for (int o = 0; o < 32; o++) {
+      for (int o = 0; o < 16; o++) {
         const float2 snd = (lane == 0) ? v[(32 - o) & 31] : v[31 - o];
         float2 zm;
         zm.x = __shfl_sync(0xffffffffu, snd.x, partner);
-        zm.y = -__shfl_sync(0xffffffffu, snd.y, partner);       // conj(Z[M-k])
-        const float2 zk = v[o];
-        const float2 A = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y + zm.y));
-        const float2 Bv = make_float2(0.5f * (zk.y - zm.y), -0.5f * (zk.x - zm.x));
-        const int k = lane + 32 * o;
-        const float2 ck = __ldg(cf + k), dk = __ldg(df + k);
-        const float2 y = cadd(cmul(ck, A), cmul(dk, Bv));
-        float xk = y.x, xnk = -y.y;
-        if (PROFILE == 0) {
-          mx = fmaxf(mx, fmaxf(fabsf(xk), (k >= 1) ? fabsf(xnk) : 0.0f));
-          if (!P.le) { xk = __uint_as_float(__byte_perm(__float_as_uint(xk), 0, 0x0123)); xnk = __uint_as_float(__byte_perm(__float_as_uint(xnk), 0, 0x0123)); }
-        }
-        X[k] = xk;
-        if (k >= 1) X[FN - k] = xnk;
-        if (o == 0 && lane == 0) {
-          const float2 cm = __ldg(cf + FM), dm = __ldg(df + FM);
-          const float2 y2 = cadd(cmul(cm, cconj(A)), cmul(dm, cconj(Bv)));
-          float xm = y2.x;
-          if (PROFILE == 0) {
-            mx = fmaxf(mx, fabsf(xm));
-            if (!P.le) xm = __uint_as_float(__byte_perm(__float_as_uint(xm), 0, 0x0123));
-          }
-          X[FM] = xm;
-        }
+        zm.y = -__shfl_sync(0xffffffffu, snd.y, partner);
+        do_pair(lane + 32 * o, v[o], zm, (o == 0) && (lane == 0));
       }
+      if (lane == 0) do_pair(FM / 2, v[16], cconj(v[16]), false);          // self-paired bin k = 512
       if (PROFILE == 0) {
         if (P.peak) {
 #pragma unroll
@@ -208,16 +227,34 @@ __global__ void __launch_bounds__(FW * 32, 2) enc2048_kernel(enc_params P, plan_
         __syncwarp();
         // ---- quantise band by band, in place (float -> int32) ----
         int* Q = (int*)X;
+        const float inv_scale = 1.0f / scalef;
         for (int bnd = 0; bnd < FRAD_NBANDS - 1; bnd++) {
           const int lo = tail->lo[bnd], hi = tail->lo[bnd + 1];
           const int n = hi - lo;
           if (n <= 0) continue;
           const double t0 = tail->thr[w][bnd], t1 = tail->thr[w][bnd + 1];
           const double step = (t1 - t0) / (double)n;
-          const float t0f = (float)t0, t1f = (float)t1, nfl = (float)n, invn = 1.0f / (float)n;
+          // ramp as a convex combination (no cancellation), pre-divided by the scale:
+          //   div / scale = (t0 (n - j) + t1 j) / (n scale)
+          const float nfl = (float)n;
+          const float t0s = (float)t0 * inv_scale / nfl, t1s = (float)t1 * inv_scale / nfl;
           for (int k = lo + lane; k < hi; k += 32) {
+            const float x = X[k];
             const float a = (float)(k - lo);
-            Q[k] = quant_one(X[k], a, nfl - a, t0f, t1f, invn, scalef, t0, step, P.scale, force_exact != 0);
+            const float dv = fmaf(a, t1s, (nfl - a) * t0s);
+            float rc, s, v;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(dv));
+            const float y = fabsf(x) * rc;
+            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(y));
+            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(v) : "f"(y * s));
+            const float big = v + 12582912.0f;            // nearest-even integer for v < 2^22
+            const float r = big - 12582912.0f;
+            // error budget of the f32 branch <= 6e-7 relative; stay 1e-6 v away from ties
+            const bool ok = (fabsf(v - r) < 0.5f - fmaf(1.0e-6f, v, 1.0e-7f)) && (v < 2.0e6f) && (dv > 0.0f) && !force_exact;
+            int m = __float_as_int(big) - 0x4B400000;
+            m = (x < 0.0f) ? -m : m;
+            if (!ok) m = quant_exact(x, k - lo, t0, step, P.scale);
+            Q[k] = m;
           }
         }
         for (int k = tail->lo[FRAD_NBANDS - 1] + lane; k < FN; k += 32) Q[k] = 0;
@@ -230,12 +267,7 @@ __global__ void __launch_bounds__(FW * 32, 2) enc2048_kernel(enc_params P, plan_
                                   : (uint4*)(P.q + (size_t)(b0 + f) * words_per_frame);
       for (int e4 = tid; e4 < words_per_frame / 4; e4 += FW * 32) {
         uint32_t o4[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int e = 4 * e4 + j;
-          const int k = e / C, c = e - k * C;
-          o4[j] = ((const uint32_t*)(seq_all + (size_t)(f * C + c) * SEQ_CPX))[k];
-        }
+        gather4<CT, SEQ_CPX * 2>((const uint32_t*)seq_all, C, f, e4, [](int k) { return k; }, [](uint32_t u) { return u; }, o4);
         dst[e4] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
       }
     }
@@ -251,44 +283,35 @@ template <typename T> struct dec_layout {
   static constexpr int WARP_BYTES = SEQ_BYTES + ((sizeof(T) == 8) ? FN * 4 : 0);
 };
 
-struct dec_smem_tail {
-  int lo[FRAD_NBANDS + 1];
-  double thr[FW][FRAD_NBANDS + 1];
-};
-
 template <typename T, int PROFILE, int CT>
 __global__ void __launch_bounds__(FW * 32, (sizeof(T) == 8) ? 1 : 2)
-dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restrict__ tw32) {
+dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restrict__ tw32, const double* __restrict__ dq64) {
   typedef typename vec2<T>::type V;
   typedef dec_layout<T> LY;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  dec_smem_tail* tail = (dec_smem_tail*)(smem_raw + (size_t)FW * LY::WARP_BYTES);
+  smem_tail* tail = (smem_tail*)(smem_raw + (size_t)FW * LY::WARP_BYTES);
   const int C = CT ? CT : P.C;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const tile_map tm = make_tiles(P.B, C);
   const V* ci = (const V*)pl.ci;
   const V* ei = (const V*)pl.ei;
-  if (PROFILE == 1 && tid <= FRAD_NBANDS) { const int e = P.bt->edge[tid]; tail->lo[tid] = (e < FN) ? e : FN; }
+  if (PROFILE == 1) {
+    if (tid <= FRAD_NBANDS) { const int e = P.bt->edge[tid]; tail->lo[tid] = (e < FN) ? e : FN; }
+    if (sizeof(T) == 4) {
+      const float inv = (float)(1.0 / P.scale);
+      for (int i = tid; i < DQ_TAB; i += FW * 32) { const float a = (float)i; tail->dq[i] = a * cbrtf(a) * inv; }
+    }
+  }
   const int words_per_frame = FN * C;
 
   for (int tile = blockIdx.x; tile < tm.ntiles; tile += gridDim.x) {
     const int b0 = tile * tm.fpc;
     const int nf = min(tm.fpc, P.B - b0);
     __syncthreads();
-    // ---- cooperative load of the 32-bit input words (payload or q), de-interleave per sequence ----
     for (int f = 0; f < nf; f++) {
       const uint4* src = (PROFILE == 0) ? (const uint4*)(P.payload + (size_t)(b0 + f) * P.payload_stride)
                                         : (const uint4*)(P.q + (size_t)(b0 + f) * words_per_frame);
-      for (int e4 = tid; e4 < words_per_frame / 4; e4 += FW * 32) {
-        const uint4 x = __ldg(src + e4);
-        const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int e = 4 * e4 + j;
-          const int k = e / C, c = e - k * C;
-          ((uint32_t*)(smem_raw + (size_t)(f * C + c) * LY::WARP_BYTES + LY::RAW_OFF))[k] = xs[j];
-        }
-      }
+      scatter_frame<CT, LY::WARP_BYTES / 4>(src, (uint32_t*)(smem_raw + LY::RAW_OFF), C, f, tid, [](int k) { return k; });
     }
     __syncthreads();
     if (w < nf * C) {
@@ -315,55 +338,74 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
         if (lane <= FRAD_NBANDS) tail->thr[w][lane] = thr;
         __syncwarp();
         const int last = tail->lo[FRAD_NBANDS - 1];
+        const double inv_scale = 1.0 / P.scale;
         for (int bnd = 0; bnd < FRAD_NBANDS - 1; bnd++) {
           const int lo = tail->lo[bnd], hi = tail->lo[bnd + 1];
           const int n = hi - lo;
           if (n <= 0) continue;
           const double t0 = tail->thr[w][bnd], t1 = tail->thr[w][bnd + 1];
           const double step = (t1 - t0) / (double)n;
-          for (int k = lo + lane; k < hi; k += 32) {
-            const int qi = (int)raw[k];
-            if (sizeof(T) == 8) {
-              const double qv = (double)qi;
-              const double coef = copysign(pow(fabs(qv), 1.0 / 0.75), qv) / P.scale;
+          if (sizeof(T) == 8) {
+            for (int k = lo + lane; k < hi; k += 32) {
+              const int qi = (int)raw[k];
+              const int qa = abs(qi);
+              const double mag = (qa < DQ_TAB64) ? __ldg(dq64 + qa) : pow((double)qa, 1.0 / 0.75);
+              const double coef = ((qi < 0) ? -mag : mag) * inv_scale;             // profile1.py:65
               X[k] = (T)(coef * __dadd_rn(__dmul_rn((double)(k - lo), step), t0));
-            } else {
-              const float qa = fabsf((float)qi);
-              const float mag = qa * cbrtf(qa);                         // |q|^(4/3)
-              const float div = (float)(((double)(k - lo)) * step + t0);
-              X[k] = (T)(copysignf(mag, (float)qi) * (float)(1.0 / P.scale) * div);
+            }
+          } else {
+            const float nfl = (float)n;
+            const float t0s = (float)t0 / nfl, t1s = (float)t1 / nfl;
+            for (int k = lo + lane; k < hi; k += 32) {
+              const int qi = (int)raw[k];
+              const int qa = abs(qi);
+              float mag;
+              if (qa < DQ_TAB) mag = tail->dq[qa];
+              else { const float af = (float)qa; mag = af * cbrtf(af) * (float)inv_scale; }
+              const float a = (float)(k - lo);
+              const float dv = fmaf(a, t1s, (nfl - a) * t0s);
+              X[k] = (T)(((qi < 0) ? -mag : mag) * dv);
             }
           }
         }
         for (int k = last + lane; k < FN; k += 32) X[k] = (T)0;
       }
       __syncwarp();
-      // ---- V_k = (X[k] - i X[N-k]) ci[k]; Z[k] = (V_k + conj V_{M-k}) + i e_k (V_k - conj V_{M-k}) ----
-      V v[32];
+      // ---- pairwise pre-processing: R1 = X[k] - i X[N-k], R2 = (X[M-k] + i X[M+k]) e^{-i pi/4},
+      //      S = ci (R1 + R2), G = ei ci (R1 - R2), Z[k] = S + iG, Z[M-k] = conj(S - iG) ----
+      V z[32];
+      V zm_keep[17];
+      const T r2 = (T)FRAD_RSQRT2;
+      auto pre_pair = [&](int k, V& zk, V& zmk) {
+        const T xk = X[k], xnk = (k == 0) ? T(0) : X[FN - k];
+        const T a = X[FM - k], bb = X[FM + k];
+        const V R1 = mk2<T>(xk, -xnk);
+        const V R2 = mk2<T>((a + bb) * r2, (bb - a) * r2);
+        const V cik = __ldg(ci + k);
+        const V S = cmul(cik, cadd(R1, R2));
+        const V G = cmul(__ldg(ei + k), cmul(cik, csub(R1, R2)));
+        zk = mk2<T>(S.x - G.y, S.y + G.x);
+        zmk = mk2<T>(S.x + G.y, -(S.y - G.x));          // conj(S - iG)
+      };
 #pragma unroll
-      for (int o = 0; o < 32; o++) {
-        const int k = lane + 32 * o;
-        const T xk = X[k];
-        const T xnk = (k == 0) ? T(0) : X[FN - k];
-        v[o] = cmul(mk2<T>(xk, -xnk), __ldg(ci + k));
-      }
-      const T xm = X[FM];
-      const V vM = cmul(mk2<T>(xm, -xm), __ldg(ci + FM));
+      for (int o = 0; o < 16; o++) pre_pair(lane + 32 * o, z[o], zm_keep[o]);
+      zm_keep[16] = mk2<T>(T(0), T(0));
+      if (lane == 0) { V dummy; pre_pair(FM / 2, zm_keep[16], dummy); }      // Z[512] (self pair)
       __syncwarp();
       const int partner = (32 - lane) & 31;
-      V z[32];
 #pragma unroll
-      for (int o = 0; o < 32; o++) {
-        const V snd = (lane == 0) ? v[(32 - o) & 31] : v[31 - o];
-        V vm;
-        vm.x = shfl_t<T>(snd.x, partner);
-        vm.y = shfl_t<T>(snd.y, partner);
-        if (o == 0 && lane == 0) vm = vM;
-        vm.y = -vm.y;                                                   // conj(V_{M-k})
-        const int k = lane + 32 * o;
-        const V s = cadd(v[o], vm);
-        const V d = cmul(__ldg(ei + k), csub(v[o], vm));
-        z[o] = mk2<T>(s.x - d.y, s.y + d.x);
+      for (int o = 0; o < 16; o++) {                     // recv[o] = partner's Z[M - k'] = my Z[lane + 32 (31 - o)]
+        V rcv;
+        rcv.x = shfl_t<T>(zm_keep[o].x, partner);
+        rcv.y = shfl_t<T>(zm_keep[o].y, partner);
+        zm_keep[o] = rcv;
+      }
+      // general lanes: z[31 - o] = recv[o]; lane 0 (its own partner): z[32 - o] = recv[o] (o >= 1), z[16] = self pair
+#pragma unroll
+      for (int j = 16; j < 32; j++) {
+        const V g = zm_keep[31 - j];
+        const V l0 = (j == 16) ? zm_keep[16] : zm_keep[32 - j];
+        z[j] = (lane == 0) ? l0 : g;
       }
       fft1024_warp<T, true>(z, buf, lane, tw32);
       // ---- undo the Makhoul reordering into the swizzled time-domain staging ----
@@ -381,20 +423,18 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
     for (int f = 0; f < nf; f++) {
       const size_t fbase = (size_t)(b0 + f) * words_per_frame;
       for (int e4 = tid; e4 < words_per_frame / 4; e4 += FW * 32) {
-        T o4[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int e = 4 * e4 + j;
-          const int n = e / C, c = e - n * C;
-          o4[j] = ((const T*)(smem_raw + (size_t)(f * C + c) * LY::WARP_BYTES))[swz(n)];
-        }
         if (P.pcm_dtype == FRAD_F64) {
+          double o4[4];
+          gather4<CT, LY::WARP_BYTES / (int)sizeof(T)>((const T*)smem_raw, C, f, e4, [](int n) { return swz(n); },
+                                                       [](T x) { return (double)x; }, o4);
           double2* dst = (double2*)((double*)P.pcm + fbase) + 2 * (size_t)e4;
-          dst[0] = make_double2((double)o4[0], (double)o4[1]);
-          dst[1] = make_double2((double)o4[2], (double)o4[3]);
+          dst[0] = make_double2(o4[0], o4[1]);
+          dst[1] = make_double2(o4[2], o4[3]);
         } else {
-          float4* dst = (float4*)((float*)P.pcm + fbase) + e4;
-          *dst = make_float4((float)o4[0], (float)o4[1], (float)o4[2], (float)o4[3]);
+          float o4[4];
+          gather4<CT, LY::WARP_BYTES / (int)sizeof(T)>((const T*)smem_raw, C, f, e4, [](int n) { return swz(n); },
+                                                       [](T x) { return (float)x; }, o4);
+          *((float4*)((float*)P.pcm + fbase) + e4) = make_float4(o4[0], o4[1], o4[2], o4[3]);
         }
       }
     }
@@ -410,6 +450,20 @@ int launch_cfg(frad_ctx* ctx, K kernel, size_t smem, int ntiles, int* grid) {
   long long g = (long long)per_sm * ctx->sm_count;
   *grid = (int)(ntiles < g ? ntiles : g);
   if (*grid < 1) *grid = 1;
+  return FRAD_OK;
+}
+
+int ensure_dq64(frad_ctx* ctx) {
+  if (ctx->dequant_table) return FRAD_OK;
+  std::vector<double> h(DQ_TAB64);
+  for (int i = 0; i < DQ_TAB64; i++) h[i] = pow((double)i, 1.0 / 0.75);     // np.abs(x) ** (1 / 0.75), p1tools.py:44
+  void* d = nullptr;
+  if (cudaMalloc(&d, sizeof(double) * DQ_TAB64) != cudaSuccess ||
+      cudaMemcpy(d, h.data(), sizeof(double) * DQ_TAB64, cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaGetLastError();
+    return frad_fail(ctx, FRAD_E_NOMEM, "dequantiser table upload failed");
+  }
+  ctx->dequant_table = d;
   return FRAD_OK;
 }
 
@@ -447,11 +501,11 @@ bool frad_fast2048_decode_ok(const dec_params& P, int prec) {
 int frad_launch_encode_2048(frad_ctx* ctx, const enc_params& P, const frad_plan* pl, int prec, int force_exact) {
   (void)prec;
   const tile_map tm = make_tiles(P.B, P.C);
-  const size_t smem = (size_t)FW * SEQ_CPX * sizeof(float2) + sizeof(enc_smem_tail);
+  const size_t smem = (size_t)FW * SEQ_CPX * sizeof(float2) + sizeof(smem_tail);
   if (P.profile == 0) {
-    if (P.C == 2) ENC_DISPATCH(0, 2); else if (P.C == 1) ENC_DISPATCH(0, 1); else if (P.C == 8) ENC_DISPATCH(0, 8); else ENC_DISPATCH(0, 0);
+    if (P.C == 2) ENC_DISPATCH(0, 2); else ENC_DISPATCH(0, 0);
   } else {
-    if (P.C == 2) ENC_DISPATCH(1, 2); else if (P.C == 1) ENC_DISPATCH(1, 1); else if (P.C == 8) ENC_DISPATCH(1, 8); else ENC_DISPATCH(1, 0);
+    if (P.C == 2) ENC_DISPATCH(1, 2); else ENC_DISPATCH(1, 0);
   }
   FRAD_LAUNCH_CHECK(ctx);
   return FRAD_OK;
@@ -461,20 +515,22 @@ int frad_launch_encode_2048(frad_ctx* ctx, const enc_params& P, const frad_plan*
   do {                                                                                                   \
     auto k = dec2048_kernel<TT, PROF, CT>;                                                               \
     int grid;                                                                                            \
-    const size_t smem = (size_t)FW * dec_layout<TT>::WARP_BYTES + sizeof(dec_smem_tail);                 \
+    const size_t smem = (size_t)FW * dec_layout<TT>::WARP_BYTES + sizeof(smem_tail);                     \
     int rc = launch_cfg(ctx, k, smem, tm.ntiles, &grid);                                                 \
     if (rc) return rc;                                                                                   \
-    k<<<grid, FW * 32, smem, ctx->stream>>>(P, plan_view(pl), (const typename vec2<TT>::type*)pl->tw32); \
+    k<<<grid, FW * 32, smem, ctx->stream>>>(P, plan_view(pl), (const typename vec2<TT>::type*)pl->tw32,  \
+                                            (const double*)ctx->dequant_table);                          \
   } while (0)
 
 #define DEC_DISPATCH_C(TT, PROF)                                                                       \
   do {                                                                                                 \
-    if (P.C == 2) DEC_DISPATCH(TT, PROF, 2); else if (P.C == 1) DEC_DISPATCH(TT, PROF, 1);             \
-    else if (P.C == 8) DEC_DISPATCH(TT, PROF, 8); else DEC_DISPATCH(TT, PROF, 0);                      \
+    if (P.C == 2) DEC_DISPATCH(TT, PROF, 2); else DEC_DISPATCH(TT, PROF, 0);                           \
   } while (0)
 
 int frad_launch_decode_2048(frad_ctx* ctx, const dec_params& P, const frad_plan* pl, int prec) {
   const tile_map tm = make_tiles(P.B, P.C);
+  int rc = ensure_dq64(ctx);
+  if (rc) return rc;
   if (prec == FRAD_PREC_F32) {
     if (P.profile == 0) DEC_DISPATCH_C(float, 0); else DEC_DISPATCH_C(float, 1);
   } else {

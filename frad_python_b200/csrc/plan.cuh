@@ -19,6 +19,7 @@ struct frad_plan {
   int npass = 0;
   int radix[FRAD_MAX_RADIX_PASSES] = {};
   void *tw = nullptr, *cf = nullptr, *df = nullptr, *ci = nullptr, *ei = nullptr;
+  void *cfh = nullptr, *dfh = nullptr;  // N == 2048 only: cf / 2, df / 2 (pairwise post-processing)
   void* tw32 = nullptr;  // N == 2048 only: [i][lane] = exp(-2 pi i * i * lane / 1024) for the 32 x 32 warp FFT
   double* ct = nullptr;
 };
@@ -27,7 +28,7 @@ struct frad_plan {
 struct plan_dev {
   int N, M, npass;
   int radix[FRAD_MAX_RADIX_PASSES];
-  const void *tw, *cf, *df, *ci, *ei;
+  const void *tw, *cf, *df, *ci, *ei, *cfh, *dfh;
   const double* ct;
 };
 
@@ -35,7 +36,7 @@ static inline plan_dev plan_view(const frad_plan* p) {
   plan_dev d;
   d.N = p->N; d.M = p->M; d.npass = p->npass;
   for (int i = 0; i < FRAD_MAX_RADIX_PASSES; i++) d.radix[i] = p->radix[i];
-  d.tw = p->tw; d.cf = p->cf; d.df = p->df; d.ci = p->ci; d.ei = p->ei; d.ct = p->ct;
+  d.tw = p->tw; d.cf = p->cf; d.df = p->df; d.ci = p->ci; d.ei = p->ei; d.ct = p->ct; d.cfh = p->cfh; d.dfh = p->dfh;
   return d;
 }
 

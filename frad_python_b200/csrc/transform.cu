@@ -60,7 +60,7 @@ static void unit_root(long long num, long long den, long double* c, long double*
 
 void frad_plan_free(frad_plan* p) {
   if (!p) return;
-  cudaFree(p->tw); cudaFree(p->cf); cudaFree(p->df); cudaFree(p->ci); cudaFree(p->ei); cudaFree(p->ct); cudaFree(p->tw32);
+  cudaFree(p->tw); cudaFree(p->cf); cudaFree(p->df); cudaFree(p->ci); cudaFree(p->ei); cudaFree(p->ct); cudaFree(p->tw32); cudaFree(p->cfh); cudaFree(p->dfh);
   delete p;
 }
 
@@ -79,6 +79,12 @@ static bool build_tables(frad_ctx* ctx, frad_plan* p) {
   }
   p->cf = upload_cpx<T>(ctx, re, im);
   p->df = upload_cpx<T>(ctx, re2, im2);
+  if (N == 2048) {
+    for (int k = 0; k <= M; k++) { re[k] /= 2; im[k] /= 2; re2[k] /= 2; im2[k] /= 2; }
+    p->cfh = upload_cpx<T>(ctx, re, im);
+    p->dfh = upload_cpx<T>(ctx, re2, im2);
+    if (!p->cfh || !p->dfh) return false;
+  }
   for (int k = 0; k <= M; k++) {
     unit_root((long long)k, 2LL * N, &re[k], &im[k]);           // exp(+i pi k / 2N)
     unit_root(4LL * k, 2LL * N, &re2[k], &im2[k]);              // exp(+2 pi i k / N)

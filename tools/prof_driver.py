@@ -1,0 +1,35 @@
+"""Small device-resident driver for ncu captures: runs the profile-1 encode and decode kernels
+(N=2048, 48 kHz stereo) a few times.  Usage: python tools/prof_driver.py [frames] [reps] [mode]"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from frad_python_b200 import Context, _abi  # noqa: E402
+from oracle.frad_oracle import synth_pcm  # noqa: E402
+
+frames = int(sys.argv[1]) if len(sys.argv) > 1 else 3000
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+mode = sys.argv[3] if len(sys.argv) > 3 else "p1"
+N, HOP, CH = 2048, 1920, 2
+L = _abi.lib()
+ctx = Context(0)
+tile = synth_pcm(2.0, 48000, CH, 1)
+need = (frames - 1) * HOP + N
+pcm = np.ascontiguousarray(np.tile(tile, (-(-need // len(tile)), 1))[:need])
+d_pcm = ctx.dev(pcm.nbytes); ctx.h2d(d_pcm, pcm)
+d_q = ctx.dev(frames * N * CH * 4); d_tq = ctx.dev(frames * 27 * CH * 4)
+d_out = ctx.dev(frames * N * CH * 8)
+d_pay = ctx.dev(frames * N * CH * 4); d_peak = ctx.dev(frames * 8)
+for _ in range(reps):
+    if mode == "p1":
+        ctx.check(L.frad_p1_encode_dev(ctx.handle, d_pcm.ptr, _abi.F32, HOP, frames, N, CH, 16, 48000, 0.5526315789473684, 0, d_q.ptr, d_tq.ptr, None))
+        ctx.check(L.frad_p1_decode_dev(ctx.handle, d_q.ptr, d_tq.ptr, None, frames, N, CH, 16, 48000, _abi.PREC_F64, d_out.ptr, _abi.F64))
+        ctx.check(L.frad_p1_decode_dev(ctx.handle, d_q.ptr, d_tq.ptr, None, frames, N, CH, 16, 48000, _abi.PREC_F32, d_out.ptr, _abi.F64))
+    else:
+        ctx.check(L.frad_p0_encode_dev(ctx.handle, d_pcm.ptr, _abi.F32, N, frames, N, CH, 32, 0, 0, d_pay.ptr, N * CH * 4, d_peak.ptr))
+        ctx.check(L.frad_p0_decode_dev(ctx.handle, d_pay.ptr, N * CH * 4, frames, N, CH, 32, 0, _abi.PREC_F64, d_out.ptr, _abi.F64))
+        ctx.check(L.frad_p0_decode_dev(ctx.handle, d_pay.ptr, N * CH * 4, frames, N, CH, 32, 0, _abi.PREC_F32, d_out.ptr, _abi.F64))
+ctx.sync()
+print("ok", ctx.launches)
