@@ -11,7 +11,8 @@ import threading
 
 import numpy as np
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libfradb200.so")
+_LIB_PATH = os.environ.get("FRADB200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib",
+                                                            "libfradb200.so")
 
 F32, F64, S8, S16, S32, S64, U8, U16, U32, U64, F16 = range(11)
 PREC_REF, PREC_F32, PREC_F64 = 0, 1, 2

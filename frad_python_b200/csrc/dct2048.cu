@@ -20,7 +20,13 @@
 
 namespace {
 
-constexpr int FN = 2048, FM = 1024, FW = 8;          // frame, half, warps per CTA
+#ifndef FRAD_FW
+#define FRAD_FW 4
+#endif
+#ifndef FRAD_MINB
+#define FRAD_MINB 4
+#endif
+constexpr int FN = 2048, FM = 1024, FW = FRAD_FW;          // frame, half, warps per CTA
 constexpr int SEQ_CPX = 1056;                        // padded complex slots per warp buffer
 constexpr int DQ_TAB = 1024;                         // f32 dequantiser table entries (|q| < DQ_TAB)
 constexpr int DQ_TAB64 = 4096;                       // f64 table (global memory)
@@ -62,8 +68,22 @@ __host__ __device__ inline tile_map make_tiles(int B, int C) {
 struct smem_tail {
   int lo[FRAD_NBANDS + 1];
   double thr[FW][FRAD_NBANDS + 1];
-  float dq[DQ_TAB];                                   // decode only: |q|^(4/3) / scale
+  float4 bp[FW][FRAD_NBANDS + 1];                     // per band: ramp end points (pre-scaled), lo, hi as floats
+  float dq[DQ_TAB];                                   // decode: |q|^(4/3) / scale
+  uint8_t bidx[FN];                                   // band index of every bin (FRAD_NBANDS - 1 = "past the ramps")
 };
+
+// band index table shared by all warps of the CTA (same N and sample rate)
+__device__ __forceinline__ void build_bidx(smem_tail* tail, const band_table* bt, int tid) {
+  if (tid <= FRAD_NBANDS) { const int e = bt->edge[tid]; tail->lo[tid] = (e < FN) ? e : FN; }
+  __syncthreads();
+  for (int k = tid; k < FN; k += FW * 32) {
+    int b = 0;
+#pragma unroll 1
+    for (int s = 16; s > 0; s >>= 1) { if (b + s <= FRAD_NBANDS - 1 && tail->lo[b + s] <= k) b += s; }
+    tail->bidx[k] = (uint8_t)b;                       // largest b <= 26 with lo[b] <= k
+  }
+}
 
 // ---- cooperative staging helpers ----------------------------------------------------------------
 // Frame words (32-bit) are interleaved [i][c]; word e = i*C + c goes to / comes from per-sequence
@@ -127,7 +147,7 @@ __device__ __noinline__ int quant_exact(float x, int j, double t0, double step, 
 }
 
 template <int PROFILE, int CT>
-__global__ void __launch_bounds__(FW * 32, 2) enc2048_kernel(enc_params P, plan_dev pl, const float2* __restrict__ tw32,
+__global__ void __launch_bounds__(FW * 32, FRAD_MINB) enc2048_kernel(enc_params P, plan_dev pl, const float2* __restrict__ tw32,
                                                              int force_exact) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* seq_all = (float2*)smem_raw;
@@ -138,7 +158,7 @@ __global__ void __launch_bounds__(FW * 32, 2) enc2048_kernel(enc_params P, plan_
   const float* pcm = (const float*)P.pcm;
   const float2* cfh = (const float2*)pl.cfh;
   const float2* dfh = (const float2*)pl.dfh;
-  if (PROFILE == 1 && tid <= FRAD_NBANDS) { const int e = P.bt->edge[tid]; tail->lo[tid] = (e < FN) ? e : FN; }
+  if (PROFILE == 1) build_bidx(tail, P.bt, tid);
   const int words_per_frame = FN * C;
 
   for (int tile = blockIdx.x; tile < tm.ntiles; tile += gridDim.x) {
@@ -196,19 +216,18 @@ __global__ void __launch_bounds__(FW * 32, 2) enc2048_kernel(enc_params P, plan_
         }
       } else {
         __syncwarp();
-        // ---- band energies of the scaled spectrum: per-lane partials, one transposed reduction ----
+        // ---- band energies of the scaled spectrum: strided partial sums + warp reduction per band ----
         const float scalef = (float)P.scale;
-        float part[32];
-#pragma unroll
-        for (int bnd = 0; bnd < 32; bnd++) {
+        float tot = 0.0f;
+#pragma unroll 1
+        for (int bnd = 0; bnd < FRAD_NBANDS; bnd++) {
+          const int hi = tail->lo[bnd + 1];
           float s = 0.0f;
-          if (bnd < FRAD_NBANDS) {
-            const int hi = tail->lo[bnd + 1];
-            for (int k = tail->lo[bnd] + lane; k < hi; k += 32) { const float xv = X[k] * scalef; s = fmaf(xv, xv, s); }
-          }
-          part[bnd] = s;
+          for (int k = tail->lo[bnd] + lane; k < hi; k += 32) { const float xv = X[k] * scalef; s = fmaf(xv, xv, s); }
+#pragma unroll
+          for (int sh = 16; sh > 0; sh >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sh);
+          if (lane == bnd) tot = s;
         }
-        const float tot = transpose_reduce32(part, lane);
         int cnt = 1;
         if (lane < FRAD_NBANDS) cnt = tail->lo[lane + 1] - tail->lo[lane];
         const unsigned empty = __ballot_sync(0xffffffffu, cnt <= 0);
@@ -224,40 +243,48 @@ __global__ void __launch_bounds__(FW * 32, 2) enc2048_kernel(enc_params P, plan_
           const double d = (vv > 0.0) ? pow(vv, 1.0 / 0.75) : 0.0;
           P.tq[((size_t)b * FRAD_NBANDS + lane) * C + c] = sat_i32(rint(d));
         }
-        __syncwarp();
-        // ---- quantise band by band, in place (float -> int32) ----
-        int* Q = (int*)X;
-        const float inv_scale = 1.0f / scalef;
-        for (int bnd = 0; bnd < FRAD_NBANDS - 1; bnd++) {
-          const int lo = tail->lo[bnd], hi = tail->lo[bnd + 1];
-          const int n = hi - lo;
-          if (n <= 0) continue;
-          const double t0 = tail->thr[w][bnd], t1 = tail->thr[w][bnd + 1];
-          const double step = (t1 - t0) / (double)n;
-          // ramp as a convex combination (no cancellation), pre-divided by the scale:
-          //   div / scale = (t0 (n - j) + t1 j) / (n scale)
-          const float nfl = (float)n;
-          const float t0s = (float)t0 * inv_scale / nfl, t1s = (float)t1 * inv_scale / nfl;
-          for (int k = lo + lane; k < hi; k += 32) {
-            const float x = X[k];
-            const float a = (float)(k - lo);
-            const float dv = fmaf(a, t1s, (nfl - a) * t0s);
-            float rc, s, v;
-            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(dv));
-            const float y = fabsf(x) * rc;
-            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(y));
-            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(v) : "f"(y * s));
-            const float big = v + 12582912.0f;            // nearest-even integer for v < 2^22
-            const float r = big - 12582912.0f;
-            // error budget of the f32 branch <= 6e-7 relative; stay 1e-6 v away from ties
-            const bool ok = (fabsf(v - r) < 0.5f - fmaf(1.0e-6f, v, 1.0e-7f)) && (v < 2.0e6f) && (dv > 0.0f) && !force_exact;
-            int m = __float_as_int(big) - 0x4B400000;
-            m = (x < 0.0f) ? -m : m;
-            if (!ok) m = quant_exact(x, k - lo, t0, step, P.scale);
-            Q[k] = m;
+        // per-band ramp parameters, one band per lane: the divisor over the scale as a convex combination
+        //   div / scale = t0s (hi - k) + t1s (k - lo),  t0s = thr[b] / (n scale), t1s = thr[b+1] / (n scale)
+        {
+          const double thr_next = __shfl_down_sync(0xffffffffu, thr, 1);
+          if (lane <= FRAD_NBANDS) {
+            float4 bpv = make_float4(1.0f, 1.0f, 0.0f, 2.0f * FN);      // harmless positive divisor for unused bands
+            if (lane < FRAD_NBANDS - 1 && cnt > 0) {
+              const double ns = (double)cnt * P.scale;
+              bpv = make_float4((float)(thr / ns), (float)(thr_next / ns), (float)tail->lo[lane], (float)tail->lo[lane + 1]);
+            }
+            tail->bp[w][lane] = bpv;
           }
         }
-        for (int k = tail->lo[FRAD_NBANDS - 1] + lane; k < FN; k += 32) Q[k] = 0;
+        __syncwarp();
+        // ---- quantise: one flat pass over the sequence, in place (float -> int32) ----
+        int* Q = (int*)X;
+        float kf = (float)lane;
+#pragma unroll 4
+        for (int k = lane; k < FN; k += 32, kf += 32.0f) {
+          const float x = X[k];
+          const int bnd = tail->bidx[k];
+          const float4 bpv = tail->bp[w][bnd];
+          const float dv = fmaf(kf - bpv.z, bpv.y, (bpv.w - kf) * bpv.x);
+          float rc, s, v;
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(dv));
+          const float y = fabsf(x) * rc;
+          asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(y));
+          asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(v) : "f"(y * s));
+          const float big = v + 12582912.0f;              // nearest-even integer for v < 2^22
+          const float r = big - 12582912.0f;
+          // error budget of the f32 branch <= 6e-7 relative; stay 1e-6 v away from ties
+          const bool ok = (fabsf(v - r) < 0.5f - fmaf(1.0e-6f, v, 1.0e-7f)) && (v < 2.0e6f) && (dv > 0.0f) && !force_exact;
+          int m = __float_as_int(big) - 0x4B400000;
+          m = (x < 0.0f) ? -m : m;
+          if (bnd == FRAD_NBANDS - 1) m = 0;              // bins past the last ramp (p1tools.py:37)
+          else if (!ok) {
+            const int lo = tail->lo[bnd], n = tail->lo[bnd + 1] - lo;
+            const double t0 = tail->thr[w][bnd], t1 = tail->thr[w][bnd + 1];
+            m = quant_exact(x, k - lo, t0, (t1 - t0) / (double)n, P.scale);
+          }
+          Q[k] = m;
+        }
       }
     }
     __syncthreads();
@@ -284,7 +311,7 @@ template <typename T> struct dec_layout {
 };
 
 template <typename T, int PROFILE, int CT>
-__global__ void __launch_bounds__(FW * 32, (sizeof(T) == 8) ? 1 : 2)
+__global__ void __launch_bounds__(FW * 32, (sizeof(T) == 8) ? FRAD_MINB / 2 : FRAD_MINB)
 dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restrict__ tw32, const double* __restrict__ dq64) {
   typedef typename vec2<T>::type V;
   typedef dec_layout<T> LY;

@@ -25,6 +25,19 @@ template <bool INV, typename V> __device__ __forceinline__ V mul_mi(V a) {
   return r;
 }
 
+// ---- sm_100 packed FP32x2 forms (FADD2 / FMUL2 / FFMA2): one issue slot per complex add, two per
+// complex multiply; the (-y, x) swap-negate and scalar broadcasts are operand modifiers in SASS ----
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 w) {
+  return __ffma2_rn(make_float2(-a.y, a.x), make_float2(w.y, w.y), __fmul2_rn(a, make_float2(w.x, w.x)));
+}
+// a * w.x + (-a.y, a.x) * w.y with w given as two scalars (compile-time twiddles)
+__device__ __forceinline__ float2 cmul_cs(float2 a, float c, float s) {
+  return __ffma2_rn(make_float2(-a.y, a.x), make_float2(s, s), __fmul2_rn(a, make_float2(c, c)));
+}
+__device__ __forceinline__ float2 cscale(float2 a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
+
 // ---- small DFTs, natural order in place; forward kernel exp(-2 pi i pq/R), inverse conjugated ----
 template <typename T, int R, bool INV> struct small_dft;
 

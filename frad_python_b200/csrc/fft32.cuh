@@ -28,6 +28,15 @@ __device__ __forceinline__ double w32_sin(int t) {   // sin(2 pi t / 32) (positi
   return s[t & 31];
 }
 
+// v * (c + i s)
+__device__ __forceinline__ float2 crot(float2 v, float c, float s) { return cmul_cs(v, c, s); }
+__device__ __forceinline__ double2 crot(double2 v, double c, double s) {
+  double2 r;
+  r.x = v.x * c - v.y * s;
+  r.y = v.x * s + v.y * c;
+  return r;
+}
+
 // v *= exp(-+ 2 pi i t / 32), t compile-time after unrolling
 template <typename T, bool INV, typename V>
 __device__ __forceinline__ V mul_w32(V v, int t) {
@@ -38,10 +47,7 @@ __device__ __forceinline__ V mul_w32(V v, int t) {
   if (t == 24) return mul_mi<!INV>(v);
   const T c = (T)w32_cos(t);
   const T s = (T)(INV ? w32_sin(t) : -w32_sin(t));
-  V r;
-  r.x = v.x * c - v.y * s;
-  r.y = v.x * s + v.y * c;
-  return r;
+  return crot(v, c, s);
 }
 
 template <typename T, bool INV, typename V>
