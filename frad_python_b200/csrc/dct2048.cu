@@ -258,32 +258,56 @@ __global__ void __launch_bounds__(FW * 32, FRAD_MINB) enc2048_kernel(enc_params 
         }
         __syncwarp();
         // ---- quantise: one flat pass over the sequence, in place (float -> int32) ----
+        // Eight coefficients per lane are evaluated branch-free (independent dependency chains for the
+        // MUFU / LDS latencies); the rare ones that sit next to a rounding tie are redone exactly afterwards.
         int* Q = (int*)X;
-        float kf = (float)lane;
-#pragma unroll 4
-        for (int k = lane; k < FN; k += 32, kf += 32.0f) {
-          const float x = X[k];
-          const int bnd = tail->bidx[k];
-          const float4 bpv = tail->bp[w][bnd];
-          const float dv = fmaf(kf - bpv.z, bpv.y, (bpv.w - kf) * bpv.x);
-          float rc, s, v;
-          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(dv));
-          const float y = fabsf(x) * rc;
-          asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(y));
-          asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(v) : "f"(y * s));
-          const float big = v + 12582912.0f;              // nearest-even integer for v < 2^22
-          const float r = big - 12582912.0f;
-          // error budget of the f32 branch <= 6e-7 relative; stay 1e-6 v away from ties
-          const bool ok = (fabsf(v - r) < 0.5f - fmaf(1.0e-6f, v, 1.0e-7f)) && (v < 2.0e6f) && (dv > 0.0f) && !force_exact;
-          int m = __float_as_int(big) - 0x4B400000;
-          m = (x < 0.0f) ? -m : m;
-          if (bnd == FRAD_NBANDS - 1) m = 0;              // bins past the last ramp (p1tools.py:37)
-          else if (!ok) {
-            const int lo = tail->lo[bnd], n = tail->lo[bnd + 1] - lo;
-            const double t0 = tail->thr[w][bnd], t1 = tail->thr[w][bnd + 1];
-            m = quant_exact(x, k - lo, t0, (t1 - t0) / (double)n, P.scale);
+        const float4* bpw = tail->bp[w];
+#pragma unroll 1
+        for (int kbase = lane; kbase < FN; kbase += 256) {
+          float xs[8];
+          int ms[8];
+          unsigned amb = 0;
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            const int k = kbase + 32 * u;
+            const float kf = (float)k;
+            const float x = X[k];
+            const int bnd = tail->bidx[k];
+            const float4 bpv = bpw[bnd];
+            const float dv = fmaf(kf - bpv.z, bpv.y, (bpv.w - kf) * bpv.x);
+            float rc, s, v;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(dv));
+            const float y = fabsf(x) * rc;
+            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(y));
+            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(v) : "f"(y * s));
+            const float big = v + 12582912.0f;            // nearest-even integer for v < 2^22
+            const float r = big - 12582912.0f;
+            // error budget of the f32 branch <= 6e-7 relative; stay 1e-6 v away from ties
+            const bool ok = (fabsf(v - r) < 0.5f - fmaf(1.0e-6f, v, 1.0e-7f)) && (v < 2.0e6f) && (dv > 0.0f);
+            int m = __float_as_int(big) - 0x4B400000;
+            m = (x < 0.0f) ? -m : m;
+            const bool past = (bnd == FRAD_NBANDS - 1);   // bins past the last ramp stay 0 (p1tools.py:37)
+            ms[u] = past ? 0 : m;
+            xs[u] = x;
+            amb |= (ok || past) ? 0u : (1u << u);
           }
-          Q[k] = m;
+          if (force_exact) amb = 0xffu;
+#pragma unroll
+          for (int u = 0; u < 8; u++) Q[kbase + 32 * u] = ms[u];
+          if (amb) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+              if ((amb >> u) & 1u) {
+                const int k = kbase + 32 * u;
+                const int bnd = tail->bidx[k];
+                if (bnd != FRAD_NBANDS - 1) {
+                  const int lo = tail->lo[bnd], n = tail->lo[bnd + 1] - lo;
+                  const double t0 = tail->thr[w][bnd], t1 = tail->thr[w][bnd + 1];
+                  Q[k] = quant_exact(xs[u], k - lo, t0, (t1 - t0) / (double)n, P.scale);
+                }
+              }
+            }
+          }
         }
       }
     }

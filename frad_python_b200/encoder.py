@@ -1,0 +1,294 @@
+"""Batched streaming encoder -- same public surface as libfrad.Encoder (libfrad/encoder.py).
+
+``process`` cuts *every* complete frame out of the byte buffer, runs the transform / quantiser / ECC /
+CRC for all of them in batched GPU calls, then frames them with ASFH headers exactly like the
+reference's per-frame loop (encoder.py:53-107).  Flush semantics (ragged last frame, force-flush
+headers, encoder.py:89-91,105) follow the reference frame by frame.
+"""
+import sys
+
+import numpy as np
+
+from . import fourier
+from ._abi import PREC_REF, default_context
+from .backend import ff_format_to_numpy_type, to_f64
+from .fourier import AVAILABLE, BIT_DEPTHS, SEGMAX
+from .fourier.profiles import COMPACT, compact
+from .tools.asfh import ASFH
+
+
+class EncodeResult:
+    def __init__(self, buf: bytes, samples: int):
+        self.buf = buf
+        self.samples = samples
+
+
+class Encoder:
+    def __init__(self, profile: int, srate: int, channels: int, bit_depth: int, frame_size: int, pcm_format: str,
+                 ctx=None, precision: int = PREC_REF):
+        if profile not in AVAILABLE:
+            print(f"Invalid profile! Available: {AVAILABLE}", file=sys.stderr)
+            raise SystemExit(1)
+        self.ctx = ctx or default_context()
+        self.precision = precision
+        self.asfh = ASFH()
+        self.buffer = b""
+        self.bit_depth = 0
+        self.channels = 0
+        self.fsize = 0
+        self.srate = 0
+        self.overlap_fragment = np.array([])
+        self.pcm_format = ff_format_to_numpy_type(pcm_format)
+        self.loss_level = 0.5
+        self.init = False
+        self.set_profile(profile, srate, channels, bit_depth, frame_size)
+
+    # ------------------------------------------------------------------------------------------
+    def _frame_len(self) -> int:
+        return compact.get_samples_min_ge(self.fsize) if self.asfh.profile in COMPACT else self.fsize
+
+    def _overlap_len(self, n: int) -> int:
+        """Samples carried into the next frame (encoder.py:46-50)."""
+        if self.asfh.profile in COMPACT and self.asfh.overlap_ratio > 1:
+            return n - n * (self.asfh.overlap_ratio - 1) // self.asfh.overlap_ratio
+        return 0
+
+    def _float_domain(self, raw: np.ndarray, keep_native_ints: bool = False) -> np.ndarray:
+        """What the reference's ``to_f64`` yields for this PCM format (values), in a device-readable dtype:
+        floats keep their precision (byte-swapped to little endian if needed), native-order integers are
+        scaled to float64 -- or left raw for the device to scale when ``keep_native_ints`` -- and
+        big-endian integers stay unscaled (the reference's pcmformat.py:34-47 falls through for them)."""
+        dt = raw.dtype
+        if dt.kind == "f":
+            return raw.astype(dt.newbyteorder("<")) if dt.byteorder == ">" else raw
+        if dt.byteorder == ">":
+            return raw.astype(np.float64)
+        return raw if keep_native_ints else to_f64(raw, dt)
+
+    def _emit(self, payloads, depth_idx, channels, srate, fsizes, crcs, flush_each: bool) -> bytes:
+        """ECC + header for a list of frames sharing the current ASFH settings."""
+        a = self.asfh
+        if a.ecc and a.ecc_codesize > 0:
+            payloads = self.ctx.rs_encode_many(payloads, a.ecc_dsize, a.ecc_codesize)
+            crcs = None
+        if crcs is None:
+            if a.profile in COMPACT:
+                crcs = self.ctx.crc_many(payloads, False) if a.ecc else [None] * len(payloads)
+            else:
+                crcs = self.ctx.crc_many(payloads, True)
+        out = []
+        for i, pay in enumerate(payloads):
+            a.bit_depth_index = depth_idx[i] if isinstance(depth_idx, (list, tuple)) else depth_idx
+            a.channels, a.fsize, a.srate = channels, fsizes[i], srate
+            out.append(a.write(pay, crcs[i]))
+            if flush_each:
+                out.append(a.force_flush())
+        return b"".join(out)
+
+    def _encode_frames(self, pcm: np.ndarray, nframes: int, n: int, hop: int, fsizes, flush_each=False) -> bytes:
+        a = self.asfh
+        if a.profile == 0:
+            pays, depth, crc = fourier.profile0.analogue_batch(pcm, nframes, n, hop, self.bit_depth, a.endian, self.ctx,
+                                                               self.precision, want_crc=not a.ecc)
+            return self._emit(pays, depth, pcm.shape[1], self.srate, fsizes, None if a.ecc else crc, flush_each)
+        mod = fourier.profile1 if a.profile == 1 else fourier.profile2
+        pays, depth, ch, sr = mod.analogue_batch(pcm, nframes, n, hop, self.bit_depth, self.srate, self.loss_level,
+                                                 self.ctx, self.precision)
+        return self._emit(pays, depth, ch, sr, fsizes, None, flush_each)
+
+    def inner(self, stream: bytes, flush: bool) -> EncodeResult:
+        self.buffer += stream
+        ret, samples = [], 0
+        if not self.init:
+            return EncodeResult(b"", 0)
+        bps = self.pcm_format.itemsize * self.channels
+
+        # ---- steady state: every complete frame in one batch --------------------------------
+        n = self._frame_len()
+        olap = self._overlap_len(n)
+        frag = self.overlap_fragment
+        frag_len = len(frag) if frag.ndim == 2 else 0
+        if n > 0 and frag_len in (0, olap) and bps > 0:
+            hop = n - olap
+            avail = len(self.buffer) // bps
+            first_need = n - frag_len
+            if avail >= first_need:
+                nframes = 1 + (avail - first_need) // hop
+                used = first_need + (nframes - 1) * hop
+                raw = np.frombuffer(self.buffer[:used * bps], self.pcm_format).reshape(-1, self.channels)
+                self.buffer = self.buffer[used * bps:]
+                pcm = self._float_domain(raw, keep_native_ints=(frag_len == 0 and olap == 0))
+                if frag_len:
+                    pcm = np.concatenate((frag.astype(pcm.dtype, copy=False), pcm), axis=0)
+                ret.append(self._encode_frames(pcm, nframes, n, hop, [n] * nframes))
+                samples += used
+                if olap:
+                    self.overlap_fragment = np.array(pcm[nframes * hop:(nframes - 1) * hop + n])
+                else:
+                    self.overlap_fragment = np.array([])
+
+        # ---- remainder: the reference's own per-frame state machine (flush / odd states) -----------
+        while True:
+            frag = self.overlap_fragment
+            overlap_len = len(frag) if frag.ndim == 2 else 0
+            rlen = self._frame_len()
+            overlap_read = min(overlap_len, rlen)
+            rlen -= overlap_read
+            read_bytes = rlen * bps
+            if len(self.buffer) < read_bytes and not flush:
+                break
+            pcm_bytes, self.buffer = self.buffer[:read_bytes], self.buffer[read_bytes:]
+            pcm_bytes = pcm_bytes[:len(pcm_bytes) // bps * bps] if bps else b""
+            frame = np.frombuffer(pcm_bytes, self.pcm_format).reshape(-1, self.channels)
+            frame = self._float_domain(frame)
+            samples_in_frame = len(frame)
+            if overlap_len:
+                frame = np.concatenate((frag[:overlap_read].astype(frame.dtype, copy=False), frame), axis=0)
+                frag = frag[overlap_read:]
+            nxt = np.array([])
+            if (not flush and self.asfh.profile in COMPACT and self.asfh.overlap_ratio > 1 and len(frag) < 1):
+                cut = len(frame) * (self.asfh.overlap_ratio - 1) // self.asfh.overlap_ratio
+                nxt = frame[cut:]
+            self.overlap_fragment = nxt
+            if frame.size == 0 and self.overlap_fragment.ndim != 2:
+                ret.append(self.asfh.force_flush())
+                break
+            samples += samples_in_frame
+            fsize = len(frame)
+            if self.asfh.profile in COMPACT:
+                nn = compact.get_samples_min_ge(fsize)
+                padded = np.pad(frame, ((0, nn - fsize), (0, 0))) if nn != fsize else frame
+                ret.append(self._encode_frames(np.ascontiguousarray(padded), 1, nn, nn, [fsize], flush_each=flush))
+            else:
+                ret.append(self._encode_frames(np.ascontiguousarray(frame), 1, fsize, fsize, [fsize], flush_each=flush))
+        return EncodeResult(b"".join(ret), samples)
+
+    def process(self, stream: bytes) -> EncodeResult:
+        return self.inner(stream, False)
+
+    def flush(self) -> EncodeResult:
+        if self.init:
+            return self.inner(b"", True)
+        return EncodeResult(b"", 0)
+
+    # ---- validators / getters / setters (encoder.py:115-215) -----------------------------------------
+    @staticmethod
+    def verify_profile(profile: int):
+        if profile not in AVAILABLE:
+            return f"Invalid profile! Available: {AVAILABLE}"
+        return None
+
+    @staticmethod
+    def verify_srate(profile: int, srate: int):
+        if srate == 0:
+            return "Sample rate cannot be zero"
+        if profile in COMPACT and compact.get_valid_srate(srate) != srate:
+            return f"Invalid sample rate! Valid rates for profile {profile}: {compact.SRATES}"
+        return None
+
+    @staticmethod
+    def verify_channels(profile: int, channels: int):
+        if channels == 0:
+            return "Channel count cannot be zero"
+        return None
+
+    @staticmethod
+    def verify_bit_depth(profile: int, bit_depth: int):
+        if bit_depth == 0:
+            return "Bit depth cannot be zero"
+        if bit_depth not in BIT_DEPTHS[profile]:
+            return f"Invalid bit depth! Valid depths for profile {profile}: {[d for d in BIT_DEPTHS[profile] if d != 0]}"
+        return None
+
+    @staticmethod
+    def verify_frame_size(profile: int, frame_size: int):
+        if frame_size == 0:
+            return "Frame size cannot be zero"
+        if frame_size > SEGMAX[profile]:
+            return f"Samples per frame cannot exceed {SEGMAX[profile]}"
+        return None
+
+    def get_profile(self) -> int:
+        return self.asfh.profile
+
+    def set_profile(self, profile: int, srate: int, channels: int, bit_depth: int, frame_size: int):
+        for err in (self.verify_profile(profile), ):
+            if err is not None:
+                return err
+        for err in (self.verify_srate(profile, srate), self.verify_channels(profile, channels),
+                    self.verify_bit_depth(profile, bit_depth), self.verify_frame_size(profile, frame_size)):
+            if err is not None:
+                return err
+        res = EncodeResult(b"", 0)
+        if (self.channels != 0 and self.channels != channels) or (self.srate != 0 and self.srate != srate):
+            res = self.flush()
+        self.asfh.profile = profile
+        self.srate, self.channels, self.bit_depth, self.fsize = srate, channels, bit_depth, frame_size
+        self.init = True
+        return res
+
+    def get_channels(self) -> int:
+        return self.channels
+
+    def set_channels(self, channels: int):
+        self.verify_channels(self.get_profile(), channels)
+        res = EncodeResult(b"", 0)
+        if self.channels != 0 and self.channels != channels:
+            res = self.flush()
+        self.channels = channels
+        return res
+
+    def get_srate(self) -> int:
+        return self.srate
+
+    def set_srate(self, srate: int):
+        err = self.verify_srate(self.get_profile(), srate)
+        if err:
+            return err
+        res = EncodeResult(b"", 0)
+        if self.srate != 0 and self.srate != srate:
+            res = self.flush()
+        self.srate = srate
+        return res
+
+    def get_frame_size(self) -> int:
+        return self.fsize
+
+    def set_frame_size(self, frame_size: int):
+        err = self.verify_frame_size(self.get_profile(), frame_size)
+        if err:
+            return err
+        self.fsize = frame_size
+
+    def get_bit_depth(self) -> int:
+        return self.bit_depth
+
+    def set_bit_depth(self, bit_depth: int):
+        err = self.verify_bit_depth(self.get_profile(), bit_depth)
+        if err:
+            return err
+        self.bit_depth = bit_depth
+
+    def set_ecc(self, ecc: bool, ecc_ratio):
+        self.asfh.ecc = ecc
+        dsize_zero, exceed_255 = ecc_ratio[0] == 0, ecc_ratio[0] + ecc_ratio[1] > 255
+        if dsize_zero or exceed_255:
+            if dsize_zero:
+                print("ECC data size must not be zero", file=sys.stderr)
+            if exceed_255:
+                print(f"ECC data size and check size must not exceed 255, given: {ecc_ratio[0]} and {ecc_ratio[1]}",
+                      file=sys.stderr)
+            print("Setting ECC to default 96 24", file=sys.stderr)
+            ecc_ratio = (96, 24)
+        self.asfh.ecc_dsize, self.asfh.ecc_codesize = ecc_ratio
+
+    def set_little_endian(self, little_endian: bool):
+        self.asfh.endian = little_endian
+
+    def set_loss_level(self, loss_level: float):
+        self.loss_level = max(abs(loss_level), 0.125)
+
+    def set_overlap_ratio(self, overlap_ratio: int):
+        if overlap_ratio != 0:
+            overlap_ratio = max(2, min(256, overlap_ratio))
+        self.asfh.overlap_ratio = overlap_ratio

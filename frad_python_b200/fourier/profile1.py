@@ -1,0 +1,102 @@
+"""Profile 1 (lossy, psychoacoustic quantisation) seams -- mirror of libfrad/fourier/profile1.py.
+
+Device: DCT-II, masking thresholds, divisor ramps, power-law quantiser (and the inverse chain).
+Host: Exp-Golomb-Rice bit strings (native C++ in libfradb200) and raw deflate (zlib)."""
+import struct
+import zlib
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+from .. import _abi
+from .._abi import PREC_REF, default_context
+from .profiles import compact
+from .profile0 import _device_pcm
+
+DEPTHS = (8, 12, 16, 24, 32, 48, 64)
+_POOL = None
+
+
+def _pool():
+    global _POOL
+    if _POOL is None:
+        import os
+        _POOL = ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1))
+    return _POOL
+
+
+def _deflate(raw: bytes) -> bytes:
+    return zlib.compress(raw, wbits=-15)
+
+
+def _inflate(frad: bytes):
+    try:
+        return zlib.decompress(frad, wbits=-15)
+    except Exception:
+        return None
+
+
+def pack_streams(q: np.ndarray, tq: np.ndarray) -> list:
+    """[B, N*C] / [B, 27*C] ints -> B deflated payloads (profile1.py:43-50)."""
+    tg = _abi.golomb_encode_rows(tq)
+    qg = _abi.golomb_encode_rows(q)
+    raws = [struct.pack(">I", len(t)) + t + g for t, g in zip(tg, qg)]
+    if len(raws) > 8:
+        return list(_pool().map(_deflate, raws))
+    return [_deflate(r) for r in raws]
+
+
+def analogue_batch(pcm: np.ndarray, nframes: int, n: int, hop: int, bits: int, srate: int, loss_level: float,
+                   ctx=None, prec: int = PREC_REF):
+    """Frames of table size ``n`` every ``hop`` samples -> (payload list, depth index, channels, srate)."""
+    ctx = ctx or default_context()
+    if bits not in DEPTHS:
+        bits = 16
+    srate = compact.get_valid_srate(srate)
+    q, tq, _ = ctx.p1_encode(_device_pcm(pcm), nframes, n, hop, bits, srate, max(abs(loss_level), 0.125), prec, 1)
+    return pack_streams(q, tq), DEPTHS.index(bits), pcm.shape[1], srate
+
+
+def analogue(pcm: np.ndarray, bits: int, srate: int, loss_level: float, ctx=None):
+    """profile1.py:15-52 -> (payload bytes, depth index, channels, srate)."""
+    n = compact.get_samples_min_ge(len(pcm))
+    if n != len(pcm):
+        pcm = np.pad(pcm, ((0, n - len(pcm)), (0, 0)))
+    out, idx, ch, sr = analogue_batch(pcm, 1, n, n, bits, srate, loss_level, ctx)
+    return out[0], idx, ch, sr
+
+
+def unpack_streams(payloads, fsize: int, channels: int):
+    """Payloads -> (q [B, fsize*C], tq [B, 27*C], ok mask); failed inflates give zero rows + ok False."""
+    nb = len(payloads)
+    if nb > 8:
+        raws = list(_pool().map(_inflate, payloads))
+    else:
+        raws = [_inflate(p) for p in payloads]
+    ok = np.array([r is not None and len(r) >= 4 for r in raws], bool)
+    tparts, qparts = [], []
+    for r, good in zip(raws, ok):
+        if not good:
+            tparts.append(b"\x00"); qparts.append(b"\x00")
+            continue
+        tlen = struct.unpack(">I", r[:4])[0]
+        tparts.append(r[4:4 + tlen] or b"\x00")
+        qparts.append(r[4 + tlen:] or b"\x00")
+    q = _abi.golomb_decode_rows(qparts, fsize * channels)
+    tq = _abi.golomb_decode_rows(tparts, _abi.NBANDS * channels)
+    return q, tq, ok
+
+
+def digital_batch(payloads, fb: int, channels: int, srate: int, fsize: int, ctx=None, prec: int = PREC_REF,
+                  out_dtype=np.float64) -> np.ndarray:
+    ctx = ctx or default_context()
+    q, tq, ok = unpack_streams(payloads, fsize, channels)
+    out = ctx.p1_decode(q, tq, None, len(payloads), fsize, channels, DEPTHS[fb], srate, prec, out_dtype)
+    if not ok.all():
+        out[~ok] = 0.0                      # inflate failure -> silent frame (profile1.py:59-60)
+    return out
+
+
+def digital(frad: bytes, fb: int, channels: int, srate: int, fsize: int, ctx=None) -> np.ndarray:
+    """profile1.py:54-77 -> float64 [fsize, C]."""
+    return digital_batch([bytes(frad)], fb, channels, srate, fsize, ctx)[0]

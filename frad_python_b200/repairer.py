@@ -1,0 +1,121 @@
+"""Batched streaming repairer -- same public surface as libfrad.Repairer (libfrad/repairer.py).
+
+Every frame in the buffer is parsed first; the Reed-Solomon repair of the old parity, the
+re-encoding with the new ratio and the payload CRCs run as batched GPU calls; headers are rewritten
+with the reference's own layout.  Bytes between frames pass through unchanged (repairer.py:58,62)."""
+import sys
+
+import numpy as np
+
+from . import common
+from ._abi import default_context
+from .fourier.profiles import COMPACT, LOSSLESS
+from .tools.asfh import ASFH
+
+
+class Repairer:
+    def __init__(self, ecc_ratio=(96, 24), ctx=None):
+        if ecc_ratio[0] == 0:
+            print("ECC data size must not be zero", file=sys.stderr)
+            print("Setting ECC to default 96 24", file=sys.stderr)
+            ecc_ratio = (96, 24)
+        if ecc_ratio[0] + ecc_ratio[1] > 255:
+            print(f"ECC data size and check size must not exceed 255, given: {ecc_ratio[0]} and {ecc_ratio[1]}",
+                  file=sys.stderr)
+            print("Setting ECC to default 96 24", file=sys.stderr)
+            ecc_ratio = (96, 24)
+        self.ctx = ctx or default_context()
+        self.asfh = ASFH()
+        self.buffer = b""
+        self.fix_error = True
+        self.ecc_ratio = tuple(ecc_ratio)
+        self.broken_frame = False
+
+    def is_empty(self) -> bool:
+        return len(self.buffer) < len(common.FRM_SIGN) or self.broken_frame
+
+    def _snapshot(self) -> ASFH:
+        s = ASFH()
+        s.__dict__.update(self.asfh.__dict__)
+        return s
+
+    def _render(self, items) -> bytes:
+        """items: raw bytes (passed through) or (header snapshot, payload) tuples in stream order."""
+        frames = [(i, it) for i, it in enumerate(items) if not isinstance(it, bytes)]
+        payloads = {i: it[1] for i, it in frames}
+        # 1. undo the old ECC (repairing where the CRC disagrees)
+        groups = {}
+        for i, (h, _) in frames:
+            if h.ecc and h.ecc_codesize > 0:
+                groups.setdefault((h.ecc_dsize, h.ecc_codesize, h.profile in LOSSLESS), []).append((i, h))
+        for (ds, cs, lossless), members in groups.items():
+            chunks = [payloads[i] for i, _ in members]
+            crcs = self.ctx.crc_many(chunks, lossless)
+            bad = np.array([int(c) != int.from_bytes(h.crc, "big") for c, (_, h) in zip(crcs, members)]) & self.fix_error
+            plain, _, _ = self.ctx.rs_decode_many([c for c, b in zip(chunks, bad) if not b], ds, cs, False)
+            fixed, _, _ = self.ctx.rs_decode_many([c for c, b in zip(chunks, bad) if b], ds, cs, True)
+            it_p, it_f = iter(plain), iter(fixed)
+            for (i, _), b in zip(members, bad):
+                payloads[i] = next(it_f) if b else next(it_p)
+        # 2. new ECC + checksums
+        order = [i for i, _ in frames]
+        if self.ecc_ratio[1] > 0:
+            enc = self.ctx.rs_encode_many([payloads[i] for i in order], self.ecc_ratio[0], self.ecc_ratio[1])
+        else:
+            enc = [payloads[i] for i in order]
+        loss_idx = [j for j, (i, (h, _)) in enumerate(frames) if h.profile not in COMPACT]
+        comp_idx = [j for j, (i, (h, _)) in enumerate(frames) if h.profile in COMPACT]
+        crc = [None] * len(frames)
+        for idxs, wide in ((loss_idx, True), (comp_idx, False)):
+            if idxs:
+                vals = self.ctx.crc_many([enc[j] for j in idxs], wide)
+                for j, v in zip(idxs, vals):
+                    crc[j] = int(v)
+        out = list(items)
+        for j, (i, (h, _)) in enumerate(frames):
+            h.ecc = True
+            h.ecc_dsize, h.ecc_codesize = self.ecc_ratio
+            out[i] = h.write(enc[j], crc[j])
+        return b"".join(out)
+
+    def process(self, stream: bytes) -> bytes:
+        self.buffer += stream
+        items = []
+        while True:
+            if self.asfh.all_set:
+                self.broken_frame = False
+                if len(self.buffer) < self.asfh.frmbytes:
+                    if len(stream) == 0:
+                        self.broken_frame = True
+                    break
+                frad, self.buffer = self.buffer[:self.asfh.frmbytes], self.buffer[self.asfh.frmbytes:]
+                items.append((self._snapshot(), frad))
+                # the reference leaves these set on its header object after each frame (repairer.py:49-50)
+                self.asfh.ecc = True
+                self.asfh.ecc_dsize, self.asfh.ecc_codesize = self.ecc_ratio
+                self.asfh.clear()
+            else:
+                if not self.asfh.buffer[:len(common.FRM_SIGN)] == common.FRM_SIGN:
+                    i = self.buffer.find(common.FRM_SIGN)
+                    if i != -1:
+                        items.append(self.buffer[:i])
+                        self.buffer = self.buffer[i:]
+                        self.asfh.buffer = self.buffer[:len(common.FRM_SIGN)]
+                        self.buffer = self.buffer[len(common.FRM_SIGN):]
+                    else:
+                        items.append(self.buffer[:-len(common.FRM_SIGN) + 1])
+                        self.buffer = self.buffer[-len(common.FRM_SIGN) + 1:]
+                        break
+                header_result, self.buffer = self.asfh.read(self.buffer)
+                if header_result == "Complete":
+                    continue
+                if header_result == "ForceFlush":
+                    items.append(self.asfh.force_flush())
+                    break
+                break
+        return self._render(items)
+
+    def flush(self) -> bytes:
+        ret = self.buffer
+        self.buffer = b""
+        return ret

@@ -151,6 +151,17 @@ int frad_rs_decode(frad_ctx* ctx, const uint8_t* buf, const uint64_t* off, const
                    uint8_t* out, const uint64_t* out_off, size_t out_stride, size_t out_total_bytes,
                    int32_t* status, int32_t* fixed);
 
+/* ---- host-side Exp-Golomb-Rice bit coder (fourier/tools/p1tools.py:46-74) --------------------------- */
+/* Pure host code (no device work): the bit strings that profile 1/2 deflate.  encode returns the number
+ * of bytes written, or -(bytes needed) when cap is too small; decode returns the number of values found
+ * (values beyond cap are counted but not stored). */
+int64_t frad_golomb_encode_host(const int32_t* vals, size_t n, uint8_t* out, size_t cap);
+int64_t frad_golomb_decode_host(const uint8_t* data, size_t len, int32_t* out, size_t cap);
+int frad_golomb_encode_batch_host(const int32_t* vals, int B, size_t n_per, uint8_t* out, size_t out_stride,
+                                  int64_t* out_len, int threads);
+int frad_golomb_decode_batch_host(const uint8_t* data, const uint64_t* off, const uint32_t* len, int B,
+                                  int32_t* out, size_t cap, int64_t* count, int threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,195 @@
+"""GPU stream-level parity: the batched Encoder / Decoder / Repairer (frad_python_b200) against byte
+streams and PCM produced by the unmodified reference (tests/golden/streams.npz)."""
+import numpy as np
+import pytest
+
+from oracle import frad_oracle as O
+
+pytestmark = pytest.mark.gpu
+LOSS0 = 1.25 ** 0 / 19 + 0.5
+
+
+@pytest.fixture(scope="module")
+def F():
+    import frad_python_b200 as F
+    return F
+
+
+def parse(stream: bytes):
+    """-> list of (kind, header fields dict, payload) using the product's ASFH reader."""
+    from frad_python_b200.tools.asfh import ASFH
+    from frad_python_b200 import common
+    out, pos = [], 0
+    while True:
+        i = stream.find(common.FRM_SIGN, pos)
+        if i < 0:
+            break
+        a = ASFH()
+        a.buffer = stream[i:i + 4]
+        res, _ = a.read(stream[i + 4:i + 64])
+        if res == "ForceFlush":
+            out.append(("flush", None, stream[i:i + 12]))
+            pos = i + 12
+            continue
+        assert res == "Complete", res
+        pay = stream[i + a.header_bytes:i + a.header_bytes + a.frmbytes]
+        out.append(("frame", a, pay))
+        pos = i + a.header_bytes + a.frmbytes
+    return out
+
+
+def run_encoder(F, pcm, profile, srate, ch, bits, fsize, fmt, ecc=False, ratio=(96, 24), le=False, overlap=16,
+                loss=LOSS0, chunk=32768):
+    enc = F.Encoder(profile, srate, ch, bits, fsize, fmt)
+    enc.set_ecc(ecc, ratio); enc.set_little_endian(le); enc.set_overlap_ratio(overlap); enc.set_loss_level(loss)
+    raw = pcm.tobytes()
+    out, samples = b"", 0
+    for i in range(0, len(raw), chunk):
+        r = enc.process(raw[i:i + chunk])
+        out += r.buf; samples += r.samples
+    r = enc.flush()
+    return out + r.buf, samples + r.samples
+
+
+def run_decoder(F, stream, fix=False, chunk=32768, **kw):
+    dec = F.Decoder(fix, **kw)
+    pcm = []
+    for i in range(0, len(stream), chunk):
+        r = dec.process(stream[i:i + chunk])
+        if r.pcm.size:
+            pcm.append(r.pcm)
+    r = dec.flush()
+    if r.pcm.size:
+        pcm.append(r.pcm)
+    return np.concatenate(pcm)
+
+
+def same_headers(a, b):
+    keys = ("profile", "ecc", "endian", "bit_depth_index", "channels", "srate", "fsize", "overlap_ratio", "ecc_dsize",
+            "ecc_codesize", "frmbytes")
+    return all(getattr(a, k) == getattr(b, k) for k in keys)
+
+
+@pytest.mark.parametrize("chunk", [32768, 1 << 22, 5000])
+def test_encoder_p0_stream_structure(F, g_streams, chunk):
+    pcm = g_streams["pcm"]
+    mine, samples = run_encoder(F, pcm, 0, 48000, 2, 32, 2048, "f32le", chunk=chunk)
+    ref = g_streams["p0_b32"].tobytes()
+    assert len(mine) == len(ref) and samples == len(pcm)
+    fm, fr = parse(mine), parse(ref)
+    assert len(fm) == len(fr) == 10
+    for (km, hm, pm), (kr, hr, pr) in zip(fm, fr):
+        assert km == kr == "frame" and same_headers(hm, hr)
+        assert int.from_bytes(hm.crc, "big") == O.crc32(pm)
+        vm, vr = np.frombuffer(pm, ">f4").astype(np.float64), np.frombuffer(pr, ">f4").astype(np.float64)
+        assert np.max(np.abs(vm - vr)) <= 4e-7
+
+
+def test_encoder_p0_ecc_le_16bit_and_int_pcm(F, g_streams):
+    pcm = g_streams["pcm"]
+    mine, _ = run_encoder(F, pcm, 0, 48000, 2, 16, 2048, "f32le", ecc=True, le=True)
+    ref = g_streams["p0_b16_le_ecc"].tobytes()
+    fm, fr = parse(mine), parse(ref)
+    assert len(mine) == len(ref) and len(fm) == len(fr)
+    for (_, hm, pm), (_, hr, pr) in zip(fm, fr):
+        assert same_headers(hm, hr) and int.from_bytes(hm.crc, "big") == O.crc32(pm)
+        dm, dr = O.ecc_decode(pm, 96, 24, False), O.ecc_decode(pr, 96, 24, False)
+        assert pm == O.ecc_encode(dm, 96, 24)                      # parity is exact for the data we produced
+        vm, vr = np.frombuffer(dm, "<f2").astype(float), np.frombuffer(dr, "<f2").astype(float)
+        assert np.max(np.abs(vm - vr)) <= 1.3e-4 and np.mean(vm != vr) < 2e-3
+    s16 = g_streams["pcm_s16"]
+    mine, samples = run_encoder(F, s16, 0, 48000, 2, 24, 1000, "s16le")
+    ref = g_streams["p0_s16_b24"].tobytes()
+    fm, fr = parse(mine), parse(ref)
+    assert len(mine) == len(ref) and len(fm) == len(fr) and samples == len(s16)
+    for (_, hm, pm), (_, hr, pr) in zip(fm, fr):
+        assert same_headers(hm, hr)
+        vm, vr = O.p0_unpack(pm, 24, False), O.p0_unpack(pr, 24, False)
+        assert np.max(np.abs(vm - vr)) <= 1.3e-7 and np.mean(vm != vr) < 1e-3   # f64 transform, 24-bit storage
+
+
+@pytest.mark.parametrize("name,profile,kw", [("p1", 1, {}), ("p1_ecc", 1, {"ecc": True}), ("p1_noov", 1, {"overlap": 0}),
+                                              ("p2", 2, {})])
+def test_encoder_lossy_stream_structure(F, g_streams, name, profile, kw):
+    pcm = g_streams["pcm"]
+    mine, samples = run_encoder(F, pcm, profile, 48000, 2, 16, 2048, "f32le", **kw)
+    ref = g_streams[name].tobytes()
+    fm, fr = parse(mine), parse(ref)
+    assert [k for k, _, _ in fm] == [k for k, _, _ in fr]          # same frames and force-flush markers
+    assert samples == len(pcm)
+    nbad, ntot = 0, 0
+    for (km, hm, pm), (kr, hr, pr) in zip(fm, fr):
+        if km == "flush":
+            assert pm == pr
+            continue
+        for k in ("profile", "ecc", "endian", "bit_depth_index", "channels", "srate", "fsize", "overlap_ratio",
+                  "ecc_dsize", "ecc_codesize"):
+            assert getattr(hm, k) == getattr(hr, k), k
+        if hm.ecc:
+            assert int.from_bytes(hm.crc, "big") == O.crc16_arc(pm)
+            pm, pr = O.ecc_decode(pm, 96, 24, False), O.ecc_decode(pr, 96, 24, False)
+        sm = O.p1_unpack(pm) if profile == 1 else O.p2_unpack(pm)
+        sr = O.p1_unpack(pr) if profile == 1 else O.p2_unpack(pr)
+        for a, b in zip(sm, sr):
+            assert len(a) == len(b) and np.max(np.abs(a - b)) <= 1
+        nbad += int(np.sum(sm[0] != sr[0])); ntot += len(sm[0])
+    assert nbad <= 1e-4 * ntot + 1
+
+
+@pytest.mark.parametrize("name,fix", [("p0_b32", False), ("p0_b16_le_ecc", True), ("p0_s16_b24", False), ("p1", False),
+                                      ("p1_ecc", True), ("p2", False)])
+def test_decoder_matches_reference_pcm(F, g_streams, name, fix):
+    want = g_streams[name + "_dec"]
+    for chunk in (32768, 1 << 22):
+        got = run_decoder(F, g_streams[name].tobytes(), fix, chunk)
+        assert got.shape == want.shape and got.dtype == np.float64
+        assert np.max(np.abs(got - want)) <= 1e-12
+
+
+def test_decoder_f32_mode_within_one_16bit_lsb(F, g_streams):
+    want = g_streams["p1_dec"]
+    got = run_decoder(F, g_streams["p1"].tobytes(), False, precision=F.PREC_F32)
+    err = np.max(np.abs(got - want))
+    snr = 10 * np.log10(np.sum(want ** 2) / np.sum((got - want) ** 2))
+    assert err <= 2.0 ** -15 and snr > 100, (err, snr)        # stated tolerance: <= 1 LSB at 16 bit
+
+
+@pytest.mark.parametrize("name", ["p1_ecc", "p0_b16_le_ecc"])
+def test_corrupted_streams_decode_and_repair_bit_exact(F, g_streams, name):
+    bad = g_streams[name + "_bad"].tobytes()
+    got = run_decoder(F, bad, True)
+    want = g_streams[name + "_bad_dec"]
+    assert got.shape == want.shape and np.max(np.abs(got - want)) <= 1e-12
+    for ratio, key in (((96, 24), "_bad_rep"), ((128, 20), "_bad_rep2")):
+        for chunk in (32768, 1 << 22, 777):
+            rp = F.Repairer(ratio)
+            out = b""
+            for i in range(0, len(bad), chunk):
+                out += rp.process(bad[i:i + chunk])
+            out += rp.flush()
+            assert out == g_streams[name + key].tobytes(), (ratio, chunk)
+
+
+def test_repair_adds_ecc_to_plain_stream(F, g_streams):
+    rp = F.Repairer((96, 24))
+    s = g_streams["p0_b32"].tobytes()
+    assert rp.process(s) + rp.flush() == g_streams["p0_b32_rep"].tobytes()
+
+
+def test_reference_style_seams_batch_of_one(F, g_p0, g_p1, g_crc):
+    """The per-call seams keep the reference signatures and return types."""
+    fr = g_p0["pcm_f32"][0]
+    pay, idx, ch, sr = F.fourier.profile0.analogue(fr, 32, 48000, False)
+    assert (idx, ch, sr) == (3, 2, 48000) and len(pay) == 2048 * 2 * 4
+    pcm = F.fourier.profile0.digital(pay, idx, ch, False)
+    assert pcm.shape == (2048, 2) and pcm.dtype == np.float64 and np.max(np.abs(pcm - fr)) < 1e-6
+    pay, idx, ch, sr = F.fourier.profile1.analogue(g_p1["s48rag_pcm"][0], 16, 48000, LOSS0)   # 1900 -> padded to 2048
+    q, tq = O.p1_unpack(pay)
+    assert len(q) == 4096 and np.max(np.abs(q - g_p1["s48rag_q"][0])) <= 1
+    out = F.fourier.profile1.digital(g_p1["s48_pay0"].tobytes(), 2, 2, 48000, 2048)
+    assert np.max(np.abs(out - g_p1["s48_dec"][0])) <= 1e-12
+    assert np.array_equal(F.fourier.profile1.digital(b"not deflate", 2, 2, 48000, 2048), np.zeros((2048, 2)))
+    b = g_crc["crc_in_4096"].tobytes()
+    assert F.common.crc32(b) == O.crc32(b) and F.common.crc16_ansi(b) == O.crc16_arc(b)
+    e = F.tools.ecc.encode(b, 96, 24)
+    assert e == O.ecc_encode(b, 96, 24) and F.tools.ecc.decode(e, 96, 24, True) == b

@@ -1,0 +1,195 @@
+"""CPU-only tests: host-side mirror logic, the native host Golomb coder, ABI symbol coverage, and
+the frame sharding used for N > 1 GPUs (gloo, world_size 2).  No GPU compute is called here."""
+import os
+import re
+import struct
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import frad_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from frad_python_b200 import _abi
+    hdr = open(os.path.join(ROOT, "include", "fradb200.h")).read()
+    declared = set(re.findall(r"\b(frad_[a-z0-9_]+)\s*\(", hdr))
+    L = _abi.lib()
+    missing = [s for s in sorted(declared) if not hasattr(L, s)]
+    assert not missing, missing
+    assert declared <= set(_abi.EXPORTS) | {"frad_ctx"}, sorted(declared - set(_abi.EXPORTS))
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from frad_python_b200 import Context, FradError
+    with pytest.raises(FradError):
+        Context(0)
+    from frad_python_b200 import common
+    with pytest.raises(FradError):
+        common.crc32(b"abc")
+
+
+def test_product_does_not_import_oracle():
+    import frad_python_b200
+    pkg = os.path.dirname(frad_python_b200.__file__)
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), (dirpath, f)
+
+
+def test_golomb_host_matches_oracle_and_golden(g_p1):
+    from frad_python_b200 import _abi
+    assert _abi.golomb_encode(g_p1["gol_in"]) == g_p1["gol_out"].tobytes()
+    assert np.array_equal(_abi.golomb_decode(g_p1["gol_out"].tobytes()), g_p1["gol_in"])
+    assert _abi.golomb_encode(np.zeros(17, int)) == g_p1["gol_zero_out"].tobytes()
+    assert _abi.golomb_encode(np.array([], int)) == b"\x00"
+    rng = np.random.default_rng(5)
+    for hi in (1, 2, 3, 5, 100, 40000, 2 ** 30):
+        v = rng.integers(-hi, hi + 1, 777)
+        e = _abi.golomb_encode(v)
+        assert e == O.golomb_encode(v)
+        assert np.array_equal(_abi.golomb_decode(e), v)
+    rows = rng.integers(-60, 60, (33, 512)).astype(np.int32)
+    enc = _abi.golomb_encode_rows(rows)
+    assert enc == [O.golomb_encode(r) for r in rows]
+    assert np.array_equal(_abi.golomb_decode_rows(enc, 512), rows)
+    assert np.array_equal(_abi.golomb_decode_rows(enc, 600)[:, 512:], np.zeros((33, 88), np.int32))   # untrim padding
+    for cut in (1, 2, 7, 40):                       # truncated input follows the reference's slicing rule
+        assert np.array_equal(_abi.golomb_decode(enc[0][:cut]), O.golomb_decode(enc[0][:cut]))
+
+
+def test_asfh_bytes_match_oracle_header():
+    from frad_python_b200.tools.asfh import ASFH
+    pay = bytes(range(200))
+    for prof, ecc, le, depth, ch, sr, fs, ov in ((0, False, False, 3, 2, 48000, 2048, 0), (0, True, True, 1, 8, 96000, 904, 0),
+                                                 (1, False, False, 2, 2, 48000, 2048, 16), (1, True, False, 2, 1, 44100, 1280, 2),
+                                                 (2, True, False, 4, 6, 8000, 128, 256)):
+        a = ASFH()
+        a.profile, a.ecc, a.endian, a.bit_depth_index = prof, ecc, le, depth
+        a.channels, a.srate, a.fsize, a.overlap_ratio = ch, sr, fs, ov
+        a.ecc_dsize, a.ecc_codesize = 96, 24
+        crc = O.crc32(pay) if prof == 0 else O.crc16_arc(pay)
+        want = O.frame_header(pay, prof, ecc, le, depth, ch, sr, fs, ov, 96, 24) + pay
+        assert a.write(pay, crc) == want
+        assert a.force_flush() == O.force_flush_header(prof, ecc, le, depth, ch, sr, fs)
+        b = ASFH()
+        b.buffer = want[:4]
+        res, rest = b.read(want[4:])
+        assert res == "Complete" and rest == pay and b.frmbytes == len(pay)
+        assert (b.profile, b.ecc, b.endian, b.bit_depth_index, b.channels) == (prof, ecc, le, depth, ch)
+        if prof == 0:
+            assert (b.srate, b.fsize) == (sr, fs) and b.crc == crc.to_bytes(4, "big")
+        else:
+            assert b.fsize == O.samples_min_ge(fs) and b.overlap_ratio == ov
+        # incremental feeding
+        c = ASFH()
+        c.buffer = want[:4]
+        res, rest = c.read(want[4:6])
+        assert res == "Incomplete"
+        res, rest = c.read(want[6:])
+        assert res == "Complete" and rest == pay
+
+
+def test_asfh_reads_reference_golden_stream(g_streams):
+    from frad_python_b200.tools.asfh import ASFH
+    from frad_python_b200 import common
+    for name in ("p0_b32", "p1", "p1_ecc", "p0_b16_le_ecc"):
+        s = g_streams[name].tobytes()
+        pos, nframes, flushes = 0, 0, 0
+        while True:
+            i = s.find(common.FRM_SIGN, pos)
+            if i < 0:
+                break
+            a = ASFH()
+            a.buffer = s[i:i + 4]
+            res, _ = a.read(s[i + 4:i + 64])
+            if res == "ForceFlush":
+                flushes += 1
+                pos = i + 4
+                continue
+            assert res == "Complete"
+            pay = s[i + a.header_bytes:i + a.header_bytes + a.frmbytes]
+            want = O.crc32(pay) if a.profile == 0 else O.crc16_arc(pay)
+            if a.profile == 0 or a.ecc:
+                assert int.from_bytes(a.crc, "big") == want
+            nframes += 1
+            pos = i + a.header_bytes + a.frmbytes
+        assert nframes == 10 and (flushes == 2 if name.startswith("p1") else flushes == 0)
+
+
+def test_backend_formats_follow_reference():
+    from frad_python_b200.backend import ff_format_to_numpy_type, to_f64, from_f64, hanning_in_overlap
+    assert ff_format_to_numpy_type("s16le") == np.dtype("<i2") and ff_format_to_numpy_type("F64BE") == np.dtype(">f8")
+    x = np.array([[-32768, 0, 16384]], "<i2")
+    assert np.array_equal(to_f64(x, x.dtype), np.array([[-1.0, 0.0, 0.5]]))
+    u = np.array([[0, 128, 255]], "u1")
+    assert np.array_equal(to_f64(u, u.dtype), np.array([[-1.0, 0.0, 127 / 128]]))
+    be = np.array([[256]], ">i2")
+    assert to_f64(be, be.dtype) is be                       # reference quirk: big-endian ints pass through
+    f = np.array([[0.5]], "<f4")
+    assert to_f64(f, f.dtype) is f
+    assert np.array_equal(from_f64(np.array([0.5, -1.0]), np.dtype("<i2")), np.array([16384, -32768], "<i2"))
+    assert np.allclose(hanning_in_overlap(128), O.hann_fade_in(128), rtol=0, atol=0)
+
+
+def test_shard_ranges():
+    from frad_python_b200 import shard
+    assert shard.frame_ranges(10, 4) == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    assert shard.frame_ranges(2, 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]
+    assert shard.pcm_slice((3, 6), 2048, 1920) == (5760, 5 * 1920 + 2048)
+    assert shard.count_frames(2048 + 1920 * 4 + 5, 2048, 1920) == 5
+
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np
+import torch.distributed as dist
+from frad_python_b200 import shard
+from oracle import frad_oracle as O
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank = dist.get_rank()
+N, HOP = 2048, 1920
+pcm = O.synth_pcm(0.25, 48000, 2, seed=77)
+nframes = shard.count_frames(len(pcm), N, HOP)
+mine = shard.frame_ranges(nframes, 2)[rank]
+lo, hi = shard.pcm_slice(mine, N, HOP)
+local = pcm[lo:hi]
+part = b""
+for j in range(mine[1] - mine[0]):
+    f = local[j * HOP:j * HOP + N]
+    pay, idx, ch, sr = O.p1_analogue(f, 16, 48000, 0.55)
+    part += O.frame_header(pay, 1, False, False, idx, ch, sr, N, 16, 0, 0) + pay
+parts = shard.gather_in_order(part, dist, 0)
+if rank == 0:
+    whole = b""
+    for j in range(nframes):
+        f = pcm[j * HOP:j * HOP + N]
+        pay, idx, ch, sr = O.p1_analogue(f, 16, 48000, 0.55)
+        whole += O.frame_header(pay, 1, False, False, idx, ch, sr, N, 16, 0, 0) + pay
+    assert b"".join(parts) == whole, "sharded bitstream differs"
+    print("SHARD_OK", nframes)
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_frame_sharding_gloo(tmp_path):
+    """World size 2 on CPU (gloo): each rank encodes its contiguous frame range (oracle stands in for the
+    GPU codec), rank 0 concatenates in rank order -> identical to the single-process bitstream."""
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "SHARD_OK" in outs[0]
