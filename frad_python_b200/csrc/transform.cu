@@ -480,7 +480,7 @@ static int launch_decode(frad_ctx* ctx, dec_params& P, int prec) {
   if (pl->direct) {
     int grid = 4 * ctx->sm_count; if (grid > nseq) grid = nseq;
     size_t need = (size_t)grid * P.N * sizeof(double);
-    size_t tns = (P.profile == 2) ? (size_t)grid * P.N * sizeof(double) : 0;
+    size_t tns = (P.profile == 2) ? (size_t)grid * 2 * P.N * sizeof(double) : 0;
     char* g = (char*)frad_scratch(ctx, 0, need + tns);
     if (!g) return FRAD_E_NOMEM;
     P.gscratch = g; P.tns_scratch = (double*)(g + need);
@@ -495,7 +495,7 @@ static int launch_decode(frad_ctx* ctx, dec_params& P, int prec) {
   const void* k = (prec == FRAD_PREC_F32) ? (const void*)seq_decode_kernel<float> : (const void*)seq_decode_kernel<double>;
   int rc = (prec == FRAD_PREC_F32) ? configure<float>(ctx, pl, nseq, k, &cfg) : configure<double>(ctx, pl, nseq, k, &cfg);
   if (rc) return rc;
-  size_t tns = (P.profile == 2) ? (size_t)cfg.grid * P.N * sizeof(double) : 0;
+  size_t tns = (P.profile == 2) ? (size_t)cfg.grid * 2 * P.N * sizeof(double) : 0;
   if (cfg.gscratch + tns) {
     char* g = (char*)frad_scratch(ctx, 0, cfg.gscratch + tns);
     if (!g) return FRAD_E_NOMEM;
