@@ -3,11 +3,11 @@
 #include "common.cuh"
 
 namespace {
-struct arena { frad_ctx* ctx; char* base; size_t used, cap; };
+struct arena { frad_ctx* ctx; char* base; size_t used, cap; bool bad; };
 // carve 256-byte aligned pieces out of scratch slot 2
 void* take(arena& a, size_t bytes) {
   size_t o = (a.used + 255) & ~(size_t)255;
-  if (o + bytes > a.cap) return nullptr;
+  if (o + bytes > a.cap) { a.bad = true; return nullptr; }
   a.used = o + bytes;
   return a.base + o;
 }
@@ -15,7 +15,7 @@ size_t rounded(size_t b) { return ((b + 255) & ~(size_t)255) + 256; }
 }  // namespace
 
 #define ARENA(ctx, a, total)                                              \
-  arena a; a.ctx = (ctx); a.used = 0; a.cap = (total);                    \
+  arena a; a.ctx = (ctx); a.used = 0; a.cap = (total); a.bad = false;     \
   a.base = (char*)frad_scratch((ctx), 2, (total));                        \
   if (!a.base) return FRAD_E_NOMEM;
 
@@ -33,6 +33,7 @@ extern "C" int frad_p0_encode(frad_ctx* ctx, const void* pcm, int pcm_dtype, int
   uint8_t* d_out = (uint8_t*)take(a, out_bytes);
   double* d_peak = (double*)take(a, 8 * (size_t)B);
   uint32_t* d_crc = (uint32_t*)take(a, 4 * (size_t)B);
+  if (a.bad) return frad_fail(ctx, FRAD_E_NOMEM, "internal arena overflow");
   int rc;
   if ((rc = frad_h2d(ctx, d_in, pcm, in_bytes))) return rc;
   if ((rc = frad_p0_encode_dev(ctx, d_in, pcm_dtype, hop, B, N, C, bits, little_endian, prec, d_out, payload_stride, d_peak))) return rc;
@@ -57,6 +58,7 @@ extern "C" int frad_p0_decode(frad_ctx* ctx, const uint8_t* payload, size_t payl
   ARENA(ctx, a, rounded(in_bytes) + rounded(out_bytes));
   uint8_t* d_in = (uint8_t*)take(a, in_bytes);
   void* d_out = take(a, out_bytes);
+  if (a.bad) return frad_fail(ctx, FRAD_E_NOMEM, "internal arena overflow");
   int rc;
   if ((rc = frad_h2d(ctx, d_in, payload, in_bytes))) return rc;
   if ((rc = frad_p0_decode_dev(ctx, d_in, payload_stride, B, N, C, bits, little_endian, prec, d_out, pcm_dtype))) return rc;
@@ -78,6 +80,7 @@ extern "C" int frad_p1_encode(frad_ctx* ctx, const void* pcm, int pcm_dtype, int
   int32_t* d_q = (int32_t*)take(a, q_bytes);
   int32_t* d_tq = (int32_t*)take(a, tq_bytes);
   int32_t* d_l = lpc ? (int32_t*)take(a, l_bytes) : nullptr;
+  if (a.bad) return frad_fail(ctx, FRAD_E_NOMEM, "internal arena overflow");
   int rc;
   if ((rc = frad_h2d(ctx, d_in, pcm, in_bytes))) return rc;
   if ((rc = frad_p1_encode_dev(ctx, d_in, pcm_dtype, hop, B, N, C, bits, srate, loss_level, prec, d_q, d_tq, d_l))) return rc;
@@ -100,6 +103,7 @@ extern "C" int frad_p1_decode(frad_ctx* ctx, const int32_t* q, const int32_t* tq
   int32_t* d_tq = (int32_t*)take(a, tq_bytes);
   int32_t* d_l = lpc ? (int32_t*)take(a, l_bytes) : nullptr;
   void* d_out = take(a, out_bytes);
+  if (a.bad) return frad_fail(ctx, FRAD_E_NOMEM, "internal arena overflow");
   int rc;
   if ((rc = frad_h2d(ctx, d_q, q, q_bytes))) return rc;
   if ((rc = frad_h2d(ctx, d_tq, tq, tq_bytes))) return rc;
@@ -113,6 +117,7 @@ extern "C" int frad_p1_decode(frad_ctx* ctx, const int32_t* q, const int32_t* tq
 static int stage_index(frad_ctx* ctx, arena& a, const uint64_t* off, const uint32_t* len, int B,
                        const uint64_t** d_off, const uint32_t** d_len) {
   *d_off = nullptr; *d_len = nullptr;
+  if (a.bad) return frad_fail(ctx, FRAD_E_NOMEM, "internal arena overflow");
   int rc;
   if (off) {
     void* p = take(a, 8 * (size_t)B);
@@ -137,6 +142,7 @@ static int crc_host(frad_ctx* ctx, const uint8_t* buf, const uint64_t* off, cons
   uint8_t* d_buf = (uint8_t*)take(a, total ? total : 1);
   uint32_t* d_out = (uint32_t*)take(a, 4 * (size_t)B);
   const uint64_t* d_off; const uint32_t* d_len;
+  if (a.bad) return frad_fail(ctx, FRAD_E_NOMEM, "internal arena overflow");
   int rc;
   if ((rc = frad_h2d(ctx, d_buf, buf, total))) return rc;
   if ((rc = stage_index(ctx, a, off, len, B, &d_off, &d_len))) return rc;
@@ -166,6 +172,7 @@ extern "C" int frad_rs_encode(frad_ctx* ctx, const uint8_t* buf, const uint64_t*
   uint8_t* d_buf = (uint8_t*)take(a, total_bytes ? total_bytes : 1);
   uint8_t* d_out = (uint8_t*)take(a, out_total_bytes ? out_total_bytes : 1);
   const uint64_t *d_off, *d_ooff = nullptr; const uint32_t* d_len;
+  if (a.bad) return frad_fail(ctx, FRAD_E_NOMEM, "internal arena overflow");
   int rc;
   if ((rc = frad_h2d(ctx, d_buf, buf, total_bytes))) return rc;
   if ((rc = stage_index(ctx, a, off, len, B, &d_off, &d_len))) return rc;
@@ -192,6 +199,7 @@ extern "C" int frad_rs_decode(frad_ctx* ctx, const uint8_t* buf, const uint64_t*
   int32_t* d_status = (int32_t*)take(a, 4 * (size_t)B);
   int32_t* d_fixed = (int32_t*)take(a, 4 * (size_t)B);
   const uint64_t *d_off, *d_ooff = nullptr; const uint32_t* d_len;
+  if (a.bad) return frad_fail(ctx, FRAD_E_NOMEM, "internal arena overflow");
   int rc;
   if ((rc = frad_h2d(ctx, d_buf, buf, total_bytes))) return rc;
   if ((rc = stage_index(ctx, a, off, len, B, &d_off, &d_len))) return rc;

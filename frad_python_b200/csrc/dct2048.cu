@@ -335,7 +335,7 @@ template <typename T> struct dec_layout {
 };
 
 template <typename T, int PROFILE, int CT>
-__global__ void __launch_bounds__(FW * 32, (sizeof(T) == 8) ? FRAD_MINB / 2 : FRAD_MINB)
+__global__ void __launch_bounds__(FW * 32, (sizeof(T) == 8) ? 2 : FRAD_MINB)
 dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restrict__ tw32, const double* __restrict__ dq64) {
   typedef typename vec2<T>::type V;
   typedef dec_layout<T> LY;
