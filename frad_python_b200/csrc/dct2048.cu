@@ -69,8 +69,15 @@ struct smem_tail {
   int lo[FRAD_NBANDS + 1];
   double thr[FW][FRAD_NBANDS + 1];
   float4 bp[FW][FRAD_NBANDS + 1];                     // per band: ramp end points (pre-scaled), lo, hi as floats
-  float dq[DQ_TAB];                                   // decode: |q|^(4/3) / scale
   uint8_t bidx[FN];                                   // band index of every bin (FRAD_NBANDS - 1 = "past the ramps")
+  float aux[(FW * FRAD_NBANDS * 32 > DQ_TAB) ? FW * FRAD_NBANDS * 32 : DQ_TAB];
+  // encode: aux = per-warp, per-lane band energy partials [w][band][lane]; decode: aux = |q|^(4/3)/scale table
+};
+
+struct dec_tail {
+  int lo[FRAD_NBANDS + 1];
+  double thr[FW][FRAD_NBANDS + 1];
+  float aux[DQ_TAB];                                  // |q|^(4/3) / scale for |q| < DQ_TAB (f32 path)
 };
 
 // band index table shared by all warps of the CTA (same N and sample rate)
@@ -182,22 +189,32 @@ __global__ void __launch_bounds__(FW * 32, FRAD_MINB) enc2048_kernel(enc_params 
       const int partner = (32 - lane) & 31;
       const bool swap_out = (PROFILE == 0) && !P.le;
       float mx = 0.0f;
+      float* part = tail->aux + (size_t)w * FRAD_NBANDS * 32 + lane;     // this lane's column of band partials
+      if (PROFILE == 1) {
+#pragma unroll
+        for (int bnd = 0; bnd < FRAD_NBANDS; bnd++) part[bnd * 32] = 0.0f;
+      }
       auto emit = [&](int k, float val) {
         if (PROFILE == 0) {
           mx = fmaxf(mx, fabsf(val));
           if (swap_out) val = __uint_as_float(__byte_perm(__float_as_uint(val), 0, 0x0123));
+        } else {
+          float* pp = part + 32 * (int)tail->bidx[k];                    // private slot: no atomics, no conflicts
+          *pp = fmaf(val, val, *pp);
         }
         X[k] = val;
       };
-      auto do_pair = [&](int k, float2 zk, float2 zm, bool first) {      // zm = conj(Z[M-k])
+      auto do_pair = [&](int k, float2 zk, float2 zm, bool first, bool self) {   // zm = conj(Z[M-k])
         const float2 A = cadd(zk, zm), D = csub(zk, zm);
         const float2 Bv = make_float2(D.y, -D.x);
         const float2 Pk = cmul(__ldg(cfh + k), A), Qk = cmul(__ldg(dfh + k), Bv);
         const float2 y = cadd(Pk, Qk), t = csub(Pk, Qk);
         emit(k, y.x);
         if (!first) emit(FN - k, -y.y);
-        emit(FM - k, (t.x - t.y) * (float)FRAD_RSQRT2);
-        if (!first) emit(FM + k, (t.x + t.y) * (float)FRAD_RSQRT2);
+        if (!self) {                                                     // k == M - k: the same two bins again
+          emit(FM - k, (t.x - t.y) * (float)FRAD_RSQRT2);
+          if (!first) emit(FM + k, (t.x + t.y) * (float)FRAD_RSQRT2);
+        }
       };
 #pragma unroll
       for (int o = 0; o < 16; o++) {
@@ -205,9 +222,9 @@ __global__ void __launch_bounds__(FW * 32, FRAD_MINB) enc2048_kernel(enc_params 
         float2 zm;
         zm.x = __shfl_sync(0xffffffffu, snd.x, partner);
         zm.y = -__shfl_sync(0xffffffffu, snd.y, partner);
-        do_pair(lane + 32 * o, v[o], zm, (o == 0) && (lane == 0));
+        do_pair(lane + 32 * o, v[o], zm, (o == 0) && (lane == 0), false);
       }
-      if (lane == 0) do_pair(FM / 2, v[16], cconj(v[16]), false);          // self-paired bin k = 512
+      if (lane == 0) do_pair(FM / 2, v[16], cconj(v[16]), false, true);          // self-paired bin k = 512
       if (PROFILE == 0) {
         if (P.peak) {
 #pragma unroll
@@ -216,17 +233,18 @@ __global__ void __launch_bounds__(FW * 32, FRAD_MINB) enc2048_kernel(enc_params 
         }
       } else {
         __syncwarp();
-        // ---- band energies of the scaled spectrum: strided partial sums + warp reduction per band ----
+        // ---- band energies of the scaled spectrum: lane b adds up row b of the per-lane partials ----
         const float scalef = (float)P.scale;
         float tot = 0.0f;
-#pragma unroll 1
-        for (int bnd = 0; bnd < FRAD_NBANDS; bnd++) {
-          const int hi = tail->lo[bnd + 1];
-          float s = 0.0f;
-          for (int k = tail->lo[bnd] + lane; k < hi; k += 32) { const float xv = X[k] * scalef; s = fmaf(xv, xv, s); }
+        if (lane < FRAD_NBANDS) {
+          const float* row = tail->aux + (size_t)w * FRAD_NBANDS * 32 + lane * 32;
+          float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f, t3 = 0.0f;
 #pragma unroll
-          for (int sh = 16; sh > 0; sh >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sh);
-          if (lane == bnd) tot = s;
+          for (int l = 0; l < 32; l += 4) {                              // rotated start: conflict-free columns
+            t0 += row[(l + lane) & 31]; t1 += row[(l + 1 + lane) & 31];
+            t2 += row[(l + 2 + lane) & 31]; t3 += row[(l + 3 + lane) & 31];
+          }
+          tot = ((t0 + t1) + (t2 + t3)) * (scalef * scalef);
         }
         int cnt = 1;
         if (lane < FRAD_NBANDS) cnt = tail->lo[lane + 1] - tail->lo[lane];
@@ -248,7 +266,7 @@ __global__ void __launch_bounds__(FW * 32, FRAD_MINB) enc2048_kernel(enc_params 
         {
           const double thr_next = __shfl_down_sync(0xffffffffu, thr, 1);
           if (lane <= FRAD_NBANDS) {
-            float4 bpv = make_float4(1.0f, 1.0f, 0.0f, 2.0f * FN);      // harmless positive divisor for unused bands
+            float4 bpv = make_float4(1.0e30f, 1.0e30f, -1.0f, 2.0f * FN);  // huge divisor: bins past the last ramp quantise to 0
             if (lane < FRAD_NBANDS - 1 && cnt > 0) {
               const double ns = (double)cnt * P.scale;
               bpv = make_float4((float)(thr / ns), (float)(thr_next / ns), (float)tail->lo[lane], (float)tail->lo[lane + 1]);
@@ -266,30 +284,45 @@ __global__ void __launch_bounds__(FW * 32, FRAD_MINB) enc2048_kernel(enc_params 
         for (int kbase = lane; kbase < FN; kbase += 256) {
           float xs[8];
           int ms[8];
-          unsigned amb = 0;
+          bool allok = true;
+          const float kb = (float)kbase;
 #pragma unroll
           for (int u = 0; u < 8; u++) {
             const int k = kbase + 32 * u;
-            const float kf = (float)k;
+            const float kf = kb + (float)(32 * u);
             const float x = X[k];
-            const int bnd = tail->bidx[k];
-            const float4 bpv = bpw[bnd];
+            const float4 bpv = bpw[tail->bidx[k]];
             const float dv = fmaf(kf - bpv.z, bpv.y, (bpv.w - kf) * bpv.x);
             float rc, s, v;
             asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(dv));
             const float y = fabsf(x) * rc;
             asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(y));
             asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(v) : "f"(y * s));
-            const float big = v + 12582912.0f;            // nearest-even integer for v < 2^22
+            // signed magic-number rounding: nearest-even integer of +-v for v < 2^22, read from the mantissa
+            const float big = copysignf(v, x) + 12582912.0f;
             const float r = big - 12582912.0f;
-            // error budget of the f32 branch <= 6e-7 relative; stay 1e-6 v away from ties
-            const bool ok = (fabsf(v - r) < 0.5f - fmaf(1.0e-6f, v, 1.0e-7f)) && (v < 2.0e6f) && (dv > 0.0f);
-            int m = __float_as_int(big) - 0x4B400000;
-            m = (x < 0.0f) ? -m : m;
-            const bool past = (bnd == FRAD_NBANDS - 1);   // bins past the last ramp stay 0 (p1tools.py:37)
-            ms[u] = past ? 0 : m;
+            // error budget of the f32 branch <= 6e-7 relative: redo exactly when closer than 1e-6 v
+            // to a tie.  Inf / NaN (zero divisor) and v >= 5e5 fail this test by themselves.
+            allok = allok && (fmaf(1.0e-6f, v, fabsf(fabsf(v) - fabsf(r))) < 0.4999999f);
+            ms[u] = __float_as_int(big) - 0x4B400000;
             xs[u] = x;
-            amb |= (ok || past) ? 0u : (1u << u);
+          }
+          unsigned amb = 0;
+          if (!allok || force_exact) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+              const int k = kbase + 32 * u;
+              const float kf = kb + (float)(32 * u);
+              const float4 bpv = bpw[tail->bidx[k]];
+              const float dv = fmaf(kf - bpv.z, bpv.y, (bpv.w - kf) * bpv.x);
+              float rc, s, v;
+              asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(dv));
+              const float y = fabsf(xs[u]) * rc;
+              asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(y));
+              asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(v) : "f"(y * s));
+              const float r = (v + 12582912.0f) - 12582912.0f;
+              if (!(fmaf(1.0e-6f, v, fabsf(v - r)) < 0.4999999f)) amb |= 1u << u;
+            }
           }
           if (force_exact) amb = 0xffu;
 #pragma unroll
@@ -340,7 +373,7 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
   typedef typename vec2<T>::type V;
   typedef dec_layout<T> LY;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  smem_tail* tail = (smem_tail*)(smem_raw + (size_t)FW * LY::WARP_BYTES);
+  dec_tail* tail = (dec_tail*)(smem_raw + (size_t)FW * LY::WARP_BYTES);
   const int C = CT ? CT : P.C;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const tile_map tm = make_tiles(P.B, C);
@@ -350,7 +383,7 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
     if (tid <= FRAD_NBANDS) { const int e = P.bt->edge[tid]; tail->lo[tid] = (e < FN) ? e : FN; }
     if (sizeof(T) == 4) {
       const float inv = (float)(1.0 / P.scale);
-      for (int i = tid; i < DQ_TAB; i += FW * 32) { const float a = (float)i; tail->dq[i] = a * cbrtf(a) * inv; }
+      for (int i = tid; i < DQ_TAB; i += FW * 32) { const float a = (float)i; tail->aux[i] = a * cbrtf(a) * inv; }
     }
   }
   const int words_per_frame = FN * C;
@@ -411,7 +444,7 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
               const int qi = (int)raw[k];
               const int qa = abs(qi);
               float mag;
-              if (qa < DQ_TAB) mag = tail->dq[qa];
+              if (qa < DQ_TAB) mag = tail->aux[qa];
               else { const float af = (float)qa; mag = af * cbrtf(af) * (float)inv_scale; }
               const float a = (float)(k - lo);
               const float dv = fmaf(a, t1s, (nfl - a) * t0s);
@@ -566,7 +599,7 @@ int frad_launch_encode_2048(frad_ctx* ctx, const enc_params& P, const frad_plan*
   do {                                                                                                   \
     auto k = dec2048_kernel<TT, PROF, CT>;                                                               \
     int grid;                                                                                            \
-    const size_t smem = (size_t)FW * dec_layout<TT>::WARP_BYTES + sizeof(smem_tail);                     \
+    const size_t smem = (size_t)FW * dec_layout<TT>::WARP_BYTES + sizeof(dec_tail);                     \
     int rc = launch_cfg(ctx, k, smem, tm.ntiles, &grid);                                                 \
     if (rc) return rc;                                                                                   \
     k<<<grid, FW * 32, smem, ctx->stream>>>(P, plan_view(pl), (const typename vec2<TT>::type*)pl->tw32,  \
