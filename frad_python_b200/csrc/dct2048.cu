@@ -74,14 +74,21 @@ struct smem_tail {
   // encode: aux = per-warp, per-lane band energy partials [w][band][lane]; decode: aux = |q|^(4/3)/scale table
 };
 
-struct dec_tail {
+template <typename T> struct dec_tail {              // f32 flavour
   int lo[FRAD_NBANDS + 1];
-  double thr[FW][FRAD_NBANDS + 1];
-  float aux[DQ_TAB];                                  // |q|^(4/3) / scale for |q| < DQ_TAB (f32 path)
+  uint8_t bidx[FN];
+  float4 bp[FW][FRAD_NBANDS + 1];                     // t0 / n, t1 / n, lo, hi
+  float aux[DQ_TAB];                                  // |q|^(4/3) / scale for |q| < DQ_TAB
+};
+template <> struct dec_tail<double> {                 // f64 flavour: exact np.linspace ramp
+  int lo[FRAD_NBANDS + 1];
+  uint8_t bidx[FN];
+  double2 rp[FW][FRAD_NBANDS + 1];                    // start, step
 };
 
 // band index table shared by all warps of the CTA (same N and sample rate)
-__device__ __forceinline__ void build_bidx(smem_tail* tail, const band_table* bt, int tid) {
+template <typename TAIL>
+__device__ __forceinline__ void build_bidx(TAIL* tail, const band_table* bt, int tid) {
   if (tid <= FRAD_NBANDS) { const int e = bt->edge[tid]; tail->lo[tid] = (e < FN) ? e : FN; }
   __syncthreads();
   for (int k = tid; k < FN; k += FW * 32) {
@@ -363,27 +370,27 @@ __global__ void __launch_bounds__(FW * 32, FRAD_MINB) enc2048_kernel(enc_params 
 // ------------------------------------------------------------------------------------------------
 template <typename T> struct dec_layout {
   static constexpr int SEQ_BYTES = SEQ_CPX * 2 * (int)sizeof(T);
-  static constexpr int RAW_OFF = (sizeof(T) == 8) ? SEQ_BYTES : 0;       // f64: raw words live beside X
-  static constexpr int WARP_BYTES = SEQ_BYTES + ((sizeof(T) == 8) ? FN * 4 : 0);
+  static constexpr int RAW_OFF = 0;            // the raw 32-bit words are consumed into registers before the exchange
+  static constexpr int WARP_BYTES = SEQ_BYTES;
 };
 
 template <typename T, int PROFILE, int CT>
-__global__ void __launch_bounds__(FW * 32, (sizeof(T) == 8) ? 2 : FRAD_MINB)
+__global__ void __launch_bounds__(FW * 32, (sizeof(T) == 8) ? 3 : FRAD_MINB)
 dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restrict__ tw32, const double* __restrict__ dq64) {
   typedef typename vec2<T>::type V;
   typedef dec_layout<T> LY;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  dec_tail* tail = (dec_tail*)(smem_raw + (size_t)FW * LY::WARP_BYTES);
+  dec_tail<T>* tail = (dec_tail<T>*)(smem_raw + (size_t)FW * LY::WARP_BYTES);
   const int C = CT ? CT : P.C;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const tile_map tm = make_tiles(P.B, C);
   const V* ci = (const V*)pl.ci;
   const V* ei = (const V*)pl.ei;
+  const double inv_scale = 1.0 / P.scale;
   if (PROFILE == 1) {
-    if (tid <= FRAD_NBANDS) { const int e = P.bt->edge[tid]; tail->lo[tid] = (e < FN) ? e : FN; }
-    if (sizeof(T) == 4) {
-      const float inv = (float)(1.0 / P.scale);
-      for (int i = tid; i < DQ_TAB; i += FW * 32) { const float a = (float)i; tail->aux[i] = a * cbrtf(a) * inv; }
+    build_bidx(tail, P.bt, tid);
+    if constexpr (sizeof(T) == 4) {
+      for (int i = tid; i < DQ_TAB; i += FW * 32) { const float a = (float)i; tail->aux[i] = a * cbrtf(a) * (float)inv_scale; }
     }
   }
   const int words_per_frame = FN * C;
@@ -404,65 +411,61 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
       V* buf = (V*)mine;
       T* X = (T*)mine;
       const uint32_t* raw = (const uint32_t*)(mine + LY::RAW_OFF);
-      // ---- dequantise / unpack into X[k] (type T) ----
-      if (PROFILE == 0) {
-        for (int k = lane; k < FN; k += 32) {
-          uint32_t u = raw[k];
-          if (!P.le) u = __byte_perm(u, 0, 0x0123);
-          float fv = __uint_as_float(u);
-          if (!isfinite(fv)) fv = 0.0f;
-          X[k] = (T)fv;
-        }
-      } else {
+      // ---- per-band ramp parameters from the threshold integers (profile1.py:66, p1tools.py:35-41) ----
+      if (PROFILE == 1) {
         double thr = 0.0;
         if (lane < FRAD_NBANDS) {
           const double tv = (double)P.tq[((size_t)b * FRAD_NBANDS + lane) * C + c];
-          thr = pow(P.bt->base, copysign(pow(fabs(tv), 0.75), tv));        // profile1.py:66
+          thr = pow(P.bt->base, copysign(pow(fabs(tv), 0.75), tv));
         }
-        if (lane <= FRAD_NBANDS) tail->thr[w][lane] = thr;
-        __syncwarp();
-        const int last = tail->lo[FRAD_NBANDS - 1];
-        const double inv_scale = 1.0 / P.scale;
-        for (int bnd = 0; bnd < FRAD_NBANDS - 1; bnd++) {
-          const int lo = tail->lo[bnd], hi = tail->lo[bnd + 1];
-          const int n = hi - lo;
-          if (n <= 0) continue;
-          const double t0 = tail->thr[w][bnd], t1 = tail->thr[w][bnd + 1];
-          const double step = (t1 - t0) / (double)n;
-          if (sizeof(T) == 8) {
-            for (int k = lo + lane; k < hi; k += 32) {
-              const int qi = (int)raw[k];
-              const int qa = abs(qi);
-              const double mag = (qa < DQ_TAB64) ? __ldg(dq64 + qa) : pow((double)qa, 1.0 / 0.75);
-              const double coef = ((qi < 0) ? -mag : mag) * inv_scale;             // profile1.py:65
-              X[k] = (T)(coef * __dadd_rn(__dmul_rn((double)(k - lo), step), t0));
-            }
+        const double thr_next = __shfl_down_sync(0xffffffffu, thr, 1);
+        if (lane <= FRAD_NBANDS) {
+          const int n = (lane < FRAD_NBANDS - 1) ? tail->lo[lane + 1] - tail->lo[lane] : 0;
+          if constexpr (sizeof(T) == 8) {
+            tail->rp[w][lane] = (n > 0) ? make_double2(thr, (thr_next - thr) / (double)n) : make_double2(0.0, 0.0);
           } else {
-            const float nfl = (float)n;
-            const float t0s = (float)t0 / nfl, t1s = (float)t1 / nfl;
-            for (int k = lo + lane; k < hi; k += 32) {
-              const int qi = (int)raw[k];
-              const int qa = abs(qi);
-              float mag;
-              if (qa < DQ_TAB) mag = tail->aux[qa];
-              else { const float af = (float)qa; mag = af * cbrtf(af) * (float)inv_scale; }
-              const float a = (float)(k - lo);
-              const float dv = fmaf(a, t1s, (nfl - a) * t0s);
-              X[k] = (T)(((qi < 0) ? -mag : mag) * dv);
-            }
+            tail->bp[w][lane] = (n > 0) ? make_float4((float)(thr / n), (float)(thr_next / n), (float)tail->lo[lane],
+                                                      (float)tail->lo[lane + 1])
+                                        : make_float4(0.0f, 0.0f, 0.0f, 1.0f);
           }
         }
-        for (int k = last + lane; k < FN; k += 32) X[k] = (T)0;
+        __syncwarp();
       }
-      __syncwarp();
+      // value X[k] from the staged 32-bit word: profile 0 unpack + scrub, profile 1 dequantiser x ramp
+      auto coef = [&](int k, float kf) -> T {
+        const uint32_t u0 = raw[k];
+        if (PROFILE == 0) {
+          const uint32_t u = P.le ? u0 : __byte_perm(u0, 0, 0x0123);
+          const float fv = __uint_as_float(u);
+          return (T)(((u & 0x7f800000u) == 0x7f800000u) ? 0.0f : fv);          // NaN / Inf -> 0 (profile0.py:66)
+        } else {
+          const int qi = (int)u0;
+          const int qa = abs(qi);
+          const int bnd = tail->bidx[k];
+          if constexpr (sizeof(T) == 8) {
+            const double mag = (qa < DQ_TAB64) ? __ldg(dq64 + qa) : pow((double)qa, 1.0 / 0.75);
+            const double2 rp = tail->rp[w][bnd];
+            const double div = __dadd_rn(__dmul_rn((double)(k - tail->lo[bnd]), rp.y), rp.x);   // j * step + start
+            return (T)((((qi < 0) ? -mag : mag) * inv_scale) * div);
+          } else {
+            float mag;
+            if (qa < DQ_TAB) mag = tail->aux[qa];
+            else { const float af = (float)qa; mag = af * cbrtf(af) * (float)inv_scale; }
+            const float4 bpv = tail->bp[w][bnd];
+            const float dv = fmaf(kf - bpv.z, bpv.y, (bpv.w - kf) * bpv.x);
+            return (T)(((qi < 0) ? -mag : mag) * dv);
+          }
+        }
+      };
       // ---- pairwise pre-processing: R1 = X[k] - i X[N-k], R2 = (X[M-k] + i X[M+k]) e^{-i pi/4},
       //      S = ci (R1 + R2), G = ei ci (R1 - R2), Z[k] = S + iG, Z[M-k] = conj(S - iG) ----
       V z[32];
       V zm_keep[17];
       const T r2 = (T)FRAD_RSQRT2;
-      auto pre_pair = [&](int k, V& zk, V& zmk) {
-        const T xk = X[k], xnk = (k == 0) ? T(0) : X[FN - k];
-        const T a = X[FM - k], bb = X[FM + k];
+      const float lf = (float)lane;
+      auto pre_pair = [&](int k, float kf, V& zk, V& zmk) {
+        const T xk = coef(k, kf), xnk = (k == 0) ? T(0) : coef(FN - k, (float)FN - kf);
+        const T a = coef(FM - k, (float)FM - kf), bb = coef(FM + k, (float)FM + kf);
         const V R1 = mk2<T>(xk, -xnk);
         const V R2 = mk2<T>((a + bb) * r2, (bb - a) * r2);
         const V cik = __ldg(ci + k);
@@ -472,9 +475,9 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
         zmk = mk2<T>(S.x + G.y, -(S.y - G.x));          // conj(S - iG)
       };
 #pragma unroll
-      for (int o = 0; o < 16; o++) pre_pair(lane + 32 * o, z[o], zm_keep[o]);
+      for (int o = 0; o < 16; o++) pre_pair(lane + 32 * o, lf + (float)(32 * o), z[o], zm_keep[o]);
       zm_keep[16] = mk2<T>(T(0), T(0));
-      if (lane == 0) { V dummy; pre_pair(FM / 2, zm_keep[16], dummy); }      // Z[512] (self pair)
+      if (lane == 0) { V dummy; pre_pair(FM / 2, (float)(FM / 2), zm_keep[16], dummy); }      // Z[512] (self pair)
       __syncwarp();
       const int partner = (32 - lane) & 31;
 #pragma unroll
@@ -599,7 +602,7 @@ int frad_launch_encode_2048(frad_ctx* ctx, const enc_params& P, const frad_plan*
   do {                                                                                                   \
     auto k = dec2048_kernel<TT, PROF, CT>;                                                               \
     int grid;                                                                                            \
-    const size_t smem = (size_t)FW * dec_layout<TT>::WARP_BYTES + sizeof(dec_tail);                     \
+    const size_t smem = (size_t)FW * dec_layout<TT>::WARP_BYTES + sizeof(dec_tail<TT>);                     \
     int rc = launch_cfg(ctx, k, smem, tm.ntiles, &grid);                                                 \
     if (rc) return rc;                                                                                   \
     k<<<grid, FW * 32, smem, ctx->stream>>>(P, plan_view(pl), (const typename vec2<TT>::type*)pl->tw32,  \
