@@ -19,6 +19,70 @@ size_t rounded(size_t b) { return ((b + 255) & ~(size_t)255) + 256; }
   a.base = (char*)frad_scratch((ctx), 2, (total));                        \
   if (!a.base) return FRAD_E_NOMEM;
 
+// ---- pipelined transform entry points ---------------------------------------------------------------
+// The batch is cut into chunks of frames; H2D copies run on ctx->s_in, kernels on ctx->stream, D2H copies on
+// ctx->s_out, chained by events, so PCIe traffic in both directions overlaps the kernels (pinned host memory
+// makes the copies truly asynchronous; pageable memory still works, just without overlap).
+namespace {
+constexpr int kChunkFrames = 1024;
+
+struct pipeline {
+  frad_ctx* ctx; int nchunks; int chunk;
+  cudaEvent_t* in_done; cudaEvent_t* k_done;
+};
+
+int pipeline_begin(frad_ctx* ctx, int B, pipeline* p) {
+  p->ctx = ctx;
+  p->chunk = kChunkFrames;
+  p->nchunks = (B + p->chunk - 1) / p->chunk;
+  while ((int)ctx->pipe_events.size() < 2 * p->nchunks + 1) {
+    cudaEvent_t e;
+    FRAD_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->pipe_events.push_back(e);
+  }
+  p->in_done = ctx->pipe_events.data();
+  p->k_done = ctx->pipe_events.data() + p->nchunks;
+  // the copy streams must not run ahead of work already queued on the main stream (buffer reuse)
+  cudaEvent_t fence = ctx->pipe_events[2 * p->nchunks];
+  FRAD_CUDA(ctx, cudaEventRecord(fence, ctx->stream));
+  FRAD_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, fence, 0));
+  FRAD_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, fence, 0));
+  return FRAD_OK;
+}
+
+// h2d(i, f0, f1, stream), run(f0, f1) [enqueues on ctx->stream], d2h(f0, f1, stream)
+template <class H2D, class RUN, class D2H>
+int pipeline_run(pipeline& p, int B, bool needs_next_chunk, H2D h2d, RUN run, D2H d2h) {
+  frad_ctx* ctx = p.ctx;
+  int rc;
+  for (int i = 0; i < p.nchunks; i++) {
+    const int f0 = i * p.chunk, f1 = (f0 + p.chunk < B) ? f0 + p.chunk : B;
+    if ((rc = h2d(i, f0, f1, ctx->s_in))) return rc;
+    FRAD_CUDA(ctx, cudaEventRecord(p.in_done[i], ctx->s_in));
+  }
+  for (int i = 0; i < p.nchunks; i++) {
+    const int f0 = i * p.chunk, f1 = (f0 + p.chunk < B) ? f0 + p.chunk : B;
+    FRAD_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, p.in_done[i], 0));
+    if (needs_next_chunk && i + 1 < p.nchunks) FRAD_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, p.in_done[i + 1], 0));
+    if ((rc = run(f0, f1))) return rc;
+    FRAD_CUDA(ctx, cudaEventRecord(p.k_done[i], ctx->stream));
+    FRAD_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, p.k_done[i], 0));
+    if ((rc = d2h(f0, f1, ctx->s_out))) return rc;
+  }
+  FRAD_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
+  FRAD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return FRAD_OK;
+}
+
+inline int copy_async(frad_ctx* ctx, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t s) {
+  if (bytes) FRAD_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, kind, s));
+  return FRAD_OK;
+}
+}  // namespace
+
+#define H2D_ cudaMemcpyHostToDevice
+#define D2H_ cudaMemcpyDeviceToHost
+
 extern "C" int frad_p0_encode(frad_ctx* ctx, const void* pcm, int pcm_dtype, int64_t hop, int B, int N, int C,
                               int bits, int little_endian, int prec,
                               uint8_t* payload, size_t payload_stride, double* peak, uint32_t* crc32) {
@@ -26,25 +90,40 @@ extern "C" int frad_p0_encode(frad_ctx* ctx, const void* pcm, int pcm_dtype, int
   const int es = frad_dtype_size(pcm_dtype);
   if (!es || B < 0 || N < 1 || C < 1 || hop < 0) return frad_fail(ctx, FRAD_E_ARG, "frad_p0_encode: bad argument");
   if (B == 0) return FRAD_OK;
-  const size_t in_bytes = ((size_t)(B - 1) * (size_t)hop + (size_t)N) * C * es;
+  FRAD_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t samp = (size_t)C * es;                                  // bytes per multichannel sample
+  const size_t in_bytes = ((size_t)(B - 1) * (size_t)hop + (size_t)N) * samp;
   const size_t out_bytes = (size_t)B * payload_stride;
   ARENA(ctx, a, rounded(in_bytes) + rounded(out_bytes) + rounded(8 * (size_t)B) + rounded(4 * (size_t)B));
-  void* d_in = take(a, in_bytes);
+  char* d_in = (char*)take(a, in_bytes);
   uint8_t* d_out = (uint8_t*)take(a, out_bytes);
   double* d_peak = (double*)take(a, 8 * (size_t)B);
   uint32_t* d_crc = (uint32_t*)take(a, 4 * (size_t)B);
   if (a.bad) return frad_fail(ctx, FRAD_E_NOMEM, "internal arena overflow");
-  int rc;
-  if ((rc = frad_h2d(ctx, d_in, pcm, in_bytes))) return rc;
-  if ((rc = frad_p0_encode_dev(ctx, d_in, pcm_dtype, hop, B, N, C, bits, little_endian, prec, d_out, payload_stride, d_peak))) return rc;
-  if (crc32) {
-    const size_t used = frad_p0_payload_bytes(N, C, bits);
-    if ((rc = frad_crc32_dev(ctx, d_out, nullptr, nullptr, payload_stride, (uint32_t)used, B, d_crc))) return rc;
-    if ((rc = frad_d2h(ctx, crc32, d_crc, 4 * (size_t)B))) return rc;
-  }
-  if ((rc = frad_d2h(ctx, payload, d_out, out_bytes))) return rc;
-  if (peak && (rc = frad_d2h(ctx, peak, d_peak, 8 * (size_t)B))) return rc;
-  return frad_sync(ctx);
+  const size_t used = frad_p0_payload_bytes(N, C, bits);
+  pipeline p;
+  int rc = pipeline_begin(ctx, B, &p);
+  if (rc) return rc;
+  return pipeline_run(p, B, hop < N,
+    [&](int, int f0, int f1, cudaStream_t s) {
+      const size_t lo = (size_t)f0 * hop * samp;
+      const size_t hi = (f1 == B) ? in_bytes : (size_t)f1 * hop * samp;
+      return copy_async(ctx, d_in + lo, (const char*)pcm + lo, hi - lo, H2D_, s);
+    },
+    [&](int f0, int f1) {
+      int r = frad_p0_encode_dev(ctx, d_in + (size_t)f0 * hop * samp, pcm_dtype, hop, f1 - f0, N, C, bits, little_endian, prec,
+                                 d_out + (size_t)f0 * payload_stride, payload_stride, d_peak + f0);
+      if (!r && crc32) r = frad_crc32_dev(ctx, d_out + (size_t)f0 * payload_stride, nullptr, nullptr, payload_stride,
+                                          (uint32_t)used, f1 - f0, d_crc + f0);
+      return r;
+    },
+    [&](int f0, int f1, cudaStream_t s) {
+      int r = copy_async(ctx, payload + (size_t)f0 * payload_stride, d_out + (size_t)f0 * payload_stride,
+                         (size_t)(f1 - f0) * payload_stride, D2H_, s);
+      if (!r && peak) r = copy_async(ctx, peak + f0, d_peak + f0, 8 * (size_t)(f1 - f0), D2H_, s);
+      if (!r && crc32) r = copy_async(ctx, crc32 + f0, d_crc + f0, 4 * (size_t)(f1 - f0), D2H_, s);
+      return r;
+    });
 }
 
 extern "C" int frad_p0_decode(frad_ctx* ctx, const uint8_t* payload, size_t payload_stride, int B, int N, int C,
@@ -53,17 +132,28 @@ extern "C" int frad_p0_decode(frad_ctx* ctx, const uint8_t* payload, size_t payl
   const int es = frad_dtype_size(pcm_dtype);
   if (!es || B < 0 || N < 1 || C < 1) return frad_fail(ctx, FRAD_E_ARG, "frad_p0_decode: bad argument");
   if (B == 0) return FRAD_OK;
+  FRAD_CUDA(ctx, cudaSetDevice(ctx->device));
   const size_t in_bytes = (size_t)B * payload_stride;
-  const size_t out_bytes = (size_t)B * N * C * es;
-  ARENA(ctx, a, rounded(in_bytes) + rounded(out_bytes));
+  const size_t fbytes = (size_t)N * C * es;
+  ARENA(ctx, a, rounded(in_bytes) + rounded((size_t)B * fbytes));
   uint8_t* d_in = (uint8_t*)take(a, in_bytes);
-  void* d_out = take(a, out_bytes);
+  char* d_out = (char*)take(a, (size_t)B * fbytes);
   if (a.bad) return frad_fail(ctx, FRAD_E_NOMEM, "internal arena overflow");
-  int rc;
-  if ((rc = frad_h2d(ctx, d_in, payload, in_bytes))) return rc;
-  if ((rc = frad_p0_decode_dev(ctx, d_in, payload_stride, B, N, C, bits, little_endian, prec, d_out, pcm_dtype))) return rc;
-  if ((rc = frad_d2h(ctx, pcm, d_out, out_bytes))) return rc;
-  return frad_sync(ctx);
+  pipeline p;
+  int rc = pipeline_begin(ctx, B, &p);
+  if (rc) return rc;
+  return pipeline_run(p, B, false,
+    [&](int, int f0, int f1, cudaStream_t s) {
+      return copy_async(ctx, d_in + (size_t)f0 * payload_stride, payload + (size_t)f0 * payload_stride,
+                        (size_t)(f1 - f0) * payload_stride, H2D_, s);
+    },
+    [&](int f0, int f1) {
+      return frad_p0_decode_dev(ctx, d_in + (size_t)f0 * payload_stride, payload_stride, f1 - f0, N, C, bits, little_endian,
+                                prec, d_out + (size_t)f0 * fbytes, pcm_dtype);
+    },
+    [&](int f0, int f1, cudaStream_t s) {
+      return copy_async(ctx, (char*)pcm + (size_t)f0 * fbytes, d_out + (size_t)f0 * fbytes, (size_t)(f1 - f0) * fbytes, D2H_, s);
+    });
 }
 
 extern "C" int frad_p1_encode(frad_ctx* ctx, const void* pcm, int pcm_dtype, int64_t hop, int B, int N, int C,
@@ -73,21 +163,36 @@ extern "C" int frad_p1_encode(frad_ctx* ctx, const void* pcm, int pcm_dtype, int
   const int es = frad_dtype_size(pcm_dtype);
   if (!es || B < 0 || N < 1 || C < 1 || hop < 0) return frad_fail(ctx, FRAD_E_ARG, "frad_p1_encode: bad argument");
   if (B == 0) return FRAD_OK;
-  const size_t in_bytes = ((size_t)(B - 1) * (size_t)hop + (size_t)N) * C * es;
-  const size_t q_bytes = (size_t)B * N * C * 4, tq_bytes = (size_t)B * FRAD_NBANDS * C * 4, l_bytes = (size_t)B * FRAD_LPC_LEN * C * 4;
-  ARENA(ctx, a, rounded(in_bytes) + rounded(q_bytes) + rounded(tq_bytes) + rounded(l_bytes));
-  void* d_in = take(a, in_bytes);
-  int32_t* d_q = (int32_t*)take(a, q_bytes);
-  int32_t* d_tq = (int32_t*)take(a, tq_bytes);
-  int32_t* d_l = lpc ? (int32_t*)take(a, l_bytes) : nullptr;
+  FRAD_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t samp = (size_t)C * es;
+  const size_t in_bytes = ((size_t)(B - 1) * (size_t)hop + (size_t)N) * samp;
+  const size_t qf = (size_t)N * C, tf = (size_t)FRAD_NBANDS * C, lf = (size_t)FRAD_LPC_LEN * C;   // ints per frame
+  ARENA(ctx, a, rounded(in_bytes) + rounded(4 * qf * B) + rounded(4 * tf * B) + rounded(4 * lf * B));
+  char* d_in = (char*)take(a, in_bytes);
+  int32_t* d_q = (int32_t*)take(a, 4 * qf * B);
+  int32_t* d_tq = (int32_t*)take(a, 4 * tf * B);
+  int32_t* d_l = lpc ? (int32_t*)take(a, 4 * lf * B) : nullptr;
   if (a.bad) return frad_fail(ctx, FRAD_E_NOMEM, "internal arena overflow");
-  int rc;
-  if ((rc = frad_h2d(ctx, d_in, pcm, in_bytes))) return rc;
-  if ((rc = frad_p1_encode_dev(ctx, d_in, pcm_dtype, hop, B, N, C, bits, srate, loss_level, prec, d_q, d_tq, d_l))) return rc;
-  if ((rc = frad_d2h(ctx, q, d_q, q_bytes))) return rc;
-  if ((rc = frad_d2h(ctx, tq, d_tq, tq_bytes))) return rc;
-  if (lpc && (rc = frad_d2h(ctx, lpc, d_l, l_bytes))) return rc;
-  return frad_sync(ctx);
+  pipeline p;
+  int rc = pipeline_begin(ctx, B, &p);
+  if (rc) return rc;
+  return pipeline_run(p, B, hop < N,
+    [&](int, int f0, int f1, cudaStream_t s) {
+      const size_t lo = (size_t)f0 * hop * samp;
+      const size_t hi = (f1 == B) ? in_bytes : (size_t)f1 * hop * samp;
+      return copy_async(ctx, d_in + lo, (const char*)pcm + lo, hi - lo, H2D_, s);
+    },
+    [&](int f0, int f1) {
+      return frad_p1_encode_dev(ctx, d_in + (size_t)f0 * hop * samp, pcm_dtype, hop, f1 - f0, N, C, bits, srate, loss_level,
+                                prec, d_q + f0 * qf, d_tq + f0 * tf, d_l ? d_l + f0 * lf : nullptr);
+    },
+    [&](int f0, int f1, cudaStream_t s) {
+      const size_t nfr = (size_t)(f1 - f0);
+      int r = copy_async(ctx, q + f0 * qf, d_q + f0 * qf, 4 * qf * nfr, D2H_, s);
+      if (!r) r = copy_async(ctx, tq + f0 * tf, d_tq + f0 * tf, 4 * tf * nfr, D2H_, s);
+      if (!r && lpc) r = copy_async(ctx, lpc + f0 * lf, d_l + f0 * lf, 4 * lf * nfr, D2H_, s);
+      return r;
+    });
 }
 
 extern "C" int frad_p1_decode(frad_ctx* ctx, const int32_t* q, const int32_t* tq, const int32_t* lpc,
@@ -96,21 +201,33 @@ extern "C" int frad_p1_decode(frad_ctx* ctx, const int32_t* q, const int32_t* tq
   const int es = frad_dtype_size(pcm_dtype);
   if (!es || B < 0 || N < 1 || C < 1) return frad_fail(ctx, FRAD_E_ARG, "frad_p1_decode: bad argument");
   if (B == 0) return FRAD_OK;
-  const size_t q_bytes = (size_t)B * N * C * 4, tq_bytes = (size_t)B * FRAD_NBANDS * C * 4, l_bytes = (size_t)B * FRAD_LPC_LEN * C * 4;
-  const size_t out_bytes = (size_t)B * N * C * es;
-  ARENA(ctx, a, rounded(out_bytes) + rounded(q_bytes) + rounded(tq_bytes) + rounded(l_bytes));
-  int32_t* d_q = (int32_t*)take(a, q_bytes);
-  int32_t* d_tq = (int32_t*)take(a, tq_bytes);
-  int32_t* d_l = lpc ? (int32_t*)take(a, l_bytes) : nullptr;
-  void* d_out = take(a, out_bytes);
+  FRAD_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t qf = (size_t)N * C, tf = (size_t)FRAD_NBANDS * C, lf = (size_t)FRAD_LPC_LEN * C;
+  const size_t fbytes = qf * es;
+  ARENA(ctx, a, rounded(fbytes * B) + rounded(4 * qf * B) + rounded(4 * tf * B) + rounded(4 * lf * B));
+  int32_t* d_q = (int32_t*)take(a, 4 * qf * B);
+  int32_t* d_tq = (int32_t*)take(a, 4 * tf * B);
+  int32_t* d_l = lpc ? (int32_t*)take(a, 4 * lf * B) : nullptr;
+  char* d_out = (char*)take(a, fbytes * B);
   if (a.bad) return frad_fail(ctx, FRAD_E_NOMEM, "internal arena overflow");
-  int rc;
-  if ((rc = frad_h2d(ctx, d_q, q, q_bytes))) return rc;
-  if ((rc = frad_h2d(ctx, d_tq, tq, tq_bytes))) return rc;
-  if (lpc && (rc = frad_h2d(ctx, d_l, lpc, l_bytes))) return rc;
-  if ((rc = frad_p1_decode_dev(ctx, d_q, d_tq, d_l, B, N, C, bits, srate, prec, d_out, pcm_dtype))) return rc;
-  if ((rc = frad_d2h(ctx, pcm, d_out, out_bytes))) return rc;
-  return frad_sync(ctx);
+  pipeline p;
+  int rc = pipeline_begin(ctx, B, &p);
+  if (rc) return rc;
+  return pipeline_run(p, B, false,
+    [&](int, int f0, int f1, cudaStream_t s) {
+      const size_t nfr = (size_t)(f1 - f0);
+      int r = copy_async(ctx, d_q + f0 * qf, q + f0 * qf, 4 * qf * nfr, H2D_, s);
+      if (!r) r = copy_async(ctx, d_tq + f0 * tf, tq + f0 * tf, 4 * tf * nfr, H2D_, s);
+      if (!r && lpc) r = copy_async(ctx, d_l + f0 * lf, lpc + f0 * lf, 4 * lf * nfr, H2D_, s);
+      return r;
+    },
+    [&](int f0, int f1) {
+      return frad_p1_decode_dev(ctx, d_q + f0 * qf, d_tq + f0 * tf, d_l ? d_l + f0 * lf : nullptr, f1 - f0, N, C, bits, srate,
+                                prec, d_out + (size_t)f0 * fbytes, pcm_dtype);
+    },
+    [&](int f0, int f1, cudaStream_t s) {
+      return copy_async(ctx, (char*)pcm + (size_t)f0 * fbytes, d_out + (size_t)f0 * fbytes, (size_t)(f1 - f0) * fbytes, D2H_, s);
+    });
 }
 
 // ---- CRC / RS over host buffers ----------------------------------------------------------------

@@ -19,6 +19,8 @@ struct frad_ctx {
   int sm_count = 0;
   size_t smem_optin = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t s_in = nullptr, s_out = nullptr;   // copy streams of the pipelined host-pointer entry points
+  std::vector<cudaEvent_t> pipe_events;
   std::string err;
   uint64_t launches = 0;
   cudaEvent_t events[FRAD_NEVENTS] = {};

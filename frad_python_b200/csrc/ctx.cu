@@ -34,6 +34,8 @@ extern "C" int frad_ctx_create(int device, frad_ctx** out) {
   ctx->sm_count = prop.multiProcessorCount;
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
   for (int i = 0; i < FRAD_NEVENTS; i++) cudaEventCreate(&ctx->events[i]);
+  cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking);
   *out = ctx;
   return FRAD_OK;
 }
@@ -49,6 +51,9 @@ extern "C" void frad_ctx_destroy(frad_ctx* ctx) {
   if (ctx->dequant_table) cudaFree(ctx->dequant_table);
   for (int i = 0; i < 8; i++) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
   for (int i = 0; i < FRAD_NEVENTS; i++) if (ctx->events[i]) cudaEventDestroy(ctx->events[i]);
+  for (auto e : ctx->pipe_events) cudaEventDestroy(e);
+  if (ctx->s_in) { cudaStreamSynchronize(ctx->s_in); cudaStreamDestroy(ctx->s_in); }
+  if (ctx->s_out) { cudaStreamSynchronize(ctx->s_out); cudaStreamDestroy(ctx->s_out); }
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -126,6 +131,8 @@ void* frad_scratch(frad_ctx* ctx, int slot, size_t bytes) {
   if (bytes <= ctx->scratch_cap[slot] && ctx->scratch[slot]) return ctx->scratch[slot];
   if (ctx->scratch[slot]) {
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->s_in) cudaStreamSynchronize(ctx->s_in);
+    if (ctx->s_out) cudaStreamSynchronize(ctx->s_out);
     cudaFree(ctx->scratch[slot]);
     ctx->scratch[slot] = nullptr;
     ctx->scratch_cap[slot] = 0;
