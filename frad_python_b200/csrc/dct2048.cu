@@ -55,16 +55,6 @@ __device__ __forceinline__ float transpose_reduce32(float* part, int lane) {
   return part[0];
 }
 
-struct tile_map { int fpc, active, ntiles; };
-
-__host__ __device__ inline tile_map make_tiles(int B, int C) {
-  tile_map t;
-  t.fpc = FW / C; if (t.fpc < 1) t.fpc = 1;
-  t.active = t.fpc * C;
-  t.ntiles = (B + t.fpc - 1) / t.fpc;
-  return t;
-}
-
 struct smem_tail {
   int lo[FRAD_NBANDS + 1];
   double thr[FW][FRAD_NBANDS + 1];
@@ -100,49 +90,59 @@ __device__ __forceinline__ void build_bidx(TAIL* tail, const band_table* bt, int
 }
 
 // ---- cooperative staging helpers ----------------------------------------------------------------
-// Frame words (32-bit) are interleaved [i][c]; word e = i*C + c goes to / comes from per-sequence
-// buffer (f*C + c) at word position POS(i).  CT == 2 is unrolled with linear addressing.
+// Frame words (32-bit) are interleaved [i][c].  A tile is a set of whole sequences that fit the CTA's
+// FW warps; CT selects how it is cut (all variants move 16 bytes per thread per step, fully coalesced):
+//   CT == 1  mono: FW frames per tile, a float4 is 4 consecutive samples of the one channel
+//   CT == 2  stereo: FW/2 frames per tile, a float4 is 2 samples x 2 channels
+//   CT == 4  C % 4 == 0: one frame x one group of 4 channels per tile, a float4 is 1 sample x 4 channels
+//   CT == 0  any C <= FW: FW/C frames per tile, element index split by a run-time division
+struct tile_map { int fpc, groups, ntiles; };
+
+template <int CT>
+__host__ __device__ inline tile_map make_tiles(int B, int C) {
+  tile_map t;
+  if (CT == 4) { t.fpc = 1; t.groups = C / 4; t.ntiles = B * t.groups; return t; }
+  t.fpc = FW / C; if (t.fpc < 1) t.fpc = 1;
+  t.groups = 1;
+  t.ntiles = (B + t.fpc - 1) / t.fpc;
+  return t;
+}
+
+template <int CT> __device__ __forceinline__ int vec_count(int C) { return (CT == 4) ? FN : FN * C / 4; }
+// 32-bit word offset inside the frame of vector step e4 (group g of 4 channels for CT == 4)
+template <int CT> __device__ __forceinline__ int vec_word(int e4, int C, int g) { return (CT == 4) ? e4 * C + 4 * g : 4 * e4; }
+// element j (0..3) of vector step e4 -> sample / bin index i and sequence slot s inside the tile
+template <int CT> __device__ __forceinline__ void vec_elem(int e4, int j, int C, int f, int& i, int& s) {
+  if (CT == 2) { i = 2 * e4 + (j >> 1); s = 2 * f + (j & 1); }
+  else if (CT == 1) { i = 4 * e4 + j; s = f; }
+  else if (CT == 4) { i = e4; s = j; }
+  else { const int e = 4 * e4 + j; i = e / C; s = f * C + (e - i * C); }
+}
+
 template <int CT, int STRIDE_WORDS, typename POS>
-__device__ __forceinline__ void scatter_frame(const uint4* __restrict__ src, uint32_t* seq_base, int C, int f, int tid, POS pos) {
-  const int words = FN * C;
-  if (CT == 2) {
+__device__ __forceinline__ void scatter_frame(const uint32_t* __restrict__ frame, uint32_t* seq_base, int C, int f, int g,
+                                              int tid, POS pos) {
+  const int cnt = vec_count<CT>(C);
+#pragma unroll 4
+  for (int e4 = tid; e4 < cnt; e4 += FW * 32) {
+    const uint4 x = __ldg((const uint4*)(frame + vec_word<CT>(e4, C, g)));
+    const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-    for (int it = 0; it < FN * 2 / 4 / (FW * 32); it++) {
-      const int e4 = tid + it * FW * 32;
-      const uint4 x = __ldg(src + e4);
-      uint32_t* s0 = seq_base + (size_t)(f * 2) * STRIDE_WORDS;
-      uint32_t* s1 = s0 + STRIDE_WORDS;
-      const int p0 = pos(2 * e4), p1 = pos(2 * e4 + 1);
-      s0[p0] = x.x; s1[p0] = x.y; s0[p1] = x.z; s1[p1] = x.w;
-    }
-  } else {
-    for (int e4 = tid; e4 < words / 4; e4 += FW * 32) {
-      const uint4 x = __ldg(src + e4);
-      const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const int e = 4 * e4 + j;
-        const int i = e / C, c = e - i * C;
-        (seq_base + (size_t)(f * C + c) * STRIDE_WORDS)[pos(i)] = xs[j];
-      }
+    for (int j = 0; j < 4; j++) {
+      int i, sq;
+      vec_elem<CT>(e4, j, C, f, i, sq);
+      (seq_base + (size_t)sq * STRIDE_WORDS)[pos(i)] = xs[j];
     }
   }
 }
 
 template <int CT, int STRIDE_WORDS, typename W, typename O, typename POS, typename CVT>
 __device__ __forceinline__ void gather4(const W* seq_base, int C, int f, int e4, POS pos, CVT cvt, O* o4) {
-  if (CT == 2) {
-    const W* s0 = seq_base + (size_t)(f * 2) * STRIDE_WORDS;
-    const W* s1 = s0 + STRIDE_WORDS;
-    const int p0 = pos(2 * e4), p1 = pos(2 * e4 + 1);
-    o4[0] = cvt(s0[p0]); o4[1] = cvt(s1[p0]); o4[2] = cvt(s0[p1]); o4[3] = cvt(s1[p1]);
-  } else {
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const int e = 4 * e4 + j;
-      const int i = e / C, c = e - i * C;
-      o4[j] = cvt((seq_base + (size_t)(f * C + c) * STRIDE_WORDS)[pos(i)]);
-    }
+  for (int j = 0; j < 4; j++) {
+    int i, sq;
+    vec_elem<CT>(e4, j, C, f, i, sq);
+    o4[j] = cvt((seq_base + (size_t)sq * STRIDE_WORDS)[pos(i)]);
   }
 }
 
@@ -166,9 +166,9 @@ __global__ void __launch_bounds__(FW * 32, FRAD_MINB) enc2048_kernel(enc_params 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2* seq_all = (float2*)smem_raw;
   smem_tail* tail = (smem_tail*)(smem_raw + (size_t)FW * SEQ_CPX * sizeof(float2));
-  const int C = CT ? CT : P.C;
+  const int C = (CT == 1 || CT == 2) ? CT : P.C;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const tile_map tm = make_tiles(P.B, C);
+  const tile_map tm = make_tiles<CT>(P.B, C);
   const float* pcm = (const float*)P.pcm;
   const float2* cfh = (const float2*)pl.cfh;
   const float2* dfh = (const float2*)pl.dfh;
@@ -176,15 +176,17 @@ __global__ void __launch_bounds__(FW * 32, FRAD_MINB) enc2048_kernel(enc_params 
   const int words_per_frame = FN * C;
 
   for (int tile = blockIdx.x; tile < tm.ntiles; tile += gridDim.x) {
-    const int b0 = tile * tm.fpc;
+    const int b0 = (CT == 4) ? tile / tm.groups : tile * tm.fpc;
+    const int grp = (CT == 4) ? tile - b0 * tm.groups : 0;
     const int nf = min(tm.fpc, P.B - b0);
+    const int nseq = (CT == 4) ? 4 : nf * C;              // sequences (= busy warps) in this tile
     __syncthreads();                                      // previous tile fully stored before restaging
     for (int f = 0; f < nf; f++)
-      scatter_frame<CT, SEQ_CPX * 2>((const uint4*)(pcm + (size_t)(b0 + f) * P.hop * C), (uint32_t*)seq_all, C, f, tid,
+      scatter_frame<CT, SEQ_CPX * 2>((const uint32_t*)(pcm + (size_t)(b0 + f) * P.hop * C), (uint32_t*)seq_all, C, f, grp, tid,
                                      [](int n) { return zword(n); });
     __syncthreads();
-    if (w < nf * C) {
-      const int f = w / C, c = w - f * C, b = b0 + f;
+    if (w < nseq) {
+      const int f = (CT == 4) ? 0 : w / C, c = (CT == 4) ? 4 * grp + w : w - f * C, b = b0 + f;
       float2* buf = seq_all + (size_t)w * SEQ_CPX;
       float* X = (float*)buf;
       float2 v[32];
@@ -354,12 +356,12 @@ __global__ void __launch_bounds__(FW * 32, FRAD_MINB) enc2048_kernel(enc_params 
     __syncthreads();
     // ---- cooperative, coalesced store: word e = k*C + c of frame f <- seq[f*C + c][k] ----
     for (int f = 0; f < nf; f++) {
-      uint4* dst = (PROFILE == 0) ? (uint4*)(P.payload + (size_t)(b0 + f) * P.payload_stride)
-                                  : (uint4*)(P.q + (size_t)(b0 + f) * words_per_frame);
-      for (int e4 = tid; e4 < words_per_frame / 4; e4 += FW * 32) {
+      uint32_t* dst = (PROFILE == 0) ? (uint32_t*)(P.payload + (size_t)(b0 + f) * P.payload_stride)
+                                     : (uint32_t*)(P.q + (size_t)(b0 + f) * words_per_frame);
+      for (int e4 = tid; e4 < vec_count<CT>(C); e4 += FW * 32) {
         uint32_t o4[4];
         gather4<CT, SEQ_CPX * 2>((const uint32_t*)seq_all, C, f, e4, [](int k) { return k; }, [](uint32_t u) { return u; }, o4);
-        dst[e4] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+        *(uint4*)(dst + vec_word<CT>(e4, C, grp)) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
       }
     }
   }
@@ -381,9 +383,9 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
   typedef dec_layout<T> LY;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   dec_tail<T>* tail = (dec_tail<T>*)(smem_raw + (size_t)FW * LY::WARP_BYTES);
-  const int C = CT ? CT : P.C;
+  const int C = (CT == 1 || CT == 2) ? CT : P.C;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const tile_map tm = make_tiles(P.B, C);
+  const tile_map tm = make_tiles<CT>(P.B, C);
   const V* ci = (const V*)pl.ci;
   const V* ei = (const V*)pl.ei;
   const double inv_scale = 1.0 / P.scale;
@@ -396,17 +398,19 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
   const int words_per_frame = FN * C;
 
   for (int tile = blockIdx.x; tile < tm.ntiles; tile += gridDim.x) {
-    const int b0 = tile * tm.fpc;
+    const int b0 = (CT == 4) ? tile / tm.groups : tile * tm.fpc;
+    const int grp = (CT == 4) ? tile - b0 * tm.groups : 0;
     const int nf = min(tm.fpc, P.B - b0);
+    const int nseq = (CT == 4) ? 4 : nf * C;
     __syncthreads();
     for (int f = 0; f < nf; f++) {
-      const uint4* src = (PROFILE == 0) ? (const uint4*)(P.payload + (size_t)(b0 + f) * P.payload_stride)
-                                        : (const uint4*)(P.q + (size_t)(b0 + f) * words_per_frame);
-      scatter_frame<CT, LY::WARP_BYTES / 4>(src, (uint32_t*)(smem_raw + LY::RAW_OFF), C, f, tid, [](int k) { return k; });
+      const uint32_t* src = (PROFILE == 0) ? (const uint32_t*)(P.payload + (size_t)(b0 + f) * P.payload_stride)
+                                           : (const uint32_t*)(P.q + (size_t)(b0 + f) * words_per_frame);
+      scatter_frame<CT, LY::WARP_BYTES / 4>(src, (uint32_t*)(smem_raw + LY::RAW_OFF), C, f, grp, tid, [](int k) { return k; });
     }
     __syncthreads();
-    if (w < nf * C) {
-      const int f = w / C, c = w - f * C, b = b0 + f;
+    if (w < nseq) {
+      const int f = (CT == 4) ? 0 : w / C, c = (CT == 4) ? 4 * grp + w : w - f * C, b = b0 + f;
       unsigned char* mine = smem_raw + (size_t)w * LY::WARP_BYTES;
       V* buf = (V*)mine;
       T* X = (T*)mine;
@@ -509,19 +513,20 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
     // ---- cooperative, coalesced store of PCM [n][c] ----
     for (int f = 0; f < nf; f++) {
       const size_t fbase = (size_t)(b0 + f) * words_per_frame;
-      for (int e4 = tid; e4 < words_per_frame / 4; e4 += FW * 32) {
+      for (int e4 = tid; e4 < vec_count<CT>(C); e4 += FW * 32) {
+        const size_t woff = fbase + (size_t)vec_word<CT>(e4, C, grp);
         if (P.pcm_dtype == FRAD_F64) {
           double o4[4];
           gather4<CT, LY::WARP_BYTES / (int)sizeof(T)>((const T*)smem_raw, C, f, e4, [](int n) { return swz(n); },
                                                        [](T x) { return (double)x; }, o4);
-          double2* dst = (double2*)((double*)P.pcm + fbase) + 2 * (size_t)e4;
+          double2* dst = (double2*)((double*)P.pcm + woff);
           dst[0] = make_double2(o4[0], o4[1]);
           dst[1] = make_double2(o4[2], o4[3]);
         } else {
           float o4[4];
           gather4<CT, LY::WARP_BYTES / (int)sizeof(T)>((const T*)smem_raw, C, f, e4, [](int n) { return swz(n); },
                                                        [](T x) { return (float)x; }, o4);
-          *((float4*)((float*)P.pcm + fbase) + e4) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+          *(float4*)((float*)P.pcm + woff) = make_float4(o4[0], o4[1], o4[2], o4[3]);
         }
       }
     }
@@ -559,7 +564,7 @@ int ensure_dq64(frad_ctx* ctx) {
 // eligibility checks shared with transform.cu
 bool frad_fast2048_encode_ok(const enc_params& P, int prec) {
   if (P.N != FN || prec != FRAD_PREC_F32 || P.pcm_dtype != FRAD_F32) return false;
-  if (P.C > FW) return false;
+  if (P.C > FW && (P.C % 4) != 0) return false;
   if (P.profile == 0 && (P.bits != 32 || (P.payload_stride % 16) != 0 || ((uintptr_t)P.payload % 16) != 0)) return false;
   if (P.profile == 2) return false;
   if (P.profile == 1 && ((uintptr_t)P.q % 16) != 0) return false;
@@ -568,7 +573,7 @@ bool frad_fast2048_encode_ok(const enc_params& P, int prec) {
 }
 bool frad_fast2048_decode_ok(const dec_params& P, int prec) {
   (void)prec;
-  if (P.N != FN || P.C > FW) return false;
+  if (P.N != FN || (P.C > FW && (P.C % 4) != 0)) return false;
   if (P.profile == 0 && (P.bits != 32 || (P.payload_stride % 16) != 0 || ((uintptr_t)P.payload % 16) != 0)) return false;
   if (P.profile == 2) return false;
   if (P.profile == 1 && ((uintptr_t)P.q % 16) != 0) return false;
@@ -579,6 +584,7 @@ bool frad_fast2048_decode_ok(const dec_params& P, int prec) {
 #define ENC_DISPATCH(PROF, CT)                                                                         \
   do {                                                                                                 \
     auto k = enc2048_kernel<PROF, CT>;                                                                 \
+    const tile_map tm = make_tiles<CT>(P.B, P.C);                                                      \
     int grid;                                                                                          \
     int rc = launch_cfg(ctx, k, smem, tm.ntiles, &grid);                                               \
     if (rc) return rc;                                                                                 \
@@ -587,13 +593,13 @@ bool frad_fast2048_decode_ok(const dec_params& P, int prec) {
 
 int frad_launch_encode_2048(frad_ctx* ctx, const enc_params& P, const frad_plan* pl, int prec, int force_exact) {
   (void)prec;
-  const tile_map tm = make_tiles(P.B, P.C);
   const size_t smem = (size_t)FW * SEQ_CPX * sizeof(float2) + sizeof(smem_tail);
-  if (P.profile == 0) {
-    if (P.C == 2) ENC_DISPATCH(0, 2); else ENC_DISPATCH(0, 0);
-  } else {
-    if (P.C == 2) ENC_DISPATCH(1, 2); else ENC_DISPATCH(1, 0);
-  }
+#define ENC_BY_C(PROF)                                                                                \
+  do {                                                                                                \
+    if (P.C == 2) ENC_DISPATCH(PROF, 2); else if (P.C == 1) ENC_DISPATCH(PROF, 1);                    \
+    else if (P.C % 4 == 0) ENC_DISPATCH(PROF, 4); else ENC_DISPATCH(PROF, 0);                         \
+  } while (0)
+  if (P.profile == 0) ENC_BY_C(0); else ENC_BY_C(1);
   FRAD_LAUNCH_CHECK(ctx);
   return FRAD_OK;
 }
@@ -601,6 +607,7 @@ int frad_launch_encode_2048(frad_ctx* ctx, const enc_params& P, const frad_plan*
 #define DEC_DISPATCH(TT, PROF, CT)                                                                       \
   do {                                                                                                   \
     auto k = dec2048_kernel<TT, PROF, CT>;                                                               \
+    const tile_map tm = make_tiles<CT>(P.B, P.C);                                                        \
     int grid;                                                                                            \
     const size_t smem = (size_t)FW * dec_layout<TT>::WARP_BYTES + sizeof(dec_tail<TT>);                     \
     int rc = launch_cfg(ctx, k, smem, tm.ntiles, &grid);                                                 \
@@ -611,11 +618,11 @@ int frad_launch_encode_2048(frad_ctx* ctx, const enc_params& P, const frad_plan*
 
 #define DEC_DISPATCH_C(TT, PROF)                                                                       \
   do {                                                                                                 \
-    if (P.C == 2) DEC_DISPATCH(TT, PROF, 2); else DEC_DISPATCH(TT, PROF, 0);                           \
+    if (P.C == 2) DEC_DISPATCH(TT, PROF, 2); else if (P.C == 1) DEC_DISPATCH(TT, PROF, 1);             \
+    else if (P.C % 4 == 0) DEC_DISPATCH(TT, PROF, 4); else DEC_DISPATCH(TT, PROF, 0);                  \
   } while (0)
 
 int frad_launch_decode_2048(frad_ctx* ctx, const dec_params& P, const frad_plan* pl, int prec) {
-  const tile_map tm = make_tiles(P.B, P.C);
   int rc = ensure_dq64(ctx);
   if (rc) return rc;
   if (prec == FRAD_PREC_F32) {

@@ -1,0 +1,103 @@
+"""Per-kernel device-resident timings (CUDA events on the library stream) with the HBM-roofline fraction of
+each: profile 0/1 at N = 2048, the generic-size path, CRC-32/16 and Reed-Solomon.  Prints one JSON line per
+kernel; `python tools/bench_kernels.py > gpurun_out/kernels.jsonl`."""
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from frad_python_b200 import Context, _abi  # noqa: E402
+from oracle.frad_oracle import synth_pcm  # noqa: E402
+
+PEAK = 6548.5
+try:
+    PEAK = float(json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+L = _abi.lib()
+ctx = Context(0)
+REPS = 10
+
+
+def timed(fn, nbytes, name, **extra):
+    for _ in range(3):
+        fn()
+    ctx.sync()
+    ctx.event(0)
+    for _ in range(REPS):
+        fn()
+    ctx.event(1)
+    ctx.sync()
+    ms = ctx.elapsed_ms(0, 1) / REPS
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    print(json.dumps({"kernel": name, "ms": round(ms, 4), "algorithmic_bytes": nbytes, "GB/s": round(gbs, 1),
+                      "frac_of_hbm_peak": round(gbs / PEAK, 4), **extra}), flush=True)
+
+
+def pcm_dev(frames, n, hop, ch, dtype=np.float32):
+    tile = synth_pcm(2.0, 48000, ch, 1)
+    need = (frames - 1) * hop + n
+    pcm = np.ascontiguousarray(np.tile(tile, (-(-need // len(tile)), 1))[:need]).astype(dtype)
+    d = ctx.dev(pcm.nbytes)
+    ctx.h2d(d, pcm)
+    ctx.sync()
+    return d, pcm
+
+
+def transforms():
+    for (n, hop, ch, frames, tag) in ((2048, 2048, 2, 15000, "S48 N=2048 C=2"), (2048, 2048, 8, 4000, "S96 N=2048 C=8"),
+                                       (2048, 2048, 1, 30000, "mono N=2048"), (1024, 1024, 2, 30000, "N=1024 generic"),
+                                       (4096, 4096, 2, 7500, "N=4096 generic"), (1280, 1280, 2, 24000, "N=1280 generic"),
+                                       (2000, 2000, 2, 15000, "N=2000 generic (lossless size)")):
+        d_pcm, _ = pcm_dev(frames, n, hop, ch)
+        ncoef = frames * n * ch
+        d_pay = ctx.dev(ncoef * 4); d_peak = ctx.dev(frames * 8); d_out = ctx.dev(ncoef * 8)
+        timed(lambda: ctx.check(L.frad_p0_encode_dev(ctx.handle, d_pcm.ptr, _abi.F32, hop, frames, n, ch, 32, 0, 0, d_pay.ptr, n * ch * 4, d_peak.ptr)),
+              ncoef * 8, f"p0 encode f32->be32 [{tag}]")
+        timed(lambda: ctx.check(L.frad_p0_decode_dev(ctx.handle, d_pay.ptr, n * ch * 4, frames, n, ch, 32, 0, _abi.PREC_F64, d_out.ptr, _abi.F64)),
+              ncoef * 12, f"p0 decode be32->f64 (f64 math) [{tag}]")
+        timed(lambda: ctx.check(L.frad_p0_decode_dev(ctx.handle, d_pay.ptr, n * ch * 4, frames, n, ch, 32, 0, _abi.PREC_F32, d_out.ptr, _abi.F32)),
+              ncoef * 8, f"p0 decode be32->f32 (f32 math) [{tag}]")
+        if n in (2048, 1024, 4096, 1280):
+            d_q = ctx.dev(ncoef * 4); d_tq = ctx.dev(frames * 27 * ch * 4)
+            timed(lambda: ctx.check(L.frad_p1_encode_dev(ctx.handle, d_pcm.ptr, _abi.F32, hop, frames, n, ch, 16, 48000, 0.5526315789473684, 0, d_q.ptr, d_tq.ptr, None)),
+                  ncoef * 8, f"p1 encode f32->int32 [{tag}]")
+            timed(lambda: ctx.check(L.frad_p1_decode_dev(ctx.handle, d_q.ptr, d_tq.ptr, None, frames, n, ch, 16, 48000, _abi.PREC_F64, d_out.ptr, _abi.F64)),
+                  ncoef * 12, f"p1 decode int32->f64 (f64 math) [{tag}]")
+            timed(lambda: ctx.check(L.frad_p1_decode_dev(ctx.handle, d_q.ptr, d_tq.ptr, None, frames, n, ch, 16, 48000, _abi.PREC_F32, d_out.ptr, _abi.F64)),
+                  ncoef * 12, f"p1 decode int32->f64 (f32 math) [{tag}]")
+            d_q.free(); d_tq.free()
+        for b in (d_pcm, d_pay, d_peak, d_out):
+            b.free()
+
+
+def crc_rs():
+    frames, flen = 15000, 16384
+    rng = np.random.default_rng(0)
+    data = rng.integers(0, 256, frames * flen, dtype=np.uint8)
+    d = ctx.dev(data.nbytes); ctx.h2d(d, data); ctx.sync()
+    d_crc = ctx.dev(frames * 4)
+    timed(lambda: ctx.check(L.frad_crc32_dev(ctx.handle, d.ptr, None, None, flen, flen, frames, d_crc.ptr)), frames * flen,
+          "crc32, 15000 x 16 KiB payloads")
+    timed(lambda: ctx.check(L.frad_crc16_dev(ctx.handle, d.ptr, None, None, flen, flen, frames, d_crc.ptr)), frames * flen,
+          "crc16, 15000 x 16 KiB payloads")
+    elen = L.frad_rs_encoded_len(flen, 96, 24)
+    estride = (elen + 15) // 16 * 16
+    d_enc = ctx.dev(frames * estride); d_dec = ctx.dev(frames * flen)
+    timed(lambda: ctx.check(L.frad_rs_encode_dev(ctx.handle, d.ptr, None, None, flen, flen, frames, 96, 24, d_enc.ptr, None, estride)),
+          int(frames * flen * 1.25), "rs encode 96/24, 15000 x 16 KiB")
+    d_st = ctx.dev(frames * 4); d_fx = ctx.dev(frames * 4)
+    timed(lambda: ctx.check(L.frad_rs_decode_dev(ctx.handle, d_enc.ptr, None, None, estride, elen, frames, 96, 24, 1, d_dec.ptr, None, flen, d_st.ptr, d_fx.ptr)),
+          int(frames * flen * 1.25), "rs decode+check 96/24 (clean), 15000 x 16 KiB")
+    timed(lambda: ctx.check(L.frad_crc32_dev(ctx.handle, d_enc.ptr, None, None, estride, elen, frames, d_crc.ptr)), frames * elen,
+          "crc32 over RS-encoded payloads (20488 B)")
+
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "transforms"):
+        transforms()
+    if which in ("all", "bytes"):
+        crc_rs()
