@@ -2,6 +2,14 @@
 // These are what a ctypes / cgo / JNI binding of the reference's per-frame seams would call.
 #include "common.cuh"
 
+void frad_rs_set_max_len(uint32_t v);   // rs.cu
+static uint32_t host_max_len(const uint32_t* len, uint32_t ulen, int B) {
+  if (!len) return ulen;
+  uint32_t m = 0;
+  for (int i = 0; i < B; i++) if (len[i] > m) m = len[i];
+  return m ? m : 1;
+}
+
 namespace {
 struct arena { frad_ctx* ctx; char* base; size_t used, cap; bool bad; };
 // carve 256-byte aligned pieces out of scratch slot 2
@@ -298,7 +306,10 @@ extern "C" int frad_rs_encode(frad_ctx* ctx, const uint8_t* buf, const uint64_t*
     if ((rc = frad_h2d(ctx, p, out_off, 8 * (size_t)B))) return rc;
     d_ooff = (const uint64_t*)p;
   }
-  if ((rc = frad_rs_encode_dev(ctx, d_buf, d_off, d_len, stride, ulen, B, dsize, csize, d_out, d_ooff, out_stride))) return rc;
+  frad_rs_set_max_len(host_max_len(len, ulen, B));
+  rc = frad_rs_encode_dev(ctx, d_buf, d_off, d_len, stride, ulen, B, dsize, csize, d_out, d_ooff, out_stride);
+  frad_rs_set_max_len(0);
+  if (rc) return rc;
   if ((rc = frad_d2h(ctx, out, d_out, out_total_bytes))) return rc;
   return frad_sync(ctx);
 }
@@ -325,7 +336,10 @@ extern "C" int frad_rs_decode(frad_ctx* ctx, const uint8_t* buf, const uint64_t*
     if ((rc = frad_h2d(ctx, p, out_off, 8 * (size_t)B))) return rc;
     d_ooff = (const uint64_t*)p;
   }
-  if ((rc = frad_rs_decode_dev(ctx, d_buf, d_off, d_len, stride, ulen, B, dsize, csize, repair, d_out, d_ooff, out_stride, d_status, d_fixed))) return rc;
+  frad_rs_set_max_len(host_max_len(len, ulen, B));
+  rc = frad_rs_decode_dev(ctx, d_buf, d_off, d_len, stride, ulen, B, dsize, csize, repair, d_out, d_ooff, out_stride, d_status, d_fixed);
+  frad_rs_set_max_len(0);
+  if (rc) return rc;
   if ((rc = frad_d2h(ctx, out, d_out, out_total_bytes))) return rc;
   if (status && (rc = frad_d2h(ctx, status, d_status, 4 * (size_t)B))) return rc;
   if (fixed && (rc = frad_d2h(ctx, fixed, d_fixed, 4 * (size_t)B))) return rc;

@@ -9,6 +9,8 @@
 // Chien / Forney (per thread, from the csize-byte remainder: S_j = rem(alpha^j)).
 #include "common.cuh"
 
+extern thread_local uint32_t g_rs_max_len;
+
 namespace {
 
 constexpr int kMaxParityWords = 64;     // csize <= 254
@@ -17,7 +19,8 @@ struct rs_table {                        // device layout: header then rows
   int csize, nw;                         // parity bytes, 32-bit words per row
   uint8_t gf_exp[512];
   uint8_t gf_log[256];
-  // followed by uint32_t rows[256][nw]
+  // followed by uint32_t rows[256][nw]            (one LFSR step: symbol f entering an empty register)
+  // then     uint32_t slice[3][256][nw]        (the same symbol followed by 1, 2, 3 zero-input steps)
 };
 
 void host_gf(uint8_t* ex, uint8_t* lg) {
@@ -31,7 +34,7 @@ const rs_table* get_table(frad_ctx* ctx, int csize) {
   auto it = ctx->rs_tables.find((uint32_t)csize);
   if (it != ctx->rs_tables.end()) return (const rs_table*)it->second;
   const int nw = (csize + 3) / 4;
-  const size_t bytes = sizeof(rs_table) + (size_t)256 * nw * 4;
+  const size_t bytes = sizeof(rs_table) + (size_t)4 * 256 * nw * 4;
   std::vector<uint8_t> h(bytes, 0);
   rs_table* t = (rs_table*)h.data();
   t->csize = csize; t->nw = nw;
@@ -46,6 +49,18 @@ const rs_table* get_table(frad_ctx* ctx, int csize) {
   }
   uint8_t* rows = h.data() + sizeof(rs_table);
   for (int f = 0; f < 256; f++) for (int j = 0; j < csize; j++) rows[(size_t)f * nw * 4 + j] = (uint8_t)mul(f, g[j + 1]);
+  // slicing tables: advance the register by further zero-input steps (par <- shift(par) ^ rows[par[0]])
+  const size_t tsz = (size_t)256 * nw * 4;
+  for (int k = 1; k <= 3; k++) {
+    const uint8_t* prev = rows + (k - 1) * tsz;
+    uint8_t* cur = rows + k * tsz;
+    for (int f = 0; f < 256; f++) {
+      const uint8_t* pr = prev + (size_t)f * nw * 4;
+      uint8_t* cr = cur + (size_t)f * nw * 4;
+      const int fb = csize > 0 ? pr[0] : 0;
+      for (int j = 0; j < csize; j++) cr[j] = (uint8_t)((j + 1 < csize ? pr[j + 1] : 0) ^ rows[(size_t)fb * nw * 4 + j]);
+    }
+  }
   void* d = nullptr;
   if (cudaMalloc(&d, bytes) != cudaSuccess || cudaMemcpy(d, h.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
     cudaGetLastError();
@@ -268,9 +283,211 @@ __global__ void __launch_bounds__(128) rs_decode_kernel(const uint8_t* __restric
   }
 }
 
+
+// ---- tile kernel: one warp = 32 consecutive codewords of one message -----------------------------------
+// Coalesced staging of the tile into shared memory (odd row pitch: conflict-free per-lane rows), LFSR by
+// four symbols per step (slicing tables: 4 row fetches of csize bytes per 4 data bytes, the register shift
+// becomes a register renaming), coalesced write-back of data || parity (encode) or of the data (decode).
+size_t table_bytes_sliced(int csize);
+constexpr int kRsWarps = 4;
+
+template <int NW, bool DECODE>
+__global__ void __launch_bounds__(kRsWarps * 32) rs_tile_kernel(
+    const uint8_t* __restrict__ buf, const uint64_t* __restrict__ off, const uint32_t* __restrict__ len, size_t stride,
+    uint32_t ulen, int B, int dsize, int repair, const rs_table* __restrict__ gt, uint8_t* __restrict__ out,
+    const uint64_t* __restrict__ out_off, size_t out_stride, int32_t* __restrict__ status, int32_t* __restrict__ fixed,
+    int tiles_per_msg, int pitch_words) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int csize = NW * 4, block = dsize + csize;
+  const size_t tbytes = sizeof(rs_table) + (size_t)4 * 256 * NW * 4;
+  {
+    const uint32_t* src = (const uint32_t*)gt;
+    uint32_t* dstw = (uint32_t*)smem;
+    for (size_t i = threadIdx.x; i < tbytes / 4; i += blockDim.x) dstw[i] = src[i];
+  }
+  __syncthreads();
+  const rs_table* st = (const rs_table*)smem;
+  rs_smem_view sv;
+  sv.gf_exp = st->gf_exp; sv.gf_log = st->gf_log; sv.rows = (const uint32_t*)(smem + sizeof(rs_table)); sv.csize = csize; sv.nw = NW;
+  const uint32_t* T3 = sv.rows;                      // symbol is the last of the four
+  const uint32_t* T2 = T3 + 256 * NW;
+  const uint32_t* T1 = T2 + 256 * NW;
+  const uint32_t* T0 = T1 + 256 * NW;                // symbol is the first of the four (3 more steps follow)
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const size_t stage_off = (tbytes + 15) & ~(size_t)15;
+  uint32_t* rows_w = (uint32_t*)(smem + stage_off) + (size_t)w * 32 * pitch_words;       // [32][pitch_words]
+  const int rowb = DECODE ? block : dsize;             // bytes per input row
+  const int outb = DECODE ? dsize : block;             // bytes per output row
+  // tile enumeration: flat over (message, tile) for uniform batches, CTA-per-message otherwise
+  const long long total_tiles = (long long)B * tiles_per_msg;
+  const long long wstep = (long long)gridDim.x * kRsWarps;
+  for (long long t = (long long)blockIdx.x * kRsWarps + w; t < total_tiles; t += wstep) {
+    const int m = (int)(t / tiles_per_msg), kt = (int)(t - (long long)m * tiles_per_msg);
+    const uint8_t* src = buf + (off ? off[m] : (uint64_t)m * stride);
+    uint8_t* dst = out + (out_off ? out_off[m] : (uint64_t)m * out_stride);
+    const uint32_t L = len ? len[m] : ulen;
+    const int ncw = (int)((L + rowb - 1) / rowb);
+    const int k0 = kt * 32;
+    if (k0 >= ncw) continue;
+    const int nrows = min(32, ncw - k0);
+    const uint8_t* tin = src + (size_t)k0 * rowb;
+    const uint32_t tbytes_in = min((uint32_t)(nrows * rowb), L - (uint32_t)k0 * rowb);
+    __syncwarp();
+    // ---- stage in ----
+    if ((((uintptr_t)tin) & 3) == 0 && (rowb & 3) == 0) {
+      const int rw = rowb >> 2, nwords = (int)(tbytes_in >> 2);
+      int r = lane / rw, c = lane - r * rw;
+      for (int wi = lane; wi < nwords; wi += 32) {
+        rows_w[r * pitch_words + c] = __ldg((const uint32_t*)tin + wi);
+        c += 32;
+        while (c >= rw) { c -= rw; r++; }
+      }
+      for (uint32_t bi = (uint32_t)nwords * 4 + lane; bi < tbytes_in; bi += 32) {       // < 4 trailing bytes
+        const int rr = (int)(bi / rowb), cc = (int)(bi - (uint32_t)rr * rowb);
+        ((uint8_t*)(rows_w + rr * pitch_words))[cc] = tin[bi];
+      }
+    } else {
+      int r = lane / rowb, c = lane - r * rowb;
+      for (uint32_t bi = lane; bi < tbytes_in; bi += 32) {
+        ((uint8_t*)(rows_w + r * pitch_words))[c] = tin[bi];
+        c += 32;
+        while (c >= rowb) { c -= rowb; r++; }
+      }
+    }
+    __syncwarp();
+    // ---- per-lane codeword ----
+    int my_fail = 0, my_fixed = 0;
+    int rowlen = 0, dlen = 0;
+    if (lane < nrows) {
+      const uint32_t start = (uint32_t)(k0 + lane) * rowb;
+      rowlen = (int)min((uint32_t)rowb, L - start);
+      dlen = DECODE ? max(rowlen - csize, 0) : rowlen;
+      uint32_t* row = rows_w + lane * pitch_words;
+      uint32_t par[NW];
+#pragma unroll
+      for (int i = 0; i < NW; i++) par[i] = 0;
+      const int nq = (!DECODE || repair) ? (dlen >> 2) : 0;
+      for (int j = 0; j < nq; j++) {
+        const uint32_t x = par[0] ^ row[j];
+        const uint32_t* a = T0 + (x & 0xFF) * NW;
+        const uint32_t* b = T1 + ((x >> 8) & 0xFF) * NW;
+        const uint32_t* c = T2 + ((x >> 16) & 0xFF) * NW;
+        const uint32_t* d = T3 + (x >> 24) * NW;
+        if constexpr ((NW & 1) == 0) {                   // 8-byte aligned rows: half as many shared-memory loads
+          const uint2 *a2 = (const uint2*)a, *b2 = (const uint2*)b, *c2 = (const uint2*)c, *d2 = (const uint2*)d;
+#pragma unroll
+          for (int i = 0; i < NW / 2; i++) {
+            const uint2 va = a2[i], vb = b2[i], vc = c2[i], vd = d2[i];
+            par[2 * i] = par[2 * i + 1] ^ va.x ^ vb.x ^ vc.x ^ vd.x;
+            par[2 * i + 1] = ((2 * i + 2 < NW) ? par[2 * i + 2] : 0u) ^ va.y ^ vb.y ^ vc.y ^ vd.y;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < NW; i++) par[i] = ((i + 1 < NW) ? par[i + 1] : 0u) ^ a[i] ^ b[i] ^ c[i] ^ d[i];
+        }
+      }
+      const uint8_t* rb = (const uint8_t*)row;
+      for (int j = nq * 4; j < ((!DECODE || repair) ? dlen : 0); j++) {
+        const uint32_t f = (par[0] ^ rb[j]) & 0xFF;
+        const uint32_t* rr = T3 + f * NW;
+#pragma unroll
+        for (int i = 0; i < NW; i++) par[i] = ((i + 1 < NW) ? __funnelshift_r(par[i], par[i + 1], 8) : (par[i] >> 8)) ^ rr[i];
+      }
+      if (!DECODE) {
+        uint8_t* pb = (uint8_t*)row + dlen;              // parity follows the data inside the staged row
+        if ((dlen & 3) == 0) {
+#pragma unroll
+          for (int i = 0; i < NW; i++) row[(dlen >> 2) + i] = par[i];
+        } else {
+          for (int j = 0; j < csize; j++) pb[j] = (uint8_t)(par[j >> 2] >> (8 * (j & 3)));
+        }
+      } else if (repair) {
+        if (rowlen <= csize) my_fail++;
+        else {
+          uint8_t rem[32];
+          int dirty = 0;
+          for (int j = 0; j < csize; j++) {
+            rem[j] = (uint8_t)(par[j >> 2] >> (8 * (j & 3))) ^ rb[dlen + j];
+            dirty |= rem[j];
+          }
+          if (dirty) {
+            uint8_t fixedrow[256];
+            const int rfix = rs_repair_word(sv, rb, rowlen, rem, fixedrow);
+            uint8_t* wb = (uint8_t*)row;
+            if (rfix < 0) { for (int i = 0; i < dlen; i++) wb[i] = 0; my_fail++; }
+            else { for (int i = 0; i < dlen; i++) wb[i] = fixedrow[i]; my_fixed += rfix; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+    // ---- write back: rows are contiguous in the output (all rows full except possibly the last) ----
+    uint8_t* tout = dst + (size_t)k0 * outb;
+    for (int r = 0; r < nrows; r++) {
+      const int rl = __shfl_sync(0xffffffffu, DECODE ? dlen : (dlen + csize), r);
+      const uint32_t* row = rows_w + r * pitch_words;
+      uint8_t* orow = tout + (size_t)r * outb;
+      if ((((uintptr_t)orow) & 3) == 0 && (rl & 3) == 0) {
+        for (int j = lane; j < (rl >> 2); j += 32) ((uint32_t*)orow)[j] = row[j];
+      } else {
+        for (int j = lane; j < rl; j += 32) orow[j] = ((const uint8_t*)row)[j];
+      }
+    }
+    if (DECODE && (status || fixed)) {
+#pragma unroll
+      for (int sft = 16; sft > 0; sft >>= 1) {
+        my_fail += __shfl_xor_sync(0xffffffffu, my_fail, sft);
+        my_fixed += __shfl_xor_sync(0xffffffffu, my_fixed, sft);
+      }
+      if (lane == 0) {
+        if (status && my_fail) atomicAdd(&status[m], my_fail);
+        if (fixed && my_fixed) atomicAdd(&fixed[m], my_fixed);
+      }
+    }
+  }
+}
+
+template <bool DECODE>
+int launch_tiles(frad_ctx* ctx, const uint8_t* buf, const uint64_t* off, const uint32_t* len, size_t stride, uint32_t ulen, int B,
+                 int dsize, int csize, int repair, const rs_table* t, uint8_t* out, const uint64_t* out_off, size_t out_stride,
+                 int32_t* status, int32_t* fixed, uint32_t max_len) {
+  const int rowb = DECODE ? dsize + csize : dsize;
+  const int staged = dsize + csize;                                   // encode appends the parity inside the staged row
+  const int pitch = ((staged + 3) / 4) | 1;
+  const int tiles_per_msg = (int)(((max_len + rowb - 1) / rowb + 31) / 32);
+  if (tiles_per_msg < 1) return FRAD_OK;
+  const size_t tb = (table_bytes_sliced(csize) + 15) & ~(size_t)15;
+  const size_t smem = tb + (size_t)kRsWarps * 32 * pitch * 4;
+  const long long total = (long long)B * tiles_per_msg;
+  long long want = (total + kRsWarps - 1) / kRsWarps;
+  const void* k = nullptr;
+#define RS_PICK(NWV) case NWV: k = (const void*)rs_tile_kernel<NWV, DECODE>; break;
+  switch (csize / 4) { RS_PICK(1) RS_PICK(2) RS_PICK(3) RS_PICK(4) RS_PICK(5) RS_PICK(6) RS_PICK(7) RS_PICK(8) default: return FRAD_E_UNSUPPORTED; }
+#undef RS_PICK
+  FRAD_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 1;
+  FRAD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kRsWarps * 32, smem));
+  if (per_sm < 1) per_sm = 1;
+  const long long cap = (long long)per_sm * ctx->sm_count;
+  const int grid = (int)(want < cap ? want : cap);
+  void* args[] = {(void*)&buf, (void*)&off, (void*)&len, (void*)&stride, (void*)&ulen, (void*)&B, (void*)&dsize, (void*)&repair,
+                  (void*)&t, (void*)&out, (void*)&out_off, (void*)&out_stride, (void*)&status, (void*)&fixed,
+                  (void*)&tiles_per_msg, (void*)&pitch};
+  FRAD_CUDA(ctx, cudaLaunchKernel(k, dim3(grid), dim3(kRsWarps * 32), args, smem, ctx->stream));
+  FRAD_LAUNCH_CHECK(ctx);
+  return FRAD_OK;
+}
+
+bool tile_ok(int csize) { return csize >= 4 && csize <= 32 && (csize & 3) == 0; }
 size_t table_bytes(int csize) { return sizeof(rs_table) + (size_t)256 * ((csize + 3) / 4) * 4; }
+size_t table_bytes_sliced(int csize) { return sizeof(rs_table) + (size_t)4 * 256 * ((csize + 3) / 4) * 4; }
 
 }  // namespace
+
+// upper bound of the message lengths behind a device-resident len[] array; set by the host-pointer entry
+// points (which know the lengths) around their *_dev call, 0 = unknown (per-message kernels are used)
+thread_local uint32_t g_rs_max_len = 0;
+void frad_rs_set_max_len(uint32_t v) { g_rs_max_len = v; }
 
 extern "C" size_t frad_rs_encoded_len(size_t len, int dsize, int csize) {
   if (dsize <= 0) return len;
@@ -293,6 +510,10 @@ extern "C" int frad_rs_encode_dev(frad_ctx* ctx, const uint8_t* buf, const uint6
   FRAD_CUDA(ctx, cudaSetDevice(ctx->device));
   const rs_table* t = get_table(ctx, csize);
   if (!t) return FRAD_E_NOMEM;
+  if (tile_ok(csize) && (!len || g_rs_max_len)) {
+    const uint32_t mx = len ? g_rs_max_len : ulen;
+    return launch_tiles<false>(ctx, buf, off, len, stride, ulen, B, dsize, csize, 1, t, out, out_off, out_stride, nullptr, nullptr, mx);
+  }
   const size_t smem = table_bytes(csize);
   FRAD_CUDA(ctx, cudaFuncSetAttribute(rs_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = B < ctx->sm_count * 8 ? B : ctx->sm_count * 8;
@@ -312,6 +533,12 @@ extern "C" int frad_rs_decode_dev(frad_ctx* ctx, const uint8_t* buf, const uint6
   FRAD_CUDA(ctx, cudaSetDevice(ctx->device));
   const rs_table* t = get_table(ctx, csize);
   if (!t) return FRAD_E_NOMEM;
+  if (tile_ok(csize) && (!len || g_rs_max_len)) {
+    const uint32_t mx = len ? g_rs_max_len : ulen;
+    if (status) FRAD_CUDA(ctx, cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)B, ctx->stream));
+    if (fixed) FRAD_CUDA(ctx, cudaMemsetAsync(fixed, 0, sizeof(int32_t) * (size_t)B, ctx->stream));
+    return launch_tiles<true>(ctx, buf, off, len, stride, ulen, B, dsize, csize, repair, t, out, out_off, out_stride, status, fixed, mx);
+  }
   const size_t smem = table_bytes(csize);
   FRAD_CUDA(ctx, cudaFuncSetAttribute(rs_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = B < ctx->sm_count * 8 ? B : ctx->sm_count * 8;
