@@ -185,6 +185,17 @@ __global__ void __launch_bounds__(FW * 32, FRAD_MINB) enc2048_kernel(enc_params 
       scatter_frame<CT, SEQ_CPX * 2>((const uint32_t*)(pcm + (size_t)(b0 + f) * P.hop * C), (uint32_t*)seq_all, C, f, grp, tid,
                                      [](int n) { return zword(n); });
     __syncthreads();
+    {   // pull the next tile of this CTA towards L2 while the current one is transformed
+      const int nt = tile + gridDim.x;
+      if (nt < tm.ntiles) {
+        const int nb0 = (CT == 4) ? nt / tm.groups : nt * tm.fpc;
+        const int nnf = min(tm.fpc, P.B - nb0);
+        const char* base = (const char*)(pcm + (size_t)nb0 * P.hop * C);
+        const size_t bytes = (size_t)nnf * words_per_frame * 4;
+        for (size_t o = (size_t)tid * 128; o < bytes; o += (size_t)FW * 32 * 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(base + o));
+      }
+    }
     if (w < nseq) {
       const int f = (CT == 4) ? 0 : w / C, c = (CT == 4) ? 4 * grp + w : w - f * C, b = b0 + f;
       float2* buf = seq_all + (size_t)w * SEQ_CPX;
@@ -207,9 +218,6 @@ __global__ void __launch_bounds__(FW * 32, FRAD_MINB) enc2048_kernel(enc_params 
         if (PROFILE == 0) {
           mx = fmaxf(mx, fabsf(val));
           if (swap_out) val = __uint_as_float(__byte_perm(__float_as_uint(val), 0, 0x0123));
-        } else {
-          float* pp = part + 32 * (int)tail->bidx[k];                    // private slot: no atomics, no conflicts
-          *pp = fmaf(val, val, *pp);
         }
         X[k] = val;
       };
@@ -242,7 +250,27 @@ __global__ void __launch_bounds__(FW * 32, FRAD_MINB) enc2048_kernel(enc_params 
         }
       } else {
         __syncwarp();
-        // ---- band energies of the scaled spectrum: lane b adds up row b of the per-lane partials ----
+        // ---- band energies of the scaled spectrum.  Each lane walks its bins k = lane + 32 j in rising order,
+        //      so its band index only ever grows: a running register sum is flushed to a private slot
+        //      [band][lane] when the band changes (no atomics, no conflicts); lane b then adds up row b ----
+        {
+          float acc = 0.0f;
+          int cur = 0;
+#pragma unroll 1
+          for (int kb = lane; kb < FN; kb += 256) {
+            float xv[8];
+            int bi[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) { xv[u] = X[kb + 32 * u]; bi[u] = tail->bidx[kb + 32 * u]; }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+              if (bi[u] != cur) { part[cur * 32] = acc; acc = 0.0f; cur = bi[u]; }
+              acc = fmaf(xv[u], xv[u], acc);
+            }
+          }
+          part[cur * 32] = acc;
+          __syncwarp();
+        }
         const float scalef = (float)P.scale;
         float tot = 0.0f;
         if (lane < FRAD_NBANDS) {
@@ -261,13 +289,14 @@ __global__ void __launch_bounds__(FW * 32, FRAD_MINB) enc2048_kernel(enc_params 
         const int first_empty = empty ? (__ffs(empty) - 1) : 32;
         double thr = 0.0;
         if (lane < FRAD_NBANDS && lane < first_empty) {
-          const double level = pow(sqrt((double)tot / (double)cnt), 0.8);
-          thr = fmax(level, P.bt->ath[lane]) * P.loss;
+          // f32 like the reference for f32 spectra: np.sqrt(np.mean(x**2)) ** 0.8 on float32 (p1tools.py:32)
+          const float level = powf(sqrtf(tot / (float)cnt), 0.8f);
+          thr = fmax((double)level, P.bt->ath[lane]) * P.loss;
         }
         if (lane <= FRAD_NBANDS) tail->thr[w][lane] = thr;             // entry 27 = 0
         if (lane < FRAD_NBANDS) {
           const double vv = log(fmax(thr, 1.0)) / P.bt->log_base;
-          const double d = (vv > 0.0) ? pow(vv, 1.0 / 0.75) : 0.0;
+          const double d = (vv > 0.0) ? vv * cbrt(vv) : 0.0;             // v^(4/3)
           P.tq[((size_t)b * FRAD_NBANDS + lane) * C + c] = sat_i32(rint(d));
         }
         // per-band ramp parameters, one band per lane: the divisor over the scale as a convex combination
