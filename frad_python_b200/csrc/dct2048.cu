@@ -438,6 +438,18 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
       scatter_frame<CT, LY::WARP_BYTES / 4>(src, (uint32_t*)(smem_raw + LY::RAW_OFF), C, f, grp, tid, [](int k) { return k; });
     }
     __syncthreads();
+    {   // pull the next tile of this CTA towards L2 while the current one is transformed
+      const int nt = tile + gridDim.x;
+      if (nt < tm.ntiles) {
+        const int nb0 = (CT == 4) ? nt / tm.groups : nt * tm.fpc;
+        const int nnf = min(tm.fpc, P.B - nb0);
+        const char* base = (PROFILE == 0) ? (const char*)(P.payload + (size_t)nb0 * P.payload_stride)
+                                          : (const char*)(P.q + (size_t)nb0 * words_per_frame);
+        const size_t bytes = (PROFILE == 0) ? (size_t)nnf * P.payload_stride : (size_t)nnf * words_per_frame * 4;
+        for (size_t o = (size_t)tid * 128; o < bytes; o += (size_t)FW * 32 * 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(base + o));
+      }
+    }
     if (w < nseq) {
       const int f = (CT == 4) ? 0 : w / C, c = (CT == 4) ? 4 * grp + w : w - f * C, b = b0 + f;
       unsigned char* mine = smem_raw + (size_t)w * LY::WARP_BYTES;
@@ -449,7 +461,8 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
         double thr = 0.0;
         if (lane < FRAD_NBANDS) {
           const double tv = (double)P.tq[((size_t)b * FRAD_NBANDS + lane) * C + c];
-          thr = pow(P.bt->base, copysign(pow(fabs(tv), 0.75), tv));
+          const double av = fabs(tv);
+          thr = exp(copysign(sqrt(av * sqrt(av)), tv) * P.bt->log_base);   // (e/2)^(sign |tq|^0.75), profile1.py:66
         }
         const double thr_next = __shfl_down_sync(0xffffffffu, thr, 1);
         if (lane <= FRAD_NBANDS) {
