@@ -30,6 +30,7 @@ constexpr int FN = 2048, FM = 1024, FW = FRAD_FW;          // frame, half, warps
 constexpr int SEQ_CPX = 1056;                        // padded complex slots per warp buffer
 constexpr int DQ_TAB = 1024;                         // f32 dequantiser table entries (|q| < DQ_TAB)
 constexpr int DQ_TAB64 = 4096;                       // f64 table (global memory)
+constexpr int DQ_SMEM64 = 256;                       // head of the f64 table kept in shared memory
 #define FRAD_RSQRT2 0.70710678118654752440
 
 __device__ __forceinline__ int zword(int n) {        // word index (units of T) of sample n inside the z layout
@@ -74,6 +75,7 @@ template <> struct dec_tail<double> {                 // f64 flavour: exact np.l
   int lo[FRAD_NBANDS + 1];
   uint8_t bidx[FN];
   double2 rp[FW][FRAD_NBANDS + 1];                    // start, step
+  double dq[DQ_SMEM64];                               // |q|^(4/3) for the most frequent small |q|
 };
 
 // band index table shared by all warps of the CTA (same N and sample rate)
@@ -399,6 +401,15 @@ __global__ void __launch_bounds__(FW * 32, FRAD_MINB) enc2048_kernel(enc_params 
 // ------------------------------------------------------------------------------------------------
 // decode
 // ------------------------------------------------------------------------------------------------
+// rare large magnitudes: kept out of line so the hot loop stays small
+__device__ __noinline__ double dequant_big(const double* __restrict__ dq64, int qa) {
+  return (qa < DQ_TAB64) ? __ldg(dq64 + qa) : pow((double)qa, 1.0 / 0.75);
+}
+__device__ __noinline__ float dequant_big_f32(int qa, float inv_scale) {
+  const float af = (float)qa;
+  return af * cbrtf(af) * inv_scale;
+}
+
 template <typename T> struct dec_layout {
   static constexpr int SEQ_BYTES = SEQ_CPX * 2 * (int)sizeof(T);
   static constexpr int RAW_OFF = 0;            // the raw 32-bit words are consumed into registers before the exchange
@@ -422,6 +433,8 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
     build_bidx(tail, P.bt, tid);
     if constexpr (sizeof(T) == 4) {
       for (int i = tid; i < DQ_TAB; i += FW * 32) { const float a = (float)i; tail->aux[i] = a * cbrtf(a) * (float)inv_scale; }
+    } else {
+      for (int i = tid; i < DQ_SMEM64; i += FW * 32) tail->dq[i] = __ldg(dq64 + i);
     }
   }
   const int words_per_frame = FN * C;
@@ -478,8 +491,7 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
         __syncwarp();
       }
       // value X[k] from the staged 32-bit word: profile 0 unpack + scrub, profile 1 dequantiser x ramp
-      auto coef = [&](int k, float kf) -> T {
-        const uint32_t u0 = raw[k];
+      auto coef = [&](uint32_t u0, int k, float kf) -> T {
         if (PROFILE == 0) {
           const uint32_t u = P.le ? u0 : __byte_perm(u0, 0, 0x0123);
           const float fv = __uint_as_float(u);
@@ -489,29 +501,49 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
           const int qa = abs(qi);
           const int bnd = tail->bidx[k];
           if constexpr (sizeof(T) == 8) {
-            const double mag = (qa < DQ_TAB64) ? __ldg(dq64 + qa) : pow((double)qa, 1.0 / 0.75);
+            double mag;
+            if (qa < DQ_SMEM64) mag = tail->dq[qa];
+            else mag = dequant_big(dq64, qa);
             const double2 rp = tail->rp[w][bnd];
             const double div = __dadd_rn(__dmul_rn((double)(k - tail->lo[bnd]), rp.y), rp.x);   // j * step + start
             return (T)((((qi < 0) ? -mag : mag) * inv_scale) * div);
           } else {
             float mag;
             if (qa < DQ_TAB) mag = tail->aux[qa];
-            else { const float af = (float)qa; mag = af * cbrtf(af) * (float)inv_scale; }
+            else mag = dequant_big_f32(qa, (float)inv_scale);
             const float4 bpv = tail->bp[w][bnd];
             const float dv = fmaf(kf - bpv.z, bpv.y, (bpv.w - kf) * bpv.x);
             return (T)(((qi < 0) ? -mag : mag) * dv);
           }
         }
       };
+      // ---- dequantise in place, highest bins first: X[k] (sizeof(T) bytes at k) may only overwrite raw words that
+      //      were already consumed, so every batch loads its eight words per lane before any lane stores ----
+      {
+        const float lf0 = (float)lane;
+#pragma unroll 1
+        for (int kb = FN - 256 + lane; kb >= 0; kb -= 256) {
+          uint32_t u[8];
+#pragma unroll
+          for (int i = 0; i < 8; i++) u[i] = raw[kb + 32 * i];
+          T xv[8];
+#pragma unroll
+          for (int i = 0; i < 8; i++) xv[i] = coef(u[i], kb + 32 * i, lf0 + (float)(kb - lane + 32 * i));
+          if (sizeof(T) == 8) __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; i++) X[kb + 32 * i] = xv[i];
+          if (sizeof(T) == 8) __syncwarp();
+        }
+      }
+      __syncwarp();
       // ---- pairwise pre-processing: R1 = X[k] - i X[N-k], R2 = (X[M-k] + i X[M+k]) e^{-i pi/4},
       //      S = ci (R1 + R2), G = ei ci (R1 - R2), Z[k] = S + iG, Z[M-k] = conj(S - iG) ----
       V z[32];
       V zm_keep[17];
       const T r2 = (T)FRAD_RSQRT2;
-      const float lf = (float)lane;
-      auto pre_pair = [&](int k, float kf, V& zk, V& zmk) {
-        const T xk = coef(k, kf), xnk = (k == 0) ? T(0) : coef(FN - k, (float)FN - kf);
-        const T a = coef(FM - k, (float)FM - kf), bb = coef(FM + k, (float)FM + kf);
+      auto pre_pair = [&](int k, V& zk, V& zmk) {
+        const T xk = X[k], xnk = (k == 0) ? T(0) : X[FN - k];
+        const T a = X[FM - k], bb = X[FM + k];
         const V R1 = mk2<T>(xk, -xnk);
         const V R2 = mk2<T>((a + bb) * r2, (bb - a) * r2);
         const V cik = __ldg(ci + k);
@@ -521,9 +553,9 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
         zmk = mk2<T>(S.x + G.y, -(S.y - G.x));          // conj(S - iG)
       };
 #pragma unroll
-      for (int o = 0; o < 16; o++) pre_pair(lane + 32 * o, lf + (float)(32 * o), z[o], zm_keep[o]);
+      for (int o = 0; o < 16; o++) pre_pair(lane + 32 * o, z[o], zm_keep[o]);
       zm_keep[16] = mk2<T>(T(0), T(0));
-      if (lane == 0) { V dummy; pre_pair(FM / 2, (float)(FM / 2), zm_keep[16], dummy); }      // Z[512] (self pair)
+      if (lane == 0) { V dummy; pre_pair(FM / 2, zm_keep[16], dummy); }      // Z[512] (self pair)
       __syncwarp();
       const int partner = (32 - lane) & 31;
 #pragma unroll
