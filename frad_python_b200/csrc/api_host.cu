@@ -271,8 +271,10 @@ static int crc_host(frad_ctx* ctx, const uint8_t* buf, const uint64_t* off, cons
   int rc;
   if ((rc = frad_h2d(ctx, d_buf, buf, total))) return rc;
   if ((rc = stage_index(ctx, a, off, len, B, &d_off, &d_len))) return rc;
+  frad_rs_set_max_len(host_max_len(len, ulen, B));       // lets the kernel cut long messages into balanced segments
   rc = IS32 ? frad_crc32_dev(ctx, d_buf, d_off, d_len, stride, ulen, B, d_out)
             : frad_crc16_dev(ctx, d_buf, d_off, d_len, stride, ulen, B, d_out);
+  frad_rs_set_max_len(0);
   if (rc) return rc;
   if ((rc = frad_d2h(ctx, out, d_out, 4 * (size_t)B))) return rc;
   return frad_sync(ctx);

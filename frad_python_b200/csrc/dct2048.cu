@@ -138,6 +138,43 @@ __device__ __forceinline__ void scatter_frame(const uint32_t* __restrict__ frame
   }
 }
 
+// Whole-tile staging: every 16-byte load of the tile (16 per thread for FW = 4) is issued before the first
+// scatter, so one global-memory latency is exposed per tile instead of one per unrolled group of four.
+// src(f) returns the first 32-bit word of frame f of the tile.
+template <int CT, int STRIDE_WORDS, typename SRC, typename POS>
+__device__ __forceinline__ void stage_tile(SRC src, uint32_t* seq_base, int C, int nf, int g, int tid, POS pos) {
+  if constexpr (CT == 0) {
+    for (int f = 0; f < nf; f++) scatter_frame<CT, STRIDE_WORDS>(src(f), seq_base, C, f, g, tid, pos);
+  } else {
+    constexpr int FPT = (CT == 4) ? 1 : FW / CT;                                  // frames per tile
+    constexpr int VPF = ((CT == 4) ? FN : FN * CT / 4) / (FW * 32);               // vector steps per thread and frame
+    static_assert(VPF * FW * 32 == ((CT == 4) ? FN : FN * CT / 4), "tile does not divide evenly");
+    uint4 x[FPT * VPF];
+#pragma unroll
+    for (int f = 0; f < FPT; f++) {
+      const uint32_t* frame = src(f < nf ? f : nf - 1) + vec_word<CT>(tid, C, g);   // a short tile re-reads its last frame
+#pragma unroll
+      for (int i = 0; i < VPF; i++) x[f * VPF + i] = __ldg((const uint4*)(frame + vec_word<CT>(i * FW * 32, C, 0)));
+    }
+#pragma unroll
+    for (int f = 0; f < FPT; f++) {
+      if (f < nf) {
+#pragma unroll
+        for (int i = 0; i < VPF; i++) {
+          const uint4 xv = x[f * VPF + i];
+          const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            int ii, sq;
+            vec_elem<CT>(tid + i * FW * 32, j, C, f, ii, sq);
+            (seq_base + (size_t)sq * STRIDE_WORDS)[pos(ii)] = xs[j];
+          }
+        }
+      }
+    }
+  }
+}
+
 template <int CT, int STRIDE_WORDS, typename W, typename O, typename POS, typename CVT>
 __device__ __forceinline__ void gather4(const W* seq_base, int C, int f, int e4, POS pos, CVT cvt, O* o4) {
 #pragma unroll
@@ -183,9 +220,8 @@ __global__ void __launch_bounds__(FW * 32, FRAD_MINB) enc2048_kernel(enc_params 
     const int nf = min(tm.fpc, P.B - b0);
     const int nseq = (CT == 4) ? 4 : nf * C;              // sequences (= busy warps) in this tile
     __syncthreads();                                      // previous tile fully stored before restaging
-    for (int f = 0; f < nf; f++)
-      scatter_frame<CT, SEQ_CPX * 2>((const uint32_t*)(pcm + (size_t)(b0 + f) * P.hop * C), (uint32_t*)seq_all, C, f, grp, tid,
-                                     [](int n) { return zword(n); });
+    stage_tile<CT, SEQ_CPX * 2>([&](int f) { return (const uint32_t*)(pcm + (size_t)(b0 + f) * P.hop * C); }, (uint32_t*)seq_all, C, nf,
+                                grp, tid, [](int n) { return zword(n); });
     __syncthreads();
     {   // pull the next tile of this CTA towards L2 while the current one is transformed
       const int nt = tile + gridDim.x;
@@ -445,11 +481,12 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
     const int nf = min(tm.fpc, P.B - b0);
     const int nseq = (CT == 4) ? 4 : nf * C;
     __syncthreads();
-    for (int f = 0; f < nf; f++) {
-      const uint32_t* src = (PROFILE == 0) ? (const uint32_t*)(P.payload + (size_t)(b0 + f) * P.payload_stride)
-                                           : (const uint32_t*)(P.q + (size_t)(b0 + f) * words_per_frame);
-      scatter_frame<CT, LY::WARP_BYTES / 4>(src, (uint32_t*)(smem_raw + LY::RAW_OFF), C, f, grp, tid, [](int k) { return k; });
-    }
+    stage_tile<CT, LY::WARP_BYTES / 4>(
+        [&](int f) {
+          return (PROFILE == 0) ? (const uint32_t*)(P.payload + (size_t)(b0 + f) * P.payload_stride)
+                                : (const uint32_t*)(P.q + (size_t)(b0 + f) * words_per_frame);
+        },
+        (uint32_t*)(smem_raw + LY::RAW_OFF), C, nf, grp, tid, [](int k) { return k; });
     __syncthreads();
     {   // pull the next tile of this CTA towards L2 while the current one is transformed
       const int nt = tile + gridDim.x;

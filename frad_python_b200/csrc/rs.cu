@@ -286,42 +286,93 @@ __global__ void __launch_bounds__(128) rs_decode_kernel(const uint8_t* __restric
 
 // ---- tile kernel: one warp = 32 consecutive codewords of one message -----------------------------------
 // Coalesced staging of the tile into shared memory (odd row pitch: conflict-free per-lane rows), LFSR by
-// four symbols per step (slicing tables: 4 row fetches of csize bytes per 4 data bytes, the register shift
-// becomes a register renaming), coalesced write-back of data || parity (encode) or of the data (decode).
+// SL symbols per step (slicing tables: one row fetch of csize bytes per data byte; with SL = 2 the register
+// shift is a byte permute), coalesced write-back of data || parity (encode) or of the data (decode).
+//
+// The row fetches are data dependent, so a plain table costs a ~3-way bank conflict per fetch.  Here every
+// table row is cut into planes of 16, 8 or 4 bytes and each plane is replicated 8, 16 or 32 times
+// (128 bytes per table entry and plane): a lane reads copy (lane mod replication), so the 8 / 16 / 32 lanes
+// that share one shared-memory wavefront of a 128- / 64- / 32-bit load always hit distinct banks.
+// The kernel is then bound by shared-memory bandwidth alone: csize bytes per data byte at 128 B/clk/SM.
 size_t table_bytes_sliced(int csize);
-constexpr int kRsWarps = 4;
+constexpr int kRsMaxWarps = 16;
+constexpr int kPlaneWords = 256 * 32;                 // 32 KiB per plane and slicing table
+
+template <int NW> struct rs_planes {
+  static constexpr int N4 = NW / 4, N2 = (NW % 4) / 2, N1 = NW % 2, COUNT = N4 + N2 + N1;
+  static constexpr int SL = (COUNT <= 2) ? 2 : 1;     // symbols per LFSR step (what fits next to the staging rows)
+};
+
+// XOR the NW-word row of symbol f (table t) into acc[]; base pointers already carry the lane's replica offset
+template <int NW>
+__device__ __forceinline__ void fetch_row(const uint32_t* const* lane_base, int t, uint32_t f, uint32_t* acc) {
+  typedef rs_planes<NW> PL;
+  const uint32_t eo = f << 5;                          // 128 bytes per entry
+  int pl = t * PL::COUNT, w = 0;
+#pragma unroll
+  for (int i = 0; i < PL::N4; i++, pl++, w += 4) {
+    const uint4 v = *(const uint4*)(lane_base[pl] + eo);
+    acc[w] ^= v.x; acc[w + 1] ^= v.y; acc[w + 2] ^= v.z; acc[w + 3] ^= v.w;
+  }
+  if (PL::N2) { const uint2 v = *(const uint2*)(lane_base[pl] + eo); acc[w] ^= v.x; acc[w + 1] ^= v.y; pl++; w += 2; }
+  if (PL::N1) { acc[w] ^= lane_base[pl][eo]; }
+}
 
 template <int NW, bool DECODE>
-__global__ void __launch_bounds__(kRsWarps * 32) rs_tile_kernel(
+__global__ void __launch_bounds__(kRsMaxWarps * 32, 1) rs_tile_kernel(
     const uint8_t* __restrict__ buf, const uint64_t* __restrict__ off, const uint32_t* __restrict__ len, size_t stride,
     uint32_t ulen, int B, int dsize, int repair, const rs_table* __restrict__ gt, uint8_t* __restrict__ out,
     const uint64_t* __restrict__ out_off, size_t out_stride, int32_t* __restrict__ status, int32_t* __restrict__ fixed,
     int tiles_per_msg, int pitch_words) {
+  typedef rs_planes<NW> PL;
+  constexpr int SL = PL::SL;
   extern __shared__ __align__(16) unsigned char smem[];
   const int csize = NW * 4, block = dsize + csize;
-  const size_t tbytes = sizeof(rs_table) + (size_t)4 * 256 * NW * 4;
+  const int nwarps = blockDim.x >> 5;
+  // shared memory: [SL][COUNT] planes | rs_table header (GF tables) | staging rows
+  uint32_t* planes = (uint32_t*)smem;
+  constexpr size_t plane_bytes = (size_t)SL * PL::COUNT * kPlaneWords * 4;
+  rs_table* st = (rs_table*)(smem + plane_bytes);
   {
     const uint32_t* src = (const uint32_t*)gt;
-    uint32_t* dstw = (uint32_t*)smem;
-    for (size_t i = threadIdx.x; i < tbytes / 4; i += blockDim.x) dstw[i] = src[i];
+    uint32_t* dstw = (uint32_t*)st;
+    for (size_t i = threadIdx.x; i < sizeof(rs_table) / 4; i += blockDim.x) dstw[i] = src[i];
+    const uint32_t* rows_g = (const uint32_t*)((const unsigned char*)gt + sizeof(rs_table));
+    // table t = 0 is "symbol followed by SL - 1 zero-input steps" (first of the group), t = SL - 1 the plain rows
+    for (int t = 0; t < SL; t++) {
+      const uint32_t* tab = rows_g + (size_t)(SL - 1 - t) * 256 * NW;
+      int pl = t * PL::COUNT, wo = 0;
+      for (int k = 0; k < PL::COUNT; k++, pl++) {
+        const int pw = (k < PL::N4) ? 4 : ((k < PL::N4 + PL::N2) ? 2 : 1);
+        uint32_t* dstp = planes + (size_t)pl * kPlaneWords;
+        for (int e = threadIdx.x; e < kPlaneWords; e += blockDim.x) {
+          const int f = e >> 5, c = (e & 31) % pw;
+          dstp[e] = __ldg(tab + f * NW + wo + c);
+        }
+        wo += pw;
+      }
+    }
   }
   __syncthreads();
-  const rs_table* st = (const rs_table*)smem;
   rs_smem_view sv;
-  sv.gf_exp = st->gf_exp; sv.gf_log = st->gf_log; sv.rows = (const uint32_t*)(smem + sizeof(rs_table)); sv.csize = csize; sv.nw = NW;
-  const uint32_t* T3 = sv.rows;                      // symbol is the last of the four
-  const uint32_t* T2 = T3 + 256 * NW;
-  const uint32_t* T1 = T2 + 256 * NW;
-  const uint32_t* T0 = T1 + 256 * NW;                // symbol is the first of the four (3 more steps follow)
+  sv.gf_exp = st->gf_exp; sv.gf_log = st->gf_log; sv.rows = nullptr; sv.csize = csize; sv.nw = NW;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const size_t stage_off = (tbytes + 15) & ~(size_t)15;
+  const uint32_t* lane_base[SL * PL::COUNT];
+#pragma unroll
+  for (int t = 0; t < SL; t++) {
+#pragma unroll
+    for (int k = 0; k < PL::COUNT; k++) {
+      const int pw = (k < PL::N4) ? 4 : ((k < PL::N4 + PL::N2) ? 2 : 1);
+      lane_base[t * PL::COUNT + k] = planes + (size_t)(t * PL::COUNT + k) * kPlaneWords + (lane % (32 / pw)) * pw;
+    }
+  }
+  const size_t stage_off = (plane_bytes + sizeof(rs_table) + 15) & ~(size_t)15;
   uint32_t* rows_w = (uint32_t*)(smem + stage_off) + (size_t)w * 32 * pitch_words;       // [32][pitch_words]
   const int rowb = DECODE ? block : dsize;             // bytes per input row
   const int outb = DECODE ? dsize : block;             // bytes per output row
-  // tile enumeration: flat over (message, tile) for uniform batches, CTA-per-message otherwise
   const long long total_tiles = (long long)B * tiles_per_msg;
-  const long long wstep = (long long)gridDim.x * kRsWarps;
-  for (long long t = (long long)blockIdx.x * kRsWarps + w; t < total_tiles; t += wstep) {
+  const long long wstep = (long long)gridDim.x * nwarps;
+  for (long long t = (long long)blockIdx.x * nwarps + w; t < total_tiles; t += wstep) {
     const int m = (int)(t / tiles_per_msg), kt = (int)(t - (long long)m * tiles_per_msg);
     const uint8_t* src = buf + (off ? off[m] : (uint64_t)m * stride);
     uint8_t* dst = out + (out_off ? out_off[m] : (uint64_t)m * out_stride);
@@ -333,19 +384,44 @@ __global__ void __launch_bounds__(kRsWarps * 32) rs_tile_kernel(
     const uint8_t* tin = src + (size_t)k0 * rowb;
     const uint32_t tbytes_in = min((uint32_t)(nrows * rowb), L - (uint32_t)k0 * rowb);
     __syncwarp();
-    // ---- stage in ----
+    // ---- stage in: row by row, lanes along the row (asynchronous 4-byte copies global -> shared, so the whole
+    //      tile is in flight at once and nothing is staged through registers) ----
     if ((((uintptr_t)tin) & 3) == 0 && (rowb & 3) == 0) {
-      const int rw = rowb >> 2, nwords = (int)(tbytes_in >> 2);
-      int r = lane / rw, c = lane - r * rw;
-      for (int wi = lane; wi < nwords; wi += 32) {
-        rows_w[r * pitch_words + c] = __ldg((const uint32_t*)tin + wi);
-        c += 32;
-        while (c >= rw) { c -= rw; r++; }
+      const int rw = rowb >> 2;
+      const int full = (int)(tbytes_in / (uint32_t)rowb);                 // complete rows; at most one short row follows
+      const uint32_t* gsrc = (const uint32_t*)tin + lane;
+      uint32_t sa = (uint32_t)__cvta_generic_to_shared(rows_w + lane);
+      const uint32_t sstep = (uint32_t)pitch_words * 4;
+      if (rw <= 32) {
+        const bool act = lane < rw;
+#pragma unroll 4
+        for (int r = 0; r < full; r++, gsrc += rw, sa += sstep)
+          if (act) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gsrc) : "memory");
+      } else {
+#pragma unroll 1
+        for (int r = 0; r < full; r++, gsrc += rw, sa += sstep) {
+#pragma unroll 1
+          for (int c = 0; c + lane < rw; c += 32)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa + (uint32_t)c * 4), "l"(gsrc + c) : "memory");
+        }
       }
-      for (uint32_t bi = (uint32_t)nwords * 4 + lane; bi < tbytes_in; bi += 32) {       // < 4 trailing bytes
-        const int rr = (int)(bi / rowb), cc = (int)(bi - (uint32_t)rr * rowb);
-        ((uint8_t*)(rows_w + rr * pitch_words))[cc] = tin[bi];
+      if (full < nrows) {                                                  // short last row of the message
+        const uint32_t left = tbytes_in - (uint32_t)full * (uint32_t)rowb;
+        const int wr = (int)(left >> 2);
+#pragma unroll 1
+        for (int c = 0; c + lane < wr; c += 32)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa + (uint32_t)c * 4), "l"(gsrc + c) : "memory");
+        if (lane < (int)(left & 3)) ((uint8_t*)(rows_w + full * pitch_words))[wr * 4 + lane] = tin[(size_t)full * rowb + wr * 4 + lane];
       }
+      {   // pull this warp's next tile towards L2 meanwhile
+        const long long tn = t + wstep;
+        if (tn < total_tiles && !off) {
+          const int mn = (int)(tn / tiles_per_msg), ktn = (int)(tn - (long long)mn * tiles_per_msg);
+          const char* nx = (const char*)buf + (uint64_t)mn * stride + (size_t)ktn * 32 * rowb;
+          if (lane * 128 < 32 * rowb) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + lane * 128));
+        }
+      }
+      asm volatile("cp.async.wait_all;" ::: "memory");
     } else {
       int r = lane / rowb, c = lane - r * rowb;
       for (uint32_t bi = lane; bi < tbytes_in; bi += 32) {
@@ -367,31 +443,34 @@ __global__ void __launch_bounds__(kRsWarps * 32) rs_tile_kernel(
 #pragma unroll
       for (int i = 0; i < NW; i++) par[i] = 0;
       const int nq = (!DECODE || repair) ? (dlen >> 2) : 0;
+#pragma unroll 2
       for (int j = 0; j < nq; j++) {
-        const uint32_t x = par[0] ^ row[j];
-        const uint32_t* a = T0 + (x & 0xFF) * NW;
-        const uint32_t* b = T1 + ((x >> 8) & 0xFF) * NW;
-        const uint32_t* c = T2 + ((x >> 16) & 0xFF) * NW;
-        const uint32_t* d = T3 + (x >> 24) * NW;
-        if constexpr ((NW & 1) == 0) {                   // 8-byte aligned rows: half as many shared-memory loads
-          const uint2 *a2 = (const uint2*)a, *b2 = (const uint2*)b, *c2 = (const uint2*)c, *d2 = (const uint2*)d;
+        const uint32_t dw = row[j];
+        if constexpr (SL == 2) {
 #pragma unroll
-          for (int i = 0; i < NW / 2; i++) {
-            const uint2 va = a2[i], vb = b2[i], vc = c2[i], vd = d2[i];
-            par[2 * i] = par[2 * i + 1] ^ va.x ^ vb.x ^ vc.x ^ vd.x;
-            par[2 * i + 1] = ((2 * i + 2 < NW) ? par[2 * i + 2] : 0u) ^ va.y ^ vb.y ^ vc.y ^ vd.y;
+          for (int h = 0; h < 2; h++) {
+            const uint32_t x = par[0] ^ (h ? (dw >> 16) : dw);
+#pragma unroll
+            for (int i = 0; i < NW; i++) par[i] = __byte_perm(par[i], (i + 1 < NW) ? par[i + 1] : 0u, 0x5432);
+            fetch_row<NW>(lane_base, 0, x & 0xFF, par);
+            fetch_row<NW>(lane_base, 1, (x >> 8) & 0xFF, par);
           }
         } else {
 #pragma unroll
-          for (int i = 0; i < NW; i++) par[i] = ((i + 1 < NW) ? par[i + 1] : 0u) ^ a[i] ^ b[i] ^ c[i] ^ d[i];
+          for (int h = 0; h < 4; h++) {
+            const uint32_t f = (par[0] ^ (dw >> (8 * h))) & 0xFF;
+#pragma unroll
+            for (int i = 0; i < NW; i++) par[i] = (i + 1 < NW) ? __funnelshift_r(par[i], par[i + 1], 8) : (par[i] >> 8);
+            fetch_row<NW>(lane_base, 0, f, par);
+          }
         }
       }
       const uint8_t* rb = (const uint8_t*)row;
       for (int j = nq * 4; j < ((!DECODE || repair) ? dlen : 0); j++) {
         const uint32_t f = (par[0] ^ rb[j]) & 0xFF;
-        const uint32_t* rr = T3 + f * NW;
 #pragma unroll
-        for (int i = 0; i < NW; i++) par[i] = ((i + 1 < NW) ? __funnelshift_r(par[i], par[i + 1], 8) : (par[i] >> 8)) ^ rr[i];
+        for (int i = 0; i < NW; i++) par[i] = (i + 1 < NW) ? __funnelshift_r(par[i], par[i + 1], 8) : (par[i] >> 8);
+        fetch_row<NW>(lane_base, SL - 1, f, par);
       }
       if (!DECODE) {
         uint8_t* pb = (uint8_t*)row + dlen;              // parity follows the data inside the staged row
@@ -423,14 +502,36 @@ __global__ void __launch_bounds__(kRsWarps * 32) rs_tile_kernel(
     __syncwarp();
     // ---- write back: rows are contiguous in the output (all rows full except possibly the last) ----
     uint8_t* tout = dst + (size_t)k0 * outb;
-    for (int r = 0; r < nrows; r++) {
-      const int rl = __shfl_sync(0xffffffffu, DECODE ? dlen : (dlen + csize), r);
-      const uint32_t* row = rows_w + r * pitch_words;
-      uint8_t* orow = tout + (size_t)r * outb;
-      if ((((uintptr_t)orow) & 3) == 0 && (rl & 3) == 0) {
-        for (int j = lane; j < (rl >> 2); j += 32) ((uint32_t*)orow)[j] = row[j];
+    const int my_out = DECODE ? dlen : (dlen + csize);
+    if ((((uintptr_t)tout) & 3) == 0 && (outb & 3) == 0) {
+      const uint32_t* row = rows_w + lane;
+      uint32_t* orow = (uint32_t*)tout + lane;
+      const int ow = outb >> 2;
+      const int last_len = __shfl_sync(0xffffffffu, my_out, nrows - 1);   // only the last row can be short
+      const int full = (last_len == outb) ? nrows : nrows - 1;
+      if (ow <= 32) {
+        const bool act = lane < ow;
+#pragma unroll 4
+        for (int r = 0; r < full; r++, row += pitch_words, orow += ow)
+          if (act) *orow = *row;
       } else {
-        for (int j = lane; j < rl; j += 32) orow[j] = ((const uint8_t*)row)[j];
+#pragma unroll 1
+        for (int r = 0; r < full; r++, row += pitch_words, orow += ow) {
+#pragma unroll 1
+          for (int j = 0; j + lane < ow; j += 32) orow[j] = row[j];
+        }
+      }
+      if (full < nrows) {
+#pragma unroll 1
+        for (int j = 0; j + lane < (last_len >> 2); j += 32) orow[j] = row[j];
+        if (lane < (last_len & 3)) ((uint8_t*)(orow - lane))[(last_len & ~3) + lane] = ((const uint8_t*)(row - lane))[(last_len & ~3) + lane];
+      }
+    } else {
+      for (int r = 0; r < nrows; r++) {
+        const int rl = __shfl_sync(0xffffffffu, my_out, r);
+        const uint8_t* row = (const uint8_t*)(rows_w + r * pitch_words);
+        uint8_t* orow = tout + (size_t)r * outb;
+        for (int j = lane; j < rl; j += 32) orow[j] = row[j];
       }
     }
     if (DECODE && (status || fixed)) {
@@ -447,35 +548,46 @@ __global__ void __launch_bounds__(kRsWarps * 32) rs_tile_kernel(
   }
 }
 
-template <bool DECODE>
-int launch_tiles(frad_ctx* ctx, const uint8_t* buf, const uint64_t* off, const uint32_t* len, size_t stride, uint32_t ulen, int B,
-                 int dsize, int csize, int repair, const rs_table* t, uint8_t* out, const uint64_t* out_off, size_t out_stride,
-                 int32_t* status, int32_t* fixed, uint32_t max_len) {
+template <int NW, bool DECODE>
+int launch_tiles_nw(frad_ctx* ctx, const uint8_t* buf, const uint64_t* off, const uint32_t* len, size_t stride, uint32_t ulen, int B,
+                    int dsize, int repair, const rs_table* t, uint8_t* out, const uint64_t* out_off, size_t out_stride,
+                    int32_t* status, int32_t* fixed, uint32_t max_len) {
+  typedef rs_planes<NW> PL;
+  const int csize = NW * 4;
   const int rowb = DECODE ? dsize + csize : dsize;
   const int staged = dsize + csize;                                   // encode appends the parity inside the staged row
   const int pitch = ((staged + 3) / 4) | 1;
   const int tiles_per_msg = (int)(((max_len + rowb - 1) / rowb + 31) / 32);
   if (tiles_per_msg < 1) return FRAD_OK;
-  const size_t tb = (table_bytes_sliced(csize) + 15) & ~(size_t)15;
-  const size_t smem = tb + (size_t)kRsWarps * 32 * pitch * 4;
+  const size_t fixed_bytes = (((size_t)PL::SL * PL::COUNT * kPlaneWords * 4 + sizeof(rs_table)) + 15) & ~(size_t)15;
+  const size_t per_warp = (size_t)32 * pitch * 4;
   const long long total = (long long)B * tiles_per_msg;
-  long long want = (total + kRsWarps - 1) / kRsWarps;
-  const void* k = nullptr;
-#define RS_PICK(NWV) case NWV: k = (const void*)rs_tile_kernel<NWV, DECODE>; break;
-  switch (csize / 4) { RS_PICK(1) RS_PICK(2) RS_PICK(3) RS_PICK(4) RS_PICK(5) RS_PICK(6) RS_PICK(7) RS_PICK(8) default: return FRAD_E_UNSUPPORTED; }
-#undef RS_PICK
+  int warps = (int)((ctx->smem_optin - fixed_bytes) / per_warp);
+  if (warps > kRsMaxWarps) warps = kRsMaxWarps;
+  if (warps < 1) return frad_fail(ctx, FRAD_E_UNSUPPORTED, "rs tile kernel does not fit in shared memory");
+  long long per_cta_even = (total + ctx->sm_count - 1) / ctx->sm_count;   // small batches: no idle warps around the tables
+  if (per_cta_even < warps) warps = (int)(per_cta_even < 1 ? 1 : per_cta_even);
+  const size_t smem = fixed_bytes + (size_t)warps * per_warp;
+  long long want = (total + warps - 1) / warps;
+  auto k = rs_tile_kernel<NW, DECODE>;
   FRAD_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 1;
-  FRAD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kRsWarps * 32, smem));
-  if (per_sm < 1) per_sm = 1;
-  const long long cap = (long long)per_sm * ctx->sm_count;
-  const int grid = (int)(want < cap ? want : cap);
-  void* args[] = {(void*)&buf, (void*)&off, (void*)&len, (void*)&stride, (void*)&ulen, (void*)&B, (void*)&dsize, (void*)&repair,
-                  (void*)&t, (void*)&out, (void*)&out_off, (void*)&out_stride, (void*)&status, (void*)&fixed,
-                  (void*)&tiles_per_msg, (void*)&pitch};
-  FRAD_CUDA(ctx, cudaLaunchKernel(k, dim3(grid), dim3(kRsWarps * 32), args, smem, ctx->stream));
+  const int grid = (int)(want < ctx->sm_count ? want : ctx->sm_count);
+  k<<<grid, warps * 32, smem, ctx->stream>>>(buf, off, len, stride, ulen, B, dsize, repair, t, out, out_off, out_stride, status, fixed,
+                                            tiles_per_msg, pitch);
   FRAD_LAUNCH_CHECK(ctx);
   return FRAD_OK;
+}
+
+template <bool DECODE>
+int launch_tiles(frad_ctx* ctx, const uint8_t* buf, const uint64_t* off, const uint32_t* len, size_t stride, uint32_t ulen, int B,
+                 int dsize, int csize, int repair, const rs_table* t, uint8_t* out, const uint64_t* out_off, size_t out_stride,
+                 int32_t* status, int32_t* fixed, uint32_t max_len) {
+#define RS_PICK(NWV)                                                                                                         \
+  case NWV:                                                                                                                  \
+    return launch_tiles_nw<NWV, DECODE>(ctx, buf, off, len, stride, ulen, B, dsize, repair, t, out, out_off, out_stride, status, \
+                                        fixed, max_len);
+  switch (csize / 4) { RS_PICK(1) RS_PICK(2) RS_PICK(3) RS_PICK(4) RS_PICK(5) RS_PICK(6) RS_PICK(7) RS_PICK(8) default: return FRAD_E_UNSUPPORTED; }
+#undef RS_PICK
 }
 
 bool tile_ok(int csize) { return csize >= 4 && csize <= 32 && (csize & 3) == 0; }

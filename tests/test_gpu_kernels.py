@@ -183,6 +183,29 @@ def test_crc_golden_and_random(ctx, g_crc):
     assert int(c32[6]) == 0xCBF43926 and int(c16[6]) == 0xBB3D
 
 
+def test_crc_unaligned_offsets_uniform_stride_and_segments(ctx):
+    """Messages at odd addresses, the uniform-stride form, and long messages in small batches (which the kernel cuts
+    into per-warp segments whose remainders are combined afterwards) must all give zlib's values."""
+    from frad_python_b200._abi import lib
+    rng = np.random.default_rng(7)
+    lens = np.array([0, 1, 2, 3, 4, 5, 7, 127, 128, 129, 131, 4099, 16384, 20488, 65537, 300001], np.uint32)
+    offs, pos = [], 1
+    for i, n in enumerate(lens):
+        offs.append(pos)
+        pos += int(n) + 1 + (i % 3)                       # every alignment class occurs
+    offs = np.array(offs, np.uint64)
+    buf = rng.integers(0, 256, pos + 8, dtype=np.uint8)
+    msgs = [buf[int(o):int(o) + int(n)].tobytes() for o, n in zip(offs, lens)]
+    for bits32, fn, ref in ((True, lib().frad_crc32, O.crc32), (False, lib().frad_crc16, O.crc16_arc)):
+        out = np.zeros(len(lens), np.uint32)
+        ctx.check(fn(ctx.handle, buf.ctypes.data, offs.ctypes.data, lens.ctypes.data, 0, 0, len(lens), buf.size, out.ctypes.data))
+        assert [int(x) for x in out] == [ref(m) for m in msgs], bits32
+        # uniform stride, no index arrays: 5 messages of 50 001 bytes, 50 003 bytes apart (odd addresses)
+        out = np.zeros(5, np.uint32)
+        ctx.check(fn(ctx.handle, buf.ctypes.data, None, None, 50003, 50001, 5, buf.size, out.ctypes.data))
+        assert [int(x) for x in out] == [ref(buf[i * 50003:i * 50003 + 50001].tobytes()) for i in range(5)], bits32
+
+
 def test_rs_encode_golden(ctx, g_crc):
     for key in g_crc.files:
         if not key.startswith("ecc_in_"):
