@@ -95,6 +95,12 @@ def lib():
             "frad_rs_decode": (i32, [vp, vp, vp, vp, sz, u32, i32, sz, i32, i32, i32, vp, vp, sz, sz, vp, vp]),
         }
         sig.update({
+            "frad_p1_raw_bound": (sz, [i32, i32, i32]),
+            "frad_p1_pack_dev": (i32, [vp, vp, vp, vp, i32, i32, i32, vp, sz, vp]),
+            "frad_compact_dev": (i32, [vp, vp, sz, vp, i32, vp, sz, vp]),
+            "frad_p1_unpack_dev": (i32, [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]),
+            "frad_p1_encode_raw": (i32, [vp, vp, i32, i64, i32, i32, i32, i32, i32, dbl, i32, i32, vp, sz, vp]),
+            "frad_p1_decode_raw": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp]),
             "frad_golomb_encode_host": (i64, [vp, sz, vp, sz]),
             "frad_golomb_decode_host": (i64, [vp, sz, vp, sz]),
             "frad_golomb_encode_batch_host": (i32, [vp, i32, sz, vp, sz, vp, i32]),
@@ -123,6 +129,8 @@ EXPORTS = [
     "frad_rs_encode", "frad_rs_decode",
     "frad_golomb_encode_host", "frad_golomb_decode_host", "frad_golomb_encode_batch_host",
     "frad_golomb_decode_batch_host",
+    "frad_p1_raw_bound", "frad_p1_pack_dev", "frad_compact_dev", "frad_p1_unpack_dev", "frad_p1_encode_raw",
+    "frad_p1_decode_raw",
 ]
 
 
@@ -277,6 +285,36 @@ class Context:
         self.check(lib().frad_p1_decode(self.handle, q.ctypes.data, tq.ctypes.data, _ptr(lpc), nframes, n, ch, bits,
                                          srate, prec, out.ctypes.data, dtype_code(out.dtype)))
         return out
+
+    def p1_encode_raw(self, pcm: np.ndarray, nframes: int, n: int, hop: int, bits: int, srate: int, loss_level: float,
+                      prec: int = PREC_REF, profile: int = 1):
+        """PCM -> the byte string of every frame that the reference deflates (profile1.py:43-46 / profile2.py:48-51),
+        Exp-Golomb-Rice packed on the device.  Returns (uint8 buffer, uint64 offsets [B+1])."""
+        pcm = np.ascontiguousarray(pcm)
+        ch = pcm.shape[1]
+        off = np.zeros(nframes + 1, np.uint64)
+        cap = max(64, nframes * (n * ch * 5 // 4 + 64))            # 10 bits per value: ample for audio; retried below if not
+        for _ in range(2):
+            raw = np.empty(cap, np.uint8)
+            rc = lib().frad_p1_encode_raw(self.handle, pcm.ctypes.data, dtype_code(pcm.dtype), hop, nframes, n, ch, bits, srate,
+                                          float(loss_level), prec, profile, raw.ctypes.data, cap, off.ctypes.data)
+            if rc == -3 and int(off[nframes]) > cap:                # FRAD_E_NOMEM: off[B] holds the size needed
+                cap = int(off[nframes])
+                continue
+            self.check(rc)
+            return raw, off
+        raise FradError("frad_p1_encode_raw: output did not fit twice")
+
+    def p1_decode_raw(self, raw: np.ndarray, off: np.ndarray, nframes: int, n: int, ch: int, bits: int, srate: int,
+                      prec: int = PREC_REF, profile: int = 1, out_dtype=np.float64):
+        """Inverse of p1_encode_raw.  Returns (pcm [B, n, ch], status int32 [B])."""
+        raw = np.ascontiguousarray(raw, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        out = np.empty((nframes, n, ch), out_dtype)
+        status = np.zeros(nframes, np.int32)
+        self.check(lib().frad_p1_decode_raw(self.handle, raw.ctypes.data, off.ctypes.data, nframes, n, ch, bits, srate, prec,
+                                             profile, out.ctypes.data, dtype_code(out.dtype), status.ctypes.data))
+        return out, status
 
     # -- CRC / RS over host byte strings ---------------------------------------------------------
     @staticmethod

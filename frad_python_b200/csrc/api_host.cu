@@ -347,3 +347,116 @@ extern "C" int frad_rs_decode(frad_ctx* ctx, const uint8_t* buf, const uint64_t*
   if (fixed && (rc = frad_d2h(ctx, fixed, d_fixed, 4 * (size_t)B))) return rc;
   return frad_sync(ctx);
 }
+
+// ---- profile 1 / 2 with the bit packing on the device: PCM <-> frame payloads before deflate -------------------
+// Same pipeline as above, but what crosses PCIe on the coded side is the Exp-Golomb-Rice byte string of every frame
+// (profile1.py:43-46 / profile2.py:48-51) instead of the int32 streams: about five times fewer bytes.
+int frad_compact_append(frad_ctx* ctx, const uint8_t* src, size_t stride, const uint32_t* len, int B, uint8_t* dst, uint64_t dst_cap,
+                        uint64_t* dst_off, uint64_t* running);   // golomb.cu
+
+extern "C" int frad_p1_encode_raw(frad_ctx* ctx, const void* pcm, int pcm_dtype, int64_t hop, int B, int N, int C,
+                                  int bits, int srate, double loss_level, int prec, int profile,
+                                  uint8_t* raw, size_t raw_cap, uint64_t* raw_off) {
+  if (!ctx) return FRAD_E_ARG;
+  const int es = frad_dtype_size(pcm_dtype);
+  if (!es || B < 0 || N < 1 || C < 1 || hop < 0 || !raw_off || (profile != 1 && profile != 2) || (!raw && raw_cap))
+    return frad_fail(ctx, FRAD_E_ARG, "frad_p1_encode_raw: bad argument");
+  raw_off[0] = 0;
+  if (B == 0) return FRAD_OK;
+  FRAD_CUDA(ctx, cudaSetDevice(ctx->device));
+  const bool p2 = profile == 2;
+  const size_t samp = (size_t)C * es;
+  const size_t in_bytes = ((size_t)(B - 1) * (size_t)hop + (size_t)N) * samp;
+  const size_t qf = (size_t)N * C, tf = (size_t)FRAD_NBANDS * C, lf = (size_t)FRAD_LPC_LEN * C;
+  const size_t stride = frad_p1_raw_bound(N, C, p2);
+  const size_t cf = (size_t)(B < kChunkFrames ? B : kChunkFrames);     // frames per chunk: the int / strided scratch is per chunk
+  ARENA(ctx, a, rounded(in_bytes) + rounded(4 * qf * cf) + rounded(4 * tf * cf) + rounded(4 * lf * cf) + rounded(stride * cf) +
+                    rounded(4 * cf) + rounded(raw_cap) + rounded(8 * ((size_t)B + 1)) + rounded(8));
+  char* d_in = (char*)take(a, in_bytes);
+  int32_t* d_q = (int32_t*)take(a, 4 * qf * cf);
+  int32_t* d_tq = (int32_t*)take(a, 4 * tf * cf);
+  int32_t* d_l = p2 ? (int32_t*)take(a, 4 * lf * cf) : nullptr;
+  uint8_t* d_strided = (uint8_t*)take(a, stride * cf);
+  uint32_t* d_len = (uint32_t*)take(a, 4 * cf);
+  uint8_t* d_raw = (uint8_t*)take(a, raw_cap ? raw_cap : 1);
+  uint64_t* d_off = (uint64_t*)take(a, 8 * ((size_t)B + 1));
+  uint64_t* d_total = (uint64_t*)take(a, 8);
+  if (a.bad) return frad_fail(ctx, FRAD_E_NOMEM, "internal arena overflow");
+  FRAD_CUDA(ctx, cudaMemsetAsync(d_total, 0, 8, ctx->stream));
+  pipeline p;
+  int rc = pipeline_begin(ctx, B, &p);
+  if (rc) return rc;
+  bool overflow = false;
+  rc = pipeline_run(p, B, hop < N,
+    [&](int, int f0, int f1, cudaStream_t s) {
+      const size_t lo = (size_t)f0 * hop * samp;
+      const size_t hi = (f1 == B) ? in_bytes : (size_t)f1 * hop * samp;
+      return copy_async(ctx, d_in + lo, (const char*)pcm + lo, hi - lo, H2D_, s);
+    },
+    [&](int f0, int f1) {
+      const int nb = f1 - f0;
+      int r = frad_p1_encode_dev(ctx, d_in + (size_t)f0 * hop * samp, pcm_dtype, hop, nb, N, C, bits, srate, loss_level, prec,
+                                 d_q, d_tq, d_l);
+      if (!r) r = frad_p1_pack_dev(ctx, d_q, d_tq, d_l, nb, N, C, d_strided, stride, d_len);
+      if (!r) r = frad_compact_append(ctx, d_strided, stride, d_len, nb, d_raw, raw_cap, d_off + f0, d_total);
+      return r;
+    },
+    [&](int f0, int f1, cudaStream_t s) -> int {
+      // offsets first (the byte range of this chunk is only known on the device), then the bytes themselves
+      int r = copy_async(ctx, raw_off + f0, d_off + f0, 8 * (size_t)(f1 - f0 + 1), D2H_, s);
+      if (r) return r;
+      FRAD_CUDA(ctx, cudaStreamSynchronize(s));
+      if (raw_off[f1] > raw_cap) { overflow = true; return (int)FRAD_OK; }
+      return copy_async(ctx, raw + raw_off[f0], d_raw + raw_off[f0], (size_t)(raw_off[f1] - raw_off[f0]), D2H_, s);
+    });
+  if (rc) return rc;
+  if (overflow) return frad_fail(ctx, FRAD_E_NOMEM, "frad_p1_encode_raw: raw_cap too small (raw_off[B] holds the size needed)");
+  return FRAD_OK;
+}
+
+extern "C" int frad_p1_decode_raw(frad_ctx* ctx, const uint8_t* raw, const uint64_t* raw_off, int B, int N, int C,
+                                  int bits, int srate, int prec, int profile, void* pcm, int pcm_dtype, int32_t* status) {
+  if (!ctx) return FRAD_E_ARG;
+  const int es = frad_dtype_size(pcm_dtype);
+  if (!es || B < 0 || N < 1 || C < 1 || !raw_off || (profile != 1 && profile != 2))
+    return frad_fail(ctx, FRAD_E_ARG, "frad_p1_decode_raw: bad argument");
+  if (B == 0) return FRAD_OK;
+  FRAD_CUDA(ctx, cudaSetDevice(ctx->device));
+  const bool p2 = profile == 2;
+  const size_t qf = (size_t)N * C, tf = (size_t)FRAD_NBANDS * C, lf = (size_t)FRAD_LPC_LEN * C;
+  const size_t fbytes = qf * es;
+  const size_t total = (size_t)raw_off[B];
+  const size_t cf = (size_t)(B < kChunkFrames ? B : kChunkFrames);
+  ARENA(ctx, a, rounded(total + 16) + rounded(8 * ((size_t)B + 1)) + rounded(4 * qf * cf) + rounded(4 * tf * cf) + rounded(4 * lf * cf) +
+                    rounded(fbytes * B) + rounded(4 * (size_t)B));
+  uint8_t* d_raw = (uint8_t*)take(a, total + 16);
+  uint64_t* d_off = (uint64_t*)take(a, 8 * ((size_t)B + 1));
+  int32_t* d_q = (int32_t*)take(a, 4 * qf * cf);
+  int32_t* d_tq = (int32_t*)take(a, 4 * tf * cf);
+  int32_t* d_l = p2 ? (int32_t*)take(a, 4 * lf * cf) : nullptr;
+  char* d_out = (char*)take(a, fbytes * B);
+  int32_t* d_status = (int32_t*)take(a, 4 * (size_t)B);
+  if (a.bad) return frad_fail(ctx, FRAD_E_NOMEM, "internal arena overflow");
+  pipeline p;
+  int rc = pipeline_begin(ctx, B, &p);
+  if (rc) return rc;
+  rc = pipeline_run(p, B, false,
+    [&](int i, int f0, int f1, cudaStream_t s) {
+      int r = FRAD_OK;
+      if (i == 0) r = copy_async(ctx, d_off, raw_off, 8 * ((size_t)B + 1), H2D_, s);
+      if (!r) r = copy_async(ctx, d_raw + raw_off[f0], raw + raw_off[f0], (size_t)(raw_off[f1] - raw_off[f0]), H2D_, s);
+      return r;
+    },
+    [&](int f0, int f1) {
+      const int nb = f1 - f0;
+      int r = frad_p1_unpack_dev(ctx, d_raw, d_off + f0, nb, N, C, p2 ? 1 : 0, d_q, d_tq, d_l, d_status + f0);
+      if (!r) r = frad_p1_decode_dev(ctx, d_q, d_tq, d_l, nb, N, C, bits, srate, prec, d_out + (size_t)f0 * fbytes, pcm_dtype);
+      return r;
+    },
+    [&](int f0, int f1, cudaStream_t s) {
+      int r = copy_async(ctx, (char*)pcm + (size_t)f0 * fbytes, d_out + (size_t)f0 * fbytes, (size_t)(f1 - f0) * fbytes, D2H_, s);
+      if (!r && status) r = copy_async(ctx, status + f0, d_status + f0, 4 * (size_t)(f1 - f0), D2H_, s);
+      return r;
+    });
+  return rc;
+}

@@ -1,0 +1,395 @@
+// Exp-Golomb-Rice bit coder of fourier/tools/p1tools.py:46-74 on the device, and the assembly / parsing of
+// the profile-1 / profile-2 frame payload that the reference deflates (profile1.py:43-46, :61-62;
+// profile2.py:48-51, :66-69).  Deflate itself stays on the host (north_star).
+//
+// Bit format (p1tools.py:46-60): one byte k = ceil(log2(max|v|)) (0 when every value is 0), then per value
+// u = 2v-1 (v > 0) else -2v, w = u + 2^k written as (bitlen(w) - k - 1) zero bits followed by w in bitlen(w)
+// bits, MSB first, zero-padded to a whole byte.  Because k is derived from the maximum, bitlen(w) <= k + 2:
+// every code is k+1 or k+3 bits long (<= 35 bits for 32-bit values).
+//
+// pack    one CTA per frame: max-reduce -> k, code lengths, block-wide exclusive scan -> bit offsets; every
+//         thread assembles the codes of its 16 consecutive values in a 64-bit register and writes whole
+//         32-bit words into a shared-memory bit buffer (atomicOr only on the two words it shares with its
+//         neighbours); the buffer is written out as bytes, stream after stream, with the length prefixes.
+// compact exclusive scan of the per-frame lengths + byte copy into one contiguous buffer (what goes over
+//         PCIe: about 5 times fewer bytes than the int32 streams).
+// unpack  one thread per frame (the code boundaries form a serial chain): a 64-bit register window over
+//         big-endian words, count-leading-zeros for the unary part, one variable shift per value; four
+//         values per 16-byte store.  Thousands of frames decode in parallel.
+#include "common.cuh"
+
+namespace {
+
+constexpr int GE_THREADS = 256;
+constexpr int GE_VPT = 16;                                  // values per thread and chunk
+constexpr int GE_CHUNK = GE_THREADS * GE_VPT;               // 4096 values
+constexpr int GE_WORDS = (GE_CHUNK * 35 + 31) / 32 + 2;     // bit buffer of one chunk (+ carried partial word)
+
+struct ge_smem {
+  uint32_t bits[GE_WORDS];
+  uint32_t warp_tot[GE_THREADS / 32];
+  uint32_t red[GE_THREADS / 32];
+};
+
+__device__ __forceinline__ uint32_t block_max(uint32_t v, ge_smem* sm) {
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, s));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sm->red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  uint32_t r = 0;
+#pragma unroll
+  for (int i = 0; i < GE_THREADS / 32; i++) r = max(r, sm->red[i]);
+  return r;
+}
+
+// exclusive prefix of `v` over the CTA; *total receives the CTA sum
+__device__ __forceinline__ uint32_t block_exscan(uint32_t v, ge_smem* sm, uint32_t* total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int s = 1; s < 32; s <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, s); if (lane >= s) inc += t; }
+  __syncthreads();
+  if (lane == 31) sm->warp_tot[w] = inc;
+  __syncthreads();
+  uint32_t base = 0, tot = 0;
+#pragma unroll
+  for (int i = 0; i < GE_THREADS / 32; i++) { const uint32_t t = sm->warp_tot[i]; if (i < w) base += t; tot += t; }
+  *total = tot;
+  return base + inc - v;
+}
+
+// code of one value: w (the bits) and its length in bits
+__device__ __forceinline__ void code_of(int32_t v, int k, uint64_t* w, int* len) {
+  const uint64_t a = (v < 0) ? (uint64_t)(-(int64_t)v) : (uint64_t)v;
+  const uint64_t u = (v > 0) ? 2 * a - 1 : 2 * a;
+  const uint64_t x = u + (1ull << k);
+  const int nb = 64 - __clzll((long long)x);
+  *w = x;
+  *len = 2 * nb - (k + 1);
+}
+
+// Encodes the stream v[0..n) to dst (k byte + bits); returns the byte length.  All threads of the CTA take part.
+__device__ uint32_t encode_stream(const int32_t* __restrict__ v, int n, uint8_t* __restrict__ dst, ge_smem* sm) {
+  const int tid = threadIdx.x;
+  if (n <= 0) { if (tid == 0) dst[0] = 0; return 1; }
+  uint32_t mx = 0;
+  for (int i = tid; i < n; i += GE_THREADS) { const int32_t x = v[i]; mx = max(mx, (uint32_t)((x < 0) ? -(int64_t)x : (int64_t)x)); }
+  mx = block_max(mx, sm);
+  const int k = (mx <= 1) ? 0 : 32 - __clz((int)(mx - 1));
+  if (tid == 0) dst[0] = (uint8_t)k;
+  uint8_t* out = dst + 1;
+  uint64_t bitpos = 0;                                        // bits already flushed to `out` (multiple of 32) + carried bits
+  uint32_t carry = 0;                                         // bits of the partial word kept in sm->bits[0]
+  for (int c0 = 0; c0 < n; c0 += GE_CHUNK) {
+    for (int i = tid; i < GE_WORDS; i += GE_THREADS) if (i > 0 || c0 == 0) sm->bits[i] = 0;
+    // this thread's values: [c0 + 16 tid, +16)
+    const int i0 = c0 + tid * GE_VPT;
+    uint64_t w[GE_VPT];
+    int len[GE_VPT];
+    uint32_t mine = 0;
+#pragma unroll
+    for (int j = 0; j < GE_VPT; j++) {
+      if (i0 + j < n) code_of(v[i0 + j], k, &w[j], &len[j]); else { w[j] = 0; len[j] = 0; }
+      mine += (uint32_t)len[j];
+    }
+    uint32_t chunk_bits;
+    const uint32_t start = carry + block_exscan(mine, sm, &chunk_bits);     // bit offset inside sm->bits
+    // (block_exscan's barriers also order the zeroing above before the writes below)
+    if (mine) {
+      uint32_t wi = start >> 5;
+      int nacc = (int)(start & 31);                           // bits of word wi that belong to the threads before
+      uint64_t acc = 0;
+      bool first = true;
+      auto emit = [&]() {
+        const uint32_t word = (uint32_t)(acc >> (nacc - 32));
+        if (first) { atomicOr(&sm->bits[wi], word); first = false; } else sm->bits[wi] = word;
+        wi++; nacc -= 32;
+      };
+#pragma unroll
+      for (int j = 0; j < GE_VPT; j++) {
+        int l = len[j];
+        if (l > 32) { acc = (acc << (l - 16)) | (w[j] >> 16); nacc += l - 16; if (nacc >= 32) emit(); w[j] &= 0xFFFFu; l = 16; }
+        if (l) { acc = (acc << l) | w[j]; nacc += l; if (nacc >= 32) emit(); }
+      }
+      if (nacc > 0) atomicOr(&sm->bits[wi], (uint32_t)(acc << (32 - nacc)));
+    }
+    __syncthreads();
+    // flush the complete words (big-endian byte order) and keep the partial one for the next chunk
+    const uint32_t filled = carry + chunk_bits;
+    const bool last = (c0 + GE_CHUNK >= n);
+    const uint32_t nbytes = last ? (filled + 7) / 8 : (filled / 32) * 4;
+    uint8_t* o = out + (bitpos >> 3);
+    for (uint32_t b = tid; b < nbytes; b += GE_THREADS) o[b] = (uint8_t)(sm->bits[b >> 2] >> (24 - 8 * (b & 3)));
+    if (last) return 1 + (uint32_t)(bitpos >> 3) + nbytes;
+    const uint32_t keep = sm->bits[filled / 32];
+    __syncthreads();
+    if (tid == 0) sm->bits[0] = keep;
+    bitpos += (filled / 32) * 32;
+    carry = filled & 31;
+    __syncthreads();
+  }
+  return 0;   // not reached
+}
+
+__global__ void __launch_bounds__(GE_THREADS) p1_pack_kernel(const int32_t* __restrict__ q, const int32_t* __restrict__ tq,
+                                                             const int32_t* __restrict__ lpc, int B, int nq, int ntq, int nlpc,
+                                                             uint8_t* __restrict__ raw, size_t stride, uint32_t* __restrict__ raw_len) {
+  __shared__ ge_smem sm;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    uint8_t* out = raw + (size_t)b * stride;
+    uint32_t pos = 0;
+    if (lpc) {                                                 // profile2.py:51  >H len || gol(lpc)
+      const uint32_t L = encode_stream(lpc + (size_t)b * nlpc, nlpc, out + 2, &sm);
+      if (threadIdx.x == 0) { out[0] = (uint8_t)(L >> 8); out[1] = (uint8_t)L; }
+      pos = 2 + L;
+      __syncthreads();
+    }
+    {                                                          // profile1.py:45  >I len || gol(thresholds)
+      const uint32_t L = encode_stream(tq + (size_t)b * ntq, ntq, out + pos + 4, &sm);
+      if (threadIdx.x == 0) { out[pos] = (uint8_t)(L >> 24); out[pos + 1] = (uint8_t)(L >> 16); out[pos + 2] = (uint8_t)(L >> 8); out[pos + 3] = (uint8_t)L; }
+      pos += 4 + L;
+      __syncthreads();
+    }
+    pos += encode_stream(q + (size_t)b * nq, nq, out + pos, &sm);
+    if (threadIdx.x == 0) raw_len[b] = pos;
+    __syncthreads();
+  }
+}
+
+// ---- compaction -----------------------------------------------------------------------------------------
+// off[0] = base, off[i+1] = off[i] + len[i]; one CTA, any B.  base = *running (0 when running == NULL); *running is
+// advanced to off[B] so that consecutive chunks append to one buffer.
+__global__ void __launch_bounds__(1024) scan_len_kernel(const uint32_t* __restrict__ len, int B, uint64_t* __restrict__ off,
+                                                        unsigned long long* running) {
+  __shared__ unsigned long long wsum[32];
+  __shared__ unsigned long long carry_s;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { carry_s = running ? *running : 0; off[0] = carry_s; }
+  __syncthreads();
+  for (int base = 0; base < B; base += 1024) {
+    const int i = base + threadIdx.x;
+    const unsigned long long v = (i < B) ? len[i] : 0;
+    unsigned long long inc = v;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) { const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, s); if (lane >= s) inc += t; }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    unsigned long long pre = carry_s;
+    for (int j = 0; j < w; j++) pre += wsum[j];
+    if (i < B) off[i + 1] = pre + inc;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = pre + inc;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && running) *running = carry_s;
+}
+
+__global__ void __launch_bounds__(128) compact_kernel(const uint8_t* __restrict__ src, size_t stride, const uint64_t* __restrict__ off,
+                                                      int B, uint8_t* __restrict__ dst, uint64_t dst_cap) {
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    if (off[b + 1] > dst_cap) continue;                      // does not fit: the caller sees off[B] > capacity
+    const uint8_t* s = src + (size_t)b * stride;
+    uint8_t* d = dst + off[b];
+    const uint32_t n = (uint32_t)(off[b + 1] - off[b]);
+    // word copies where source and destination agree modulo 4, bytes otherwise
+    const uint32_t head = min(n, (uint32_t)((4 - ((uintptr_t)d & 3)) & 3));
+    if ((((uintptr_t)(s + head)) & 3) == 0) {
+      if (threadIdx.x < head) d[threadIdx.x] = s[threadIdx.x];
+      const uint32_t nw = (n - head) >> 2;
+      const uint32_t* sw = (const uint32_t*)(s + head);
+      uint32_t* dw = (uint32_t*)(d + head);
+      for (uint32_t i = threadIdx.x; i < nw; i += blockDim.x) dw[i] = sw[i];
+      for (uint32_t i = head + nw * 4 + threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
+    } else {
+      // misaligned pair: aligned destination words assembled from two aligned source words
+      if (threadIdx.x < head) d[threadIdx.x] = s[threadIdx.x];
+      const uint32_t nw = (n - head) >> 2;
+      const uint8_t* sp = s + head;
+      const uint32_t sh = (uint32_t)((uintptr_t)sp & 3) * 8;
+      const uint32_t* sw = (const uint32_t*)((uintptr_t)sp & ~(uintptr_t)3);
+      uint32_t* dw = (uint32_t*)(d + head);
+      for (uint32_t i = threadIdx.x; i < nw; i += blockDim.x) dw[i] = __funnelshift_r(sw[i], sw[i + 1], sh);
+      for (uint32_t i = head + nw * 4 + threadIdx.x; i < n; i += blockDim.x) d[i] = s[i];
+    }
+  }
+}
+
+// ---- decode ---------------------------------------------------------------------------------------------
+struct bit_window {
+  const uint32_t* w; uint32_t wi, nwords, last_mask;
+  uint64_t win; int navail;
+  __device__ __forceinline__ uint32_t word() {
+    uint32_t x = 0;
+    if (wi < nwords) {
+      x = __byte_perm(__ldg(w + wi), 0, 0x0123);
+      if (wi == nwords - 1) x &= last_mask;
+    }
+    wi++;
+    return x;
+  }
+  __device__ __forceinline__ void refill() {                   // navail <= 32 -> navail in (32, 64]
+    if (navail <= 32) { win |= (uint64_t)word() << (32 - navail); navail += 32; }
+  }
+  __device__ __forceinline__ void drop(int n) { win = (n >= 64) ? 0 : (win << n); navail -= n; }
+};
+
+// p1tools.py:62-74.  d[0..len): k byte + bits.  Writes min(count, cap) values, zero-fills up to cap; returns 0, or 1 when
+// the stream holds a code no 32-bit value can produce (k > 32 or a unary run > 32) -- decoding stops there.
+__device__ int decode_stream(const uint8_t* __restrict__ d, uint64_t len, int32_t* __restrict__ out, int cap) {
+  int count = 0, bad = 0;
+  const bool vec = (((uintptr_t)out) & 15) == 0;
+  int32_t q4[4];
+  auto push = [&](int32_t v) {
+    if (vec) { q4[count & 3] = v; if ((count & 3) == 3) *(int4*)(out + count - 3) = make_int4(q4[0], q4[1], q4[2], q4[3]); }
+    else out[count] = v;
+    count++;
+  };
+  if (len > 1 && cap > 0) {
+    const int k = d[0];
+    if (k > 32) bad = 1;
+    else {
+      const uint8_t* p = d + 1;
+      uint64_t remaining = (len - 1) * 8;
+      const int skip = (int)((uintptr_t)p & 3) * 8;
+      bit_window bw;
+      bw.w = (const uint32_t*)((uintptr_t)p & ~(uintptr_t)3);
+      const uint64_t span = (uint64_t)skip + remaining;
+      bw.nwords = (uint32_t)((span + 31) >> 5);
+      const int lastbits = (int)(span - 32ull * (bw.nwords - 1));
+      bw.last_mask = (lastbits >= 32) ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> lastbits);
+      bw.wi = 0;
+      bw.win = ((uint64_t)(bw.word() << skip)) << 32;
+      bw.navail = 32 - skip;
+      const int64_t bias = (int64_t)1 << k;
+      while (count < cap) {
+        bw.refill();
+        if (bw.win == 0) {
+          if (remaining <= (uint64_t)bw.navail) break;          // only padding left
+          bad = 1; break;                                       // > 32 zero bits in front of a code
+        }
+        const int m = __clzll((long long)bw.win);
+        int nbv = m + k + 1;                                   // bits of the binary part
+        if (m > 32 || nbv > 62) { bad = 1; break; }
+        const bool trunc = (uint64_t)(m + nbv) > remaining;     // Python slicing: a short tail is still parsed
+        if (trunc) nbv = (int)remaining - m;
+        bw.drop(m); remaining -= m;
+        uint64_t x;
+        if (nbv <= 32) {
+          bw.refill();
+          x = bw.win >> (64 - nbv);
+          bw.drop(nbv);
+        } else {
+          bw.refill();
+          const uint64_t hi = bw.win >> 32;
+          bw.drop(32);
+          bw.refill();
+          x = (hi << (nbv - 32)) | (bw.win >> (64 - (nbv - 32)));
+          bw.drop(nbv - 32);
+        }
+        remaining -= nbv;
+        const int64_t nv = (int64_t)x - bias;
+        const int64_t val = (nv & 1) ? ((nv + 1) >> 1) : -(nv >> 1);
+        push((int32_t)max((int64_t)-2147483647 - 1, min((int64_t)2147483647, val)));
+        if (trunc || remaining == 0) break;
+      }
+    }
+  }
+  // tail of a partially filled vector, then zeros
+  if (vec) {
+    const int base = count & ~3;
+    for (int i = base; i < count; i++) out[i] = q4[i & 3];
+  }
+  int i = count;
+  for (; i < cap && (!vec || (i & 3)); i++) out[i] = 0;
+  if (vec) for (; i + 4 <= cap; i += 4) *(int4*)(out + i) = make_int4(0, 0, 0, 0);
+  for (; i < cap; i++) out[i] = 0;
+  return bad;
+}
+
+__device__ __forceinline__ uint64_t min64(uint64_t a, uint64_t b) { return a < b ? a : b; }
+
+// one thread per frame.  status[b]: bit 0 = payload too short for its prefixes (silent frame), bit 1 = malformed code
+__global__ void __launch_bounds__(32) p1_unpack_kernel(const uint8_t* __restrict__ raw, const uint64_t* __restrict__ off, int B, int nq,
+                                                       int ntq, int nlpc, int32_t* __restrict__ q, int32_t* __restrict__ tq,
+                                                       int32_t* __restrict__ lpc, int32_t* __restrict__ status) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const uint8_t* r = raw + off[b];
+  const uint64_t L = off[b + 1] - off[b];
+  int st = 0;
+  uint64_t pos = 0;
+  uint64_t l_at = 0, l_len = 0, t_at = 0, t_len = 0, q_at = 0, q_len = 0;
+  if (L < (lpc ? 6u : 4u)) st = 1;
+  else {
+    if (lpc) {                                                 // profile2.py:66-67
+      const uint64_t ll = ((uint64_t)r[0] << 8) | r[1];
+      l_at = 2; l_len = min64(ll, L - 2);
+      pos = 2 + l_len;
+    }
+    if (L - pos >= 4) {                                        // profile1.py:61-62
+      const uint64_t tl = ((uint64_t)r[pos] << 24) | ((uint64_t)r[pos + 1] << 16) | ((uint64_t)r[pos + 2] << 8) | r[pos + 3];
+      t_at = pos + 4; t_len = min64(tl, L - t_at);
+      q_at = t_at + t_len; q_len = L - q_at;
+    }
+  }
+  if (lpc) st |= decode_stream(r + l_at, l_len, lpc + (size_t)b * nlpc, nlpc) << 1;
+  st |= decode_stream(r + t_at, t_len, tq + (size_t)b * ntq, ntq) << 1;
+  st |= decode_stream(r + q_at, q_len, q + (size_t)b * nq, nq) << 1;
+  if (status) status[b] = st;
+}
+
+}  // namespace
+
+extern "C" size_t frad_p1_raw_bound(int N, int C, int with_lpc) {
+  auto gol = [](size_t n) { return 1 + (n * 35 + 7) / 8; };
+  size_t b = 4 + gol((size_t)FRAD_NBANDS * C) + gol((size_t)N * C);
+  if (with_lpc) b += 2 + gol((size_t)FRAD_LPC_LEN * C);
+  return (b + 15) & ~(size_t)15;
+}
+
+extern "C" int frad_p1_pack_dev(frad_ctx* ctx, const int32_t* q, const int32_t* tq, const int32_t* lpc, int B, int N, int C,
+                                uint8_t* raw, size_t raw_stride, uint32_t* raw_len) {
+  if (!ctx) return FRAD_E_ARG;
+  if (B < 0 || N < 1 || C < 1 || !q || !tq || !raw || !raw_len || raw_stride < frad_p1_raw_bound(N, C, lpc != nullptr))
+    return frad_fail(ctx, FRAD_E_ARG, "frad_p1_pack_dev: bad argument (raw_stride must be >= frad_p1_raw_bound)");
+  if (B == 0) return FRAD_OK;
+  FRAD_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int grid = B < ctx->sm_count * 8 ? B : ctx->sm_count * 8;
+  p1_pack_kernel<<<grid, GE_THREADS, 0, ctx->stream>>>(q, tq, lpc, B, N * C, FRAD_NBANDS * C, FRAD_LPC_LEN * C, raw, raw_stride, raw_len);
+  FRAD_LAUNCH_CHECK(ctx);
+  return FRAD_OK;
+}
+
+// internal form: appends at *running (device counter, may be NULL) and never writes beyond dst_cap
+int frad_compact_append(frad_ctx* ctx, const uint8_t* src, size_t stride, const uint32_t* len, int B, uint8_t* dst, uint64_t dst_cap,
+                        uint64_t* dst_off, uint64_t* running) {
+  FRAD_CUDA(ctx, cudaSetDevice(ctx->device));
+  scan_len_kernel<<<1, 1024, 0, ctx->stream>>>(len, B, dst_off, (unsigned long long*)running);
+  FRAD_LAUNCH_CHECK(ctx);
+  if (B == 0) return FRAD_OK;
+  const int grid = B < ctx->sm_count * 16 ? B : ctx->sm_count * 16;
+  compact_kernel<<<grid, 128, 0, ctx->stream>>>(src, stride, dst_off, B, dst, dst_cap);
+  FRAD_LAUNCH_CHECK(ctx);
+  return FRAD_OK;
+}
+
+extern "C" int frad_compact_dev(frad_ctx* ctx, const uint8_t* src, size_t stride, const uint32_t* len, int B, uint8_t* dst,
+                                size_t dst_cap, uint64_t* dst_off) {
+  if (!ctx) return FRAD_E_ARG;
+  if (B < 0 || !src || !len || !dst || !dst_off) return frad_fail(ctx, FRAD_E_ARG, "frad_compact_dev: bad argument");
+  return frad_compact_append(ctx, src, stride, len, B, dst, dst_cap, dst_off, nullptr);
+}
+
+extern "C" int frad_p1_unpack_dev(frad_ctx* ctx, const uint8_t* raw, const uint64_t* raw_off, int B, int N, int C, int with_lpc,
+                                  int32_t* q, int32_t* tq, int32_t* lpc, int32_t* status) {
+  if (!ctx) return FRAD_E_ARG;
+  if (B < 0 || N < 1 || C < 1 || !raw || !raw_off || !q || !tq || (with_lpc && !lpc))
+    return frad_fail(ctx, FRAD_E_ARG, "frad_p1_unpack_dev: bad argument");
+  if (B == 0) return FRAD_OK;
+  FRAD_CUDA(ctx, cudaSetDevice(ctx->device));
+  p1_unpack_kernel<<<(B + 31) / 32, 32, 0, ctx->stream>>>(raw, raw_off, B, N * C, FRAD_NBANDS * C, FRAD_LPC_LEN * C, q, tq,
+                                                        with_lpc ? lpc : nullptr, status);
+  FRAD_LAUNCH_CHECK(ctx);
+  return FRAD_OK;
+}

@@ -1,7 +1,7 @@
 """Profile 1 (lossy, psychoacoustic quantisation) seams -- mirror of libfrad/fourier/profile1.py.
 
-Device: DCT-II, masking thresholds, divisor ramps, power-law quantiser (and the inverse chain).
-Host: Exp-Golomb-Rice bit strings (native C++ in libfradb200) and raw deflate (zlib)."""
+Device: DCT-II, masking thresholds, divisor ramps, power-law quantiser, Exp-Golomb-Rice bit strings and the
+frame payload layout (and the inverse chain).  Host: raw deflate / inflate (zlib) only."""
 import struct
 import zlib
 from concurrent.futures import ThreadPoolExecutor
@@ -37,13 +37,23 @@ def _inflate(frad: bytes):
 
 
 def pack_streams(q: np.ndarray, tq: np.ndarray) -> list:
-    """[B, N*C] / [B, 27*C] ints -> B deflated payloads (profile1.py:43-50)."""
+    """[B, N*C] / [B, 27*C] ints -> B deflated payloads (profile1.py:43-50); host bit coder, used by tests."""
     tg = _abi.golomb_encode_rows(tq)
     qg = _abi.golomb_encode_rows(q)
     raws = [struct.pack(">I", len(t)) + t + g for t, g in zip(tg, qg)]
+    return deflate_all(raws)
+
+
+def deflate_all(raws) -> list:
     if len(raws) > 8:
         return list(_pool().map(_deflate, raws))
     return [_deflate(r) for r in raws]
+
+
+def split_raw(raw: np.ndarray, off: np.ndarray) -> list:
+    mv = memoryview(raw)
+    o = off.astype(np.int64).tolist()
+    return [mv[o[i]:o[i + 1]] for i in range(len(o) - 1)]
 
 
 def analogue_batch(pcm: np.ndarray, nframes: int, n: int, hop: int, bits: int, srate: int, loss_level: float,
@@ -53,8 +63,8 @@ def analogue_batch(pcm: np.ndarray, nframes: int, n: int, hop: int, bits: int, s
     if bits not in DEPTHS:
         bits = 16
     srate = compact.get_valid_srate(srate)
-    q, tq, _ = ctx.p1_encode(_device_pcm(pcm), nframes, n, hop, bits, srate, max(abs(loss_level), 0.125), prec, 1)
-    return pack_streams(q, tq), DEPTHS.index(bits), pcm.shape[1], srate
+    raw, off = ctx.p1_encode_raw(_device_pcm(pcm), nframes, n, hop, bits, srate, max(abs(loss_level), 0.125), prec, 1)
+    return deflate_all(split_raw(raw, off)), DEPTHS.index(bits), pcm.shape[1], srate
 
 
 def analogue(pcm: np.ndarray, bits: int, srate: int, loss_level: float, ctx=None):
@@ -87,13 +97,23 @@ def unpack_streams(payloads, fsize: int, channels: int):
     return q, tq, ok
 
 
+def inflate_all(payloads):
+    """Payloads -> (concatenated inflated bytes, offsets [B+1]); a failed inflate contributes zero bytes, which the
+    device parser turns into a silent frame (profile1.py:59-60)."""
+    nb = len(payloads)
+    raws = list(_pool().map(_inflate, payloads)) if nb > 8 else [_inflate(p) for p in payloads]
+    lens = np.fromiter((0 if r is None else len(r) for r in raws), dtype=np.uint64, count=nb)
+    off = np.zeros(nb + 1, np.uint64)
+    np.cumsum(lens, out=off[1:])
+    buf = np.frombuffer(b"".join(r for r in raws if r is not None) or b"\0", np.uint8)
+    return buf, off
+
+
 def digital_batch(payloads, fb: int, channels: int, srate: int, fsize: int, ctx=None, prec: int = PREC_REF,
                   out_dtype=np.float64) -> np.ndarray:
     ctx = ctx or default_context()
-    q, tq, ok = unpack_streams(payloads, fsize, channels)
-    out = ctx.p1_decode(q, tq, None, len(payloads), fsize, channels, DEPTHS[fb], srate, prec, out_dtype)
-    if not ok.all():
-        out[~ok] = 0.0                      # inflate failure -> silent frame (profile1.py:59-60)
+    buf, off = inflate_all(payloads)
+    out, _ = ctx.p1_decode_raw(buf, off, len(payloads), fsize, channels, DEPTHS[fb], srate, prec, 1, out_dtype)
     return out
 
 

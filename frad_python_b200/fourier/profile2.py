@@ -7,7 +7,7 @@ from .. import _abi
 from .._abi import PREC_REF, default_context
 from .profiles import compact
 from .profile0 import _device_pcm
-from .profile1 import _deflate, _inflate, _pool
+from .profile1 import _deflate, _inflate, _pool, deflate_all, inflate_all, split_raw
 
 DEPTHS = (8, 10, 12, 14, 16, 20, 24)
 
@@ -26,8 +26,8 @@ def analogue_batch(pcm, nframes, n, hop, bits, srate, loss_level, ctx=None, prec
     if bits not in DEPTHS:
         bits = 16
     srate = compact.get_valid_srate(srate)
-    q, tq, lpc = ctx.p1_encode(_device_pcm(pcm), nframes, n, hop, bits, srate, max(abs(loss_level), 0.125), prec, 2)
-    return pack_streams(q, tq, lpc), DEPTHS.index(bits), pcm.shape[1], srate
+    raw, off = ctx.p1_encode_raw(_device_pcm(pcm), nframes, n, hop, bits, srate, max(abs(loss_level), 0.125), prec, 2)
+    return deflate_all(split_raw(raw, off)), DEPTHS.index(bits), pcm.shape[1], srate
 
 
 def analogue(pcm, bits, srate, loss_level, ctx=None):
@@ -62,10 +62,8 @@ def unpack_streams(payloads, fsize, channels):
 
 def digital_batch(payloads, fb, channels, srate, fsize, ctx=None, prec: int = PREC_REF, out_dtype=np.float64):
     ctx = ctx or default_context()
-    q, tq, lpc, ok = unpack_streams(payloads, fsize, channels)
-    out = ctx.p1_decode(q, tq, lpc, len(payloads), fsize, channels, DEPTHS[fb], srate, prec, out_dtype)
-    if not ok.all():
-        out[~ok] = 0.0
+    buf, off = inflate_all(payloads)
+    out, _ = ctx.p1_decode_raw(buf, off, len(payloads), fsize, channels, DEPTHS[fb], srate, prec, 2, out_dtype)
     return out
 
 

@@ -116,6 +116,31 @@ int frad_p1_encode(frad_ctx* ctx, const void* pcm, int pcm_dtype, int64_t hop, i
 int frad_p1_decode(frad_ctx* ctx, const int32_t* q, const int32_t* tq, const int32_t* lpc,
                    int B, int N, int C, int bits, int srate, int prec, void* pcm, int pcm_dtype);
 
+/* ---- profile 1 / 2 frame payloads before deflate, packed on the device ---------------------------------- */
+/* The byte string the reference hands to zlib (profile1.py:43-46: >I len || gol(tq) || gol(q); profile2.py:48-51:
+ * >H len || gol(lpc) || >I len || gol(tq) || gol(q)) with gol() = Exp-Golomb-Rice (p1tools.py:46-60).
+ * frad_p1_raw_bound: worst-case bytes of one frame (a multiple of 16); raw_stride must be at least that.
+ * pack: q/tq[/lpc] -> raw[b*raw_stride ..], raw_len[b].  lpc == NULL selects the profile-1 layout.
+ * compact: B strided byte strings -> one contiguous buffer; dst_off[B+1] receives the offsets (dst_off[B] = total);
+ *          strings that would end beyond dst_cap are not written (check dst_off[B] <= dst_cap).
+ * unpack: raw_off[B+1] delimits the (inflated) payloads inside raw; missing values are zero (profile1.py:67-68),
+ *         status[b] (may be NULL): bit 0 = shorter than its length prefixes (decodes to silence),
+ *         bit 1 = a code no 32-bit value can produce (decoding of that stream stopped there). */
+size_t frad_p1_raw_bound(int N, int C, int with_lpc);
+int frad_p1_pack_dev(frad_ctx* ctx, const int32_t* q, const int32_t* tq, const int32_t* lpc, int B, int N, int C,
+                     uint8_t* raw, size_t raw_stride, uint32_t* raw_len);
+int frad_compact_dev(frad_ctx* ctx, const uint8_t* src, size_t stride, const uint32_t* len, int B,
+                     uint8_t* dst, size_t dst_cap, uint64_t* dst_off);
+int frad_p1_unpack_dev(frad_ctx* ctx, const uint8_t* raw, const uint64_t* raw_off, int B, int N, int C, int with_lpc,
+                       int32_t* q, int32_t* tq, int32_t* lpc, int32_t* status);
+/* Host pointers, pipelined: PCM -> payloads (raw_off[B+1]; FRAD_E_NOMEM with raw_off[B] = bytes needed when raw_cap is
+ * too small) and payloads -> PCM.  profile is 1 or 2. */
+int frad_p1_encode_raw(frad_ctx* ctx, const void* pcm, int pcm_dtype, int64_t hop, int B, int N, int C,
+                       int bits, int srate, double loss_level, int prec, int profile,
+                       uint8_t* raw, size_t raw_cap, uint64_t* raw_off);
+int frad_p1_decode_raw(frad_ctx* ctx, const uint8_t* raw, const uint64_t* raw_off, int B, int N, int C,
+                       int bits, int srate, int prec, int profile, void* pcm, int pcm_dtype, int32_t* status);
+
 /* ---- CRC (zlib.crc32 / crc16_ansi) ---------------------------------------------------------- */
 /* Message i is buf[off[i] .. off[i]+len[i]); off == NULL means i*stride, len == NULL means ulen. */
 int frad_crc32_dev(frad_ctx* ctx, const uint8_t* buf, const uint64_t* off, const uint32_t* len,

@@ -95,9 +95,32 @@ def crc_rs():
           "crc32 over RS-encoded payloads (20488 B)")
 
 
+def golomb():
+    """Device bit coder on the bench workload: 15000 frames of 48 kHz stereo profile-1 integers."""
+    n, hop, ch, frames = 2048, 1920, 2, 15000
+    d_pcm, _ = pcm_dev(frames, n, hop, ch)
+    ncoef = frames * n * ch
+    d_q = ctx.dev(ncoef * 4); d_tq = ctx.dev(frames * 27 * ch * 4)
+    ctx.check(L.frad_p1_encode_dev(ctx.handle, d_pcm.ptr, _abi.F32, hop, frames, n, ch, 16, 48000, 0.5526315789473684, 0, d_q.ptr, d_tq.ptr, None))
+    stride = L.frad_p1_raw_bound(n, ch, 0)
+    d_raw = ctx.dev(frames * stride); d_len = ctx.dev(frames * 4); d_cmp = ctx.dev(frames * stride); d_off = ctx.dev((frames + 1) * 8)
+    timed(lambda: ctx.check(L.frad_p1_pack_dev(ctx.handle, d_q.ptr, d_tq.ptr, None, frames, n, ch, d_raw.ptr, stride, d_len.ptr)),
+          ncoef * 4, "golomb pack int32 -> frame payloads (read side only counted)")
+    ctx.check(L.frad_compact_dev(ctx.handle, d_raw.ptr, stride, d_len.ptr, frames, d_cmp.ptr, frames * stride, d_off.ptr))
+    off = np.zeros(frames + 1, np.uint64); ctx.d2h(off, d_off.ptr); ctx.sync()
+    total = int(off[-1])
+    timed(lambda: ctx.check(L.frad_compact_dev(ctx.handle, d_raw.ptr, stride, d_len.ptr, frames, d_cmp.ptr, frames * stride, d_off.ptr)),
+          2 * total, "compact frame payloads (scan + copy)", payload_bytes=total, bits_per_value=round(8 * total / ncoef, 2))
+    d_q2 = ctx.dev(ncoef * 4); d_tq2 = ctx.dev(frames * 27 * ch * 4); d_st = ctx.dev(frames * 4)
+    timed(lambda: ctx.check(L.frad_p1_unpack_dev(ctx.handle, d_cmp.ptr, d_off.ptr, frames, n, ch, 0, d_q2.ptr, d_tq2.ptr, None, d_st.ptr)),
+          ncoef * 4 + total, "golomb unpack frame payloads -> int32 (one thread per frame)")
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     if which in ("all", "transforms"):
         transforms()
     if which in ("all", "bytes"):
         crc_rs()
+    if which in ("all", "golomb"):
+        golomb()
