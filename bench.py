@@ -3,11 +3,14 @@
 
 Workload (BASELINE.json configs[1]): profile-1 lossy encode+decode of 10 min of synthetic 48 kHz
 stereo f32 PCM, frame 2048, overlap 1/16 (hop 1920), 16-bit scale, loss level 0 -> 15 000 frames.
-One "step" = one encode pass (PCM -> quantised integers q/tq) + one decode pass (q/tq -> PCM) over
-the whole clip.  Metric: encode+decode MSamples/s (scalar PCM values = samples x channels).
+One "step" = one encode pass + one decode pass over the whole clip.  Metric: encode+decode MSamples/s (scalar
+PCM values = samples x channels consumed per pass).
 
-  value     device-resident (inputs already in HBM), CUDA events on the library's stream
-  e2e       same work through the host-pointer C ABI (pinned host buffers, H2D/D2H inside the region)
+  value     device-resident (inputs already in HBM), CUDA events on the library's stream: the transform +
+            quantiser kernels, PCM -> quantised integers q/tq -> PCM (north_star's hot path)
+  e2e       through the host-pointer C ABI with pinned host buffers, H2D/D2H inside the region: f32 PCM ->
+            frame payloads before deflate (profile1.py:43-46; the bit packing runs on the device too, so only
+            those bytes cross PCIe) -> f32 PCM.  The reference arm and cpu_baseline do exactly this work.
   roofline  dominant kernel: algorithmic bytes / event time vs MEASURED_PEAKS.json hbm_gbs
   cpu_baseline  the oracle port of the reference NumPy/SciPy path on a bounded sample, 1 core
 
@@ -97,13 +100,22 @@ class ClockSampler:
 
 
 def cpu_sample(frames_pcm):
-    """Oracle port of the reference path for a list of frames: ints out, PCM back.  Returns seconds."""
+    """Oracle port of the reference path for a list of frames, per frame like the reference: PCM -> integers ->
+    Exp-Golomb-Rice payload (profile1.py:21-46, without deflate) and back (profile1.py:61-77).  Returns seconds."""
+    import struct
     from oracle import frad_oracle as O
     t0 = time.perf_counter()
     for f in frames_pcm:
         q, tq, n, b, sr = O.p1_analogue_ints(f, BITS, SRATE, LOSS)
-        O.p1_digital_ints(q, tq, b, CH, sr, n)
+        tg = O.golomb_encode(tq)
+        raw = struct.pack(">I", len(tg)) + tg + O.golomb_encode(q)
+        tl = struct.unpack(">I", raw[:4])[0]
+        O.p1_digital_ints(O.golomb_decode(raw[4 + tl:]), O.golomb_decode(raw[4:4 + tl]), b, CH, sr, n)
     return time.perf_counter() - t0
+
+
+PORT_NOTE = ("oracle port of profile1 analogue/digital incl. the Exp-Golomb-Rice coder, without deflate; the port's bit "
+             "coder is vectorised / str.find based and about twice as fast as the reference's own string loop")
 
 
 def _cpu_worker(args):
@@ -132,7 +144,7 @@ def run_reference(args, rank, world):
             if step >= args.warmup:
                 times.append(dt)
     total = sum(times)
-    scal = sample_frames * N * CH * len(times)
+    scal = sample_frames * HOP * CH * len(times)
     val = scal / total / 1e6
     line = {
         "impl": "reference", "metric": "encode+decode MSamples/s (profile 1, 48 kHz stereo)", "value": val,
@@ -142,8 +154,7 @@ def run_reference(args, rank, world):
         "x_realtime": val * 1e6 / (SRATE * CH),
         "config": workload_config(sample_frames),
         "cpu_baseline": {"value": val, "unit": "MSamples/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample_frames} frames of the workload per step ({per_core} per core), "
-                                   "oracle port of profile1 analogue/digital without Golomb/deflate"},
+                         "sample": f"{sample_frames} frames of the workload per step ({per_core} per core), " + PORT_NOTE},
         "e2e": {"value": val, "unit": "MSamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -151,7 +162,9 @@ def run_reference(args, rank, world):
 
 def workload_config(frames):
     return {"workload": "configs[1]: profile 1 encode+decode, 10 min 48 kHz stereo f32, N=2048, hop=1920, 16-bit, "
-                        "loss level 0 (hot path: PCM <-> quantised ints; Golomb/deflate excluded)",
+                        "loss level 0.  value: PCM <-> quantised ints (transform + quantiser kernels, device-resident). "
+                        "e2e / reference arm / cpu_baseline: f32 PCM <-> frame payload before deflate (adds the "
+                        "Exp-Golomb-Rice bit coder; deflate stays on the host and is excluded), f32 PCM out",
             "frames": frames, "channels": CH, "frame_size": N, "hop": HOP, "srate": SRATE,
             "cache": "inputs (230 MB PCM / 246 MB ints) larger than the 126 MB L2"}
 
@@ -237,17 +250,46 @@ def main():
     ctx.sync()
     dec32_ms = ctx.elapsed_ms(7, 8) / args.steps
 
+    # ---- device-resident timing of the bit-coder kernels (not part of `value`; they are on the e2e path) -------
+    stride = L.frad_p1_raw_bound(N, CH, 0)
+    d_raw = ctx.dev(B * stride); d_len = ctx.dev(B * 4); d_cmp = ctx.dev(B * 6144); d_off = ctx.dev((B + 1) * 8)
+    d_st = ctx.dev(B * 4)
+
+    def pack():
+        ctx.check(L.frad_p1_pack_dev(ctx.handle, d_q.ptr, d_tq.ptr, None, B, N, CH, d_raw.ptr, stride, d_len.ptr))
+        ctx.check(L.frad_compact_dev(ctx.handle, d_raw.ptr, stride, d_len.ptr, B, d_cmp.ptr, B * 6144, d_off.ptr))
+
+    def unpack():
+        ctx.check(L.frad_p1_unpack_dev(ctx.handle, d_cmp.ptr, d_off.ptr, B, N, CH, 0, d_q.ptr, d_tq.ptr, None, d_st.ptr))
+
+    enc(); pack(); unpack(); ctx.sync()
+    ctx.event(9)
+    for _ in range(args.steps):
+        pack()
+    ctx.event(10)
+    for _ in range(args.steps):
+        unpack()
+    ctx.event(11)
+    ctx.sync()
+    pack_ms, unpack_ms = ctx.elapsed_ms(9, 10) / args.steps, ctx.elapsed_ms(10, 11) / args.steps
+    for d in (d_raw, d_len, d_cmp, d_off, d_st):
+        d.free()
+
     # ---- end-to-end leg: host buffers through the C ABI ------------------------------------------
+    # f32 PCM -> frame payloads (before deflate) -> f32 PCM; what crosses PCIe: PCM in, payload bytes out and back in,
+    # PCM out in the clip's own sample format (the fused output conversion of backend/pcmformat.py).
     h_pcm = ctx.pinned(pcm_host.shape, np.float32); h_pcm[...] = pcm_host
-    h_q = ctx.pinned((B, N * CH), np.int32)
-    h_tq = ctx.pinned((B, NBANDS * CH), np.int32)
-    h_out = ctx.pinned((B, N, CH), np.float64)
+    raw_cap = B * 6144
+    h_raw = ctx.pinned((raw_cap,), np.uint8)
+    h_off = ctx.pinned((B + 1,), np.uint64)
+    h_out = ctx.pinned((B, N, CH), np.float32)
+    h_st = ctx.pinned((B,), np.int32)
 
     def e2e_step():
-        ctx.check(L.frad_p1_encode(ctx.handle, h_pcm.ctypes.data, _abi.F32, HOP, B, N, CH, BITS, SRATE, LOSS,
-                                   _abi.PREC_REF, h_q.ctypes.data, h_tq.ctypes.data, None))
-        ctx.check(L.frad_p1_decode(ctx.handle, h_q.ctypes.data, h_tq.ctypes.data, None, B, N, CH, BITS, SRATE,
-                                   _abi.PREC_REF, h_out.ctypes.data, _abi.F64))
+        ctx.check(L.frad_p1_encode_raw(ctx.handle, h_pcm.ctypes.data, _abi.F32, HOP, B, N, CH, BITS, SRATE, LOSS,
+                                       _abi.PREC_REF, 1, h_raw.ctypes.data, raw_cap, h_off.ctypes.data))
+        ctx.check(L.frad_p1_decode_raw(ctx.handle, h_raw.ctypes.data, h_off.ctypes.data, B, N, CH, BITS, SRATE,
+                                       _abi.PREC_REF, 1, h_out.ctypes.data, _abi.F32, h_st.ctypes.data))
 
     e2e_step()
     barrier()
@@ -259,11 +301,31 @@ def main():
     ctx.event(6)
     barrier()
     e2e_ms = max(ctx.elapsed_ms(5, 6), 1e3 * (time.perf_counter() - t0))
-    launches += 0
+    raw_bytes = int(h_off[B])
+
+    # the same through the int32 entry points with float64 PCM out (the per-frame seam's types; PCIe carries 4x more)
+    h_q = ctx.pinned((B, N * CH), np.int32)
+    h_tq = ctx.pinned((B, NBANDS * CH), np.int32)
+    h_out64 = ctx.pinned((B, N, CH), np.float64)
+
+    def e2e_int_step():
+        ctx.check(L.frad_p1_encode(ctx.handle, h_pcm.ctypes.data, _abi.F32, HOP, B, N, CH, BITS, SRATE, LOSS,
+                                   _abi.PREC_REF, h_q.ctypes.data, h_tq.ctypes.data, None))
+        ctx.check(L.frad_p1_decode(ctx.handle, h_q.ctypes.data, h_tq.ctypes.data, None, B, N, CH, BITS, SRATE,
+                                   _abi.PREC_REF, h_out64.ctypes.data, _abi.F64))
+
+    e2e_int_step()
+    ctx.sync()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        e2e_int_step()
+    ctx.sync()
+    e2e_int_ms = 1e3 * (time.perf_counter() - t0) / 2
     clocks = sampler.stop()
 
     # sanity: the e2e result must be real data (decoded audio close to the input)
     err = float(np.max(np.abs(h_out[1, :HOP].astype(np.float64) - pcm_host[HOP:2 * HOP])))
+    same = bool(np.array_equal(h_out[B // 2], h_out64[B // 2].astype(np.float32))) and int(h_st.max()) == 0
 
     if dist is not None:
         import torch
@@ -298,27 +360,33 @@ def main():
         "x_realtime": value * 1e6 / (SRATE * CH),
         "config": workload_config(B),
         "e2e": {"value": e2e_val, "unit": "MSamples/s",
-                "h2d_bytes_per_step": int(h_pcm.nbytes + h_q.nbytes + h_tq.nbytes),
-                "d2h_bytes_per_step": int(h_q.nbytes + h_tq.nbytes + h_out.nbytes),
-                "x_realtime": e2e_val * 1e6 / (SRATE * CH), "roundtrip_max_abs_err": err},
+                "h2d_bytes_per_step": int(h_pcm.nbytes + raw_bytes + h_off.nbytes),
+                "d2h_bytes_per_step": int(raw_bytes + h_off.nbytes + h_out.nbytes + h_st.nbytes),
+                "x_realtime": e2e_val * 1e6 / (SRATE * CH), "roundtrip_max_abs_err": err,
+                "payload_bytes_per_step": raw_bytes, "matches_int_path": same,
+                "path": "frad_p1_encode_raw + frad_p1_decode_raw (pinned host buffers, 3-stream pipeline, f32 PCM out)",
+                "int32_f64_path": {"value": world * nscal / (e2e_int_ms * 1e-3) / 1e6, "unit": "MSamples/s",
+                                   "h2d_bytes_per_step": int(h_pcm.nbytes + h_q.nbytes + h_tq.nbytes),
+                                   "d2h_bytes_per_step": int(h_q.nbytes + h_tq.nbytes + h_out64.nbytes),
+                                   "path": "frad_p1_encode + frad_p1_decode (int32 streams and float64 PCM over PCIe)"}},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": dom["gbs"], "peak": hbm, "unit": "GB/s", "frac": dom["frac"],
                      "traffic": None, "kernel": dom["kernel"], "peak_source": how,
                      "algorithmic_bytes_per_launch": dom["bytes"], "launch_ms": dom["ms"]},
-        "kernels": [k_enc, k_dec, k_dec32],
+        "kernels": [k_enc, k_dec, k_dec32,
+                    {"kernel": "p1_pack_kernel + scan_len + compact (Exp-Golomb-Rice bit packing, e2e path only)", "ms": pack_ms},
+                    {"kernel": "p1_unpack_kernel (Exp-Golomb-Rice parsing, one thread per frame, e2e path only)", "ms": unpack_ms}],
         "f32_inverse_mode": {"value": world * nscal / ((enc_ms + dec32_ms) * 1e-3) / 1e6, "unit": "MSamples/s",
                              "tolerance": "decoded PCM within 1 LSB at 16 bit of the f64 reference (measured 1.2e-7)"},
     }
     if not args.no_cpu and world == 1:
         from oracle.frad_oracle import synth_pcm  # noqa: F401
-        nsample = 1500
+        nsample = 1000
         frames = [pcm_host[i * HOP:i * HOP + N] for i in range(nsample)]
         dt = cpu_sample(frames)
-        line["cpu_baseline"] = {"value": nsample * N * CH / dt / 1e6, "unit": "MSamples/s", "cores": 1, "kind": "port",
-                                "sample": f"first {nsample} frames of the workload, oracle port of profile1 "
-                                          "analogue/digital (NumPy/SciPy, per frame like the reference), "
-                                          "without Golomb/deflate"}
+        line["cpu_baseline"] = {"value": nsample * HOP * CH / dt / 1e6, "unit": "MSamples/s", "cores": 1, "kind": "port",
+                                "sample": f"first {nsample} frames of the workload, per frame like the reference: " + PORT_NOTE}
     else:
         line["cpu_baseline"] = None
     print(json.dumps(line))

@@ -633,11 +633,28 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
           double2* dst = (double2*)((double*)P.pcm + woff);
           dst[0] = make_double2(o4[0], o4[1]);
           dst[1] = make_double2(o4[2], o4[3]);
-        } else {
+        } else if (P.pcm_dtype == FRAD_F32) {
           float o4[4];
           gather4<CT, LY::WARP_BYTES / (int)sizeof(T)>((const T*)smem_raw, C, f, e4, [](int n) { return swz(n); },
                                                        [](T x) { return (float)x; }, o4);
           *(float4*)((float*)P.pcm + woff) = make_float4(o4[0], o4[1], o4[2], o4[3]);
+        } else {
+          // the other sample formats of pcmformat.py:49-62, converted in registers: 4 samples per thread and store
+          const int dt = P.pcm_dtype;
+          uint64_t o4[4];
+          gather4<CT, LY::WARP_BYTES / (int)sizeof(T)>((const T*)smem_raw, C, f, e4, [](int n) { return swz(n); },
+                                                       [dt](T x) { return pcm_image((double)x, dt); }, o4);
+          switch (pcm_size(dt)) {
+            case 8: {
+              uint4* dst = (uint4*)((uint64_t*)P.pcm + woff);
+              dst[0] = make_uint4((uint32_t)o4[0], (uint32_t)(o4[0] >> 32), (uint32_t)o4[1], (uint32_t)(o4[1] >> 32));
+              dst[1] = make_uint4((uint32_t)o4[2], (uint32_t)(o4[2] >> 32), (uint32_t)o4[3], (uint32_t)(o4[3] >> 32));
+              break;
+            }
+            case 4: *(uint4*)((uint32_t*)P.pcm + woff) = make_uint4((uint32_t)o4[0], (uint32_t)o4[1], (uint32_t)o4[2], (uint32_t)o4[3]); break;
+            case 2: *(uint2*)((uint16_t*)P.pcm + woff) = make_uint2((uint32_t)o4[0] | ((uint32_t)o4[1] << 16), (uint32_t)o4[2] | ((uint32_t)o4[3] << 16)); break;
+            default: *(uint32_t*)((uint8_t*)P.pcm + woff) = (uint32_t)o4[0] | ((uint32_t)o4[1] << 8) | ((uint32_t)o4[2] << 16) | ((uint32_t)o4[3] << 24); break;
+          }
         }
       }
     }

@@ -128,9 +128,55 @@ template <typename T> __device__ __forceinline__ T load_pcm(const void* p, int d
   }
 }
 
+// f64 -> sample format, what `from_f64(pcm, fmt).astype(fmt)` yields (pcmformat.py:49-62, src/decoder.py:23): floats
+// round to nearest even; integers scale by 2^(bits-1) (unsigned: after + 1) and TRUNCATE towards zero.  Out-of-range
+// values follow NumPy on x86-64 (a C cast: cvttsd2si gives the "integer indefinite" 0x80..0, then the low bytes are
+// kept), so e.g. +1.0 wraps to the most negative 16-bit sample exactly like the reference.
+__device__ __forceinline__ int32_t cvtt32_x86(double v) {
+  return (v > -2147483649.0 && v < 2147483648.0) ? __double2int_rz(v) : (int32_t)0x80000000;
+}
+__device__ __forceinline__ long long cvtt64_x86(double v) {
+  return (v >= -9223372036854775808.0 && v < 9223372036854775808.0) ? __double2ll_rz(v) : (long long)0x8000000000000000ull;
+}
+// little-endian image of one sample in the low frad_dtype_size(dt) bytes
+__device__ __forceinline__ uint64_t pcm_image(double v, int dt) {
+  switch (dt) {
+    case FRAD_F64: return (uint64_t)__double_as_longlong(v);
+    case FRAD_F32: return (uint64_t)__float_as_uint(__double2float_rn(v));
+    case FRAD_F16: return (uint64_t)__half_as_ushort(__double2half(v));
+    case FRAD_S8:  return (uint64_t)(uint8_t)cvtt32_x86(v * 128.0);
+    case FRAD_S16: return (uint64_t)(uint16_t)cvtt32_x86(v * 32768.0);
+    case FRAD_S32: return (uint64_t)(uint32_t)cvtt32_x86(v * 2147483648.0);
+    case FRAD_S64: return (uint64_t)cvtt64_x86(v * 9223372036854775808.0);
+    case FRAD_U8:  return (uint64_t)(uint8_t)cvtt32_x86((v + 1.0) * 128.0);
+    case FRAD_U16: return (uint64_t)(uint16_t)cvtt32_x86((v + 1.0) * 32768.0);
+    case FRAD_U32: return (uint64_t)(uint32_t)cvtt64_x86((v + 1.0) * 2147483648.0);
+    case FRAD_U64: {
+      const double x = (v + 1.0) * 9223372036854775808.0;
+      // C cast double -> uint64 as gcc emits it: values >= 2^63 go through (x - 2^63) with the top bit set afterwards
+      return (x >= 9223372036854775808.0) ? ((uint64_t)cvtt64_x86(x - 9223372036854775808.0) ^ 0x8000000000000000ull)
+                                          : (uint64_t)cvtt64_x86(x);
+    }
+    default: return 0;
+  }
+}
+__device__ __forceinline__ int pcm_size(int dt) {
+  switch (dt) {
+    case FRAD_F64: case FRAD_S64: case FRAD_U64: return 8;
+    case FRAD_F32: case FRAD_S32: case FRAD_U32: return 4;
+    case FRAD_F16: case FRAD_S16: case FRAD_U16: return 2;
+    default: return 1;
+  }
+}
+
 template <typename T> __device__ __forceinline__ void store_pcm(void* p, int dt, int64_t i, T v) {
-  if (dt == FRAD_F64) ((double*)p)[i] = (double)v;
-  else ((float*)p)[i] = (float)v;
+  const uint64_t u = pcm_image((double)v, dt);
+  switch (pcm_size(dt)) {
+    case 8: ((uint64_t*)p)[i] = u; break;
+    case 4: ((uint32_t*)p)[i] = (uint32_t)u; break;
+    case 2: ((uint16_t*)p)[i] = (uint16_t)u; break;
+    default: ((uint8_t*)p)[i] = (uint8_t)u; break;
+  }
 }
 
 // ---- profile-0 value <-> bytes (profile0.py:28-42, 51-66) -------------------------------------

@@ -13,9 +13,10 @@
 //         neighbours); the buffer is written out as bytes, stream after stream, with the length prefixes.
 // compact exclusive scan of the per-frame lengths + byte copy into one contiguous buffer (what goes over
 //         PCIe: about 5 times fewer bytes than the int32 streams).
-// unpack  one thread per frame (the code boundaries form a serial chain): a 64-bit register window over
-//         big-endian words, count-leading-zeros for the unary part, one variable shift per value; four
-//         values per 16-byte store.  Thousands of frames decode in parallel.
+// unpack  one warp per frame.  The code boundaries form a serial chain, but the code is self-synchronising, so the
+//         32 lanes decode 32 segments of the bit string speculatively and fix their entry points up afterwards
+//         (see decode_stream_warp).  Per lane: a 64-bit register window over big-endian words, count-leading-
+//         zeros for the unary part, one variable shift per value; four values per 16-byte store.
 #include "common.cuh"
 
 namespace {
@@ -234,86 +235,154 @@ struct bit_window {
   __device__ __forceinline__ void drop(int n) { win = (n >= 64) ? 0 : (win << n); navail -= n; }
 };
 
-// p1tools.py:62-74.  d[0..len): k byte + bits.  Writes min(count, cap) values, zero-fills up to cap; returns 0, or 1 when
-// the stream holds a code no 32-bit value can produce (k > 32 or a unary run > 32) -- decoding stops there.
-__device__ int decode_stream(const uint8_t* __restrict__ d, uint64_t len, int32_t* __restrict__ out, int cap) {
-  int count = 0, bad = 0;
+__device__ __forceinline__ uint64_t min64(uint64_t a, uint64_t b) { return a < b ? a : b; }
+
+// ---- warp-parallel decode of one stream ---------------------------------------------------------------------
+// The code boundaries form a serial chain, but the code is self-synchronising: a decoder started at a wrong bit
+// almost always falls into step with the true chain within a few codes.  The bit string is cut into 32 segments, one
+// per lane.  Pass 1: every lane decodes from the first bit of its segment (a guess) and reports where its chain leaves
+// the segment.  Pass 2: every lane restarts where its left neighbour's chain ended; this repeats until no entry point
+// changes any more (lane 0 starts at the true bit 0, so after round r lanes 0..r are final; in practice one round).
+// A prefix sum of the per-lane counts gives the output positions and a last pass writes the values.
+struct stream_view {
+  const uint32_t* w; uint32_t nwords, last_mask, nbits; int skip, k;
+};
+
+struct lane_chain {
+  uint32_t end;      // bit position where the chain leaves the segment (nbits when the stream ends inside it)
+  int count;         // codes decoded
+  int bad;           // stopped at a code no 32-bit value can produce
+};
+
+// Decodes codes from bit `pos` while pos < seg_hi.  WRITE: stores value i at out[obase + i] when obase + i < cap
+// (four values per 16-byte store once the position is aligned).
+template <bool WRITE>
+__device__ __forceinline__ lane_chain run_chain(const stream_view& sv, uint32_t pos, uint32_t seg_hi, int32_t* __restrict__ out,
+                                                int obase, int cap) {
+  lane_chain r; r.count = 0; r.bad = 0;
+  int32_t v0 = 0, v1 = 0, v2 = 0;
+  int filled = 0;                                              // values held for the current aligned group of four
   const bool vec = (((uintptr_t)out) & 15) == 0;
-  int32_t q4[4];
-  auto push = [&](int32_t v) {
-    if (vec) { q4[count & 3] = v; if ((count & 3) == 3) *(int4*)(out + count - 3) = make_int4(q4[0], q4[1], q4[2], q4[3]); }
-    else out[count] = v;
-    count++;
-  };
-  if (len > 1 && cap > 0) {
-    const int k = d[0];
-    if (k > 32) bad = 1;
-    else {
-      const uint8_t* p = d + 1;
-      uint64_t remaining = (len - 1) * 8;
-      const int skip = (int)((uintptr_t)p & 3) * 8;
-      bit_window bw;
-      bw.w = (const uint32_t*)((uintptr_t)p & ~(uintptr_t)3);
-      const uint64_t span = (uint64_t)skip + remaining;
-      bw.nwords = (uint32_t)((span + 31) >> 5);
-      const int lastbits = (int)(span - 32ull * (bw.nwords - 1));
-      bw.last_mask = (lastbits >= 32) ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> lastbits);
-      bw.wi = 0;
-      bw.win = ((uint64_t)(bw.word() << skip)) << 32;
-      bw.navail = 32 - skip;
-      const int64_t bias = (int64_t)1 << k;
-      while (count < cap) {
+  if (pos < seg_hi) {
+    bit_window bw;
+    bw.w = sv.w; bw.nwords = sv.nwords; bw.last_mask = sv.last_mask;
+    const uint32_t abs0 = (uint32_t)sv.skip + pos;
+    bw.wi = abs0 >> 5;
+    const int off = (int)(abs0 & 31);
+    bw.win = ((uint64_t)(bw.word() << off)) << 32;
+    bw.navail = 32 - off;
+    const int64_t bias = (int64_t)1 << sv.k;
+    while (pos < seg_hi) {
+      bw.refill();
+      const uint32_t remaining = sv.nbits - pos;
+      if (bw.win == 0) {                                       // only padding left, or > 32 zeros in front of a code
+        if (remaining > (uint32_t)bw.navail) r.bad = 1;
+        pos = sv.nbits;
+        break;
+      }
+      const int m = __clzll((long long)bw.win);
+      int nbv = m + sv.k + 1;
+      if (m > 32 || nbv > 62) { r.bad = 1; pos = sv.nbits; break; }
+      const bool trunc = (uint32_t)(m + nbv) > remaining;      // Python slicing: a cut last code is still parsed
+      if (trunc) nbv = (int)remaining - m;
+      bw.drop(m);
+      uint64_t x;
+      if (nbv <= 32) {
         bw.refill();
-        if (bw.win == 0) {
-          if (remaining <= (uint64_t)bw.navail) break;          // only padding left
-          bad = 1; break;                                       // > 32 zero bits in front of a code
-        }
-        const int m = __clzll((long long)bw.win);
-        int nbv = m + k + 1;                                   // bits of the binary part
-        if (m > 32 || nbv > 62) { bad = 1; break; }
-        const bool trunc = (uint64_t)(m + nbv) > remaining;     // Python slicing: a short tail is still parsed
-        if (trunc) nbv = (int)remaining - m;
-        bw.drop(m); remaining -= m;
-        uint64_t x;
-        if (nbv <= 32) {
-          bw.refill();
-          x = bw.win >> (64 - nbv);
-          bw.drop(nbv);
-        } else {
-          bw.refill();
-          const uint64_t hi = bw.win >> 32;
-          bw.drop(32);
-          bw.refill();
-          x = (hi << (nbv - 32)) | (bw.win >> (64 - (nbv - 32)));
-          bw.drop(nbv - 32);
-        }
-        remaining -= nbv;
+        x = bw.win >> (64 - nbv);
+        bw.drop(nbv);
+      } else {
+        bw.refill();
+        const uint64_t hi = bw.win >> 32;
+        bw.drop(32);
+        bw.refill();
+        x = (hi << (nbv - 32)) | (bw.win >> (64 - (nbv - 32)));
+        bw.drop(nbv - 32);
+      }
+      pos = trunc ? sv.nbits : pos + (uint32_t)(m + nbv);
+      if (WRITE) {
         const int64_t nv = (int64_t)x - bias;
         const int64_t val = (nv & 1) ? ((nv + 1) >> 1) : -(nv >> 1);
-        push((int32_t)max((int64_t)-2147483647 - 1, min((int64_t)2147483647, val)));
-        if (trunc || remaining == 0) break;
+        const int32_t v = (int32_t)max((int64_t)-2147483647 - 1, min((int64_t)2147483647, val));
+        const int at = obase + r.count;
+        if (at < cap) {
+          const int slot = at & 3;
+          if (slot == 3 && filled == 3 && vec) { *(int4*)(out + at - 3) = make_int4(v0, v1, v2, v); filled = 0; }
+          else if (slot == 3) {                                // group started in the middle (or unaligned row): scalar stores
+            if (filled >= 3) out[at - 3] = v0;
+            if (filled >= 2) out[at - 2] = v1;
+            if (filled >= 1) out[at - 1] = v2;
+            out[at] = v; filled = 0;
+          } else { v0 = v1; v1 = v2; v2 = v; filled++; }       // v2 is the most recent value
+        }
       }
+      r.count++;
     }
   }
-  // tail of a partially filled vector, then zeros
-  if (vec) {
-    const int base = count & ~3;
-    for (int i = base; i < count; i++) out[i] = q4[i & 3];
+  if (WRITE && filled) {                                       // flush an incomplete last group
+    const int at = obase + r.count;                            // first index not written
+    const int hi = min(at, cap);
+    if (filled >= 3 && hi - 3 >= 0) out[hi - 3] = v0;
+    if (filled >= 2) out[hi - 2] = v1;
+    out[hi - 1] = v2;
   }
-  int i = count;
-  for (; i < cap && (!vec || (i & 3)); i++) out[i] = 0;
-  if (vec) for (; i + 4 <= cap; i += 4) *(int4*)(out + i) = make_int4(0, 0, 0, 0);
-  for (; i < cap; i++) out[i] = 0;
+  r.end = pos;
+  return r;
+}
+
+// all 32 lanes of a warp; returns the (warp-uniform) malformed flag
+__device__ int decode_stream_warp(const uint8_t* __restrict__ d, uint64_t len, int32_t* __restrict__ out, int cap, int lane) {
+  int total = 0, bad = 0;
+  if (len > 1 && cap > 0) {
+    stream_view sv;
+    sv.k = d[0];
+    if (sv.k > 32 || len > (1ull << 28)) bad = 1;
+    else {
+      const uint8_t* p = d + 1;
+      sv.nbits = (uint32_t)((len - 1) * 8);
+      sv.skip = (int)((uintptr_t)p & 3) * 8;
+      sv.w = (const uint32_t*)((uintptr_t)p & ~(uintptr_t)3);
+      const uint32_t span = (uint32_t)sv.skip + sv.nbits;
+      sv.nwords = (span + 31) >> 5;
+      const int lastbits = (int)(span - 32u * (sv.nwords - 1));
+      sv.last_mask = (lastbits >= 32) ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> lastbits);
+      uint32_t S = (sv.nbits + 31) / 32;
+      S = (S + 31) & ~31u;
+      if (S < 64) S = 64;
+      const uint32_t seg_lo = min((uint32_t)lane * S, sv.nbits), seg_hi = min(seg_lo + S, sv.nbits);
+      uint32_t entry = seg_lo;
+      lane_chain ch = run_chain<false>(sv, entry, seg_hi, out, 0, 0);
+      for (int round = 0; round < 32; round++) {
+        uint32_t e = __shfl_up_sync(0xffffffffu, ch.end, 1);
+        if (lane == 0) e = 0;
+        e = max(e, seg_lo);                                    // a chain never ends before the next segment starts
+        const bool redo = (e != entry);
+        if (!__any_sync(0xffffffffu, redo)) break;
+        if (redo) { entry = e; ch = run_chain<false>(sv, entry, seg_hi, out, 0, 0); }
+      }
+      // exclusive prefix of the counts
+      int inc = ch.count;
+#pragma unroll
+      for (int s2 = 1; s2 < 32; s2 <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, s2); if (lane >= s2) inc += t; }
+      total = __shfl_sync(0xffffffffu, inc, 31);
+      const int obase = inc - ch.count;
+      const lane_chain fin = run_chain<true>(sv, entry, seg_hi, out, obase, cap);
+      bad = __any_sync(0xffffffffu, fin.bad && obase + fin.count < cap) ? 1 : 0;
+    }
+  }
+  __syncwarp();
+  for (int i = min(total, cap) + lane; i < cap; i += 32) out[i] = 0;
   return bad;
 }
 
-__device__ __forceinline__ uint64_t min64(uint64_t a, uint64_t b) { return a < b ? a : b; }
-
-// one thread per frame.  status[b]: bit 0 = payload too short for its prefixes (silent frame), bit 1 = malformed code
-__global__ void __launch_bounds__(32) p1_unpack_kernel(const uint8_t* __restrict__ raw, const uint64_t* __restrict__ off, int B, int nq,
-                                                       int ntq, int nlpc, int32_t* __restrict__ q, int32_t* __restrict__ tq,
-                                                       int32_t* __restrict__ lpc, int32_t* __restrict__ status) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per frame.  status[b]: bit 0 = payload too short for its prefixes (silent frame), bit 1 = malformed code
+constexpr int GD_WARPS = 4;
+__global__ void __launch_bounds__(GD_WARPS * 32) p1_unpack_kernel(const uint8_t* __restrict__ raw, const uint64_t* __restrict__ off,
+                                                                  int B, int nq, int ntq, int nlpc, int32_t* __restrict__ q,
+                                                                  int32_t* __restrict__ tq, int32_t* __restrict__ lpc,
+                                                                  int32_t* __restrict__ status) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * GD_WARPS + (threadIdx.x >> 5);
   if (b >= B) return;
   const uint8_t* r = raw + off[b];
   const uint64_t L = off[b + 1] - off[b];
@@ -333,10 +402,10 @@ __global__ void __launch_bounds__(32) p1_unpack_kernel(const uint8_t* __restrict
       q_at = t_at + t_len; q_len = L - q_at;
     }
   }
-  if (lpc) st |= decode_stream(r + l_at, l_len, lpc + (size_t)b * nlpc, nlpc) << 1;
-  st |= decode_stream(r + t_at, t_len, tq + (size_t)b * ntq, ntq) << 1;
-  st |= decode_stream(r + q_at, q_len, q + (size_t)b * nq, nq) << 1;
-  if (status) status[b] = st;
+  if (lpc) st |= decode_stream_warp(r + l_at, l_len, lpc + (size_t)b * nlpc, nlpc, lane) << 1;
+  st |= decode_stream_warp(r + t_at, t_len, tq + (size_t)b * ntq, ntq, lane) << 1;
+  st |= decode_stream_warp(r + q_at, q_len, q + (size_t)b * nq, nq, lane) << 1;
+  if (status && lane == 0) status[b] = st;
 }
 
 }  // namespace
@@ -388,8 +457,8 @@ extern "C" int frad_p1_unpack_dev(frad_ctx* ctx, const uint8_t* raw, const uint6
     return frad_fail(ctx, FRAD_E_ARG, "frad_p1_unpack_dev: bad argument");
   if (B == 0) return FRAD_OK;
   FRAD_CUDA(ctx, cudaSetDevice(ctx->device));
-  p1_unpack_kernel<<<(B + 31) / 32, 32, 0, ctx->stream>>>(raw, raw_off, B, N * C, FRAD_NBANDS * C, FRAD_LPC_LEN * C, q, tq,
-                                                        with_lpc ? lpc : nullptr, status);
+  p1_unpack_kernel<<<(B + GD_WARPS - 1) / GD_WARPS, GD_WARPS * 32, 0, ctx->stream>>>(raw, raw_off, B, N * C, FRAD_NBANDS * C,
+                                                                                   FRAD_LPC_LEN * C, q, tq, with_lpc ? lpc : nullptr, status);
   FRAD_LAUNCH_CHECK(ctx);
   return FRAD_OK;
 }

@@ -551,7 +551,7 @@ extern "C" int frad_p0_encode_dev(frad_ctx* ctx, const void* pcm, int pcm_dtype,
 extern "C" int frad_p0_decode_dev(frad_ctx* ctx, const uint8_t* payload, size_t payload_stride, int B, int N, int C,
                                   int bits, int little_endian, int prec, void* pcm, int pcm_dtype) {
   if (!ctx) return FRAD_E_ARG;
-  if (B < 0 || N < 1 || C < 1 || !p0_bits_ok(bits) || !pcm || !payload || (pcm_dtype != FRAD_F64 && pcm_dtype != FRAD_F32))
+  if (B < 0 || N < 1 || C < 1 || !p0_bits_ok(bits) || !pcm || !payload || !frad_dtype_size(pcm_dtype))
     return frad_fail(ctx, FRAD_E_ARG, "frad_p0_decode_dev: bad argument");
   if (payload_stride < frad_p0_payload_bytes(N, C, bits)) return frad_fail(ctx, FRAD_E_ARG, "payload_stride too small");
   FRAD_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -646,7 +646,7 @@ extern "C" int frad_p1_decode_dev(frad_ctx* ctx, const int32_t* q, const int32_t
                                   int B, int N, int C, int bits, int srate, int prec, void* pcm, int pcm_dtype) {
   if (!ctx) return FRAD_E_ARG;
   if (B < 0 || C < 1 || !pcm || !q || !tq || !compact_size_ok(N) || !compact_srate_ok(srate) ||
-      !p12_bits_ok(bits, lpc != nullptr) || (pcm_dtype != FRAD_F64 && pcm_dtype != FRAD_F32))
+      !p12_bits_ok(bits, lpc != nullptr) || !frad_dtype_size(pcm_dtype))
     return frad_fail(ctx, FRAD_E_ARG, "frad_p1_decode_dev: bad argument");
   FRAD_CUDA(ctx, cudaSetDevice(ctx->device));
   dec_params P = {};

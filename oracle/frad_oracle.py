@@ -231,32 +231,26 @@ def golomb_encode(vals: np.ndarray) -> bytes:
 
 
 def golomb_decode(data: bytes) -> np.ndarray:
-    """p1tools.py:62-74 (same stopping rule: ends when no set bit remains)."""
+    """p1tools.py:62-74 (same stopping rule: ends when no set bit remains; a cut last code is parsed as far as it goes,
+    like the reference's string slicing).  Works on one bit string with str.find instead of re-slicing it per value."""
     if len(data) == 0:
         return np.array([], dtype=np.int64)
     k = data[0]
-    bits = np.unpackbits(np.frombuffer(data[1:], np.uint8))
-    ones = np.flatnonzero(bits)
+    bits = bin(int.from_bytes(b"\x01" + bytes(data[1:]), "big"))[3:]      # leading zeros kept by the sentinel byte
     out = []
-    pos, total = 0, len(bits)
-    oi = 0
-    bl = bits.tolist()
-    while True:
-        oi = int(np.searchsorted(ones, pos))
-        if oi >= len(ones):
+    pos, total, bias = 0, len(bits), 1 << k
+    while pos < total:
+        one = bits.find("1", pos)
+        if one < 0:
             break
-        m = int(ones[oi]) - pos
-        width = 2 * m + k + 1
-        word = bl[pos:pos + width]
-        v = 0
-        for bit in word:
-            v = (v << 1) | bit
-        v -= 1 << k
+        width = 2 * (one - pos) + k + 1
+        v = int(bits[one:pos + width], 2) - bias
         out.append((v + 1) >> 1 if v & 1 else -(v >> 1))
         pos += width
-        if pos >= total:
-            break
-    return np.array(out, dtype=np.int64)
+    try:
+        return np.array(out, dtype=np.int64)
+    except OverflowError:                      # absurd k in a corrupt stream: Python integers, like the reference
+        return np.array(out, dtype=object)
 
 
 # ----------------------------------------------------------------------------------------
@@ -613,6 +607,18 @@ def force_flush_header(profile: int, ecc: bool, little_endian: bool, depth_index
 def hann_fade_in(length: int) -> np.ndarray:
     """backend/__init__.py:3"""
     return 0.5 * (1 - np.cos(np.pi * np.arange(1, length + 1) / (length + 1)))
+
+
+def pcm_from_f64(pcm: np.ndarray, dtype) -> np.ndarray:
+    """Decoded float64 PCM -> sample format, as the reference application writes it: from_f64(pcm, fmt).astype(fmt)
+    (backend/pcmformat.py:49-62, src/decoder.py:23).  Integers are scaled by 2^(bits-1) (unsigned after adding 1) and
+    truncated by NumPy's cast -- values outside [-1, 1) wrap, they are not clipped; floats are rounded."""
+    dt = np.dtype(dtype)
+    with np.errstate(all="ignore"):
+        if dt.kind == "f":
+            return pcm.astype(dt)
+        scale = float(2 ** (8 * dt.itemsize - 1))
+        return ((pcm + 1) * scale if dt.kind == "u" else pcm * scale).astype(dt)
 
 
 # ----------------------------------------------------------------------------------------

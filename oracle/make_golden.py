@@ -288,7 +288,25 @@ def gen_crc_ecc():
     np.savez_compressed(os.path.join(OUT, "crc_ecc.npz"), **d)
 
 
+def gen_pcmfmt():
+    """Output sample formats: what the reference application writes, from_f64(pcm, fmt).astype(fmt)
+    (backend/pcmformat.py:49-62, src/decoder.py:23), including values outside [-1, 1) -- they wrap, they are not clipped."""
+    from libfrad.backend.pcmformat import from_f64, ff_format_to_numpy_type
+    rng = np.random.default_rng(600)
+    x = np.concatenate([rng.uniform(-1, 1, 4000), rng.uniform(-2.5, 2.5, 96),
+                        [0.0, -0.0, 1.0, -1.0, 0.999999, -0.999999, 0.5 / 32768, -0.5 / 32768, 1.5 / 32768, 32767.9 / 32768]])
+    d = {"x": x}
+    with np.errstate(all="ignore"):
+        for fmt in ("u8", "s8", "u16le", "s16le", "u32le", "s32le", "u64le", "s64le", "f16le", "f32le", "f64le"):
+            dt = ff_format_to_numpy_type(fmt)
+            d[fmt] = from_f64(x.copy(), dt).astype(dt)
+    np.savez_compressed(os.path.join(OUT, "pcmfmt.npz"), **d)
+
+
 if __name__ == "__main__":
-    gen_p0(); gen_p1(); gen_p2(); gen_crc_ecc(); gen_streams()
+    if len(sys.argv) > 1 and sys.argv[1] == "pcmfmt":
+        gen_pcmfmt()
+    else:
+        gen_p0(); gen_p1(); gen_p2(); gen_crc_ecc(); gen_streams(); gen_pcmfmt()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -290,3 +290,34 @@ def test_fast2048_matches_generic_path(ctx):
         assert np.max(np.abs(a[5] - ref1)) <= 1e-13
         # f32 inverse (fast mode): stated tolerance 1 LSB at 16 bit = 3.05e-5; measured ~1e-6
         assert np.max(np.abs(a[6] - ref1)) <= 3e-6
+
+
+@pytest.mark.parametrize("fast", [True, False])
+def test_decode_output_sample_formats(ctx, fast):
+    """Fused output conversion (pcmformat.py:49-62): every sample format the reference application can write, produced
+    by the decode kernels' stores, equals the oracle conversion of the same kernels' float64 output -- bit for bit,
+    including PCM outside [-1, 1) (wraps like NumPy's cast, no clipping).  Fast N = 2048 kernels and the generic path."""
+    from frad_python_b200 import _abi
+    n, c, nb = (2048, 2, 5) if fast else (1280, 3, 3)
+    rng = np.random.default_rng(12)
+    coef = (rng.standard_normal((nb, n * c)) * 0.02).astype(np.float32)
+    coef[:, : 2 * c] += np.float32(0.6)                               # pushes part of the PCM beyond +-1
+    payload = coef.astype(">f4").view(np.uint8).reshape(nb, -1)
+    ref = ctx.p0_decode(payload, nb, n, c, 32, False)
+    assert np.abs(ref).max() > 1.2
+    inr = (ref >= -1.0) & (ref < 1.0)
+    for dt in ("u1", "i1", "<u2", "<i2", "<u4", "<i4", "<u8", "<i8", "<f2", "<f4"):
+        got = ctx.p0_decode(payload, nb, n, c, 32, False, out_dtype=np.dtype(dt))
+        want = O.pcm_from_f64(ref, dt)
+        # out of range the reference's cast is a C cast with undefined behaviour: signed formats behave the same on every
+        # x86-64 NumPy (cvttsd2si + truncation, which the kernels reproduce); unsigned ones do not, so only in-range there
+        sel = inr if np.dtype(dt).kind == "u" else np.ones_like(inr)
+        assert np.array_equal(got[sel], want[sel]), dt
+    # profile 1 goes through the same store
+    q = np.rint(rng.laplace(0, 6, (nb, n * c))).astype(np.int32)
+    tq = rng.integers(0, 30, (nb, 27 * c)).astype(np.int32)
+    ref1 = ctx.p1_decode(q, tq, None, nb, n, c, 16, 48000)
+    for dt in ("<i2", "<i4", "<f4", "u1"):
+        got = ctx.p1_decode(q, tq, None, nb, n, c, 16, 48000, out_dtype=np.dtype(dt))
+        sel = ((ref1 >= -1.0) & (ref1 < 1.0)) if np.dtype(dt).kind == "u" else np.ones(ref1.shape, bool)
+        assert np.array_equal(got[sel], O.pcm_from_f64(ref1, dt)[sel]), dt

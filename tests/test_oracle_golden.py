@@ -158,3 +158,15 @@ def test_p2_tools_golden(g_p2):
     res, aq = O.tns_analysis(g_p2["tool_x"])
     assert np.array_equal(aq, g_p2["tool_aq"]) and np.array_equal(res, g_p2["tool_res"])
     assert np.array_equal(O.tns_synthesis(res, aq), g_p2["tool_syn"])
+
+
+def test_pcm_output_formats_match_the_reference():
+    """pcm_from_f64 == the reference's from_f64(...).astype(fmt) on in-range and out-of-range values (they wrap)."""
+    from conftest import load_golden
+    g = load_golden("pcmfmt")
+    for fmt, dt in (("u8", "u1"), ("s8", "i1"), ("u16le", "<u2"), ("s16le", "<i2"), ("u32le", "<u4"), ("s32le", "<i4"),
+                    ("u64le", "<u8"), ("s64le", "<i8"), ("f16le", "<f2"), ("f32le", "<f4"), ("f64le", "<f8")):
+        got = O.pcm_from_f64(g["x"], dt)
+        # outside [-1, 1) the cast is undefined behaviour in C; only the signed formats are stable across x86-64 builds
+        sel = ((g["x"] >= -1) & (g["x"] < 1)) if np.dtype(dt).kind == "u" else np.ones(g["x"].shape, bool)
+        assert got.dtype == g[fmt].dtype and np.array_equal(got[sel], g[fmt][sel]), fmt
