@@ -138,6 +138,14 @@ __device__ __forceinline__ void scatter_frame(const uint32_t* __restrict__ frame
   }
 }
 
+// streaming 16-byte load: read-only path, no L1 allocation (the small L1 left beside ~210 KB of shared memory is kept
+// for the twiddle tables, which every sequence re-reads)
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
 // Whole-tile staging: every 16-byte load of the tile (16 per thread for FW = 4) is issued before the first
 // scatter, so one global-memory latency is exposed per tile instead of one per unrolled group of four.
 // src(f) returns the first 32-bit word of frame f of the tile.
@@ -154,7 +162,7 @@ __device__ __forceinline__ void stage_tile(SRC src, uint32_t* seq_base, int C, i
     for (int f = 0; f < FPT; f++) {
       const uint32_t* frame = src(f < nf ? f : nf - 1) + vec_word<CT>(tid, C, g);   // a short tile re-reads its last frame
 #pragma unroll
-      for (int i = 0; i < VPF; i++) x[f * VPF + i] = __ldg((const uint4*)(frame + vec_word<CT>(i * FW * 32, C, 0)));
+      for (int i = 0; i < VPF; i++) x[f * VPF + i] = ldg_stream((const uint4*)(frame + vec_word<CT>(i * FW * 32, C, 0)));
     }
 #pragma unroll
     for (int f = 0; f < FPT; f++) {
