@@ -186,6 +186,8 @@ def main():
         return
 
     dist = None
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
     if world > 1:
         import torch
         import torch.distributed as dist

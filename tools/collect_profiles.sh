@@ -1,0 +1,23 @@
+#!/bin/bash
+# Runs on the GPU box: bench lines, per-kernel timings, the ncu launch list of the bench command and one
+# `ncu --set full` capture per hot kernel (each ncu run only after the same command exited 0 without ncu).
+# usage: bash tools/collect_profiles.sh <tag>      -> files under gpurun_out/
+set -u
+tag=${1:-rX}
+out=gpurun_out
+python bench.py --steps 10 --warmup 3 > $out/${tag}_bench_line.json 2> $out/${tag}_bench.err || exit 1
+python bench.py --impl reference --steps 3 --warmup 1 > $out/${tag}_bench_reference_line.json 2>> $out/${tag}_bench.err
+python tools/bench_kernels.py > $out/${tag}_kernels.jsonl 2>> $out/${tag}_bench.err
+python bench.py --steps 2 --warmup 3 --no-cpu > /dev/null 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/${tag}_launches_bench.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu > $out/${tag}_ncu_bench.log 2>&1
+python tools/prof_driver.py 15000 2 p1 > /dev/null 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:"enc2048|dec2048" -s 3 -c 3 -o $out/${tag}_full_p1 -f \
+    python tools/prof_driver.py 15000 2 p1 > $out/${tag}_ncu_p1.log 2>&1
+python tools/prof_bytes.py 2 > /dev/null 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:"crc_kernel|rs_tile" -s 3 -c 3 -o $out/${tag}_full_bytes -f \
+    python tools/prof_bytes.py 2 > $out/${tag}_ncu_bytes.log 2>&1
+python tools/prof_driver.py 15000 2 golomb > /dev/null 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:"p1_pack|p1_unpack|compact_kernel" -s 3 -c 3 -o $out/${tag}_full_golomb -f \
+    python tools/prof_driver.py 15000 2 golomb > $out/${tag}_ncu_golomb.log 2>&1
+ls -la $out | tail -20

@@ -22,8 +22,17 @@ d_pcm = ctx.dev(pcm.nbytes); ctx.h2d(d_pcm, pcm)
 d_q = ctx.dev(frames * N * CH * 4); d_tq = ctx.dev(frames * 27 * CH * 4)
 d_out = ctx.dev(frames * N * CH * 8)
 d_pay = ctx.dev(frames * N * CH * 4); d_peak = ctx.dev(frames * 8)
+if mode == "golomb":
+    ctx.check(L.frad_p1_encode_dev(ctx.handle, d_pcm.ptr, _abi.F32, HOP, frames, N, CH, 16, 48000, 0.5526315789473684, 0, d_q.ptr, d_tq.ptr, None))
+    stride = L.frad_p1_raw_bound(N, CH, 0)
+    d_raw = ctx.dev(frames * stride); d_len = ctx.dev(frames * 4); d_cmp = ctx.dev(frames * 6144); d_off = ctx.dev((frames + 1) * 8)
+    d_st = ctx.dev(frames * 4)
 for _ in range(reps):
-    if mode == "p1":
+    if mode == "golomb":
+        ctx.check(L.frad_p1_pack_dev(ctx.handle, d_q.ptr, d_tq.ptr, None, frames, N, CH, d_raw.ptr, stride, d_len.ptr))
+        ctx.check(L.frad_compact_dev(ctx.handle, d_raw.ptr, stride, d_len.ptr, frames, d_cmp.ptr, frames * 6144, d_off.ptr))
+        ctx.check(L.frad_p1_unpack_dev(ctx.handle, d_cmp.ptr, d_off.ptr, frames, N, CH, 0, d_q.ptr, d_tq.ptr, None, d_st.ptr))
+    elif mode == "p1":
         ctx.check(L.frad_p1_encode_dev(ctx.handle, d_pcm.ptr, _abi.F32, HOP, frames, N, CH, 16, 48000, 0.5526315789473684, 0, d_q.ptr, d_tq.ptr, None))
         ctx.check(L.frad_p1_decode_dev(ctx.handle, d_q.ptr, d_tq.ptr, None, frames, N, CH, 16, 48000, _abi.PREC_F64, d_out.ptr, _abi.F64))
         ctx.check(L.frad_p1_decode_dev(ctx.handle, d_q.ptr, d_tq.ptr, None, frames, N, CH, 16, 48000, _abi.PREC_F32, d_out.ptr, _abi.F64))
