@@ -101,6 +101,8 @@ def lib():
             "frad_p1_unpack_dev": (i32, [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]),
             "frad_p1_encode_raw": (i32, [vp, vp, i32, i64, i32, i32, i32, i32, i32, dbl, i32, i32, vp, sz, vp]),
             "frad_p1_decode_raw": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp]),
+            "frad_overlap_dev": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp, i32, vp]),
+            "frad_p1_decode_stream": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp]),
             "frad_golomb_encode_host": (i64, [vp, sz, vp, sz]),
             "frad_golomb_decode_host": (i64, [vp, sz, vp, sz]),
             "frad_golomb_encode_batch_host": (i32, [vp, i32, sz, vp, sz, vp, i32]),
@@ -130,7 +132,7 @@ EXPORTS = [
     "frad_golomb_encode_host", "frad_golomb_decode_host", "frad_golomb_encode_batch_host",
     "frad_golomb_decode_batch_host",
     "frad_p1_raw_bound", "frad_p1_pack_dev", "frad_compact_dev", "frad_p1_unpack_dev", "frad_p1_encode_raw",
-    "frad_p1_decode_raw",
+    "frad_p1_decode_raw", "frad_overlap_dev", "frad_p1_decode_stream",
 ]
 
 
@@ -315,6 +317,30 @@ class Context:
         self.check(lib().frad_p1_decode_raw(self.handle, raw.ctypes.data, off.ctypes.data, nframes, n, ch, bits, srate, prec,
                                              profile, out.ctypes.data, dtype_code(out.dtype), status.ctypes.data))
         return out, status
+
+    def p1_decode_stream(self, raw: np.ndarray, off: np.ndarray, nframes: int, n: int, ch: int, bits: int, srate: int,
+                         ratio: int, fade: np.ndarray, prev_tail=None, prec: int = PREC_REF, profile: int = 1,
+                         out_dtype=np.float64):
+        """Payloads of a run of equal-sized lossy frames -> PCM as the reference's Decoder emits it: inverse transform,
+        cross-fade with the previous frame (decoder.py:28-46) and output sample format on the device.
+        Returns (pcm [B*cut, ch], tail f64 [n-cut, ch] to pass as prev_tail next time, status int32 [B])."""
+        raw = np.ascontiguousarray(raw, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        cut = n * (ratio - 1) // ratio
+        fade = np.ascontiguousarray(fade, dtype=np.float64)
+        if fade.size != n - cut:
+            raise FradError("fade window must have N - cut values")
+        if prev_tail is not None:
+            prev_tail = np.ascontiguousarray(prev_tail, dtype=np.float64)
+            if prev_tail.shape != (n - cut, ch):
+                raise FradError("prev_tail must be [N - cut, C]")
+        out = np.empty((nframes * cut, ch), out_dtype)
+        tail = np.empty((n - cut, ch), np.float64)
+        status = np.zeros(nframes, np.int32)
+        self.check(lib().frad_p1_decode_stream(self.handle, raw.ctypes.data, off.ctypes.data, nframes, n, ch, bits, srate, prec,
+                                                profile, ratio, fade.ctypes.data, _ptr(prev_tail), out.ctypes.data,
+                                                dtype_code(out.dtype), tail.ctypes.data, status.ctypes.data))
+        return out, tail, status
 
     # -- CRC / RS over host byte strings ---------------------------------------------------------
     @staticmethod

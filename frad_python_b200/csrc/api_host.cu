@@ -351,6 +351,8 @@ extern "C" int frad_rs_decode(frad_ctx* ctx, const uint8_t* buf, const uint64_t*
 // ---- profile 1 / 2 with the bit packing on the device: PCM <-> frame payloads before deflate -------------------
 // Same pipeline as above, but what crosses PCIe on the coded side is the Exp-Golomb-Rice byte string of every frame
 // (profile1.py:43-46 / profile2.py:48-51) instead of the int32 streams: about five times fewer bytes.
+extern "C" int frad_overlap_dev(frad_ctx* ctx, const double* frames, int B, int N, int C, int ratio, const double* fade,
+                                const double* prev_tail, void* out, int out_dtype, double* tail_out);
 int frad_compact_append(frad_ctx* ctx, const uint8_t* src, size_t stride, const uint32_t* len, int B, uint8_t* dst, uint64_t dst_cap,
                         uint64_t* dst_off, uint64_t* running);   // golomb.cu
 
@@ -456,6 +458,72 @@ extern "C" int frad_p1_decode_raw(frad_ctx* ctx, const uint8_t* raw, const uint6
     [&](int f0, int f1, cudaStream_t s) {
       int r = copy_async(ctx, (char*)pcm + (size_t)f0 * fbytes, d_out + (size_t)f0 * fbytes, (size_t)(f1 - f0) * fbytes, D2H_, s);
       if (!r && status) r = copy_async(ctx, status + f0, d_status + f0, 4 * (size_t)(f1 - f0), D2H_, s);
+      return r;
+    });
+  return rc;
+}
+
+// Payloads -> PCM as the reference's Decoder emits it for a run of equal-sized lossy frames: inverse transform, cross-fade
+// with the previous frame (decoder.py:28-46) and conversion to the output sample format (pcmformat.py:49-62), all on the
+// device; per frame only cut = N*(ratio-1)/ratio samples come back.  fade: L = N - cut window values (host);
+// prev_tail / tail_out: f64 [L][C] carried between calls (prev_tail NULL: first frame is not faded).
+extern "C" int frad_p1_decode_stream(frad_ctx* ctx, const uint8_t* raw, const uint64_t* raw_off, int B, int N, int C,
+                                     int bits, int srate, int prec, int profile, int ratio, const double* fade,
+                                     const double* prev_tail, void* pcm, int pcm_dtype, double* tail_out, int32_t* status) {
+  if (!ctx) return FRAD_E_ARG;
+  const int es = frad_dtype_size(pcm_dtype);
+  if (!es || B < 0 || N < 1 || C < 1 || !raw_off || (profile != 1 && profile != 2) || ratio < 2 || !fade)
+    return frad_fail(ctx, FRAD_E_ARG, "frad_p1_decode_stream: bad argument");
+  if (B == 0) return FRAD_OK;
+  FRAD_CUDA(ctx, cudaSetDevice(ctx->device));
+  const bool p2 = profile == 2;
+  const int cut = (int)((long long)N * (ratio - 1) / ratio), L = N - cut;
+  const size_t qf = (size_t)N * C, tf = (size_t)FRAD_NBANDS * C, lf = (size_t)FRAD_LPC_LEN * C;
+  const size_t fbytes = qf * 8, obytes = (size_t)cut * C * es, tbytes = (size_t)L * C * 8;
+  const size_t total = (size_t)raw_off[B];
+  const size_t cf = (size_t)(B < kChunkFrames ? B : kChunkFrames);
+  ARENA(ctx, a, rounded(total + 16) + rounded(8 * ((size_t)B + 1)) + rounded(4 * qf * cf) + rounded(4 * tf * cf) + rounded(4 * lf * cf) +
+                    rounded(fbytes * B) + rounded(obytes * B) + rounded(4 * (size_t)B) + rounded(8 * (size_t)L) + 2 * rounded(tbytes));
+  uint8_t* d_raw = (uint8_t*)take(a, total + 16);
+  uint64_t* d_off = (uint64_t*)take(a, 8 * ((size_t)B + 1));
+  int32_t* d_q = (int32_t*)take(a, 4 * qf * cf);
+  int32_t* d_tq = (int32_t*)take(a, 4 * tf * cf);
+  int32_t* d_l = p2 ? (int32_t*)take(a, 4 * lf * cf) : nullptr;
+  double* d_frames = (double*)take(a, fbytes * B);
+  char* d_out = (char*)take(a, obytes * B);
+  int32_t* d_status = (int32_t*)take(a, 4 * (size_t)B);
+  double* d_fade = (double*)take(a, 8 * (size_t)L);
+  double* d_prev = (double*)take(a, tbytes);
+  double* d_tail = (double*)take(a, tbytes);
+  if (a.bad) return frad_fail(ctx, FRAD_E_NOMEM, "internal arena overflow");
+  pipeline p;
+  int rc = pipeline_begin(ctx, B, &p);
+  if (rc) return rc;
+  rc = pipeline_run(p, B, false,
+    [&](int i, int f0, int f1, cudaStream_t s) {
+      int r = FRAD_OK;
+      if (i == 0) {
+        r = copy_async(ctx, d_off, raw_off, 8 * ((size_t)B + 1), H2D_, s);
+        if (!r) r = copy_async(ctx, d_fade, fade, 8 * (size_t)L, H2D_, s);
+        if (!r && prev_tail) r = copy_async(ctx, d_prev, prev_tail, tbytes, H2D_, s);
+      }
+      if (!r) r = copy_async(ctx, d_raw + raw_off[f0], raw + raw_off[f0], (size_t)(raw_off[f1] - raw_off[f0]), H2D_, s);
+      return r;
+    },
+    [&](int f0, int f1) {
+      const int nb = f1 - f0;
+      int r = frad_p1_unpack_dev(ctx, d_raw, d_off + f0, nb, N, C, p2 ? 1 : 0, d_q, d_tq, d_l, d_status + f0);
+      if (!r) r = frad_p1_decode_dev(ctx, d_q, d_tq, d_l, nb, N, C, bits, srate, prec, d_frames + (size_t)f0 * qf, FRAD_F64);
+      // the chunk's first frame fades against the last frame of the previous chunk, which sits right before it in d_frames
+      const double* tail_in = (f0 == 0) ? (prev_tail ? d_prev : nullptr) : d_frames + ((size_t)(f0 - 1) * N + cut) * C;
+      if (!r) r = frad_overlap_dev(ctx, d_frames + (size_t)f0 * qf, nb, N, C, ratio, d_fade, tail_in, d_out + (size_t)f0 * obytes,
+                                   pcm_dtype, (f1 == B) ? d_tail : nullptr);
+      return r;
+    },
+    [&](int f0, int f1, cudaStream_t s) {
+      int r = copy_async(ctx, (char*)pcm + (size_t)f0 * obytes, d_out + (size_t)f0 * obytes, (size_t)(f1 - f0) * obytes, D2H_, s);
+      if (!r && status) r = copy_async(ctx, status + f0, d_status + f0, 4 * (size_t)(f1 - f0), D2H_, s);
+      if (!r && tail_out && f1 == B) r = copy_async(ctx, tail_out, d_tail, tbytes, D2H_, s);
       return r;
     });
   return rc;

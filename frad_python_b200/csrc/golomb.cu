@@ -462,3 +462,50 @@ extern "C" int frad_p1_unpack_dev(frad_ctx* ctx, const uint8_t* raw, const uint6
   FRAD_LAUNCH_CHECK(ctx);
   return FRAD_OK;
 }
+
+// ---- decoder cross-fade (decoder.py:28-46) + output sample format -----------------------------------------------------
+// frames: f64 [B][N][C] straight from the inverse transform.  Frame b contributes its first cut = N*(ratio-1)/ratio
+// samples; the first L = N - cut of them are blended with the tail of frame b-1 (prev_tail for b == 0):
+//   out = rn(rn(cur * fade[i]) + rn(tail * fade[L-1-i]))      -- NumPy's two products and one sum, no FMA contraction
+// and then converted to the requested sample format (pcmformat.py:49-62).  One thread per output sample, coalesced.
+#include "devmath.cuh"
+namespace {
+__global__ void __launch_bounds__(256) overlap_kernel(const double* __restrict__ frames, long long B, int N, int C, int cut, int L,
+                                                      const double* __restrict__ fade, const double* __restrict__ prev_tail,
+                                                      void* __restrict__ out, int out_dtype, double* __restrict__ tail_out) {
+  const long long per = (long long)cut * C, total = B * per;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const long long b = e / per;
+    const int r = (int)(e - b * per), i = r / C, c = r - i * C;
+    double v = frames[(b * N + i) * C + c];
+    if (i < L && (b > 0 || prev_tail)) {
+      const double t = (b > 0) ? frames[((b - 1) * N + cut + i) * C + c] : prev_tail[(long long)i * C + c];
+      v = __dadd_rn(__dmul_rn(v, fade[i]), __dmul_rn(t, fade[L - 1 - i]));
+    }
+    store_pcm<double>(out, out_dtype, e, v);
+  }
+  if (tail_out) {
+    const long long tl = (long long)L * C;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < tl; e += stride)
+      tail_out[e] = frames[((B - 1) * N + cut) * C + e];
+  }
+}
+}  // namespace
+
+extern "C" int frad_overlap_dev(frad_ctx* ctx, const double* frames, int B, int N, int C, int ratio, const double* fade,
+                                const double* prev_tail, void* out, int out_dtype, double* tail_out) {
+  if (!ctx) return FRAD_E_ARG;
+  if (B < 0 || N < 1 || C < 1 || ratio < 2 || !frames || !fade || !out || !frad_dtype_size(out_dtype))
+    return frad_fail(ctx, FRAD_E_ARG, "frad_overlap_dev: bad argument");
+  if (B == 0) return FRAD_OK;
+  FRAD_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int cut = (int)((long long)N * (ratio - 1) / ratio), L = N - cut;
+  const long long total = (long long)B * cut * C;
+  long long want = (total + 255) / 256;
+  const long long cap = (long long)ctx->sm_count * 16;
+  overlap_kernel<<<(int)(want < cap ? (want < 1 ? 1 : want) : cap), 256, 0, ctx->stream>>>(frames, B, N, C, cut, L, fade, prev_tail, out,
+                                                                                      out_dtype, tail_out);
+  FRAD_LAUNCH_CHECK(ctx);
+  return FRAD_OK;
+}

@@ -3,14 +3,17 @@
 ``process`` parses every complete frame out of the byte buffer first (header sync is cheap host
 work), then runs CRC check / Reed-Solomon repair / dequantisation / inverse DCT for all of them in
 batched GPU calls grouped by frame parameters, and finally applies the cross-fade overlap in stream
-order (decoder.py:28-46, vectorised).  Frames whose CRC matches skip the RS decoder: the output is
-identical because the CRC covers data and parity.
+order (decoder.py:28-46).  A batch of lossy frames that share one set of parameters -- the normal case -- takes the
+fused route: bit parsing, dequantisation, inverse DCT, cross-fade and (optionally) the output sample format all run
+on the device and only the samples that are kept come back; anything irregular (parameter changes inside the batch,
+profile 0, a fragment of another size) falls back to the per-frame vectorised NumPy overlap.  Frames whose CRC
+matches skip the RS decoder: the output is identical because the CRC covers data and parity.
 """
 import numpy as np
 
 from . import common, fourier
 from ._abi import PREC_REF, default_context
-from .backend import hanning_in_overlap
+from .backend import from_f64, hanning_in_overlap
 from .fourier.profiles import COMPACT, LOSSLESS
 from .tools.asfh import ASFH
 
@@ -30,9 +33,13 @@ class _Pending:
 
 
 class Decoder:
-    def __init__(self, fix_error: bool = False, ctx=None, precision: int = PREC_REF):
+    def __init__(self, fix_error: bool = False, ctx=None, precision: int = PREC_REF, pcm_format=None):
+        """``pcm_format`` (numpy dtype, optional): deliver PCM in that sample format instead of float64 -- what the
+        reference application does afterwards with from_f64(pcm, fmt).astype(fmt) (src/decoder.py:23); on the fused
+        route the conversion happens on the device."""
         self.ctx = ctx or default_context()
         self.precision = precision
+        self.pcm_format = None if pcm_format is None else np.dtype(pcm_format)
         self.asfh = ASFH()
         self.info = ASFH()
         self.buffer = b""
@@ -97,6 +104,10 @@ class Decoder:
             it_p, it_f = iter(plain), iter(fixed)
             for i, r in zip(idxs, repair):
                 payloads[i] = next(it_f) if r else next(it_p)
+        # 2a. fused route: one parameter set, lossy profile with overlap -> everything up to the final samples on the device
+        fused = self._decode_fused(pend, payloads)
+        if fused is not None:
+            return fused
         # 2. transforms, grouped by everything that fixes the kernel configuration
         tgroups = {}
         for i, p in enumerate(pend):
@@ -117,7 +128,37 @@ class Decoder:
             for j, i in enumerate(idxs):
                 pcm[i] = out[j]
         # 3. overlap in stream order
-        return [self.overlap(pcm[i], p.profile, p.overlap_ratio) for i, p in enumerate(pend)]
+        return [self._fmt(self.overlap(pcm[i], p.profile, p.overlap_ratio)) for i, p in enumerate(pend)]
+
+    def _fmt(self, pcm: np.ndarray) -> np.ndarray:
+        if self.pcm_format is None or getattr(pcm, "ndim", 1) != 2:
+            return pcm
+        with np.errstate(all="ignore"):
+            return from_f64(pcm, self.pcm_format).astype(self.pcm_format)
+
+    def _decode_fused(self, pend, payloads):
+        p0 = pend[0]
+        if p0.profile not in (1, 2) or p0.overlap_ratio < 2:
+            return None
+        key = (p0.profile, p0.depth, p0.channels, p0.srate, p0.fsize, p0.overlap_ratio)
+        if any((p.profile, p.depth, p.channels, p.srate, p.fsize, p.overlap_ratio) != key for p in pend):
+            return None
+        n, ch, ratio = p0.fsize, p0.channels, p0.overlap_ratio
+        cut = n * (ratio - 1) // ratio
+        frag = self.overlap_fragment
+        have = frag.ndim == 2 and len(frag) > 0
+        if self.overlap_prog != 0 or (have and frag.shape != (n - cut, ch)) or n - cut < 1 or cut < n - cut:
+            return None
+        prof_mod = fourier.profile1 if p0.profile == 1 else fourier.profile2
+        buf, off = fourier.profile1.inflate_all(payloads)
+        out_dtype = np.float64 if self.pcm_format is None else self.pcm_format.newbyteorder("=")
+        if out_dtype != np.float64 and np.dtype(out_dtype).byteorder == ">":
+            return None
+        pcm, tail, _ = self.ctx.p1_decode_stream(buf, off, len(pend), n, ch, prof_mod.DEPTHS[p0.depth], p0.srate, ratio,
+                                                 hanning_in_overlap(n - cut), frag if have else None, self.precision,
+                                                 p0.profile, out_dtype)
+        self.overlap_fragment, self.overlap_prog = tail, 0
+        return [pcm]
 
     def _queue_frame(self, frad: bytes):
         a = self.asfh
@@ -170,7 +211,7 @@ class Decoder:
         return DecodeResult(ret_pcm, self.asfh.srate, frames, False)
 
     def flush(self) -> DecodeResult:
-        ret = self.overlap_fragment
+        ret = self._fmt(self.overlap_fragment)
         self.overlap_fragment = np.array([])
         self.asfh.clear()
         return DecodeResult([ret], self.asfh.srate, 0, False)

@@ -141,6 +141,18 @@ int frad_p1_encode_raw(frad_ctx* ctx, const void* pcm, int pcm_dtype, int64_t ho
 int frad_p1_decode_raw(frad_ctx* ctx, const uint8_t* raw, const uint64_t* raw_off, int B, int N, int C,
                        int bits, int srate, int prec, int profile, void* pcm, int pcm_dtype, int32_t* status);
 
+/* ---- decoder cross-fade (decoder.py:28-46) fused with the output sample format (pcmformat.py:49-62) ------------- */
+/* frames: f64 [B][N][C] (device).  Each frame yields its first cut = N*(ratio-1)/ratio samples; the first L = N - cut of
+ * them are blended with the previous frame's tail: out = cur*fade[i] + tail*fade[L-1-i] (fade: L window values, device).
+ * prev_tail: f64 [L][C] from the previous call or NULL (then frame 0 is not faded); out: [B*cut][C] samples of out_dtype;
+ * tail_out (may be NULL): f64 [L][C], the tail of frame B-1 for the next call. */
+int frad_overlap_dev(frad_ctx* ctx, const double* frames, int B, int N, int C, int ratio, const double* fade,
+                     const double* prev_tail, void* out, int out_dtype, double* tail_out);
+/* Host pointers, pipelined: payloads (as for frad_p1_decode_raw) -> cross-faded PCM in pcm_dtype, [B*cut][C]. */
+int frad_p1_decode_stream(frad_ctx* ctx, const uint8_t* raw, const uint64_t* raw_off, int B, int N, int C,
+                          int bits, int srate, int prec, int profile, int ratio, const double* fade,
+                          const double* prev_tail, void* pcm, int pcm_dtype, double* tail_out, int32_t* status);
+
 /* ---- CRC (zlib.crc32 / crc16_ansi) ---------------------------------------------------------- */
 /* Message i is buf[off[i] .. off[i]+len[i]); off == NULL means i*stride, len == NULL means ulen. */
 int frad_crc32_dev(frad_ctx* ctx, const uint8_t* buf, const uint64_t* off, const uint32_t* len,

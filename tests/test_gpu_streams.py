@@ -193,3 +193,60 @@ def test_reference_style_seams_batch_of_one(F, g_p0, g_p1, g_crc):
     assert F.common.crc32(b) == O.crc32(b) and F.common.crc16_ansi(b) == O.crc16_arc(b)
     e = F.tools.ecc.encode(b, 96, 24)
     assert e == O.ecc_encode(b, 96, 24) and F.tools.ecc.decode(e, 96, 24, True) == b
+
+
+@pytest.mark.parametrize("name", ["p1", "p2", "p1_ecc"])
+def test_decoder_fused_route_matches_per_frame_route_and_output_formats(F, g_streams, name, monkeypatch):
+    """The device cross-fade (decoder.py:28-46 fused after the inverse transform) gives bit for bit what the per-frame
+    NumPy overlap gives, for any chunking of the input (the fragment is carried between calls), and with `pcm_format`
+    the samples equal the reference application's from_f64(pcm, fmt).astype(fmt) of that float64 PCM."""
+    from frad_python_b200 import decoder as D
+    stream = g_streams[name].tobytes()
+    fused = [run_decoder(F, stream, name == "p1_ecc", chunk) for chunk in (4096, 32768, 1 << 22)]
+    calls = []
+    orig = D.Decoder._decode_fused
+    monkeypatch.setattr(D.Decoder, "_decode_fused", lambda self, pend, payloads: calls.append(len(pend)))   # -> None: fallback
+    slow = run_decoder(F, stream, name == "p1_ecc", 32768)
+    monkeypatch.setattr(D.Decoder, "_decode_fused", orig)
+    assert calls and slow.dtype == np.float64
+    for got in fused:
+        assert got.shape == slow.shape and np.array_equal(got, slow)
+    for fmt in ("<i2", "<f4", "<i4", "u1"):
+        got = run_decoder(F, stream, name == "p1_ecc", 32768, pcm_format=fmt)
+        want = O.pcm_from_f64(slow, fmt)
+        sel = ((slow >= -1) & (slow < 1)) if np.dtype(fmt).kind == "u" else np.ones(slow.shape, bool)
+        assert got.dtype == np.dtype(fmt) and np.array_equal(got[sel], want[sel]), fmt
+
+
+def test_overlap_kernel_against_numpy(F):
+    """frad_overlap_dev alone: random frames, with and without a carried-in tail, several ratios."""
+    from frad_python_b200._abi import lib, dtype_code
+    from frad_python_b200.backend import hanning_in_overlap
+    ctx = F.default_context()
+    rng = np.random.default_rng(3)
+    for (nb, n, c, ratio, carry) in ((5, 2048, 2, 16, False), (3, 512, 3, 2, True), (1, 256, 1, 7, True), (4, 2048, 8, 32, True)):
+        frames = rng.uniform(-1, 1, (nb, n, c))
+        cut = n * (ratio - 1) // ratio
+        L = n - cut
+        fade = hanning_in_overlap(L)
+        prev = rng.uniform(-1, 1, (L, c)) if carry else None
+        want, tail = [], prev
+        for f in frames:
+            f = f.copy()
+            if tail is not None:
+                head = f[:L] * fade[:, None]
+                head += tail * fade[::-1][:, None]
+                f[:L] = head
+            want.append(f[:cut]); tail = f[cut:]
+        want = np.concatenate(want)
+        d_fr = ctx.dev(frames.nbytes); ctx.h2d(d_fr, frames)
+        d_fd = ctx.dev(fade.nbytes); ctx.h2d(d_fd, fade)
+        d_pv = None
+        if carry:
+            d_pv = ctx.dev(prev.nbytes); ctx.h2d(d_pv, prev)
+        out = np.empty((nb * cut, c), np.float64); tl = np.empty((L, c), np.float64)
+        d_out = ctx.dev(out.nbytes); d_tl = ctx.dev(tl.nbytes)
+        ctx.check(lib().frad_overlap_dev(ctx.handle, d_fr.ptr, nb, n, c, ratio, d_fd.ptr, d_pv.ptr if d_pv else None, d_out.ptr,
+                                         dtype_code(np.float64), d_tl.ptr))
+        ctx.d2h(out, d_out.ptr); ctx.d2h(tl, d_tl.ptr); ctx.sync()
+        assert np.array_equal(out, want) and np.array_equal(tl, frames[-1][cut:])
