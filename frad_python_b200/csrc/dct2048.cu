@@ -38,6 +38,12 @@ __device__ __forceinline__ int zword(int n) {        // word index (units of T) 
   return 2 * padc(nn >> 2) + ((nn >> 1) & 1);
 }
 __device__ __forceinline__ int swz(int n) { return (n & ~31) | ((n + (n >> 5)) & 31); }
+// time-domain staging swizzle by element size: rows of 128 bytes (32 floats / 16 doubles) rotated by the row number, so
+// that the stride-4 scatter after the FFT and the stride-1/2/4 gathers of the store are both conflict-free per wavefront
+template <typename T> __device__ __forceinline__ int swzT(int n) {
+  if constexpr (sizeof(T) == 8) return (n & ~15) | ((n + (n >> 4)) & 15);
+  else return swz(n);
+}
 
 template <typename T> __device__ __forceinline__ T shfl_t(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
@@ -176,6 +182,67 @@ __device__ __forceinline__ void stage_tile(SRC src, uint32_t* seq_base, int C, i
             int ii, sq;
             vec_elem<CT>(tid + i * FW * 32, j, C, f, ii, sq);
             (seq_base + (size_t)sq * STRIDE_WORDS)[pos(ii)] = xs[j];
+          }
+        }
+      }
+    }
+  }
+}
+
+// Decoder staging: like stage_tile, but every loaded 32-bit word is converted on the fly (profile-0 unpack or profile-1
+// dequantiser x ramp, `cvt(word, k, slot)`) and stored as T at index k of its sequence -- the raw words never touch
+// shared memory.  Neighbouring bins of one sequence are stored as one 2 x T vector (conflict-free).
+template <int CT, int STRIDE_T, typename T, typename SRC, typename CVT, typename CVT4>
+__device__ __forceinline__ void stage_convert_tile(SRC src, T* seq_base, int C, int nf, int g, int tid, CVT cvt, CVT4 cvt4) {
+  typedef typename vec2<T>::type V2;
+  if constexpr (CT == 0) {
+    for (int f = 0; f < nf; f++) {
+      const uint32_t* frame = src(f);
+      const int cnt = vec_count<CT>(C);
+#pragma unroll 4
+      for (int e4 = tid; e4 < cnt; e4 += FW * 32) {
+        const uint4 x = ldg_stream((const uint4*)(frame + vec_word<CT>(e4, C, g)));
+        const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          int k, sq;
+          vec_elem<CT>(e4, j, C, f, k, sq);
+          (seq_base + (size_t)sq * STRIDE_T)[k] = cvt(xs[j], k, sq);
+        }
+      }
+    }
+  } else {
+    constexpr int FPT = (CT == 4) ? 1 : FW / CT;
+    constexpr int VPF = ((CT == 4) ? FN : FN * CT / 4) / (FW * 32);
+    uint4 x[FPT * VPF];
+#pragma unroll
+    for (int f = 0; f < FPT; f++) {
+      const uint32_t* frame = src(f < nf ? f : nf - 1) + vec_word<CT>(tid, C, g);
+#pragma unroll
+      for (int i = 0; i < VPF; i++) x[f * VPF + i] = ldg_stream((const uint4*)(frame + vec_word<CT>(i * FW * 32, C, 0)));
+    }
+#pragma unroll
+    for (int f = 0; f < FPT; f++) {
+      if (f < nf) {
+#pragma unroll
+        for (int i = 0; i < VPF; i++) {
+          const uint4 xv = x[f * VPF + i];
+          const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w};
+          const int e4 = tid + i * FW * 32;
+          T v[4];
+          int ks[4], sqs[4];
+#pragma unroll
+          for (int j = 0; j < 4; j++) vec_elem<CT>(e4, j, C, f, ks[j], sqs[j]);
+          cvt4(xs, ks, sqs, v);
+          if constexpr (CT == 2) {            // (k, c0) (k, c1) (k+1, c0) (k+1, c1): one pair of bins per channel
+            *(V2*)(seq_base + (size_t)sqs[0] * STRIDE_T + ks[0]) = mk2<T>(v[0], v[2]);
+            *(V2*)(seq_base + (size_t)sqs[1] * STRIDE_T + ks[1]) = mk2<T>(v[1], v[3]);
+          } else if constexpr (CT == 1) {     // four consecutive bins of the one channel
+            *(V2*)(seq_base + (size_t)sqs[0] * STRIDE_T + ks[0]) = mk2<T>(v[0], v[1]);
+            *(V2*)(seq_base + (size_t)sqs[2] * STRIDE_T + ks[2]) = mk2<T>(v[2], v[3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) (seq_base + (size_t)sqs[j] * STRIDE_T)[ks[j]] = v[j];
           }
         }
       }
@@ -478,7 +545,7 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
     if constexpr (sizeof(T) == 4) {
       for (int i = tid; i < DQ_TAB; i += FW * 32) { const float a = (float)i; tail->aux[i] = a * cbrtf(a) * (float)inv_scale; }
     } else {
-      for (int i = tid; i < DQ_SMEM64; i += FW * 32) tail->dq[i] = __ldg(dq64 + i);
+      for (int i = tid; i < DQ_SMEM64; i += FW * 32) tail->dq[i] = __ldg(dq64 + i) * inv_scale;
     }
   }
   const int words_per_frame = FN * C;
@@ -488,13 +555,108 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
     const int grp = (CT == 4) ? tile - b0 * tm.groups : 0;
     const int nf = min(tm.fpc, P.B - b0);
     const int nseq = (CT == 4) ? 4 : nf * C;
-    __syncthreads();
-    stage_tile<CT, LY::WARP_BYTES / 4>(
+    // ---- per-band ramp parameters of this warp's sequence from its threshold integers (profile1.py:66,
+    //      p1tools.py:35-41); every thread of the CTA reads them while it converts the tile below ----
+    if (PROFILE == 1 && w < nseq) {
+      const int f = (CT == 4) ? 0 : w / C, c = (CT == 4) ? 4 * grp + w : w - f * C, b = b0 + f;
+      double thr = 0.0;
+      if (lane < FRAD_NBANDS) {
+        const double tv = (double)P.tq[((size_t)b * FRAD_NBANDS + lane) * C + c];
+        const double av = fabs(tv);
+        thr = exp(copysign(sqrt(av * sqrt(av)), tv) * P.bt->log_base);   // (e/2)^(sign |tq|^0.75), profile1.py:66
+      }
+      const double thr_next = __shfl_down_sync(0xffffffffu, thr, 1);
+      if (lane <= FRAD_NBANDS) {
+        const int n = (lane < FRAD_NBANDS - 1) ? tail->lo[lane + 1] - tail->lo[lane] : 0;
+        if constexpr (sizeof(T) == 8) {
+          tail->rp[w][lane] = (n > 0) ? make_double2(thr, (thr_next - thr) / (double)n) : make_double2(0.0, 0.0);
+        } else {
+          tail->bp[w][lane] = (n > 0) ? make_float4((float)(thr / n), (float)(thr_next / n), (float)tail->lo[lane],
+                                                    (float)tail->lo[lane + 1])
+                                      : make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+        }
+      }
+    }
+    __syncthreads();                                        // previous tile stored, ramp tables visible
+    // value X[k] of sequence slot sq from the 32-bit word: profile 0 unpack + scrub, profile 1 dequantiser x ramp.
+    // The dequantiser table already carries the 1 / 2^(bits-1) of profile1.py:65 (a power of two: exact).
+    auto coef = [&](uint32_t u0, int k, int sq) -> T {
+      if (PROFILE == 0) {
+        const uint32_t u = P.le ? u0 : __byte_perm(u0, 0, 0x0123);
+        const float fv = __uint_as_float(u);
+        return (T)(((u & 0x7f800000u) == 0x7f800000u) ? 0.0f : fv);          // NaN / Inf -> 0 (profile0.py:66)
+      } else {
+        const int qi = (int)u0;
+        const int qa = abs(qi);
+        const int bnd = tail->bidx[k];
+        if constexpr (sizeof(T) == 8) {
+          double mag;
+          if (qa < DQ_SMEM64) mag = tail->dq[qa];
+          else mag = dequant_big(dq64, qa) * inv_scale;
+          const double2 rp = tail->rp[sq][bnd];
+          const double div = __dadd_rn(__dmul_rn((double)(k - tail->lo[bnd]), rp.y), rp.x);   // j * step + start
+          return (T)(((qi < 0) ? -mag : mag) * div);
+        } else {
+          float mag;
+          if (qa < DQ_TAB) mag = tail->aux[qa];
+          else mag = dequant_big_f32(qa, (float)inv_scale);
+          const float4 bpv = tail->bp[sq][bnd];
+          const float kf = (float)k;
+          const float dv = fmaf(kf - bpv.z, bpv.y, (bpv.w - kf) * bpv.x);
+          return (T)(((qi < 0) ? -mag : mag) * dv);
+        }
+      }
+    };
+    // four words of one 16-byte load.  For CT == 2 they are (k, c0) (k, c1) (k+1, c0) (k+1, c1): the two bins of a channel
+    // usually lie in the same band, so its ramp parameters (a 16-byte shared-memory fetch = 4 wavefronts) are loaded once
+    auto coef4 = [&](const uint32_t* u, const int* ks, const int* sqs, T* v) {
+      if constexpr (PROFILE == 1 && CT == 2) {
+        const int k0 = ks[0];
+        const uint32_t b2 = *(const uint16_t*)(tail->bidx + k0);              // k0 is even
+        const int bnd0 = (int)(b2 & 0xFFu), bnd1 = (int)(b2 >> 8);
+        const int lo0 = tail->lo[bnd0];
+        const int lo1 = (bnd1 == bnd0) ? lo0 : tail->lo[bnd1];
+#pragma unroll
+        for (int ch = 0; ch < 2; ch++) {
+          const int sq = sqs[ch];
+          const int q0 = (int)u[ch], q1 = (int)u[2 + ch];
+          const int a0 = abs(q0), a1 = abs(q1);
+          if constexpr (sizeof(T) == 8) {
+            const double2 rp0 = tail->rp[sq][bnd0];
+            double2 rp1 = rp0;
+            if (bnd1 != bnd0) rp1 = tail->rp[sq][bnd1];
+            double m0, m1;
+            if (a0 < DQ_SMEM64) m0 = tail->dq[a0]; else m0 = dequant_big(dq64, a0) * inv_scale;
+            if (a1 < DQ_SMEM64) m1 = tail->dq[a1]; else m1 = dequant_big(dq64, a1) * inv_scale;
+            const double d0 = __dadd_rn(__dmul_rn((double)(k0 - lo0), rp0.y), rp0.x);       // j * step + start
+            const double d1 = __dadd_rn(__dmul_rn((double)(k0 + 1 - lo1), rp1.y), rp1.x);
+            v[ch] = (T)(((q0 < 0) ? -m0 : m0) * d0);
+            v[2 + ch] = (T)(((q1 < 0) ? -m1 : m1) * d1);
+          } else {
+            const float4 bp0 = tail->bp[sq][bnd0];
+            float4 bp1 = bp0;
+            if (bnd1 != bnd0) bp1 = tail->bp[sq][bnd1];
+            float m0, m1;
+            if (a0 < DQ_TAB) m0 = tail->aux[a0]; else m0 = dequant_big_f32(a0, (float)inv_scale);
+            if (a1 < DQ_TAB) m1 = tail->aux[a1]; else m1 = dequant_big_f32(a1, (float)inv_scale);
+            const float kf0 = (float)k0, kf1 = (float)(k0 + 1);
+            const float d0 = fmaf(kf0 - bp0.z, bp0.y, (bp0.w - kf0) * bp0.x);
+            const float d1 = fmaf(kf1 - bp1.z, bp1.y, (bp1.w - kf1) * bp1.x);
+            v[ch] = (T)(((q0 < 0) ? -m0 : m0) * d0);
+            v[2 + ch] = (T)(((q1 < 0) ? -m1 : m1) * d1);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[j] = coef(u[j], ks[j], sqs[j]);
+      }
+    };
+    stage_convert_tile<CT, LY::WARP_BYTES / (int)sizeof(T), T>(
         [&](int f) {
           return (PROFILE == 0) ? (const uint32_t*)(P.payload + (size_t)(b0 + f) * P.payload_stride)
                                 : (const uint32_t*)(P.q + (size_t)(b0 + f) * words_per_frame);
         },
-        (uint32_t*)(smem_raw + LY::RAW_OFF), C, nf, grp, tid, [](int k) { return k; });
+        (T*)smem_raw, C, nf, grp, tid, coef, coef4);
     __syncthreads();
     {   // pull the next tile of this CTA towards L2 while the current one is transformed
       const int nt = tile + gridDim.x;
@@ -509,78 +671,9 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
       }
     }
     if (w < nseq) {
-      const int f = (CT == 4) ? 0 : w / C, c = (CT == 4) ? 4 * grp + w : w - f * C, b = b0 + f;
       unsigned char* mine = smem_raw + (size_t)w * LY::WARP_BYTES;
       V* buf = (V*)mine;
       T* X = (T*)mine;
-      const uint32_t* raw = (const uint32_t*)(mine + LY::RAW_OFF);
-      // ---- per-band ramp parameters from the threshold integers (profile1.py:66, p1tools.py:35-41) ----
-      if (PROFILE == 1) {
-        double thr = 0.0;
-        if (lane < FRAD_NBANDS) {
-          const double tv = (double)P.tq[((size_t)b * FRAD_NBANDS + lane) * C + c];
-          const double av = fabs(tv);
-          thr = exp(copysign(sqrt(av * sqrt(av)), tv) * P.bt->log_base);   // (e/2)^(sign |tq|^0.75), profile1.py:66
-        }
-        const double thr_next = __shfl_down_sync(0xffffffffu, thr, 1);
-        if (lane <= FRAD_NBANDS) {
-          const int n = (lane < FRAD_NBANDS - 1) ? tail->lo[lane + 1] - tail->lo[lane] : 0;
-          if constexpr (sizeof(T) == 8) {
-            tail->rp[w][lane] = (n > 0) ? make_double2(thr, (thr_next - thr) / (double)n) : make_double2(0.0, 0.0);
-          } else {
-            tail->bp[w][lane] = (n > 0) ? make_float4((float)(thr / n), (float)(thr_next / n), (float)tail->lo[lane],
-                                                      (float)tail->lo[lane + 1])
-                                        : make_float4(0.0f, 0.0f, 0.0f, 1.0f);
-          }
-        }
-        __syncwarp();
-      }
-      // value X[k] from the staged 32-bit word: profile 0 unpack + scrub, profile 1 dequantiser x ramp
-      auto coef = [&](uint32_t u0, int k, float kf) -> T {
-        if (PROFILE == 0) {
-          const uint32_t u = P.le ? u0 : __byte_perm(u0, 0, 0x0123);
-          const float fv = __uint_as_float(u);
-          return (T)(((u & 0x7f800000u) == 0x7f800000u) ? 0.0f : fv);          // NaN / Inf -> 0 (profile0.py:66)
-        } else {
-          const int qi = (int)u0;
-          const int qa = abs(qi);
-          const int bnd = tail->bidx[k];
-          if constexpr (sizeof(T) == 8) {
-            double mag;
-            if (qa < DQ_SMEM64) mag = tail->dq[qa];
-            else mag = dequant_big(dq64, qa);
-            const double2 rp = tail->rp[w][bnd];
-            const double div = __dadd_rn(__dmul_rn((double)(k - tail->lo[bnd]), rp.y), rp.x);   // j * step + start
-            return (T)((((qi < 0) ? -mag : mag) * inv_scale) * div);
-          } else {
-            float mag;
-            if (qa < DQ_TAB) mag = tail->aux[qa];
-            else mag = dequant_big_f32(qa, (float)inv_scale);
-            const float4 bpv = tail->bp[w][bnd];
-            const float dv = fmaf(kf - bpv.z, bpv.y, (bpv.w - kf) * bpv.x);
-            return (T)(((qi < 0) ? -mag : mag) * dv);
-          }
-        }
-      };
-      // ---- dequantise in place, highest bins first: X[k] (sizeof(T) bytes at k) may only overwrite raw words that
-      //      were already consumed, so every batch loads its eight words per lane before any lane stores ----
-      {
-        const float lf0 = (float)lane;
-#pragma unroll 1
-        for (int kb = FN - 256 + lane; kb >= 0; kb -= 256) {
-          uint32_t u[8];
-#pragma unroll
-          for (int i = 0; i < 8; i++) u[i] = raw[kb + 32 * i];
-          T xv[8];
-#pragma unroll
-          for (int i = 0; i < 8; i++) xv[i] = coef(u[i], kb + 32 * i, lf0 + (float)(kb - lane + 32 * i));
-          if (sizeof(T) == 8) __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 8; i++) X[kb + 32 * i] = xv[i];
-          if (sizeof(T) == 8) __syncwarp();
-        }
-      }
-      __syncwarp();
       // ---- pairwise pre-processing: R1 = X[k] - i X[N-k], R2 = (X[M-k] + i X[M+k]) e^{-i pi/4},
       //      S = ci (R1 + R2), G = ei ci (R1 - R2), Z[k] = S + iG, Z[M-k] = conj(S - iG) ----
       V z[32];
@@ -624,8 +717,8 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
         const int m = lane + 32 * o;
         const int n0 = (o < 16) ? 4 * m : (2 * FN - 1 - 4 * m);
         const int n1 = (o < 16) ? 4 * m + 2 : (2 * FN - 3 - 4 * m);
-        X[swz(n0)] = z[o].x;
-        X[swz(n1)] = z[o].y;
+        X[swzT<T>(n0)] = z[o].x;
+        X[swzT<T>(n1)] = z[o].y;
       }
     }
     __syncthreads();
@@ -636,21 +729,21 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
         const size_t woff = fbase + (size_t)vec_word<CT>(e4, C, grp);
         if (P.pcm_dtype == FRAD_F64) {
           double o4[4];
-          gather4<CT, LY::WARP_BYTES / (int)sizeof(T)>((const T*)smem_raw, C, f, e4, [](int n) { return swz(n); },
+          gather4<CT, LY::WARP_BYTES / (int)sizeof(T)>((const T*)smem_raw, C, f, e4, [](int n) { return swzT<T>(n); },
                                                        [](T x) { return (double)x; }, o4);
           double2* dst = (double2*)((double*)P.pcm + woff);
           dst[0] = make_double2(o4[0], o4[1]);
           dst[1] = make_double2(o4[2], o4[3]);
         } else if (P.pcm_dtype == FRAD_F32) {
           float o4[4];
-          gather4<CT, LY::WARP_BYTES / (int)sizeof(T)>((const T*)smem_raw, C, f, e4, [](int n) { return swz(n); },
+          gather4<CT, LY::WARP_BYTES / (int)sizeof(T)>((const T*)smem_raw, C, f, e4, [](int n) { return swzT<T>(n); },
                                                        [](T x) { return (float)x; }, o4);
           *(float4*)((float*)P.pcm + woff) = make_float4(o4[0], o4[1], o4[2], o4[3]);
         } else {
           // the other sample formats of pcmformat.py:49-62, converted in registers: 4 samples per thread and store
           const int dt = P.pcm_dtype;
           uint64_t o4[4];
-          gather4<CT, LY::WARP_BYTES / (int)sizeof(T)>((const T*)smem_raw, C, f, e4, [](int n) { return swz(n); },
+          gather4<CT, LY::WARP_BYTES / (int)sizeof(T)>((const T*)smem_raw, C, f, e4, [](int n) { return swzT<T>(n); },
                                                        [dt](T x) { return pcm_image((double)x, dt); }, o4);
           switch (pcm_size(dt)) {
             case 8: {
