@@ -560,11 +560,7 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
     if (PROFILE == 1 && w < nseq) {
       const int f = (CT == 4) ? 0 : w / C, c = (CT == 4) ? 4 * grp + w : w - f * C, b = b0 + f;
       double thr = 0.0;
-      if (lane < FRAD_NBANDS) {
-        const double tv = (double)P.tq[((size_t)b * FRAD_NBANDS + lane) * C + c];
-        const double av = fabs(tv);
-        thr = exp(copysign(sqrt(av * sqrt(av)), tv) * P.bt->log_base);   // (e/2)^(sign |tq|^0.75), profile1.py:66
-      }
+      if (lane < FRAD_NBANDS) thr = decode_threshold(P.bt, P.tq[((size_t)b * FRAD_NBANDS + lane) * C + c]);   // profile1.py:66
       const double thr_next = __shfl_down_sync(0xffffffffu, thr, 1);
       if (lane <= FRAD_NBANDS) {
         const int n = (lane < FRAD_NBANDS - 1) ? tail->lo[lane + 1] - tail->lo[lane] : 0;
@@ -679,21 +675,32 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
       V z[32];
       V zm_keep[17];
       const T r2 = (T)FRAD_RSQRT2;
-      auto pre_pair = [&](int k, V& zk, V& zmk) {
+      // twiddles of bin k = lane + 32 o.  f64: ci[k] = ci[lane] e^{i pi o / 128}, ei[k] = ei[lane] e^{i pi o / 32} -- one
+      // per-lane table value times a compile-time constant instead of two 16-byte loads per pair (see fft1024_warp)
+      V ci_lane = mk2<T>(T(0), T(0)), ei_lane = ci_lane;
+      if constexpr (sizeof(T) == 8) { ci_lane = __ldg(ci + lane); ei_lane = __ldg(ei + lane); }
+      auto pre_pair = [&](int k, int o, V& zk, V& zmk) {
         const T xk = X[k], xnk = (k == 0) ? T(0) : X[FN - k];
         const T a = X[FM - k], bb = X[FM + k];
         const V R1 = mk2<T>(xk, -xnk);
         const V R2 = mk2<T>((a + bb) * r2, (bb - a) * r2);
-        const V cik = __ldg(ci + k);
+        V cik, eik;
+        if constexpr (sizeof(T) == 8) {
+          cik = cmul(ci_lane, mk2<T>((T)g128_cos(o), (T)g128_sin(o)));
+          eik = cmul(ei_lane, mk2<T>((T)g32_cos(o), (T)g32_sin(o)));
+        } else {
+          cik = __ldg(ci + k);
+          eik = __ldg(ei + k);
+        }
         const V S = cmul(cik, cadd(R1, R2));
-        const V G = cmul(__ldg(ei + k), cmul(cik, csub(R1, R2)));
+        const V G = cmul(eik, cmul(cik, csub(R1, R2)));
         zk = mk2<T>(S.x - G.y, S.y + G.x);
         zmk = mk2<T>(S.x + G.y, -(S.y - G.x));          // conj(S - iG)
       };
 #pragma unroll
-      for (int o = 0; o < 16; o++) pre_pair(lane + 32 * o, z[o], zm_keep[o]);
+      for (int o = 0; o < 16; o++) pre_pair(lane + 32 * o, o, z[o], zm_keep[o]);
       zm_keep[16] = mk2<T>(T(0), T(0));
-      if (lane == 0) { V dummy; pre_pair(FM / 2, zm_keep[16], dummy); }      // Z[512] (self pair)
+      if (lane == 0) { V dummy; pre_pair(FM / 2, 16, zm_keep[16], dummy); }      // Z[512] (self pair): lane 0, o = 16
       __syncwarp();
       const int partner = (32 - lane) & 31;
 #pragma unroll

@@ -28,6 +28,44 @@ __device__ __forceinline__ double w32_sin(int t) {   // sin(2 pi t / 32) (positi
   return s[t & 31];
 }
 
+// exp(+i pi o / 128) and exp(+i pi o / 32), o = 0..16 (correctly rounded doubles; folded to immediates after unrolling)
+__device__ __forceinline__ double g128_cos(int o) {
+  const double t[17] = {
+      1.0, 0.9996988186962042, 0.9987954562051724, 0.9972904566786902,
+      0.9951847266721969, 0.99247953459871, 0.989176509964781, 0.9852776423889412,
+      0.9807852804032304, 0.9757021300385286, 0.970031253194544, 0.9637760657954398,
+      0.9569403357322088, 0.9495281805930367, 0.9415440651830208, 0.9329927988347388,
+      0.9238795325112867};
+  return t[o];
+}
+__device__ __forceinline__ double g128_sin(int o) {
+  const double t[17] = {
+      0.0, 0.024541228522912288, 0.049067674327418015, 0.07356456359966743,
+      0.0980171403295606, 0.1224106751992162, 0.14673047445536175, 0.17096188876030122,
+      0.19509032201612828, 0.2191012401568698, 0.2429801799032639, 0.26671275747489837,
+      0.2902846772544624, 0.31368174039889146, 0.33688985339222005, 0.35989503653498817,
+      0.3826834323650898};
+  return t[o];
+}
+__device__ __forceinline__ double g32_cos(int o) {
+  const double t[17] = {
+      1.0, 0.9951847266721969, 0.9807852804032304, 0.9569403357322088,
+      0.9238795325112867, 0.881921264348355, 0.8314696123025452, 0.773010453362737,
+      0.7071067811865476, 0.6343932841636455, 0.5555702330196022, 0.47139673682599764,
+      0.3826834323650898, 0.2902846772544624, 0.19509032201612828, 0.0980171403295606,
+      -5.053478687678417e-52};
+  return t[o];
+}
+__device__ __forceinline__ double g32_sin(int o) {
+  const double t[17] = {
+      0.0, 0.0980171403295606, 0.19509032201612828, 0.2902846772544624,
+      0.3826834323650898, 0.47139673682599764, 0.5555702330196022, 0.6343932841636455,
+      0.7071067811865476, 0.773010453362737, 0.8314696123025452, 0.881921264348355,
+      0.9238795325112867, 0.9569403357322088, 0.9807852804032304, 0.9951847266721969,
+      1.0};
+  return t[o];
+}
+
 // v * (c + i s)
 __device__ __forceinline__ float2 crot(float2 v, float c, float s) { return cmul_cs(v, c, s); }
 __device__ __forceinline__ double2 crot(double2 v, double c, double s) {
@@ -104,11 +142,29 @@ __device__ __forceinline__ void fft1024_warp(typename vec2<T>::type* v, typename
 #pragma unroll
   for (int i = 0; i < 32; i++) v[i] = buf[lane + 33 * i];
   __syncwarp();
+  if constexpr (sizeof(T) == 8) {
+    // f64: the 31 cross twiddles w^(i lane) are powers of one per-lane value, generated in registers (four independent
+    // chains of step w^4: <= 9 roundings, ~1e-15) instead of 31 16-byte table loads per lane -- the 16 KiB table does not
+    // stay in the little L1 that is left beside the shared memory and the loads stall on L2 latency
+    V b = __ldg(&tw32[32 + lane]);
+    if (INV) b.y = -b.y;
+    const V b2 = cmul(b, b), b4 = cmul(b2, b2);
+    V w0 = b, w1 = b2, w2 = cmul(b2, b), w3 = b4;            // w^1 .. w^4
 #pragma unroll
-  for (int i = 1; i < 32; i++) {
-    V w = __ldg(&tw32[i * 32 + lane]);
-    if (INV) w.y = -w.y;
-    v[i] = cmul(v[i], w);
+    for (int i = 1; i < 32; i += 4) {
+      v[i] = cmul(v[i], w0);
+      if (i + 1 < 32) v[i + 1] = cmul(v[i + 1], w1);
+      if (i + 2 < 32) v[i + 2] = cmul(v[i + 2], w2);
+      if (i + 3 < 32) v[i + 3] = cmul(v[i + 3], w3);
+      if (i + 4 < 32) { w0 = cmul(w0, b4); w1 = cmul(w1, b4); w2 = cmul(w2, b4); w3 = cmul(w3, b4); }
+    }
+  } else {
+#pragma unroll
+    for (int i = 1; i < 32; i++) {
+      V w = __ldg(&tw32[i * 32 + lane]);
+      if (INV) w.y = -w.y;
+      v[i] = cmul(v[i], w);
+    }
   }
   fft32_perm<T, INV>(v);
   V t[32];

@@ -14,7 +14,16 @@ struct band_table {
   double ath[FRAD_NBANDS];     // min(absolute hearing threshold at band centre, 1)
   double log_base;             // ln(e/2)
   double base;                 // e/2
+  // decoded thresholds (e/2)^(sign(t) |t|^0.75) for the threshold integers |t| <= FRAD_THR_TAB (profile1.py:66), computed
+  // on the host with libm's pow exactly in the reference's order; larger |t| are evaluated on the device
+  double thr_pow[2 * 255 + 1];
 };
+#define FRAD_THR_TAB 255
+__device__ __forceinline__ double decode_threshold(const band_table* bt, int t) {
+  if (t >= -FRAD_THR_TAB && t <= FRAD_THR_TAB) return __ldg(&bt->thr_pow[t + FRAD_THR_TAB]);
+  const double v = (double)t;
+  return pow(bt->base, copysign(pow(fabs(v), 0.75), v));
+}
 
 struct band_work {             // per-CTA shared scratch
   double thr[FRAD_NBANDS + 1];
@@ -381,9 +390,7 @@ __device__ void p1_prologue(const dec_params& P, T* X, int N, int b, int c, band
   if (t <= FRAD_NBANDS) { const int e = bt->edge[t]; bw->lo[t] = (e < N) ? e : N; }
   if (t < FRAD_NBANDS) {
     // profile1.py:66: (e/2) ** (sign(tq) |tq|^0.75)
-    const double v = (double)P.tq[((size_t)b * FRAD_NBANDS + t) * C + c];
-    const double e = copysign(pow(fabs(v), 0.75), v);
-    bw->thr[t] = (v == 0.0) ? 1.0 : pow(bt->base, e);
+    bw->thr[t] = decode_threshold(bt, P.tq[((size_t)b * FRAD_NBANDS + t) * C + c]);
   }
   if (t == 0) bw->thr[FRAD_NBANDS] = 0.0;
   __syncthreads();

@@ -604,6 +604,10 @@ static const band_table* get_band_table(frad_ctx* ctx, int N, int srate) {
   }
   h.log_base = log(M_E / 2.0);      // np.log(np.e / 2)
   h.base = M_E / 2.0;
+  for (int t = -FRAD_THR_TAB; t <= FRAD_THR_TAB; t++) {
+    const double v = (double)t;      // np.power(np.e / 2, sign(t) * |t| ** 0.75), profile1.py:66
+    h.thr_pow[t + FRAD_THR_TAB] = pow(M_E / 2.0, copysign(pow(fabs(v), 0.75), v));
+  }
   void* d = nullptr;
   if (cudaMalloc(&d, sizeof(band_table)) != cudaSuccess ||
       cudaMemcpy(d, &h, sizeof(band_table), cudaMemcpyHostToDevice) != cudaSuccess) {
