@@ -46,11 +46,11 @@ def pcm_dev(frames, n, hop, ch, dtype=np.float32):
     return d, pcm
 
 
-def transforms():
+def transforms(limit=None):
     for (n, hop, ch, frames, tag) in ((2048, 2048, 2, 15000, "S48 N=2048 C=2"), (2048, 2048, 8, 4000, "S96 N=2048 C=8"),
                                        (2048, 2048, 1, 30000, "mono N=2048"), (1024, 1024, 2, 30000, "N=1024 generic"),
                                        (4096, 4096, 2, 7500, "N=4096 generic"), (1280, 1280, 2, 24000, "N=1280 generic"),
-                                       (2000, 2000, 2, 15000, "N=2000 generic (lossless size)")):
+                                       (2000, 2000, 2, 15000, "N=2000 generic (lossless size)"))[:limit]:
         d_pcm, _ = pcm_dev(frames, n, hop, ch)
         ncoef = frames * n * ch
         d_pay = ctx.dev(ncoef * 4); d_peak = ctx.dev(frames * 8); d_out = ctx.dev(ncoef * 8)
@@ -120,6 +120,8 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     if which in ("all", "transforms"):
         transforms()
+    if which == "quick":                      # the three N = 2048 shapes only
+        transforms(3)
     if which in ("all", "bytes"):
         crc_rs()
     if which in ("all", "golomb"):
