@@ -28,6 +28,15 @@ namespace {
 #ifndef FRAD_MINB
 #define FRAD_MINB 4
 #endif
+#ifndef FRAD_ENC_EARLY
+#define FRAD_ENC_EARLY 0          // measured: requesting the next tile before the store phase costs the encoder 3 %
+#endif
+#ifndef FRAD_DEC_PRELOAD
+#define FRAD_DEC_PRELOAD 1
+#endif
+#ifndef FRAD_ENC_F32THR
+#define FRAD_ENC_F32THR 1
+#endif
 constexpr int FN = 2048, FM = 1024, FW = FRAD_FW;          // frame, half, warps per CTA
 constexpr int SEQ_CPX = 1056;                        // padded complex slots per warp buffer
 constexpr int DQ_TAB = 1024;                         // f32 dequantiser table entries (|q| < DQ_TAB)
@@ -69,6 +78,7 @@ __device__ __forceinline__ float transpose_reduce32(float* part, int lane) {
 struct smem_tail {
   int lo[FRAD_NBANDS + 1];
   double thr[FW][FRAD_NBANDS + 1];
+  double inv_ns[FRAD_NBANDS + 1];                     // 1 / (band width x scale)
   float4 bp[FW][FRAD_NBANDS + 1];                     // per band: ramp end points (pre-scaled), lo, hi as floats
   uint8_t bidx[FN];                                   // band index of every bin (FRAD_NBANDS - 1 = "past the ramps")
   float aux[(FW * FRAD_NBANDS * 32 > DQ_TAB) ? FW * FRAD_NBANDS * 32 : DQ_TAB];
@@ -236,6 +246,27 @@ __device__ __forceinline__ void load_tile(SRC src, int C, int nf, int g, int tid
     for (int i = 0; i < VPF; i++) x[f * VPF + i] = ldg_stream((const uint4*)(frame + vec_word<CT>(i * FW * 32, C, 0)));
   }
 }
+// encoder side: the loaded words go to position pos(i) of their sequence unchanged
+template <int CT, int STRIDE_WORDS, typename POS>
+__device__ __forceinline__ void scatter_tile(const uint4* x, uint32_t* seq_base, int C, int nf, int tid, POS pos) {
+  constexpr int FPT = tile_regs<CT>::FPT, VPF = tile_regs<CT>::VPF;
+#pragma unroll
+  for (int f = 0; f < FPT; f++) {
+    if (f < nf) {
+#pragma unroll
+      for (int i = 0; i < VPF; i++) {
+        const uint4 xv = x[f * VPF + i];
+        const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          int ii, sq;
+          vec_elem<CT>(tid + i * FW * 32, j, C, f, ii, sq);
+          (seq_base + (size_t)sq * STRIDE_WORDS)[pos(ii)] = xs[j];
+        }
+      }
+    }
+  }
+}
 template <int CT, int STRIDE_T, typename T, typename CVT4>
 __device__ __forceinline__ void convert_tile(const uint4* x, T* seq_base, int C, int nf, int tid, CVT4 cvt4) {
   typedef typename vec2<T>::type V2;
@@ -311,6 +342,12 @@ __device__ __noinline__ int quant_exact(float x, int j, double t0, double step, 
   return (x < 0.0f) ? -m : m;
 }
 
+__device__ __noinline__ int tq_exact(double thr, double log_base) {
+  const double vv = log(fmax(thr, 1.0)) / log_base;
+  const double d = (vv > 0.0) ? vv * cbrt(vv) : 0.0;                     // v^(4/3)
+  return sat_i32(rint(d));
+}
+
 template <int PROFILE, int CT>
 __global__ void __launch_bounds__(FW * 32, FRAD_MINB) enc2048_kernel(enc_params P, plan_dev pl, const float2* __restrict__ tw32,
                                                              int force_exact) {
@@ -323,8 +360,26 @@ __global__ void __launch_bounds__(FW * 32, FRAD_MINB) enc2048_kernel(enc_params 
   const float* pcm = (const float*)P.pcm;
   const float2* cfh = (const float2*)pl.cfh;
   const float2* dfh = (const float2*)pl.dfh;
-  if (PROFILE == 1) build_bidx(tail, P.bt, tid);
+  if (PROFILE == 1) {
+    build_bidx(tail, P.bt, tid);                            // (its barrier makes lo[] visible)
+    if (tid < FRAD_NBANDS) {
+      const int n = tail->lo[tid + 1] - tail->lo[tid];
+      tail->inv_ns[tid] = (n > 0) ? 1.0 / ((double)n * P.scale) : 0.0;
+    }
+  }
   const int words_per_frame = FN * C;
+
+  // the PCM words of a tile travel through registers; those of the next tile are requested before this one is stored
+  uint4 x[tile_regs<CT>::NX];
+  auto request_tile = [&](int t) {
+    if (CT == 0) return;
+    if (t >= tm.ntiles) t = tm.ntiles - 1;                // always overwrite x (nothing stale stays alive across the transform)
+    const int tb0 = (CT == 4) ? t / tm.groups : t * tm.fpc;
+    const int tgrp = (CT == 4) ? t - tb0 * tm.groups : 0;
+    load_tile<CT>([&](int f) { return (const uint32_t*)(pcm + (size_t)(tb0 + f) * P.hop * C); }, C, min(tm.fpc, P.B - tb0), tgrp, tid, x);
+  };
+  constexpr bool EARLY = (CT != 0) && FRAD_ENC_EARLY;
+  if (EARLY) request_tile(blockIdx.x);
 
   for (int tile = blockIdx.x; tile < tm.ntiles; tile += gridDim.x) {
     const int b0 = (CT == 4) ? tile / tm.groups : tile * tm.fpc;
@@ -332,8 +387,13 @@ __global__ void __launch_bounds__(FW * 32, FRAD_MINB) enc2048_kernel(enc_params 
     const int nf = min(tm.fpc, P.B - b0);
     const int nseq = (CT == 4) ? 4 : nf * C;              // sequences (= busy warps) in this tile
     __syncthreads();                                      // previous tile fully stored before restaging
-    stage_tile<CT, SEQ_CPX * 2>([&](int f) { return (const uint32_t*)(pcm + (size_t)(b0 + f) * P.hop * C); }, (uint32_t*)seq_all, C, nf,
-                                grp, tid, [](int n) { return zword(n); });
+    if constexpr (CT == 0) {
+      stage_tile<CT, SEQ_CPX * 2>([&](int f) { return (const uint32_t*)(pcm + (size_t)(b0 + f) * P.hop * C); }, (uint32_t*)seq_all, C, nf,
+                                  grp, tid, [](int n) { return zword(n); });
+    } else {
+      if (!EARLY) request_tile(tile);
+      scatter_tile<CT, SEQ_CPX * 2>(x, (uint32_t*)seq_all, C, nf, tid, [](int n) { return zword(n); });
+    }
     __syncthreads();
     {   // pull the next tile of this CTA towards L2 while the current one is transformed
       const int nt = tile + gridDim.x;
@@ -422,6 +482,7 @@ __global__ void __launch_bounds__(FW * 32, FRAD_MINB) enc2048_kernel(enc_params 
           __syncwarp();
         }
         const float scalef = (float)P.scale;
+        const float inv_log_base_f = (float)(1.0 / 0.30685281944005469058);   // 1 / ln(e/2)
         float tot = 0.0f;
         if (lane < FRAD_NBANDS) {
           const float* row = tail->aux + (size_t)w * FRAD_NBANDS * 32 + lane * 32;
@@ -445,9 +506,20 @@ __global__ void __launch_bounds__(FW * 32, FRAD_MINB) enc2048_kernel(enc_params 
         }
         if (lane <= FRAD_NBANDS) tail->thr[w][lane] = thr;             // entry 27 = 0
         if (lane < FRAD_NBANDS) {
-          const double vv = log(fmax(thr, 1.0)) / P.bt->log_base;
-          const double d = (vv > 0.0) ? vv * cbrt(vv) : 0.0;             // v^(4/3)
-          P.tq[((size_t)b * FRAD_NBANDS + lane) * C + c] = sat_i32(rint(d));
+          // threshold integer round((ln(max(thr, 1)) / ln(e/2))^(4/3)) (profile1.py:38-40).  f32 first: the relative error of
+          // logf / cbrtf and of the operand rounding is < 1e-6, so the integer is already decided unless d lies within
+          // 1e-3 (1 + d) of a rounding tie (or is huge) -- only then the f64 formula runs
+          int tqi = 0;
+          bool exact = !FRAD_ENC_F32THR;
+          if (FRAD_ENC_F32THR && thr > 1.0) {
+            const float lv = logf((float)thr) * inv_log_base_f;
+            const float df = lv * cbrtf(lv);
+            const float rf = rintf(df);
+            exact = !(fabsf(fabsf(df - rf) - 0.5f) > 1.0e-3f * (1.0f + df) && df < 1.0e6f);
+            tqi = (int)rf;
+          }
+          if (exact) tqi = tq_exact(thr, P.bt->log_base);
+          P.tq[((size_t)b * FRAD_NBANDS + lane) * C + c] = tqi;
         }
         // per-band ramp parameters, one band per lane: the divisor over the scale as a convex combination
         //   div / scale = t0s (hi - k) + t1s (k - lo),  t0s = thr[b] / (n scale), t1s = thr[b+1] / (n scale)
@@ -456,8 +528,13 @@ __global__ void __launch_bounds__(FW * 32, FRAD_MINB) enc2048_kernel(enc_params 
           if (lane <= FRAD_NBANDS) {
             float4 bpv = make_float4(1.0e30f, 1.0e30f, -1.0f, 2.0f * FN);  // huge divisor: bins past the last ramp quantise to 0
             if (lane < FRAD_NBANDS - 1 && cnt > 0) {
+#if FRAD_ENC_F32THR
+              const double ins = tail->inv_ns[lane];                      // 1 / (n scale)
+              bpv = make_float4((float)(thr * ins), (float)(thr_next * ins), (float)tail->lo[lane], (float)tail->lo[lane + 1]);
+#else
               const double ns = (double)cnt * P.scale;
               bpv = make_float4((float)(thr / ns), (float)(thr_next / ns), (float)tail->lo[lane], (float)tail->lo[lane + 1]);
+#endif
             }
             tail->bp[w][lane] = bpv;
           }
@@ -533,6 +610,7 @@ __global__ void __launch_bounds__(FW * 32, FRAD_MINB) enc2048_kernel(enc_params 
       }
     }
     __syncthreads();
+    if (EARLY) request_tile(tile + gridDim.x);            // in flight while this tile is stored
     // ---- cooperative, coalesced store: word e = k*C + c of frame f <- seq[f*C + c][k] ----
     for (int f = 0; f < nf; f++) {
       uint32_t* dst = (PROFILE == 0) ? (uint32_t*)(P.payload + (size_t)(b0 + f) * P.payload_stride)
@@ -844,6 +922,9 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
       convert_tile<CT, LY::WARP_BYTES / (int)sizeof(T), T>(x, (T*)smem_raw, C, nf, tid, coef4);
     }
     }
+    // f64: the three per-lane twiddle bases (cross twiddle, ci, ei) are fetched before the barrier, not at their first use
+    V ci_lane = mk2<T>(T(0), T(0)), ei_lane = ci_lane, tw_lane = ci_lane;
+    if constexpr (sizeof(T) == 8 && FRAD_DEC_PRELOAD) { ci_lane = __ldg(ci + lane); ei_lane = __ldg(ei + lane); tw_lane = __ldg(&tw32[32 + lane]); }
     __syncthreads();
     {   // pull the next tile of this CTA towards L2 while the current one is transformed
       const int nt = tile + gridDim.x;
@@ -869,8 +950,7 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
       const T r2 = (T)FRAD_RSQRT2;
       // twiddles of bin k = lane + 32 o.  f64: ci[k] = ci[lane] e^{i pi o / 128}, ei[k] = ei[lane] e^{i pi o / 32} -- one
       // per-lane table value times a compile-time constant instead of two 16-byte loads per pair (see fft1024_warp)
-      V ci_lane = mk2<T>(T(0), T(0)), ei_lane = ci_lane;
-      if constexpr (sizeof(T) == 8) { ci_lane = __ldg(ci + lane); ei_lane = __ldg(ei + lane); }
+      if constexpr (sizeof(T) == 8 && !FRAD_DEC_PRELOAD) { ci_lane = __ldg(ci + lane); ei_lane = __ldg(ei + lane); }
       auto pre_pair = [&](int k, int o, V& zk, V& zmk) {
         const T xk = X[k], xnk = (k == 0) ? T(0) : X[FN - k];
         const T a = X[FM - k], bb = X[FM + k];
@@ -909,7 +989,7 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
         const V l0 = (j == 16) ? zm_keep[16] : zm_keep[32 - j];
         z[j] = (lane == 0) ? l0 : g;
       }
-      fft1024_warp<T, true>(z, buf, lane, tw32);
+      fft1024_warp<T, true>(z, buf, lane, tw32, (sizeof(T) == 8 && FRAD_DEC_PRELOAD) ? &tw_lane : nullptr);
       // ---- undo the Makhoul reordering into the swizzled time-domain staging.  Output m = lane + 32 o goes to samples
       //      n = 4m, 4m + 2 (o < 16) or 2N - 1 - 4m, 2N - 3 - 4m (o >= 16); swzT(n) = per-lane base + 128 o, where the
       //      base only depends on the parity of o (f64: 16-element rows rotated by the row number) or not at all (f32:

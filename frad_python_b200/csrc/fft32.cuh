@@ -131,9 +131,11 @@ __device__ __forceinline__ int padc(int a) { return a + (a >> 5); }
 
 // Warp-level 1024-point FFT.  In: v[i] = z[lane + 32 i].  Out: v[o] = Z[lane + 32 o].
 // buf: this warp's exchange buffer (>= 1056 complex).  tw32: table [i][lane] = exp(-2 pi i * i * lane / 1024).
+// f64 only: `wlane` (optional) = tw32[32 + lane] already fetched by the caller, so its latency is not exposed here.
 template <typename T, bool INV>
 __device__ __forceinline__ void fft1024_warp(typename vec2<T>::type* v, typename vec2<T>::type* buf, int lane,
-                                             const typename vec2<T>::type* __restrict__ tw32) {
+                                             const typename vec2<T>::type* __restrict__ tw32,
+                                             const typename vec2<T>::type* wlane = nullptr) {
   typedef typename vec2<T>::type V;
   fft32_perm<T, INV>(v);
 #pragma unroll
@@ -146,7 +148,7 @@ __device__ __forceinline__ void fft1024_warp(typename vec2<T>::type* v, typename
     // f64: the 31 cross twiddles w^(i lane) are powers of one per-lane value, generated in registers (four independent
     // chains of step w^4: <= 9 roundings, ~1e-15) instead of 31 16-byte table loads per lane -- the 16 KiB table does not
     // stay in the little L1 that is left beside the shared memory and the loads stall on L2 latency
-    V b = __ldg(&tw32[32 + lane]);
+    V b = wlane ? *wlane : __ldg(&tw32[32 + lane]);
     if (INV) b.y = -b.y;
     const V b2 = cmul(b, b), b4 = cmul(b2, b2);
     V w0 = b, w1 = b2, w2 = cmul(b2, b), w3 = b4;            // w^1 .. w^4
