@@ -36,20 +36,22 @@ constexpr int kChunkFrames = 1024;
 
 struct pipeline {
   frad_ctx* ctx; int nchunks; int chunk;
-  cudaEvent_t* in_done; cudaEvent_t* k_done;
+  cudaEvent_t* in_done; cudaEvent_t* k_done; cudaEvent_t* aux; cudaEvent_t* out_done;     // one event of each kind per chunk
 };
 
 int pipeline_begin(frad_ctx* ctx, int B, pipeline* p) {
   p->ctx = ctx;
   p->chunk = kChunkFrames;
   p->nchunks = (B + p->chunk - 1) / p->chunk;
-  while ((int)ctx->pipe_events.size() < 2 * p->nchunks + 1) {
+  while ((int)ctx->pipe_events.size() < 4 * p->nchunks + 1) {
     cudaEvent_t e;
     FRAD_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     ctx->pipe_events.push_back(e);
   }
   p->in_done = ctx->pipe_events.data();
   p->k_done = ctx->pipe_events.data() + p->nchunks;
+  p->aux = ctx->pipe_events.data() + 2 * p->nchunks + 1;
+  p->out_done = ctx->pipe_events.data() + 3 * p->nchunks + 1;
   // the copy streams must not run ahead of work already queued on the main stream (buffer reuse)
   cudaEvent_t fence = ctx->pipe_events[2 * p->nchunks];
   FRAD_CUDA(ctx, cudaEventRecord(fence, ctx->stream));
@@ -59,24 +61,51 @@ int pipeline_begin(frad_ctx* ctx, int B, pipeline* p) {
 }
 
 // h2d(i, f0, f1, stream), run(f0, f1) [enqueues on ctx->stream], d2h(f0, f1, stream)
-template <class H2D, class RUN, class D2H>
-int pipeline_run(pipeline& p, int B, bool needs_next_chunk, H2D h2d, RUN run, D2H d2h) {
+// fin(stream): optional last step on the output stream before the final synchronisation
+struct no_fin { int operator()(cudaStream_t) const { return FRAD_OK; } };
+template <class H2D, class RUN, class D2H, class FIN = no_fin>
+int pipeline_run(pipeline& p, int B, bool needs_next_chunk, H2D h2d, RUN run, D2H d2h, FIN fin = FIN()) {
   frad_ctx* ctx = p.ctx;
   int rc;
+  // The host paces the copy queues: a chunk's input copy is submitted when the previous one has completed, its output
+  // copy when its kernels have finished and the previous output copy has left, so no stream ever holds more than one
+  // ready copy.  Measured on B200 with a decoder and an encoder running side by side on two contexts (one D2H-heavy, the
+  // other H2D-heavy): with the whole batch queued up front, or with three chunks of look-ahead, the second context's
+  // copies are only served after the first call has finished (9.9 ms for the pair = the sum of the two calls); paced
+  // like this the two calls interleave chunk by chunk (8.3 ms).  A call running alone pays about 3 % for the pacing.
+  int submitted_in = 0;
+  auto queue_in_upto = [&](int last) -> int {
+    for (; submitted_in <= last && submitted_in < p.nchunks; submitted_in++) {
+      const int i = submitted_in;
+      if (i > 0) FRAD_CUDA(ctx, cudaEventSynchronize(p.in_done[i - 1]));
+      const int f0 = i * p.chunk, f1 = (f0 + p.chunk < B) ? f0 + p.chunk : B;
+      int r = h2d(i, f0, f1, ctx->s_in);
+      if (r) return r;
+      FRAD_CUDA(ctx, cudaEventRecord(p.in_done[i], ctx->s_in));
+    }
+    return FRAD_OK;
+  };
+  auto queue_out = [&](int i) -> int {                     // chunk i's kernels are done: its results can leave
+    const int f0 = i * p.chunk, f1 = (f0 + p.chunk < B) ? f0 + p.chunk : B;
+    FRAD_CUDA(ctx, cudaEventSynchronize(p.k_done[i]));
+    if (i > 0) FRAD_CUDA(ctx, cudaEventSynchronize(p.out_done[i - 1]));
+    int r = d2h(f0, f1, ctx->s_out);
+    if (r) return r;
+    FRAD_CUDA(ctx, cudaEventRecord(p.out_done[i], ctx->s_out));
+    return FRAD_OK;
+  };
   for (int i = 0; i < p.nchunks; i++) {
     const int f0 = i * p.chunk, f1 = (f0 + p.chunk < B) ? f0 + p.chunk : B;
-    if ((rc = h2d(i, f0, f1, ctx->s_in))) return rc;
-    FRAD_CUDA(ctx, cudaEventRecord(p.in_done[i], ctx->s_in));
-  }
-  for (int i = 0; i < p.nchunks; i++) {
-    const int f0 = i * p.chunk, f1 = (f0 + p.chunk < B) ? f0 + p.chunk : B;
+    if ((rc = queue_in_upto(i + (needs_next_chunk ? 1 : 0)))) return rc;
     FRAD_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, p.in_done[i], 0));
     if (needs_next_chunk && i + 1 < p.nchunks) FRAD_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, p.in_done[i + 1], 0));
     if ((rc = run(f0, f1))) return rc;
     FRAD_CUDA(ctx, cudaEventRecord(p.k_done[i], ctx->stream));
-    FRAD_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, p.k_done[i], 0));
-    if ((rc = d2h(f0, f1, ctx->s_out))) return rc;
+    if ((rc = queue_in_upto(i + 1 + (needs_next_chunk ? 1 : 0)))) return rc;   // next input while these kernels run
+    if (i > 0 && (rc = queue_out(i - 1))) return rc;
   }
+  if ((rc = queue_out(p.nchunks - 1))) return rc;
+  if ((rc = fin(ctx->s_out))) return rc;
   FRAD_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
   FRAD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return FRAD_OK;
@@ -389,6 +418,12 @@ extern "C" int frad_p1_encode_raw(frad_ctx* ctx, const void* pcm, int pcm_dtype,
   int rc = pipeline_begin(ctx, B, &p);
   if (rc) return rc;
   bool overflow = false;
+  auto fetch_bytes = [&](int i, cudaStream_t s) -> int {       // payload bytes of chunk i, once its offsets are on the host
+    const int f0 = i * p.chunk, f1 = (f0 + p.chunk < B) ? f0 + p.chunk : B;
+    FRAD_CUDA(ctx, cudaEventSynchronize(p.aux[i]));
+    if (overflow || raw_off[f1] > raw_cap) { overflow = true; return (int)FRAD_OK; }
+    return copy_async(ctx, raw + raw_off[f0], d_raw + raw_off[f0], (size_t)(raw_off[f1] - raw_off[f0]), D2H_, s);
+  };
   rc = pipeline_run(p, B, hop < N,
     [&](int, int f0, int f1, cudaStream_t s) {
       const size_t lo = (size_t)f0 * hop * samp;
@@ -404,13 +439,17 @@ extern "C" int frad_p1_encode_raw(frad_ctx* ctx, const void* pcm, int pcm_dtype,
       return r;
     },
     [&](int f0, int f1, cudaStream_t s) -> int {
-      // offsets first (the byte range of this chunk is only known on the device), then the bytes themselves
+      // The byte range of a chunk is only known on the device: its offsets come back first, the bytes follow one chunk
+      // later -- by then the offsets have normally arrived, so the host does not stall the queue of kernels and copies
+      // waiting for one small transfer (which may sit behind another context's large copies on the D2H engine).
+      const int i = f0 / p.chunk;
       int r = copy_async(ctx, raw_off + f0, d_off + f0, 8 * (size_t)(f1 - f0 + 1), D2H_, s);
       if (r) return r;
-      FRAD_CUDA(ctx, cudaStreamSynchronize(s));
-      if (raw_off[f1] > raw_cap) { overflow = true; return (int)FRAD_OK; }
-      return copy_async(ctx, raw + raw_off[f0], d_raw + raw_off[f0], (size_t)(raw_off[f1] - raw_off[f0]), D2H_, s);
-    });
+      FRAD_CUDA(ctx, cudaEventRecord(p.aux[i], s));
+      if (i > 0) r = fetch_bytes(i - 1, s);
+      return r;
+    },
+    [&](cudaStream_t s) -> int { return fetch_bytes(p.nchunks - 1, s); });
   if (rc) return rc;
   if (overflow) return frad_fail(ctx, FRAD_E_NOMEM, "frad_p1_encode_raw: raw_cap too small (raw_off[B] holds the size needed)");
   return FRAD_OK;
