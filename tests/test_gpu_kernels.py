@@ -321,3 +321,30 @@ def test_decode_output_sample_formats(ctx, fast):
         got = ctx.p1_decode(q, tq, None, nb, n, c, 16, 48000, out_dtype=np.dtype(dt))
         sel = ((ref1 >= -1.0) & (ref1 < 1.0)) if np.dtype(dt).kind == "u" else np.ones(ref1.shape, bool)
         assert np.array_equal(got[sel], O.pcm_from_f64(ref1, dt)[sel]), dt
+
+
+@pytest.mark.parametrize("c", [1, 2, 4])
+def test_fast2048_decode_large_magnitudes_and_partial_tiles(ctx, c):
+    """Dequantiser table limits of the N = 2048 decode kernels: |q| beyond the shared-memory table (256 f64 / 1024 f32),
+    beyond the global table (4096) and at the int32 limits, negative threshold integers, an odd frame count (a tile
+    with a single frame).  Reference: profile1.py:65-77 on the same integers."""
+    from frad_python_b200 import _abi
+    rng = np.random.default_rng(77 + c)
+    nb = 5
+    q = np.rint(rng.laplace(0, 4, (nb, 2048 * c))).astype(np.int64)
+    for lim, cnt in ((300, 200), (1500, 100), (5000, 60), (10 ** 6, 30), (2 ** 31 - 1, 6)):
+        idx = rng.integers(0, q.size, cnt)
+        q.reshape(-1)[idx] = rng.integers(-lim, lim + 1, cnt)
+    q.reshape(-1)[[3, 2048 * c + 5]] = (2 ** 31 - 1, -(2 ** 31) + 1)
+    q = q.astype(np.int32)
+    tq = rng.integers(-3, 25, (nb, 27 * c)).astype(np.int32)
+    want = np.stack([O.p1_digital_ints(q[i], tq[i], 16, c, 48000, 2048) for i in range(nb)])
+    got = ctx.p1_decode(q, tq, None, nb, 2048, c, 16, 48000)
+    scale = np.max(np.abs(want))
+    assert np.max(np.abs(got - want)) <= 1e-12 * scale
+    got32 = ctx.p1_decode(q, tq, None, nb, 2048, c, 16, 48000, prec=_abi.PREC_F32)
+    assert np.max(np.abs(got32 - want)) <= 2e-5 * scale
+    # a quiet stream (everything inside the tables) through the same kernels
+    q2 = np.clip(q, -200, 200)
+    want2 = np.stack([O.p1_digital_ints(q2[i], tq[i], 16, c, 48000, 2048) for i in range(nb)])
+    assert np.max(np.abs(ctx.p1_decode(q2, tq, None, nb, 2048, c, 16, 48000) - want2)) <= 1e-12 * np.max(np.abs(want2))
