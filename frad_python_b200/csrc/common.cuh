@@ -1,5 +1,6 @@
 // Shared host/device plumbing for libfradb200 (context, error handling, plan cache).
 #pragma once
+#define FRAD_DQ_LEN 4096            // entries of the global |q|^(4/3) table (frad_ensure_dq64)
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -69,3 +70,5 @@ static inline int frad_dtype_size(int dt) {
     default: return 0;
   }
 }
+
+int frad_ensure_dq64(struct frad_ctx* ctx);   // transform.cu

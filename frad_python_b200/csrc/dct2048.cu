@@ -40,7 +40,7 @@ namespace {
 constexpr int FN = 2048, FM = 1024, FW = FRAD_FW;          // frame, half, warps per CTA
 constexpr int SEQ_CPX = 1056;                        // padded complex slots per warp buffer
 constexpr int DQ_TAB = 1024;                         // f32 dequantiser table entries (|q| < DQ_TAB)
-constexpr int DQ_TAB64 = 4096;                       // f64 table (global memory)
+constexpr int DQ_TAB64 = FRAD_DQ_LEN;                // f64 table (global memory, frad_ensure_dq64)
 constexpr int DQ_SMEM64 = 256;                       // head of the f64 table kept in shared memory
 #define FRAD_RSQRT2 0.70710678118654752440
 
@@ -737,7 +737,7 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
   const V* ci = (const V*)pl.ci;
   const V* ei = (const V*)pl.ei;
   const double inv_scale = 1.0 / P.scale;
-  if (PROFILE == 1) {
+  if (PROFILE != 0) {
     if constexpr (PAIR) build_ptab(tail, P.bt, tid); else build_bidx(tail, P.bt, tid);
     if constexpr (sizeof(T) == 4) {
       for (int i = tid; i < DQ_TAB; i += FW * 32) { const float a = (float)i; tail->aux[i] = a * cbrtf(a) * (float)inv_scale; }
@@ -751,7 +751,7 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
   //      They are only read while a tile is staged, so the warp prepares those of its NEXT tile while it transforms the
   //      current one: the threshold integers are fetched before the FFT, the table is written after it ----
   auto fetch_tq = [&](int t) -> int {
-    if (PROFILE != 1 || t >= tm.ntiles) return 0;
+    if (PROFILE == 0 || t >= tm.ntiles) return 0;
     const int tb0 = (CT == 4) ? t / tm.groups : t * tm.fpc;
     const int tgrp = (CT == 4) ? t - tb0 * tm.groups : 0;
     const int tnseq = (CT == 4) ? 4 : min(tm.fpc, P.B - tb0) * C;
@@ -760,7 +760,7 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
     return __ldg(P.tq + ((size_t)(tb0 + f) * FRAD_NBANDS + lane) * C + c);
   };
   auto put_ramps = [&](int tqv) {
-    if (PROFILE != 1) return;
+    if (PROFILE == 0) return;
     double thr = 0.0;
     if (lane < FRAD_NBANDS) thr = decode_threshold(P.bt, tqv);                                      // profile1.py:66
     const double thr_next = __shfl_down_sync(0xffffffffu, thr, 1);
@@ -775,7 +775,7 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
       }
     }
   };
-  if (PROFILE == 1) {
+  if (PROFILE != 0) {
     __syncthreads();                                        // lo[] of the tail is complete
     put_ramps(fetch_tq(blockIdx.x));
   }
@@ -783,7 +783,7 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
   // the tile's 32-bit words travel through registers: those of tile t + gridDim.x are requested before tile t is stored
   uint4 x[tile_regs<CT>::NX];
   auto request_tile = [&](int t) {
-    if (CT == 0) return;
+    if (CT == 0 || PROFILE == 2) return;
     if (t >= tm.ntiles) t = tm.ntiles - 1;      // always overwrite x (no stale values kept alive across the transform): re-read the last tile
     const int tb0 = (CT == 4) ? t / tm.groups : t * tm.fpc;
     const int tgrp = (CT == 4) ? t - tb0 * tm.groups : 0;
@@ -806,7 +806,35 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
     const int nseq = (CT == 4) ? 4 : nf * C;
     __syncthreads();                                        // previous tile stored, ramp tables visible
     if (!EARLY) request_tile(tile);
-    if constexpr (PAIR) {
+    if constexpr (PROFILE == 2) {
+      // ---- profile 2: the spectrum arrives dequantised and TNS-synthesised (tns_synth_kernel) as f64 [B][N][C];
+      //      what is left of profile2.py:85-91 is the ramp multiplication ----
+      constexpr int STRIDE_T = LY::WARP_BYTES / (int)sizeof(T);
+      T* seq_base = (T*)smem_raw;
+      const int Cg = (CT == 4) ? 4 : C, c0 = (CT == 4) ? 4 * grp : 0;
+      for (int f = 0; f < nf; f++) {
+        const double* src = P.spec + (size_t)(b0 + f) * FN * C + c0;
+#pragma unroll 4
+        for (int idx = tid; idx < FN * Cg; idx += FW * 32) {
+          int k, cc;
+          if (CT == 1) { k = idx; cc = 0; } else if (CT == 2) { k = idx >> 1; cc = idx & 1; }
+          else if (CT == 4) { k = idx >> 2; cc = idx & 3; } else { k = idx / C; cc = idx - k * C; }
+          const double v = __ldg(src + (size_t)k * C + cc);
+          const int sq = (CT == 4) ? cc : f * C + cc;
+          const int bnd = tail->bidx[k];
+          T val;
+          if constexpr (sizeof(T) == 8) {
+            const double2 rp = tail->rp[sq][bnd];
+            val = v * __dadd_rn(__dmul_rn((double)(k - tail->lo[bnd]), rp.y), rp.x);      // j * step + start
+          } else {
+            const float4 bpv = tail->bp[sq][bnd];
+            const float kf = (float)k;
+            val = (float)v * fmaf(kf - bpv.z, bpv.y, (bpv.w - kf) * bpv.x);
+          }
+          seq_base[(size_t)sq * STRIDE_T + k] = val;
+        }
+      }
+    } else if constexpr (PAIR) {
       // ---- stereo profile-1 staging: thread `tid` converts the bin pairs p = tid + 128 i of all four sequences ----
       constexpr int VPF = FN * 2 / 4 / (FW * 32);
       constexpr int STRIDE_T = LY::WARP_BYTES / (int)sizeof(T);
@@ -1061,20 +1089,6 @@ int launch_cfg(frad_ctx* ctx, K kernel, size_t smem, int ntiles, int* grid) {
   return FRAD_OK;
 }
 
-int ensure_dq64(frad_ctx* ctx) {
-  if (ctx->dequant_table) return FRAD_OK;
-  std::vector<double> h(DQ_TAB64);
-  for (int i = 0; i < DQ_TAB64; i++) h[i] = pow((double)i, 1.0 / 0.75);     // np.abs(x) ** (1 / 0.75), p1tools.py:44
-  void* d = nullptr;
-  if (cudaMalloc(&d, sizeof(double) * DQ_TAB64) != cudaSuccess ||
-      cudaMemcpy(d, h.data(), sizeof(double) * DQ_TAB64, cudaMemcpyHostToDevice) != cudaSuccess) {
-    cudaGetLastError();
-    return frad_fail(ctx, FRAD_E_NOMEM, "dequantiser table upload failed");
-  }
-  ctx->dequant_table = d;
-  return FRAD_OK;
-}
-
 }  // namespace
 
 // eligibility checks shared with transform.cu
@@ -1091,7 +1105,7 @@ bool frad_fast2048_decode_ok(const dec_params& P, int prec) {
   (void)prec;
   if (P.N != FN || (P.C > FW && (P.C % 4) != 0)) return false;
   if (P.profile == 0 && (P.bits != 32 || (P.payload_stride % 16) != 0 || ((uintptr_t)P.payload % 16) != 0)) return false;
-  if (P.profile == 2) return false;
+  if (P.profile == 2 && !P.spec) return false;
   if (P.profile == 1 && ((uintptr_t)P.q % 16) != 0) return false;
   if (((uintptr_t)P.pcm % 16) != 0) return false;
   return true;
@@ -1139,12 +1153,12 @@ int frad_launch_encode_2048(frad_ctx* ctx, const enc_params& P, const frad_plan*
   } while (0)
 
 int frad_launch_decode_2048(frad_ctx* ctx, const dec_params& P, const frad_plan* pl, int prec) {
-  int rc = ensure_dq64(ctx);
+  int rc = frad_ensure_dq64(ctx);
   if (rc) return rc;
   if (prec == FRAD_PREC_F32) {
-    if (P.profile == 0) DEC_DISPATCH_C(float, 0); else DEC_DISPATCH_C(float, 1);
+    if (P.profile == 0) DEC_DISPATCH_C(float, 0); else if (P.profile == 1) DEC_DISPATCH_C(float, 1); else DEC_DISPATCH_C(float, 2);
   } else {
-    if (P.profile == 0) DEC_DISPATCH_C(double, 0); else DEC_DISPATCH_C(double, 1);
+    if (P.profile == 0) DEC_DISPATCH_C(double, 0); else if (P.profile == 1) DEC_DISPATCH_C(double, 1); else DEC_DISPATCH_C(double, 2);
   }
   FRAD_LAUNCH_CHECK(ctx);
   return FRAD_OK;

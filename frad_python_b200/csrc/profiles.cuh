@@ -54,6 +54,7 @@ struct dec_params {
   double scale; const band_table* bt; const int32_t* q; const int32_t* tq; const int32_t* lpc;
   void* pcm; int pcm_dtype;
   void* gscratch; double* tns_scratch;
+  const double* spec;          // profile 2: dequantised spectrum after TNS synthesis, [B][N][C] (tns_synth_kernel)
 };
 
 // ---- block reductions (all threads get the result) ---------------------------------------------
@@ -290,28 +291,6 @@ static __device__ void tns_analysis_block(const double* x, double* work, int N, 
   __syncthreads();
 }
 
-// all-pole synthesis lfilter([1], a, x) by one thread, scipy's transposed direct form II order.
-// x: N doubles (input), y: N doubles (output).  Returns through bw->flag whether y is usable.
-static __device__ void tns_synthesis_block(const double* x, double* y, int N, band_work* bw) {
-  if (threadIdx.x == 0) {
-    double z[FRAD_LPC_LEN];
-    for (int i = 0; i < FRAD_LPC_LEN; i++) z[i] = 0.0;
-    double mx = 0.0; int bad = 0;
-    for (int n = 0; n < N; n++) {
-      const double xn = x[n];
-      const double yn = __dadd_rn(z[0], xn);
-#pragma unroll
-      for (int i = 0; i < FRAD_LPC_LEN - 2; i++) z[i] = __dsub_rn(__dadd_rn(z[i + 1], __dmul_rn(xn, 0.0)), __dmul_rn(yn, bw->a[i + 1]));
-      z[FRAD_LPC_LEN - 2] = __dsub_rn(__dmul_rn(xn, 0.0), __dmul_rn(yn, bw->a[FRAD_LPC_LEN - 1]));
-      y[n] = yn;
-      if (!isfinite(yn)) bad = 1;
-      mx = fmax(mx, fabs(yn));
-    }
-    bw->flag = !(bad || mx > 1e6);
-  }
-  __syncthreads();
-}
-
 // ---- profile 1 / 2 encode epilogue --------------------------------------------------------------
 template <typename T>
 __device__ void p1_epilogue(const enc_params& P, const T* X, int N, int b, int c, band_work* bw, int cta) {
@@ -405,22 +384,8 @@ __device__ void p1_prologue(const dec_params& P, T* X, int N, int b, int c, band
     }
     return;
   }
-  double* coef = P.tns_scratch + (size_t)cta * 2 * N;
-  double* synth = coef + N;
-  for (int k = t; k < N; k += blockDim.x) {
-    const double qv = (double)qrow[(size_t)k * C + c];
-    coef[k] = copysign(pow(fabs(qv), 1.0 / 0.75), qv) / P.scale;
-  }
-  if (t < FRAD_LPC_LEN) bw->aq[t] = P.lpc[((size_t)b * FRAD_LPC_LEN + t) * C + c];
-  __syncthreads();
-  int any = 0;
-  for (int i = 0; i < FRAD_LPC_LEN; i++) any |= (bw->aq[i] != 0);      // np.all(lpc_quant == 0), p2tools.py:98
-  const double* src = coef;
-  if (any) {
-    if (t < FRAD_LPC_LEN) bw->a[t] = (t == 0) ? 1.0 : (double)bw->aq[t] / 15.0;
-    __syncthreads();
-    tns_synthesis_block(coef, synth, N, bw);
-    if (bw->flag) src = synth;
-  }
-  for (int k = t; k < N; k += blockDim.x) X[k] = (T)(src[k] * ramp_value(bw, k));
+  // profile 2: the dequantiser and the all-pole TNS synthesis (profile2.py:80-85, p2tools.py:97-106) have already run for
+  // every sequence of the batch (tns_synth_kernel, one thread per sequence); only the ramp is left
+  const double* src = P.spec + (size_t)b * N * C + c;
+  for (int k = t; k < N; k += blockDim.x) X[k] = (T)(src[(size_t)k * C] * ramp_value(bw, k));
 }

@@ -360,6 +360,58 @@ __global__ void __launch_bounds__(256) seq_decode_direct_kernel(dec_params P, pl
   }
 }
 
+// Profile-2 decode, first step (profile2.py:80-85): dequantise the coefficients of every (frame, channel) sequence and run
+// the all-pole TNS synthesis lfilter([1], lpc / 15, x) over them (p2tools.py:97-106) -- a recurrence along the bins, so
+// the parallelism is across sequences: one thread per sequence, filter state in registers, SciPy's transposed direct
+// form II order of operations.  A sequence whose LPC integers are all zero, or whose output is not finite / exceeds 1e6,
+// keeps its unfiltered coefficients.  q, spec: [B][N][C]; lpc: [B][13][C]; dq64: |q|^(4/3) for |q| < 4096 (host libm).
+__global__ void __launch_bounds__(128) tns_synth_kernel(const int32_t* __restrict__ q, const int32_t* __restrict__ lpc, int B, int N, int C,
+                                                         double inv_scale, const double* __restrict__ dq64, int dq_len,
+                                                         double* __restrict__ spec) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= B * C) return;
+  const int b = s / C, c = s - b * C;
+  const int32_t* qs = q + (size_t)b * N * C + c;
+  double* out = spec + (size_t)b * N * C + c;
+  double a[FRAD_LPC_LEN];
+  int any = 0;
+#pragma unroll
+  for (int i = 0; i < FRAD_LPC_LEN; i++) {
+    const int v = lpc[((size_t)b * FRAD_LPC_LEN + i) * C + c];
+    any |= (v != 0);
+    a[i] = (i == 0) ? 1.0 : (double)v / 15.0;                          // dequantise_lpc, p2tools.py:49-55
+  }
+  auto coef = [&](int n) -> double {                                   // sign(q) |q|^(4/3) / 2^(bits-1), profile2.py:80
+    const int qv = __ldg(qs + (size_t)n * C);
+    const uint32_t qa = (qv < 0) ? 0u - (uint32_t)qv : (uint32_t)qv;
+    const double mag = ((qa < (uint32_t)dq_len) ? __ldg(dq64 + qa) : pow((double)qa, 1.0 / 0.75)) * inv_scale;
+    return (qv < 0) ? -mag : mag;
+  };
+  bool ok = false;
+  if (any) {
+    double z[FRAD_LPC_LEN - 1];
+#pragma unroll
+    for (int i = 0; i < FRAD_LPC_LEN - 1; i++) z[i] = 0.0;
+    double mx = 0.0;
+    bool bad = false;
+#pragma unroll 2
+    for (int n = 0; n < N; n++) {
+      const double xn = coef(n);
+      const double yn = __dadd_rn(z[0], xn);
+#pragma unroll
+      for (int i = 0; i < FRAD_LPC_LEN - 2; i++) z[i] = __dsub_rn(__dadd_rn(z[i + 1], __dmul_rn(xn, 0.0)), __dmul_rn(yn, a[i + 1]));
+      z[FRAD_LPC_LEN - 2] = __dsub_rn(__dmul_rn(xn, 0.0), __dmul_rn(yn, a[FRAD_LPC_LEN - 1]));
+      out[(size_t)n * C] = yn;
+      bad |= !isfinite(yn);
+      mx = fmax(mx, fabs(yn));
+    }
+    ok = !(bad || mx > 1e6);
+  }
+  if (!ok) {
+    for (int n = 0; n < N; n++) out[(size_t)n * C] = coef(n);
+  }
+}
+
 // 12-bit packing helpers (profile0.py:37-41, 54-58): 16-bit scratch <-> nibble-packed payload
 __global__ void pack12_kernel(const uint16_t* __restrict__ half_top12, size_t nvals, int B, uint8_t* payload, size_t stride) {
   const size_t npairs = (nvals + 1) / 2;
@@ -472,15 +524,48 @@ static int launch_encode(frad_ctx* ctx, enc_params& P, int prec) {
   return FRAD_OK;
 }
 
+// |q|^(4/3) for |q| < FRAD_DQ_LEN, computed on the host with libm's pow exactly like the reference (p1tools.py:44)
+int frad_ensure_dq64(frad_ctx* ctx) {
+  if (ctx->dequant_table) return FRAD_OK;
+  std::vector<double> h(FRAD_DQ_LEN);
+  for (int i = 0; i < FRAD_DQ_LEN; i++) h[i] = pow((double)i, 1.0 / 0.75);
+  void* d = nullptr;
+  if (cudaMalloc(&d, sizeof(double) * FRAD_DQ_LEN) != cudaSuccess ||
+      cudaMemcpy(d, h.data(), sizeof(double) * FRAD_DQ_LEN, cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaGetLastError();
+    return frad_fail(ctx, FRAD_E_NOMEM, "dequantiser table upload failed");
+  }
+  ctx->dequant_table = d;
+  return FRAD_OK;
+}
+
+// profile 2: dequantiser + TNS synthesis of the whole batch into ctx scratch slot 4; sets P.spec
+static int run_tns_synthesis(frad_ctx* ctx, dec_params& P) {
+  int rc = frad_ensure_dq64(ctx);
+  if (rc) return rc;
+  double* spec = (double*)frad_scratch(ctx, 4, sizeof(double) * (size_t)P.B * P.N * P.C);
+  if (!spec) return FRAD_E_NOMEM;
+  const int nseq = P.B * P.C;
+  tns_synth_kernel<<<(nseq + 127) / 128, 128, 0, ctx->stream>>>(P.q, P.lpc, P.B, P.N, P.C, 1.0 / P.scale, (const double*)ctx->dequant_table,
+                                                              FRAD_DQ_LEN, spec);
+  FRAD_LAUNCH_CHECK(ctx);
+  P.spec = spec;
+  return FRAD_OK;
+}
+
 static int launch_decode(frad_ctx* ctx, dec_params& P, int prec) {
   if (P.B <= 0) return FRAD_OK;
   frad_plan* pl = frad_get_plan(ctx, P.N, prec);
   if (!pl) return FRAD_E_NOMEM;
   const int nseq = P.B * P.C;
+  if (P.profile == 2) {
+    int rc = run_tns_synthesis(ctx, P);
+    if (rc) return rc;
+  }
   if (pl->direct) {
     int grid = 4 * ctx->sm_count; if (grid > nseq) grid = nseq;
     size_t need = (size_t)grid * P.N * sizeof(double);
-    size_t tns = (P.profile == 2) ? (size_t)grid * 2 * P.N * sizeof(double) : 0;
+    size_t tns = 0;
     char* g = (char*)frad_scratch(ctx, 0, need + tns);
     if (!g) return FRAD_E_NOMEM;
     P.gscratch = g; P.tns_scratch = (double*)(g + need);
@@ -495,7 +580,7 @@ static int launch_decode(frad_ctx* ctx, dec_params& P, int prec) {
   const void* k = (prec == FRAD_PREC_F32) ? (const void*)seq_decode_kernel<float> : (const void*)seq_decode_kernel<double>;
   int rc = (prec == FRAD_PREC_F32) ? configure<float>(ctx, pl, nseq, k, &cfg) : configure<double>(ctx, pl, nseq, k, &cfg);
   if (rc) return rc;
-  size_t tns = (P.profile == 2) ? (size_t)cfg.grid * 2 * P.N * sizeof(double) : 0;
+  size_t tns = 0;
   if (cfg.gscratch + tns) {
     char* g = (char*)frad_scratch(ctx, 0, cfg.gscratch + tns);
     if (!g) return FRAD_E_NOMEM;

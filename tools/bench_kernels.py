@@ -68,6 +68,16 @@ def transforms(limit=None):
                   ncoef * 12, f"p1 decode int32->f64 (f64 math) [{tag}]")
             timed(lambda: ctx.check(L.frad_p1_decode_dev(ctx.handle, d_q.ptr, d_tq.ptr, None, frames, n, ch, 16, 48000, _abi.PREC_F32, d_out.ptr, _abi.F64)),
                   ncoef * 12, f"p1 decode int32->f64 (f32 math) [{tag}]")
+            if n == 2048 and ch == 2:      # profile 2 (TNS) on the same shape: lpc != NULL selects it
+                d_lpc = ctx.dev(frames * 13 * ch * 4)
+                timed(lambda: ctx.check(L.frad_p1_encode_dev(ctx.handle, d_pcm.ptr, _abi.F32, hop, frames, n, ch, 16, 48000, 0.5526315789473684, 0, d_q.ptr, d_tq.ptr, d_lpc.ptr)),
+                      ncoef * 8, f"p2 encode f32->int32 + lpc [{tag}]")
+                timed(lambda: ctx.check(L.frad_p1_decode_dev(ctx.handle, d_q.ptr, d_tq.ptr, d_lpc.ptr, frames, n, ch, 16, 48000, _abi.PREC_F64, d_out.ptr, _abi.F64)),
+                      ncoef * 12, f"p2 decode int32 + lpc->f64 (f64 math) [{tag}]")
+                lp = np.zeros(frames * 13 * ch, np.int32); ctx.d2h(lp, d_lpc.ptr); ctx.sync()
+                print(json.dumps({"note": "profile 2: share of (frame, channel) sequences with TNS active",
+                                  "value": float(np.mean(np.any(lp.reshape(frames, 13, ch) != 0, axis=1)))}), flush=True)
+                d_lpc.free()
             d_q.free(); d_tq.free()
         for b in (d_pcm, d_pay, d_peak, d_out):
             b.free()
