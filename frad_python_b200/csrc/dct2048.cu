@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(FW * 32, FRAD_MINB) enc2048_kernel(enc_params 
   const float* pcm = (const float*)P.pcm;
   const float2* cfh = (const float2*)pl.cfh;
   const float2* dfh = (const float2*)pl.dfh;
-  if (PROFILE == 1) {
+  if (PROFILE != 0) {
     build_bidx(tail, P.bt, tid);                            // (its barrier makes lo[] visible)
     if (tid < FRAD_NBANDS) {
       const int n = tail->lo[tid + 1] - tail->lo[tid];
@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(FW * 32, FRAD_MINB) enc2048_kernel(enc_params 
       const bool swap_out = (PROFILE == 0) && !P.le;
       float mx = 0.0f;
       float* part = tail->aux + (size_t)w * FRAD_NBANDS * 32 + lane;     // this lane's column of band partials
-      if (PROFILE == 1) {
+      if (PROFILE != 0) {
 #pragma unroll
         for (int bnd = 0; bnd < FRAD_NBANDS; bnd++) part[bnd * 32] = 0.0f;
       }
@@ -521,6 +521,12 @@ __global__ void __launch_bounds__(FW * 32, FRAD_MINB) enc2048_kernel(enc_params 
           if (exact) tqi = tq_exact(thr, P.bt->log_base);
           P.tq[((size_t)b * FRAD_NBANDS + lane) * C + c] = tqi;
         }
+        if constexpr (PROFILE == 2) {
+          // profile 2: TNS works on the whole masked spectrum in f64 (profile2.py:32) -- a separate kernel (tns_encode_kernel,
+          // transform.cu) takes over from here.  It gets the spectrum (stored below as float bits in the q array) and
+          // this sequence's thresholds, [b][c][28] doubles.
+          if (lane <= FRAD_NBANDS) P.tns_scratch[((size_t)b * C + c) * (FRAD_NBANDS + 1) + lane] = thr;
+        } else {
         // per-band ramp parameters, one band per lane: the divisor over the scale as a convex combination
         //   div / scale = t0s (hi - k) + t1s (k - lo),  t0s = thr[b] / (n scale), t1s = thr[b+1] / (n scale)
         {
@@ -607,6 +613,7 @@ __global__ void __launch_bounds__(FW * 32, FRAD_MINB) enc2048_kernel(enc_params 
             }
           }
         }
+        }   // PROFILE == 1
       }
     }
     __syncthreads();
@@ -1096,8 +1103,7 @@ bool frad_fast2048_encode_ok(const enc_params& P, int prec) {
   if (P.N != FN || prec != FRAD_PREC_F32 || P.pcm_dtype != FRAD_F32) return false;
   if (P.C > FW && (P.C % 4) != 0) return false;
   if (P.profile == 0 && (P.bits != 32 || (P.payload_stride % 16) != 0 || ((uintptr_t)P.payload % 16) != 0)) return false;
-  if (P.profile == 2) return false;
-  if (P.profile == 1 && ((uintptr_t)P.q % 16) != 0) return false;
+  if (P.profile != 0 && ((uintptr_t)P.q % 16) != 0) return false;
   if (((uintptr_t)P.pcm % 16) != 0 || ((P.hop * P.C) % 4) != 0) return false;
   return true;
 }
@@ -1129,7 +1135,7 @@ int frad_launch_encode_2048(frad_ctx* ctx, const enc_params& P, const frad_plan*
     if (P.C == 2) ENC_DISPATCH(PROF, 2); else if (P.C == 1) ENC_DISPATCH(PROF, 1);                    \
     else if (P.C % 4 == 0) ENC_DISPATCH(PROF, 4); else ENC_DISPATCH(PROF, 0);                         \
   } while (0)
-  if (P.profile == 0) ENC_BY_C(0); else ENC_BY_C(1);
+  if (P.profile == 0) ENC_BY_C(0); else if (P.profile == 1) ENC_BY_C(1); else ENC_BY_C(2);   // 2: P.tns_scratch = thresholds out
   FRAD_LAUNCH_CHECK(ctx);
   return FRAD_OK;
 }

@@ -31,6 +31,7 @@ struct band_work {             // per-CTA shared scratch
   double sum[FRAD_NBANDS + 1];
   int lo[FRAD_NBANDS + 1];
   double red[33];
+  double redm[FRAD_LPC_LEN * 32];   // block_sum_multi: [value][warp]
   double r[FRAD_LPC_LEN + 3];
   double a[FRAD_LPC_LEN + 3];
   int aq[FRAD_LPC_LEN + 3];
@@ -87,6 +88,26 @@ __device__ __forceinline__ double block_max(double v, double* red) {
   double t = red[0];
   for (int i = 1; i < nw; i++) t = fmax(t, red[i]);
   return t;
+}
+
+// K sums in one round (two barriers instead of 2 K).  Every value goes through exactly the additions of block_sum.
+template <int K>
+__device__ __forceinline__ void block_sum_multi(double (&v)[K], double* red /* K * 32 doubles */) {
+  const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int j = 0; j < K; j++) v[j] = warp_sum(v[j]);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int j = 0; j < K; j++) red[j * 32 + w] = v[j];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < K; j++) {
+    double t = 0.0;
+    for (int i = 0; i < nw; i++) t += red[j * 32 + i];
+    v[j] = t;
+  }
 }
 
 // ---- profile 0 ---------------------------------------------------------------------------------
@@ -169,6 +190,57 @@ __device__ __forceinline__ double np_sum_small(const double* a, int n) {
   return res;
 }
 
+template <int NN>
+__device__ __forceinline__ double np_sum_small_t(const double (&a)[FRAD_LPC_LEN]) {     // np_sum_small(a, NN), unrolled
+  if (NN < 8) {
+    double r = 0.0;
+#pragma unroll
+    for (int i = 0; i < NN; i++) r = __dadd_rn(r, a[i]);
+    return r;
+  }
+  double r[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) r[j] = a[j];
+  constexpr int full = NN - (NN % 8);
+#pragma unroll
+  for (int i = 8; i < full; i += 8) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) r[j] = __dadd_rn(r[j], a[i + j]);
+  }
+  double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                         __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+#pragma unroll
+  for (int i = (full < 8 ? 8 : full); i < NN; i++) res = __dadd_rn(res, a[i]);
+  return res;
+}
+
+// one Levinson-Durbin step (p2tools.py:22-32) with every index a compile-time constant: the arrays stay in registers
+template <int I>
+__device__ __forceinline__ void levinson_step(double (&a)[FRAD_LPC_LEN], const double (&r)[FRAD_LPC_LEN], double& err, bool& go) {
+  if (go) {
+    double prod[FRAD_LPC_LEN], tmp[FRAD_LPC_LEN];
+#pragma unroll
+    for (int j = 0; j < FRAD_LPC_LEN; j++) { prod[j] = (j < I) ? __dmul_rn(a[j], r[(I - j) > 0 ? (I - j) : 0]) : 0.0; tmp[j] = a[j]; }
+    double k = -np_sum_small_t<I>(prod) / err;
+    if (fabs(k) >= 0.96) k = (k > 0.0) ? 0.96 : -0.96;
+    a[I] = k;
+#pragma unroll
+    for (int j = 1; j < I; j++) a[j] = __dadd_rn(a[j], __dmul_rn(k, tmp[I - j]));
+    err = __dmul_rn(err, __dsub_rn(1.0, __dmul_rn(k, k)));
+    if (err <= 1e-12) go = false;
+  }
+}
+
+// round(sign(y) |y|^0.75) (p1tools.py:43): f32 first, the f64 formula only next to a rounding tie.  f32 budget: operand
+// rounding 6e-8, two correctly rounded square roots and a product < 2e-7 relative in total; guard 1e-6 v.
+__device__ __forceinline__ int32_t quant075(double y) {
+  const float af = (float)fabs(y);
+  const float v = sqrtf(af * sqrtf(af));
+  const float r = rintf(v);
+  if (fabsf(fabsf(v - r) - 0.5f) > 1.0e-6f * v + 1.0e-7f && v < 4.0e6f) { const int m = (int)r; return (y < 0.0) ? -m : m; }
+  return sat_i32(rint(copysign(pow075(fabs(y)), y)));
+}
+
 // ---- TNS (p2tools.py) --------------------------------------------------------------------------
 // x: masked spectrum (double, N), work: N doubles.  On return bw->flag != 0 means the residual in
 // `work` replaces x and bw->aq holds the quantised LPC; otherwise x stands and aq is all zero.
@@ -178,14 +250,27 @@ static __device__ void tns_analysis_block(const double* x, double* work, int N, 
   if (t == 0) bw->flag = 0;
   __syncthreads();
   if (N < 2 * (FRAD_LPC_LEN - 1)) return;
-  double sl = 0.0, sa = 0.0, se = 0.0, sx = 0.0;
+  // lpc_cond (p2tools.py:108-111): spectral flatness exp(mean log(|x| + 1e-10)) / (mean |x| + 1e-10) < 0.5.  The logarithms
+  // only feed this yes/no decision, so they are taken in f32 first (relative error of the ratio < 1e-5); the f64 sum of
+  // logs is only formed when the ratio lands within 1e-3 of the limit.  The other sums are f64 as before.
+  double s4[4] = {0.0, 0.0, 0.0, 0.0};                 // sum log(|x| + 1e-10), sum |x|, sum x^2, sum x
+  float slf = 0.0f;
   for (int n = t; n < N; n += blockDim.x) {
     const double v = x[n], m = fabs(v);
-    sl += log(m + 1e-10); sa += m; se += v * v; sx += v;
+    slf += logf((float)(m + 1e-10)); s4[1] += m; s4[2] += v * v; s4[3] += v;
   }
-  sl = block_sum(sl, bw->red); sa = block_sum(sa, bw->red); se = block_sum(se, bw->red); sx = block_sum(sx, bw->red);
-  const double geo = exp(sl / N), arith = sa / N;
-  if (!(geo / (arith + 1e-10) < 0.5)) return;          // lpc_cond, p2tools.py:108-111
+  s4[0] = (double)slf;
+  block_sum_multi<4>(s4, bw->redm);
+  const double sa = s4[1], se = s4[2], sx = s4[3];
+  const double arith = sa / N;
+  double flat = exp(s4[0] / N) / (arith + 1e-10);
+  if (!(fabs(flat - 0.5) > 1e-3)) {                    // too close to call (or NaN): exact sum, same for every thread
+    double sl = 0.0;
+    for (int n = t; n < N; n += blockDim.x) sl += log(fabs(x[n]) + 1e-10);
+    sl = block_sum(sl, bw->red);
+    flat = exp(sl / N) / (arith + 1e-10);
+  }
+  if (!(flat < 0.5)) return;
   if (se < 1e-10) return;
   // autocorrelation of the mean-removed, unit-norm signal (p2tools.py:8-15)
   const double mean = sx / N;
@@ -205,84 +290,111 @@ static __device__ void tns_analysis_block(const double* x, double* work, int N, 
 #pragma unroll
     for (int l = 0; l < FRAD_LPC_LEN; l++) if (n + l < N) acc[l] += s0 * work[n + l];
   }
+  // the 13 lag sums are only needed by the thread that runs the recursion: warp totals to shared memory, thread l adds up
+  // lag l (the additions of block_sum, in its order) and applies the lag window (p2tools.py:14)
+  {
+    const int w = t >> 5, nw = (blockDim.x + 31) >> 5;
 #pragma unroll
-  for (int l = 0; l < FRAD_LPC_LEN; l++) {
-    const double v = block_sum(acc[l], bw->red);
-    if (t == 0) { const double wl = 0.01 * l; bw->r[l] = v * exp(-0.5 * (wl * wl)); }
+    for (int l = 0; l < FRAD_LPC_LEN; l++) acc[l] = warp_sum(acc[l]);
+    __syncthreads();
+    if ((t & 31) == 0) {
+#pragma unroll
+      for (int l = 0; l < FRAD_LPC_LEN; l++) bw->redm[l * 32 + w] = acc[l];
+    }
+    __syncthreads();
+    if (t < FRAD_LPC_LEN) {
+      double v = 0.0;
+      for (int i = 0; i < nw; i++) v += bw->redm[t * 32 + i];
+      const double wl = 0.01 * t;
+      bw->r[t] = v * exp(-0.5 * (wl * wl));
+    }
+    __syncthreads();
   }
-  __syncthreads();
   if (t == 0) {
     // Levinson-Durbin (p2tools.py:17-34)
-    double a[FRAD_LPC_LEN], tmp[FRAD_LPC_LEN], prod[FRAD_LPC_LEN];
+    double r[FRAD_LPC_LEN];
+#pragma unroll
+    for (int l = 0; l < FRAD_LPC_LEN; l++) r[l] = bw->r[l];
+    double a[FRAD_LPC_LEN];
+#pragma unroll
     for (int i = 0; i < FRAD_LPC_LEN; i++) a[i] = 0.0;
     a[0] = 1.0;
-    double err = bw->r[0];
-    if (err > 1e-10) {
-      for (int i = 1; i < FRAD_LPC_LEN; i++) {
-        for (int j = 0; j < i; j++) prod[j] = __dmul_rn(a[j], bw->r[i - j]);
-        double k = -np_sum_small(prod, i) / err;
-        if (fabs(k) >= 0.96) k = (k > 0.0) ? 0.96 : -0.96;
-        for (int j = 0; j < FRAD_LPC_LEN; j++) tmp[j] = a[j];
-        a[i] = k;
-        for (int j = 1; j < i; j++) a[j] = __dadd_rn(a[j], __dmul_rn(k, tmp[i - j]));
-        err = __dmul_rn(err, __dsub_rn(1.0, __dmul_rn(k, k)));
-        if (err <= 1e-12) break;
-      }
-    }
+    double err = r[0];
+    bool go = err > 1e-10;
+    levinson_step<1>(a, r, err, go); levinson_step<2>(a, r, err, go); levinson_step<3>(a, r, err, go);
+    levinson_step<4>(a, r, err, go); levinson_step<5>(a, r, err, go); levinson_step<6>(a, r, err, go);
+    levinson_step<7>(a, r, err, go); levinson_step<8>(a, r, err, go); levinson_step<9>(a, r, err, go);
+    levinson_step<10>(a, r, err, go); levinson_step<11>(a, r, err, go); levinson_step<12>(a, r, err, go);
+    double prod[FRAD_LPC_LEN];
+#pragma unroll
     for (int j = 0; j < FRAD_LPC_LEN - 1; j++) prod[j] = fabs(a[j + 1]);
-    int ok = !(np_sum_small(prod, FRAD_LPC_LEN - 1) < 0.01);
+    prod[FRAD_LPC_LEN - 1] = 0.0;
+    const bool ok = !(np_sum_small_t<FRAD_LPC_LEN - 1>(prod) < 0.01);
     int any = 0;
-    if (ok) {
-      bw->aq[0] = 0;
-      for (int j = 1; j < FRAD_LPC_LEN; j++) {
-        double v = a[j] * 15.0;
-        v = fmin(fmax(v, -15.0), 14.0);
-        const int qv = (int)rint(v);
-        bw->aq[j] = qv; any |= (qv != 0);
-      }
+    int aqv[FRAD_LPC_LEN];
+    aqv[0] = 0;
+#pragma unroll
+    for (int j = 1; j < FRAD_LPC_LEN; j++) {
+      double v = a[j] * 15.0;
+      v = fmin(fmax(v, -15.0), 14.0);
+      aqv[j] = (int)rint(v);
+      any |= (aqv[j] != 0);
     }
     if (ok && any) {
-      bw->a[0] = 1.0;
-      for (int j = 1; j < FRAD_LPC_LEN; j++) bw->a[j] = (double)bw->aq[j] / 15.0;
+#pragma unroll
+      for (int j = 0; j < FRAD_LPC_LEN; j++) { bw->aq[j] = aqv[j]; bw->a[j] = (j == 0) ? 1.0 : (double)aqv[j] / 15.0; }
       bw->flag = 1;
     } else {
+#pragma unroll
       for (int j = 0; j < FRAD_LPC_LEN; j++) bw->aq[j] = 0;
     }
   }
   __syncthreads();
   if (!bw->flag) return;
   // FIR residual, lfilter(lpc_deq, [1], x): b0 x[n] + (b1 x[n-1] + (... + b12 x[n-12]))
-  double mxv = 0.0, sr = 0.0;
-  int bad = 0;
-  for (int n = t; n < N; n += blockDim.x) {
-    double a12 = 0.0;
-    bool first = true;
+  double cf[FRAD_LPC_LEN];
 #pragma unroll
-    for (int i = FRAD_LPC_LEN - 1; i >= 1; i--) {
-      if (n - i >= 0) {
-        const double p = __dmul_rn(bw->a[i], x[n - i]);
-        a12 = first ? p : __dadd_rn(a12, p);
-        first = false;
+  for (int i = 0; i < FRAD_LPC_LEN; i++) cf[i] = bw->a[i];
+  double mxv = 0.0;
+  double s2[2] = {0.0, 0.0};                           // count of non-finite outputs, sum of the residual
+  for (int n = t; n < N; n += blockDim.x) {
+    double y;
+    if (n >= FRAD_LPC_LEN - 1) {                        // all taps present: the same sums without the per-tap tests
+      double a12 = __dmul_rn(cf[FRAD_LPC_LEN - 1], x[n - (FRAD_LPC_LEN - 1)]);
+#pragma unroll
+      for (int i = FRAD_LPC_LEN - 2; i >= 1; i--) a12 = __dadd_rn(a12, __dmul_rn(cf[i], x[n - i]));
+      y = __dadd_rn(a12, __dmul_rn(cf[0], x[n]));
+    } else {
+      double a12 = 0.0;
+      bool first = true;
+#pragma unroll
+      for (int i = FRAD_LPC_LEN - 1; i >= 1; i--) {
+        if (n - i >= 0) {
+          const double p = __dmul_rn(cf[i], x[n - i]);
+          a12 = first ? p : __dadd_rn(a12, p);
+          first = false;
+        }
       }
+      y = first ? __dmul_rn(cf[0], x[n]) : __dadd_rn(a12, __dmul_rn(cf[0], x[n]));
     }
-    const double y = first ? __dmul_rn(bw->a[0], x[n]) : __dadd_rn(a12, __dmul_rn(bw->a[0], x[n]));
     work[n] = y;
-    if (!isfinite(y)) bad = 1;
+    if (!isfinite(y)) s2[0] = 1.0;
     mxv = fmax(mxv, fabs(y));
-    sr += y;
+    s2[1] += y;
   }
   mxv = block_max(mxv, bw->red);
-  const double badsum = block_sum((double)bad, bw->red);
-  sr = block_sum(sr, bw->red);
-  int accept = !(badsum > 0.0 || mxv > 1e6);
+  block_sum_multi<2>(s2, bw->redm);
+  const double sr = s2[1];
+  int accept = !(s2[0] > 0.0 || mxv > 1e6);
   // prediction gain (p2tools.py:57-70)
   const double mo = sx / N, mr = sr / N;
-  double eo = 0.0, er = 0.0;
+  double e2[2] = {0.0, 0.0};
   for (int n = t; n < N; n += blockDim.x) {
     const double d0 = x[n] - mo, d1 = work[n] - mr;
-    eo += d0 * d0; er += d1 * d1;
+    e2[0] += d0 * d0; e2[1] += d1 * d1;
   }
-  eo = block_sum(eo, bw->red); er = block_sum(er, bw->red);
+  block_sum_multi<2>(e2, bw->redm);
+  const double eo = e2[0], er = e2[1];
   double gain = 0.0;
   if (!(eo < 1e-10 || er < 1e-10 || er >= eo)) gain = 20.0 * log10(eo / er);
   if (gain < 0.030102999566398118) accept = 0;       // log10(2) / 10

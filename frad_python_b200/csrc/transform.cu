@@ -360,6 +360,56 @@ __global__ void __launch_bounds__(256) seq_decode_direct_kernel(dec_params P, pl
   }
 }
 
+// Profile-2 encode, second step after the N = 2048 transform kernel: one CTA per (frame, channel) sequence.  Reads the
+// spectrum (float bits left in the q array, [B][N][C]) and the sequence's thresholds ([B][C][28] doubles), forms the masked
+// spectrum X / div in f64 (profile2.py:28-31), runs the TNS analysis on it (p2tools.py:72-95) and quantises the residual --
+// or the masked spectrum where TNS is rejected -- in place (profile2.py:34-46).  Same device routines and thread count as
+// the generic path's epilogue, so the integers are identical to it.
+__global__ void __launch_bounds__(256, 3) tns_encode_kernel(enc_params P, const double* __restrict__ thr_in) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  band_work* bw = (band_work*)smem_raw;
+  double* masked = (double*)(smem_raw + ((sizeof(band_work) + 15) & ~(size_t)15));
+  double* work = masked + P.N;
+  uint8_t* bidx = (uint8_t*)(work + P.N);               // band of every bin (same for all sequences): 255 = past the ramps
+  const int t = threadIdx.x, N = P.N, C = P.C;
+  const int nseq = P.B * C;
+  if (t <= FRAD_NBANDS) { const int e = P.bt->edge[t]; bw->lo[t] = (e < N) ? e : N; }
+  __syncthreads();
+  for (int k = t; k < N; k += blockDim.x) {
+    int b = 0;
+#pragma unroll 1
+    for (int sh = 16; sh > 0; sh >>= 1) { if (b + sh <= FRAD_NBANDS - 2 && bw->lo[b + sh] <= k) b += sh; }
+    bidx[k] = (k >= bw->lo[FRAD_NBANDS - 1]) ? 255 : (uint8_t)b;     // exactly ramp_value's search
+  }
+  for (int s = blockIdx.x; s < nseq; s += gridDim.x) {
+    const int b = s / C, c = s - b * C;
+    __syncthreads();
+    if (t <= FRAD_NBANDS) {
+      const int e = P.bt->edge[t];
+      bw->lo[t] = (e < N) ? e : N;
+      bw->thr[t] = thr_in[(size_t)s * (FRAD_NBANDS + 1) + t];
+    }
+    __syncthreads();
+    ramp_setup(bw, P.bt, N);
+    __syncthreads();
+    int32_t* qrow = P.q + (size_t)b * N * C + c;
+    for (int k = t; k < N; k += blockDim.x) {
+      const double x = (double)__int_as_float(qrow[(size_t)k * C]);
+      const int bnd = bidx[k];
+      const double div = (bnd == 255) ? 0.0 : __dadd_rn(__dmul_rn((double)(k - bw->lo[bnd]), bw->step[bnd]), bw->thr[bnd]);
+      masked[k] = (div == 0.0) ? 0.0 : x / div;
+    }
+    __syncthreads();
+    tns_analysis_block(masked, work, N, bw);
+    const double* src = bw->flag ? work : masked;
+    if (t < FRAD_LPC_LEN) P.lpc[((size_t)b * FRAD_LPC_LEN + t) * C + c] = bw->aq[t];
+    for (int k = t; k < N; k += blockDim.x) {
+      const double y = src[k] * P.scale;
+      qrow[(size_t)k * C] = quant075(y);
+    }
+  }
+}
+
 // Profile-2 decode, first step (profile2.py:80-85): dequantise the coefficients of every (frame, channel) sequence and run
 // the all-pole TNS synthesis lfilter([1], lpc / 15, x) over them (p2tools.py:97-106) -- a recurrence along the bins, so
 // the parallelism is across sequences: one thread per sequence, filter state in registers, SciPy's transposed direct
@@ -394,16 +444,26 @@ __global__ void __launch_bounds__(128) tns_synth_kernel(const int32_t* __restric
     for (int i = 0; i < FRAD_LPC_LEN - 1; i++) z[i] = 0.0;
     double mx = 0.0;
     bool bad = false;
-#pragma unroll 2
-    for (int n = 0; n < N; n++) {
-      const double xn = coef(n);
-      const double yn = __dadd_rn(z[0], xn);
+    // the recurrence is serial along n; the loads are not: a block of coefficients is fetched and dequantised ahead of
+    // the filter steps that consume it, so the two dependent memory accesses per bin are off the critical path
+    constexpr int BLK = 16;
+    for (int n0 = 0; n0 < N; n0 += BLK) {
+      double xv[BLK];
 #pragma unroll
-      for (int i = 0; i < FRAD_LPC_LEN - 2; i++) z[i] = __dsub_rn(__dadd_rn(z[i + 1], __dmul_rn(xn, 0.0)), __dmul_rn(yn, a[i + 1]));
-      z[FRAD_LPC_LEN - 2] = __dsub_rn(__dmul_rn(xn, 0.0), __dmul_rn(yn, a[FRAD_LPC_LEN - 1]));
-      out[(size_t)n * C] = yn;
-      bad |= !isfinite(yn);
-      mx = fmax(mx, fabs(yn));
+      for (int j = 0; j < BLK; j++) xv[j] = (n0 + j < N) ? coef(n0 + j) : 0.0;
+#pragma unroll
+      for (int j = 0; j < BLK; j++) {
+        if (n0 + j < N) {
+          const double xn = xv[j];
+          const double yn = __dadd_rn(z[0], xn);
+#pragma unroll
+          for (int i = 0; i < FRAD_LPC_LEN - 2; i++) z[i] = __dsub_rn(__dadd_rn(z[i + 1], __dmul_rn(xn, 0.0)), __dmul_rn(yn, a[i + 1]));
+          z[FRAD_LPC_LEN - 2] = __dsub_rn(__dmul_rn(xn, 0.0), __dmul_rn(yn, a[FRAD_LPC_LEN - 1]));
+          out[(size_t)(n0 + j) * C] = yn;
+          bad |= !isfinite(yn);
+          mx = fmax(mx, fabs(yn));
+        }
+      }
     }
     ok = !(bad || mx > 1e6);
   }
@@ -506,7 +566,24 @@ static int launch_encode(frad_ctx* ctx, enc_params& P, int prec) {
     return FRAD_OK;
   }
 #ifdef FRAD_HAVE_FAST2048
-  if (!ctx->opt_force_generic && frad_fast2048_encode_ok(P, prec)) return frad_launch_encode_2048(ctx, P, pl, prec, ctx->opt_exact_quant);
+  if (!ctx->opt_force_generic && frad_fast2048_encode_ok(P, prec)) {
+    if (P.profile != 2) return frad_launch_encode_2048(ctx, P, pl, prec, ctx->opt_exact_quant);
+    // profile 2: transform + thresholds, then the TNS kernel (one CTA per sequence, masked spectrum and residual in smem)
+    double* thr = (double*)frad_scratch(ctx, 4, sizeof(double) * (size_t)nseq * (FRAD_NBANDS + 1));
+    if (!thr) return FRAD_E_NOMEM;
+    P.tns_scratch = thr;
+    int rc = frad_launch_encode_2048(ctx, P, pl, prec, ctx->opt_exact_quant);
+    if (rc) return rc;
+    const size_t smem = ((sizeof(band_work) + 15) & ~(size_t)15) + 2 * (size_t)P.N * sizeof(double) + (size_t)P.N;
+    FRAD_CUDA(ctx, cudaFuncSetAttribute(tns_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    FRAD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tns_encode_kernel, 256, smem));
+    if (per_sm < 1) per_sm = 1;
+    int grid = per_sm * ctx->sm_count; if (grid > nseq) grid = nseq;
+    tns_encode_kernel<<<grid, 256, smem, ctx->stream>>>(P, thr);
+    FRAD_LAUNCH_CHECK(ctx);
+    return FRAD_OK;
+  }
 #endif
   launch_cfg cfg;
   const void* k = (prec == FRAD_PREC_F32) ? (const void*)seq_encode_kernel<float> : (const void*)seq_encode_kernel<double>;

@@ -32,6 +32,11 @@ for _ in range(reps):
         ctx.check(L.frad_p1_pack_dev(ctx.handle, d_q.ptr, d_tq.ptr, None, frames, N, CH, d_raw.ptr, stride, d_len.ptr))
         ctx.check(L.frad_compact_dev(ctx.handle, d_raw.ptr, stride, d_len.ptr, frames, d_cmp.ptr, frames * 6144, d_off.ptr))
         ctx.check(L.frad_p1_unpack_dev(ctx.handle, d_cmp.ptr, d_off.ptr, frames, N, CH, 0, d_q.ptr, d_tq.ptr, None, d_st.ptr))
+    elif mode == "p2":
+        if _ == 0:
+            d_lpc = ctx.dev(frames * 13 * CH * 4)
+        ctx.check(L.frad_p1_encode_dev(ctx.handle, d_pcm.ptr, _abi.F32, HOP, frames, N, CH, 16, 48000, 0.5526315789473684, 0, d_q.ptr, d_tq.ptr, d_lpc.ptr))
+        ctx.check(L.frad_p1_decode_dev(ctx.handle, d_q.ptr, d_tq.ptr, d_lpc.ptr, frames, N, CH, 16, 48000, _abi.PREC_F64, d_out.ptr, _abi.F64))
     elif mode == "p1":
         ctx.check(L.frad_p1_encode_dev(ctx.handle, d_pcm.ptr, _abi.F32, HOP, frames, N, CH, 16, 48000, 0.5526315789473684, 0, d_q.ptr, d_tq.ptr, None))
         ctx.check(L.frad_p1_decode_dev(ctx.handle, d_q.ptr, d_tq.ptr, None, frames, N, CH, 16, 48000, _abi.PREC_F64, d_out.ptr, _abi.F64))
