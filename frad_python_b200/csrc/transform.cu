@@ -448,17 +448,32 @@ __global__ void __launch_bounds__(128) tns_synth_kernel(const int32_t* __restric
     // the filter steps that consume it, so the two dependent memory accesses per bin are off the critical path
     constexpr int BLK = 16;
     for (int n0 = 0; n0 < N; n0 += BLK) {
+      int qv[BLK];
       double xv[BLK];
 #pragma unroll
-      for (int j = 0; j < BLK; j++) xv[j] = (n0 + j < N) ? coef(n0 + j) : 0.0;
+      for (int j = 0; j < BLK; j++) qv[j] = (n0 + j < N) ? __ldg(qs + (size_t)(n0 + j) * C) : 0;   // independent loads first
+      uint32_t big = 0;
+#pragma unroll
+      for (int j = 0; j < BLK; j++) {                                  // table look-ups without branches in between
+        const uint32_t qa = (qv[j] < 0) ? 0u - (uint32_t)qv[j] : (uint32_t)qv[j];
+        big |= qa;
+        const double mag = __ldg(dq64 + min(qa, (uint32_t)(dq_len - 1))) * inv_scale;
+        xv[j] = (qv[j] < 0) ? -mag : mag;
+      }
+      if (big >= (uint32_t)dq_len) {                                   // rare: magnitudes beyond the table
+#pragma unroll 1
+        for (int j = 0; j < BLK; j++) if (n0 + j < N) xv[j] = coef(n0 + j);
+      }
 #pragma unroll
       for (int j = 0; j < BLK; j++) {
         if (n0 + j < N) {
           const double xn = xv[j];
           const double yn = __dadd_rn(z[0], xn);
+          // SciPy also adds b[i] x[n] with b[i] = 0 to every state; x[n] is finite here (|q| < 2^31), so those terms are
+          // +-0 and could only flip the sign of a state that is exactly zero -- left out (half of the arithmetic)
 #pragma unroll
-          for (int i = 0; i < FRAD_LPC_LEN - 2; i++) z[i] = __dsub_rn(__dadd_rn(z[i + 1], __dmul_rn(xn, 0.0)), __dmul_rn(yn, a[i + 1]));
-          z[FRAD_LPC_LEN - 2] = __dsub_rn(__dmul_rn(xn, 0.0), __dmul_rn(yn, a[FRAD_LPC_LEN - 1]));
+          for (int i = 0; i < FRAD_LPC_LEN - 2; i++) z[i] = __dsub_rn(z[i + 1], __dmul_rn(yn, a[i + 1]));
+          z[FRAD_LPC_LEN - 2] = -__dmul_rn(yn, a[FRAD_LPC_LEN - 1]);
           out[(size_t)(n0 + j) * C] = yn;
           bad |= !isfinite(yn);
           mx = fmax(mx, fabs(yn));
