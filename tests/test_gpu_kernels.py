@@ -348,3 +348,43 @@ def test_fast2048_decode_large_magnitudes_and_partial_tiles(ctx, c):
     q2 = np.clip(q, -200, 200)
     want2 = np.stack([O.p1_digital_ints(q2[i], tq[i], 16, c, 48000, 2048) for i in range(nb)])
     assert np.max(np.abs(ctx.p1_decode(q2, tq, None, nb, 2048, c, 16, 48000) - want2)) <= 1e-12 * np.max(np.abs(want2))
+
+
+@pytest.mark.parametrize("c", [1, 2, 8])
+def test_p2_fast2048_route_matches_generic_route_and_oracle(ctx, c):
+    """Profile 2 at N = 2048 goes through the warp-per-sequence transform kernels plus the TNS kernels (tns_encode_kernel,
+    tns_synth_kernel); forcing the generic path runs the one-CTA-per-sequence kernels.  Same LPC integers, quantised
+    integers within one step (rare), decoded PCM equal to 1e-11, and both against the oracle's profile2 restatement."""
+    from frad_python_b200 import _abi
+    pcm = O.synth_pcm(0.3, 48000, c, seed=60 + c)
+    nb = (len(pcm) - 2048) // 1920 + 1
+    res = {}
+    for mode in (0, 1):
+        ctx.set_option(_abi.OPT_FORCE_GENERIC, mode)
+        try:
+            q, tq, lpc = ctx.p1_encode(pcm, nb, 2048, 1920, 16, 48000, LOSS0, profile=2)
+            dec = ctx.p1_decode(q, tq, lpc, nb, 2048, c, 16, 48000)
+            dec32 = ctx.p1_decode(q, tq, lpc, nb, 2048, c, 16, 48000, prec=_abi.PREC_F32)
+            res[mode] = (q, tq, lpc, dec, dec32)
+        finally:
+            ctx.set_option(_abi.OPT_FORCE_GENERIC, 0)
+    a, b = res[0], res[1]
+    assert np.any(a[2] != 0)                                            # TNS is active on this signal
+    assert np.array_equal(a[2], b[2])
+    assert np.max(np.abs(a[1] - b[1])) <= 1
+    assert np.max(np.abs(a[0].astype(np.int64) - b[0])) <= 1 and np.mean(a[0] != b[0]) <= 1e-4 + 1.0 / a[0].size
+    # decode of identical integers through both routes
+    ctx.set_option(_abi.OPT_FORCE_GENERIC, 1)
+    try:
+        ref = ctx.p1_decode(a[0], a[1], a[2], nb, 2048, c, 16, 48000)
+    finally:
+        ctx.set_option(_abi.OPT_FORCE_GENERIC, 0)
+    scale = max(1.0, np.max(np.abs(ref)))
+    assert np.max(np.abs(a[3] - ref)) <= 1e-11 * scale
+    assert np.max(np.abs(a[4] - ref)) <= 3e-6 * scale                     # f32 inverse mode
+    for i in (0, nb - 1):
+        oq, otq, olpc, *_ = O.p2_analogue_ints(pcm[i * 1920:i * 1920 + 2048], 16, 48000, LOSS0)
+        assert np.array_equal(a[2][i], np.asarray(olpc).ravel())
+        assert np.max(np.abs(a[0][i].astype(np.int64) - np.asarray(oq).ravel())) <= 1
+        want = O.p2_digital_ints(a[0][i], a[1][i], a[2][i], 16, c, 48000, 2048)
+        assert np.max(np.abs(a[3][i] - want)) <= 1e-11 * scale
