@@ -157,7 +157,7 @@ def run_reference(args, rank, world):
                          "sample": f"{sample_frames} frames of the workload per step ({per_core} per core), " + PORT_NOTE},
         "e2e": {"value": val, "unit": "MSamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(frames):
@@ -169,7 +169,29 @@ def workload_config(frames):
             "cache": "inputs (230 MB PCM / 246 MB ints) larger than the 126 MB L2"}
 
 
+_STDOUT_FD = None
+
+
+def quiet_stdout():
+    """Everything that libraries print to fd 1 (NCCL's version banner, for one) goes to stderr; the JSON line is written
+    to the real stdout by emit()."""
+    global _STDOUT_FD
+    if _STDOUT_FD is None:
+        sys.stdout.flush()
+        _STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _STDOUT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_STDOUT_FD, data)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -454,7 +476,7 @@ def main():
                                 "sample": f"first {nsample} frames of the workload, per frame like the reference: " + PORT_NOTE}
     else:
         line["cpu_baseline"] = None
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 

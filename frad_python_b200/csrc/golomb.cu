@@ -17,6 +17,7 @@
 //         32 lanes decode 32 segments of the bit string speculatively and fix their entry points up afterwards
 //         (see decode_stream_warp).  Per lane: a 64-bit register window over big-endian words, count-leading-
 //         zeros for the unary part, one variable shift per value; four values per 16-byte store.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace {
@@ -375,6 +376,96 @@ __device__ int decode_stream_warp(const uint8_t* __restrict__ d, uint64_t len, i
   return bad;
 }
 
+// The same scheme with all GD_CTA threads of a CTA on one stream (four times as many, four times shorter segments): what
+// the chunked host pipelines use, where a call only carries ~1000 frames and a warp per frame leaves the GPU waiting on
+// 1000 long serial chains.  Neighbour hand-over and the prefix sum go through shared memory.  Returns the malformed flag
+// (uniform over the CTA).  sh: 2 * GD_CTA + 8 ints of shared scratch.
+constexpr int GD_CTA = 128;
+__device__ int decode_stream_cta(const uint8_t* __restrict__ d, uint64_t len, int32_t* __restrict__ out, int cap, int* sh) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  uint32_t* ends = (uint32_t*)sh;
+  int* wsum = sh + GD_CTA;
+  int total = 0, bad = 0;
+  if (len > 1 && cap > 0) {                                    // uniform over the CTA
+    stream_view sv;
+    sv.k = d[0];
+    if (sv.k > 32 || len > (1ull << 28)) bad = 1;
+    else {
+      const uint8_t* p = d + 1;
+      sv.nbits = (uint32_t)((len - 1) * 8);
+      sv.skip = (int)((uintptr_t)p & 3) * 8;
+      sv.w = (const uint32_t*)((uintptr_t)p & ~(uintptr_t)3);
+      const uint32_t span = (uint32_t)sv.skip + sv.nbits;
+      sv.nwords = (span + 31) >> 5;
+      const int lastbits = (int)(span - 32u * (sv.nwords - 1));
+      sv.last_mask = (lastbits >= 32) ? 0xFFFFFFFFu : ~(0xFFFFFFFFu >> lastbits);
+      uint32_t S = (sv.nbits + GD_CTA - 1) / GD_CTA;
+      S = (S + 31) & ~31u;
+      if (S < 64) S = 64;
+      const uint32_t seg_lo = min((uint32_t)tid * S, sv.nbits), seg_hi = min(seg_lo + S, sv.nbits);
+      uint32_t entry = seg_lo;
+      lane_chain ch = run_chain<false>(sv, entry, seg_hi, out, 0, 0);
+      for (int round = 0; round < GD_CTA; round++) {
+        __syncthreads();
+        ends[tid] = ch.end;
+        __syncthreads();
+        uint32_t e = (tid == 0) ? 0u : ends[tid - 1];
+        e = max(e, seg_lo);                                    // a chain never ends before the next segment starts
+        const bool redo = (e != entry);
+        if (!__syncthreads_or(redo)) break;
+        if (redo) { entry = e; ch = run_chain<false>(sv, entry, seg_hi, out, 0, 0); }
+      }
+      // exclusive prefix of the counts: warp scan, then the warp totals
+      int inc = ch.count;
+#pragma unroll
+      for (int s2 = 1; s2 < 32; s2 <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, s2); if (lane >= s2) inc += t; }
+      __syncthreads();
+      if (lane == 31) wsum[wid] = inc;
+      __syncthreads();
+      int before = 0;
+      for (int w = 0; w < GD_CTA / 32; w++) { const int t = wsum[w]; if (w < wid) before += t; total += t; }
+      const int obase = before + inc - ch.count;
+      const lane_chain fin = run_chain<true>(sv, entry, seg_hi, out, obase, cap);
+      bad = __syncthreads_or(fin.bad && obase + fin.count < cap) ? 1 : 0;
+    }
+  }
+  __syncthreads();
+  for (int i = min(total, cap) + tid; i < cap; i += GD_CTA) out[i] = 0;
+  return bad;
+}
+
+// one CTA per frame
+__global__ void __launch_bounds__(GD_CTA) p1_unpack_cta_kernel(const uint8_t* __restrict__ raw, const uint64_t* __restrict__ off,
+                                                               int B, int nq, int ntq, int nlpc, int32_t* __restrict__ q,
+                                                               int32_t* __restrict__ tq, int32_t* __restrict__ lpc,
+                                                               int32_t* __restrict__ status) {
+  __shared__ int sh[2 * GD_CTA + 8];
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    const uint8_t* r = raw + off[b];
+    const uint64_t L = off[b + 1] - off[b];
+    int st = 0;
+    uint64_t pos = 0;
+    uint64_t l_at = 0, l_len = 0, t_at = 0, t_len = 0, q_at = 0, q_len = 0;
+    if (L < (lpc ? 6u : 4u)) st = 1;
+    else {
+      if (lpc) {                                               // profile2.py:66-67
+        const uint64_t ll = ((uint64_t)r[0] << 8) | r[1];
+        l_at = 2; l_len = min64(ll, L - 2);
+        pos = 2 + l_len;
+      }
+      if (L - pos >= 4) {                                      // profile1.py:61-62
+        const uint64_t tl = ((uint64_t)r[pos] << 24) | ((uint64_t)r[pos + 1] << 16) | ((uint64_t)r[pos + 2] << 8) | r[pos + 3];
+        t_at = pos + 4; t_len = min64(tl, L - t_at);
+        q_at = t_at + t_len; q_len = L - q_at;
+      }
+    }
+    if (lpc) st |= decode_stream_cta(r + l_at, l_len, lpc + (size_t)b * nlpc, nlpc, sh) << 1;
+    st |= decode_stream_cta(r + t_at, t_len, tq + (size_t)b * ntq, ntq, sh) << 1;
+    st |= decode_stream_cta(r + q_at, q_len, q + (size_t)b * nq, nq, sh) << 1;
+    if (status && threadIdx.x == 0) status[b] = st;
+  }
+}
+
 // one warp per frame.  status[b]: bit 0 = payload too short for its prefixes (silent frame), bit 1 = malformed code
 constexpr int GD_WARPS = 4;
 __global__ void __launch_bounds__(GD_WARPS * 32) p1_unpack_kernel(const uint8_t* __restrict__ raw, const uint64_t* __restrict__ off,
@@ -457,8 +548,17 @@ extern "C" int frad_p1_unpack_dev(frad_ctx* ctx, const uint8_t* raw, const uint6
     return frad_fail(ctx, FRAD_E_ARG, "frad_p1_unpack_dev: bad argument");
   if (B == 0) return FRAD_OK;
   FRAD_CUDA(ctx, cudaSetDevice(ctx->device));
-  p1_unpack_kernel<<<(B + GD_WARPS - 1) / GD_WARPS, GD_WARPS * 32, 0, ctx->stream>>>(raw, raw_off, B, N * C, FRAD_NBANDS * C,
-                                                                                   FRAD_LPC_LEN * C, q, tq, with_lpc ? lpc : nullptr, status);
+  // few frames (the chunks of the host pipelines): a CTA per frame, so that the serial chains are four times shorter;
+  // many frames: a warp per frame (less synchronisation per value).  FRAD_UNPACK_CTA=0/1 forces one of them.
+  static const char* force = getenv("FRAD_UNPACK_CTA");
+  const bool cta = force ? (force[0] == '1') : (B <= 16 * ctx->sm_count);
+  if (cta) {
+    p1_unpack_cta_kernel<<<B, GD_CTA, 0, ctx->stream>>>(raw, raw_off, B, N * C, FRAD_NBANDS * C, FRAD_LPC_LEN * C, q, tq,
+                                                        with_lpc ? lpc : nullptr, status);
+  } else {
+    p1_unpack_kernel<<<(B + GD_WARPS - 1) / GD_WARPS, GD_WARPS * 32, 0, ctx->stream>>>(raw, raw_off, B, N * C, FRAD_NBANDS * C,
+                                                                                     FRAD_LPC_LEN * C, q, tq, with_lpc ? lpc : nullptr, status);
+  }
   FRAD_LAUNCH_CHECK(ctx);
   return FRAD_OK;
 }

@@ -208,3 +208,17 @@ def test_encode_raw_and_decode_raw_match_the_int_path(ctx):
         rc = lib().frad_p1_encode_raw(ctx.handle, pcm.ctypes.data, dtype_code(pcm.dtype), hop, nb, n, c, bits, sr, LOSS0, 0, profile,
                                       small.ctypes.data, small.size, off2.ctypes.data)
         assert rc == -3 and int(off2[nb]) == int(off[nb])
+
+
+@pytest.mark.gpu
+def test_unpack_warp_per_frame_kernel_forced():
+    """Small batches pick the CTA-per-frame parser; the same tests again with the warp-per-frame one forced
+    (FRAD_UNPACK_CTA=0 is read once per process, hence the subprocess)."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, FRAD_UNPACK_CTA="0")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_golomb.py"), "-m", "gpu", "-q", "-x",
+                        "-k", "unpack and not forced or golden_payloads or decode_raw"], env=env, cwd=root, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

@@ -20,4 +20,11 @@ ncu --set full --clock-control none --import-source on -k regex:"crc_kernel|rs_t
 python tools/prof_driver.py 15000 2 golomb > /dev/null 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:"p1_pack|p1_unpack|compact_kernel" -s 3 -c 3 -o $out/${tag}_full_golomb -f \
     python tools/prof_driver.py 15000 2 golomb > $out/${tag}_ncu_golomb.log 2>&1
+python tools/prof_driver.py 15000 2 p2 > /dev/null 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:"tns_|enc2048|dec2048" -s 4 -c 4 -o $out/${tag}_full_p2 -f \
+    python tools/prof_driver.py 15000 2 p2 > $out/${tag}_ncu_p2.log 2>&1
+# summaries on the box; only the profile-1 report travels back (gpurun_out is capped at 64 MiB)
+python tools/ncu_summary.py $out/${tag}_full_p1.ncu-rep $out/${tag}_full_bytes.ncu-rep $out/${tag}_full_golomb.ncu-rep $out/${tag}_full_p2.ncu-rep \
+    > $out/${tag}_ncu_full_summary.csv 2>> $out/${tag}_bench.err
+rm -f $out/${tag}_full_bytes.ncu-rep $out/${tag}_full_golomb.ncu-rep $out/${tag}_full_p2.ncu-rep
 ls -la $out | tail -20

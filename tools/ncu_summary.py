@@ -37,6 +37,10 @@ for rep in sys.argv[1:]:
         out = [rep.split("/")[-1], d.get("Kernel Name", "")[:110]]
         for k, name in KEYS:
             v = d.get(k, "")
+            if name == "time_us" and v:
+                f = float(v.replace(",", ""))
+                f *= {"ns": 1e-3, "nsecond": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3, "s": 1e6, "second": 1e6}.get(u.get(k, "us"), 1.0)
+                v = f"{f:.1f}"
             if name.endswith("_MB") and v:
                 f = float(v.replace(",", ""))
                 f *= {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}.get(u.get(k, "Mbyte"), 1.0)
