@@ -1,5 +1,6 @@
 // Host-pointer entry points: copy in, run the *_dev path, copy out, synchronise.
 // These are what a ctypes / cgo / JNI binding of the reference's per-frame seams would call.
+#include <cstdlib>
 #include "common.cuh"
 
 void frad_rs_set_max_len(uint32_t v);   // rs.cu
@@ -32,7 +33,7 @@ size_t rounded(size_t b) { return ((b + 255) & ~(size_t)255) + 256; }
 // ctx->s_out, chained by events, so PCIe traffic in both directions overlaps the kernels (pinned host memory
 // makes the copies truly asynchronous; pageable memory still works, just without overlap).
 namespace {
-constexpr int kChunkFrames = 1024;
+static const int kChunkFrames = getenv("FRAD_CHUNK") ? atoi(getenv("FRAD_CHUNK")) : 1024;
 
 struct pipeline {
   frad_ctx* ctx; int nchunks; int chunk;
@@ -73,11 +74,12 @@ int pipeline_run(pipeline& p, int B, bool needs_next_chunk, H2D h2d, RUN run, D2
   // other H2D-heavy): with the whole batch queued up front, or with three chunks of look-ahead, the second context's
   // copies are only served after the first call has finished (9.9 ms for the pair = the sum of the two calls); paced
   // like this the two calls interleave chunk by chunk (8.3 ms).  A call running alone pays about 3 % for the pacing.
+  static const int kDepth = getenv("FRAD_COPY_DEPTH") ? atoi(getenv("FRAD_COPY_DEPTH")) : 1;   // ready copies per stream
   int submitted_in = 0;
   auto queue_in_upto = [&](int last) -> int {
     for (; submitted_in <= last && submitted_in < p.nchunks; submitted_in++) {
       const int i = submitted_in;
-      if (i > 0) FRAD_CUDA(ctx, cudaEventSynchronize(p.in_done[i - 1]));
+      if (i >= kDepth) FRAD_CUDA(ctx, cudaEventSynchronize(p.in_done[i - kDepth]));
       const int f0 = i * p.chunk, f1 = (f0 + p.chunk < B) ? f0 + p.chunk : B;
       int r = h2d(i, f0, f1, ctx->s_in);
       if (r) return r;
@@ -88,7 +90,7 @@ int pipeline_run(pipeline& p, int B, bool needs_next_chunk, H2D h2d, RUN run, D2
   auto queue_out = [&](int i) -> int {                     // chunk i's kernels are done: its results can leave
     const int f0 = i * p.chunk, f1 = (f0 + p.chunk < B) ? f0 + p.chunk : B;
     FRAD_CUDA(ctx, cudaEventSynchronize(p.k_done[i]));
-    if (i > 0) FRAD_CUDA(ctx, cudaEventSynchronize(p.out_done[i - 1]));
+    if (i >= kDepth) FRAD_CUDA(ctx, cudaEventSynchronize(p.out_done[i - kDepth]));
     int r = d2h(f0, f1, ctx->s_out);
     if (r) return r;
     FRAD_CUDA(ctx, cudaEventRecord(p.out_done[i], ctx->s_out));
