@@ -280,15 +280,31 @@ static __device__ void tns_analysis_block(const double* x, double* work, int N, 
   const double nrm = sqrt(ss);
   const double inv_applied = (nrm > 1e-6) ? 1.0 : 0.0;
   __syncthreads();
-  if (inv_applied != 0.0) { for (int n = t; n < N; n += blockDim.x) work[n] = work[n] / nrm; }
+  if (inv_applied != 0.0) {
+    // x / nrm with one division per thread: q0 = x r, q = q0 + (x - q0 nrm) r with r = RN(1 / nrm) is the correctly rounded
+    // quotient (Markstein), except possibly when the significand of nrm is all ones -- that case divides
+    const double rinv = 1.0 / nrm;
+    const bool plain = ((unsigned long long)__double_as_longlong(nrm) & 0xFFFFFFFFFFFFFull) == 0xFFFFFFFFFFFFFull;
+    for (int n = t; n < N; n += blockDim.x) {
+      const double w = work[n];
+      const double q0 = w * rinv;
+      const double q1 = fma(fma(-q0, nrm, w), rinv, q0);
+      work[n] = plain ? w / nrm : q1;
+    }
+  }
   __syncthreads();
   double acc[FRAD_LPC_LEN];
 #pragma unroll
   for (int l = 0; l < FRAD_LPC_LEN; l++) acc[l] = 0.0;
   for (int n = t; n < N; n += blockDim.x) {
     const double s0 = work[n];
+    if (n + FRAD_LPC_LEN <= N) {
 #pragma unroll
-    for (int l = 0; l < FRAD_LPC_LEN; l++) if (n + l < N) acc[l] += s0 * work[n + l];
+      for (int l = 0; l < FRAD_LPC_LEN; l++) acc[l] += s0 * work[n + l];
+    } else {
+#pragma unroll
+      for (int l = 0; l < FRAD_LPC_LEN; l++) if (n + l < N) acc[l] += s0 * work[n + l];
+    }
   }
   // the 13 lag sums are only needed by the thread that runs the recursion: warp totals to shared memory, thread l adds up
   // lag l (the additions of block_sum, in its order) and applies the lag window (p2tools.py:14)

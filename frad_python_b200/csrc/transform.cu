@@ -360,12 +360,16 @@ __global__ void __launch_bounds__(256) seq_decode_direct_kernel(dec_params P, pl
   }
 }
 
-// Profile-2 encode, second step after the N = 2048 transform kernel: one CTA per (frame, channel) sequence.  Reads the
-// spectrum (float bits left in the q array, [B][N][C]) and the sequence's thresholds ([B][C][28] doubles), forms the masked
-// spectrum X / div in f64 (profile2.py:28-31), runs the TNS analysis on it (p2tools.py:72-95) and quantises the residual --
-// or the masked spectrum where TNS is rejected -- in place (profile2.py:34-46).  Same device routines and thread count as
-// the generic path's epilogue, so the integers are identical to it.
-__global__ void __launch_bounds__(256, 3) tns_encode_kernel(enc_params P, const double* __restrict__ thr_in) {
+// Profile-2 encode, second step after the N = 2048 transform kernel: one CTA of FRAD_TNS_THREADS threads per (frame,
+// channel) sequence.  Reads the spectrum (float bits left in the q array, [B][N][C]) and the sequence's thresholds
+// ([B][C][28] doubles), forms the masked spectrum X / div in f64 (profile2.py:28-31), runs the TNS analysis on it
+// (p2tools.py:72-95) and quantises the residual -- or the masked spectrum where TNS is rejected -- in place
+// (profile2.py:34-46).  Same device routines as the generic path's epilogue; the CTA is smaller (the per-thread partial
+// sums group differently, i.e. the last bits of the f64 reductions differ, the LPC integers do not).
+#ifndef FRAD_TNS_THREADS
+#define FRAD_TNS_THREADS 128         // measured: 1.75 ms with 256 threads (3 CTAs/SM), 1.49 ms with 128 (6 CTAs/SM, limited by shared memory)
+#endif
+__global__ void __launch_bounds__(FRAD_TNS_THREADS, 768 / FRAD_TNS_THREADS) tns_encode_kernel(enc_params P, const double* __restrict__ thr_in) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   band_work* bw = (band_work*)smem_raw;
   double* masked = (double*)(smem_raw + ((sizeof(band_work) + 15) & ~(size_t)15));
@@ -592,10 +596,10 @@ static int launch_encode(frad_ctx* ctx, enc_params& P, int prec) {
     const size_t smem = ((sizeof(band_work) + 15) & ~(size_t)15) + 2 * (size_t)P.N * sizeof(double) + (size_t)P.N;
     FRAD_CUDA(ctx, cudaFuncSetAttribute(tns_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
-    FRAD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tns_encode_kernel, 256, smem));
+    FRAD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tns_encode_kernel, FRAD_TNS_THREADS, smem));
     if (per_sm < 1) per_sm = 1;
     int grid = per_sm * ctx->sm_count; if (grid > nseq) grid = nseq;
-    tns_encode_kernel<<<grid, 256, smem, ctx->stream>>>(P, thr);
+    tns_encode_kernel<<<grid, FRAD_TNS_THREADS, smem, ctx->stream>>>(P, thr);
     FRAD_LAUNCH_CHECK(ctx);
     return FRAD_OK;
   }

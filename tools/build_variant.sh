@@ -6,8 +6,10 @@ set -e
 cd "$(dirname "$0")/../frad_python_b200/csrc"
 name=$1; shift
 mkdir -p build/var_$name ../lib/variants
+# VARIANT_SRC: which source gets the flags (default dct2048; e.g. VARIANT_SRC=transform)
+src=${VARIANT_SRC:-dct2048}
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-O2,-Wall -DFRAD_HAVE_FAST2048 "$@" \
-  -c dct2048.cu -o build/var_$name/dct2048.o 2> build/var_$name/ptxas.log || { cat build/var_$name/ptxas.log; exit 1; }
-objs=$(ls build/*.o | grep -v dct2048.o)
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../lib/variants/$name.so $objs build/var_$name/dct2048.o -lcudart
+  -c $src.cu -o build/var_$name/$src.o 2> build/var_$name/ptxas.log || { cat build/var_$name/ptxas.log; exit 1; }
+objs=$(ls build/*.o | grep -v "/$src.o")
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../lib/variants/$name.so $objs build/var_$name/$src.o -lcudart
 echo built ../lib/variants/$name.so
