@@ -414,6 +414,12 @@ __global__ void __launch_bounds__(FRAD_TNS_THREADS, 768 / FRAD_TNS_THREADS) tns_
   }
 }
 
+__device__ __noinline__ double dequant_slow(int qv, const double* __restrict__ dq64, int dq_len, double inv_scale) {
+  const uint32_t qa = (qv < 0) ? 0u - (uint32_t)qv : (uint32_t)qv;
+  const double mag = ((qa < (uint32_t)dq_len) ? __ldg(dq64 + qa) : pow((double)qa, 1.0 / 0.75)) * inv_scale;
+  return (qv < 0) ? -mag : mag;
+}
+
 // Profile-2 decode, first step (profile2.py:80-85): dequantise the coefficients of every (frame, channel) sequence and run
 // the all-pole TNS synthesis lfilter([1], lpc / 15, x) over them (p2tools.py:97-106) -- a recurrence along the bins, so
 // the parallelism is across sequences: one thread per sequence, filter state in registers, SciPy's transposed direct
@@ -448,14 +454,15 @@ __global__ void __launch_bounds__(128) tns_synth_kernel(const int32_t* __restric
     for (int i = 0; i < FRAD_LPC_LEN - 1; i++) z[i] = 0.0;
     double mx = 0.0;
     bool bad = false;
-    // the recurrence is serial along n; the loads are not: a block of coefficients is fetched and dequantised ahead of
-    // the filter steps that consume it, so the two dependent memory accesses per bin are off the critical path
+    // The recurrence is serial along n; the loads are not.  Two blocks ahead of the filter: the integers of block k + 2 are
+    // requested and block k + 1 is dequantised (table look-ups) before the filter steps of block k run, so both dependent
+    // memory accesses per bin are off the critical path.
     constexpr int BLK = 16;
-    for (int n0 = 0; n0 < N; n0 += BLK) {
-      int qv[BLK];
-      double xv[BLK];
+    auto fetch = [&](int n0, int (&qv)[BLK]) {
 #pragma unroll
-      for (int j = 0; j < BLK; j++) qv[j] = (n0 + j < N) ? __ldg(qs + (size_t)(n0 + j) * C) : 0;   // independent loads first
+      for (int j = 0; j < BLK; j++) qv[j] = (n0 + j < N) ? __ldg(qs + (size_t)(n0 + j) * C) : 0;
+    };
+    auto dequant = [&](int n0, const int (&qv)[BLK], double (&xv)[BLK]) {
       uint32_t big = 0;
 #pragma unroll
       for (int j = 0; j < BLK; j++) {                                  // table look-ups without branches in between
@@ -465,13 +472,22 @@ __global__ void __launch_bounds__(128) tns_synth_kernel(const int32_t* __restric
         xv[j] = (qv[j] < 0) ? -mag : mag;
       }
       if (big >= (uint32_t)dq_len) {                                   // rare: magnitudes beyond the table
-#pragma unroll 1
-        for (int j = 0; j < BLK; j++) if (n0 + j < N) xv[j] = coef(n0 + j);
+#pragma unroll
+        for (int j = 0; j < BLK; j++) xv[j] = dequant_slow(qv[j], dq64, dq_len, inv_scale);   // (static indices: xv stays in registers)
       }
+    };
+    int qnext[BLK];
+    double xcur[BLK], xnext[BLK];
+    fetch(0, qnext);
+    dequant(0, qnext, xcur);
+    fetch(BLK, qnext);
+    for (int n0 = 0; n0 < N; n0 += BLK) {
+      dequant(n0 + BLK, qnext, xnext);
+      fetch(n0 + 2 * BLK, qnext);
 #pragma unroll
       for (int j = 0; j < BLK; j++) {
         if (n0 + j < N) {
-          const double xn = xv[j];
+          const double xn = xcur[j];
           const double yn = __dadd_rn(z[0], xn);
           // SciPy also adds b[i] x[n] with b[i] = 0 to every state; x[n] is finite here (|q| < 2^31), so those terms are
           // +-0 and could only flip the sign of a state that is exactly zero -- left out (half of the arithmetic)
@@ -483,6 +499,8 @@ __global__ void __launch_bounds__(128) tns_synth_kernel(const int32_t* __restric
           mx = fmax(mx, fabs(yn));
         }
       }
+#pragma unroll
+      for (int j = 0; j < BLK; j++) xcur[j] = xnext[j];
     }
     ok = !(bad || mx > 1e6);
   }
