@@ -79,6 +79,10 @@ def lib():
             "frad_p0_decode_dev": (i32, [vp, vp, sz, i32, i32, i32, i32, i32, i32, vp, i32]),
             "frad_p0_encode": (i32, [vp, vp, i32, i64, i32, i32, i32, i32, i32, i32, vp, sz, vp, vp]),
             "frad_p0_decode": (i32, [vp, vp, sz, i32, i32, i32, i32, i32, i32, vp, i32]),
+            "frad_p4_encode_dev": (i32, [vp, vp, i32, i64, i32, i32, i32, i32, i32, vp, sz, vp]),
+            "frad_p4_decode_dev": (i32, [vp, vp, sz, i32, i32, i32, i32, i32, vp, i32]),
+            "frad_p4_encode": (i32, [vp, vp, i32, i64, i32, i32, i32, i32, i32, vp, sz, vp, vp]),
+            "frad_p4_decode": (i32, [vp, vp, sz, i32, i32, i32, i32, i32, vp, i32]),
             "frad_p1_encode_dev": (i32, [vp, vp, i32, i64, i32, i32, i32, i32, i32, dbl, i32, vp, vp, vp]),
             "frad_p1_decode_dev": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, i32]),
             "frad_p1_encode": (i32, [vp, vp, i32, i64, i32, i32, i32, i32, i32, dbl, i32, vp, vp, vp]),
@@ -125,6 +129,7 @@ EXPORTS = [
     "frad_sm_count", "frad_kernel_launches", "frad_set_option", "frad_host_alloc", "frad_host_free", "frad_dev_alloc", "frad_dev_free",
     "frad_h2d", "frad_d2h", "frad_memset_dev", "frad_event_record", "frad_event_elapsed_ms",
     "frad_p0_payload_bytes", "frad_p0_encode_dev", "frad_p0_decode_dev", "frad_p0_encode", "frad_p0_decode",
+    "frad_p4_encode_dev", "frad_p4_decode_dev", "frad_p4_encode", "frad_p4_decode",
     "frad_p1_encode_dev", "frad_p1_decode_dev", "frad_p1_encode", "frad_p1_decode",
     "frad_crc32_dev", "frad_crc16_dev", "frad_crc32", "frad_crc16",
     "frad_rs_encoded_len", "frad_rs_decoded_len", "frad_rs_encode_dev", "frad_rs_decode_dev",
@@ -244,25 +249,34 @@ class Context:
 
     # -- profile 0 ---------------------------------------------------------------------------
     def p0_encode(self, pcm: np.ndarray, nframes: int, n: int, hop: int, bits: int, little_endian: bool,
-                  prec: int = PREC_REF, want_crc: bool = True):
-        """pcm: [samples, C] host array.  Returns (payload uint8 [B, nbytes], peak f64 [B], crc32 u32 [B] or None)."""
+                  prec: int = PREC_REF, want_crc: bool = True, profile: int = 0):
+        """pcm: [samples, C] host array.  Returns (payload uint8 [B, nbytes], peak f64 [B], crc32 u32 [B] or None).
+        profile = 4: the PCM archive of fourier/profile4.py (same packing, no transform)."""
         pcm = np.ascontiguousarray(pcm)
         ch = pcm.shape[1]
         nbytes = lib().frad_p0_payload_bytes(n, ch, bits)
         payload = np.empty((nframes, nbytes), np.uint8)
         peak = np.zeros(nframes, np.float64)
         crc = np.zeros(nframes, np.uint32) if want_crc else None
-        self.check(lib().frad_p0_encode(self.handle, pcm.ctypes.data, dtype_code(pcm.dtype), hop, nframes, n, ch, bits,
-                                         int(little_endian), prec, payload.ctypes.data, nbytes, peak.ctypes.data,
-                                         _ptr(crc)))
+        if profile == 4:
+            self.check(lib().frad_p4_encode(self.handle, pcm.ctypes.data, dtype_code(pcm.dtype), hop, nframes, n, ch, bits,
+                                             int(little_endian), payload.ctypes.data, nbytes, peak.ctypes.data, _ptr(crc)))
+        else:
+            self.check(lib().frad_p0_encode(self.handle, pcm.ctypes.data, dtype_code(pcm.dtype), hop, nframes, n, ch, bits,
+                                             int(little_endian), prec, payload.ctypes.data, nbytes, peak.ctypes.data,
+                                             _ptr(crc)))
         return payload, peak, crc
 
     def p0_decode(self, payload: np.ndarray, nframes: int, n: int, ch: int, bits: int, little_endian: bool,
-                  prec: int = PREC_REF, out_dtype=np.float64) -> np.ndarray:
+                  prec: int = PREC_REF, out_dtype=np.float64, profile: int = 0) -> np.ndarray:
         payload = np.ascontiguousarray(payload, dtype=np.uint8).reshape(nframes, -1)
         out = np.empty((nframes, n, ch), out_dtype)
-        self.check(lib().frad_p0_decode(self.handle, payload.ctypes.data, payload.shape[1], nframes, n, ch, bits,
-                                         int(little_endian), prec, out.ctypes.data, dtype_code(out.dtype)))
+        if profile == 4:
+            self.check(lib().frad_p4_decode(self.handle, payload.ctypes.data, payload.shape[1], nframes, n, ch, bits,
+                                             int(little_endian), out.ctypes.data, dtype_code(out.dtype)))
+        else:
+            self.check(lib().frad_p0_decode(self.handle, payload.ctypes.data, payload.shape[1], nframes, n, ch, bits,
+                                             int(little_endian), prec, out.ctypes.data, dtype_code(out.dtype)))
         return out
 
     # -- profiles 1 / 2 ------------------------------------------------------------------------

@@ -122,9 +122,9 @@ inline int copy_async(frad_ctx* ctx, void* dst, const void* src, size_t bytes, c
 #define H2D_ cudaMemcpyHostToDevice
 #define D2H_ cudaMemcpyDeviceToHost
 
-extern "C" int frad_p0_encode(frad_ctx* ctx, const void* pcm, int pcm_dtype, int64_t hop, int B, int N, int C,
-                              int bits, int little_endian, int prec,
-                              uint8_t* payload, size_t payload_stride, double* peak, uint32_t* crc32) {
+static int lossless_encode(frad_ctx* ctx, int profile, const void* pcm, int pcm_dtype, int64_t hop, int B, int N, int C,
+                           int bits, int little_endian, int prec,
+                           uint8_t* payload, size_t payload_stride, double* peak, uint32_t* crc32) {
   if (!ctx) return FRAD_E_ARG;
   const int es = frad_dtype_size(pcm_dtype);
   if (!es || B < 0 || N < 1 || C < 1 || hop < 0) return frad_fail(ctx, FRAD_E_ARG, "frad_p0_encode: bad argument");
@@ -150,8 +150,11 @@ extern "C" int frad_p0_encode(frad_ctx* ctx, const void* pcm, int pcm_dtype, int
       return copy_async(ctx, d_in + lo, (const char*)pcm + lo, hi - lo, H2D_, s);
     },
     [&](int f0, int f1) {
-      int r = frad_p0_encode_dev(ctx, d_in + (size_t)f0 * hop * samp, pcm_dtype, hop, f1 - f0, N, C, bits, little_endian, prec,
-                                 d_out + (size_t)f0 * payload_stride, payload_stride, d_peak + f0);
+      int r = (profile == 4)
+                  ? frad_p4_encode_dev(ctx, d_in + (size_t)f0 * hop * samp, pcm_dtype, hop, f1 - f0, N, C, bits, little_endian,
+                                       d_out + (size_t)f0 * payload_stride, payload_stride, d_peak + f0)
+                  : frad_p0_encode_dev(ctx, d_in + (size_t)f0 * hop * samp, pcm_dtype, hop, f1 - f0, N, C, bits, little_endian, prec,
+                                       d_out + (size_t)f0 * payload_stride, payload_stride, d_peak + f0);
       if (!r && crc32) r = frad_crc32_dev(ctx, d_out + (size_t)f0 * payload_stride, nullptr, nullptr, payload_stride,
                                           (uint32_t)used, f1 - f0, d_crc + f0);
       return r;
@@ -165,8 +168,18 @@ extern "C" int frad_p0_encode(frad_ctx* ctx, const void* pcm, int pcm_dtype, int
     });
 }
 
-extern "C" int frad_p0_decode(frad_ctx* ctx, const uint8_t* payload, size_t payload_stride, int B, int N, int C,
-                              int bits, int little_endian, int prec, void* pcm, int pcm_dtype) {
+extern "C" int frad_p0_encode(frad_ctx* ctx, const void* pcm, int pcm_dtype, int64_t hop, int B, int N, int C,
+                              int bits, int little_endian, int prec,
+                              uint8_t* payload, size_t payload_stride, double* peak, uint32_t* crc32) {
+  return lossless_encode(ctx, 0, pcm, pcm_dtype, hop, B, N, C, bits, little_endian, prec, payload, payload_stride, peak, crc32);
+}
+extern "C" int frad_p4_encode(frad_ctx* ctx, const void* pcm, int pcm_dtype, int64_t hop, int B, int N, int C,
+                              int bits, int little_endian, uint8_t* payload, size_t payload_stride, double* peak, uint32_t* crc32) {
+  return lossless_encode(ctx, 4, pcm, pcm_dtype, hop, B, N, C, bits, little_endian, FRAD_PREC_REF, payload, payload_stride, peak, crc32);
+}
+
+static int lossless_decode(frad_ctx* ctx, int profile, const uint8_t* payload, size_t payload_stride, int B, int N, int C,
+                           int bits, int little_endian, int prec, void* pcm, int pcm_dtype) {
   if (!ctx) return FRAD_E_ARG;
   const int es = frad_dtype_size(pcm_dtype);
   if (!es || B < 0 || N < 1 || C < 1) return frad_fail(ctx, FRAD_E_ARG, "frad_p0_decode: bad argument");
@@ -187,12 +200,23 @@ extern "C" int frad_p0_decode(frad_ctx* ctx, const uint8_t* payload, size_t payl
                         (size_t)(f1 - f0) * payload_stride, H2D_, s);
     },
     [&](int f0, int f1) {
-      return frad_p0_decode_dev(ctx, d_in + (size_t)f0 * payload_stride, payload_stride, f1 - f0, N, C, bits, little_endian,
-                                prec, d_out + (size_t)f0 * fbytes, pcm_dtype);
+      return (profile == 4)
+                 ? frad_p4_decode_dev(ctx, d_in + (size_t)f0 * payload_stride, payload_stride, f1 - f0, N, C, bits, little_endian,
+                                      d_out + (size_t)f0 * fbytes, pcm_dtype)
+                 : frad_p0_decode_dev(ctx, d_in + (size_t)f0 * payload_stride, payload_stride, f1 - f0, N, C, bits, little_endian,
+                                      prec, d_out + (size_t)f0 * fbytes, pcm_dtype);
     },
     [&](int f0, int f1, cudaStream_t s) {
       return copy_async(ctx, (char*)pcm + (size_t)f0 * fbytes, d_out + (size_t)f0 * fbytes, (size_t)(f1 - f0) * fbytes, D2H_, s);
     });
+}
+extern "C" int frad_p0_decode(frad_ctx* ctx, const uint8_t* payload, size_t payload_stride, int B, int N, int C,
+                              int bits, int little_endian, int prec, void* pcm, int pcm_dtype) {
+  return lossless_decode(ctx, 0, payload, payload_stride, B, N, C, bits, little_endian, prec, pcm, pcm_dtype);
+}
+extern "C" int frad_p4_decode(frad_ctx* ctx, const uint8_t* payload, size_t payload_stride, int B, int N, int C,
+                              int bits, int little_endian, void* pcm, int pcm_dtype) {
+  return lossless_decode(ctx, 4, payload, payload_stride, B, N, C, bits, little_endian, FRAD_PREC_REF, pcm, pcm_dtype);
 }
 
 extern "C" int frad_p1_encode(frad_ctx* ctx, const void* pcm, int pcm_dtype, int64_t hop, int B, int N, int C,

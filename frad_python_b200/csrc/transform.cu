@@ -509,6 +509,45 @@ __global__ void __launch_bounds__(128) tns_synth_kernel(const int32_t* __restric
   }
 }
 
+// ---- profile 4 (fourier/profile4.py): the PCM itself, no transform -- the value packing of profile 0 applied to the
+// samples in their interleaved order (profile4.py:28-41), and back (profile4.py:46-63).  One CTA per frame on the way
+// in (per-frame peak for the depth bump of profile4.py:23-25), one thread per value on the way out.
+__global__ void __launch_bounds__(256) p4_encode_kernel(enc_params P) {
+  __shared__ double red[33];
+  const size_t nv = (size_t)P.N * P.C;
+  for (int b = blockIdx.x; b < P.B; b += gridDim.x) {
+    uint8_t* frame = P.payload + (size_t)b * P.payload_stride;
+    const int64_t base = (int64_t)b * P.hop * P.C;
+    double mx = 0.0;
+    for (size_t e = threadIdx.x; e < nv; e += blockDim.x) {
+      const double v = load_pcm<double>(P.pcm, P.pcm_dtype, base + (int64_t)e);
+      mx = fmax(mx, fabs(v));
+      if (P.bits == 12) P.half_scratch[(size_t)b * nv + e] = (uint16_t)(f2h_bits(v) >> 4);
+      else p0_store_value<double>(frame + e * (size_t)(P.bits >> 3), v, P.bits, P.le != 0);
+    }
+    if (P.peak) {
+      mx = block_max(mx, red);
+      if (threadIdx.x == 0) P.peak[b] = mx;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) p4_decode_kernel(dec_params P) {
+  const size_t nv = (size_t)P.N * P.C, total = nv * (size_t)P.B;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / nv, e = i - b * nv;
+    double v;
+    if (P.bits == 12) {
+      v = (double)__half2float(__ushort_as_half(P.half_scratch[i]));
+      if (!isfinite(v)) v = 0.0;
+    } else {
+      v = p0_load_value(P.payload + b * P.payload_stride + e * (size_t)(P.bits >> 3), P.bits, P.le != 0);   // NaN / Inf -> 0
+    }
+    store_pcm<double>(P.pcm, P.pcm_dtype, (int64_t)i, v);
+  }
+}
+
 // 12-bit packing helpers (profile0.py:37-41, 54-58): 16-bit scratch <-> nibble-packed payload
 __global__ void pack12_kernel(const uint16_t* __restrict__ half_top12, size_t nvals, int B, uint8_t* payload, size_t stride) {
   const size_t npairs = (nvals + 1) / 2;
@@ -717,9 +756,9 @@ extern "C" size_t frad_p0_payload_bytes(int N, int C, int bits) {
   return nv * (size_t)(bits / 8);
 }
 
-extern "C" int frad_p0_encode_dev(frad_ctx* ctx, const void* pcm, int pcm_dtype, int64_t hop, int B, int N, int C,
-                                  int bits, int little_endian, int prec,
-                                  uint8_t* payload, size_t payload_stride, double* peak) {
+static int lossless_encode_dev(frad_ctx* ctx, int profile, const void* pcm, int pcm_dtype, int64_t hop, int B, int N, int C,
+                               int bits, int little_endian, int prec,
+                               uint8_t* payload, size_t payload_stride, double* peak) {
   if (!ctx) return FRAD_E_ARG;
   if (B < 0 || N < 1 || C < 1 || !p0_bits_ok(bits) || !frad_dtype_size(pcm_dtype) || !pcm || !payload)
     return frad_fail(ctx, FRAD_E_ARG, "frad_p0_encode_dev: bad argument");
@@ -727,7 +766,7 @@ extern "C" int frad_p0_encode_dev(frad_ctx* ctx, const void* pcm, int pcm_dtype,
   FRAD_CUDA(ctx, cudaSetDevice(ctx->device));
   enc_params P = {};
   P.pcm = pcm; P.pcm_dtype = pcm_dtype; P.hop = hop; P.B = B; P.N = N; P.C = C;
-  P.profile = 0; P.bits = bits; P.le = (little_endian && bits % 8 == 0) ? 1 : 0;
+  P.profile = profile; P.bits = bits; P.le = (little_endian && bits % 8 == 0) ? 1 : 0;
   P.payload = payload; P.payload_stride = payload_stride; P.peak = peak;
   P.fast_ok = 1;
   const size_t nvals = (size_t)N * C;
@@ -736,7 +775,16 @@ extern "C" int frad_p0_encode_dev(frad_ctx* ctx, const void* pcm, int pcm_dtype,
     if (!P.half_scratch) return FRAD_E_NOMEM;
   }
   if (peak) FRAD_CUDA(ctx, cudaMemsetAsync(peak, 0, sizeof(double) * (size_t)B, ctx->stream));
-  int rc = launch_encode(ctx, P, resolve_prec_fwd(prec, pcm_dtype));
+  int rc = FRAD_OK;
+  if (profile == 4) {
+    if (B > 0) {
+      const int grid = B < ctx->sm_count * 8 ? B : ctx->sm_count * 8;
+      p4_encode_kernel<<<grid, 256, 0, ctx->stream>>>(P);
+      FRAD_LAUNCH_CHECK(ctx);
+    }
+  } else {
+    rc = launch_encode(ctx, P, resolve_prec_fwd(prec, pcm_dtype));
+  }
   if (rc) return rc;
   if (bits == 12 && B > 0) {
     size_t total = ((nvals + 1) / 2) * (size_t)B;
@@ -747,15 +795,25 @@ extern "C" int frad_p0_encode_dev(frad_ctx* ctx, const void* pcm, int pcm_dtype,
   return FRAD_OK;
 }
 
-extern "C" int frad_p0_decode_dev(frad_ctx* ctx, const uint8_t* payload, size_t payload_stride, int B, int N, int C,
-                                  int bits, int little_endian, int prec, void* pcm, int pcm_dtype) {
+extern "C" int frad_p0_encode_dev(frad_ctx* ctx, const void* pcm, int pcm_dtype, int64_t hop, int B, int N, int C,
+                                  int bits, int little_endian, int prec,
+                                  uint8_t* payload, size_t payload_stride, double* peak) {
+  return lossless_encode_dev(ctx, 0, pcm, pcm_dtype, hop, B, N, C, bits, little_endian, prec, payload, payload_stride, peak);
+}
+extern "C" int frad_p4_encode_dev(frad_ctx* ctx, const void* pcm, int pcm_dtype, int64_t hop, int B, int N, int C,
+                                  int bits, int little_endian, uint8_t* payload, size_t payload_stride, double* peak) {
+  return lossless_encode_dev(ctx, 4, pcm, pcm_dtype, hop, B, N, C, bits, little_endian, FRAD_PREC_REF, payload, payload_stride, peak);
+}
+
+static int lossless_decode_dev(frad_ctx* ctx, int profile, const uint8_t* payload, size_t payload_stride, int B, int N, int C,
+                               int bits, int little_endian, int prec, void* pcm, int pcm_dtype) {
   if (!ctx) return FRAD_E_ARG;
   if (B < 0 || N < 1 || C < 1 || !p0_bits_ok(bits) || !pcm || !payload || !frad_dtype_size(pcm_dtype))
     return frad_fail(ctx, FRAD_E_ARG, "frad_p0_decode_dev: bad argument");
   if (payload_stride < frad_p0_payload_bytes(N, C, bits)) return frad_fail(ctx, FRAD_E_ARG, "payload_stride too small");
   FRAD_CUDA(ctx, cudaSetDevice(ctx->device));
   dec_params P = {};
-  P.B = B; P.N = N; P.C = C; P.profile = 0; P.bits = bits; P.le = (little_endian && bits % 8 == 0) ? 1 : 0;
+  P.B = B; P.N = N; P.C = C; P.profile = profile; P.bits = bits; P.le = (little_endian && bits % 8 == 0) ? 1 : 0;
   P.payload = payload; P.payload_stride = payload_stride; P.pcm = pcm; P.pcm_dtype = pcm_dtype;
   P.fast_ok = 1;
   const size_t nvals = (size_t)N * C;
@@ -768,7 +826,24 @@ extern "C" int frad_p0_decode_dev(frad_ctx* ctx, const uint8_t* payload, size_t 
     FRAD_LAUNCH_CHECK(ctx);
     P.half_scratch = hs;
   }
+  if (profile == 4) {
+    if (B > 0) {
+      const size_t total = nvals * (size_t)B;
+      int grid = (int)((total + 255) / 256); if (grid > ctx->sm_count * 16) grid = ctx->sm_count * 16;
+      p4_decode_kernel<<<grid, 256, 0, ctx->stream>>>(P);
+      FRAD_LAUNCH_CHECK(ctx);
+    }
+    return FRAD_OK;
+  }
   return launch_decode(ctx, P, resolve_prec_inv(prec));
+}
+extern "C" int frad_p0_decode_dev(frad_ctx* ctx, const uint8_t* payload, size_t payload_stride, int B, int N, int C,
+                                  int bits, int little_endian, int prec, void* pcm, int pcm_dtype) {
+  return lossless_decode_dev(ctx, 0, payload, payload_stride, B, N, C, bits, little_endian, prec, pcm, pcm_dtype);
+}
+extern "C" int frad_p4_decode_dev(frad_ctx* ctx, const uint8_t* payload, size_t payload_stride, int B, int N, int C,
+                                  int bits, int little_endian, void* pcm, int pcm_dtype) {
+  return lossless_decode_dev(ctx, 4, payload, payload_stride, B, N, C, bits, little_endian, FRAD_PREC_REF, pcm, pcm_dtype);
 }
 
 // ------------------------------------------------------------------------------------------------

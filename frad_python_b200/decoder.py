@@ -123,6 +123,8 @@ class Decoder:
                 out = fourier.profile1.digital_batch(chunk, key[1], key[2], key[3], key[4], self.ctx, self.precision)
             elif prof == 2:
                 out = fourier.profile2.digital_batch(chunk, key[1], key[2], key[3], key[4], self.ctx, self.precision)
+            elif prof == 4:
+                out = fourier.profile4.digital_batch(chunk, key[1], key[2], key[3], self.ctx, self.precision)
             else:
                 out = fourier.profile0.digital_batch(chunk, key[1], key[2], key[3], self.ctx, self.precision)
             for j, i in enumerate(idxs):

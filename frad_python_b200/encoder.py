@@ -87,9 +87,10 @@ class Encoder:
 
     def _encode_frames(self, pcm: np.ndarray, nframes: int, n: int, hop: int, fsizes, flush_each=False) -> bytes:
         a = self.asfh
-        if a.profile == 0:
-            pays, depth, crc = fourier.profile0.analogue_batch(pcm, nframes, n, hop, self.bit_depth, a.endian, self.ctx,
-                                                               self.precision, want_crc=not a.ecc)
+        if a.profile in (0, 4):
+            mod0 = fourier.profile0 if a.profile == 0 else fourier.profile4
+            pays, depth, crc = mod0.analogue_batch(pcm, nframes, n, hop, self.bit_depth, a.endian, self.ctx,
+                                                   self.precision, want_crc=not a.ecc)
             return self._emit(pays, depth, pcm.shape[1], self.srate, fsizes, None if a.ecc else crc, flush_each)
         mod = fourier.profile1 if a.profile == 1 else fourier.profile2
         pays, depth, ch, sr = mod.analogue_batch(pcm, nframes, n, hop, self.bit_depth, self.srate, self.loss_level,

@@ -20,7 +20,7 @@ def _device_pcm(pcm: np.ndarray) -> np.ndarray:
 
 
 def analogue_batch(pcm: np.ndarray, nframes: int, n: int, hop: int, bits: int, little_endian: bool, ctx=None,
-                   prec: int = PREC_REF, want_crc: bool = True):
+                   prec: int = PREC_REF, want_crc: bool = True, profile: int = 0):
     """Encode ``nframes`` frames of ``n`` samples starting every ``hop`` samples of ``pcm`` [samples, C].
 
     Returns (list of payload bytes, list of depth indices, crc32 array or None).  Frames whose
@@ -29,7 +29,7 @@ def analogue_batch(pcm: np.ndarray, nframes: int, n: int, hop: int, bits: int, l
     if bits not in DEPTHS:
         bits = 16
     pcm = _device_pcm(pcm)
-    payload, peak, crc = ctx.p0_encode(pcm, nframes, n, hop, bits, little_endian, prec, want_crc)
+    payload, peak, crc = ctx.p0_encode(pcm, nframes, n, hop, bits, little_endian, prec, want_crc, profile)
     out = [payload[i].tobytes() for i in range(nframes)]
     depth = [DEPTHS.index(bits)] * nframes
     for i in np.flatnonzero(peak > _FLOAT_MAX[bits]):
@@ -38,7 +38,7 @@ def analogue_batch(pcm: np.ndarray, nframes: int, n: int, hop: int, bits: int, l
             if b not in _NEXT:
                 raise Exception("Overflow with reaching the max bit depth.")
             b = _NEXT[b]
-        p1, _, c1 = ctx.p0_encode(pcm[i * hop:i * hop + n], 1, n, n, b, little_endian, prec, want_crc)
+        p1, _, c1 = ctx.p0_encode(pcm[i * hop:i * hop + n], 1, n, n, b, little_endian, prec, want_crc, profile)
         out[i], depth[i] = p1[0].tobytes(), DEPTHS.index(b)
         if crc is not None:
             crc[i] = c1[0]
@@ -59,7 +59,7 @@ def values_in(frad_len: int, bits: int) -> int:
 
 
 def digital_batch(payloads, fb: int, channels: int, little_endian: bool, ctx=None, prec: int = PREC_REF,
-                  out_dtype=np.float64) -> np.ndarray:
+                  out_dtype=np.float64, profile: int = 0) -> np.ndarray:
     """Decode equally long payloads -> [B, N, C] (float64 by default, as the reference returns)."""
     ctx = ctx or default_context()
     bits = DEPTHS[fb]
@@ -72,7 +72,7 @@ def digital_batch(payloads, fb: int, channels: int, little_endian: bool, ctx=Non
         buf[i, :used] = np.frombuffer(p, np.uint8)[:used]
     if n == 0:
         return np.zeros((nb, 0, channels), out_dtype)
-    return ctx.p0_decode(buf, nb, n, channels, bits, little_endian, prec, out_dtype)
+    return ctx.p0_decode(buf, nb, n, channels, bits, little_endian, prec, out_dtype, profile)
 
 
 def ctx_bytes(n: int, channels: int, bits: int) -> int:

@@ -18,6 +18,8 @@ def patch_reference(libfrad):
         (ref_fourier.profile1, "digital", fourier.profile1.digital),
         (ref_fourier.profile2, "analogue", fourier.profile2.analogue),
         (ref_fourier.profile2, "digital", fourier.profile2.digital),
+        (ref_fourier.profile4, "analogue", fourier.profile4.analogue),
+        (ref_fourier.profile4, "digital", fourier.profile4.digital),
         (libfrad.tools.ecc, "encode", tools.ecc.encode),
         (libfrad.tools.ecc, "decode", tools.ecc.decode),
         (libfrad.tools.asfh, "crc32", common.crc32),

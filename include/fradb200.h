@@ -3,6 +3,7 @@
  * Drop-in boundary for the numeric seams of H4n-uL/FrAD_Python (paths relative to the
  * reference's src/libfrad/):
  *   fourier/profile0.py:14,46   analogue / digital   -> frad_p0_encode*, frad_p0_decode*
+ *   fourier/profile4.py:14,46   analogue / digital   -> frad_p4_encode*, frad_p4_decode*
  *   fourier/profile1.py:15,54   analogue / digital   -> frad_p1_encode*, frad_p1_decode*  (numeric part;
  *   fourier/profile2.py:15,58   analogue / digital   -> frad_p2_encode*, frad_p2_decode*   Golomb via frad_golomb_*,
  *                                                                                          deflate stays on the host)
@@ -101,6 +102,20 @@ int frad_p0_encode(frad_ctx* ctx, const void* pcm, int pcm_dtype, int64_t hop, i
                    uint8_t* payload, size_t payload_stride, double* peak, uint32_t* crc32 /* may be NULL */);
 int frad_p0_decode(frad_ctx* ctx, const uint8_t* payload, size_t payload_stride, int B, int N, int C,
                    int bits, int little_endian, int prec, void* pcm, int pcm_dtype);
+
+/* ---- profile 4: PCM archive (fourier/profile4.py:14-63; the reference CLI's default profile, src/tools/cli.py:28) ---- */
+/* No transform: the samples themselves go through profile 0's value packing (cast to f16 / f32 / f64, 12 / 24 / 48-bit
+ * truncation) in their interleaved order; peak[b] = max|sample| of frame b for the depth bump of profile4.py:23-25.
+ * Payload size and layout are those of frad_p0_payload_bytes. */
+int frad_p4_encode_dev(frad_ctx* ctx, const void* pcm, int pcm_dtype, int64_t hop, int B, int N, int C,
+                       int bits, int little_endian, uint8_t* payload, size_t payload_stride, double* peak);
+int frad_p4_decode_dev(frad_ctx* ctx, const uint8_t* payload, size_t payload_stride, int B, int N, int C,
+                       int bits, int little_endian, void* pcm, int pcm_dtype);
+int frad_p4_encode(frad_ctx* ctx, const void* pcm, int pcm_dtype, int64_t hop, int B, int N, int C,
+                   int bits, int little_endian, uint8_t* payload, size_t payload_stride, double* peak,
+                   uint32_t* crc32 /* may be NULL */);
+int frad_p4_decode(frad_ctx* ctx, const uint8_t* payload, size_t payload_stride, int B, int N, int C,
+                   int bits, int little_endian, void* pcm, int pcm_dtype);
 
 /* ---- profile 1 / 2: psychoacoustic quantisation (profile1.py, profile2.py, p1tools, p2tools) - */
 /* N must be one of the 32 compact frame sizes; srate one of the 12 compact rates; the caller pads

@@ -152,6 +152,24 @@ def p0_digital(frad: bytes, fb: int, channels: int, little_endian: bool) -> np.n
     return dct3_inverse(vals.reshape(-1, channels).T)
 
 
+def p4_analogue(pcm: np.ndarray, bits: int, srate: int, little_endian: bool):
+    """profile4.py:14-44 -> (payload, depth index, channels, srate): profile 0's packing applied to the PCM itself,
+    samples in their interleaved order (pcm.ravel()); the depth is bumped while max|pcm| exceeds the float format."""
+    if bits not in P0_DEPTHS:
+        bits = 16
+    peak = np.max(np.abs(pcm))
+    while peak > np.finfo(_P0_FLOAT[bits]).max:
+        if bits not in _P0_NEXT:
+            raise OverflowError("Overflow with reaching the max bit depth.")
+        bits = _P0_NEXT[bits]
+    return p0_pack(pcm.ravel(), bits, little_endian), P0_DEPTHS.index(bits), pcm.shape[1], srate
+
+
+def p4_digital(frad: bytes, fb: int, channels: int, little_endian: bool) -> np.ndarray:
+    """profile4.py:46-63 -> float64 [N, C] (NaN / Inf scrubbed to 0)."""
+    return p0_unpack(frad, P0_DEPTHS[fb], little_endian).reshape(-1, channels)
+
+
 # ----------------------------------------------------------------------------------------
 # profile 1 tools (src/libfrad/fourier/tools/p1tools.py)
 # ----------------------------------------------------------------------------------------

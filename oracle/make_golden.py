@@ -303,10 +303,65 @@ def gen_pcmfmt():
     np.savez_compressed(os.path.join(OUT, "pcmfmt.npz"), **d)
 
 
+def gen_p4():
+    """Profile 4 (PCM archive, the CLI default): per-frame seams and whole streams, from the reference's own code."""
+    from libfrad.fourier import profile4
+    d = {}
+    pcm = synth_pcm(0.5, 48000, 2, seed=140)
+    fr = np.stack(frames_of(pcm, 2048, 2048, 3))
+    d["pcm_f32"] = fr
+    for bits in (12, 16, 24, 32, 48, 64):
+        for le in (0, 1):
+            pay = [profile4.analogue(f, bits, 48000, bool(le))[0] for f in fr]
+            d[f"pay_f32_b{bits}_le{le}"] = np.frombuffer(b"".join(pay), np.uint8)
+            d[f"dec_f32_b{bits}_le{le}"] = np.stack([profile4.digital(p, profile4.DEPTHS.index(bits), 2, bool(le)) for p in pay])
+    fr64 = fr.astype(np.float64) * 1.0000001
+    d["pcm_f64"] = fr64
+    for bits in (16, 24, 32, 48, 64):
+        pay = [profile4.analogue(f, bits, 48000, False)[0] for f in fr64]
+        d[f"pay_f64_b{bits}_le0"] = np.frombuffer(b"".join(pay), np.uint8)
+    rng = np.random.default_rng(141)
+    for n, c in ((904, 2), (1, 1), (7, 3), (1000, 8), (513, 5)):
+        x = (rng.standard_normal((n, c)) * 0.3).astype(np.float32)
+        d[f"rag_in_{n}_{c}"] = x
+        pay = profile4.analogue(x, 24, 44100, True)[0]
+        d[f"rag_pay_{n}_{c}"] = np.frombuffer(pay, np.uint8)
+        d[f"rag_dec_{n}_{c}"] = profile4.digital(pay, 2, c, True)
+    x = (rng.standard_normal((5, 1)) * 0.3).astype(np.float32)
+    d["odd12_in"] = x
+    d["odd12_pay"] = np.frombuffer(profile4.analogue(x, 12, 48000, False)[0], np.uint8)
+    d["odd12_dec"] = profile4.digital(d["odd12_pay"].tobytes(), 0, 1, False)
+    big = (rng.standard_normal((256, 2)) * 1e6).astype(np.float32)
+    d["bump_in"] = big
+    pay, idx, _, _ = profile4.analogue(big, 16, 48000, False)
+    d["bump_pay"] = np.frombuffer(pay, np.uint8)
+    d["bump_idx"] = np.array([idx])
+    bad = np.array([1.0, np.nan, np.inf, -np.inf, 0.5, -0.25, 3.0, 4.0], dtype=">f4")
+    d["scrub_pay"] = np.frombuffer(bad.tobytes(), np.uint8)
+    d["scrub_dec"] = profile4.digital(bad.tobytes(), 3, 2, False)
+    # whole streams through the reference Encoder / Decoder / Repairer
+    spcm = synth_pcm(0.4, 48000, 2, seed=400)
+    d["s_pcm"] = spcm
+    d["s_b32"] = np.frombuffer(run_encoder(spcm, 4, 48000, 2, 32, 2048, "f32le"), np.uint8)
+    d["s_b32_dec"] = run_decoder(d["s_b32"].tobytes())
+    d["s_b16_le_ecc"] = np.frombuffer(run_encoder(spcm, 4, 48000, 2, 16, 2048, "f32le", ecc_on=True, le=True), np.uint8)
+    d["s_b16_le_ecc_dec"] = run_decoder(d["s_b16_le_ecc"].tobytes(), fix=True)
+    s16 = (spcm * 32767).astype("<i2")
+    d["s_pcm_s16"] = s16
+    d["s_s16_b24"] = np.frombuffer(run_encoder(s16, 4, 48000, 2, 24, 1000, "s16le"), np.uint8)
+    d["s_s16_b24_dec"] = run_decoder(d["s_s16_b24"].tobytes())
+    d["s_b16_le_ecc_bad"] = np.frombuffer(corrupt(d["s_b16_le_ecc"].tobytes(), 433), np.uint8)
+    d["s_b16_le_ecc_bad_dec"] = run_decoder(d["s_b16_le_ecc_bad"].tobytes(), fix=True)
+    d["s_b16_le_ecc_bad_rep"] = np.frombuffer(run_repairer(d["s_b16_le_ecc_bad"].tobytes(), (96, 24)), np.uint8)
+    np.savez_compressed(os.path.join(OUT, "p4.npz"), **d)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "pcmfmt":
         gen_pcmfmt()
+    elif len(sys.argv) > 1 and sys.argv[1] == "p4":
+        gen_p4()
     else:
-        gen_p0(); gen_p1(); gen_p2(); gen_crc_ecc(); gen_streams(); gen_pcmfmt()
+        gen_p0(); gen_p1(); gen_p2(); gen_crc_ecc(); gen_streams(); gen_pcmfmt(); gen_p4()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -39,5 +39,10 @@ def g_crc():
 
 
 @pytest.fixture(scope="session")
+def g_p4():
+    return load_golden("p4")
+
+
+@pytest.fixture(scope="session")
 def g_streams():
     return load_golden("streams")

@@ -222,3 +222,35 @@ def test_unpack_warp_per_frame_kernel_forced():
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_golomb.py"), "-m", "gpu", "-q", "-x",
                         "-k", "unpack and not forced or golden_payloads or decode_raw"], env=env, cwd=root, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_two_contexts_side_by_side_give_the_serial_results():
+    """Distinct contexts are independent: an encoder and a decoder running at the same time on two host
+    threads -- what bench.py's e2e leg does -- produce exactly the bytes / PCM of the calls made one after the other."""
+    import threading
+    from frad_python_b200 import Context
+    pcm = O.synth_pcm(1.5, 48000, 2, seed=91)
+    nb = (len(pcm) - 2048) // 1920 + 1
+    a, b = Context(0), Context(0)
+    try:
+        raw0, off0 = a.p1_encode_raw(pcm, nb, 2048, 1920, 16, 48000, LOSS0)
+        out0, st0 = a.p1_decode_raw(raw0[:int(off0[-1])], off0, nb, 2048, 2, 16, 48000)
+        res = {}
+
+        def enc():
+            for _ in range(3):
+                res["enc"] = a.p1_encode_raw(pcm, nb, 2048, 1920, 16, 48000, LOSS0)
+
+        def dec():
+            for _ in range(3):
+                res["dec"] = b.p1_decode_raw(raw0[:int(off0[-1])], off0, nb, 2048, 2, 16, 48000)
+
+        ta, tb = threading.Thread(target=enc), threading.Thread(target=dec)
+        ta.start(); tb.start(); ta.join(); tb.join()
+        raw1, off1 = res["enc"]
+        out1, st1 = res["dec"]
+        assert np.array_equal(off0, off1) and np.array_equal(raw0[:int(off0[-1])], raw1[:int(off1[-1])])
+        assert np.array_equal(out0, out1) and not st1.any() and not st0.any()
+    finally:
+        a.close(); b.close()

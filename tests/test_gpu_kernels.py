@@ -388,3 +388,40 @@ def test_p2_fast2048_route_matches_generic_route_and_oracle(ctx, c):
         assert np.max(np.abs(a[0][i].astype(np.int64) - np.asarray(oq).ravel())) <= 1
         want = O.p2_digital_ints(a[0][i], a[1][i], a[2][i], 16, c, 48000, 2048)
         assert np.max(np.abs(a[3][i] - want)) <= 1e-11 * scale
+
+
+def test_p4_golden_bit_exact(ctx, g_p4):
+    """Profile 4 (fourier/profile4.py, the CLI default): no arithmetic beyond the float cast, so payload bytes, the
+    depth bump and the decoded PCM are bit-exact against the reference's vectors -- every depth and byte order, f64
+    input, ragged sizes, the 12-bit nibble pad, NaN / Inf scrub, and the fused output formats."""
+    from frad_python_b200.fourier import profile4 as P4
+    g = g_p4
+    fr = g["pcm_f32"]
+    nb = len(fr)
+    for bits in (12, 16, 24, 32, 48, 64):
+        for le in (0, 1):
+            pay, peak, crc = ctx.p0_encode(fr.reshape(-1, 2), nb, 2048, 2048, bits, bool(le), profile=4)
+            want = g[f"pay_f32_b{bits}_le{le}"].reshape(nb, -1)
+            assert np.array_equal(pay, want), (bits, le)
+            assert [int(c) for c in crc] == [O.crc32(want[i].tobytes()) for i in range(nb)]
+            assert np.array_equal(peak, np.max(np.abs(fr.astype(np.float64)), axis=(1, 2)))
+            dec = ctx.p0_decode(want, nb, 2048, 2, bits, bool(le), profile=4)
+            assert np.array_equal(dec, g[f"dec_f32_b{bits}_le{le}"])
+    for bits in (16, 24, 32, 48, 64):
+        pay, _, _ = ctx.p0_encode(g["pcm_f64"].reshape(-1, 2), nb, 2048, 2048, bits, False, profile=4)
+        assert np.array_equal(pay.reshape(-1), g[f"pay_f64_b{bits}_le0"])
+    for n, c in ((904, 2), (1, 1), (7, 3), (1000, 8), (513, 5)):
+        pay, depth, ch, sr = P4.analogue(g[f"rag_in_{n}_{c}"], 24, 44100, True, ctx)
+        assert pay == g[f"rag_pay_{n}_{c}"].tobytes() and depth == 2 and ch == c and sr == 44100
+        assert np.array_equal(P4.digital(pay, 2, c, True, ctx), g[f"rag_dec_{n}_{c}"])
+    assert P4.analogue(g["odd12_in"], 12, 48000, False, ctx)[0] == g["odd12_pay"].tobytes()
+    assert np.array_equal(P4.digital(g["odd12_pay"].tobytes(), 0, 1, False, ctx), g["odd12_dec"])
+    pay, idx, _, _ = P4.analogue(g["bump_in"], 16, 48000, False, ctx)
+    assert pay == g["bump_pay"].tobytes() and idx == int(g["bump_idx"][0])
+    assert np.array_equal(P4.digital(g["scrub_pay"].tobytes(), 3, 2, False, ctx), g["scrub_dec"])
+    # fused output sample format (src/decoder.py:23) on the profile-4 decode
+    want = g["pay_f32_b32_le0"].reshape(nb, -1)
+    ref = g["dec_f32_b32_le0"]
+    for dt in ("<i2", "<i4", "<f4", "u1"):
+        got = ctx.p0_decode(want, nb, 2048, 2, 32, False, out_dtype=np.dtype(dt), profile=4)
+        assert np.array_equal(got, O.pcm_from_f64(ref, dt)), dt

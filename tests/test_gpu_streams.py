@@ -250,3 +250,28 @@ def test_overlap_kernel_against_numpy(F):
                                          dtype_code(np.float64), d_tl.ptr))
         ctx.d2h(out, d_out.ptr); ctx.d2h(tl, d_tl.ptr); ctx.sync()
         assert np.array_equal(out, want) and np.array_equal(tl, frames[-1][cut:])
+
+
+def test_profile4_streams_byte_exact(F, g_p4):
+    """Profile 4 through the batched Encoder / Decoder / Repairer: the streams are byte-identical to the reference's
+    (headers, payloads, CRC-32, RS parity), the decoded PCM is identical, corrupted frames repair / zero-fill alike."""
+    g = g_p4
+    pcm = g["s_pcm"]
+    for chunk in (32768, 1 << 22, 5000):
+        mine, samples = run_encoder(F, pcm, 4, 48000, 2, 32, 2048, "f32le", chunk=chunk)
+        assert mine == g["s_b32"].tobytes() and samples == len(pcm)
+    assert np.array_equal(run_decoder(F, g["s_b32"].tobytes()), g["s_b32_dec"])
+    mine, _ = run_encoder(F, pcm, 4, 48000, 2, 16, 2048, "f32le", ecc=True, le=True)
+    assert mine == g["s_b16_le_ecc"].tobytes()
+    assert np.array_equal(run_decoder(F, mine, fix=True), g["s_b16_le_ecc_dec"])
+    mine, samples = run_encoder(F, g["s_pcm_s16"], 4, 48000, 2, 24, 1000, "s16le")
+    assert mine == g["s_s16_b24"].tobytes() and samples == len(pcm)
+    assert np.array_equal(run_decoder(F, mine), g["s_s16_b24_dec"])
+    bad = g["s_b16_le_ecc_bad"].tobytes()
+    assert np.array_equal(run_decoder(F, bad, fix=True), g["s_b16_le_ecc_bad_dec"])
+    rp = F.Repairer((96, 24))
+    out = b"".join(rp.process(bad[i:i + 32768]) for i in range(0, len(bad), 32768)) + rp.flush()
+    assert out == g["s_b16_le_ecc_bad_rep"].tobytes()
+    # the decoder can hand out the file's own sample format
+    got = run_decoder(F, g["s_b32"].tobytes(), pcm_format="<i2")
+    assert np.array_equal(got, O.pcm_from_f64(g["s_b32_dec"], "<i2"))

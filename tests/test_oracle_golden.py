@@ -170,3 +170,29 @@ def test_pcm_output_formats_match_the_reference():
         # outside [-1, 1) the cast is undefined behaviour in C; only the signed formats are stable across x86-64 builds
         sel = ((g["x"] >= -1) & (g["x"] < 1)) if np.dtype(dt).kind == "u" else np.ones(g["x"].shape, bool)
         assert got.dtype == g[fmt].dtype and np.array_equal(got[sel], g[fmt][sel]), fmt
+
+
+def test_profile4_oracle_against_reference_vectors(g_p4):
+    """fourier/profile4.py (PCM archive, the CLI default profile): the oracle's restatement reproduces the reference's
+    payload bytes, depth bump and decoded PCM bit for bit."""
+    g = g_p4
+    fr = g["pcm_f32"]
+    for bits in (12, 16, 24, 32, 48, 64):
+        for le in (0, 1):
+            pay = b"".join(O.p4_analogue(f, bits, 48000, bool(le))[0] for f in fr)
+            assert pay == g[f"pay_f32_b{bits}_le{le}"].tobytes(), (bits, le)
+            n = len(pay) // len(fr)
+            dec = np.stack([O.p4_digital(pay[i * n:(i + 1) * n], O.P0_DEPTHS.index(bits), 2, bool(le)) for i in range(len(fr))])
+            assert np.array_equal(dec, g[f"dec_f32_b{bits}_le{le}"])
+    for bits in (16, 24, 32, 48, 64):
+        pay = b"".join(O.p4_analogue(f, bits, 48000, False)[0] for f in g["pcm_f64"])
+        assert pay == g[f"pay_f64_b{bits}_le0"].tobytes()
+    for n, c in ((904, 2), (1, 1), (7, 3), (1000, 8), (513, 5)):
+        pay = O.p4_analogue(g[f"rag_in_{n}_{c}"], 24, 44100, True)[0]
+        assert pay == g[f"rag_pay_{n}_{c}"].tobytes()
+        assert np.array_equal(O.p4_digital(pay, 2, c, True), g[f"rag_dec_{n}_{c}"])
+    assert O.p4_analogue(g["odd12_in"], 12, 48000, False)[0] == g["odd12_pay"].tobytes()
+    assert np.array_equal(O.p4_digital(g["odd12_pay"].tobytes(), 0, 1, False), g["odd12_dec"])
+    pay, idx, _, _ = O.p4_analogue(g["bump_in"], 16, 48000, False)
+    assert pay == g["bump_pay"].tobytes() and idx == int(g["bump_idx"][0])
+    assert np.array_equal(O.p4_digital(g["scrub_pay"].tobytes(), 3, 2, False), g["scrub_dec"])

@@ -60,6 +60,11 @@ def transforms(limit=None):
               ncoef * 12, f"p0 decode be32->f64 (f64 math) [{tag}]")
         timed(lambda: ctx.check(L.frad_p0_decode_dev(ctx.handle, d_pay.ptr, n * ch * 4, frames, n, ch, 32, 0, _abi.PREC_F32, d_out.ptr, _abi.F32)),
               ncoef * 8, f"p0 decode be32->f32 (f32 math) [{tag}]")
+        if n == 2048:      # profile 4 (PCM archive, no transform): the same payload through the packing kernels only
+            timed(lambda: ctx.check(L.frad_p4_encode_dev(ctx.handle, d_pcm.ptr, _abi.F32, hop, frames, n, ch, 32, 0, d_pay.ptr, n * ch * 4, d_peak.ptr)),
+                  ncoef * 8, f"p4 encode f32->be32 [{tag}]")
+            timed(lambda: ctx.check(L.frad_p4_decode_dev(ctx.handle, d_pay.ptr, n * ch * 4, frames, n, ch, 32, 0, d_out.ptr, _abi.F64)),
+                  ncoef * 12, f"p4 decode be32->f64 [{tag}]")
         if n in (2048, 1024, 4096, 1280):
             d_q = ctx.dev(ncoef * 4); d_tq = ctx.dev(frames * 27 * ch * 4)
             timed(lambda: ctx.check(L.frad_p1_encode_dev(ctx.handle, d_pcm.ptr, _abi.F32, hop, frames, n, ch, 16, 48000, 0.5526315789473684, 0, d_q.ptr, d_tq.ptr, None)),
