@@ -512,18 +512,62 @@ __global__ void __launch_bounds__(128) tns_synth_kernel(const int32_t* __restric
 // ---- profile 4 (fourier/profile4.py): the PCM itself, no transform -- the value packing of profile 0 applied to the
 // samples in their interleaved order (profile4.py:28-41), and back (profile4.py:46-63).  One CTA per frame on the way
 // in (per-frame peak for the depth bump of profile4.py:23-25), one thread per value on the way out.
-__global__ void __launch_bounds__(256) p4_encode_kernel(enc_params P) {
+// four values -> their packed images (whole-word depths 16 / 32 / 64), one vector store
+__device__ __forceinline__ void p4_store4(uint8_t* dst, const double* v, int bits, bool le) {
+  if (bits == 32) {
+    uint32_t u[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) { u[j] = f2f_bits(v[j]); if (!le) u[j] = __byte_perm(u[j], 0, 0x0123); }
+    *(uint4*)dst = make_uint4(u[0], u[1], u[2], u[3]);
+  } else if (bits == 16) {
+    uint32_t h[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) { h[j] = f2h_bits(v[j]); if (!le) h[j] = ((h[j] >> 8) | (h[j] << 8)) & 0xFFFFu; }
+    *(uint2*)dst = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
+  } else {
+    uint32_t w[8];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint64_t u = f2d_bits(v[j]);
+      const uint32_t lo = (uint32_t)u, hi = (uint32_t)(u >> 32);
+      w[2 * j] = le ? lo : __byte_perm(hi, 0, 0x0123);
+      w[2 * j + 1] = le ? hi : __byte_perm(lo, 0, 0x0123);
+    }
+    ((uint4*)dst)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    ((uint4*)dst)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+}
+
+__global__ void __launch_bounds__(256) p4_encode_kernel(enc_params P, int vec) {
   __shared__ double red[33];
   const size_t nv = (size_t)P.N * P.C;
   for (int b = blockIdx.x; b < P.B; b += gridDim.x) {
     uint8_t* frame = P.payload + (size_t)b * P.payload_stride;
     const int64_t base = (int64_t)b * P.hop * P.C;
     double mx = 0.0;
-    for (size_t e = threadIdx.x; e < nv; e += blockDim.x) {
-      const double v = load_pcm<double>(P.pcm, P.pcm_dtype, base + (int64_t)e);
-      mx = fmax(mx, fabs(v));
-      if (P.bits == 12) P.half_scratch[(size_t)b * nv + e] = (uint16_t)(f2h_bits(v) >> 4);
-      else p0_store_value<double>(frame + e * (size_t)(P.bits >> 3), v, P.bits, P.le != 0);
+    if (vec) {
+      // float PCM, whole-word depth, everything 16-byte aligned: four samples per thread and step
+      const int ob = 4 * (P.bits >> 3);
+      for (size_t e4 = threadIdx.x; e4 < nv / 4; e4 += blockDim.x) {
+        double v[4];
+        if (P.pcm_dtype == FRAD_F32) {
+          const float4 x = __ldg((const float4*)((const float*)P.pcm + base) + e4);
+          v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+        } else {
+          const double2* src = (const double2*)((const double*)P.pcm + base) + 2 * e4;
+          const double2 x0 = __ldg(src), x1 = __ldg(src + 1);
+          v[0] = x0.x; v[1] = x0.y; v[2] = x1.x; v[3] = x1.y;
+        }
+        mx = fmax(fmax(mx, fmax(fabs(v[0]), fabs(v[1]))), fmax(fabs(v[2]), fabs(v[3])));
+        p4_store4(frame + e4 * ob, v, P.bits, P.le != 0);
+      }
+    } else {
+      for (size_t e = threadIdx.x; e < nv; e += blockDim.x) {
+        const double v = load_pcm<double>(P.pcm, P.pcm_dtype, base + (int64_t)e);
+        mx = fmax(mx, fabs(v));
+        if (P.bits == 12) P.half_scratch[(size_t)b * nv + e] = (uint16_t)(f2h_bits(v) >> 4);
+        else p0_store_value<double>(frame + e * (size_t)(P.bits >> 3), v, P.bits, P.le != 0);
+      }
     }
     if (P.peak) {
       mx = block_max(mx, red);
@@ -533,8 +577,38 @@ __global__ void __launch_bounds__(256) p4_encode_kernel(enc_params P) {
   }
 }
 
-__global__ void __launch_bounds__(256) p4_decode_kernel(dec_params P) {
+__global__ void __launch_bounds__(256) p4_decode_kernel(dec_params P, int vec) {
   const size_t nv = (size_t)P.N * P.C, total = nv * (size_t)P.B;
+  if (vec) {
+    // 32-bit values, payload rows and output 16-byte aligned, nv % 4 == 0: four values per thread and step
+    const size_t q4 = nv / 4, total4 = q4 * (size_t)P.B;
+    const int dt = P.pcm_dtype;
+    for (size_t i4 = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i4 < total4; i4 += (size_t)gridDim.x * blockDim.x) {
+      const size_t b = i4 / q4, e4 = i4 - b * q4;
+      const uint4 x = __ldg((const uint4*)(P.payload + b * P.payload_stride) + e4);
+      const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+      uint64_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const uint32_t u = P.le ? xs[j] : __byte_perm(xs[j], 0, 0x0123);
+        const double v = ((u & 0x7f800000u) == 0x7f800000u) ? 0.0 : (double)__uint_as_float(u);    // NaN / Inf -> 0
+        o[j] = pcm_image(v, dt);
+      }
+      const size_t at = b * nv + 4 * e4;
+      switch (pcm_size(dt)) {
+        case 8: {
+          uint4* dst = (uint4*)((uint64_t*)P.pcm + at);
+          dst[0] = make_uint4((uint32_t)o[0], (uint32_t)(o[0] >> 32), (uint32_t)o[1], (uint32_t)(o[1] >> 32));
+          dst[1] = make_uint4((uint32_t)o[2], (uint32_t)(o[2] >> 32), (uint32_t)o[3], (uint32_t)(o[3] >> 32));
+          break;
+        }
+        case 4: *(uint4*)((uint32_t*)P.pcm + at) = make_uint4((uint32_t)o[0], (uint32_t)o[1], (uint32_t)o[2], (uint32_t)o[3]); break;
+        case 2: *(uint2*)((uint16_t*)P.pcm + at) = make_uint2((uint32_t)o[0] | ((uint32_t)o[1] << 16), (uint32_t)o[2] | ((uint32_t)o[3] << 16)); break;
+        default: *(uint32_t*)((uint8_t*)P.pcm + at) = (uint32_t)o[0] | ((uint32_t)o[1] << 8) | ((uint32_t)o[2] << 16) | ((uint32_t)o[3] << 24); break;
+      }
+    }
+    return;
+  }
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const size_t b = i / nv, e = i - b * nv;
     double v;
@@ -779,7 +853,11 @@ static int lossless_encode_dev(frad_ctx* ctx, int profile, const void* pcm, int 
   if (profile == 4) {
     if (B > 0) {
       const int grid = B < ctx->sm_count * 8 ? B : ctx->sm_count * 8;
-      p4_encode_kernel<<<grid, 256, 0, ctx->stream>>>(P);
+      const int es = frad_dtype_size(pcm_dtype);
+      const int vec = (pcm_dtype == FRAD_F32 || pcm_dtype == FRAD_F64) && (bits == 16 || bits == 32 || bits == 64) && (nvals % 4) == 0 &&
+                      ((uintptr_t)pcm % 16) == 0 && (((size_t)hop * C * es) % 16) == 0 && ((uintptr_t)payload % 16) == 0 &&
+                      (payload_stride % 16) == 0;
+      p4_encode_kernel<<<grid, 256, 0, ctx->stream>>>(P, vec);
       FRAD_LAUNCH_CHECK(ctx);
     }
   } else {
@@ -828,9 +906,12 @@ static int lossless_decode_dev(frad_ctx* ctx, int profile, const uint8_t* payloa
   }
   if (profile == 4) {
     if (B > 0) {
-      const size_t total = nvals * (size_t)B;
+      size_t total = nvals * (size_t)B;
       int grid = (int)((total + 255) / 256); if (grid > ctx->sm_count * 16) grid = ctx->sm_count * 16;
-      p4_decode_kernel<<<grid, 256, 0, ctx->stream>>>(P);
+      const int vec = bits == 32 && (nvals % 4) == 0 && ((uintptr_t)payload % 16) == 0 && (payload_stride % 16) == 0 &&
+                      ((uintptr_t)pcm % 16) == 0;
+      if (vec) { total = (nvals / 4) * (size_t)B; grid = (int)((total + 255) / 256); if (grid > ctx->sm_count * 16) grid = ctx->sm_count * 16; }
+      p4_decode_kernel<<<grid, 256, 0, ctx->stream>>>(P, vec);
       FRAD_LAUNCH_CHECK(ctx);
     }
     return FRAD_OK;
