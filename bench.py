@@ -47,7 +47,7 @@ def peaks():
 
 def make_pcm(seed):
     """Synthetic PCM of SURVEY 8(d): built from a 10 s tile to keep generation fast."""
-    from oracle.frad_oracle import synth_pcm
+    from frad_python_b200.testsignal import synth_pcm
     tile = synth_pcm(10.0, SRATE, CH, seed)
     need = (NFRAMES - 1) * HOP + N
     reps = -(-need // len(tile))
@@ -468,7 +468,6 @@ def main():
                              "tolerance": "decoded PCM within 1 LSB at 16 bit of the f64 reference (measured 1.2e-7)"},
     }
     if not args.no_cpu and world == 1:
-        from oracle.frad_oracle import synth_pcm  # noqa: F401
         nsample = 1000
         frames = [pcm_host[i * HOP:i * HOP + N] for i in range(nsample)]
         dt = cpu_sample(frames)

@@ -193,3 +193,23 @@ def test_two_rank_frame_sharding_gloo(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "SHARD_OK" in outs[0]
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under frad_python_b200/ may import it (bench.py only does so in its
+    CPU legs, __graft_entry__.smoke() as the checker)."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hits = []
+    for dp, _, fns in os.walk(os.path.join(root, "frad_python_b200")):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, fn), encoding="utf-8", errors="ignore").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M):
+                    hits.append(os.path.join(dp, fn))
+    assert not hits, hits
+    bench = open(os.path.join(root, "bench.py")).read()
+    uses = [m.start() for m in re.finditer(r"from oracle", bench)]
+    cpu_legs = [bench.index("def cpu_sample"), bench.index("def _cpu_worker")]
+    assert len(uses) == 2 and all(any(0 < u - c < 600 for c in cpu_legs) for u in uses)

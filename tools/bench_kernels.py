@@ -9,7 +9,7 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from frad_python_b200 import Context, _abi  # noqa: E402
-from oracle.frad_oracle import synth_pcm  # noqa: E402
+from frad_python_b200.testsignal import synth_pcm  # noqa: E402
 
 PEAK = 6548.5
 try:

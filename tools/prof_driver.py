@@ -7,7 +7,7 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from frad_python_b200 import Context, _abi  # noqa: E402
-from oracle.frad_oracle import synth_pcm  # noqa: E402
+from frad_python_b200.testsignal import synth_pcm  # noqa: E402
 
 frames = int(sys.argv[1]) if len(sys.argv) > 1 else 3000
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
