@@ -425,3 +425,25 @@ def test_p4_golden_bit_exact(ctx, g_p4):
     for dt in ("<i2", "<i4", "<f4", "u1"):
         got = ctx.p0_decode(want, nb, 2048, 2, 32, False, out_dtype=np.dtype(dt), profile=4)
         assert np.array_equal(got, O.pcm_from_f64(ref, dt)), dt
+
+
+@pytest.mark.parametrize("c", [1, 2])
+def test_p2_decode_large_magnitudes_and_rejected_synthesis(ctx, c):
+    """tns_synth_kernel beyond the comfortable range: |q| outside the dequantiser table (slow path), a synthesis whose
+    output exceeds 1e6 (rejected: the unfiltered coefficients stand, p2tools.py:103-105), all-zero LPC (no filtering)."""
+    rng = np.random.default_rng(300 + c)
+    nb = 4
+    q = np.rint(rng.laplace(0, 3, (nb, 2048 * c))).astype(np.int64)
+    q.reshape(-1)[rng.integers(0, q.size, 40)] = rng.integers(-6000, 6001, 40)          # beyond the 4096-entry table
+    q[1].reshape(-1)[::2] = 2 ** 27                                                      # frame 1: synthesis blows past 1e6
+    q = q.astype(np.int32)
+    tq = rng.integers(0, 20, (nb, 27 * c)).astype(np.int32)
+    lpc = np.zeros((nb, 13 * c), np.int32)
+    lpc[0, c:5 * c] = rng.integers(-6, 7, 4 * c)
+    lpc[1, c:3 * c] = 14                                                                 # strongly resonant filter
+    lpc[3, c:4 * c] = rng.integers(-3, 4, 3 * c)                                         # frame 2 keeps all zeros
+    want = np.stack([O.p2_digital_ints(q[i], tq[i], lpc[i], 16, c, 48000, 2048) for i in range(nb)])
+    got = ctx.p1_decode(q, tq, lpc, nb, 2048, c, 16, 48000)
+    for i in range(nb):
+        scale = max(1.0, np.max(np.abs(want[i])))
+        assert np.max(np.abs(got[i] - want[i])) <= 1e-11 * scale, i
