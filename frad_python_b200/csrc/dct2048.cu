@@ -60,21 +60,6 @@ template <typename T> __device__ __forceinline__ int swzT(int n) {
 
 template <typename T> __device__ __forceinline__ T shfl_t(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
-// 32 per-lane partial sums (index = band) -> lane b holds the warp total of band b.  31 shuffles.
-__device__ __forceinline__ float transpose_reduce32(float* part, int lane) {
-#pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
-    const bool up = (lane & s) != 0;
-#pragma unroll
-    for (int j = 0; j < s; j++) {
-      const float send = up ? part[j] : part[j + s];
-      const float keep = up ? part[j + s] : part[j];
-      part[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-    }
-  }
-  return part[0];
-}
-
 struct smem_tail {
   int lo[FRAD_NBANDS + 1];
   double thr[FW][FRAD_NBANDS + 1];
@@ -646,7 +631,6 @@ __device__ __noinline__ float dequant_big_f32(int qa, float inv_scale) {
 
 template <typename T> struct dec_layout {
   static constexpr int SEQ_BYTES = SEQ_CPX * 2 * (int)sizeof(T);
-  static constexpr int RAW_OFF = 0;            // the raw 32-bit words are consumed into registers before the exchange
   static constexpr int WARP_BYTES = SEQ_BYTES;
 };
 

@@ -192,26 +192,29 @@ __device__ __forceinline__ double np_sum_small(const double* a, int n) {
 
 template <int NN>
 __device__ __forceinline__ double np_sum_small_t(const double (&a)[FRAD_LPC_LEN]) {     // np_sum_small(a, NN), unrolled
-  if (NN < 8) {
+  if constexpr (NN < 8) {
     double r = 0.0;
 #pragma unroll
     for (int i = 0; i < NN; i++) r = __dadd_rn(r, a[i]);
     return r;
+  } else {
+    double r[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) r[j] = a[j];
+    constexpr int full = NN - (NN % 8);
+    if constexpr (full > 8) {                         // (never with 13 LPC coefficients; kept for other orders)
+#pragma unroll
+      for (int i = 8; i < full; i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) r[j] = __dadd_rn(r[j], a[i + j]);
+      }
+    }
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+#pragma unroll
+    for (int i = full; i < NN; i++) res = __dadd_rn(res, a[i]);
+    return res;
   }
-  double r[8];
-#pragma unroll
-  for (int j = 0; j < 8; j++) r[j] = a[j];
-  constexpr int full = NN - (NN % 8);
-#pragma unroll
-  for (int i = 8; i < full; i += 8) {
-#pragma unroll
-    for (int j = 0; j < 8; j++) r[j] = __dadd_rn(r[j], a[i + j]);
-  }
-  double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                         __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-#pragma unroll
-  for (int i = (full < 8 ? 8 : full); i < NN; i++) res = __dadd_rn(res, a[i]);
-  return res;
 }
 
 // one Levinson-Durbin step (p2tools.py:22-32) with every index a compile-time constant: the arrays stay in registers

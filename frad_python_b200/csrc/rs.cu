@@ -294,7 +294,6 @@ __global__ void __launch_bounds__(128) rs_decode_kernel(const uint8_t* __restric
 // (128 bytes per table entry and plane): a lane reads copy (lane mod replication), so the 8 / 16 / 32 lanes
 // that share one shared-memory wavefront of a 128- / 64- / 32-bit load always hit distinct banks.
 // The kernel is then bound by shared-memory bandwidth alone: csize bytes per data byte at 128 B/clk/SM.
-size_t table_bytes_sliced(int csize);
 constexpr int kRsMaxWarps = 16;
 constexpr int kPlaneWords = 256 * 32;                 // 32 KiB per plane and slicing table
 
@@ -592,7 +591,6 @@ int launch_tiles(frad_ctx* ctx, const uint8_t* buf, const uint64_t* off, const u
 
 bool tile_ok(int csize) { return csize >= 4 && csize <= 32 && (csize & 3) == 0; }
 size_t table_bytes(int csize) { return sizeof(rs_table) + (size_t)256 * ((csize + 3) / 4) * 4; }
-size_t table_bytes_sliced(int csize) { return sizeof(rs_table) + (size_t)4 * 256 * ((csize + 3) / 4) * 4; }
 
 }  // namespace
 
