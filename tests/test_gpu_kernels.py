@@ -447,3 +447,25 @@ def test_p2_decode_large_magnitudes_and_rejected_synthesis(ctx, c):
     for i in range(nb):
         scale = max(1.0, np.max(np.abs(want[i])))
         assert np.max(np.abs(got[i] - want[i])) <= 1e-11 * scale, i
+
+
+def test_fast2048_every_legal_sample_rate(ctx):
+    """Band layout changes with the sample rate (p1tools.py:15-16: 22 non-empty bands at 48 kHz, all 27 and narrow ones at
+    the high rates, fewer at the low ones): the N = 2048 encoder's per-lane band partials, the pair table of the stereo
+    decoder and the ramp tables against the oracle at each of the 12 legal rates, stereo and mono."""
+    from frad_python_b200.fourier.profiles import compact
+    for sr in compact.SRATES:
+        for c in (2, 1):
+            pcm = O.synth_pcm(3 * 2048 / 48000, 48000, c, seed=500 + sr % 97 + c)[: 3 * 2048]
+            q, tq, _ = ctx.p1_encode(pcm, 3, 2048, 2048, 16, sr, LOSS0)
+            for i in range(3):
+                oq, otq, *_ = O.p1_analogue_ints(pcm[i * 2048:(i + 1) * 2048], 16, sr, LOSS0)
+                assert np.max(np.abs(tq[i] - np.asarray(otq).ravel())) <= 1, (sr, c, i)
+                dq = np.abs(q[i].astype(np.int64) - np.asarray(oq).ravel())
+                # a threshold integer off by one is legal (<= 1e-3 of them) but moves a whole band's divisor: compare the
+                # coefficients only where the thresholds agree
+                if np.array_equal(tq[i], np.asarray(otq).ravel()):
+                    assert dq.max() <= 1 and np.mean(dq != 0) <= 2e-4 + 2.0 / dq.size, (sr, c, i)
+            out = ctx.p1_decode(q, tq, None, 3, 2048, c, 16, sr)
+            want = np.stack([O.p1_digital_ints(q[i], tq[i], 16, c, sr, 2048) for i in range(3)])
+            assert np.max(np.abs(out - want)) <= 1e-11 * max(1.0, np.max(np.abs(want))), (sr, c)
