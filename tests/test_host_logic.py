@@ -213,3 +213,30 @@ def test_product_never_touches_the_oracle():
     uses = [m.start() for m in re.finditer(r"from oracle", bench)]
     cpu_legs = [bench.index("def cpu_sample"), bench.index("def _cpu_worker")]
     assert len(uses) == 2 and all(any(0 < u - c < 600 for c in cpu_legs) for u in uses)
+
+
+def test_committed_bench_lines_follow_the_contract():
+    """profiles/r1_bench_line*.json are what bench.py printed on B200: the keys of the bench contract are all there."""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = json.load(open(os.path.join(root, "profiles", "r1_bench_line.json")))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None
+    assert "workload" in d["config"] and "model" not in d["config"]
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(d["e2e"])
+    assert d["e2e"]["h2d_bytes_per_step"] > 2e8 and d["e2e"]["d2h_bytes_per_step"] > 2e8 and d["e2e"]["value"] < d["value"]
+    r = d["roofline"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and r["bound"] == "hbm" and r["unit"] == "GB/s"
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"] is not None and 0 < r["frac"] < 1
+    c = d["cpu_baseline"]
+    assert {"value", "unit", "cores", "kind", "sample"} <= set(c) and c["kind"] in ("port", "reference") and c["cores"] == 1
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"]) and d["gpu_launches"] > 0
+    ref = json.load(open(os.path.join(root, "profiles", "r1_bench_reference_line.json")))
+    assert ref["impl"] == "reference" and ref["metric"] == d["metric"] and ref["unit"] == d["unit"]
+    assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["cpu_baseline"]["value"] == ref["value"]
+    for n in (2, 4, 8):
+        m = json.load(open(os.path.join(root, "profiles", f"r1_bench_line_{n}gpu.json")))
+        assert m["n_gpus"] == n and m["value"] > 0.9 * n * d["value"] * 0.9
