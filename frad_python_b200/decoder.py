@@ -171,44 +171,55 @@ class Decoder:
         self._pending.append(p)
 
     def process(self, stream: bytes) -> DecodeResult:
-        self.buffer += stream
+        """Same state machine as decoder.py:48-104; the input buffer is walked with a cursor instead of being re-sliced
+        after every frame (the reference is fed 32 KiB reads, where that does not matter; with MB-sized pieces the copies
+        would be quadratic)."""
+        buf = self.buffer + stream
+        pos = 0
+        sign, slen = common.FRM_SIGN, len(common.FRM_SIGN)
         ret_pcm, frames = [], 0
         while True:
             if self.asfh.all_set:
                 self.broken_frame = False
-                if len(self.buffer) < self.asfh.frmbytes:
+                if len(buf) - pos < self.asfh.frmbytes:
                     if len(stream) == 0:
                         self.broken_frame = True
                     break
-                frad, self.buffer = self.buffer[:self.asfh.frmbytes], self.buffer[self.asfh.frmbytes:]
+                frad = buf[pos:pos + self.asfh.frmbytes]
+                pos += self.asfh.frmbytes
                 self._queue_frame(frad)
                 frames += 1
                 self.asfh.clear()
             else:
-                if not self.asfh.buffer[:len(common.FRM_SIGN)] == common.FRM_SIGN:
-                    i = self.buffer.find(common.FRM_SIGN)
+                if not self.asfh.buffer[:slen] == sign:
+                    i = buf.find(sign, pos)
                     if i != -1:
-                        self.buffer = self.buffer[i:]
-                        self.asfh.buffer = self.buffer[:len(common.FRM_SIGN)]
-                        self.buffer = self.buffer[len(common.FRM_SIGN):]
+                        self.asfh.buffer = buf[i:i + slen]
+                        pos = i + slen
                     else:
-                        self.buffer = self.buffer[-len(common.FRM_SIGN) + 1:]
+                        pos = max(pos, len(buf) - (slen - 1))       # keep a possible partial signature
                         break
-                header_result, self.buffer = self.asfh.read(self.buffer)
+                window = buf[pos:pos + 48]                           # a header needs at most 36 more bytes
+                header_result, rest = self.asfh.read(window)
+                pos += len(window) - len(rest)
                 if header_result == "Complete":
                     if not self.asfh.criteq(self.info):
                         srate, chnl = self.info.srate, self.info.channels
                         self.info = self.asfh
                         if srate or chnl:
+                            self.buffer = buf[pos:]
                             ret_pcm.extend(self._decode_pending())
                             ret_pcm.append(self.flush().pcm)
                             return DecodeResult(ret_pcm, srate, frames, True)
                 elif header_result == "ForceFlush":
+                    self.buffer = buf[pos:]
                     ret_pcm.extend(self._decode_pending())
                     ret_pcm.append(self.flush().pcm)
+                    buf, pos = self.buffer, 0
                     break
                 else:
                     break
+        self.buffer = buf[pos:]
         ret_pcm.extend(self._decode_pending())
         return DecodeResult(ret_pcm, self.asfh.srate, frames, False)
 

@@ -79,40 +79,47 @@ class Repairer:
         return b"".join(out)
 
     def process(self, stream: bytes) -> bytes:
-        self.buffer += stream
+        """Same state machine as repairer.py:28-74, walking the buffer with a cursor (no re-slicing per frame)."""
+        buf = self.buffer + stream
+        pos = 0
+        sign, slen = common.FRM_SIGN, len(common.FRM_SIGN)
         items = []
         while True:
             if self.asfh.all_set:
                 self.broken_frame = False
-                if len(self.buffer) < self.asfh.frmbytes:
+                if len(buf) - pos < self.asfh.frmbytes:
                     if len(stream) == 0:
                         self.broken_frame = True
                     break
-                frad, self.buffer = self.buffer[:self.asfh.frmbytes], self.buffer[self.asfh.frmbytes:]
+                frad = buf[pos:pos + self.asfh.frmbytes]
+                pos += self.asfh.frmbytes
                 items.append((self._snapshot(), frad))
                 # the reference leaves these set on its header object after each frame (repairer.py:49-50)
                 self.asfh.ecc = True
                 self.asfh.ecc_dsize, self.asfh.ecc_codesize = self.ecc_ratio
                 self.asfh.clear()
             else:
-                if not self.asfh.buffer[:len(common.FRM_SIGN)] == common.FRM_SIGN:
-                    i = self.buffer.find(common.FRM_SIGN)
+                if not self.asfh.buffer[:slen] == sign:
+                    i = buf.find(sign, pos)
                     if i != -1:
-                        items.append(self.buffer[:i])
-                        self.buffer = self.buffer[i:]
-                        self.asfh.buffer = self.buffer[:len(common.FRM_SIGN)]
-                        self.buffer = self.buffer[len(common.FRM_SIGN):]
+                        items.append(buf[pos:i])
+                        self.asfh.buffer = buf[i:i + slen]
+                        pos = i + slen
                     else:
-                        items.append(self.buffer[:-len(common.FRM_SIGN) + 1])
-                        self.buffer = self.buffer[-len(common.FRM_SIGN) + 1:]
+                        keep = max(pos, len(buf) - (slen - 1))      # bytes that may start a signature stay in the buffer
+                        items.append(buf[pos:keep])
+                        pos = keep
                         break
-                header_result, self.buffer = self.asfh.read(self.buffer)
+                window = buf[pos:pos + 48]
+                header_result, rest = self.asfh.read(window)
+                pos += len(window) - len(rest)
                 if header_result == "Complete":
                     continue
                 if header_result == "ForceFlush":
                     items.append(self.asfh.force_flush())
                     break
                 break
+        self.buffer = buf[pos:]
         return self._render(items)
 
     def flush(self) -> bytes:
