@@ -387,6 +387,14 @@ __global__ void __launch_bounds__(FRAD_TNS_THREADS, 768 / FRAD_TNS_THREADS) tns_
   }
   for (int s = blockIdx.x; s < nseq; s += gridDim.x) {
     const int b = s / C, c = s - b * C;
+    {   // the frame of this CTA's next sequence: towards L2 now, read at the top of the next iteration
+      const int s2 = s + gridDim.x;
+      if (s2 < nseq) {
+        const char* nxt = (const char*)(P.q + (size_t)(s2 / C) * N * C);
+        const size_t bytes = (size_t)N * C * 4;
+        for (size_t o = (size_t)t * 128; o < bytes; o += (size_t)blockDim.x * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + o));
+      }
+    }
     __syncthreads();
     if (t <= FRAD_NBANDS) {
       const int e = P.bt->edge[t];
