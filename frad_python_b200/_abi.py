@@ -107,10 +107,6 @@ def lib():
             "frad_p1_decode_raw": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp]),
             "frad_overlap_dev": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp, i32, vp]),
             "frad_p1_decode_stream": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp]),
-            "frad_golomb_encode_host": (i64, [vp, sz, vp, sz]),
-            "frad_golomb_decode_host": (i64, [vp, sz, vp, sz]),
-            "frad_golomb_encode_batch_host": (i32, [vp, i32, sz, vp, sz, vp, i32]),
-            "frad_golomb_decode_batch_host": (i32, [vp, vp, vp, i32, vp, sz, vp, i32]),
         })
         optional = {}
         for name, (res, args) in sig.items():
@@ -134,8 +130,6 @@ EXPORTS = [
     "frad_crc32_dev", "frad_crc16_dev", "frad_crc32", "frad_crc16",
     "frad_rs_encoded_len", "frad_rs_decoded_len", "frad_rs_encode_dev", "frad_rs_decode_dev",
     "frad_rs_encode", "frad_rs_decode",
-    "frad_golomb_encode_host", "frad_golomb_decode_host", "frad_golomb_encode_batch_host",
-    "frad_golomb_decode_batch_host",
     "frad_p1_raw_bound", "frad_p1_pack_dev", "frad_compact_dev", "frad_p1_unpack_dev", "frad_p1_encode_raw",
     "frad_p1_decode_raw", "frad_overlap_dev", "frad_p1_decode_stream",
 ]
@@ -422,60 +416,3 @@ def default_context(device: int = 0) -> Context:
     if ctx is None:
         ctx = _default[device] = Context(device)
     return ctx
-
-
-# ---- host-side Exp-Golomb-Rice coder (native, no device needed) ------------------------------------
-def golomb_encode(vals) -> bytes:
-    """Bit string of fourier/tools/p1tools.py:46-60 for an int array."""
-    v = np.ascontiguousarray(vals, dtype=np.int32).ravel()
-    cap = 8 + v.size * 9
-    out = np.empty(cap, np.uint8)
-    n = lib().frad_golomb_encode_host(v.ctypes.data, v.size, out.ctypes.data, cap)
-    if n < 0:
-        raise FradError("golomb encode buffer too small")
-    return out[:n].tobytes()
-
-
-def golomb_decode(data: bytes, cap: int | None = None) -> np.ndarray:
-    """Inverse of golomb_encode (p1tools.py:62-74); returns int32 values."""
-    buf = np.frombuffer(bytes(data), np.uint8)
-    if cap is None:
-        cap = max(len(buf) * 8, 1)
-    out = np.empty(cap, np.int32)
-    n = lib().frad_golomb_decode_host(buf.ctypes.data, buf.size, out.ctypes.data, cap)
-    return out[:min(n, cap)].copy()
-
-
-def golomb_encode_rows(rows: np.ndarray, threads: int = 0) -> list:
-    """Encode every row of an int32 matrix [B, n]; returns a list of B byte strings."""
-    rows = np.ascontiguousarray(rows, dtype=np.int32)
-    if rows.ndim != 2:
-        raise FradError("rows must be 2-D")
-    nb, n = rows.shape
-    if nb == 0:
-        return []
-    stride = 8 + n * 9
-    out = np.empty((nb, stride), np.uint8)
-    lens = np.empty(nb, np.int64)
-    rc = lib().frad_golomb_encode_batch_host(rows.ctypes.data, nb, n, out.ctypes.data, stride, lens.ctypes.data, threads)
-    if rc != 0 or (lens < 0).any():
-        raise FradError("golomb batch encode failed")
-    return [out[i, :lens[i]].tobytes() for i in range(nb)]
-
-
-def golomb_decode_rows(chunks, cap: int, threads: int = 0) -> np.ndarray:
-    """Decode byte strings into an int32 matrix [B, cap] (short rows zero-padded, profile1.py:12-13)."""
-    nb = len(chunks)
-    out = np.zeros((nb, cap), np.int32)
-    if nb == 0:
-        return out
-    lens = np.fromiter((len(c) for c in chunks), dtype=np.uint32, count=nb)
-    offs = np.zeros(nb, np.uint64)
-    np.cumsum(lens[:-1].astype(np.uint64), out=offs[1:])
-    buf = np.frombuffer(b"".join(chunks) or b"\0", np.uint8)
-    counts = np.empty(nb, np.int64)
-    rc = lib().frad_golomb_decode_batch_host(buf.ctypes.data, offs.ctypes.data, lens.ctypes.data, nb, out.ctypes.data,
-                                             cap, counts.ctypes.data, threads)
-    if rc != 0:
-        raise FradError("golomb batch decode failed")
-    return out

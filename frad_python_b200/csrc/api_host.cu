@@ -3,7 +3,6 @@
 #include <cstdlib>
 #include "common.cuh"
 
-void frad_rs_set_max_len(uint32_t v);   // rs.cu
 static uint32_t host_max_len(const uint32_t* len, uint32_t ulen, int B) {
   if (!len) return ulen;
   uint32_t m = 0;
@@ -326,10 +325,9 @@ static int crc_host(frad_ctx* ctx, const uint8_t* buf, const uint64_t* off, cons
   int rc;
   if ((rc = frad_h2d(ctx, d_buf, buf, total))) return rc;
   if ((rc = stage_index(ctx, a, off, len, B, &d_off, &d_len))) return rc;
-  frad_rs_set_max_len(host_max_len(len, ulen, B));       // lets the kernel cut long messages into balanced segments
-  rc = IS32 ? frad_crc32_dev(ctx, d_buf, d_off, d_len, stride, ulen, B, d_out)
-            : frad_crc16_dev(ctx, d_buf, d_off, d_len, stride, ulen, B, d_out);
-  frad_rs_set_max_len(0);
+  const uint32_t mx = host_max_len(len, ulen, B);        // lets the kernel cut long messages into balanced segments
+  rc = IS32 ? frad_crc32_dev(ctx, d_buf, d_off, d_len, stride, mx, B, d_out)
+            : frad_crc16_dev(ctx, d_buf, d_off, d_len, stride, mx, B, d_out);
   if (rc) return rc;
   if ((rc = frad_d2h(ctx, out, d_out, 4 * (size_t)B))) return rc;
   return frad_sync(ctx);
@@ -363,9 +361,7 @@ extern "C" int frad_rs_encode(frad_ctx* ctx, const uint8_t* buf, const uint64_t*
     if ((rc = frad_h2d(ctx, p, out_off, 8 * (size_t)B))) return rc;
     d_ooff = (const uint64_t*)p;
   }
-  frad_rs_set_max_len(host_max_len(len, ulen, B));
-  rc = frad_rs_encode_dev(ctx, d_buf, d_off, d_len, stride, ulen, B, dsize, csize, d_out, d_ooff, out_stride);
-  frad_rs_set_max_len(0);
+  rc = frad_rs_encode_dev(ctx, d_buf, d_off, d_len, stride, host_max_len(len, ulen, B), B, dsize, csize, d_out, d_ooff, out_stride);
   if (rc) return rc;
   if ((rc = frad_d2h(ctx, out, d_out, out_total_bytes))) return rc;
   return frad_sync(ctx);
@@ -393,9 +389,8 @@ extern "C" int frad_rs_decode(frad_ctx* ctx, const uint8_t* buf, const uint64_t*
     if ((rc = frad_h2d(ctx, p, out_off, 8 * (size_t)B))) return rc;
     d_ooff = (const uint64_t*)p;
   }
-  frad_rs_set_max_len(host_max_len(len, ulen, B));
-  rc = frad_rs_decode_dev(ctx, d_buf, d_off, d_len, stride, ulen, B, dsize, csize, repair, d_out, d_ooff, out_stride, d_status, d_fixed);
-  frad_rs_set_max_len(0);
+  rc = frad_rs_decode_dev(ctx, d_buf, d_off, d_len, stride, host_max_len(len, ulen, B), B, dsize, csize, repair, d_out, d_ooff,
+                          out_stride, d_status, d_fixed);
   if (rc) return rc;
   if ((rc = frad_d2h(ctx, out, d_out, out_total_bytes))) return rc;
   if (status && (rc = frad_d2h(ctx, status, d_status, 4 * (size_t)B))) return rc;

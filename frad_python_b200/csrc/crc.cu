@@ -14,7 +14,6 @@
 // host from the polynomial alone.
 #include "common.cuh"
 
-extern thread_local uint32_t g_rs_max_len;      // upper bound of len[] when the host knows it (api_host.cu)
 
 namespace {
 
@@ -232,7 +231,7 @@ int crc_dev(frad_ctx* ctx, const uint8_t* buf, const uint64_t* off, const uint32
   const crc_tables_all* all = (const crc_tables_all*)ctx->crc_tables;
   const crc_tables* t = IS32 ? &all->t32 : &all->t16;
   // segmentation: aim at >= 8 segments per resident warp, segments of at least 1 KiB (multiples of 32 words)
-  const uint32_t max_len = len ? g_rs_max_len : ulen;          // 0 = unknown: one segment per message
+  const uint32_t max_len = ulen;          // with len[]: its upper bound; 0 = unknown: one segment per message
   const long long warps = (long long)ctx->sm_count * kCrcWarps;
   int S = 1;
   uint32_t seg_words = 0x40000000u;

@@ -9,7 +9,6 @@
 // Chien / Forney (per thread, from the csize-byte remainder: S_j = rem(alpha^j)).
 #include "common.cuh"
 
-extern thread_local uint32_t g_rs_max_len;
 
 namespace {
 
@@ -594,11 +593,6 @@ size_t table_bytes(int csize) { return sizeof(rs_table) + (size_t)256 * ((csize 
 
 }  // namespace
 
-// upper bound of the message lengths behind a device-resident len[] array; set by the host-pointer entry
-// points (which know the lengths) around their *_dev call, 0 = unknown (per-message kernels are used)
-thread_local uint32_t g_rs_max_len = 0;
-void frad_rs_set_max_len(uint32_t v) { g_rs_max_len = v; }
-
 extern "C" size_t frad_rs_encoded_len(size_t len, int dsize, int csize) {
   if (dsize <= 0) return len;
   return len + ((len + dsize - 1) / dsize) * (size_t)csize;
@@ -620,8 +614,8 @@ extern "C" int frad_rs_encode_dev(frad_ctx* ctx, const uint8_t* buf, const uint6
   FRAD_CUDA(ctx, cudaSetDevice(ctx->device));
   const rs_table* t = get_table(ctx, csize);
   if (!t) return FRAD_E_NOMEM;
-  if (tile_ok(csize) && (!len || g_rs_max_len)) {
-    const uint32_t mx = len ? g_rs_max_len : ulen;
+  if (tile_ok(csize) && ulen) {                  // with len[]: ulen is its upper bound (0 = unknown: per-message kernels)
+    const uint32_t mx = ulen;
     return launch_tiles<false>(ctx, buf, off, len, stride, ulen, B, dsize, csize, 1, t, out, out_off, out_stride, nullptr, nullptr, mx);
   }
   const size_t smem = table_bytes(csize);
@@ -643,8 +637,8 @@ extern "C" int frad_rs_decode_dev(frad_ctx* ctx, const uint8_t* buf, const uint6
   FRAD_CUDA(ctx, cudaSetDevice(ctx->device));
   const rs_table* t = get_table(ctx, csize);
   if (!t) return FRAD_E_NOMEM;
-  if (tile_ok(csize) && (!len || g_rs_max_len)) {
-    const uint32_t mx = len ? g_rs_max_len : ulen;
+  if (tile_ok(csize) && ulen) {                  // with len[]: ulen is its upper bound (0 = unknown: per-message kernels)
+    const uint32_t mx = ulen;
     if (status) FRAD_CUDA(ctx, cudaMemsetAsync(status, 0, sizeof(int32_t) * (size_t)B, ctx->stream));
     if (fixed) FRAD_CUDA(ctx, cudaMemsetAsync(fixed, 0, sizeof(int32_t) * (size_t)B, ctx->stream));
     return launch_tiles<true>(ctx, buf, off, len, stride, ulen, B, dsize, csize, repair, t, out, out_off, out_stride, status, fixed, mx);

@@ -153,9 +153,9 @@ class Decoder:
             return None
         prof_mod = fourier.profile1 if p0.profile == 1 else fourier.profile2
         buf, off = fourier.profile1.inflate_all(payloads)
-        out_dtype = np.float64 if self.pcm_format is None else self.pcm_format.newbyteorder("=")
-        if out_dtype != np.float64 and np.dtype(out_dtype).byteorder == ">":
-            return None
+        if self.pcm_format is not None and not self.pcm_format.isnative:
+            return None            # big-endian output keeps the per-frame route (from_f64 leaves big-endian ints unscaled)
+        out_dtype = np.float64 if self.pcm_format is None else self.pcm_format
         pcm, tail, _ = self.ctx.p1_decode_stream(buf, off, len(pend), n, ch, prof_mod.DEPTHS[p0.depth], p0.srate, ratio,
                                                  hanning_in_overlap(n - cut), frag if have else None, self.precision,
                                                  p0.profile, out_dtype)

@@ -36,14 +36,6 @@ def _inflate(frad: bytes):
         return None
 
 
-def pack_streams(q: np.ndarray, tq: np.ndarray) -> list:
-    """[B, N*C] / [B, 27*C] ints -> B deflated payloads (profile1.py:43-50); host bit coder, used by tests."""
-    tg = _abi.golomb_encode_rows(tq)
-    qg = _abi.golomb_encode_rows(q)
-    raws = [struct.pack(">I", len(t)) + t + g for t, g in zip(tg, qg)]
-    return deflate_all(raws)
-
-
 def deflate_all(raws) -> list:
     if len(raws) > 8:
         return list(_pool().map(_deflate, raws))
@@ -74,27 +66,6 @@ def analogue(pcm: np.ndarray, bits: int, srate: int, loss_level: float, ctx=None
         pcm = np.pad(pcm, ((0, n - len(pcm)), (0, 0)))
     out, idx, ch, sr = analogue_batch(pcm, 1, n, n, bits, srate, loss_level, ctx)
     return out[0], idx, ch, sr
-
-
-def unpack_streams(payloads, fsize: int, channels: int):
-    """Payloads -> (q [B, fsize*C], tq [B, 27*C], ok mask); failed inflates give zero rows + ok False."""
-    nb = len(payloads)
-    if nb > 8:
-        raws = list(_pool().map(_inflate, payloads))
-    else:
-        raws = [_inflate(p) for p in payloads]
-    ok = np.array([r is not None and len(r) >= 4 for r in raws], bool)
-    tparts, qparts = [], []
-    for r, good in zip(raws, ok):
-        if not good:
-            tparts.append(b"\x00"); qparts.append(b"\x00")
-            continue
-        tlen = struct.unpack(">I", r[:4])[0]
-        tparts.append(r[4:4 + tlen] or b"\x00")
-        qparts.append(r[4 + tlen:] or b"\x00")
-    q = _abi.golomb_decode_rows(qparts, fsize * channels)
-    tq = _abi.golomb_decode_rows(tparts, _abi.NBANDS * channels)
-    return q, tq, ok
 
 
 def inflate_all(payloads):

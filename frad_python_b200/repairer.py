@@ -116,8 +116,12 @@ class Repairer:
                 if header_result == "Complete":
                     continue
                 if header_result == "ForceFlush":
+                    # The reference re-emits the marker and leaves its 12 bytes in the header buffer (repairer.py:64-67), so
+                    # it parses them again on every later call and never reaches end of stream.  Here the marker is
+                    # consumed: emitted once, header state cleared, and the walk goes on with whatever follows it.
                     items.append(self.asfh.force_flush())
-                    break
+                    self.asfh.clear()
+                    continue
                 break
         self.buffer = buf[pos:]
         return self._render(items)

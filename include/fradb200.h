@@ -5,7 +5,7 @@
  *   fourier/profile0.py:14,46   analogue / digital   -> frad_p0_encode*, frad_p0_decode*
  *   fourier/profile4.py:14,46   analogue / digital   -> frad_p4_encode*, frad_p4_decode*
  *   fourier/profile1.py:15,54   analogue / digital   -> frad_p1_encode*, frad_p1_decode*  (numeric part;
- *   fourier/profile2.py:15,58   analogue / digital   -> frad_p2_encode*, frad_p2_decode*   Golomb via frad_golomb_*,
+ *   fourier/profile2.py:15,58   analogue / digital   -> frad_p2_encode*, frad_p2_decode*   bit strings via frad_p1_pack/unpack_dev,
  *                                                                                          deflate stays on the host)
  *   tools/ecc.py:6,14           encode / decode      -> frad_rs_encode*, frad_rs_decode*
  *   tools/asfh.py:4,69 (zlib.crc32), common.py:6 (crc16_ansi) -> frad_crc32*, frad_crc16*
@@ -169,7 +169,9 @@ int frad_p1_decode_stream(frad_ctx* ctx, const uint8_t* raw, const uint64_t* raw
                           const double* prev_tail, void* pcm, int pcm_dtype, double* tail_out, int32_t* status);
 
 /* ---- CRC (zlib.crc32 / crc16_ansi) ---------------------------------------------------------- */
-/* Message i is buf[off[i] .. off[i]+len[i]); off == NULL means i*stride, len == NULL means ulen. */
+/* Message i is buf[off[i] .. off[i]+len[i]); off == NULL means i*stride, len == NULL means every message has ulen bytes.
+ * With len != NULL, ulen is an upper bound of len[] (the *_dev entry points cannot read device memory on the host):
+ * 0 = unknown, which is correct but selects the one-message-per-warp / one-codeword-per-thread kernels. */
 int frad_crc32_dev(frad_ctx* ctx, const uint8_t* buf, const uint64_t* off, const uint32_t* len,
                    size_t stride, uint32_t ulen, int B, uint32_t* out);
 int frad_crc16_dev(frad_ctx* ctx, const uint8_t* buf, const uint64_t* off, const uint32_t* len,
@@ -202,17 +204,6 @@ int frad_rs_decode(frad_ctx* ctx, const uint8_t* buf, const uint64_t* off, const
                    size_t stride, uint32_t ulen, int B, size_t total_bytes, int dsize, int csize, int repair,
                    uint8_t* out, const uint64_t* out_off, size_t out_stride, size_t out_total_bytes,
                    int32_t* status, int32_t* fixed);
-
-/* ---- host-side Exp-Golomb-Rice bit coder (fourier/tools/p1tools.py:46-74) --------------------------- */
-/* Pure host code (no device work): the bit strings that profile 1/2 deflate.  encode returns the number
- * of bytes written, or -(bytes needed) when cap is too small; decode returns the number of values found
- * (values beyond cap are counted but not stored). */
-int64_t frad_golomb_encode_host(const int32_t* vals, size_t n, uint8_t* out, size_t cap);
-int64_t frad_golomb_decode_host(const uint8_t* data, size_t len, int32_t* out, size_t cap);
-int frad_golomb_encode_batch_host(const int32_t* vals, int B, size_t n_per, uint8_t* out, size_t out_stride,
-                                  int64_t* out_len, int threads);
-int frad_golomb_decode_batch_host(const uint8_t* data, const uint64_t* off, const uint32_t* len, int B,
-                                  int32_t* out, size_t cap, int64_t* count, int threads);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,235 @@
+"""Level-1 drop-in (frad_python_b200/install.py): the reference's module-level seams rebound to the GPU functions.
+
+CPU part (build container only, where /root/reference exists): every seam install.patch_reference touches exists in the
+real reference with the same call signature, and unpatch restores the originals.  GPU part: a stub module tree shaped
+like libfrad drives an Encoder -> Decoder round of one frame through the patched seams exactly the way
+libfrad/encoder.py:96-104 and decoder.py:63-74 call them (attribute lookup at call time).
+CPU part also covers the Repairer's host logic on streams that end in ForceFlush headers (oracle-backed stub context)."""
+import inspect
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+
+from oracle import frad_oracle as O
+from stubctx import OracleCtx
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_SRC = "/root/reference/src"
+LOSS0 = 1.25 ** 0 / 19 + 0.5
+
+SEAMS = [("fourier.profile0", "analogue"), ("fourier.profile0", "digital"), ("fourier.profile1", "analogue"),
+         ("fourier.profile1", "digital"), ("fourier.profile2", "analogue"), ("fourier.profile2", "digital"),
+         ("fourier.profile4", "analogue"), ("fourier.profile4", "digital"), ("tools.ecc", "encode"), ("tools.ecc", "decode"),
+         ("tools.asfh", "crc32"), ("tools.asfh", "crc16_ansi"), ("common", "crc16_ansi")]
+
+
+def _resolve(pkg, dotted):
+    m = pkg
+    for part in dotted.split("."):
+        m = getattr(m, part)
+    return m
+
+
+@pytest.fixture
+def reference_libfrad():
+    if not os.path.isdir(REF_SRC):
+        pytest.skip("the reference tree only exists in the build container")
+    added = [os.path.join(ROOT, "oracle", "shim"), REF_SRC]
+    for p in added:
+        sys.path.insert(0, p)
+    try:
+        import libfrad
+        yield libfrad
+    finally:
+        for p in added:
+            sys.path.remove(p)
+        for name in [n for n in sys.modules if n == "libfrad" or n.startswith("libfrad.") or n == "reedsolo"]:
+            del sys.modules[name]
+
+
+def _positional(fn):
+    return [p.name for p in inspect.signature(fn).parameters.values()
+            if p.kind in (p.POSITIONAL_ONLY, p.POSITIONAL_OR_KEYWORD) and p.default is p.empty]
+
+
+def test_patch_reference_binds_every_seam_of_the_real_reference(reference_libfrad):
+    """install.py:12-34 against /root/reference/src/libfrad: attributes exist, required positional parameters have the
+    reference's names and order (ours may add optional ones such as ctx=None), unpatch restores the originals."""
+    from frad_python_b200 import install
+    lf = reference_libfrad
+    before = {(m, a): getattr(_resolve(lf, m), a) for m, a in SEAMS}           # KeyError/AttributeError = seam missing
+    avail_before = list(lf.fourier.AVAILABLE)
+    install.patch_reference(lf)
+    try:
+        for (m, a), orig in before.items():
+            new = getattr(_resolve(lf, m), a)
+            assert new is not orig, (m, a)
+            assert new.__module__.startswith("frad_python_b200"), (m, a, new.__module__)
+            if inspect.isbuiltin(orig):                                           # zlib.crc32: (data[, value])
+                assert _positional(new) == ["data"], (m, a)
+            else:
+                assert _positional(new) == _positional(orig), (m, a, _positional(new), _positional(orig))
+        assert 2 in lf.fourier.AVAILABLE
+        # the names the codec objects resolve at call time are the patched ones (encoder.py:96-104, decoder.py:63-74)
+        from libfrad import encoder as ref_enc, decoder as ref_dec, repairer as ref_rep
+        import frad_python_b200 as F
+        assert ref_enc.fourier.profile1.analogue is F.fourier.profile1.analogue
+        assert ref_dec.fourier.profile0.digital is F.fourier.profile0.digital
+        assert ref_enc.ecc.encode is F.tools.ecc.encode and ref_rep.ecc.decode is F.tools.ecc.decode
+        assert ref_dec.common.crc16_ansi is F.common.crc16_ansi
+        assert ref_enc.AVAILABLE is lf.fourier.AVAILABLE                       # same list object
+    finally:
+        install.unpatch_reference()
+    for (m, a), orig in before.items():
+        assert getattr(_resolve(lf, m), a) is orig, (m, a)
+    assert avail_before == [x for x in lf.fourier.AVAILABLE if x in avail_before]
+    install.unpatch_reference()                                                   # idempotent
+
+
+def test_patched_reference_without_a_gpu_fails_loudly(reference_libfrad):
+    """No CPU fallback behind the seams: with the library patched in and no device, the reference's own Encoder raises."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from frad_python_b200 import FradError, install
+    lf = reference_libfrad
+    install.patch_reference(lf)
+    try:
+        enc = lf.Encoder(0, 48000, 2, 32, 2048, "f32le")
+        with pytest.raises(FradError):
+            enc.process(np.zeros((2048, 2), np.float32).tobytes())
+    finally:
+        install.unpatch_reference()
+
+
+# ---- Repairer host logic on ForceFlush headers (livelock copied from reference repairer.py:66) ----------------
+def _repair_like_the_reference_loop(F, stream: bytes, chunk: int, ratio=(96, 24), limit=10000):
+    rp = F.Repairer(ratio, ctx=OracleCtx())
+    out, pos, calls = b"", 0, 0
+    while True:                                            # the reference application's loop: until eof and is_empty()
+        piece = stream[pos:pos + chunk]
+        pos += len(piece)
+        out += rp.process(piece)
+        calls += 1
+        assert calls < limit, "Repairer does not terminate"
+        if not piece and rp.is_empty():
+            break
+    return out + rp.flush()
+
+
+def _with_flush_markers_of(want: bytes, src: bytes) -> bytes:
+    """The same clip encoded by the reference with ECC 96/24, except that a repairer passes ForceFlush markers through
+    with the flag byte they came with (repairer.py:66: no ECC bit), while an ECC encoder sets the bit in its own."""
+    w = bytearray(want)
+    w[-24 + 8], w[-12 + 8] = src[-24 + 8], src[-12 + 8]
+    return bytes(w)
+
+
+@pytest.mark.parametrize("chunk", [32768, 777, 13])
+def test_repairer_terminates_on_streams_ending_in_force_flush(g_streams, chunk):
+    import frad_python_b200 as F
+    s = g_streams["p1"].tobytes()                          # [frames ...][frame][FF][FF] (encoder.py:90,105)
+    assert s[-24:-20] == O.FRM_SIGN and s[-12:-8] == O.FRM_SIGN
+    out = _repair_like_the_reference_loop(F, s, chunk)
+    assert out == _with_flush_markers_of(g_streams["p1_ecc"].tobytes(), s)
+    # an already protected stream, damaged: identical to the reference's own repair (one process() call + flush)
+    bad = g_streams["p1_ecc_bad"].tobytes()
+    assert _repair_like_the_reference_loop(F, bad, chunk) == g_streams["p1_ecc_bad_rep"].tobytes()
+    assert _repair_like_the_reference_loop(F, bad, chunk, (128, 20)) == g_streams["p1_ecc_bad_rep2"].tobytes()
+
+
+def test_repairer_continues_after_a_force_flush_in_mid_stream(g_streams):
+    import frad_python_b200 as F
+    s = g_streams["p1"].tobytes()
+    two = s + s                                            # ... [FF][FF][frames ...][FF][FF]
+    want = _with_flush_markers_of(g_streams["p1_ecc"].tobytes(), s)
+    for chunk in (1 << 20, 500):
+        assert _repair_like_the_reference_loop(F, two, chunk) == want + want
+
+
+# ---- GPU: patched seams driven the way the reference's codec objects drive them -------------------------------------------
+def _stub_libfrad():
+    """Module tree with the reference's shape; every seam raises until patched."""
+    def boom(*a, **k):
+        raise AssertionError("unpatched reference seam was called")
+    lf = types.ModuleType("libfrad_stub")
+    lf.fourier = types.ModuleType("libfrad_stub.fourier")
+    lf.fourier.AVAILABLE = [0, 1, 4]
+    for p in (0, 1, 2, 4):
+        m = types.ModuleType(f"libfrad_stub.fourier.profile{p}")
+        m.analogue, m.digital = boom, boom
+        setattr(lf.fourier, f"profile{p}", m)
+    lf.tools = types.ModuleType("libfrad_stub.tools")
+    lf.tools.ecc = types.ModuleType("libfrad_stub.tools.ecc")
+    lf.tools.ecc.encode, lf.tools.ecc.decode = boom, boom
+    lf.tools.asfh = types.ModuleType("libfrad_stub.tools.asfh")
+    lf.tools.asfh.crc32, lf.tools.asfh.crc16_ansi = boom, boom
+    lf.common = types.ModuleType("libfrad_stub.common")
+    lf.common.crc16_ansi = boom
+    return lf
+
+
+@pytest.mark.gpu
+def test_patched_seams_encoder_to_decoder_batch_of_one(g_p0, g_p1):
+    from frad_python_b200 import install
+    lf = _stub_libfrad()
+    install.patch_reference(lf)
+    try:
+        fourier, ecc, asfh, common = lf.fourier, lf.tools.ecc, lf.tools.asfh, lf.common
+        assert 2 in fourier.AVAILABLE
+        # --- profile 1 + ECC, as encoder.py:97,102,104(asfh.py:62) then decoder.py:66,68,71 ---
+        frame = g_p1["s48_pcm"][0] if "s48_pcm" in g_p1.files else O.synth_pcm(2048 / 48000, 48000, 2, 9)[:2048]
+        frad, bit_depth_index, channels, srate = fourier.profile1.analogue(frame, 16, 48000, LOSS0)
+        assert isinstance(frad, bytes) and (bit_depth_index, channels, srate) == (2, 2, 48000)
+        oq, otq, *_ = O.p1_analogue_ints(frame, 16, 48000, LOSS0)
+        gq, gtq = O.p1_unpack(frad)
+        assert np.max(np.abs(gq - oq)) <= 1 and np.mean(gq != oq) <= 1e-3 and np.max(np.abs(gtq - otq)) <= 1
+        prot = ecc.encode(frad, 96, 24)
+        assert prot == O.ecc_encode(frad, 96, 24)
+        crc = asfh.crc16_ansi(prot)
+        assert crc == O.crc16_arc(prot) == common.crc16_ansi(prot)
+        hit = bytearray(prot); hit[5] ^= 0xFF; hit[200] ^= 0x55
+        assert common.crc16_ansi(bytes(hit)) != crc
+        back = ecc.decode(bytes(hit), 96, 24, True)
+        assert back == frad and ecc.decode(prot, 96, 24, False) == frad
+        pcm = fourier.profile1.digital(back, bit_depth_index, channels, srate, 2048)
+        assert pcm.shape == (2048, 2) and pcm.dtype == np.float64
+        assert np.max(np.abs(pcm - O.p1_digital(frad, 2, 2, 48000, 2048))) <= 1e-12
+        # --- profile 0, as encoder.py:100,104(asfh.py:69) then decoder.py:65,74 ---
+        fr0 = g_p0["pcm_f32"][1]
+        frad0, idx0, ch0, sr0 = fourier.profile0.analogue(fr0, 32, 48000, False)
+        assert (idx0, ch0, sr0) == (3, 2, 48000)
+        assert asfh.crc32(frad0) == O.crc32(frad0)
+        want = np.frombuffer(O.p0_analogue(fr0, 32, 48000, False)[0], ">f4").astype(float)
+        assert np.max(np.abs(np.frombuffer(frad0, ">f4").astype(float) - want)) <= 4e-7
+        out0 = fourier.profile0.digital(frad0, idx0, ch0, False)
+        assert np.max(np.abs(out0 - O.p0_digital(frad0, 3, 2, False))) <= 1e-12
+        # --- profile 2 and 4 seams answer with the reference's return shapes ---
+        frad2, i2, c2, s2 = fourier.profile2.analogue(frame, 16, 48000, LOSS0)
+        assert fourier.profile2.digital(frad2, i2, c2, s2, 2048).shape == (2048, 2)
+        frad4, i4, c4, s4 = fourier.profile4.analogue(fr0, 32, 48000, True)
+        assert frad4 == O.p4_analogue(fr0, 32, 48000, True)[0]
+        assert np.array_equal(fourier.profile4.digital(frad4, i4, c4, True), fr0.astype(np.float64))
+    finally:
+        install.unpatch_reference()
+    with pytest.raises(AssertionError):
+        lf.fourier.profile1.analogue(None, 16, 48000, LOSS0)     # restored to the stub
+
+
+@pytest.mark.gpu
+def test_repairer_force_flush_streams_on_the_device(g_streams):
+    import frad_python_b200 as F
+    s = g_streams["p1"].tobytes()
+    for chunk in (32768, 777):
+        rp = F.Repairer((96, 24))
+        out, pos, calls = b"", 0, 0
+        while True:
+            piece = s[pos:pos + chunk]; pos += len(piece)
+            out += rp.process(piece); calls += 1
+            assert calls < 1000
+            if not piece and rp.is_empty():
+                break
+        assert out + rp.flush() == _with_flush_markers_of(g_streams["p1_ecc"].tobytes(), s)

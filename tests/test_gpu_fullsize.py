@@ -105,6 +105,70 @@ def test_config1_p1_10min_full_size(F):
     assert snr > 5, snr            # masking removes the -34 dB noise floor of the synthetic clip: ~8 dB by design
 
 
+def test_config2_p2_10min_full_size(F):
+    """configs[2]: profile 2 (profile 1 + TNS), 10 min 48 kHz stereo, hop 1920: 14 999 frames in one batched call, then the
+    full decode and the bitstream round trip through the codec objects on a 30 s cut."""
+    from frad_python_b200 import _abi
+    ctx = F.default_context()
+    pcm = tiled_pcm(600, 48000, 2, 2)
+    n, hop = 2048, 1920
+    nb = (len(pcm) - n) // hop + 1
+    assert nb == 14999
+    q, tq, lpc = ctx.p1_encode(pcm, nb, n, hop, 16, 48000, LOSS0, profile=2)
+    assert lpc.shape == (nb, 26) and np.abs(lpc).max() <= 15 and lpc.any()          # TNS active on this clip
+    # the tiled clip repeats every 5 s = 125 hops
+    assert np.array_equal(q[:1000], q[125:1125]) and np.array_equal(lpc[:1000], lpc[125:1125])
+    # fast N = 2048 route == generic route on a cut (LPC ints exactly, q exactly: both evaluate the same f64 formulas)
+    ctx.set_option(_abi.OPT_FORCE_GENERIC, 1)
+    try:
+        qg, tqg, lpcg = ctx.p1_encode(pcm[:400 * hop + n], 401, n, hop, 16, 48000, LOSS0, profile=2)
+    finally:
+        ctx.set_option(_abi.OPT_FORCE_GENERIC, 0)
+    assert np.array_equal(lpc[:401], lpcg) and np.array_equal(tq[:401], tqg)
+    assert np.max(np.abs(q[:401] - qg)) <= 1 and np.mean(q[:401] != qg) <= 1e-4
+    # oracle on sampled frames: LPC integers exact, quantised ints within a step
+    rng = np.random.default_rng(2)
+    bad = tot = 0
+    for i in rng.choice(nb, 16, replace=False):
+        oq, otq, olpc, *_ = O.p2_analogue_ints(pcm[i * hop:i * hop + n], 16, 48000, LOSS0)
+        assert np.array_equal(lpc[i], np.asarray(olpc).ravel())
+        assert np.max(np.abs(q[i] - np.asarray(oq).ravel())) <= 1 and np.max(np.abs(tq[i] - np.asarray(otq).ravel())) <= 1
+        bad += int(np.sum(q[i] != np.asarray(oq).ravel())); tot += q[i].size
+    assert bad <= 1e-4 * tot + 1
+    # full decode: f64 against the oracle on samples; f32 mode within one 16-bit LSB everywhere
+    out = ctx.p1_decode(q, tq, lpc, nb, n, 2, 16, 48000)
+    for i in rng.choice(nb, 8, replace=False):
+        want = O.p2_digital_ints(q[i], tq[i], lpc[i], 16, 2, 48000, n)
+        assert np.max(np.abs(out[i] - want)) <= 1e-11
+    out32 = ctx.p1_decode(q, tq, lpc, nb, n, 2, 16, 48000, prec=_abi.PREC_F32)
+    assert np.max(np.abs(out32 - out)) <= 2.0 ** -15
+    body = out[:, 128:hop].reshape(-1, 2)
+    ref = np.stack([pcm[i * hop + 128:i * hop + hop] for i in range(nb)]).reshape(-1, 2)
+    snr = 10 * np.log10(np.sum(ref.astype(float) ** 2) / np.sum((body - ref) ** 2))
+    assert snr > 5, snr
+    # bitstream round trip through Encoder -> Decoder (deflate, headers, cross-fade): the stream's payloads carry exactly
+    # the integers above, and the decoder's PCM equals the cross-faded device frames
+    cut = pcm[:30 * 48000]
+    enc = F.Encoder(2, 48000, 2, 16, 2048, "f32le")
+    enc.set_overlap_ratio(16); enc.set_loss_level(LOSS0)
+    stream = enc.process(cut.tobytes()).buf + enc.flush().buf
+    pos, k = 0, 0
+    while k < 700:
+        i = stream.find(O.FRM_SIGN, pos)
+        ln = int.from_bytes(stream[i + 4:i + 8], "big")
+        fq, ftq, flpc = O.p2_unpack(stream[i + 12:i + 12 + ln])
+        assert np.array_equal(O._pad_to(fq, n * 2), q[k]) and np.array_equal(O._pad_to(ftq, 54), tq[k]), k
+        assert np.array_equal(O._pad_to(flpc, 26), lpc[k]), k
+        pos, k = i + 12 + ln, k + 1
+    got = F.Decoder().process(stream).pcm
+    L = n - hop
+    w = O.hann_fade_in(L)[:, None]
+    for k in (1, 350, 699):
+        want = out[k, :hop].copy()
+        want[:L] = want[:L] * w + out[k - 1, hop:] * w[::-1]
+        assert np.max(np.abs(got[k * hop:(k + 1) * hop] - want)) <= 1e-12, k
+
+
 def test_config3_p1_ecc_corruption_repair(F):
     """configs[3]: profile 1 + ECC 96/24, 60 s; payload corruption classes A/B/C of SURVEY 8(d)."""
     pcm = tiled_pcm(60, 48000, 2, 3)

@@ -158,8 +158,6 @@ def test_unpack_short_ragged_and_truncated_payloads(ctx):
         wq[:min(len(dq), n * c)] = dq[:n * c]; wt[:min(len(dt), 27 * c)] = dt[:27 * c]
         assert np.array_equal(gq[i], wq), i
         assert np.array_equal(gt[i], wt), i
-        # the native host decoder (the per-stream ABI) agrees as well
-        assert np.array_equal(_abi.golomb_decode(qpart or b"\0", n * c), dq[:n * c].astype(np.int32)), i
 
 
 def test_golden_payloads_from_the_reference(ctx, g_p1, g_p2):

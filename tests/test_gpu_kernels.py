@@ -216,6 +216,40 @@ def test_rs_encode_golden(ctx, g_crc):
     assert ctx.rs_encode_many([b"hello world"], 245, 10)[0] == b"hello world\xed%T\xc4\xfd\xfd\x89\xf3\xa8\xaa"
 
 
+def test_rs_encode_is_the_code_by_definition(ctx):
+    """GPU output checked against the DEFINITION of the code, not against the oracle's LFSR: every encoded word, read as a
+    polynomial, vanishes at alpha^0 .. alpha^(csize-1) (GF(2^8), 0x11D, alpha = 2), and its parity equals the remainder of
+    a schoolbook division by the generator polynomial published in ISO/IEC 18004 Annex A.  Systematic parity is unique
+    given (0x11D, alpha, fcr), so this pins frad_rs_encode independently of oracle/rs.py.  All BASELINE ratios, whole and
+    shortened last chunks (tools/ecc.py:6-12)."""
+    from test_oracle_golden import QR_GENERATORS, gf_mul_plain, alpha_pow, parity_by_long_division
+    mul = np.zeros((256, 256), np.uint8)                       # plain multiplication table built from the bitwise product
+    for a in range(256):
+        for b in range(a, 256):
+            mul[a, b] = mul[b, a] = gf_mul_plain(a, b)
+    rng = np.random.default_rng(11)
+    for ds, cs in ((96, 24), (128, 20), (223, 32), (10, 7), (200, 55), (1, 2), (64, 16)):
+        lens = [ds * 5, ds * 3 + 1, ds - 1 if ds > 1 else 1, 16384, 1]
+        msgs = [rng.integers(0, 256, n, dtype=np.uint8).tobytes() for n in lens]
+        encs = ctx.rs_encode_many(msgs, ds, cs)
+        roots = [alpha_pow(j) for j in range(cs)]
+        for m, e in zip(msgs, encs):
+            assert len(e) == len(m) + -(-len(m) // ds) * cs
+            pos = 0
+            for c0 in range(0, len(m), ds):
+                chunk = m[c0:c0 + ds]
+                word = np.frombuffer(e[pos:pos + len(chunk) + cs], np.uint8)
+                pos += len(chunk) + cs
+                assert word[:len(chunk)].tobytes() == chunk                       # systematic
+                for r in roots:                                                   # Horner: word(alpha^j) == 0
+                    acc = 0
+                    for byte in word:
+                        acc = int(mul[acc, r]) ^ int(byte)
+                    assert acc == 0, (ds, cs, r)
+                if cs in QR_GENERATORS and c0 == 0:
+                    assert word[len(chunk):].tobytes() == parity_by_long_division(chunk, QR_GENERATORS[cs])
+
+
 def test_rs_repair_matches_oracle(ctx):
     rng = np.random.default_rng(2)
     for ds, cs in ((96, 24), (128, 20), (200, 55), (10, 7)):

@@ -218,6 +218,22 @@ def test_decoder_fused_route_matches_per_frame_route_and_output_formats(F, g_str
         assert got.dtype == np.dtype(fmt) and np.array_equal(got[sel], want[sel]), fmt
 
 
+@pytest.mark.parametrize("fmt", [">i2", ">f4", ">f8"])
+def test_decoder_big_endian_output_formats_take_one_semantic(F, g_streams, fmt):
+    """A big-endian pcm_format never takes the fused device route: whatever the chunking -- i.e. whether a
+    batch would have qualified for it or not -- values and dtype are those of the reference application's
+    from_f64(pcm, fmt).astype(fmt) (backend/pcmformat.py:49-62: big-endian integers are NOT scaled there)."""
+    from frad_python_b200.backend import from_f64
+    stream = g_streams["p1"].tobytes()
+    f64 = run_decoder(F, stream, False, 32768)
+    with np.errstate(all="ignore"):
+        want = from_f64(f64, np.dtype(fmt)).astype(fmt)
+    for chunk in (4096, 32768, 1 << 22):
+        got = run_decoder(F, stream, False, chunk, pcm_format=fmt)
+        assert got.dtype == np.dtype(fmt) and got.shape == want.shape
+        assert np.array_equal(got, want), (fmt, chunk)
+
+
 def test_overlap_kernel_against_numpy(F):
     """frad_overlap_dev alone: random frames, with and without a carried-in tail, several ratios."""
     from frad_python_b200._abi import lib, dtype_code

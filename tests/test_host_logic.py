@@ -46,27 +46,6 @@ def test_product_does_not_import_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), (dirpath, f)
 
 
-def test_golomb_host_matches_oracle_and_golden(g_p1):
-    from frad_python_b200 import _abi
-    assert _abi.golomb_encode(g_p1["gol_in"]) == g_p1["gol_out"].tobytes()
-    assert np.array_equal(_abi.golomb_decode(g_p1["gol_out"].tobytes()), g_p1["gol_in"])
-    assert _abi.golomb_encode(np.zeros(17, int)) == g_p1["gol_zero_out"].tobytes()
-    assert _abi.golomb_encode(np.array([], int)) == b"\x00"
-    rng = np.random.default_rng(5)
-    for hi in (1, 2, 3, 5, 100, 40000, 2 ** 30):
-        v = rng.integers(-hi, hi + 1, 777)
-        e = _abi.golomb_encode(v)
-        assert e == O.golomb_encode(v)
-        assert np.array_equal(_abi.golomb_decode(e), v)
-    rows = rng.integers(-60, 60, (33, 512)).astype(np.int32)
-    enc = _abi.golomb_encode_rows(rows)
-    assert enc == [O.golomb_encode(r) for r in rows]
-    assert np.array_equal(_abi.golomb_decode_rows(enc, 512), rows)
-    assert np.array_equal(_abi.golomb_decode_rows(enc, 600)[:, 512:], np.zeros((33, 88), np.int32))   # untrim padding
-    for cut in (1, 2, 7, 40):                       # truncated input follows the reference's slicing rule
-        assert np.array_equal(_abi.golomb_decode(enc[0][:cut]), O.golomb_decode(enc[0][:cut]))
-
-
 def test_asfh_bytes_match_oracle_header():
     from frad_python_b200.tools.asfh import ASFH
     pay = bytes(range(200))

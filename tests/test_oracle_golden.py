@@ -21,6 +21,86 @@ def test_rs_kats():
     assert bytes(R.RSCodec(10).encode(b"hello world")) == b"hello world\xed%T\xc4\xfd\xfd\x89\xf3\xa8\xaa"
 
 
+# Generator polynomials of ISO/IEC 18004 (QR code) Annex A, as exponents of alpha (GF(2^8), 0x11D, alpha = 2, first root
+# alpha^0 -- reedsolo's defaults), highest degree first.  A systematic code's parity is msg(x) x^nsym mod g(x), so a published
+# g(x) pins every parity byte the encoder can produce for that nsym -- 24 is the reference's default ratio (cli.py:32).
+QR_GENERATORS = {
+    7: [0, 87, 229, 146, 149, 238, 102, 21],
+    10: [0, 251, 67, 46, 61, 118, 70, 64, 94, 32, 45],
+    13: [0, 74, 152, 176, 100, 86, 100, 106, 104, 130, 218, 206, 140, 78],
+    15: [0, 8, 183, 61, 91, 202, 37, 51, 58, 58, 237, 140, 124, 5, 99, 105],
+    16: [0, 120, 104, 107, 109, 102, 161, 76, 3, 91, 191, 147, 169, 182, 194, 225, 120],
+    17: [0, 43, 139, 206, 78, 43, 239, 123, 206, 214, 147, 24, 99, 150, 39, 243, 163, 136],
+    18: [0, 215, 234, 158, 94, 184, 97, 118, 170, 79, 187, 152, 148, 252, 179, 5, 98, 96, 153],
+    20: [0, 17, 60, 79, 50, 61, 163, 26, 187, 202, 180, 221, 225, 83, 239, 156, 164, 212, 212, 188, 190],
+    22: [0, 210, 171, 247, 242, 93, 230, 14, 109, 221, 53, 200, 74, 8, 172, 98, 80, 219, 134, 160, 105, 165, 231],
+    24: [0, 229, 121, 135, 48, 211, 117, 251, 126, 159, 180, 169, 152, 192, 226, 228, 218, 111, 0, 117, 232, 87, 96, 227, 21],
+    26: [0, 173, 125, 158, 2, 103, 182, 118, 17, 145, 201, 111, 28, 165, 53, 161, 21, 245, 142, 13, 102, 48, 227, 153, 145, 218,
+         70],
+    28: [0, 168, 223, 200, 104, 224, 234, 108, 180, 110, 190, 195, 147, 205, 27, 232, 201, 21, 43, 245, 87, 42, 195, 212, 119,
+         242, 37, 9, 123],
+    30: [0, 41, 173, 145, 152, 216, 31, 179, 182, 50, 48, 110, 86, 239, 96, 222, 125, 42, 173, 226, 193, 224, 130, 156, 37, 251,
+         216, 238, 40, 192, 180],
+}
+
+
+def gf_mul_plain(a: int, b: int) -> int:
+    """Carry-less multiply mod 0x11D, written out (no tables shared with the oracle)."""
+    r = 0
+    while b:
+        if b & 1:
+            r ^= a
+        a <<= 1
+        if a & 0x100:
+            a ^= 0x11D
+        b >>= 1
+    return r
+
+
+def alpha_pow(e: int) -> int:
+    r = 1
+    for _ in range(e % 255):
+        r = gf_mul_plain(r, 2)
+    return r
+
+
+def parity_by_long_division(msg: bytes, gen_exponents) -> bytes:
+    """msg(x) x^nsym mod g(x) with g given by its published exponents (schoolbook division, independent of oracle/rs.py)."""
+    g = [alpha_pow(e) for e in gen_exponents]
+    nsym = len(g) - 1
+    rem = list(msg) + [0] * nsym
+    for i in range(len(msg)):
+        c = rem[i]
+        if c:
+            for j in range(1, nsym + 1):
+                rem[i + j] ^= gf_mul_plain(g[j], c)
+    return bytes(rem[len(msg):])
+
+
+def test_rs_generator_polynomials_match_the_published_qr_tables():
+    for nsym, exps in QR_GENERATORS.items():
+        assert [int(R.GF_LOG[c]) for c in R.generator_poly(nsym)] == exps, nsym
+
+
+def test_rs_more_published_vectors():
+    # QR version 1-M "HELLO WORLD" (the worked example of the thonky.com QR tutorial): 16 data + 10 EC codewords
+    d = bytes([32, 91, 11, 120, 209, 114, 220, 77, 67, 64, 236, 17, 236, 17, 236, 17])
+    assert list(R.encode_msg(d, 10)[16:]) == [196, 35, 39, 119, 235, 215, 231, 226, 93, 23]
+    # oracle encoder == schoolbook division by the published g(x), every published nsym, full and shortened words
+    rng = np.random.default_rng(7)
+    for nsym, exps in QR_GENERATORS.items():
+        for k in (1, 17, 96, 255 - nsym):
+            msg = rng.integers(0, 256, k, dtype=np.uint8).tobytes()
+            assert R.encode_msg(msg, nsym)[k:] == parity_by_long_division(msg, exps), (nsym, k)
+    # the reference's chunking (tools/ecc.py:6-12) at its default ratio, last chunk shortened
+    data = rng.integers(0, 256, 96 * 3 + 41, dtype=np.uint8).tobytes()
+    enc = O.ecc_encode(data, 96, 24)
+    for i in range(4):
+        chunk = data[96 * i:96 * (i + 1)]
+        blk = enc[120 * i:120 * i + len(chunk) + 24]
+        assert blk == chunk + parity_by_long_division(chunk, QR_GENERATORS[24])
+
+
 def test_rs_correction_limits():
     rng = np.random.default_rng(0)
     for k, nsym in ((96, 24), (17, 24), (200, 55), (1, 2)):
