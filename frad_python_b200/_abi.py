@@ -62,6 +62,7 @@ def lib():
             "frad_sync": (i32, [vp]),
             "frad_stream": (vp, [vp]),
             "frad_device_count": (i32, []),
+            "frad_device_pci_bus_id": (i32, [i32, C.c_char_p, i32]),
             "frad_sm_count": (i32, [vp]),
             "frad_kernel_launches": (C.c_uint64, [vp]),
             "frad_set_option": (i32, [vp, i32, i32]),
@@ -122,6 +123,7 @@ def lib():
 
 EXPORTS = [
     "frad_ctx_create", "frad_ctx_destroy", "frad_last_error", "frad_sync", "frad_stream", "frad_device_count",
+    "frad_device_pci_bus_id",
     "frad_sm_count", "frad_kernel_launches", "frad_set_option", "frad_host_alloc", "frad_host_free", "frad_dev_alloc", "frad_dev_free",
     "frad_h2d", "frad_d2h", "frad_memset_dev", "frad_event_record", "frad_event_elapsed_ms",
     "frad_p0_payload_bytes", "frad_p0_encode_dev", "frad_p0_decode_dev", "frad_p0_encode", "frad_p0_decode",

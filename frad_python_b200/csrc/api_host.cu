@@ -32,26 +32,38 @@ size_t rounded(size_t b) { return ((b + 255) & ~(size_t)255) + 256; }
 // ctx->s_out, chained by events, so PCIe traffic in both directions overlaps the kernels (pinned host memory
 // makes the copies truly asynchronous; pageable memory still works, just without overlap).
 namespace {
-static const int kChunkFrames = getenv("FRAD_CHUNK") ? atoi(getenv("FRAD_CHUNK")) : 1024;
+static int env_int(const char* name, int dflt, int lo) {
+  const char* v = getenv(name);
+  if (!v) return dflt;
+  const int x = atoi(v);
+  return x < lo ? lo : x;
+}
+static const int kChunkFrames = env_int("FRAD_CHUNK", 1024, 1);
+// Host waits: by default the pacing waits below block in the driver (cudaEventBlockingSync) instead of spinning -- with
+// one rank per GPU and two pipelines per rank, spinning waits keep 16 host threads busy on a box that may have 16 cores.
+// FRAD_SPIN=1 restores spinning waits (lowest latency for a single rank).
+static const bool kSpin = env_int("FRAD_SPIN", 0, 0) != 0;
 
 struct pipeline {
   frad_ctx* ctx; int nchunks; int chunk;
   cudaEvent_t* in_done; cudaEvent_t* k_done; cudaEvent_t* aux; cudaEvent_t* out_done;     // one event of each kind per chunk
+  cudaEvent_t fin;
 };
 
 int pipeline_begin(frad_ctx* ctx, int B, pipeline* p) {
   p->ctx = ctx;
   p->chunk = kChunkFrames;
   p->nchunks = (B + p->chunk - 1) / p->chunk;
-  while ((int)ctx->pipe_events.size() < 4 * p->nchunks + 1) {
+  while ((int)ctx->pipe_events.size() < 4 * p->nchunks + 2) {
     cudaEvent_t e;
-    FRAD_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    FRAD_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming | (kSpin ? 0 : cudaEventBlockingSync)));
     ctx->pipe_events.push_back(e);
   }
   p->in_done = ctx->pipe_events.data();
   p->k_done = ctx->pipe_events.data() + p->nchunks;
-  p->aux = ctx->pipe_events.data() + 2 * p->nchunks + 1;
-  p->out_done = ctx->pipe_events.data() + 3 * p->nchunks + 1;
+  p->aux = ctx->pipe_events.data() + 2 * p->nchunks + 2;
+  p->out_done = ctx->pipe_events.data() + 3 * p->nchunks + 2;
+  p->fin = ctx->pipe_events[2 * p->nchunks + 1];
   // the copy streams must not run ahead of work already queued on the main stream (buffer reuse)
   cudaEvent_t fence = ctx->pipe_events[2 * p->nchunks];
   FRAD_CUDA(ctx, cudaEventRecord(fence, ctx->stream));
@@ -60,11 +72,32 @@ int pipeline_begin(frad_ctx* ctx, int B, pipeline* p) {
   return FRAD_OK;
 }
 
+// Nothing may still be in flight towards the caller's buffers or the shared arena when a call returns -- also when it
+// returns an error from the middle of the pipeline.
+static void pipeline_drain(frad_ctx* ctx) {
+  cudaStreamSynchronize(ctx->s_in);
+  cudaStreamSynchronize(ctx->stream);
+  cudaStreamSynchronize(ctx->s_out);
+}
+
+// Input chunk i covers the samples [i chunk hop, (i + 1) chunk hop) (the last one runs to the end of the input).  The frames
+// of chunk i read up to sample (f1 - 1) hop + N: returns the last input chunk that must have arrived before they run.
+static int last_input_chunk(int i, int chunk, int nchunks, int B, int64_t hop, int N) {
+  const int f1 = ((i + 1) * chunk < B) ? (i + 1) * chunk : B;
+  if (hop <= 0) return nchunks - 1;                       // every frame reads the same samples: they travel with the last chunk
+  const int64_t end = (int64_t)(f1 - 1) * hop + N;        // one past the last sample read
+  int64_t j = (end - 1) / ((int64_t)chunk * hop);
+  if (j > nchunks - 1) j = nchunks - 1;
+  return (int)(j < i ? i : j);
+}
+
 // h2d(i, f0, f1, stream), run(f0, f1) [enqueues on ctx->stream], d2h(f0, f1, stream)
+// need(i): index of the last input chunk the kernels of chunk i read (i itself when frames do not overlap)
 // fin(stream): optional last step on the output stream before the final synchronisation
 struct no_fin { int operator()(cudaStream_t) const { return FRAD_OK; } };
-template <class H2D, class RUN, class D2H, class FIN = no_fin>
-int pipeline_run(pipeline& p, int B, bool needs_next_chunk, H2D h2d, RUN run, D2H d2h, FIN fin = FIN()) {
+struct need_self { int operator()(int i) const { return i; } };
+template <class NEED, class H2D, class RUN, class D2H, class FIN = no_fin>
+int pipeline_run_inner(pipeline& p, int B, NEED need, H2D h2d, RUN run, D2H d2h, FIN fin) {
   frad_ctx* ctx = p.ctx;
   int rc;
   // The host paces the copy queues: a chunk's input copy is submitted when the previous one has completed, its output
@@ -73,7 +106,7 @@ int pipeline_run(pipeline& p, int B, bool needs_next_chunk, H2D h2d, RUN run, D2
   // other H2D-heavy): with the whole batch queued up front, or with three chunks of look-ahead, the second context's
   // copies are only served after the first call has finished (9.9 ms for the pair = the sum of the two calls); paced
   // like this the two calls interleave chunk by chunk (8.3 ms).  A call running alone pays about 3 % for the pacing.
-  static const int kDepth = getenv("FRAD_COPY_DEPTH") ? atoi(getenv("FRAD_COPY_DEPTH")) : 1;   // ready copies per stream
+  static const int kDepth = env_int("FRAD_COPY_DEPTH", 1, 1);   // ready copies per stream
   int submitted_in = 0;
   auto queue_in_upto = [&](int last) -> int {
     for (; submitted_in <= last && submitted_in < p.nchunks; submitted_in++) {
@@ -97,20 +130,31 @@ int pipeline_run(pipeline& p, int B, bool needs_next_chunk, H2D h2d, RUN run, D2
   };
   for (int i = 0; i < p.nchunks; i++) {
     const int f0 = i * p.chunk, f1 = (f0 + p.chunk < B) ? f0 + p.chunk : B;
-    if ((rc = queue_in_upto(i + (needs_next_chunk ? 1 : 0)))) return rc;
-    FRAD_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, p.in_done[i], 0));
-    if (needs_next_chunk && i + 1 < p.nchunks) FRAD_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, p.in_done[i + 1], 0));
+    const int last = need(i);
+    if ((rc = queue_in_upto(last))) return rc;
+    FRAD_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, p.in_done[last], 0));    // s_in is in order: covers every earlier chunk
     if ((rc = run(f0, f1))) return rc;
     FRAD_CUDA(ctx, cudaEventRecord(p.k_done[i], ctx->stream));
-    if ((rc = queue_in_upto(i + 1 + (needs_next_chunk ? 1 : 0)))) return rc;   // next input while these kernels run
+    if (i + 1 < p.nchunks && (rc = queue_in_upto(need(i + 1)))) return rc;   // next input while these kernels run
     if (i > 0 && (rc = queue_out(i - 1))) return rc;
   }
   if ((rc = queue_out(p.nchunks - 1))) return rc;
   if ((rc = fin(ctx->s_out))) return rc;
-  FRAD_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
-  FRAD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  FRAD_CUDA(ctx, cudaEventRecord(p.fin, ctx->s_out));      // the kernels of every chunk precede its output copy
+  FRAD_CUDA(ctx, cudaEventSynchronize(p.fin));
   return FRAD_OK;
 }
+template <class NEED, class H2D, class RUN, class D2H, class FIN = no_fin>
+int pipeline_run(pipeline& p, int B, NEED need, H2D h2d, RUN run, D2H d2h, FIN fin = FIN()) {
+  const int rc = pipeline_run_inner(p, B, need, h2d, run, d2h, fin);
+  if (rc) pipeline_drain(p.ctx);
+  return rc;
+}
+// frames of N samples every hop samples
+struct need_hop {
+  const pipeline* p; int B; int64_t hop; int N;
+  int operator()(int i) const { return last_input_chunk(i, p->chunk, p->nchunks, B, hop, N); }
+};
 
 inline int copy_async(frad_ctx* ctx, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t s) {
   if (bytes) FRAD_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, kind, s));
@@ -142,7 +186,7 @@ static int lossless_encode(frad_ctx* ctx, int profile, const void* pcm, int pcm_
   pipeline p;
   int rc = pipeline_begin(ctx, B, &p);
   if (rc) return rc;
-  return pipeline_run(p, B, hop < N,
+  return pipeline_run(p, B, need_hop{&p, B, hop, N},
     [&](int, int f0, int f1, cudaStream_t s) {
       const size_t lo = (size_t)f0 * hop * samp;
       const size_t hi = (f1 == B) ? in_bytes : (size_t)f1 * hop * samp;
@@ -193,7 +237,7 @@ static int lossless_decode(frad_ctx* ctx, int profile, const uint8_t* payload, s
   pipeline p;
   int rc = pipeline_begin(ctx, B, &p);
   if (rc) return rc;
-  return pipeline_run(p, B, false,
+  return pipeline_run(p, B, need_self(),
     [&](int, int f0, int f1, cudaStream_t s) {
       return copy_async(ctx, d_in + (size_t)f0 * payload_stride, payload + (size_t)f0 * payload_stride,
                         (size_t)(f1 - f0) * payload_stride, H2D_, s);
@@ -238,7 +282,7 @@ extern "C" int frad_p1_encode(frad_ctx* ctx, const void* pcm, int pcm_dtype, int
   pipeline p;
   int rc = pipeline_begin(ctx, B, &p);
   if (rc) return rc;
-  return pipeline_run(p, B, hop < N,
+  return pipeline_run(p, B, need_hop{&p, B, hop, N},
     [&](int, int f0, int f1, cudaStream_t s) {
       const size_t lo = (size_t)f0 * hop * samp;
       const size_t hi = (f1 == B) ? in_bytes : (size_t)f1 * hop * samp;
@@ -275,7 +319,7 @@ extern "C" int frad_p1_decode(frad_ctx* ctx, const int32_t* q, const int32_t* tq
   pipeline p;
   int rc = pipeline_begin(ctx, B, &p);
   if (rc) return rc;
-  return pipeline_run(p, B, false,
+  return pipeline_run(p, B, need_self(),
     [&](int, int f0, int f1, cudaStream_t s) {
       const size_t nfr = (size_t)(f1 - f0);
       int r = copy_async(ctx, d_q + f0 * qf, q + f0 * qf, 4 * qf * nfr, H2D_, s);
@@ -445,7 +489,7 @@ extern "C" int frad_p1_encode_raw(frad_ctx* ctx, const void* pcm, int pcm_dtype,
     if (overflow || raw_off[f1] > raw_cap) { overflow = true; return (int)FRAD_OK; }
     return copy_async(ctx, raw + raw_off[f0], d_raw + raw_off[f0], (size_t)(raw_off[f1] - raw_off[f0]), D2H_, s);
   };
-  rc = pipeline_run(p, B, hop < N,
+  rc = pipeline_run(p, B, need_hop{&p, B, hop, N},
     [&](int, int f0, int f1, cudaStream_t s) {
       const size_t lo = (size_t)f0 * hop * samp;
       const size_t hi = (f1 == B) ? in_bytes : (size_t)f1 * hop * samp;
@@ -502,7 +546,7 @@ extern "C" int frad_p1_decode_raw(frad_ctx* ctx, const uint8_t* raw, const uint6
   pipeline p;
   int rc = pipeline_begin(ctx, B, &p);
   if (rc) return rc;
-  rc = pipeline_run(p, B, false,
+  rc = pipeline_run(p, B, need_self(),
     [&](int i, int f0, int f1, cudaStream_t s) {
       int r = FRAD_OK;
       if (i == 0) r = copy_async(ctx, d_off, raw_off, 8 * ((size_t)B + 1), H2D_, s);
@@ -559,7 +603,7 @@ extern "C" int frad_p1_decode_stream(frad_ctx* ctx, const uint8_t* raw, const ui
   pipeline p;
   int rc = pipeline_begin(ctx, B, &p);
   if (rc) return rc;
-  rc = pipeline_run(p, B, false,
+  rc = pipeline_run(p, B, need_self(),
     [&](int i, int f0, int f1, cudaStream_t s) {
       int r = FRAD_OK;
       if (i == 0) {

@@ -11,6 +11,12 @@ extern "C" int frad_device_count(void) {
   return n;
 }
 
+extern "C" int frad_device_pci_bus_id(int device, char* out, int cap) {
+  if (!out || cap < 16) return FRAD_E_ARG;
+  if (cudaDeviceGetPCIBusId(out, cap, device) != cudaSuccess) { cudaGetLastError(); return FRAD_E_CUDA; }
+  return FRAD_OK;
+}
+
 extern "C" int frad_ctx_create(int device, frad_ctx** out) {
   if (!out) return FRAD_E_ARG;
   *out = nullptr;

@@ -67,6 +67,9 @@ const char* frad_last_error(frad_ctx* ctx);      /* ctx may be NULL: last creati
 int  frad_sync(frad_ctx* ctx);
 void* frad_stream(frad_ctx* ctx);                /* the cudaStream_t work is enqueued on */
 int  frad_device_count(void);
+/* "domain:bus:device.function" of a GPU (>= 16 bytes), e.g. to look up its NUMA node under /sys/bus/pci/devices/ so that a
+ * rank's pinned staging buffers are allocated next to the GPU they feed (frad_python_b200/shard.py: bind_host_near_gpu) */
+int  frad_device_pci_bus_id(int device, char* out, int cap);
 int  frad_sm_count(frad_ctx* ctx);
 uint64_t frad_kernel_launches(frad_ctx* ctx);    /* kernels launched through this ctx so far */
 
