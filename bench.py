@@ -15,8 +15,13 @@ PCM values = samples x channels consumed per pass).
   cpu_baseline  the oracle port of the reference NumPy/SciPy path on a bounded sample, 1 core
 
 `--impl reference` times the oracle port (the reference cannot travel / be compiled: it is Python,
-see DESIGN.md) on all host cores.  N > 1: one process per GPU (torchrun), frames sharded by
-contiguous range, no collective on the data path; weak scaling (each rank encodes its own clip).
+see DESIGN.md) on all host cores.
+
+N > 1: one process per GPU (torchrun), no collective on the data path.  Two kinds of numbers:
+  value / e2e   WEAK scaling -- every rank encodes + decodes its OWN 10-minute clip (independent work, `scaling: weak`)
+  strong        STRONG scaling -- ONE stream (configs[4] shape: 64 s block of 96 kHz 8-channel PCM) whose frames are cut by
+                contiguous range over the ranks, parts concatenated in rank order in shared memory, result checked against
+                one GPU doing the whole block (tools/strong_leg.py).  Runs at every N (N = 1 is its own baseline).
 """
 import argparse
 import json
@@ -199,6 +204,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--frames", type=int, default=NFRAMES)
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling (frame-sharded single stream) leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -220,6 +226,8 @@ def main():
     from frad_python_b200 import Context, _abi
     L = _abi.lib()
     ctx = Context(local)
+    from frad_python_b200.shard import bind_host_near_gpu
+    host_bind = bind_host_near_gpu(local)           # pinned buffers next to the GPU where the kernel exposes NUMA nodes
     B = args.frames
     pcm_host = make_pcm(1 + rank)[: (B - 1) * HOP + N]
     nscal = B * HOP * CH                                              # scalar PCM values consumed per pass
@@ -281,6 +289,33 @@ def main():
     ctx.event(8)
     ctx.sync()
     dec32_ms = ctx.elapsed_ms(7, 8) / args.steps
+
+    # ---- profile 0 on the same clip shape (BASELINE's metric is quoted on "p0/p1"): f32 PCM -> 32-bit BE coefficients -> f64 PCM
+    B0 = (len(pcm_host)) // N
+    d_pay = ctx.dev(B0 * N * CH * 4); d_peak = ctx.dev(B0 * 8)
+
+    def enc0():
+        ctx.check(L.frad_p0_encode_dev(ctx.handle, d_pcm.ptr, _abi.F32, N, B0, N, CH, 32, 0, _abi.PREC_REF, d_pay.ptr, N * CH * 4,
+                                       d_peak.ptr))
+
+    def dec0(prec=_abi.PREC_REF):
+        ctx.check(L.frad_p0_decode_dev(ctx.handle, d_pay.ptr, N * CH * 4, B0, N, CH, 32, 0, prec, d_out.ptr, _abi.F64))
+
+    enc0(); dec0(); dec0(_abi.PREC_F32); ctx.sync()
+    ctx.event(12)
+    for _ in range(args.steps):
+        enc0()
+    ctx.event(13)
+    for _ in range(args.steps):
+        dec0()
+    ctx.event(14)
+    for _ in range(args.steps):
+        dec0(_abi.PREC_F32)
+    ctx.event(15)
+    ctx.sync()
+    p0_enc_ms, p0_dec_ms, p0_dec32_ms = (ctx.elapsed_ms(12, 13) / args.steps, ctx.elapsed_ms(13, 14) / args.steps,
+                                         ctx.elapsed_ms(14, 15) / args.steps)
+    d_pay.free(); d_peak.free()
 
     # ---- device-resident timing of the bit-coder kernels (not part of `value`; they are on the e2e path) -------
     stride = L.frad_p1_raw_bound(N, CH, 0)
@@ -406,6 +441,11 @@ def main():
         e2e_int_step()
     ctx.sync()
     e2e_int_ms = 1e3 * (time.perf_counter() - t0) / 2
+    strong = None
+    if not args.no_strong:
+        from tools import strong_leg
+        strong = strong_leg.run(ctx, dist, rank, world, max(2, min(args.steps, 5)),
+                                os.environ.get("MASTER_PORT", "0") + "_" + str(os.getppid() if world > 1 else os.getpid()))
     clocks = sampler.stop()
 
     # sanity: the e2e result must be real data (decoded audio close to the input)
@@ -467,14 +507,40 @@ def main():
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": dom["gbs"], "peak": hbm, "unit": "GB/s", "frac": dom["frac"],
                      "traffic": (traffic or {}).get("dec2048_f64" if dom is k_dec else "enc2048"), "kernel": dom["kernel"],
-                     "traffic_source": (traffic or {}).get("source"), "peak_source": how,
+                     "traffic_source": "static, from a committed capture -- " + str((traffic or {}).get("source")), "peak_source": how,
                      "algorithmic_bytes_per_launch": dom["bytes"], "launch_ms": dom["ms"]},
         "kernels": [k_enc, k_dec, k_dec32,
                     {"kernel": "p1_pack_kernel + scan_len + compact (Exp-Golomb-Rice bit packing, e2e path only)", "ms": pack_ms},
                     {"kernel": "p1_unpack_kernel (Exp-Golomb-Rice parsing, one thread per frame, e2e path only)", "ms": unpack_ms}],
         "f32_inverse_mode": {"value": world * nscal / ((enc_ms + dec32_ms) * 1e-3) / 1e6, "unit": "MSamples/s",
                              "tolerance": "decoded PCM within 1 LSB at 16 bit of the f64 reference (measured 1.2e-7)"},
+        "host_bind": host_bind,
     }
+    # profile 0 of the same clip shape (rank 0's timings; f32 PCM -> 32-bit big-endian coefficients -> f64 PCM)
+    nval0 = B0 * N * CH
+    p0k = [{"kernel": "enc2048_kernel<0,2> (f32 forward DCT -> BE f32 payload + peak)", "bytes": nval0 * 8.0, "ms": p0_enc_ms},
+           {"kernel": "dec2048_kernel<double,0,2> (unpack + f64 inverse DCT -> f64 PCM; reference precision)", "bytes": nval0 * 12.0,
+            "ms": p0_dec_ms},
+           {"kernel": "dec2048_kernel<float,0,2> (f32 inverse, f64 PCM out; <= 1 LSB at 16 bit)", "bytes": nval0 * 12.0,
+            "ms": p0_dec32_ms}]
+    for k in p0k:
+        k["gbs"] = k["bytes"] / (k["ms"] * 1e-3) / 1e9
+        k["frac"] = k["gbs"] / hbm
+    line["p0"] = {"workload": "profile 0, 32-bit, same 10 min 48 kHz stereo clip, hop = N = 2048 (%d frames), device-resident" % B0,
+                  "value": nval0 / ((p0_enc_ms + p0_dec_ms) * 1e-3) / 1e6, "unit": "MSamples/s (one rank)",
+                  "x_realtime": nval0 / ((p0_enc_ms + p0_dec_ms) * 1e-3) / (SRATE * CH), "kernels": p0k}
+    if strong is not None:
+        line["strong"] = strong
+    try:                                            # e2e against the box's measured copy ceiling at this N (tools/pcie_probe.py)
+        ceil = json.load(open(os.path.join(ROOT, "profiles", "r2_pcie_ceiling.json"))).get(str(world))
+        if ceil:
+            line["e2e"]["copy_ceiling"] = {"value": ceil["e2e_ceiling_MSamples_per_s"], "unit": "MSamples/s",
+                                           "frac": e2e_val / ceil["e2e_ceiling_MSamples_per_s"],
+                                           "source": "profiles/r2_pcie_ceiling.json: plain pinned cudaMemcpyAsync of one step's "
+                                                     "bytes in both directions at once, all ranks together (static, measured "
+                                                     "with tools/pcie_probe.py on a box of this pool)"}
+    except Exception:
+        pass
     if not args.no_cpu and world == 1:
         nsample = 1000
         frames = [pcm_host[i * HOP:i * HOP + N] for i in range(nsample)]

@@ -68,6 +68,8 @@ def lib():
             "frad_set_option": (i32, [vp, i32, i32]),
             "frad_host_alloc": (vp, [vp, sz]),
             "frad_host_free": (None, [vp, vp]),
+            "frad_host_register": (i32, [vp, vp, sz]),
+            "frad_host_unregister": (i32, [vp, vp]),
             "frad_dev_alloc": (vp, [vp, sz]),
             "frad_dev_free": (None, [vp, vp]),
             "frad_h2d": (i32, [vp, vp, vp, sz]),
@@ -124,7 +126,7 @@ def lib():
 EXPORTS = [
     "frad_ctx_create", "frad_ctx_destroy", "frad_last_error", "frad_sync", "frad_stream", "frad_device_count",
     "frad_device_pci_bus_id",
-    "frad_sm_count", "frad_kernel_launches", "frad_set_option", "frad_host_alloc", "frad_host_free", "frad_dev_alloc", "frad_dev_free",
+    "frad_sm_count", "frad_kernel_launches", "frad_set_option", "frad_host_alloc", "frad_host_free", "frad_host_register", "frad_host_unregister", "frad_dev_alloc", "frad_dev_free",
     "frad_h2d", "frad_d2h", "frad_memset_dev", "frad_event_record", "frad_event_elapsed_ms",
     "frad_p0_payload_bytes", "frad_p0_encode_dev", "frad_p0_decode_dev", "frad_p0_encode", "frad_p0_decode",
     "frad_p4_encode_dev", "frad_p4_decode_dev", "frad_p4_encode", "frad_p4_decode",
@@ -223,6 +225,13 @@ class Context:
         self._pinned.append(p)
         buf = (C.c_char * max(n, 1)).from_address(p)
         return np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+
+    def register(self, arr: np.ndarray):
+        """Page-lock an existing host array (a shared-memory mapping, say) for asynchronous copies; undo with unregister."""
+        self.check(lib().frad_host_register(self.handle, arr.ctypes.data, arr.nbytes))
+
+    def unregister(self, arr: np.ndarray):
+        self.check(lib().frad_host_unregister(self.handle, arr.ctypes.data))
 
     def dev(self, nbytes: int) -> DeviceBuffer:
         return DeviceBuffer(self, nbytes)

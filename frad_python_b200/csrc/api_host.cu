@@ -1,6 +1,7 @@
 // Host-pointer entry points: copy in, run the *_dev path, copy out, synchronise.
 // These are what a ctypes / cgo / JNI binding of the reference's per-frame seams would call.
 #include <cstdlib>
+#include <sched.h>
 #include "common.cuh"
 
 static uint32_t host_max_len(const uint32_t* len, uint32_t ulen, int B) {
@@ -39,10 +40,24 @@ static int env_int(const char* name, int dflt, int lo) {
   return x < lo ? lo : x;
 }
 static const int kChunkFrames = env_int("FRAD_CHUNK", 1024, 1);
-// Host waits: by default the pacing waits below block in the driver (cudaEventBlockingSync) instead of spinning -- with
-// one rank per GPU and two pipelines per rank, spinning waits keep 16 host threads busy on a box that may have 16 cores.
-// FRAD_SPIN=1 restores spinning waits (lowest latency for a single rank).
-static const bool kSpin = env_int("FRAD_SPIN", 0, 0) != 0;
+// Host waits of the pacing below.  FRAD_WAIT=yield (default): poll the event and give the core away between polls -- as
+// quick as a spinning wait when cores are free, and other ranks' threads get the core when they are not (one rank per GPU
+// with two pipelines each is 16 waiting threads on a 16-core box).  spin: cudaEventSynchronize on a spinning event;
+// block: cudaEventBlockingSync (measured on B200, one rank: 26 % slower end to end -- a wake-up per chunk and stream).
+static int wait_mode() {
+  const char* v = getenv("FRAD_WAIT");
+  if (!v) return 0;
+  return (v[0] == 's') ? 1 : (v[0] == 'b') ? 2 : 0;
+}
+static const int kWait = wait_mode();
+static inline cudaError_t wait_event(cudaEvent_t e) {
+  if (kWait != 0) return cudaEventSynchronize(e);
+  for (;;) {
+    const cudaError_t r = cudaEventQuery(e);
+    if (r != cudaErrorNotReady) return r;
+    sched_yield();
+  }
+}
 
 struct pipeline {
   frad_ctx* ctx; int nchunks; int chunk;
@@ -56,7 +71,7 @@ int pipeline_begin(frad_ctx* ctx, int B, pipeline* p) {
   p->nchunks = (B + p->chunk - 1) / p->chunk;
   while ((int)ctx->pipe_events.size() < 4 * p->nchunks + 2) {
     cudaEvent_t e;
-    FRAD_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming | (kSpin ? 0 : cudaEventBlockingSync)));
+    FRAD_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming | (kWait == 2 ? cudaEventBlockingSync : 0)));
     ctx->pipe_events.push_back(e);
   }
   p->in_done = ctx->pipe_events.data();
@@ -111,7 +126,7 @@ int pipeline_run_inner(pipeline& p, int B, NEED need, H2D h2d, RUN run, D2H d2h,
   auto queue_in_upto = [&](int last) -> int {
     for (; submitted_in <= last && submitted_in < p.nchunks; submitted_in++) {
       const int i = submitted_in;
-      if (i >= kDepth) FRAD_CUDA(ctx, cudaEventSynchronize(p.in_done[i - kDepth]));
+      if (i >= kDepth) FRAD_CUDA(ctx, wait_event(p.in_done[i - kDepth]));
       const int f0 = i * p.chunk, f1 = (f0 + p.chunk < B) ? f0 + p.chunk : B;
       int r = h2d(i, f0, f1, ctx->s_in);
       if (r) return r;
@@ -121,8 +136,8 @@ int pipeline_run_inner(pipeline& p, int B, NEED need, H2D h2d, RUN run, D2H d2h,
   };
   auto queue_out = [&](int i) -> int {                     // chunk i's kernels are done: its results can leave
     const int f0 = i * p.chunk, f1 = (f0 + p.chunk < B) ? f0 + p.chunk : B;
-    FRAD_CUDA(ctx, cudaEventSynchronize(p.k_done[i]));
-    if (i >= kDepth) FRAD_CUDA(ctx, cudaEventSynchronize(p.out_done[i - kDepth]));
+    FRAD_CUDA(ctx, wait_event(p.k_done[i]));
+    if (i >= kDepth) FRAD_CUDA(ctx, wait_event(p.out_done[i - kDepth]));
     int r = d2h(f0, f1, ctx->s_out);
     if (r) return r;
     FRAD_CUDA(ctx, cudaEventRecord(p.out_done[i], ctx->s_out));
@@ -141,7 +156,7 @@ int pipeline_run_inner(pipeline& p, int B, NEED need, H2D h2d, RUN run, D2H d2h,
   if ((rc = queue_out(p.nchunks - 1))) return rc;
   if ((rc = fin(ctx->s_out))) return rc;
   FRAD_CUDA(ctx, cudaEventRecord(p.fin, ctx->s_out));      // the kernels of every chunk precede its output copy
-  FRAD_CUDA(ctx, cudaEventSynchronize(p.fin));
+  FRAD_CUDA(ctx, wait_event(p.fin));
   return FRAD_OK;
 }
 template <class NEED, class H2D, class RUN, class D2H, class FIN = no_fin>
@@ -485,7 +500,7 @@ extern "C" int frad_p1_encode_raw(frad_ctx* ctx, const void* pcm, int pcm_dtype,
   bool overflow = false;
   auto fetch_bytes = [&](int i, cudaStream_t s) -> int {       // payload bytes of chunk i, once its offsets are on the host
     const int f0 = i * p.chunk, f1 = (f0 + p.chunk < B) ? f0 + p.chunk : B;
-    FRAD_CUDA(ctx, cudaEventSynchronize(p.aux[i]));
+    FRAD_CUDA(ctx, wait_event(p.aux[i]));
     if (overflow || raw_off[f1] > raw_cap) { overflow = true; return (int)FRAD_OK; }
     return copy_async(ctx, raw + raw_off[f0], d_raw + raw_off[f0], (size_t)(raw_off[f1] - raw_off[f0]), D2H_, s);
   };

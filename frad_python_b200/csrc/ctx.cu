@@ -88,6 +88,20 @@ extern "C" void* frad_host_alloc(frad_ctx* ctx, size_t bytes) {
 }
 extern "C" void frad_host_free(frad_ctx* ctx, void* p) { (void)ctx; if (p) cudaFreeHost(p); }
 
+// Page-lock memory the caller already owns (e.g. a shared-memory mapping the ranks of one box assemble their output in), so
+// that copies to and from it are asynchronous like those of frad_host_alloc memory.
+extern "C" int frad_host_register(frad_ctx* ctx, void* p, size_t bytes) {
+  if (!ctx || !p || !bytes) return FRAD_E_ARG;
+  cudaSetDevice(ctx->device);
+  FRAD_CUDA(ctx, cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+  return FRAD_OK;
+}
+extern "C" int frad_host_unregister(frad_ctx* ctx, void* p) {
+  if (!ctx || !p) return FRAD_E_ARG;
+  FRAD_CUDA(ctx, cudaHostUnregister(p));
+  return FRAD_OK;
+}
+
 extern "C" void* frad_dev_alloc(frad_ctx* ctx, size_t bytes) {
   if (!ctx) return nullptr;
   void* p = nullptr;

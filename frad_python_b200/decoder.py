@@ -22,6 +22,8 @@ class DecodeResult:
     def __init__(self, pcm, srate: int, frames: int, crit: bool):
         pcm = [p for p in pcm if getattr(p, "ndim", 1) == 2 and len(p)]
         self.pcm = np.concatenate(pcm) if pcm else np.array([])
+        if pcm and self.pcm.dtype != pcm[0].dtype and all(p.dtype == pcm[0].dtype for p in pcm):
+            self.pcm = self.pcm.astype(pcm[0].dtype)          # np.concatenate drops a non-native byte order
         self.srate = srate
         self.frames = frames
         self.crit = crit

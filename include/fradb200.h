@@ -80,6 +80,8 @@ int  frad_set_option(frad_ctx* ctx, int option, int value);
 
 void* frad_host_alloc(frad_ctx* ctx, size_t bytes);   /* pinned host memory, NULL on failure */
 void  frad_host_free(frad_ctx* ctx, void* p);
+int   frad_host_register(frad_ctx* ctx, void* p, size_t bytes);   /* page-lock caller-owned memory (e.g. a shared mapping) */
+int   frad_host_unregister(frad_ctx* ctx, void* p);
 void* frad_dev_alloc(frad_ctx* ctx, size_t bytes);    /* device memory, NULL on failure */
 void  frad_dev_free(frad_ctx* ctx, void* p);
 int  frad_h2d(frad_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);   /* async on the stream */

@@ -101,16 +101,16 @@ def test_sharded_bitstream_and_pcm_identical_to_one_gpu(prof, bits, fmt):
     try:
         for chunk in (1 << 24, 1 << 20):
             one, n1 = run_enc(_setup(F.Encoder(prof, 48000, 2, bits, 2048, fmt), prof), pcm, chunk)
-            se = _setup(ShardedEncoder(prof, 48000, 2, bits, 2048, fmt, ctxs=ctxs), prof)
+            se = _setup(ShardedEncoder(prof, 48000, 2, bits, 2048, fmt, ctxs=ctxs, min_frames_per_shard=16), prof)
             sh, n2 = run_enc(se, pcm, chunk)
             assert se.sharded_batches >= 1 and se.last_shards >= 1
             assert n1 == n2 and sh == one, (prof, chunk, ndev)
             d1 = run_dec(F.Decoder(), one, chunk)
-            sd = ShardedDecoder(ctxs=ctxs)
+            sd = ShardedDecoder(ctxs=ctxs, min_frames_per_shard=16)
             d2 = run_dec(sd, one, chunk)
             assert sd.sharded_batches >= 1 and d1.shape == d2.shape and np.array_equal(d1, d2), (prof, chunk, ndev)
             if prof in (1, 2):                                # the fused device route with an output sample format
-                d3 = run_dec(ShardedDecoder(ctxs=ctxs, pcm_format="<i2"), one, chunk)
+                d3 = run_dec(ShardedDecoder(ctxs=ctxs, min_frames_per_shard=16, pcm_format="<i2"), one, chunk)
                 assert np.array_equal(d3, run_dec(F.Decoder(pcm_format="<i2"), one, chunk))
     finally:
         for c in ctxs:

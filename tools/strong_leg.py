@@ -1,0 +1,257 @@
+"""Strong-scaling leg of bench.py: ONE stream, frames cut by contiguous range over the ranks (SURVEY 8e, configs[4] shape).
+
+Workload: a 64 s block of 96 kHz 8-channel f32 PCM (the tile configs[4]'s 8 h clip is built from) -- 3 000
+profile-0 frames / 3 199 profile-1 frames (hop 1920).  Rank g takes frames [gF/G, (g+1)F/G) (libfrad/encoder.py:46-50 fixes
+the frame geometry) and its PCM slice with the N - hop halo; there is no collective on the data path.
+
+  device   per rank: encode + decode kernels over its shard, device-resident, CUDA events; max over ranks
+  e2e      per rank: PCM slice (pinned) -> frad_p1_encode_raw / frad_p0_encode -> its part of the bitstream, copied into ONE
+           shared-memory segment at its byte offset (the host-side concatenation in rank order; profile 1: offsets from an
+           all-gather of part lengths, control plane only; profile 0: fixed-size payloads, written in place by the device)
+           -> every rank decodes its frame range out of that segment (lossy: the one halo frame in front first, for the
+           cross-fade seam of libfrad/decoder.py:28-46) -> f32 PCM straight into a shared PCM segment (the segments are
+           page-locked by every rank).  Wall clock over the steps, max over ranks.
+  check    rank 0 encodes and decodes the whole block alone (untimed) and compares: bitstream bytes, frame offsets and decoded
+           PCM must be identical to what the ranks assembled.
+"""
+import mmap
+import os
+import tempfile
+import time
+
+import numpy as np
+
+SR4, CH4, N, RATIO, BITS = 96000, 8, 2048, 16, 16
+HOP = N * (RATIO - 1) // RATIO
+LOSS = 1.25 ** 0 / 19 + 0.5
+SECONDS = 64
+
+
+def _pcm():
+    from frad_python_b200.testsignal import synth_pcm
+    tile = synth_pcm(4.0, SR4, CH4, 4)
+    return np.ascontiguousarray(np.tile(tile, (SECONDS // 4, 1)))
+
+
+class _Shared:
+    """A byte range shared by the ranks of one box: a file under /dev/shm (or /tmp when /dev/shm is too small) mapped by
+    every rank.  Rank 0 creates it, the others attach after a barrier."""
+
+    def __init__(self, name, nbytes, create):
+        nbytes = max(int(nbytes), 1)
+        base = "/dev/shm"
+        try:
+            st = os.statvfs(base)
+            if st.f_bavail * st.f_frsize < (1 << 30):
+                base = tempfile.gettempdir()
+        except OSError:
+            base = tempfile.gettempdir()
+        self.path = os.path.join(base, name)
+        if create:
+            with open(self.path, "wb") as f:
+                f.truncate(nbytes)
+        self.f = open(self.path, "r+b")
+        self.map = mmap.mmap(self.f.fileno(), nbytes)
+        self.buf = memoryview(self.map)
+
+    def close(self, unlink=False):
+        self.buf.release()
+        self.map.close()
+        self.f.close()
+        if unlink:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+
+
+def run(ctx, dist, rank, world, steps, tag):
+    """Returns the dict bench.py puts under "strong" (rank 0) or None (other ranks)."""
+    import torch
+    from frad_python_b200 import _abi, shard
+    from frad_python_b200.backend import hanning_in_overlap
+    L = _abi.lib()
+    pcm = _pcm()
+    nsamp = len(pcm)
+    out = {}
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            dist.barrier()
+
+    def maxr(x):
+        if dist is None:
+            return float(x)
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def gather_i64(x):
+        if dist is None:
+            return [int(x)]
+        t = torch.tensor([int(x)], device="cuda", dtype=torch.int64)
+        allv = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allv, t)
+        return [int(v.item()) for v in allv]
+
+    fade = np.ascontiguousarray(hanning_in_overlap(N - HOP), dtype=np.float64)
+    for prof in (1, 0):
+        hop = HOP if prof == 1 else N
+        F = shard.count_frames(nsamp, N, hop)
+        a, b = shard.frame_ranges(F, world)[rank]
+        nb = b - a
+        lo, hi = shard.pcm_slice((a, b), N, hop)
+        mine = ctx.pinned((hi - lo, CH4), np.float32)
+        mine[...] = pcm[lo:hi]
+        nscal = F * hop * CH4                                   # scalar PCM values of the whole block per pass
+
+        # ---- device-resident -------------------------------------------------------------------------------
+        d_pcm = ctx.dev(mine.nbytes); ctx.h2d(d_pcm, mine)
+        d_out = ctx.dev(nb * N * CH4 * 8)
+        if prof == 1:
+            d_q = ctx.dev(nb * N * CH4 * 4); d_tq = ctx.dev(nb * 27 * CH4 * 4)
+
+            def dev_step():
+                ctx.check(L.frad_p1_encode_dev(ctx.handle, d_pcm.ptr, _abi.F32, hop, nb, N, CH4, BITS, SR4, LOSS, _abi.PREC_REF,
+                                               d_q.ptr, d_tq.ptr, None))
+                ctx.check(L.frad_p1_decode_dev(ctx.handle, d_q.ptr, d_tq.ptr, None, nb, N, CH4, BITS, SR4, _abi.PREC_REF,
+                                               d_out.ptr, _abi.F64))
+        else:
+            stride = N * CH4 * 4
+            d_pay = ctx.dev(nb * stride); d_peak = ctx.dev(nb * 8)
+
+            def dev_step():
+                ctx.check(L.frad_p0_encode_dev(ctx.handle, d_pcm.ptr, _abi.F32, hop, nb, N, CH4, 32, 0, _abi.PREC_REF, d_pay.ptr,
+                                               stride, d_peak.ptr))
+                ctx.check(L.frad_p0_decode_dev(ctx.handle, d_pay.ptr, stride, nb, N, CH4, 32, 0, _abi.PREC_REF, d_out.ptr, _abi.F64))
+        for _ in range(3):
+            dev_step()
+        barrier()
+        ctx.event(20)
+        for _ in range(steps):
+            dev_step()
+        ctx.event(21)
+        barrier()
+        dev_ms = maxr(ctx.elapsed_ms(20, 21) / steps)
+        for d in (d_pcm, d_out) + ((d_q, d_tq) if prof == 1 else (d_pay, d_peak)):
+            d.free()
+
+        # ---- end to end with in-order concatenation in shared memory -----------------------------------------------
+        cut = hop
+        per_frame_cap = 2 * N * CH4 if prof == 1 else N * CH4 * 4
+        bit_cap = F * per_frame_cap
+        names = [f"fradb200_{tag}_{prof}_{k}" for k in ("bits", "offs", "pcm")]
+        sizes = [bit_cap, 8 * (F + 1), F * cut * CH4 * 4]
+        segs = []
+        if rank == 0:
+            segs = [_Shared(nm, sz, True) for nm, sz in zip(names, sizes)]
+        barrier()
+        if rank != 0:
+            segs = [_Shared(nm, sz, False) for nm, sz in zip(names, sizes)]
+        s_bits = np.frombuffer(segs[0].buf, np.uint8, bit_cap)
+        s_offs = np.frombuffer(segs[1].buf, np.uint64, F + 1)
+        s_pcm = np.frombuffer(segs[2].buf, np.float32, F * cut * CH4).reshape(F * cut, CH4)
+        # the shared segments are page-locked in every rank: results are copied from the device straight into the assembled
+        # stream / PCM (no staging copy) wherever the destination offset is known before the call
+        ctx.register(s_bits); ctx.register(s_pcm)
+        halo = 1 if (prof == 1 and a > 0) else 0
+        h_raw = ctx.pinned((max(nb, 1) * per_frame_cap,), np.uint8) if prof == 1 else None
+        h_off = ctx.pinned((nb + 1,), np.uint64)
+        h_ioff = ctx.pinned((nb + 2,), np.uint64)
+        h_halo = ctx.pinned((cut, CH4), np.float32)
+        h_tail = ctx.pinned((max(N - cut, 1), CH4), np.float64)
+        h_tail2 = ctx.pinned((max(N - cut, 1), CH4), np.float64)
+        h_st = ctx.pinned((nb + 1,), np.int32)
+        h_peak = ctx.pinned((max(nb, 1),), np.float64)
+        bits_ptr, pcm_ptr = s_bits.ctypes.data, s_pcm.ctypes.data
+
+        def e2e_step():
+            # encode my range
+            if prof == 1:
+                ctx.check(L.frad_p1_encode_raw(ctx.handle, mine.ctypes.data, _abi.F32, hop, nb, N, CH4, BITS, SR4, LOSS,
+                                               _abi.PREC_REF, 1, h_raw.ctypes.data, h_raw.size, h_off.ctypes.data))
+                mybytes = int(h_off[nb])
+                # concatenate in rank order: my part goes to the byte offset given by the parts before it
+                lens = gather_i64(mybytes)
+                base = sum(lens[:rank])
+                s_bits[base:base + mybytes] = h_raw[:mybytes]
+                s_offs[a:b + 1] = h_off[:nb + 1] + np.uint64(base)
+            else:
+                # fixed-size payloads: the offset of my part is known, the device writes it in place
+                ctx.check(L.frad_p0_encode(ctx.handle, mine.ctypes.data, _abi.F32, hop, nb, N, CH4, 32, 0, _abi.PREC_REF,
+                                           bits_ptr + a * per_frame_cap, per_frame_cap, h_peak.ctypes.data, None))
+                lens = [(y - x) * per_frame_cap for x, y in shard.frame_ranges(F, world)]
+                s_offs[a:b + 1] = np.arange(a, b + 1, dtype=np.uint64) * np.uint64(per_frame_cap)
+            if dist is not None:
+                dist.barrier()                                   # the whole bitstream is in place
+            # decode my range out of the assembled stream, PCM straight into the shared PCM at my sample offset
+            if prof == 1:
+                prev = None
+                if halo:                                         # the seam: the frame in front of my range gives the tail to fade against
+                    o0 = int(s_offs[a - 1])
+                    h_ioff[:2] = s_offs[a - 1:a + 1] - np.uint64(o0)
+                    ctx.check(L.frad_p1_decode_stream(ctx.handle, bits_ptr + o0, h_ioff.ctypes.data, 1, N, CH4, BITS, SR4,
+                                                      _abi.PREC_REF, 1, RATIO, fade.ctypes.data, None, h_halo.ctypes.data, _abi.F32,
+                                                      h_tail.ctypes.data, h_st.ctypes.data))
+                    prev = h_tail.ctypes.data
+                o0 = int(s_offs[a])
+                h_off[:nb + 1] = s_offs[a:b + 1] - np.uint64(o0)
+                ctx.check(L.frad_p1_decode_stream(ctx.handle, bits_ptr + o0, h_off.ctypes.data, nb, N, CH4, BITS, SR4,
+                                                  _abi.PREC_REF, 1, RATIO, fade.ctypes.data, prev, pcm_ptr + a * cut * CH4 * 4, _abi.F32,
+                                                  h_tail2.ctypes.data, h_st.ctypes.data))
+            else:
+                ctx.check(L.frad_p0_decode(ctx.handle, bits_ptr + a * per_frame_cap, per_frame_cap, nb, N, CH4, 32, 0, _abi.PREC_REF,
+                                           pcm_ptr + a * cut * CH4 * 4, _abi.F32))
+            return sum(lens)
+
+        e2e_step()
+        barrier()
+        esteps = max(2, min(steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(esteps):
+            total_bytes = e2e_step()
+        barrier()
+        e2e_ms = maxr(1e3 * (time.perf_counter() - t0) / esteps)
+
+        # ---- check against one GPU doing the whole block ---------------------------------------------------------------
+        same = None
+        if rank == 0:
+            whole = ctx.pinned(pcm.shape, np.float32); whole[...] = pcm
+            if prof == 1:
+                w_raw = np.empty(bit_cap, np.uint8); w_off = np.zeros(F + 1, np.uint64)
+                ctx.check(L.frad_p1_encode_raw(ctx.handle, whole.ctypes.data, _abi.F32, hop, F, N, CH4, BITS, SR4, LOSS,
+                                               _abi.PREC_REF, 1, w_raw.ctypes.data, bit_cap, w_off.ctypes.data))
+                tot = int(w_off[F])
+                w_pcm = np.empty((F * cut, CH4), np.float32); w_tail = np.empty((N - cut, CH4), np.float64)
+                w_st = np.zeros(F, np.int32)
+                ctx.check(L.frad_p1_decode_stream(ctx.handle, w_raw.ctypes.data, w_off.ctypes.data, F, N, CH4, BITS, SR4,
+                                                  _abi.PREC_REF, 1, RATIO, fade.ctypes.data, None, w_pcm.ctypes.data, _abi.F32,
+                                                  w_tail.ctypes.data, w_st.ctypes.data))
+                same = bool(tot == total_bytes and np.array_equal(w_off, s_offs) and np.array_equal(w_raw[:tot], s_bits[:tot])
+                            and np.array_equal(w_pcm, s_pcm))
+            else:
+                w_pay = np.empty((F, per_frame_cap), np.uint8); w_peak = np.zeros(F)
+                ctx.check(L.frad_p0_encode(ctx.handle, whole.ctypes.data, _abi.F32, hop, F, N, CH4, 32, 0, _abi.PREC_REF,
+                                           w_pay.ctypes.data, per_frame_cap, w_peak.ctypes.data, None))
+                w_pcm = np.empty((F, N, CH4), np.float32)
+                ctx.check(L.frad_p0_decode(ctx.handle, w_pay.ctypes.data, per_frame_cap, F, N, CH4, 32, 0, _abi.PREC_REF,
+                                           w_pcm.ctypes.data, _abi.F32))
+                same = bool(np.array_equal(w_pay.ravel(), s_bits[:F * per_frame_cap]) and np.array_equal(w_pcm.reshape(-1, CH4), s_pcm))
+        barrier()
+        ctx.unregister(s_bits); ctx.unregister(s_pcm)
+        del s_bits, s_offs, s_pcm
+        for s in segs:
+            s.close(unlink=(rank == 0))
+        out["p%d" % prof] = {
+            "frames": F, "frames_per_rank": [y - x for x, y in shard.frame_ranges(F, world)],
+            "device": {"value": nscal / (dev_ms * 1e-3) / 1e6, "unit": "MSamples/s", "ms": dev_ms},
+            "e2e": {"value": nscal / (e2e_ms * 1e-3) / 1e6, "unit": "MSamples/s", "ms": e2e_ms, "bitstream_bytes": int(total_bytes)},
+            "identical_to_one_gpu": same,
+        }
+    if rank != 0:
+        return None
+    out["scaling"] = "strong"
+    out["workload"] = ("configs[4] shape: one 64 s block of 96 kHz 8-channel f32 PCM (the tile the 8 h clip is built from), "
+                       "frames cut by contiguous range over the ranks; bitstream and PCM concatenated in rank order in shared memory")
+    return out
