@@ -5,73 +5,18 @@
 // block-wide barriers are the two around the cooperative, fully coalesced 16-byte global loads /
 // stores of the interleaved [n][c] / [k][c] layouts.  The profile pro/epilogues run per warp on the
 // sequence while it sits in shared memory:
-//   encode  PCM f32 -> DCT-II -> profile 0: big/little-endian f32 payload + per-frame peak
-//                             -> profile 1: band energies (register partials + transposed warp
-//                                reduction), thresholds, divisor ramps, power-law quantiser (f32 fast
-//                                branch with an exact f64 re-evaluation next to rounding boundaries)
-//   decode  payload / quantised ints -> dequantise -> DCT-III -> PCM (f64 or f32 out)
+//   decode  payload / quantised ints -> dequantise -> DCT-III -> PCM (f64 or f32 out)        (this file)
+//   encode  PCM f32 -> DCT-II -> profile 0 payload / profile 1 quantised ints               (enc2048.cu)
 // The real-FFT split and the DCT twiddles are applied pairwise (k, M-k): one pair yields
 // X[k], X[N-k], X[M-k], X[M+k] from two complex multiplies (see DESIGN.md "Transform").
 // Reference lines: fourier/profile0.py:21-30,63-69; fourier/profile1.py:21-40,65-77;
 // fourier/tools/p1tools.py:18-44.
 #include <cstdio>
 #include <cstdlib>
-#include "plan.cuh"
-#include "fft32.cuh"
-#include "profiles.cuh"
+#include "tile2048.cuh"
 
 namespace {
 
-#ifndef FRAD_FW
-#define FRAD_FW 4
-#endif
-#ifndef FRAD_MINB
-#define FRAD_MINB 4
-#endif
-#ifndef FRAD_ENC_EARLY
-#define FRAD_ENC_EARLY 0          // measured: requesting the next tile before the store phase costs the encoder 3 %
-#endif
-#ifndef FRAD_DEC_PRELOAD
-#define FRAD_DEC_PRELOAD 1
-#endif
-#ifndef FRAD_ENC_F32THR
-#define FRAD_ENC_F32THR 1
-#endif
-constexpr int FN = 2048, FM = 1024, FW = FRAD_FW;          // frame, half, warps per CTA
-constexpr int SEQ_CPX = 1056;                        // padded complex slots per warp buffer
-constexpr int DQ_TAB = 1024;                         // f32 dequantiser table entries (|q| < DQ_TAB)
-constexpr int DQ_TAB64 = FRAD_DQ_LEN;                // f64 table (global memory, frad_ensure_dq64)
-constexpr int DQ_SMEM64 = 256;                       // head of the f64 table kept in shared memory
-#define FRAD_RSQRT2 0.70710678118654752440
-
-__device__ __forceinline__ int zword(int n) {        // word index (units of T) of sample n inside the z layout
-  const int nn = (n & 1) ? (2 * FN - 1 - n) : n;
-  return 2 * padc(nn >> 2) + ((nn >> 1) & 1);
-}
-// f32 time-domain staging: 32-element rows rotated by (row & 3) -- enough to separate the four rows a stride-4 scatter
-// touches, and unchanged by the 128 o offsets of the FFT output order (immediate-offset stores)
-__device__ __forceinline__ int swz(int n) { return (n & ~31) | ((n + ((n >> 5) & 3)) & 31); }
-// time-domain staging swizzle by element size: rows of 128 bytes (32 floats / 16 doubles) rotated by the row number, so
-// that the stride-4 scatter after the FFT and the stride-1/2/4 gathers of the store are both conflict-free per wavefront
-template <typename T> __device__ __forceinline__ int swzT(int n) {
-  if constexpr (sizeof(T) == 8) return (n & ~15) | ((n + (n >> 4)) & 15);
-  else return swz(n);
-}
-
-template <typename T> __device__ __forceinline__ T shfl_t(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-
-struct smem_tail {
-  int lo[FRAD_NBANDS + 1];
-  double thr[FW][FRAD_NBANDS + 1];
-  double inv_ns[FRAD_NBANDS + 1];                     // 1 / (band width x scale)
-  float4 bp[FW][FRAD_NBANDS + 1];                     // per band: ramp end points (pre-scaled), lo, hi as floats
-  uint8_t bidx[FN];                                   // band index of every bin (FRAD_NBANDS - 1 = "past the ramps")
-  float part[FW][64];
-  // per-warp band energy partials.  Lane l sums the 64 contiguous bins [64 l, 64 l + 64); the (lane, band) pairs that occur
-  // form a staircase (bands do not decrease with the lane), so pair (l, b) has the slot b + l of its own: 59 floats per
-  // warp instead of a [band][lane] matrix.  The small tail lets the SM take a smaller shared-memory carve-out (4 CTAs
-  // still fit) and the L1 that is left holds the twiddle tables.
-};
 
 // Decoder tails.  PAIR (stereo tiling, CT == 2): instead of a band index per bin the CTA keeps one word per pair of
 // neighbouring bins (2p, 2p + 1) -- j0 | band(2p) << 16 | band(2p + 1) << 24 with j0 = 2p - lo[band(2p)] -- because the
@@ -122,501 +67,6 @@ __device__ __forceinline__ void build_ptab(TAIL* tail, const band_table* bt, int
     tail->ptab[p] = (uint32_t)(2 * p - tail->lo[bb[0]]) | ((uint32_t)bb[0] << 16) | ((uint32_t)bb[1] << 24);
   }
 }
-// ---- cooperative staging helpers ----------------------------------------------------------------
-// Frame words (32-bit) are interleaved [i][c].  A tile is a set of whole sequences that fit the CTA's
-// FW warps; CT selects how it is cut (all variants move 16 bytes per thread per step, fully coalesced):
-//   CT == 1  mono: FW frames per tile, a float4 is 4 consecutive samples of the one channel
-//   CT == 2  stereo: FW/2 frames per tile, a float4 is 2 samples x 2 channels
-//   CT == 4  C % 4 == 0: one frame x one group of 4 channels per tile, a float4 is 1 sample x 4 channels
-//   CT == 0  any C <= FW: FW/C frames per tile, element index split by a run-time division
-struct tile_map { int fpc, groups, ntiles; };
-
-template <int CT>
-__host__ __device__ inline tile_map make_tiles(int B, int C) {
-  tile_map t;
-  if (CT == 4) { t.fpc = 1; t.groups = C / 4; t.ntiles = B * t.groups; return t; }
-  t.fpc = FW / C; if (t.fpc < 1) t.fpc = 1;
-  t.groups = 1;
-  t.ntiles = (B + t.fpc - 1) / t.fpc;
-  return t;
-}
-
-template <int CT> __device__ __forceinline__ int vec_count(int C) { return (CT == 4) ? FN : FN * C / 4; }
-// 32-bit word offset inside the frame of vector step e4 (group g of 4 channels for CT == 4)
-template <int CT> __device__ __forceinline__ int vec_word(int e4, int C, int g) { return (CT == 4) ? e4 * C + 4 * g : 4 * e4; }
-// element j (0..3) of vector step e4 -> sample / bin index i and sequence slot s inside the tile
-template <int CT> __device__ __forceinline__ void vec_elem(int e4, int j, int C, int f, int& i, int& s) {
-  if (CT == 2) { i = 2 * e4 + (j >> 1); s = 2 * f + (j & 1); }
-  else if (CT == 1) { i = 4 * e4 + j; s = f; }
-  else if (CT == 4) { i = e4; s = j; }
-  else { const int e = 4 * e4 + j; i = e / C; s = f * C + (e - i * C); }
-}
-
-template <int CT, int STRIDE_WORDS, typename POS>
-__device__ __forceinline__ void scatter_frame(const uint32_t* __restrict__ frame, uint32_t* seq_base, int C, int f, int g,
-                                              int tid, POS pos) {
-  const int cnt = vec_count<CT>(C);
-#pragma unroll 4
-  for (int e4 = tid; e4 < cnt; e4 += FW * 32) {
-    const uint4 x = __ldg((const uint4*)(frame + vec_word<CT>(e4, C, g)));
-    const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      int i, sq;
-      vec_elem<CT>(e4, j, C, f, i, sq);
-      (seq_base + (size_t)sq * STRIDE_WORDS)[pos(i)] = xs[j];
-    }
-  }
-}
-
-// streaming 16-byte load: read-only path, no L1 allocation (the small L1 left beside ~210 KB of shared memory is kept
-// for the twiddle tables, which every sequence re-reads)
-__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
-  uint4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-  return v;
-}
-
-// Whole-tile staging: every 16-byte load of the tile (16 per thread for FW = 4) is issued before the first
-// scatter, so one global-memory latency is exposed per tile instead of one per unrolled group of four.
-// src(f) returns the first 32-bit word of frame f of the tile.
-template <int CT, int STRIDE_WORDS, typename SRC, typename POS>
-__device__ __forceinline__ void stage_tile(SRC src, uint32_t* seq_base, int C, int nf, int g, int tid, POS pos) {
-  if constexpr (CT == 0) {
-    for (int f = 0; f < nf; f++) scatter_frame<CT, STRIDE_WORDS>(src(f), seq_base, C, f, g, tid, pos);
-  } else {
-    constexpr int FPT = (CT == 4) ? 1 : FW / CT;                                  // frames per tile
-    constexpr int VPF = ((CT == 4) ? FN : FN * CT / 4) / (FW * 32);               // vector steps per thread and frame
-    static_assert(VPF * FW * 32 == ((CT == 4) ? FN : FN * CT / 4), "tile does not divide evenly");
-    uint4 x[FPT * VPF];
-#pragma unroll
-    for (int f = 0; f < FPT; f++) {
-      const uint32_t* frame = src(f < nf ? f : nf - 1) + vec_word<CT>(tid, C, g);   // a short tile re-reads its last frame
-#pragma unroll
-      for (int i = 0; i < VPF; i++) x[f * VPF + i] = ldg_stream((const uint4*)(frame + vec_word<CT>(i * FW * 32, C, 0)));
-    }
-#pragma unroll
-    for (int f = 0; f < FPT; f++) {
-      if (f < nf) {
-#pragma unroll
-        for (int i = 0; i < VPF; i++) {
-          const uint4 xv = x[f * VPF + i];
-          const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            int ii, sq;
-            vec_elem<CT>(tid + i * FW * 32, j, C, f, ii, sq);
-            (seq_base + (size_t)sq * STRIDE_WORDS)[pos(ii)] = xs[j];
-          }
-        }
-      }
-    }
-  }
-}
-
-// Decoder staging.  The 16-byte loads of a tile and their conversion are two steps, so that the kernel can issue the
-// loads of its NEXT tile before it stores the current one (their latency is hidden behind the store phase); the words wait
-// in registers.  Every word is converted on the way into shared memory (profile-0 unpack or profile-1 dequantiser x ramp,
-// `cvt4`) and stored as T at index k of its sequence -- the raw words never touch shared memory.  Neighbouring bins of one
-// sequence are stored as one 2 x T vector (conflict-free).
-template <int CT> struct tile_regs {
-  static constexpr int FPT = (CT == 4) ? 1 : ((CT == 0) ? 1 : FW / CT);
-  static constexpr int VPF = (CT == 0) ? 1 : ((CT == 4) ? FN : FN * CT / 4) / (FW * 32);
-  static constexpr int NX = FPT * VPF;
-};
-template <int CT, typename SRC>
-__device__ __forceinline__ void load_tile(SRC src, int C, int nf, int g, int tid, uint4* x) {
-  constexpr int FPT = tile_regs<CT>::FPT, VPF = tile_regs<CT>::VPF;
-#pragma unroll
-  for (int f = 0; f < FPT; f++) {
-    const uint32_t* frame = src(f < nf ? f : nf - 1) + vec_word<CT>(tid, C, g);       // a short tile re-reads its last frame
-#pragma unroll
-    for (int i = 0; i < VPF; i++) x[f * VPF + i] = ldg_stream((const uint4*)(frame + vec_word<CT>(i * FW * 32, C, 0)));
-  }
-}
-// encoder side: the loaded words go to position pos(i) of their sequence unchanged
-template <int CT, int STRIDE_WORDS, typename POS>
-__device__ __forceinline__ void scatter_tile(const uint4* x, uint32_t* seq_base, int C, int nf, int tid, POS pos) {
-  constexpr int FPT = tile_regs<CT>::FPT, VPF = tile_regs<CT>::VPF;
-#pragma unroll
-  for (int f = 0; f < FPT; f++) {
-    if (f < nf) {
-#pragma unroll
-      for (int i = 0; i < VPF; i++) {
-        const uint4 xv = x[f * VPF + i];
-        const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          int ii, sq;
-          vec_elem<CT>(tid + i * FW * 32, j, C, f, ii, sq);
-          (seq_base + (size_t)sq * STRIDE_WORDS)[pos(ii)] = xs[j];
-        }
-      }
-    }
-  }
-}
-template <int CT, int STRIDE_T, typename T, typename CVT4>
-__device__ __forceinline__ void convert_tile(const uint4* x, T* seq_base, int C, int nf, int tid, CVT4 cvt4) {
-  typedef typename vec2<T>::type V2;
-  constexpr int FPT = tile_regs<CT>::FPT, VPF = tile_regs<CT>::VPF;
-#pragma unroll
-  for (int f = 0; f < FPT; f++) {
-    if (f < nf) {
-#pragma unroll
-      for (int i = 0; i < VPF; i++) {
-        const uint4 xv = x[f * VPF + i];
-        const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w};
-        const int e4 = tid + i * FW * 32;
-        T v[4];
-        int ks[4], sqs[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) vec_elem<CT>(e4, j, C, f, ks[j], sqs[j]);
-        cvt4(xs, ks, sqs, v);
-        if constexpr (CT == 2) {            // (k, c0) (k, c1) (k+1, c0) (k+1, c1): one pair of bins per channel
-          *(V2*)(seq_base + (size_t)sqs[0] * STRIDE_T + ks[0]) = mk2<T>(v[0], v[2]);
-          *(V2*)(seq_base + (size_t)sqs[1] * STRIDE_T + ks[1]) = mk2<T>(v[1], v[3]);
-        } else if constexpr (CT == 1) {     // four consecutive bins of the one channel
-          *(V2*)(seq_base + (size_t)sqs[0] * STRIDE_T + ks[0]) = mk2<T>(v[0], v[1]);
-          *(V2*)(seq_base + (size_t)sqs[2] * STRIDE_T + ks[2]) = mk2<T>(v[2], v[3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; j++) (seq_base + (size_t)sqs[j] * STRIDE_T)[ks[j]] = v[j];
-        }
-      }
-    }
-  }
-}
-// run-time channel count (CT == 0): plain loop, loads and conversion together
-template <int STRIDE_T, typename T, typename SRC, typename CVT>
-__device__ __forceinline__ void stage_convert_any(SRC src, T* seq_base, int C, int nf, int tid, CVT cvt) {
-  for (int f = 0; f < nf; f++) {
-    const uint32_t* frame = src(f);
-    const int cnt = vec_count<0>(C);
-#pragma unroll 4
-    for (int e4 = tid; e4 < cnt; e4 += FW * 32) {
-      const uint4 x = ldg_stream((const uint4*)(frame + vec_word<0>(e4, C, 0)));
-      const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        int k, sq;
-        vec_elem<0>(e4, j, C, f, k, sq);
-        (seq_base + (size_t)sq * STRIDE_T)[k] = cvt(xs[j], k, sq);
-      }
-    }
-  }
-}
-
-template <int CT, int STRIDE_WORDS, typename W, typename O, typename POS, typename CVT>
-__device__ __forceinline__ void gather4(const W* seq_base, int C, int f, int e4, POS pos, CVT cvt, O* o4) {
-#pragma unroll
-  for (int j = 0; j < 4; j++) {
-    int i, sq;
-    vec_elem<CT>(e4, j, C, f, i, sq);
-    o4[j] = cvt((seq_base + (size_t)sq * STRIDE_WORDS)[pos(i)]);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// encode
-// ------------------------------------------------------------------------------------------------
-// exact quantiser of one coefficient (the f64 formula of profile1.py:31-36 with np.linspace's ramp)
-__device__ __noinline__ int quant_exact(float x, int j, double t0, double step, double scale) {
-  const double div = __dadd_rn(__dmul_rn((double)j, step), t0);
-  if (div == 0.0) return 0;
-  const double yy = fabs(((double)x / div) * scale);
-  const double rr = rint(sqrt(yy * sqrt(yy)));
-  if (!(rr == rr)) return 0;
-  const int m = (rr >= 2147483647.0) ? 2147483647 : (int)rr;
-  return (x < 0.0f) ? -m : m;
-}
-
-__device__ __noinline__ int tq_exact(double thr, double log_base) {
-  const double vv = log(fmax(thr, 1.0)) / log_base;
-  const double d = (vv > 0.0) ? vv * cbrt(vv) : 0.0;                     // v^(4/3)
-  return sat_i32(rint(d));
-}
-
-template <int PROFILE, int CT>
-__global__ void __launch_bounds__(FW * 32, FRAD_MINB) enc2048_kernel(enc_params P, plan_dev pl, const float2* __restrict__ tw32,
-                                                             int force_exact) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2* seq_all = (float2*)smem_raw;
-  smem_tail* tail = (smem_tail*)(smem_raw + (size_t)FW * SEQ_CPX * sizeof(float2));
-  const int C = (CT == 1 || CT == 2) ? CT : P.C;
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const tile_map tm = make_tiles<CT>(P.B, C);
-  const float* pcm = (const float*)P.pcm;
-  const float2* cfh = (const float2*)pl.cfh;
-  const float2* dfh = (const float2*)pl.dfh;
-  if (PROFILE != 0) {
-    build_bidx(tail, P.bt, tid);                            // (its barrier makes lo[] visible)
-    if (tid < FRAD_NBANDS) {
-      const int n = tail->lo[tid + 1] - tail->lo[tid];
-      tail->inv_ns[tid] = (n > 0) ? 1.0 / ((double)n * P.scale) : 0.0;
-    }
-  }
-  const int words_per_frame = FN * C;
-
-  // the PCM words of a tile travel through registers; those of the next tile are requested before this one is stored
-  uint4 x[tile_regs<CT>::NX];
-  auto request_tile = [&](int t) {
-    if (CT == 0) return;
-    if (t >= tm.ntiles) t = tm.ntiles - 1;                // always overwrite x (nothing stale stays alive across the transform)
-    const int tb0 = (CT == 4) ? t / tm.groups : t * tm.fpc;
-    const int tgrp = (CT == 4) ? t - tb0 * tm.groups : 0;
-    load_tile<CT>([&](int f) { return (const uint32_t*)(pcm + (size_t)(tb0 + f) * P.hop * C); }, C, min(tm.fpc, P.B - tb0), tgrp, tid, x);
-  };
-  constexpr bool EARLY = (CT != 0) && FRAD_ENC_EARLY;
-  if (EARLY) request_tile(blockIdx.x);
-
-  for (int tile = blockIdx.x; tile < tm.ntiles; tile += gridDim.x) {
-    const int b0 = (CT == 4) ? tile / tm.groups : tile * tm.fpc;
-    const int grp = (CT == 4) ? tile - b0 * tm.groups : 0;
-    const int nf = min(tm.fpc, P.B - b0);
-    const int nseq = (CT == 4) ? 4 : nf * C;              // sequences (= busy warps) in this tile
-    __syncthreads();                                      // previous tile fully stored before restaging
-    if constexpr (CT == 0) {
-      stage_tile<CT, SEQ_CPX * 2>([&](int f) { return (const uint32_t*)(pcm + (size_t)(b0 + f) * P.hop * C); }, (uint32_t*)seq_all, C, nf,
-                                  grp, tid, [](int n) { return zword(n); });
-    } else {
-      if (!EARLY) request_tile(tile);
-      scatter_tile<CT, SEQ_CPX * 2>(x, (uint32_t*)seq_all, C, nf, tid, [](int n) { return zword(n); });
-    }
-    __syncthreads();
-    {   // pull the next tile of this CTA towards L2 while the current one is transformed
-      const int nt = tile + gridDim.x;
-      if (nt < tm.ntiles) {
-        const int nb0 = (CT == 4) ? nt / tm.groups : nt * tm.fpc;
-        const int nnf = min(tm.fpc, P.B - nb0);
-        const char* base = (const char*)(pcm + (size_t)nb0 * P.hop * C);
-        const size_t bytes = (size_t)nnf * words_per_frame * 4;
-        for (size_t o = (size_t)tid * 128; o < bytes; o += (size_t)FW * 32 * 128)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(base + o));
-      }
-    }
-    if (w < nseq) {
-      const int f = (CT == 4) ? 0 : w / C, c = (CT == 4) ? 4 * grp + w : w - f * C, b = b0 + f;
-      float2* buf = seq_all + (size_t)w * SEQ_CPX;
-      float* X = (float*)buf;
-      float2 v[32];
-#pragma unroll
-      for (int i = 0; i < 32; i++) v[i] = buf[lane + 33 * i];
-      __syncwarp();
-      fft1024_warp<float, false>(v, buf, lane, tw32);
-      // ---- pairwise real-FFT split + DCT twiddle: (k, M-k) -> X[k], X[N-k], X[M-k], X[M+k] ----
-      const int partner = (32 - lane) & 31;
-      const bool swap_out = (PROFILE == 0) && !P.le;
-      float mx = 0.0f;
-      float* part = tail->part[w] + lane;                                 // slot of (lane, band): part[band]
-      if (PROFILE != 0) { tail->part[w][lane] = 0.0f; tail->part[w][lane + 32] = 0.0f; }
-      auto emit = [&](int k, float val) {
-        if (PROFILE == 0) {
-          mx = fmaxf(mx, fabsf(val));
-          if (swap_out) val = __uint_as_float(__byte_perm(__float_as_uint(val), 0, 0x0123));
-        }
-        X[k] = val;
-      };
-      auto do_pair = [&](int k, float2 zk, float2 zm, bool first, bool self) {   // zm = conj(Z[M-k])
-        const float2 A = cadd(zk, zm), D = csub(zk, zm);
-        const float2 Bv = make_float2(D.y, -D.x);
-        const float2 Pk = cmul(__ldg(cfh + k), A), Qk = cmul(__ldg(dfh + k), Bv);
-        const float2 y = cadd(Pk, Qk), t = csub(Pk, Qk);
-        emit(k, y.x);
-        if (!first) emit(FN - k, -y.y);
-        if (!self) {                                                     // k == M - k: the same two bins again
-          emit(FM - k, (t.x - t.y) * (float)FRAD_RSQRT2);
-          if (!first) emit(FM + k, (t.x + t.y) * (float)FRAD_RSQRT2);
-        }
-      };
-#pragma unroll
-      for (int o = 0; o < 16; o++) {
-        const float2 snd = (lane == 0) ? v[(32 - o) & 31] : v[31 - o];
-        float2 zm;
-        zm.x = __shfl_sync(0xffffffffu, snd.x, partner);
-        zm.y = -__shfl_sync(0xffffffffu, snd.y, partner);
-        do_pair(lane + 32 * o, v[o], zm, (o == 0) && (lane == 0), false);
-      }
-      if (lane == 0) do_pair(FM / 2, v[16], cconj(v[16]), false, true);          // self-paired bin k = 512
-      if (PROFILE == 0) {
-        if (P.peak) {
-#pragma unroll
-          for (int s = 16; s > 0; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
-          if (lane == 0) atomicMax((unsigned long long*)&P.peak[b], (unsigned long long)__double_as_longlong((double)mx));
-        }
-      } else {
-        __syncwarp();
-        // ---- band energies of the scaled spectrum.  Lane l owns the bins [64 l, 64 l + 64) and walks them in the rotated
-        //      order r = (j + l) & 63 (bank (j + l) mod 32: conflict-free).  Its band index rises, drops once at the
-        //      wrap-around and rises again, so every band is left at most once inside the loop (plain store of the
-        //      running sum into the pair's slot); only the band the walk ends in may already hold the sum of the walk's
-        //      first bins, hence the add at the end.  Lane b then adds the slots of the lanes that reach into band b ----
-        {
-          const int base = 64 * lane;
-          float acc = 0.0f;
-          int cur = tail->bidx[base + lane];
-#pragma unroll 1
-          for (int j0 = 0; j0 < 64; j0 += 8) {
-            float xv[8];
-            int bi[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) { const int r = (j0 + u + lane) & 63; xv[u] = X[base + r]; bi[u] = tail->bidx[base + r]; }
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-              if (bi[u] != cur) { part[cur] = acc; acc = 0.0f; cur = bi[u]; }
-              acc = fmaf(xv[u], xv[u], acc);
-            }
-          }
-          part[cur] += acc;
-          __syncwarp();
-        }
-        const float scalef = (float)P.scale;
-        const float inv_log_base_f = (float)(1.0 / 0.30685281944005469058);   // 1 / ln(e/2)
-        float tot = 0.0f;
-        if (lane < FRAD_NBANDS) {
-          const int blo = tail->lo[lane], bhi = tail->lo[lane + 1];
-          if (bhi > blo) {
-            const float* row = tail->part[w] + lane;
-            for (int l = blo >> 6; l <= (bhi - 1) >> 6; l++) tot += row[l];
-          }
-          tot *= scalef * scalef;
-        }
-        int cnt = 1;
-        if (lane < FRAD_NBANDS) cnt = tail->lo[lane + 1] - tail->lo[lane];
-        const unsigned empty = __ballot_sync(0xffffffffu, cnt <= 0);
-        const int first_empty = empty ? (__ffs(empty) - 1) : 32;
-        double thr = 0.0;
-        if (lane < FRAD_NBANDS && lane < first_empty) {
-          // f32 like the reference for f32 spectra: np.sqrt(np.mean(x**2)) ** 0.8 on float32 (p1tools.py:32)
-          const float level = powf(sqrtf(tot / (float)cnt), 0.8f);
-          thr = fmax((double)level, P.bt->ath[lane]) * P.loss;
-        }
-        if (lane <= FRAD_NBANDS) tail->thr[w][lane] = thr;             // entry 27 = 0
-        if (lane < FRAD_NBANDS) {
-          // threshold integer round((ln(max(thr, 1)) / ln(e/2))^(4/3)) (profile1.py:38-40).  f32 first: the relative error of
-          // logf / cbrtf and of the operand rounding is < 1e-6, so the integer is already decided unless d lies within
-          // 1e-3 (1 + d) of a rounding tie (or is huge) -- only then the f64 formula runs
-          int tqi = 0;
-          bool exact = !FRAD_ENC_F32THR;
-          if (FRAD_ENC_F32THR && thr > 1.0) {
-            const float lv = logf((float)thr) * inv_log_base_f;
-            const float df = lv * cbrtf(lv);
-            const float rf = rintf(df);
-            exact = !(fabsf(fabsf(df - rf) - 0.5f) > 1.0e-3f * (1.0f + df) && df < 1.0e6f);
-            tqi = (int)rf;
-          }
-          if (exact) tqi = tq_exact(thr, P.bt->log_base);
-          P.tq[((size_t)b * FRAD_NBANDS + lane) * C + c] = tqi;
-        }
-        if constexpr (PROFILE == 2) {
-          // profile 2: TNS works on the whole masked spectrum in f64 (profile2.py:32) -- a separate kernel (tns_encode_kernel,
-          // transform.cu) takes over from here.  It gets the spectrum (stored below as float bits in the q array) and
-          // this sequence's thresholds, [b][c][28] doubles.
-          if (lane <= FRAD_NBANDS) P.tns_scratch[((size_t)b * C + c) * (FRAD_NBANDS + 1) + lane] = thr;
-        } else {
-        // per-band ramp parameters, one band per lane: the divisor over the scale as a convex combination
-        //   div / scale = t0s (hi - k) + t1s (k - lo),  t0s = thr[b] / (n scale), t1s = thr[b+1] / (n scale)
-        {
-          const double thr_next = __shfl_down_sync(0xffffffffu, thr, 1);
-          if (lane <= FRAD_NBANDS) {
-            float4 bpv = make_float4(1.0e30f, 1.0e30f, -1.0f, 2.0f * FN);  // huge divisor: bins past the last ramp quantise to 0
-            if (lane < FRAD_NBANDS - 1 && cnt > 0) {
-#if FRAD_ENC_F32THR
-              const double ins = tail->inv_ns[lane];                      // 1 / (n scale)
-              bpv = make_float4((float)(thr * ins), (float)(thr_next * ins), (float)tail->lo[lane], (float)tail->lo[lane + 1]);
-#else
-              const double ns = (double)cnt * P.scale;
-              bpv = make_float4((float)(thr / ns), (float)(thr_next / ns), (float)tail->lo[lane], (float)tail->lo[lane + 1]);
-#endif
-            }
-            tail->bp[w][lane] = bpv;
-          }
-        }
-        __syncwarp();
-        // ---- quantise: one flat pass over the sequence, in place (float -> int32) ----
-        // Eight coefficients per lane are evaluated branch-free (independent dependency chains for the
-        // MUFU / LDS latencies); the rare ones that sit next to a rounding tie are redone exactly afterwards.
-        int* Q = (int*)X;
-        const float4* bpw = tail->bp[w];
-#pragma unroll 1
-        for (int kbase = lane; kbase < FN; kbase += 256) {
-          float xs[8];
-          int ms[8];
-          bool allok = true;
-          const float kb = (float)kbase;
-#pragma unroll
-          for (int u = 0; u < 8; u++) {
-            const int k = kbase + 32 * u;
-            const float kf = kb + (float)(32 * u);
-            const float x = X[k];
-            const float4 bpv = bpw[tail->bidx[k]];
-            const float dv = fmaf(kf - bpv.z, bpv.y, (bpv.w - kf) * bpv.x);
-            float rc, s, v;
-            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(dv));
-            const float y = fabsf(x) * rc;
-            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(y));
-            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(v) : "f"(y * s));
-            // signed magic-number rounding: nearest-even integer of +-v for v < 2^22, read from the mantissa
-            const float big = copysignf(v, x) + 12582912.0f;
-            const float r = big - 12582912.0f;
-            // error budget of the f32 branch <= 6e-7 relative: redo exactly when closer than 1e-6 v
-            // to a tie.  Inf / NaN (zero divisor) and v >= 5e5 fail this test by themselves.
-            allok = allok && (fmaf(1.0e-6f, v, fabsf(fabsf(v) - fabsf(r))) < 0.4999999f);
-            ms[u] = __float_as_int(big) - 0x4B400000;
-            xs[u] = x;
-          }
-          unsigned amb = 0;
-          if (!allok || force_exact) {
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-              const int k = kbase + 32 * u;
-              const float kf = kb + (float)(32 * u);
-              const float4 bpv = bpw[tail->bidx[k]];
-              const float dv = fmaf(kf - bpv.z, bpv.y, (bpv.w - kf) * bpv.x);
-              float rc, s, v;
-              asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(dv));
-              const float y = fabsf(xs[u]) * rc;
-              asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(y));
-              asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(v) : "f"(y * s));
-              const float r = (v + 12582912.0f) - 12582912.0f;
-              if (!(fmaf(1.0e-6f, v, fabsf(v - r)) < 0.4999999f)) amb |= 1u << u;
-            }
-          }
-          if (force_exact) amb = 0xffu;
-#pragma unroll
-          for (int u = 0; u < 8; u++) Q[kbase + 32 * u] = ms[u];
-          if (amb) {
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-              if ((amb >> u) & 1u) {
-                const int k = kbase + 32 * u;
-                const int bnd = tail->bidx[k];
-                if (bnd != FRAD_NBANDS - 1) {
-                  const int lo = tail->lo[bnd], n = tail->lo[bnd + 1] - lo;
-                  const double t0 = tail->thr[w][bnd], t1 = tail->thr[w][bnd + 1];
-                  Q[k] = quant_exact(xs[u], k - lo, t0, (t1 - t0) / (double)n, P.scale);
-                }
-              }
-            }
-          }
-        }
-        }   // PROFILE == 1
-      }
-    }
-    __syncthreads();
-    if (EARLY) request_tile(tile + gridDim.x);            // in flight while this tile is stored
-    // ---- cooperative, coalesced store: word e = k*C + c of frame f <- seq[f*C + c][k] ----
-    for (int f = 0; f < nf; f++) {
-      uint32_t* dst = (PROFILE == 0) ? (uint32_t*)(P.payload + (size_t)(b0 + f) * P.payload_stride)
-                                     : (uint32_t*)(P.q + (size_t)(b0 + f) * words_per_frame);
-      for (int e4 = tid; e4 < vec_count<CT>(C); e4 += FW * 32) {
-        uint32_t o4[4];
-        gather4<CT, SEQ_CPX * 2>((const uint32_t*)seq_all, C, f, e4, [](int k) { return k; }, [](uint32_t u) { return u; }, o4);
-        *(uint4*)(dst + vec_word<CT>(e4, C, grp)) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
-      }
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
 // decode
 // ------------------------------------------------------------------------------------------------
@@ -1068,19 +518,6 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
   }
 }
 
-template <typename K>
-int launch_cfg(frad_ctx* ctx, K kernel, size_t smem, int ntiles, int* grid) {
-  FRAD_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 0;
-  FRAD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, FW * 32, smem));
-  if (per_sm < 1) return frad_fail(ctx, FRAD_E_UNSUPPORTED, "fast path does not fit on this device");
-  if (getenv("FRAD_DEBUG_LAUNCH")) fprintf(stderr, "[fradb200] fast2048 launch: smem %zu B, %d CTAs/SM, %d tiles\n", smem, per_sm, ntiles);
-  long long g = (long long)per_sm * ctx->sm_count;
-  *grid = (int)(ntiles < g ? ntiles : g);
-  if (*grid < 1) *grid = 1;
-  return FRAD_OK;
-}
-
 }  // namespace
 
 // eligibility checks shared with transform.cu
@@ -1100,31 +537,6 @@ bool frad_fast2048_decode_ok(const dec_params& P, int prec) {
   if (P.profile == 1 && ((uintptr_t)P.q % 16) != 0) return false;
   if (((uintptr_t)P.pcm % 16) != 0) return false;
   return true;
-}
-
-#define ENC_DISPATCH(PROF, CT)                                                                         \
-  do {                                                                                                 \
-    auto k = enc2048_kernel<PROF, CT>;                                                                 \
-    const tile_map tm = make_tiles<CT>(P.B, P.C);                                                      \
-    int grid;                                                                                          \
-    int rc = launch_cfg(ctx, k, smem, tm.ntiles, &grid);                                               \
-    if (rc) return rc;                                                                                 \
-    k<<<grid, FW * 32, smem, ctx->stream>>>(P, plan_view(pl), (const float2*)pl->tw32, force_exact);   \
-  } while (0)
-
-int frad_launch_encode_2048(frad_ctx* ctx, const enc_params& P, const frad_plan* pl, int prec, int force_exact) {
-  (void)prec;
-  // profile 0 has no per-band state: its CTAs only carry the sequence buffers, the SM takes a smaller shared-memory
-  // carve-out and the L1 that is left holds the twiddle tables (measured: 0.128 -> 0.117 ms)
-  const size_t smem = (size_t)FW * SEQ_CPX * sizeof(float2) + ((P.profile == 0) ? 16 : sizeof(smem_tail));
-#define ENC_BY_C(PROF)                                                                                \
-  do {                                                                                                \
-    if (P.C == 2) ENC_DISPATCH(PROF, 2); else if (P.C == 1) ENC_DISPATCH(PROF, 1);                    \
-    else if (P.C % 4 == 0) ENC_DISPATCH(PROF, 4); else ENC_DISPATCH(PROF, 0);                         \
-  } while (0)
-  if (P.profile == 0) ENC_BY_C(0); else if (P.profile == 1) ENC_BY_C(1); else ENC_BY_C(2);   // 2: P.tns_scratch = thresholds out
-  FRAD_LAUNCH_CHECK(ctx);
-  return FRAD_OK;
 }
 
 #define DEC_DISPATCH(TT, PROF, CT)                                                                       \

@@ -698,7 +698,10 @@ static int resolve_prec_fwd(int prec, int pcm_dtype) {
 }
 static int resolve_prec_inv(int prec) { return (prec == FRAD_PREC_F32) ? FRAD_PREC_F32 : FRAD_PREC_F64; }
 
-int frad_launch_encode_2048(frad_ctx* ctx, const enc_params& P, const frad_plan* pl, int prec, int force_exact);   // dct2048.cu
+int frad_launch_encode_2048r(frad_ctx* ctx, const enc_params& P, const frad_plan* pl, int prec, int force_exact);     // enc2048.cu
+static int frad_launch_encode_2048(frad_ctx* ctx, const enc_params& P, const frad_plan* pl, int prec, int force_exact) {
+  return frad_launch_encode_2048r(ctx, P, pl, prec, force_exact);
+}
 int frad_launch_decode_2048(frad_ctx* ctx, const dec_params& P, const frad_plan* pl, int prec);
 bool frad_fast2048_encode_ok(const enc_params& P, int prec);
 bool frad_fast2048_decode_ok(const dec_params& P, int prec);
