@@ -205,6 +205,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--frames", type=int, default=NFRAMES)
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling (frame-sharded single stream) leg")
+    ap.add_argument("--full-8h", type=int, default=0, metavar="BLOCKS",
+                    help="also run configs[4] at full length: BLOCKS x the 64 s block (450 = 8 h), sharded over the ranks")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -446,6 +448,10 @@ def main():
         from tools import strong_leg
         strong = strong_leg.run(ctx, dist, rank, world, max(2, min(args.steps, 5)),
                                 os.environ.get("MASTER_PORT", "0") + "_" + str(os.getppid() if world > 1 else os.getpid()))
+    cfg4 = None
+    if args.full_8h > 0:
+        from tools import strong_leg
+        cfg4 = strong_leg.full_8h(ctx, dist, rank, world, args.full_8h)
     clocks = sampler.stop()
 
     # sanity: the e2e result must be real data (decoded audio close to the input)
@@ -531,6 +537,8 @@ def main():
                   "x_realtime": nval0 / ((p0_enc_ms + p0_dec_ms) * 1e-3) / (SRATE * CH), "kernels": p0k}
     if strong is not None:
         line["strong"] = strong
+    if cfg4 is not None:
+        line["config4_8h"] = cfg4
     try:                                            # e2e against the box's measured copy ceiling at this N (tools/pcie_probe.py)
         ceil = json.load(open(os.path.join(ROOT, "profiles", "r2_pcie_ceiling.json"))).get(str(world))
         if ceil:

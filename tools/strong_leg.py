@@ -255,3 +255,122 @@ def run(ctx, dist, rank, world, steps, tag):
     out["workload"] = ("configs[4] shape: one 64 s block of 96 kHz 8-channel f32 PCM (the tile the 8 h clip is built from), "
                        "frames cut by contiguous range over the ranks; bitstream and PCM concatenated in rank order in shared memory")
     return out
+
+
+def full_8h(ctx, dist, rank, world, tiles=450):
+    """configs[4] at full length: 8 h of 96 kHz 8-channel PCM = `tiles` x the 64 s block (22.1 G scalar samples, 88.5 GB as f32 --
+    more than the host holds, so the block is streamed `tiles` times).  Frames are cut by contiguous range over the
+    ranks: rank g takes the blocks [g T/G, (g+1) T/G) (a block boundary is a frame boundary for profile 0; profile-1 frames
+    that straddle it read the first 128 samples of the next, identical block).  Per block and rank:
+      device  encode + decode kernels on the resident block (CUDA events over all of the rank's blocks)
+      e2e     pinned PCM -> frad_p0_encode / frad_p1_encode_raw -> host bitstream -> frad_p0_decode / frad_p1_decode_stream
+              (cross-fade tail carried from block to block) -> f32 PCM on the host; wall clock over all of the rank's blocks
+    Returns the dict bench.py puts under "config4_8h" (rank 0) or None."""
+    import torch
+    from frad_python_b200 import _abi, shard
+    from frad_python_b200.backend import hanning_in_overlap
+    L = _abi.lib()
+    base = _pcm()
+    pcm = np.concatenate([base, base[:N - HOP]])              # one block + the halo of the next (identical) one
+    t0, t1 = shard.frame_ranges(tiles, world)[rank]
+    mine = t1 - t0
+    h_pcm = ctx.pinned(pcm.shape, np.float32); h_pcm[...] = pcm
+    fade = np.ascontiguousarray(hanning_in_overlap(N - HOP), dtype=np.float64)
+    out = {}
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            dist.barrier()
+
+    def maxr(x):
+        if dist is None:
+            return float(x)
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    d_pcm = ctx.dev(h_pcm.nbytes); ctx.h2d(d_pcm, h_pcm)
+    for prof in (0, 1):
+        hop = HOP if prof == 1 else N
+        F = len(base) // hop                                  # frames that START in one block: 3000 / 3200
+        nscal = tiles * F * hop * CH4
+        d_out = ctx.dev(F * N * CH4 * 8)
+        if prof == 1:
+            d_q = ctx.dev(F * N * CH4 * 4); d_tq = ctx.dev(F * 27 * CH4 * 4)
+
+            def dev_block():
+                ctx.check(L.frad_p1_encode_dev(ctx.handle, d_pcm.ptr, _abi.F32, hop, F, N, CH4, BITS, SR4, LOSS, _abi.PREC_REF,
+                                               d_q.ptr, d_tq.ptr, None))
+                ctx.check(L.frad_p1_decode_dev(ctx.handle, d_q.ptr, d_tq.ptr, None, F, N, CH4, BITS, SR4, _abi.PREC_REF, d_out.ptr,
+                                               _abi.F64))
+        else:
+            stride = N * CH4 * 4
+            d_pay = ctx.dev(F * stride); d_peak = ctx.dev(F * 8)
+
+            def dev_block():
+                ctx.check(L.frad_p0_encode_dev(ctx.handle, d_pcm.ptr, _abi.F32, hop, F, N, CH4, 32, 0, _abi.PREC_REF, d_pay.ptr,
+                                               stride, d_peak.ptr))
+                ctx.check(L.frad_p0_decode_dev(ctx.handle, d_pay.ptr, stride, F, N, CH4, 32, 0, _abi.PREC_REF, d_out.ptr, _abi.F64))
+        dev_block(); barrier()
+        ctx.event(22)
+        for _ in range(mine):
+            dev_block()
+        ctx.event(23)
+        barrier()
+        dev_ms = maxr(ctx.elapsed_ms(22, 23))
+        for d in (d_out,) + ((d_q, d_tq) if prof == 1 else (d_pay, d_peak)):
+            d.free()
+        # e2e
+        cap = 2 * N * CH4 if prof == 1 else N * CH4 * 4
+        h_raw = ctx.pinned((F * cap,), np.uint8)
+        h_off = ctx.pinned((F + 1,), np.uint64)
+        h_out = ctx.pinned((F * hop, CH4), np.float32) if prof == 1 else ctx.pinned((F, N, CH4), np.float32)
+        h_keep = np.empty(h_out.shape, np.float32)
+        h_tail = [ctx.pinned((N - HOP, CH4), np.float64), ctx.pinned((N - HOP, CH4), np.float64)]
+        h_st = ctx.pinned((F,), np.int32); h_peak = ctx.pinned((F,), np.float64)
+        nbytes = 0
+
+        def e2e_block(i, first):
+            nonlocal nbytes
+            if prof == 1:
+                ctx.check(L.frad_p1_encode_raw(ctx.handle, h_pcm.ctypes.data, _abi.F32, hop, F, N, CH4, BITS, SR4, LOSS,
+                                               _abi.PREC_REF, 1, h_raw.ctypes.data, h_raw.size, h_off.ctypes.data))
+                nbytes = int(h_off[F])
+                prev = None if first else h_tail[(i + 1) & 1].ctypes.data
+                ctx.check(L.frad_p1_decode_stream(ctx.handle, h_raw.ctypes.data, h_off.ctypes.data, F, N, CH4, BITS, SR4,
+                                                  _abi.PREC_REF, 1, RATIO, fade.ctypes.data, prev, h_out.ctypes.data, _abi.F32,
+                                                  h_tail[i & 1].ctypes.data, h_st.ctypes.data))
+            else:
+                ctx.check(L.frad_p0_encode(ctx.handle, h_pcm.ctypes.data, _abi.F32, hop, F, N, CH4, 32, 0, _abi.PREC_REF,
+                                           h_raw.ctypes.data, cap, h_peak.ctypes.data, None))
+                nbytes = F * cap
+                ctx.check(L.frad_p0_decode(ctx.handle, h_raw.ctypes.data, cap, F, N, CH4, 32, 0, _abi.PREC_REF, h_out.ctypes.data,
+                                           _abi.F32))
+
+        e2e_block(0, True); e2e_block(1, False)
+        h_keep[...] = h_out                                   # a block decoded after an identical block: every later one must equal it
+        barrier()
+        w0 = time.perf_counter()
+        for i in range(mine):
+            e2e_block(i, i == 0 and t0 == 0)
+        barrier()
+        e2e_ms = maxr(1e3 * (time.perf_counter() - w0))
+        same = bool(np.array_equal(h_out, h_keep)) if mine > 1 else None
+        audio_s = tiles * SECONDS
+        out["p%d" % prof] = {
+            "frames": tiles * F, "blocks_per_rank": mine, "bitstream_bytes": tiles * nbytes,
+            "device": {"value": nscal / (dev_ms * 1e-3) / 1e6, "unit": "MSamples/s", "seconds": dev_ms * 1e-3,
+                       "x_realtime": audio_s / (dev_ms * 1e-3)},
+            "e2e": {"value": nscal / (e2e_ms * 1e-3) / 1e6, "unit": "MSamples/s", "seconds": e2e_ms * 1e-3,
+                    "x_realtime": audio_s / (e2e_ms * 1e-3)},
+            "last_block_equals_reference_block": same,
+        }
+    d_pcm.free()
+    if rank != 0:
+        return None
+    out["workload"] = ("configs[4]: 8 h of 96 kHz 8-channel f32 PCM as %d x one 64 s block (the block is streamed, not held: "
+                       "88.5 GB exceed the host), profile 0 (32 bit) and profile 1 (16 bit, overlap 1/16), encode + decode; "
+                       "blocks cut by contiguous range over the ranks" % tiles)
+    out["scaling"] = "strong"
+    return out
