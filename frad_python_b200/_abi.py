@@ -110,6 +110,12 @@ def lib():
             "frad_p1_decode_raw": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp]),
             "frad_overlap_dev": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp, i32, vp]),
             "frad_p1_decode_stream": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp]),
+            "frad_deflate_bound": (sz, [sz]),
+            "frad_deflate_frames": (i32, [vp, vp, i32, vp, sz, vp, i32]),
+            "frad_inflate_frames": (i32, [vp, vp, vp, i32, vp, sz, vp, i32]),
+            "frad_asfh_write_frames": (i64, [i32, i32, i32, i32, vp, i32, i32, u32, vp, u32, i32, i32, i32, vp, vp, vp, vp, i32,
+                                             vp, sz]),
+            "frad_asfh_scan": (i32, [C.c_char_p, sz, sz, i32, vp, vp, vp, vp, vp]),
         })
         optional = {}
         for name, (res, args) in sig.items():
@@ -136,6 +142,7 @@ EXPORTS = [
     "frad_rs_encode", "frad_rs_decode",
     "frad_p1_raw_bound", "frad_p1_pack_dev", "frad_compact_dev", "frad_p1_unpack_dev", "frad_p1_encode_raw",
     "frad_p1_decode_raw", "frad_overlap_dev", "frad_p1_decode_stream",
+    "frad_deflate_bound", "frad_deflate_frames", "frad_inflate_frames", "frad_asfh_write_frames", "frad_asfh_scan",
 ]
 
 
@@ -374,6 +381,57 @@ class Context:
             buf[int(o):int(o) + len(c)] = np.frombuffer(c, np.uint8)
         return buf, offs, lens, total
 
+    # packed variants: messages addressed inside one uint8 buffer by offs / lens (what the batched codec objects use)
+    def crc_packed(self, buf: np.ndarray, offs: np.ndarray, lens: np.ndarray, bits32: bool) -> np.ndarray:
+        nb = len(lens)
+        out = np.zeros(nb, np.uint32)
+        if nb == 0:
+            return out
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        lens = np.ascontiguousarray(lens, dtype=np.uint32)
+        fn = lib().frad_crc32 if bits32 else lib().frad_crc16
+        self.check(fn(self.handle, buf.ctypes.data, offs.ctypes.data, lens.ctypes.data, 0, 0, nb, buf.size, out.ctypes.data))
+        return out
+
+    def rs_encode_packed(self, buf: np.ndarray, offs: np.ndarray, lens: np.ndarray, dsize: int, csize: int):
+        """-> (out buffer, out offsets uint64 [B], out lengths uint32 [B]); messages 16-byte aligned in `out`."""
+        nb = len(lens)
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        lens = np.ascontiguousarray(lens, dtype=np.uint32)
+        l64 = lens.astype(np.uint64)
+        olens = l64 + ((l64 + np.uint64(dsize - 1)) // np.uint64(dsize)) * np.uint64(csize)
+        ooffs = np.zeros(nb, np.uint64)
+        if nb > 1:
+            np.cumsum(((olens[:-1] + np.uint64(15)) // np.uint64(16)) * np.uint64(16), out=ooffs[1:])
+        ototal = int(ooffs[-1] + olens[-1]) if nb else 0
+        out = np.zeros(max(ototal, 1), np.uint8)
+        if nb:
+            self.check(lib().frad_rs_encode(self.handle, buf.ctypes.data, offs.ctypes.data, lens.ctypes.data, 0, 0, nb, buf.size,
+                                             dsize, csize, out.ctypes.data, ooffs.ctypes.data, 0, ototal))
+        return out, ooffs, olens.astype(np.uint32)
+
+    def rs_decode_packed(self, buf: np.ndarray, offs: np.ndarray, lens: np.ndarray, dsize: int, csize: int, repair: bool):
+        """-> (out buffer, out offsets uint64 [B], out lengths uint32 [B], failed codewords [B], corrected bytes [B])."""
+        nb = len(lens)
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        lens = np.ascontiguousarray(lens, dtype=np.uint32)
+        block = dsize + csize
+        l64 = lens.astype(np.int64)
+        rem = l64 % block
+        olens = ((l64 // block) * dsize + np.where(rem > csize, rem - csize, 0)).astype(np.uint64)
+        ooffs = np.zeros(nb, np.uint64)
+        if nb > 1:
+            np.cumsum(((olens[:-1] + np.uint64(15)) // np.uint64(16)) * np.uint64(16), out=ooffs[1:])
+        ototal = int(ooffs[-1] + olens[-1]) if nb else 0
+        out = np.zeros(max(ototal, 1), np.uint8)
+        status = np.zeros(nb, np.int32)
+        fixed = np.zeros(nb, np.int32)
+        if nb:
+            self.check(lib().frad_rs_decode(self.handle, buf.ctypes.data, offs.ctypes.data, lens.ctypes.data, 0, 0, nb, buf.size,
+                                             dsize, csize, int(bool(repair)), out.ctypes.data, ooffs.ctypes.data, 0, ototal,
+                                             status.ctypes.data, fixed.ctypes.data))
+        return out, ooffs, olens.astype(np.uint32), status, fixed
+
     def crc_many(self, chunks, bits32: bool) -> np.ndarray:
         """CRC-32 (bits32) or CRC-16/ARC of every byte string in ``chunks``."""
         if not chunks:
@@ -427,3 +485,83 @@ def default_context(device: int = 0) -> Context:
     if ctx is None:
         ctx = _default[device] = Context(device)
     return ctx
+
+
+# ---- host-side batch framing (csrc/hostframe.cpp; no device needed) ----------------------------------------------------
+def deflate_frames(raw: np.ndarray, off: np.ndarray, threads: int = 0):
+    """Raw deflate (zlib.compress(x, wbits=-15)) of every frame raw[off[i]:off[i+1]] -> (uint8 buffer, uint64 offsets [B+1])."""
+    raw = np.ascontiguousarray(raw, dtype=np.uint8)
+    off = np.ascontiguousarray(off, dtype=np.uint64)
+    nb = len(off) - 1
+    out_off = np.zeros(nb + 1, np.uint64)
+    if nb <= 0:
+        return np.zeros(0, np.uint8), out_off
+    longest = int(np.max(off[1:] - off[:-1]))
+    slot = int(lib().frad_deflate_bound(longest))
+    out = np.empty(nb * slot, np.uint8)
+    rc = lib().frad_deflate_frames(raw.ctypes.data, off.ctypes.data, nb, out.ctypes.data, slot, out_off.ctypes.data, threads)
+    if rc != 0:
+        raise FradError(f"frad_deflate_frames failed ({rc})")
+    return out[:int(out_off[nb])], out_off
+
+
+def inflate_frames(buf: np.ndarray, pay_off: np.ndarray, pay_len: np.ndarray, slot: int, threads: int = 0):
+    """Inverse of deflate_frames for payloads buf[pay_off[i]:pay_off[i]+pay_len[i]]; a frame that does not inflate gives
+    zero bytes (profile1.py:59-60).  -> (uint8 buffer, uint64 offsets [B+1])."""
+    buf = np.ascontiguousarray(buf, dtype=np.uint8)
+    pay_off = np.ascontiguousarray(pay_off, dtype=np.uint64)
+    pay_len = np.ascontiguousarray(pay_len, dtype=np.uint32)
+    nb = len(pay_len)
+    out_off = np.zeros(nb + 1, np.uint64)
+    if nb == 0:
+        return np.zeros(1, np.uint8), out_off
+    out = np.empty(nb * int(slot) + 16, np.uint8)
+    rc = lib().frad_inflate_frames(buf.ctypes.data, pay_off.ctypes.data, pay_len.ctypes.data, nb, out.ctypes.data, int(slot),
+                                   out_off.ctypes.data, threads)
+    if rc != 0:
+        raise FradError(f"frad_inflate_frames failed ({rc})")
+    return out[:max(int(out_off[nb]), 1)], out_off
+
+
+def asfh_write_frames(profile: int, ecc: bool, little_endian: bool, depth, channels: int, srate: int, fsize, overlap_ratio: int,
+                      ecc_dsize: int, ecc_csize: int, pay: np.ndarray, pay_off: np.ndarray, pay_len: np.ndarray, crc,
+                      flush_each: bool = False) -> bytes:
+    """tools/asfh.py:51-73 for a run of frames with one parameter set.  depth / fsize: int or per-frame array."""
+    nb = len(pay_len)
+    if nb == 0:
+        return b""
+    pay = np.ascontiguousarray(pay, dtype=np.uint8)
+    pay_off = np.ascontiguousarray(pay_off, dtype=np.uint64)
+    pay_len = np.ascontiguousarray(pay_len, dtype=np.uint32)
+    d_arr = None if np.isscalar(depth) else np.ascontiguousarray(depth, dtype=np.uint8)
+    f_arr = None if np.isscalar(fsize) else np.ascontiguousarray(fsize, dtype=np.uint32)
+    c_arr = None if crc is None else np.ascontiguousarray(crc, dtype=np.uint32)
+    compact = profile in (1, 2)
+    cap = int(pay_len.astype(np.int64).sum()) + nb * ((16 if ecc else 12) if compact else 32) + (12 * nb if (flush_each and compact) else 0)
+    out = np.empty(cap, np.uint8)
+    n = lib().frad_asfh_write_frames(nb, profile, int(bool(ecc)), int(bool(little_endian)), _ptr(d_arr),
+                                     0 if d_arr is not None else int(depth), channels, int(srate), _ptr(f_arr),
+                                     0 if f_arr is not None else int(fsize), overlap_ratio, ecc_dsize, ecc_csize, pay.ctypes.data,
+                                     pay_off.ctypes.data, pay_len.ctypes.data, _ptr(c_arr), int(bool(flush_each)),
+                                     out.ctypes.data, cap)
+    if n < 0:
+        raise FradError("frad_asfh_write_frames: output did not fit")
+    return out[:n].tobytes()
+
+
+_SCAN_MAX = 1 << 16
+
+
+def asfh_scan(buf: bytes, pos: int, max_frames: int = _SCAN_MAX):
+    """The complete frames at buf[pos:] that share one parameter set (see hostframe.cpp).
+    -> (n, params int64[12], payload positions uint64[n], payload lengths uint32[n], checksums uint32[n], next position)."""
+    max_frames = min(max_frames, _SCAN_MAX)
+    params = np.zeros(12, np.int64)
+    ppos = np.empty(max_frames, np.uint64)
+    plen = np.empty(max_frames, np.uint32)
+    crc = np.empty(max_frames, np.uint32)
+    nxt = C.c_size_t(pos)
+    mv = (C.c_char * len(buf)).from_buffer_copy(buf) if isinstance(buf, bytearray) else buf
+    n = lib().frad_asfh_scan(mv, len(buf), pos, max_frames, params.ctypes.data, ppos.ctypes.data, plen.ctypes.data,
+                             crc.ctypes.data, C.byref(nxt))
+    return n, params, ppos[:n], plen[:n], crc[:n], int(nxt.value)

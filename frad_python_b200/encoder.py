@@ -9,7 +9,7 @@ import sys
 
 import numpy as np
 
-from . import fourier
+from . import _abi, fourier
 from ._abi import PREC_REF, default_context
 from .backend import ff_format_to_numpy_type, to_f64
 from .fourier import AVAILABLE, BIT_DEPTHS, SEGMAX
@@ -66,7 +66,8 @@ class Encoder:
         return raw if keep_native_ints else to_f64(raw, dt)
 
     def _emit(self, payloads, depth_idx, channels, srate, fsizes, crcs, flush_each: bool) -> bytes:
-        """ECC + header for a list of frames sharing the current ASFH settings."""
+        """ECC + header for a list of frames sharing the current ASFH settings (per-frame route: mixed depths after an
+        overflow bump, contexts without the packed calls)."""
         a = self.asfh
         if a.ecc and a.ecc_codesize > 0:
             payloads = self.ctx.rs_encode_many(payloads, a.ecc_dsize, a.ecc_codesize)
@@ -85,14 +86,41 @@ class Encoder:
                 out.append(a.force_flush())
         return b"".join(out)
 
+    def _emit_packed(self, buf, offs, lens, depth_idx: int, channels, srate, fsizes, crcs, flush_each: bool) -> bytes:
+        """The same for a run of frames held in one buffer (frame i = buf[offs[i] : offs[i] + lens[i]]): ECC and checksums in
+        one device call each, headers + payloads assembled by one native call (tools/asfh.py:51-73 byte for byte)."""
+        a = self.asfh
+        if a.ecc and a.ecc_codesize > 0:
+            buf, offs, lens = self.ctx.rs_encode_packed(buf, offs, lens, a.ecc_dsize, a.ecc_codesize)
+            crcs = None
+        if crcs is None and (a.profile not in COMPACT or a.ecc):
+            crcs = self.ctx.crc_packed(buf, offs, lens, a.profile not in COMPACT)
+        a.bit_depth_index, a.channels, a.srate, a.fsize = depth_idx, channels, srate, fsizes[-1]
+        uniform = len(set(fsizes)) == 1
+        return _abi.asfh_write_frames(a.profile, a.ecc, a.endian, depth_idx, channels, srate,
+                                      fsizes[0] if uniform else np.asarray(fsizes, np.uint32), a.overlap_ratio, a.ecc_dsize,
+                                      a.ecc_codesize, buf, offs, lens, crcs, flush_each)
+
     def _encode_frames(self, pcm: np.ndarray, nframes: int, n: int, hop: int, fsizes, flush_each=False) -> bytes:
         a = self.asfh
+        packed = hasattr(self.ctx, "rs_encode_packed")
         if a.profile in (0, 4):
             mod0 = fourier.profile0 if a.profile == 0 else fourier.profile4
+            if packed:
+                got = mod0.analogue_batch_packed(pcm, nframes, n, hop, self.bit_depth, a.endian, self.ctx, self.precision,
+                                                 want_crc=not a.ecc)
+                if got is not None:                       # None: some frame overflowed its float format (depth bump)
+                    buf, offs, lens, depth, crc = got
+                    return self._emit_packed(buf, offs, lens, depth, pcm.shape[1], self.srate, fsizes, None if a.ecc else crc,
+                                             flush_each)
             pays, depth, crc = mod0.analogue_batch(pcm, nframes, n, hop, self.bit_depth, a.endian, self.ctx,
                                                    self.precision, want_crc=not a.ecc)
             return self._emit(pays, depth, pcm.shape[1], self.srate, fsizes, None if a.ecc else crc, flush_each)
         mod = fourier.profile1 if a.profile == 1 else fourier.profile2
+        if packed:
+            buf, off, depth, ch, sr = mod.analogue_batch_packed(pcm, nframes, n, hop, self.bit_depth, self.srate, self.loss_level,
+                                                                self.ctx, self.precision)
+            return self._emit_packed(buf, off[:-1], (off[1:] - off[:-1]).astype(np.uint32), depth, ch, sr, fsizes, None, flush_each)
         pays, depth, ch, sr = mod.analogue_batch(pcm, nframes, n, hop, self.bit_depth, self.srate, self.loss_level,
                                                  self.ctx, self.precision)
         return self._emit(pays, depth, ch, sr, fsizes, None, flush_each)
@@ -116,11 +144,15 @@ class Encoder:
             if avail >= first_need:
                 nframes = 1 + (avail - first_need) // hop
                 used = first_need + (nframes - 1) * hop
-                raw = np.frombuffer(self.buffer[:used * bps], self.pcm_format).reshape(-1, self.channels)
-                self.buffer = self.buffer[used * bps:]
+                mv = memoryview(self.buffer)                  # views, not slices: a 32 MiB piece is copied once, not four times
+                raw = np.frombuffer(mv[:used * bps], self.pcm_format).reshape(-1, self.channels)
+                self.buffer = bytes(mv[used * bps:])
                 pcm = self._float_domain(raw, keep_native_ints=(frag_len == 0 and olap == 0))
                 if frag_len:
-                    pcm = np.concatenate((frag.astype(pcm.dtype, copy=False), pcm), axis=0)
+                    whole = np.empty((frag_len + len(pcm), self.channels), pcm.dtype)
+                    whole[:frag_len] = frag
+                    whole[frag_len:] = pcm
+                    pcm = whole
                 ret.append(self._encode_frames(pcm, nframes, n, hop, [n] * nframes))
                 samples += used
                 if olap:

@@ -45,6 +45,21 @@ def analogue_batch(pcm: np.ndarray, nframes: int, n: int, hop: int, bits: int, l
     return out, depth, crc
 
 
+def analogue_batch_packed(pcm: np.ndarray, nframes: int, n: int, hop: int, bits: int, little_endian: bool, ctx=None,
+                          prec: int = PREC_REF, want_crc: bool = True, profile: int = 0):
+    """analogue_batch without per-frame Python objects: (payload buffer, offsets [B], lengths [B], depth index, crc32 or
+    None), or None when a frame overflows its float format (profile0.py:24-26) -- the caller then takes the list route."""
+    ctx = ctx or default_context()
+    if bits not in DEPTHS:
+        bits = 16
+    payload, peak, crc = ctx.p0_encode(_device_pcm(pcm), nframes, n, hop, bits, little_endian, prec, want_crc, profile)
+    if np.any(peak > _FLOAT_MAX[bits]):
+        return None
+    nbytes = payload.shape[1]
+    offs = np.arange(nframes, dtype=np.uint64) * np.uint64(nbytes)
+    return payload.reshape(-1), offs, np.full(nframes, nbytes, np.uint32), DEPTHS.index(bits), crc
+
+
 def analogue(pcm: np.ndarray, bits: int, srate: int, little_endian: bool, ctx=None):
     """profile0.py:14-44 -> (payload bytes, depth index, channels, srate)."""
     out, depth, _ = analogue_batch(pcm, 1, len(pcm), len(pcm), bits, little_endian, ctx, want_crc=False)

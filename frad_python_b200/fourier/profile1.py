@@ -59,6 +59,19 @@ def analogue_batch(pcm: np.ndarray, nframes: int, n: int, hop: int, bits: int, s
     return deflate_all(split_raw(raw, off)), DEPTHS.index(bits), pcm.shape[1], srate
 
 
+def analogue_batch_packed(pcm: np.ndarray, nframes: int, n: int, hop: int, bits: int, srate: int, loss_level: float,
+                          ctx=None, prec: int = PREC_REF, profile: int = 1, depths=DEPTHS):
+    """analogue_batch without per-frame Python objects: (deflated payloads in one buffer, offsets [B+1], depth index,
+    channels, srate).  Bit packing on the device, raw deflate of all frames by one native call (host thread pool)."""
+    ctx = ctx or default_context()
+    if bits not in depths:
+        bits = 16
+    srate = compact.get_valid_srate(srate)
+    raw, off = ctx.p1_encode_raw(_device_pcm(pcm), nframes, n, hop, bits, srate, max(abs(loss_level), 0.125), prec, profile)
+    buf, poff = _abi.deflate_frames(raw, off)
+    return buf, poff, depths.index(bits), pcm.shape[1], srate
+
+
 def analogue(pcm: np.ndarray, bits: int, srate: int, loss_level: float, ctx=None):
     """profile1.py:15-52 -> (payload bytes, depth index, channels, srate)."""
     n = compact.get_samples_min_ge(len(pcm))

@@ -18,6 +18,11 @@ def analogue_batch(pcm, nframes, n, hop, bits, srate, loss_level, ctx=None, prec
     return deflate_all(split_raw(raw, off)), DEPTHS.index(bits), pcm.shape[1], srate
 
 
+def analogue_batch_packed(pcm, nframes, n, hop, bits, srate, loss_level, ctx=None, prec: int = PREC_REF):
+    from .profile1 import analogue_batch_packed as p1_packed
+    return p1_packed(pcm, nframes, n, hop, bits, srate, loss_level, ctx, prec, 2, DEPTHS)
+
+
 def analogue(pcm, bits, srate, loss_level, ctx=None):
     """profile2.py:15-56"""
     n = compact.get_samples_min_ge(len(pcm))

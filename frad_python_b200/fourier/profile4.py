@@ -17,6 +17,11 @@ def analogue_batch(pcm: np.ndarray, nframes: int, n: int, hop: int, bits: int, l
     return profile0.analogue_batch(pcm, nframes, n, hop, bits, little_endian, ctx, prec, want_crc, profile=4)
 
 
+def analogue_batch_packed(pcm: np.ndarray, nframes: int, n: int, hop: int, bits: int, little_endian: bool, ctx=None,
+                          prec: int = PREC_REF, want_crc: bool = True):
+    return profile0.analogue_batch_packed(pcm, nframes, n, hop, bits, little_endian, ctx, prec, want_crc, profile=4)
+
+
 def analogue(pcm: np.ndarray, bits: int, srate: int, little_endian: bool, ctx=None):
     """profile4.py:14-44 -> (payload bytes, depth index, channels, srate)."""
     out, depth, _ = analogue_batch(pcm, 1, len(pcm), len(pcm), bits, little_endian, ctx, want_crc=False)

@@ -7,9 +7,10 @@ import sys
 
 import numpy as np
 
-from . import common
+from . import _abi, common
 from ._abi import default_context
 from .fourier.profiles import COMPACT, LOSSLESS
+from .decoder import _Run
 from .tools.asfh import ASFH
 
 
@@ -30,6 +31,7 @@ class Repairer:
         self.fix_error = True
         self.ecc_ratio = tuple(ecc_ratio)
         self.broken_frame = False
+        self._fast_scan = hasattr(self.ctx, "rs_decode_packed")
 
     def is_empty(self) -> bool:
         return len(self.buffer) < len(common.FRM_SIGN) or self.broken_frame
@@ -39,8 +41,34 @@ class Repairer:
         s.__dict__.update(self.asfh.__dict__)
         return s
 
+    def _render_run(self, run: _Run) -> bytes:
+        """A run of frames with one parameter set: undo the old ECC (repairing), add the new one, checksums, headers -- one
+        batched call each (repairer.py:39-53 per frame in the reference)."""
+        buf = np.frombuffer(run.buf, np.uint8)
+        pos, length = run.pos, run.length
+        if run.ecc and run.csize > 0:
+            # the reference repairs every block when fix_error is set (its CRC comparison never matches, SURVEY F7)
+            buf, pos, length = self.ctx.rs_decode_packed(buf, pos, length, run.dsize, run.csize, self.fix_error)[:3]
+        if self.ecc_ratio[1] > 0:
+            buf, pos, length = self.ctx.rs_encode_packed(buf, pos, length, self.ecc_ratio[0], self.ecc_ratio[1])
+        crc = self.ctx.crc_packed(buf, pos, length, run.profile not in COMPACT)
+        return _abi.asfh_write_frames(run.profile, True, run.endian, run.depth, run.channels, run.srate, run.fsize,
+                                      run.overlap_ratio, self.ecc_ratio[0], self.ecc_ratio[1], buf, pos, length, crc)
+
     def _render(self, items) -> bytes:
-        """items: raw bytes (passed through) or (header snapshot, payload) tuples in stream order."""
+        """items: raw bytes (passed through), runs of frames, or (header snapshot, payload) tuples in stream order."""
+        if any(isinstance(it, _Run) for it in items):
+            out, group = [], []
+            for it in items:
+                if isinstance(it, _Run):
+                    if group:
+                        out.append(self._render(group)); group = []
+                    out.append(self._render_run(it))
+                else:
+                    group.append(it)
+            if group:
+                out.append(self._render(group))
+            return b"".join(out)
         frames = [(i, it) for i, it in enumerate(items) if not isinstance(it, bytes)]
         payloads = {i: it[1] for i, it in frames}
         # 1. undo the old ECC (repairing where the CRC disagrees)
@@ -99,6 +127,25 @@ class Repairer:
                 self.asfh.ecc_dsize, self.asfh.ecc_codesize = self.ecc_ratio
                 self.asfh.clear()
             else:
+                if self._fast_scan and not self.asfh.buffer and buf[pos:pos + slen] == sign:
+                    n, prm, ppos, plen, pcrc, nxt = _abi.asfh_scan(buf, pos)
+                    if n >= 4:
+                        a = self.asfh
+                        (a.profile, ecc, le, a.bit_depth_index, a.channels, a.srate, a.fsize, a.overlap_ratio, a.ecc_dsize,
+                         a.ecc_codesize, a.header_bytes) = (int(x) for x in prm[:11])
+                        a.endian, a.frmbytes = bool(le), int(plen[-1])
+                        run = _Run()
+                        run.buf, run.pos, run.length, run.crc = buf, ppos, plen, pcrc
+                        run.profile, run.ecc, run.dsize, run.csize, run.endian = a.profile, bool(ecc), a.ecc_dsize, a.ecc_codesize, a.endian
+                        run.depth, run.channels, run.srate, run.fsize, run.overlap_ratio = (a.bit_depth_index, a.channels, a.srate,
+                                                                                           a.fsize, a.overlap_ratio)
+                        items.append(run)
+                        # the reference leaves these set on its header object after each frame (repairer.py:49-50)
+                        a.ecc = True
+                        a.ecc_dsize, a.ecc_codesize = self.ecc_ratio
+                        pos = nxt
+                        self.broken_frame = False
+                        continue
                 if not self.asfh.buffer[:slen] == sign:
                     i = buf.find(sign, pos)
                     if i != -1:

@@ -176,56 +176,38 @@ class ShardedDecoder(Decoder):
         self.last_shards, self.sharded_batches = 1, 0
         super().__init__(fix_error, ctx=self.ctxs[0], **kw)
 
-    @staticmethod
-    def _key(p):
-        return (p.profile, p.ecc, p.dsize, p.csize, p.endian, p.depth, p.channels, p.srate, p.fsize, p.overlap_ratio)
-
-    def _decode_pending(self) -> list:
-        """Runs of frames with one parameter set are sharded; the rest (a ragged last lossless frame, parameter changes)
-        goes through the single-context route.  Runs are handled in stream order, so the overlap state carries over."""
-        pend, self._pending = self._pending, []
-        out, i = [], 0
-        while i < len(pend):
-            key = (self._key(pend[i]), len(pend[i].payload) if pend[i].profile not in COMPACT else 0)
-            j = i + 1
-            while j < len(pend) and (self._key(pend[j]), len(pend[j].payload) if pend[j].profile not in COMPACT else 0) == key:
-                j += 1
-            out.extend(self._decode_run(pend[i:j]))
-            i = j
-        return out
-
-    def _decode_run(self, pend) -> list:
-        shards = min(len(self.ctxs), len(pend) // self.min_frames_per_shard)
-        lossy = pend[0].profile in COMPACT
-        ratio, n = pend[0].overlap_ratio, pend[0].fsize
+    def _decode_run(self, run) -> list:
+        """A run of frames with one parameter set (found by the native header walk) is cut by contiguous range over the
+        contexts; anything the fused / batched route cannot take whole goes through the single-context route."""
+        shards = min(len(self.ctxs), len(run) // self.min_frames_per_shard)
+        lossy = run.profile in COMPACT
+        ratio, n = run.overlap_ratio, run.fsize
         cut = n * (ratio - 1) // ratio if (lossy and ratio > 1) else n
         frag = self.overlap_fragment
         have = frag.ndim == 2 and len(frag) > 0
         regular = shards >= 2 and self.overlap_prog == 0
         if lossy:
             # whole frames and a fragment of the stream's own size (or none): every shard then sees the same kind of state
-            regular = regular and ratio > 1 and 0 < n - cut <= cut and (not have or frag.shape == (n - cut, pend[0].channels))
+            regular = regular and ratio > 1 and 0 < n - cut <= cut and (not have or frag.shape == (n - cut, run.channels))
         else:
             regular = regular and not have
         if not regular:
-            self._pending = list(pend)
-            return Decoder._decode_pending(self)
+            return Decoder._decode_run(self, run)
         self.last_shards = shards
         self.sharded_batches += 1
-        ranges = frame_ranges(len(pend), shards)
+        ranges = frame_ranges(len(run), shards)
         workers = []
         for g, (a, b) in enumerate(ranges):
             w = copy.copy(self)
             w.ctx, w.asfh, w.info = self.ctxs[g], _clone_asfh(self.asfh), self.info
             halo = 1 if (lossy and g > 0) else 0
-            w._pending = list(pend[a - halo:b])
             w.overlap_fragment = frag if g == 0 else np.array([])
             w.overlap_prog = 0
-            workers.append((w, halo))
+            workers.append((w, halo, run.cut(a - halo, b)))
 
         def work(g):
-            w, halo = workers[g]
-            res = Decoder._decode_pending(w)
+            w, halo, sub = workers[g]
+            res = Decoder._decode_run(w, sub)
             if halo:                                         # drop the halo frame's own samples; its tail has been used
                 res = [np.concatenate([o for o in res if getattr(o, "ndim", 1) == 2])[cut:]]
             return res

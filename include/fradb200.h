@@ -210,6 +210,29 @@ int frad_rs_decode(frad_ctx* ctx, const uint8_t* buf, const uint64_t* off, const
                    uint8_t* out, const uint64_t* out_off, size_t out_stride, size_t out_total_bytes,
                    int32_t* status, int32_t* fixed);
 
+/* ---- host-side batch framing (no device work; csrc/hostframe.cpp) ------------------------------------------------------
+ * What the reference does per frame in Python around the seams above, for a whole batch in one call: raw deflate / inflate of
+ * the profile 1 / 2 payloads (fourier/profile1.py:50,59 -- zlib, same parameters as zlib.compress(raw, wbits=-15), on a
+ * thread pool; the byte compressor stays on the host), the frame headers (tools/asfh.py:51-73) and the header walk of the
+ * decoder (tools/asfh.py:98-134, decoder.py:82-91).  threads <= 0: one per hardware thread (at most 32).
+ * deflate: frame i = raw[raw_off[i] .. raw_off[i+1]) -> out + out_off[i]; out must hold B * slot_stride bytes with
+ *          slot_stride >= frad_deflate_bound(longest frame); out_off[B] = total.
+ * inflate: frame i = pay[pay_off[i] .. +pay_len[i]) -> out + out_off[i] (same scratch rule; slot_stride = the longest legal
+ *          payload, frad_p1_raw_bound); a frame that does not inflate contributes zero bytes (it decodes to silence).
+ * write:   headers + payloads of B frames sharing one parameter set -> out; returns bytes written or -(bytes needed).
+ * scan:    the complete frames at buf[pos..] that share one parameter set; stops before anything else (see hostframe.cpp). */
+size_t frad_deflate_bound(size_t raw_bytes);
+int frad_deflate_frames(const uint8_t* raw, const uint64_t* raw_off, int B, uint8_t* out, size_t slot_stride,
+                        uint64_t* out_off, int threads);
+int frad_inflate_frames(const uint8_t* pay, const uint64_t* pay_off, const uint32_t* pay_len, int B, uint8_t* out,
+                        size_t slot_stride, uint64_t* out_off, int threads);
+int64_t frad_asfh_write_frames(int B, int profile, int ecc, int little_endian, const uint8_t* depth_idx, int depth0,
+                               int channels, uint32_t srate, const uint32_t* fsize, uint32_t fsize0, int overlap_ratio,
+                               int ecc_dsize, int ecc_csize, const uint8_t* pay, const uint64_t* pay_off,
+                               const uint32_t* pay_len, const uint32_t* crc, int flush_each, uint8_t* out, size_t out_cap);
+int frad_asfh_scan(const uint8_t* buf, size_t len, size_t pos, int max_frames, int64_t* params, uint64_t* pay_pos,
+                   uint32_t* pay_len, uint32_t* crc, size_t* next_pos);
+
 #ifdef __cplusplus
 }
 #endif

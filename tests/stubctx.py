@@ -99,3 +99,27 @@ class OracleCtx:
             out[i * cut:(i + 1) * cut] = cur
             tail = fr[i, cut:]
         return O.pcm_from_f64(out, out_dtype) if np.dtype(out_dtype) != np.float64 else out, np.array(tail), np.zeros(nframes, np.int32)
+
+    # ---- packed variants (one buffer + offsets / lengths), what the batched codec objects prefer --------------------------
+    def crc_packed(self, buf, offs, lens, bits32):
+        b = np.asarray(buf, np.uint8).tobytes()
+        f = O.crc32 if bits32 else O.crc16_arc
+        return np.array([f(b[int(o):int(o) + int(n)]) for o, n in zip(offs, lens)], np.uint32)
+
+    @staticmethod
+    def _pack(parts):
+        lens = np.array([len(p) for p in parts], np.uint32)
+        offs = np.zeros(len(parts), np.uint64)
+        if len(parts) > 1:
+            np.cumsum(lens[:-1].astype(np.uint64), out=offs[1:])
+        return np.frombuffer(b"".join(parts) or b"\0", np.uint8), offs, lens
+
+    def rs_encode_packed(self, buf, offs, lens, dsize, csize):
+        b = np.asarray(buf, np.uint8).tobytes()
+        return self._pack([O.ecc_encode(b[int(o):int(o) + int(n)], dsize, csize) for o, n in zip(offs, lens)])
+
+    def rs_decode_packed(self, buf, offs, lens, dsize, csize, repair):
+        b = np.asarray(buf, np.uint8).tobytes()
+        out = self._pack([O.ecc_decode(b[int(o):int(o) + int(n)], dsize, csize, bool(repair)) for o, n in zip(offs, lens)])
+        z = np.zeros(len(lens), np.int32)
+        return out + (z, z.copy())

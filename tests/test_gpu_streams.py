@@ -204,10 +204,15 @@ def test_decoder_fused_route_matches_per_frame_route_and_output_formats(F, g_str
     stream = g_streams[name].tobytes()
     fused = [run_decoder(F, stream, name == "p1_ecc", chunk) for chunk in (4096, 32768, 1 << 22)]
     calls = []
-    orig = D.Decoder._decode_fused
+    orig, run_min = D.Decoder._decode_fused, D.Decoder.RUN_MIN
+    monkeypatch.setattr(D.Decoder, "RUN_MIN", 1 << 30)            # no runs from the native header walk: frame by frame
     monkeypatch.setattr(D.Decoder, "_decode_fused", lambda self, pend, payloads: calls.append(len(pend)))   # -> None: fallback
     slow = run_decoder(F, stream, name == "p1_ecc", 32768)
     monkeypatch.setattr(D.Decoder, "_decode_fused", orig)
+    one_by_one = [run_decoder(F, stream, name == "p1_ecc", chunk) for chunk in (4096, 1 << 22)]   # fused route on queued frames
+    monkeypatch.setattr(D.Decoder, "RUN_MIN", run_min)
+    for got in one_by_one:
+        assert np.array_equal(got, slow)
     assert calls and slow.dtype == np.float64
     for got in fused:
         assert got.shape == slow.shape and np.array_equal(got, slow)
