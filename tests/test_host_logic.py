@@ -219,3 +219,59 @@ def test_committed_bench_lines_follow_the_contract():
     for n in (2, 4, 8):
         m = json.load(open(os.path.join(root, "profiles", f"r1_bench_line_{n}gpu.json")))
         assert m["n_gpus"] == n and m["value"] > 0.9 * n * d["value"] * 0.9
+
+
+def test_native_batch_framing_matches_zlib_and_the_header_mirror(g_streams):
+    """csrc/hostframe.cpp (no device needed): raw deflate / inflate of a batch == zlib.compress / decompress(wbits=-15) frame
+    by frame, failures included (profile1.py:50,59-60); the header walk + header writer reproduce streams written by the
+    unmodified reference byte for byte (tools/asfh.py:51-73,98-134)."""
+    import zlib
+    from frad_python_b200 import _abi
+    from frad_python_b200.tools.asfh import ASFH
+    rng = np.random.default_rng(0)
+    raws = [bytes(rng.integers(0, 7, int(rng.integers(0, 5000)), dtype=np.uint8)) for _ in range(300)]
+    off = np.zeros(len(raws) + 1, np.uint64)
+    np.cumsum([len(r) for r in raws], out=off[1:])
+    out, ooff = _abi.deflate_frames(np.frombuffer(b"".join(raws), np.uint8), off)
+    for i, r in enumerate(raws):
+        assert out[int(ooff[i]):int(ooff[i + 1])].tobytes() == zlib.compress(r, wbits=-15), i
+    lens = (ooff[1:] - ooff[:-1]).astype(np.uint32)
+    bad = out.copy()
+    bad[int(ooff[5]) + 3:int(ooff[5]) + 10] ^= 0xFF                      # damaged frame
+    trunc_len = lens.copy(); trunc_len[7] //= 2                          # cut frame
+    inf, ioff = _abi.inflate_frames(bad, ooff[:-1], trunc_len, 8192)
+    for i in range(len(raws)):
+        src = bad[int(ooff[i]):int(ooff[i]) + int(trunc_len[i])].tobytes()
+        try:
+            want = zlib.decompress(src, wbits=-15)
+        except zlib.error:
+            want = b""
+        assert inf[int(ioff[i]):int(ioff[i + 1])].tobytes() == want, i
+    for name in ("p1", "p1_ecc", "p0_b32", "p0_b16_le_ecc", "p2", "p1_noov"):
+        s = g_streams[name].tobytes()
+        n, prm, ppos, plen, crc, nxt = _abi.asfh_scan(s, 0)
+        assert n >= 9
+        # the walk agrees with the per-frame header reader
+        a, pos = ASFH(), 0
+        for i in range(n):
+            a.buffer = s[pos:pos + 4]
+            res, _ = a.read(s[pos + 4:pos + 64])
+            assert res == "Complete" and pos + a.header_bytes == int(ppos[i]) and a.frmbytes == int(plen[i])
+            assert [a.profile, int(a.ecc), int(a.endian), a.bit_depth_index, a.channels, a.srate, a.fsize, a.overlap_ratio] == \
+                [int(x) for x in prm[:8]]
+            assert int.from_bytes(a.crc, "big") == int(crc[i]) or not (a.ecc or a.profile in (0, 4))
+            pos += a.header_bytes + a.frmbytes
+            a.clear()
+        assert pos == nxt
+        prof, ecc, le, depth, ch, sr, fs, ov, ds, cs = [int(x) for x in prm[:10]]
+        again = _abi.asfh_write_frames(prof, bool(ecc), bool(le), depth, ch, sr, fs, ov, ds, cs, np.frombuffer(s, np.uint8), ppos, plen,
+                                       crc if (ecc or prof in (0, 4)) else None)
+        assert again == s[:nxt], name
+    # the walk stops at force-flush markers, parameter changes, garbage and incomplete frames
+    s = g_streams["p1"].tobytes()
+    n, *_, nxt = _abi.asfh_scan(s, 0)
+    assert s[nxt:nxt + 4] == O.FRM_SIGN and nxt == len(s) - 24           # [FF][FF] left for the per-frame state machine
+    assert _abi.asfh_scan(s[:1000], 0)[0] == 0 and _abi.asfh_scan(b"junk" + s, 0)[0] == 0
+    mixed = g_streams["p0_b32"].tobytes()[:2 * (32 + 16384)] + s
+    n, prm, *_ , nxt = _abi.asfh_scan(mixed, 0)
+    assert n == 2 and nxt == 2 * (32 + 16384) and int(prm[0]) == 0
