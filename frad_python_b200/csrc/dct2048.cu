@@ -521,14 +521,6 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
 }  // namespace
 
 // eligibility checks shared with transform.cu
-bool frad_fast2048_encode_ok(const enc_params& P, int prec) {
-  if (P.N != FN || prec != FRAD_PREC_F32 || P.pcm_dtype != FRAD_F32) return false;
-  if (P.C > FW && (P.C % 4) != 0) return false;
-  if (P.profile == 0 && (P.bits != 32 || (P.payload_stride % 16) != 0 || ((uintptr_t)P.payload % 16) != 0)) return false;
-  if (P.profile != 0 && ((uintptr_t)P.q % 16) != 0) return false;
-  if (((uintptr_t)P.pcm % 16) != 0 || ((P.hop * P.C) % 4) != 0) return false;
-  return true;
-}
 bool frad_fast2048_decode_ok(const dec_params& P, int prec) {
   (void)prec;
   if (P.N != FN || (P.C > FW && (P.C % 4) != 0)) return false;

@@ -11,6 +11,9 @@
 //   * global I/O of the stereo tiling is 32 bytes per thread and instruction (LDG.256 / STG.256): four samples x two
 //     channels in, four bins x two channels out.
 //
+// The kernel is a template over the arithmetic type: float for f16 / f32 PCM, double for integer and f64 PCM -- the reference's
+// rule (scipy transforms in the input's precision, and to_f64 makes every integer format float64) -- and reads
+// every sample format of backend/pcmformat.py:4-32.  Profile 0 packs all six depths of profile0.py:28-42 in its store phase.
 // Measured against the first kernel (15 000 stereo frames, B200): see profiles/README.md.
 // Reference lines: fourier/profile0.py:21-30; fourier/profile1.py:21-40; fourier/tools/p1tools.py:18-44.
 #include "tile2048.cuh"
@@ -20,23 +23,30 @@ namespace {
 constexpr int ESEQ = 1088;                           // complex slots per warp buffer: 2176 words = the padded spectrum layout
 __device__ __forceinline__ int xpos(int k) { return k + ((k >> 6) << 2); }
 
-struct enc_tail {
+// int32 position of quantised bin k inside a sequence buffer: the lane that owns the run writes it into its own run
+// (f32: in place, word for word; f64: the first half of the 8-byte run, so no lane writes where another still reads)
+template <typename T> __device__ __forceinline__ int qpos(int k) {
+  if constexpr (sizeof(T) == 8) return 136 * (k >> 6) + (k & 63);
+  else return xpos(k);
+}
+
+template <typename T> struct enc_tail {
   int lo[FRAD_NBANDS + 1];
   double thr[FW][FRAD_NBANDS + 1];
   double inv_ns[FRAD_NBANDS + 1];                     // 1 / (band width x scale)
   float4 bp[FW][FRAD_NBANDS + 1];                     // per band: ramp end points (pre-scaled), lo, hi as floats
-  float part[FW][64];                                 // (lane, band) partial energies at slot lane + band (a staircase)
+  T part[FW][64];                                     // (lane, band) partial energies at slot lane + band (a staircase)
 };
 
 // exact quantiser of one coefficient (the f64 formula of profile1.py:31-36 with np.linspace's ramp)
-__device__ __noinline__ int quant_exact_r(float x, int j, double t0, double step, double scale) {
+__device__ __noinline__ int quant_exact_r(double x, int j, double t0, double step, double scale) {
   const double div = __dadd_rn(__dmul_rn((double)j, step), t0);
   if (div == 0.0) return 0;
-  const double yy = fabs(((double)x / div) * scale);
+  const double yy = fabs((x / div) * scale);
   const double rr = rint(sqrt(yy * sqrt(yy)));
   if (!(rr == rr)) return 0;
   const int m = (rr >= 2147483647.0) ? 2147483647 : (int)rr;
-  return (x < 0.0f) ? -m : m;
+  return (x < 0.0) ? -m : m;
 }
 __device__ __noinline__ int tq_exact_r(double thr, double log_base) {
   const double vv = log(fmax(thr, 1.0)) / log_base;
@@ -58,19 +68,70 @@ __device__ __forceinline__ void stg256(void* p, const w8& r) {
                : "memory");
 }
 
-template <int PROFILE, int CT>
-__global__ void __launch_bounds__(FW * 32, FRAD_MINB)
-enc2048r_kernel(enc_params P, plan_dev pl, const float2* __restrict__ tw32, int force_exact, int wide) {
+// ---- profile-0 value packing of the store phase (profile0.py:28-42): four consecutive values -> 4 * bits / 8 bytes --------
+// image of one value in stream order (first stream byte in the low byte)
+template <typename T> __device__ __forceinline__ uint64_t p0_image(T x, int bits, bool le) {
+  if (bits == 16) { const uint32_t h = f2h_bits(x); return le ? h : (uint64_t)__byte_perm(h, 0, 0x4401); }
+  if (bits == 32) { const uint32_t u = f2f_bits(x); return le ? u : (uint64_t)__byte_perm(u, 0, 0x0123); }
+  if (bits == 24) { const uint32_t u = f2f_bits(x); return le ? (u >> 8) : (uint64_t)__byte_perm(u, 0, 0x4123); }   // top 3 bytes
+  const uint64_t u = f2d_bits(x);
+  if (bits == 64 || bits == 48) {
+    if (le) return bits == 64 ? u : (u >> 16);
+    const uint64_t sw = ((uint64_t)__byte_perm((uint32_t)u, 0, 0x0123) << 32) | __byte_perm((uint32_t)(u >> 32), 0, 0x0123);
+    return bits == 64 ? sw : (sw & 0xffffffffffffull);                        // big endian: the six most significant bytes first
+  }
+  return 0;
+}
+// dst: start of the four values' bytes (4-byte aligned for every depth because value index vi is a multiple of 4)
+template <typename T> __device__ __forceinline__ void p0_store4(uint8_t* dst, const T* v, int bits, bool le) {
+  if (bits == 12) {                          // top 12 bits of the big-endian half, nibble-packed (always big endian)
+    const uint32_t a = f2h_bits(v[0]) >> 4, b = f2h_bits(v[1]) >> 4, c = f2h_bits(v[2]) >> 4, d = f2h_bits(v[3]) >> 4;
+    const uint32_t w0 = (a >> 4) | (((a & 15u) << 4 | (b >> 8)) << 8) | ((b & 255u) << 16) | ((c >> 4) << 24);
+    const uint32_t w1 = ((c & 15u) << 4 | (d >> 8)) | ((d & 255u) << 8);
+    if (((uintptr_t)dst & 3) == 0) { *(uint32_t*)dst = w0; *(uint16_t*)(dst + 4) = (uint16_t)w1; }
+    else { *(uint16_t*)dst = (uint16_t)w0; *(uint32_t*)(dst + 2) = (w0 >> 16) | (w1 << 16); }
+    return;
+  }
+  const uint64_t a = p0_image(v[0], bits, le), b = p0_image(v[1], bits, le), c = p0_image(v[2], bits, le), d = p0_image(v[3], bits, le);
+  switch (bits) {
+    case 16: *(uint2*)dst = make_uint2((uint32_t)(a | (b << 16)), (uint32_t)(c | (d << 16))); break;
+    case 24: {
+      uint32_t* w = (uint32_t*)dst;
+      w[0] = (uint32_t)(a | (b << 24)); w[1] = (uint32_t)((b >> 8) | (c << 16)); w[2] = (uint32_t)((c >> 16) | (d << 8));
+      break;
+    }
+    case 32: *(uint4*)dst = make_uint4((uint32_t)a, (uint32_t)b, (uint32_t)c, (uint32_t)d); break;
+    case 48: {
+      uint64_t* q = (uint64_t*)dst;
+      q[0] = a | (b << 48); q[1] = (b >> 16) | (c << 32); q[2] = (c >> 32) | (d << 16);
+      break;
+    }
+    default: {
+      uint4* q = (uint4*)dst;
+      q[0] = make_uint4((uint32_t)a, (uint32_t)(a >> 32), (uint32_t)b, (uint32_t)(b >> 32));
+      q[1] = make_uint4((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)d, (uint32_t)(d >> 32));
+    }
+  }
+}
+
+template <typename T, int PROFILE, int CT>
+__global__ void __launch_bounds__(FW * 32, (sizeof(T) == 8) ? 3 : FRAD_MINB)
+enc2048r_kernel(enc_params P, plan_dev pl, const typename vec2<T>::type* __restrict__ tw32, int force_exact, int wide) {
+  typedef typename vec2<T>::type V;
+  typedef enc_tail<T> TAIL;
+  constexpr bool F32 = sizeof(T) == 4;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2* seq_all = (float2*)smem_raw;
-  enc_tail* tail = (enc_tail*)(smem_raw + (size_t)FW * ESEQ * sizeof(float2));
+  V* seq_all = (V*)smem_raw;
+  TAIL* tail = (TAIL*)(smem_raw + (size_t)FW * ESEQ * sizeof(V));
   const int C = (CT == 1 || CT == 2) ? CT : P.C;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const tile_map tm = make_tiles<CT>(P.B, C);
   const float* pcm = (const float*)P.pcm;
-  const float2* cfh = (const float2*)pl.cfh;
-  const float2* dfh = (const float2*)pl.dfh;
+  const V* cfh = (const V*)pl.cfh;
+  const V* dfh = (const V*)pl.dfh;
   const int words_per_frame = FN * C;
+  const bool raw32 = F32 && P.pcm_dtype == FRAD_F32;       // f32 samples travel as 32-bit words, no conversion
+  const bool p0_words = (PROFILE == 0) && F32 && P.bits == 32;   // profile 0 at 32 bits: byte order applied in registers, words copied
 
   // ---- static run description of this lane: band of bin 64 lane, and the bins of the run where a new band starts ----
   int bfirst = 0;
@@ -97,7 +158,7 @@ enc2048r_kernel(enc_params P, plan_dev pl, const float2* __restrict__ tw32, int 
     const int nf = min(tm.fpc, P.B - b0);
     const int nseq = (CT == 4) ? 4 : nf * C;              // sequences (= busy warps) in this tile
     __syncthreads();                                      // previous tile fully stored before restaging
-    if (CT == 2 && wide) {
+    if (F32 && CT == 2 && wide) {
       // thread t takes the sample quads m = t + 128 i of both frames: 32 bytes = samples 4m .. 4m+3 of both channels.
       // Makhoul order: z[m] = (x[4m], x[4m+2]), z[1023 - m] = (x[4m+3], x[4m+1])  (see zword)
       w8 qd[8];
@@ -123,9 +184,25 @@ enc2048r_kernel(enc_params P, plan_dev pl, const float2* __restrict__ tw32, int 
           }
         }
       }
+    } else if (raw32) {
+      if constexpr (F32)
+        stage_tile<CT, ESEQ * 2>([&](int f) { return (const uint32_t*)(pcm + (size_t)(b0 + f) * P.hop * C); }, (uint32_t*)seq_all, C, nf,
+                                 grp, tid, [](int n) { return zword(n); });
     } else {
-      stage_tile<CT, ESEQ * 2>([&](int f) { return (const uint32_t*)(pcm + (size_t)(b0 + f) * P.hop * C); }, (uint32_t*)seq_all, C, nf,
-                               grp, tid, [](int n) { return zword(n); });
+      // any sample format (backend/pcmformat.py:34-47: integers become x / 2^(bits-1), unsigned ones minus 1), converted to T on
+      // the way in; consecutive threads read consecutive samples of the tile's channels
+      T* zall = (T*)seq_all;
+      const int Cg = (CT == 4) ? 4 : C, c0 = (CT == 4) ? 4 * grp : 0;
+      for (int f = 0; f < nf; f++) {
+        const int64_t fbase = (int64_t)(b0 + f) * P.hop * C + c0;
+        for (int e = tid; e < FN * Cg; e += FW * 32) {
+          int n, cc;
+          if (CT == 1) { n = e; cc = 0; } else if (CT == 2) { n = e >> 1; cc = e & 1; }
+          else if (CT == 4) { n = e >> 2; cc = e & 3; } else { n = e / C; cc = e - n * C; }
+          const int sq = (CT == 4) ? cc : f * C + cc;
+          zall[(size_t)sq * (2 * ESEQ) + zword(n)] = load_pcm<T>(P.pcm, P.pcm_dtype, fbase + (int64_t)n * C + cc);
+        }
+      }
     }
     __syncthreads();
     {   // pull the next tile of this CTA towards L2 while the current one is transformed
@@ -133,102 +210,108 @@ enc2048r_kernel(enc_params P, plan_dev pl, const float2* __restrict__ tw32, int 
       if (nt < tm.ntiles) {
         const int nb0 = (CT == 4) ? nt / tm.groups : nt * tm.fpc;
         const int nnf = min(tm.fpc, P.B - nb0);
-        const char* base = (const char*)(pcm + (size_t)nb0 * P.hop * C);
-        const size_t bytes = (size_t)nnf * words_per_frame * 4;
+        const size_t es = (size_t)pcm_size(P.pcm_dtype);
+        const char* base = (const char*)P.pcm + (size_t)nb0 * P.hop * C * es;
+        const size_t bytes = (size_t)nnf * words_per_frame * es;
         for (size_t o = (size_t)tid * 128; o < bytes; o += (size_t)FW * 32 * 128)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(base + o));
       }
     }
     if (w < nseq) {
       const int f = (CT == 4) ? 0 : w / C, c = (CT == 4) ? 4 * grp + w : w - f * C, b = b0 + f;
-      float2* buf = seq_all + (size_t)w * ESEQ;
-      float* X = (float*)buf;
-      float2 v[32];
+      V* buf = seq_all + (size_t)w * ESEQ;
+      T* X = (T*)buf;
+      V v[32];
 #pragma unroll
       for (int i = 0; i < 32; i++) v[i] = buf[lane + 33 * i];
       __syncwarp();
-      fft1024_warp<float, false>(v, buf, lane, tw32);
+      fft1024_warp<T, false>(v, buf, lane, tw32);
       __syncwarp();                                       // every lane has read its exchange rows: the buffer becomes X
       // ---- pairwise real-FFT split + DCT twiddle: (k, M-k) -> X[k], X[N-k], X[M-k], X[M+k], k = lane + 32 o.
       //      Padded positions: two steps of o move 64 bins = 68 words, so every store takes an immediate offset from one of
       //      eight per-lane bases (k, M+k ascending; N-k, M-k descending; even and odd o) ----
       const int partner = (32 - lane) & 31;
-      const bool swap_out = (PROFILE == 0) && !P.le;
-      float mx = 0.0f;
+      const bool swap_out = p0_words && !P.le;
+      T mx = T(0);
       const int oK[2] = {xpos(lane), xpos(lane + 32)};
       const int oMK[2] = {xpos(FM + lane), xpos(FM + lane + 32)};
       const int oNK[2] = {xpos(FN - lane), xpos(FN - lane - 32)};             // o = 0, lane 0 (bin 2048) is never stored
       const int oMmK[2] = {xpos(FM - lane), xpos(FM - lane - 32)};
-      auto put = [&](int pos, float val) {
+      auto put = [&](int pos, T val) {
         if (PROFILE == 0) {
-          mx = fmaxf(mx, fabsf(val));
-          if (swap_out) val = __uint_as_float(__byte_perm(__float_as_uint(val), 0, 0x0123));
+          mx = fmax(mx, fabs(val));
+          if constexpr (F32) { if (swap_out) val = __uint_as_float(__byte_perm(__float_as_uint(val), 0, 0x0123)); }
         }
         X[pos] = val;
       };
+      const T r2 = (T)FRAD_RSQRT2;
 #pragma unroll
       for (int o = 0; o < 16; o++) {
-        const float2 snd = (lane == 0) ? v[(32 - o) & 31] : v[31 - o];
-        float2 zm;
-        zm.x = __shfl_sync(0xffffffffu, snd.x, partner);
-        zm.y = -__shfl_sync(0xffffffffu, snd.y, partner);                   // conj(Z[M-k])
+        const V snd = (lane == 0) ? v[(32 - o) & 31] : v[31 - o];
+        V zm;
+        zm.x = shfl_t<T>(snd.x, partner);
+        zm.y = -shfl_t<T>(snd.y, partner);                                  // conj(Z[M-k])
         const int k = lane + 32 * o;
         const bool first = (o == 0) && (lane == 0);
-        const float2 A = cadd(v[o], zm), D = csub(v[o], zm);
-        const float2 Bv = make_float2(D.y, -D.x);
-        const float2 Pk = cmul(__ldg(cfh + k), A), Qk = cmul(__ldg(dfh + k), Bv);
-        const float2 y = cadd(Pk, Qk), t = csub(Pk, Qk);
+        const V A = cadd(v[o], zm), D = csub(v[o], zm);
+        const V Bv = mk2<T>(D.y, -D.x);
+        const V Pk = cmul(__ldg(cfh + k), A), Qk = cmul(__ldg(dfh + k), Bv);
+        const V y = cadd(Pk, Qk), t = csub(Pk, Qk);
         const int h = o >> 1, e = o & 1;
         put(oK[e] + 68 * h, y.x);
         if (!first) put(oNK[e] - 68 * h, -y.y);
-        put(oMmK[e] - 68 * h, (t.x - t.y) * (float)FRAD_RSQRT2);
-        if (!first) put(oMK[e] + 68 * h, (t.x + t.y) * (float)FRAD_RSQRT2);
+        put(oMmK[e] - 68 * h, (t.x - t.y) * r2);
+        if (!first) put(oMK[e] + 68 * h, (t.x + t.y) * r2);
       }
       if (lane == 0) {                                                     // self-paired bin k = 512 (and N - 512)
-        const float2 zk = v[16], zm = cconj(v[16]);
-        const float2 A = cadd(zk, zm), D = csub(zk, zm);
-        const float2 Bv = make_float2(D.y, -D.x);
-        const float2 y = cadd(cmul(__ldg(cfh + FM / 2), A), cmul(__ldg(dfh + FM / 2), Bv));
+        const V zk = v[16], zm = cconj(v[16]);
+        const V A = cadd(zk, zm), D = csub(zk, zm);
+        const V Bv = mk2<T>(D.y, -D.x);
+        const V y = cadd(cmul(__ldg(cfh + FM / 2), A), cmul(__ldg(dfh + FM / 2), Bv));
         put(xpos(FM / 2), y.x);
         put(xpos(FN - FM / 2), -y.y);
       }
       if (PROFILE == 0) {
         if (P.peak) {
 #pragma unroll
-          for (int s = 16; s > 0; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+          for (int s = 16; s > 0; s >>= 1) mx = fmax(mx, (T)__shfl_xor_sync(0xffffffffu, mx, s));
           if (lane == 0) atomicMax((unsigned long long*)&P.peak[b], (unsigned long long)__double_as_longlong((double)mx));
         }
       } else {
         __syncwarp();
         // ---- the lane's run: bins [64 lane, 64 lane + 64), sixteen 16-byte loads (conflict-free: 68-word pitch).
         //      Band energies of the spectrum (scaled below): running sum, closed where a new band starts ----
-        const float4* run = (const float4*)(X + 68 * lane);
+        const T* run = X + 68 * lane;
         {
-          float* slot = tail->part[w] + lane + bfirst;
-          float acc = 0.0f;
+          T* slot = tail->part[w] + lane + bfirst;
+          T acc = T(0);
 #pragma unroll
           for (int i = 0; i < 16; i++) {
-            const float4 t = run[i];
-            const float xe[4] = {t.x, t.y, t.z, t.w};
+            T xe[4];
+            if constexpr (F32) { const float4 t = ((const float4*)run)[i]; xe[0] = t.x; xe[1] = t.y; xe[2] = t.z; xe[3] = t.w; }
+            else {
+              const double2 t0 = ((const double2*)run)[2 * i], t1 = ((const double2*)run)[2 * i + 1];
+              xe[0] = t0.x; xe[1] = t0.y; xe[2] = t1.x; xe[3] = t1.y;
+            }
 #pragma unroll
             for (int e = 0; e < 4; e++) {
               const int j = 4 * i + e;
-              if (j > 0 && flag(j)) { *slot = acc; slot++; acc = 0.0f; }
-              acc = fmaf(xe[e], xe[e], acc);
+              if (j > 0 && flag(j)) { *slot = acc; slot++; acc = T(0); }
+              acc = fma(xe[e], xe[e], acc);
             }
           }
           *slot = acc;
         }
         __syncwarp();
-        const float scalef = (float)P.scale;
+        const T scalef = (T)P.scale;
         const float inv_log_base_f = (float)(1.0 / 0.30685281944005469058);   // 1 / ln(e/2)
-        float tot = 0.0f;
+        T tot = T(0);
         int cnt = 1;
         if (lane < FRAD_NBANDS) {
           const int blo = tail->lo[lane], bhi = tail->lo[lane + 1];
           cnt = bhi - blo;
           if (bhi > blo) {
-            const float* row = tail->part[w] + lane;
+            const T* row = tail->part[w] + lane;
             for (int l = blo >> 6; l <= (bhi - 1) >> 6; l++) tot += row[l];
           }
           tot *= scalef * scalef;
@@ -237,9 +320,11 @@ enc2048r_kernel(enc_params P, plan_dev pl, const float2* __restrict__ tw32, int 
         const int first_empty = empty ? (__ffs(empty) - 1) : 32;
         double thr = 0.0;
         if (lane < FRAD_NBANDS && lane < first_empty) {
-          // f32 like the reference for f32 spectra: np.sqrt(np.mean(x**2)) ** 0.8 on float32 (p1tools.py:32)
-          const float level = powf(sqrtf(tot / (float)cnt), 0.8f);
-          thr = fmax((double)level, P.bt->ath[lane]) * P.loss;
+          // in the spectrum's precision like the reference: np.sqrt(np.mean(x**2)) ** 0.8 on float32 / float64 (p1tools.py:32)
+          double level;
+          if constexpr (F32) level = (double)powf(sqrtf(tot / (float)cnt), 0.8f);
+          else level = pow(sqrt(tot / (double)cnt), 0.8);
+          thr = fmax(level, P.bt->ath[lane]) * P.loss;
         }
         if (lane <= FRAD_NBANDS) tail->thr[w][lane] = thr;             // entry 27 = 0
         if (lane < FRAD_NBANDS) {
@@ -282,13 +367,22 @@ enc2048r_kernel(enc_params P, plan_dev pl, const float2* __restrict__ tw32, int 
           const float4* bpp = tail->bp[w] + bfirst;
           float4 bpv = *bpp;
           const float kb = (float)(64 * lane);
-          int4* qrun = (int4*)(X + 68 * lane);
+          int4* qrun = (int4*)((int*)X + qpos<T>(64 * lane));
 #pragma unroll 1
           for (int g = 0; g < 8; g++) {
             int ms[8];
             bool allok = true;
-            const float4 xa = run[2 * g], xb = run[2 * g + 1];
-            const float xs[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+            T xt[8];
+            if constexpr (F32) {
+              const float4 xa = ((const float4*)run)[2 * g], xb = ((const float4*)run)[2 * g + 1];
+              xt[0] = xa.x; xt[1] = xa.y; xt[2] = xa.z; xt[3] = xa.w; xt[4] = xb.x; xt[5] = xb.y; xt[6] = xb.z; xt[7] = xb.w;
+            } else {
+#pragma unroll
+              for (int u2 = 0; u2 < 4; u2++) { const double2 t = ((const double2*)run)[4 * g + u2]; xt[2 * u2] = t.x; xt[2 * u2 + 1] = t.y; }
+            }
+            float xs[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) xs[u] = (float)xt[u];
             const uint32_t fb = ((g < 4) ? (fl_lo >> (8 * g)) : (fl_hi >> (8 * g - 32))) & (g == 0 ? 0xfeu : 0xffu);   // band starts in this group
             const float kg = kb + (float)(8 * g);
 #pragma unroll
@@ -314,7 +408,7 @@ enc2048r_kernel(enc_params P, plan_dev pl, const float2* __restrict__ tw32, int 
             if (!allok || force_exact) {
 #pragma unroll
               for (int u = 0; u < 8; u++) {
-                const int j = 8 * g + u;
+                const int j = 8 * g + u;                 // bin of the run
                 // band of bin j of the run: the first one plus the band starts up to j
                 const unsigned long long fl = ((unsigned long long)fl_hi << 32) | fl_lo;
                 const int bn = bfirst + __popcll(fl & ((j >= 63) ? ~0ull : ((2ull << j) - 1ull)));
@@ -334,7 +428,7 @@ enc2048r_kernel(enc_params P, plan_dev pl, const float2* __restrict__ tw32, int 
                 if (redo && bn != FRAD_NBANDS - 1) {
                   const int lo = tail->lo[bn], n = tail->lo[bn + 1] - lo;
                   const double t0 = tail->thr[w][bn], t1 = tail->thr[w][bn + 1];
-                  ms[u] = quant_exact_r(xs[u], 64 * lane + j - lo, t0, (t1 - t0) / (double)n, P.scale);
+                  ms[u] = quant_exact_r((double)xt[u], 64 * lane + j - lo, t0, (t1 - t0) / (double)n, P.scale);
                 }
               }
             }
@@ -345,8 +439,9 @@ enc2048r_kernel(enc_params P, plan_dev pl, const float2* __restrict__ tw32, int 
       }
     }
     __syncthreads();
-    // ---- cooperative, coalesced store: word e = k*C + c of frame f <- seq[f*C + c][xpos(k)] ----
-    if (CT == 2 && wide) {
+    // ---- cooperative, coalesced store: value e = k*C + c of frame f <- seq[f*C + c][xpos(k)] ----
+    const bool words = (PROFILE != 0) || p0_words;           // 32-bit words copied as they are (quantised ints / finished f32 words)
+    if (F32 && CT == 2 && wide && words) {
 #pragma unroll
       for (int f = 0; f < 2; f++) {
         if (f < nf) {
@@ -365,14 +460,30 @@ enc2048r_kernel(enc_params P, plan_dev pl, const float2* __restrict__ tw32, int 
           }
         }
       }
-    } else {
+    } else if (words) {
+      constexpr int STRIDE_W = ESEQ * 2 * (int)(sizeof(T) / 4);         // 32-bit words per sequence buffer
       for (int f = 0; f < nf; f++) {
         uint32_t* dst = (PROFILE == 0) ? (uint32_t*)(P.payload + (size_t)(b0 + f) * P.payload_stride)
                                        : (uint32_t*)(P.q + (size_t)(b0 + f) * words_per_frame);
         for (int e4 = tid; e4 < vec_count<CT>(C); e4 += FW * 32) {
           uint32_t o4[4];
-          gather4<CT, ESEQ * 2>((const uint32_t*)seq_all, C, f, e4, [](int k) { return xpos(k); }, [](uint32_t u) { return u; }, o4);
+          gather4<CT, STRIDE_W>((const uint32_t*)seq_all, C, f, e4, [](int k) { return (PROFILE == 0) ? xpos(k) : qpos<T>(k); },
+                                [](uint32_t u) { return u; }, o4);
           *(uint4*)(dst + vec_word<CT>(e4, C, grp)) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+        }
+      }
+    } else {
+      // profile 0 at the other depths (and from a double spectrum): four consecutive values -> their bytes (profile0.py:28-42)
+      if constexpr (PROFILE == 0) {
+        const bool le = P.le != 0;
+        for (int f = 0; f < nf; f++) {
+          uint8_t* frame = P.payload + (size_t)(b0 + f) * P.payload_stride;
+          for (int e4 = tid; e4 < vec_count<CT>(C); e4 += FW * 32) {
+            T o4[4];
+            gather4<CT, ESEQ * 2>((const T*)seq_all, C, f, e4, [](int k) { return xpos(k); }, [](T u) { return u; }, o4);
+            const size_t vi = (size_t)vec_word<CT>(e4, C, grp);          // index of the first of the four values
+            p0_store4<T>(frame + (P.bits == 12 ? vi * 3 / 2 : vi * (size_t)(P.bits >> 3)), o4, P.bits, le);
+          }
         }
       }
     }
@@ -381,29 +492,46 @@ enc2048r_kernel(enc_params P, plan_dev pl, const float2* __restrict__ tw32, int 
 
 }  // namespace
 
-#define ENCR_DISPATCH(PROF, CT)                                                                              \
+#define ENCR_DISPATCH(TT, PROF, CT)                                                                          \
   do {                                                                                                       \
-    auto k = enc2048r_kernel<PROF, CT>;                                                                      \
+    auto k = enc2048r_kernel<TT, PROF, CT>;                                                                  \
     const tile_map tm = make_tiles<CT>(P.B, P.C);                                                            \
     int grid;                                                                                                \
+    const size_t smem = (size_t)FW * ESEQ * sizeof(vec2<TT>::type) + ((PROF == 0) ? 16 : sizeof(enc_tail<TT>)); \
     int rc = launch_cfg(ctx, k, smem, tm.ntiles, &grid);                                                     \
     if (rc) return rc;                                                                                       \
-    k<<<grid, FW * 32, smem, ctx->stream>>>(P, plan_view(pl), (const float2*)pl->tw32, force_exact, wide);   \
+    k<<<grid, FW * 32, smem, ctx->stream>>>(P, plan_view(pl), (const vec2<TT>::type*)pl->tw32, force_exact, wide); \
   } while (0)
 
+#define ENCR_BY_C(TT, PROF)                                                                             \
+  do {                                                                                                  \
+    if (P.C == 2) ENCR_DISPATCH(TT, PROF, 2); else if (P.C == 1) ENCR_DISPATCH(TT, PROF, 1);            \
+    else if (P.C % 4 == 0) ENCR_DISPATCH(TT, PROF, 4); else ENCR_DISPATCH(TT, PROF, 0);                 \
+  } while (0)
+
+// eligibility (transform.cu asks before it takes this path)
+bool frad_fast2048_encode_ok(const enc_params& P, int prec) {
+  if (P.N != FN || (prec != FRAD_PREC_F32 && prec != FRAD_PREC_F64)) return false;
+  if (P.C > FW && (P.C % 4) != 0) return false;
+  if (prec == FRAD_PREC_F64 && P.profile == 2) return false;      // the TNS kernel takes an f32 spectrum from this path
+  if (P.profile == 0) {
+    if ((P.payload_stride % 16) != 0 || ((uintptr_t)P.payload % 16) != 0) return false;
+    if (P.bits != 12 && P.bits != 16 && P.bits != 24 && P.bits != 32 && P.bits != 48 && P.bits != 64) return false;
+  } else if (((uintptr_t)P.q % 16) != 0) return false;
+  if (P.pcm_dtype == FRAD_F32 && prec == FRAD_PREC_F32 && ((((uintptr_t)P.pcm) % 16) != 0 || ((P.hop * P.C) % 4) != 0)) return false;
+  return true;
+}
+
 int frad_launch_encode_2048r(frad_ctx* ctx, const enc_params& P, const frad_plan* pl, int prec, int force_exact) {
-  (void)prec;
-  const size_t smem = (size_t)FW * ESEQ * sizeof(float2) + ((P.profile == 0) ? 16 : sizeof(enc_tail));
   // 32-byte global accesses of the stereo tiling need 32-byte aligned frames on both sides
   const void* out = (P.profile == 0) ? (const void*)P.payload : (const void*)P.q;
-  const int wide = (P.C == 2 && ((uintptr_t)P.pcm % 32) == 0 && ((P.hop * 2) % 8) == 0 && ((uintptr_t)out % 32) == 0 &&
-                    (P.profile != 0 || (P.payload_stride % 32) == 0)) ? 1 : 0;
-#define ENCR_BY_C(PROF)                                                                                 \
-  do {                                                                                                  \
-    if (P.C == 2) ENCR_DISPATCH(PROF, 2); else if (P.C == 1) ENCR_DISPATCH(PROF, 1);                    \
-    else if (P.C % 4 == 0) ENCR_DISPATCH(PROF, 4); else ENCR_DISPATCH(PROF, 0);                         \
-  } while (0)
-  if (P.profile == 0) ENCR_BY_C(0); else if (P.profile == 1) ENCR_BY_C(1); else ENCR_BY_C(2);   // 2: P.tns_scratch = thresholds out
+  const int wide = (P.C == 2 && prec == FRAD_PREC_F32 && P.pcm_dtype == FRAD_F32 && ((uintptr_t)P.pcm % 32) == 0 &&
+                    ((P.hop * 2) % 8) == 0 && ((uintptr_t)out % 32) == 0 && (P.profile != 0 || (P.payload_stride % 32) == 0)) ? 1 : 0;
+  if (prec == FRAD_PREC_F32) {
+    if (P.profile == 0) ENCR_BY_C(float, 0); else if (P.profile == 1) ENCR_BY_C(float, 1); else ENCR_BY_C(float, 2);   // 2: P.tns_scratch = thresholds out
+  } else {
+    if (P.profile == 0) ENCR_BY_C(double, 0); else ENCR_BY_C(double, 1);
+  }
   FRAD_LAUNCH_CHECK(ctx);
   return FRAD_OK;
 }

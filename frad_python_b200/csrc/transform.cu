@@ -728,6 +728,7 @@ static int launch_encode(frad_ctx* ctx, enc_params& P, int prec) {
   }
 #ifdef FRAD_HAVE_FAST2048
   if (!ctx->opt_force_generic && frad_fast2048_encode_ok(P, prec)) {
+    P.fast_ok = 2;                                   // tells the caller that 12-bit payloads are already nibble-packed
     if (P.profile != 2) return frad_launch_encode_2048(ctx, P, pl, prec, ctx->opt_exact_quant);
     // profile 2: transform + thresholds, then the TNS kernel (one CTA per sequence, masked spectrum and residual in smem)
     double* thr = (double*)frad_scratch(ctx, 4, sizeof(double) * (size_t)nseq * (FRAD_NBANDS + 1));
@@ -875,7 +876,7 @@ static int lossless_encode_dev(frad_ctx* ctx, int profile, const void* pcm, int 
     rc = launch_encode(ctx, P, resolve_prec_fwd(prec, pcm_dtype));
   }
   if (rc) return rc;
-  if (bits == 12 && B > 0) {
+  if (bits == 12 && B > 0 && P.fast_ok != 2) {
     size_t total = ((nvals + 1) / 2) * (size_t)B;
     int grid = (int)((total + 255) / 256); if (grid > ctx->sm_count * 16) grid = ctx->sm_count * 16;
     pack12_kernel<<<grid, 256, 0, ctx->stream>>>(P.half_scratch, nvals, B, payload, payload_stride);

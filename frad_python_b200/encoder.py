@@ -38,6 +38,7 @@ class Encoder:
         self.fsize = 0
         self.srate = 0
         self.overlap_fragment = np.array([])
+        self._frag_raw = None
         self.pcm_format = ff_format_to_numpy_type(pcm_format)
         self.loss_level = 0.5
         self.init = False
@@ -147,18 +148,23 @@ class Encoder:
                 mv = memoryview(self.buffer)                  # views, not slices: a 32 MiB piece is copied once, not four times
                 raw = np.frombuffer(mv[:used * bps], self.pcm_format).reshape(-1, self.channels)
                 self.buffer = bytes(mv[used * bps:])
-                pcm = self._float_domain(raw, keep_native_ints=(frag_len == 0 and olap == 0))
+                # native-order integers stay raw (the device scales them like to_f64, pcmformat.py:34-47); a carried fragment is
+                # kept in the same raw form beside its float-domain twin, which the per-frame state machine below uses
+                fr_raw = self._frag_raw
+                raw_ok = frag_len == 0 or (fr_raw is not None and fr_raw.dtype == raw.dtype and len(fr_raw) == frag_len)
+                pcm = self._float_domain(raw, keep_native_ints=raw_ok)
                 if frag_len:
                     whole = np.empty((frag_len + len(pcm), self.channels), pcm.dtype)
-                    whole[:frag_len] = frag
+                    whole[:frag_len] = fr_raw if (raw_ok and pcm.dtype == raw.dtype) else frag
                     whole[frag_len:] = pcm
                     pcm = whole
                 ret.append(self._encode_frames(pcm, nframes, n, hop, [n] * nframes))
                 samples += used
                 if olap:
-                    self.overlap_fragment = np.array(pcm[nframes * hop:(nframes - 1) * hop + n])
+                    self._frag_raw = np.array(pcm[nframes * hop:(nframes - 1) * hop + n])
+                    self.overlap_fragment = self._float_domain(self._frag_raw)
                 else:
-                    self.overlap_fragment = np.array([])
+                    self._frag_raw, self.overlap_fragment = None, np.array([])
 
         # ---- remainder: the reference's own per-frame state machine (flush / odd states) -----------
         while True:
@@ -183,6 +189,7 @@ class Encoder:
                 cut = len(frame) * (self.asfh.overlap_ratio - 1) // self.asfh.overlap_ratio
                 nxt = frame[cut:]
             self.overlap_fragment = nxt
+            self._frag_raw = None
             if frame.size == 0 and self.overlap_fragment.ndim != 2:
                 ret.append(self.asfh.force_flush())
                 break

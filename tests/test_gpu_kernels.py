@@ -503,3 +503,62 @@ def test_fast2048_every_legal_sample_rate(ctx):
             out = ctx.p1_decode(q, tq, None, 3, 2048, c, 16, sr)
             want = np.stack([O.p1_digital_ints(q[i], tq[i], 16, c, sr, 2048) for i in range(3)])
             assert np.max(np.abs(out - want)) <= 1e-11 * max(1.0, np.max(np.abs(want))), (sr, c)
+
+
+@pytest.mark.parametrize("dtype", ["<f4", "<f8", "<i2", "<i4", "u1", "<f2"])
+def test_fast2048_encoder_every_sample_format_and_depth(ctx, dtype):
+    """Round 2: the N = 2048 encoder reads every sample format (backend/pcmformat.py:34-47) in the reference's precision
+    (f32 for f16 / f32 PCM, f64 for the rest) and packs all six profile-0 depths (profile0.py:28-42).
+    Checked against the generic kernels (A/B through FRAD_OPT_FORCE_GENERIC) and against the oracle."""
+    from frad_python_b200 import _abi
+    from frad_python_b200.backend import to_f64
+    f32 = O.synth_pcm(0.35, 48000, 2, seed=51)
+    dt = np.dtype(dtype)
+    if dt.kind == "f":
+        pcm = f32.astype(dt)
+    elif dt.kind == "i":
+        pcm = np.clip(np.round(f32.astype(np.float64) * 2 ** (8 * dt.itemsize - 1)), -2 ** (8 * dt.itemsize - 1), 2 ** (8 * dt.itemsize - 1) - 1).astype(dt)
+    else:
+        pcm = np.clip(np.round((f32.astype(np.float64) + 1) * 128), 0, 255).astype(dt)
+    nb = len(pcm) // 2048
+    ref_in = to_f64(pcm, dt) if dt.kind in "iu" else pcm                    # what the reference's transform sees
+    f64_path = not (dt.kind == "f" and dt.itemsize <= 4)
+    tol = TOL_F64 * 50 if f64_path else TOL_F32
+    for bits in (12, 16, 24, 32, 48, 64):
+        for le in (False, True):
+            fast, pk_f, _ = ctx.p0_encode(pcm, nb, 2048, 2048, bits, le)
+            ctx.set_option(_abi.OPT_FORCE_GENERIC, 1)
+            try:
+                gen, pk_g, _ = ctx.p0_encode(pcm, nb, 2048, 2048, bits, le)
+            finally:
+                ctx.set_option(_abi.OPT_FORCE_GENERIC, 0)
+            assert fast.shape == gen.shape
+            vf, vg = values(fast.tobytes(), bits, le), values(gen.tobytes(), bits, le)
+            # one unit in the last place of the stored format where the two transforms straddle a rounding boundary
+            ulp = {12: 2.0 ** -7, 16: 2.0 ** -10, 24: 2.0 ** -15, 32: 2.0 ** -23, 48: 2.0 ** -36, 64: 2.0 ** -52}[bits]
+            assert np.max(np.abs(vf - vg)) <= tol + ulp * np.max(np.abs(vg)), (dtype, bits, le)
+            if f64_path and bits <= 32:                   # two f64 transforms agree to ~1e-15: the stored values hardly ever differ
+                assert np.mean(vf != vg) <= 2e-3, (dtype, bits, le)
+            assert np.max(np.abs(pk_f - pk_g)) <= 1e-6
+            want = values(O.p0_analogue(ref_in[:2048], bits, 48000, le)[0], bits, le)
+            assert np.max(np.abs(vf[:4096] - want)) <= tol + ulp * np.max(np.abs(want)), (dtype, bits, le)
+    # profile 1 on the same input: integers within a step of the generic kernels and of the oracle
+    hop = 1920
+    nb1 = (len(pcm) - 2048) // hop + 1
+    q, tq, _ = ctx.p1_encode(pcm, nb1, 2048, hop, 16, 48000, LOSS0)
+    ctx.set_option(_abi.OPT_FORCE_GENERIC, 1)
+    try:
+        qg, tqg, _ = ctx.p1_encode(pcm, nb1, 2048, hop, 16, 48000, LOSS0)
+    finally:
+        ctx.set_option(_abi.OPT_FORCE_GENERIC, 0)
+    assert np.max(np.abs(q - qg)) <= 1 and np.mean(q != qg) <= 1e-4 and np.max(np.abs(tq - tqg)) <= 1
+    for i in (0, nb1 - 1):
+        oq, otq, *_ = O.p1_analogue_ints(ref_in[i * hop:i * hop + 2048], 16, 48000, LOSS0)
+        assert np.max(np.abs(q[i] - oq)) <= 1 and np.mean(q[i] != oq) <= 1e-3 and np.max(np.abs(tq[i] - otq)) <= 1
+    if f64_path:                                          # exact-branch consistency of the f64 kernel's quantiser
+        ctx.set_option(_abi.OPT_EXACT_QUANT, 1)
+        try:
+            q2, tq2, _ = ctx.p1_encode(pcm, nb1, 2048, hop, 16, 48000, LOSS0)
+        finally:
+            ctx.set_option(_abi.OPT_EXACT_QUANT, 0)
+        assert np.array_equal(q, q2) and np.array_equal(tq, tq2)
