@@ -164,6 +164,62 @@ __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
   return v;
 }
 
+// Eight consecutive profile-0 values from their bytes (profile0.py:51-66), word loads only: src is 4-byte aligned because
+// eight values take 12 / 16 / 24 / 48 / 64 bytes.  NaN / Inf become 0.
+__device__ __forceinline__ uint32_t byte_of(const uint32_t* w, int i) { return (w[i >> 2] >> (8 * (i & 3))) & 255u; }
+template <typename T> __device__ __forceinline__ void p0_load8(const uint8_t* src, int bits, bool le, T* out) {
+  const uint32_t* g = (const uint32_t*)src;
+  if (bits == 16 || bits == 12) {
+    uint32_t w[4];
+    if (bits == 16) { const uint4 a = __ldg((const uint4*)g); w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; }
+    else { w[0] = __ldg(g); w[1] = __ldg(g + 1); w[2] = __ldg(g + 2); w[3] = 0; }
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      uint32_t h;
+      if (bits == 16) {
+        h = (w[j >> 1] >> (16 * (j & 1))) & 0xffffu;
+        if (!le) h = ((h & 255u) << 8) | (h >> 8);
+      } else {
+        const int p = 3 * (j >> 1);
+        h = (j & 1) ? (((byte_of(w, p + 1) & 15u) << 8) | byte_of(w, p + 2)) : ((byte_of(w, p) << 4) | (byte_of(w, p + 1) >> 4));
+        h <<= 4;
+      }
+      const float f = __half2float(__ushort_as_half((unsigned short)h));
+      out[j] = (T)(((h & 0x7c00u) == 0x7c00u) ? 0.0f : f);
+    }
+  } else if (bits == 24) {
+    uint32_t w[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) w[i] = __ldg(g + i);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const uint32_t b0 = byte_of(w, 3 * j), b1 = byte_of(w, 3 * j + 1), b2 = byte_of(w, 3 * j + 2);
+      const uint32_t u = le ? ((b0 << 8) | (b1 << 16) | (b2 << 24)) : ((b0 << 24) | (b1 << 16) | (b2 << 8));
+      out[j] = (T)(((u & 0x7f800000u) == 0x7f800000u) ? 0.0f : __uint_as_float(u));
+    }
+  } else {
+    uint32_t w[16];
+    const int nw = (bits == 48) ? 12 : 16;
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+      if (i < nw) { const uint4 a = __ldg((const uint4*)(g + i)); w[i] = a.x; w[i + 1] = a.y; w[i + 2] = a.z; w[i + 3] = a.w; }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      uint64_t u = 0;
+      if (bits == 64) {
+        u = le ? (((uint64_t)w[2 * j + 1] << 32) | w[2 * j])
+               : (((uint64_t)__byte_perm(w[2 * j], 0, 0x0123) << 32) | __byte_perm(w[2 * j + 1], 0, 0x0123));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 6; i++) u |= (uint64_t)byte_of(w, 6 * j + i) << (le ? (16 + 8 * i) : (56 - 8 * i));
+      }
+      const double d = __longlong_as_double((long long)u);
+      out[j] = (T)((((u >> 52) & 0x7ffull) == 0x7ffull) ? 0.0 : d);
+    }
+  }
+}
+
 template <typename T, int PROFILE, int CT>
 __global__ void __launch_bounds__(FW * 32, (sizeof(T) == 8) ? 3 : FRAD_MINB)
 dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restrict__ tw32, const double* __restrict__ dq64) {
@@ -224,8 +280,9 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
 
   // the tile's 32-bit words travel through registers: those of tile t + gridDim.x are requested before tile t is stored
   uint4 x[tile_regs<CT>::NX];
+  const bool p0_any = (PROFILE == 0) && P.bits != 32;      // profile 0 at the other depths: values unpacked from bytes
   auto request_tile = [&](int t) {
-    if (CT == 0 || PROFILE == 2) return;
+    if (CT == 0 || PROFILE == 2 || p0_any) return;
     if (t >= tm.ntiles) t = tm.ntiles - 1;      // always overwrite x (no stale values kept alive across the transform): re-read the last tile
     const int tb0 = (CT == 4) ? t / tm.groups : t * tm.fpc;
     const int tgrp = (CT == 4) ? t - tb0 * tm.groups : 0;
@@ -381,7 +438,53 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
 #pragma unroll
       for (int j = 0; j < 4; j++) v[j] = coef(u[j], ks[j], sqs[j]);
     };
-    if constexpr (CT == 0) {
+    if (p0_any) {
+      // profile 0 at 12 / 16 / 24 / 48 / 64 bits (profile0.py:51-66): every value from its bytes, NaN / Inf scrubbed;
+      // consecutive threads take consecutive values of the tile's channels
+      if constexpr (PROFILE == 0) {
+        constexpr int STRIDE_T = LY::WARP_BYTES / (int)sizeof(T);
+        T* seq_base = (T*)smem_raw;
+        const int Cg = (CT == 4) ? 4 : C, c0 = (CT == 4) ? 4 * grp : 0;
+        const int bits = P.bits;
+        const bool le = P.le != 0;
+        for (int f = 0; f < nf; f++) {
+          const uint8_t* frame = P.payload + (size_t)(b0 + f) * P.payload_stride;
+          if constexpr (CT == 1 || CT == 2) {             // eight consecutive values per thread and step, word loads
+            for (int e8 = tid; e8 < FN * C / 8; e8 += FW * 32) {
+              T v8[8];
+              p0_load8<T>(frame + (size_t)e8 * bits, bits, le, v8);
+              if constexpr (CT == 2) {                    // bins 4 e8 .. 4 e8 + 3 of both channels
+                T* d0 = seq_base + (size_t)(2 * f) * STRIDE_T + 4 * e8;
+                T* d1 = d0 + STRIDE_T;
+#pragma unroll
+                for (int j = 0; j < 4; j++) { d0[j] = v8[2 * j]; d1[j] = v8[2 * j + 1]; }
+              } else {
+                T* d0 = seq_base + (size_t)f * STRIDE_T + 8 * e8;
+#pragma unroll
+                for (int j = 0; j < 8; j++) d0[j] = v8[j];
+              }
+            }
+            continue;
+          }
+          for (int idx = tid; idx < FN * Cg; idx += FW * 32) {
+            int k, cc;
+            if (CT == 1) { k = idx; cc = 0; } else if (CT == 2) { k = idx >> 1; cc = idx & 1; }
+            else if (CT == 4) { k = idx >> 2; cc = idx & 3; } else { k = idx / C; cc = idx - k * C; }
+            const size_t vi = (size_t)k * C + c0 + cc;
+            double v;
+            if (bits == 12) {                              // two values in three bytes, big-endian nibbles
+              const uint8_t* p3 = frame + (vi >> 1) * 3;
+              const uint32_t h12 = (vi & 1) ? (((uint32_t)(p3[1] & 15u) << 8) | p3[2]) : (((uint32_t)p3[0] << 4) | (p3[1] >> 4));
+              v = (double)__half2float(__ushort_as_half((unsigned short)(h12 << 4)));
+              if (!isfinite(v)) v = 0.0;
+            } else {
+              v = p0_load_value(frame + vi * (size_t)(bits >> 3), bits, le);
+            }
+            seq_base[(size_t)((CT == 4) ? cc : f * C + cc) * STRIDE_T + k] = (T)v;
+          }
+        }
+      }
+    } else if constexpr (CT == 0) {
       stage_convert_any<LY::WARP_BYTES / (int)sizeof(T), T>(
           [&](int f) {
             return (PROFILE == 0) ? (const uint32_t*)(P.payload + (size_t)(b0 + f) * P.payload_stride)
@@ -524,7 +627,7 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
 bool frad_fast2048_decode_ok(const dec_params& P, int prec) {
   (void)prec;
   if (P.N != FN || (P.C > FW && (P.C % 4) != 0)) return false;
-  if (P.profile == 0 && (P.bits != 32 || (P.payload_stride % 16) != 0 || ((uintptr_t)P.payload % 16) != 0)) return false;
+  if (P.profile == 0 && ((P.payload_stride % 16) != 0 || ((uintptr_t)P.payload % 16) != 0)) return false;
   if (P.profile == 2 && !P.spec) return false;
   if (P.profile == 1 && ((uintptr_t)P.q % 16) != 0) return false;
   if (((uintptr_t)P.pcm % 16) != 0) return false;

@@ -68,6 +68,47 @@ __device__ __forceinline__ void stg256(void* p, const w8& r) {
                : "memory");
 }
 
+// eight consecutive samples (index i0 .. i0 + 7 of the interleaved PCM, i0 a multiple of 8) of any format, as T
+template <typename T> __device__ __forceinline__ void load_quad8(const void* pcm, int dt, int64_t i0, T* q) {
+  switch (dt) {
+    case FRAD_F32: {
+      const uint4 a = __ldg((const uint4*)((const float*)pcm + i0)), b = __ldg((const uint4*)((const float*)pcm + i0) + 1);
+      const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int j = 0; j < 8; j++) q[j] = (T)__uint_as_float(w[j]);
+      break;
+    }
+    case FRAD_F64: {
+      const double2* p = (const double2*)((const double*)pcm + i0);
+#pragma unroll
+      for (int j = 0; j < 4; j++) { const double2 d = __ldg(p + j); q[2 * j] = (T)d.x; q[2 * j + 1] = (T)d.y; }
+      break;
+    }
+    case FRAD_S16: case FRAD_U16: case FRAD_F16: {
+      const uint4 a = __ldg((const uint4*)((const uint16_t*)pcm + i0));
+      const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const uint32_t h = (w[j >> 1] >> (16 * (j & 1))) & 0xffffu;
+        if (dt == FRAD_S16) q[j] = (T)((double)(int16_t)h / 32768.0);
+        else if (dt == FRAD_U16) q[j] = (T)((double)h / 32768.0 - 1.0);
+        else q[j] = (T)__half2float(__ushort_as_half((unsigned short)h));
+      }
+      break;
+    }
+    case FRAD_S32: case FRAD_U32: {
+      const uint4 a = __ldg((const uint4*)((const uint32_t*)pcm + i0)), b = __ldg((const uint4*)((const uint32_t*)pcm + i0) + 1);
+      const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int j = 0; j < 8; j++) q[j] = (dt == FRAD_S32) ? (T)((double)(int32_t)w[j] / 2147483648.0) : (T)((double)w[j] / 2147483648.0 - 1.0);
+      break;
+    }
+    default:
+#pragma unroll
+      for (int j = 0; j < 8; j++) q[j] = load_pcm<T>(pcm, dt, i0 + j);
+  }
+}
+
 // ---- profile-0 value packing of the store phase (profile0.py:28-42): four consecutive values -> 4 * bits / 8 bytes --------
 // image of one value in stream order (first stream byte in the low byte)
 template <typename T> __device__ __forceinline__ uint64_t p0_image(T x, int bits, bool le) {
@@ -188,6 +229,24 @@ enc2048r_kernel(enc_params P, plan_dev pl, const typename vec2<T>::type* __restr
       if constexpr (F32)
         stage_tile<CT, ESEQ * 2>([&](int f) { return (const uint32_t*)(pcm + (size_t)(b0 + f) * P.hop * C); }, (uint32_t*)seq_all, C, nf,
                                  grp, tid, [](int n) { return zword(n); });
+    } else if (CT == 2 && (P.hop % 4) == 0 && (((uintptr_t)P.pcm) % 16) == 0) {
+      // stereo, any sample format: a thread takes whole sample quads (4 samples x 2 channels = 8 values, 8 .. 64 bytes in
+      // one or two loads), converts them like to_f64 (pcmformat.py:34-47) and stores the two complex values per channel
+      for (int f = 0; f < nf; f++) {
+        V* s0 = seq_all + (size_t)(2 * f) * ESEQ;
+        V* s1 = seq_all + (size_t)(2 * f + 1) * ESEQ;
+        const int64_t fbase = (int64_t)(b0 + f) * P.hop * 2;
+#pragma unroll 2
+        for (int i = 0; i < 4; i++) {
+          const int m = tid + 128 * i;
+          T q[8];
+          load_quad8<T>(P.pcm, P.pcm_dtype, fbase + 8 * (int64_t)m, q);
+          s0[padc(m)] = mk2<T>(q[0], q[4]);
+          s0[padc(FM - 1 - m)] = mk2<T>(q[6], q[2]);
+          s1[padc(m)] = mk2<T>(q[1], q[5]);
+          s1[padc(FM - 1 - m)] = mk2<T>(q[7], q[3]);
+        }
+      }
     } else {
       // any sample format (backend/pcmformat.py:34-47: integers become x / 2^(bits-1), unsigned ones minus 1), converted to T on
       // the way in; consecutive threads read consecutive samples of the tile's channels
@@ -245,6 +304,20 @@ enc2048r_kernel(enc_params P, plan_dev pl, const typename vec2<T>::type* __restr
         X[pos] = val;
       };
       const T r2 = (T)FRAD_RSQRT2;
+      // f64: cf[k] = cf[lane] e^{-i pi o / 128}, df[k] = df[lane] e^{-i pi o / 128} e^{-i pi o / 32} for k = lane + 32 o -- one
+      // per-lane table value times a compile-time constant instead of two 16-byte loads per pair (the 32 KiB of tables do not
+      // stay in the little L1 that is left beside 3 x 70 KiB of shared memory; same scheme as the f64 decoder)
+      V cf_lane = mk2<T>(T(0), T(0)), df_lane = cf_lane;
+      if constexpr (!F32) { cf_lane = __ldg(cfh + lane); df_lane = __ldg(dfh + lane); }
+      auto post_tw = [&](int k, int o, V& ck, V& dk) {
+        if constexpr (F32) { ck = __ldg(cfh + k); dk = __ldg(dfh + k); }
+        else {
+          const V g = mk2<T>((T)g128_cos(o), (T)(-g128_sin(o)));
+          const V g2 = mk2<T>((T)g32_cos(o), (T)(-g32_sin(o)));
+          ck = cmul(cf_lane, g);
+          dk = cmul(cmul(df_lane, g), g2);
+        }
+      };
 #pragma unroll
       for (int o = 0; o < 16; o++) {
         const V snd = (lane == 0) ? v[(32 - o) & 31] : v[31 - o];
@@ -255,7 +328,9 @@ enc2048r_kernel(enc_params P, plan_dev pl, const typename vec2<T>::type* __restr
         const bool first = (o == 0) && (lane == 0);
         const V A = cadd(v[o], zm), D = csub(v[o], zm);
         const V Bv = mk2<T>(D.y, -D.x);
-        const V Pk = cmul(__ldg(cfh + k), A), Qk = cmul(__ldg(dfh + k), Bv);
+        V ck, dk;
+        post_tw(k, o, ck, dk);
+        const V Pk = cmul(ck, A), Qk = cmul(dk, Bv);
         const V y = cadd(Pk, Qk), t = csub(Pk, Qk);
         const int h = o >> 1, e = o & 1;
         put(oK[e] + 68 * h, y.x);

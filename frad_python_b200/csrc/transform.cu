@@ -907,7 +907,8 @@ static int lossless_decode_dev(frad_ctx* ctx, int profile, const uint8_t* payloa
   P.payload = payload; P.payload_stride = payload_stride; P.pcm = pcm; P.pcm_dtype = pcm_dtype;
   P.fast_ok = 1;
   const size_t nvals = (size_t)N * C;
-  if (bits == 12 && B > 0) {
+  const bool fast12 = profile == 0 && !ctx->opt_force_generic && frad_fast2048_decode_ok(P, prec);   // unpacks the nibbles itself
+  if (bits == 12 && B > 0 && !fast12) {
     uint16_t* hs = (uint16_t*)frad_scratch(ctx, 1, nvals * (size_t)B * sizeof(uint16_t));
     if (!hs) return FRAD_E_NOMEM;
     size_t total = nvals * (size_t)B;

@@ -542,6 +542,16 @@ def test_fast2048_encoder_every_sample_format_and_depth(ctx, dtype):
             assert np.max(np.abs(pk_f - pk_g)) <= 1e-6
             want = values(O.p0_analogue(ref_in[:2048], bits, 48000, le)[0], bits, le)
             assert np.max(np.abs(vf[:4096] - want)) <= tol + ulp * np.max(np.abs(want)), (dtype, bits, le)
+            if dtype == "<f4":                            # the decoder's fast path unpacks every depth too (profile0.py:51-66)
+                d_fast = ctx.p0_decode(fast, nb, 2048, 2, bits, le)
+                d_f32 = ctx.p0_decode(fast, nb, 2048, 2, bits, le, prec=_abi.PREC_F32)
+                ctx.set_option(_abi.OPT_FORCE_GENERIC, 1)
+                try:
+                    d_gen = ctx.p0_decode(fast, nb, 2048, 2, bits, le)
+                finally:
+                    ctx.set_option(_abi.OPT_FORCE_GENERIC, 0)
+                assert np.max(np.abs(d_fast - d_gen)) <= 1e-13 and np.max(np.abs(d_f32 - d_gen)) <= 2.0 ** -15, (bits, le)
+                assert np.max(np.abs(d_fast[0] - O.p0_digital(fast[0].tobytes()[:2048 * 2 * bits // 8], O.P0_DEPTHS.index(bits), 2, le))) <= 1e-13
     # profile 1 on the same input: integers within a step of the generic kernels and of the oracle
     hop = 1920
     nb1 = (len(pcm) - 2048) // hop + 1

@@ -88,6 +88,34 @@ def transforms(limit=None):
             b.free()
 
 
+def formats():
+    """N = 2048 stereo with other sample formats / depths (round-2 fast paths): algorithmic bytes = input + output sizes."""
+    n, ch, frames = 2048, 2, 15000
+    ncoef = frames * n * ch
+    f32 = pcm_dev(frames, n, n, ch)[1]
+    s16 = np.clip(np.round(f32 * 32767.0), -32768, 32767).astype(np.int16)
+    for name, host, code, isz in (("s16", s16, _abi.S16, 2), ("f64", f32.astype(np.float64), _abi.F64, 8), ("f32", f32, _abi.F32, 4)):
+        d_pcm = ctx.dev(host.nbytes); ctx.h2d(d_pcm, host); ctx.sync()
+        d_out = ctx.dev(ncoef * 8); d_peak = ctx.dev(frames * 8)
+        d_q = ctx.dev(ncoef * 4); d_tq = ctx.dev(frames * 27 * ch * 4)
+        d_pcm_out = ctx.dev(ncoef * 8)
+        for bits in ((16, 64) if name != "f32" else (12, 16, 24, 48, 64)):
+            stride = (n * ch * bits // 8 + 15) // 16 * 16
+            timed(lambda: ctx.check(L.frad_p0_encode_dev(ctx.handle, d_pcm.ptr, code, n, frames, n, ch, bits, 0, 0, d_out.ptr, stride, d_peak.ptr)),
+                  ncoef * (isz + bits / 8), f"p0 encode {name}->{bits}-bit BE [S48 N=2048 C=2]")
+            timed(lambda: ctx.check(L.frad_p0_decode_dev(ctx.handle, d_out.ptr, stride, frames, n, ch, bits, 0, _abi.PREC_F64, d_pcm_out.ptr, _abi.F64)),
+                  ncoef * (8 + bits / 8), f"p0 decode {bits}-bit BE->f64 (f64 math; payload from {name}) [S48 N=2048 C=2]")
+        if name != "f32":
+            timed(lambda: ctx.check(L.frad_p1_encode_dev(ctx.handle, d_pcm.ptr, code, n, frames, n, ch, 16, 48000, 0.5526315789473684, 0, d_q.ptr, d_tq.ptr, None)),
+                  ncoef * (isz + 4), f"p1 encode {name}->int32 (f64 math, the reference's precision) [S48 N=2048 C=2]")
+            timed(lambda: ctx.check(L.frad_p1_encode_dev(ctx.handle, d_pcm.ptr, code, n, frames, n, ch, 16, 48000, 0.5526315789473684, _abi.PREC_F32, d_q.ptr, d_tq.ptr, None)),
+                  ncoef * (isz + 4), f"p1 encode {name}->int32 (f32 math) [S48 N=2048 C=2]")
+            timed(lambda: ctx.check(L.frad_p1_decode_dev(ctx.handle, d_q.ptr, d_tq.ptr, None, frames, n, ch, 16, 48000, _abi.PREC_F64, d_pcm_out.ptr, code)),
+                  ncoef * (isz + 4), f"p1 decode int32->{name} (f64 math) [S48 N=2048 C=2]")
+        for b in (d_pcm, d_out, d_peak, d_q, d_tq, d_pcm_out):
+            b.free()
+
+
 def crc_rs():
     frames, flen = 15000, 16384
     rng = np.random.default_rng(0)
@@ -137,6 +165,8 @@ if __name__ == "__main__":
         transforms()
     if which == "quick":                      # the three N = 2048 shapes only
         transforms(3)
+    if which in ("all", "formats"):
+        formats()
     if which in ("all", "bytes"):
         crc_rs()
     if which in ("all", "golomb"):
