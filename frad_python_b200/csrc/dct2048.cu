@@ -164,62 +164,6 @@ __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
   return v;
 }
 
-// Eight consecutive profile-0 values from their bytes (profile0.py:51-66), word loads only: src is 4-byte aligned because
-// eight values take 12 / 16 / 24 / 48 / 64 bytes.  NaN / Inf become 0.
-__device__ __forceinline__ uint32_t byte_of(const uint32_t* w, int i) { return (w[i >> 2] >> (8 * (i & 3))) & 255u; }
-template <typename T> __device__ __forceinline__ void p0_load8(const uint8_t* src, int bits, bool le, T* out) {
-  const uint32_t* g = (const uint32_t*)src;
-  if (bits == 16 || bits == 12) {
-    uint32_t w[4];
-    if (bits == 16) { const uint4 a = __ldg((const uint4*)g); w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; }
-    else { w[0] = __ldg(g); w[1] = __ldg(g + 1); w[2] = __ldg(g + 2); w[3] = 0; }
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-      uint32_t h;
-      if (bits == 16) {
-        h = (w[j >> 1] >> (16 * (j & 1))) & 0xffffu;
-        if (!le) h = ((h & 255u) << 8) | (h >> 8);
-      } else {
-        const int p = 3 * (j >> 1);
-        h = (j & 1) ? (((byte_of(w, p + 1) & 15u) << 8) | byte_of(w, p + 2)) : ((byte_of(w, p) << 4) | (byte_of(w, p + 1) >> 4));
-        h <<= 4;
-      }
-      const float f = __half2float(__ushort_as_half((unsigned short)h));
-      out[j] = (T)(((h & 0x7c00u) == 0x7c00u) ? 0.0f : f);
-    }
-  } else if (bits == 24) {
-    uint32_t w[6];
-#pragma unroll
-    for (int i = 0; i < 6; i++) w[i] = __ldg(g + i);
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-      const uint32_t b0 = byte_of(w, 3 * j), b1 = byte_of(w, 3 * j + 1), b2 = byte_of(w, 3 * j + 2);
-      const uint32_t u = le ? ((b0 << 8) | (b1 << 16) | (b2 << 24)) : ((b0 << 24) | (b1 << 16) | (b2 << 8));
-      out[j] = (T)(((u & 0x7f800000u) == 0x7f800000u) ? 0.0f : __uint_as_float(u));
-    }
-  } else {
-    uint32_t w[16];
-    const int nw = (bits == 48) ? 12 : 16;
-#pragma unroll
-    for (int i = 0; i < 16; i += 4) {
-      if (i < nw) { const uint4 a = __ldg((const uint4*)(g + i)); w[i] = a.x; w[i + 1] = a.y; w[i + 2] = a.z; w[i + 3] = a.w; }
-    }
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-      uint64_t u = 0;
-      if (bits == 64) {
-        u = le ? (((uint64_t)w[2 * j + 1] << 32) | w[2 * j])
-               : (((uint64_t)__byte_perm(w[2 * j], 0, 0x0123) << 32) | __byte_perm(w[2 * j + 1], 0, 0x0123));
-      } else {
-#pragma unroll
-        for (int i = 0; i < 6; i++) u |= (uint64_t)byte_of(w, 6 * j + i) << (le ? (16 + 8 * i) : (56 - 8 * i));
-      }
-      const double d = __longlong_as_double((long long)u);
-      out[j] = (T)((((u >> 52) & 0x7ffull) == 0x7ffull) ? 0.0 : d);
-    }
-  }
-}
-
 template <typename T, int PROFILE, int CT>
 __global__ void __launch_bounds__(FW * 32, (sizeof(T) == 8) ? 3 : FRAD_MINB)
 dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restrict__ tw32, const double* __restrict__ dq64) {

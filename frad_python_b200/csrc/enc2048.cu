@@ -565,6 +565,333 @@ enc2048r_kernel(enc_params P, plan_dev pl, const typename vec2<T>::type* __restr
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Frame lengths N = 64 R1 < 2048 (R1 = 16, 8, 4: N = 1024, 512, 256 of the compact table, fourier/profiles.py:14-23): the same
+// kernel with S = 32 / R1 sequences per warp.  Lane L = s R1 + k1 of a warp works on sequence s: in the first FFT pass it
+// transforms R1 points, after the exchange it holds Z_s[k1 + R1 o] (fft32.cuh: fft_multi_warp), and in the epilogue it owns the
+// 64 contiguous bins [64 k1, 64 k1 + 64) of its sequence -- which in the padded layout start at word 68 L of the warp buffer,
+// exactly as in the N = 2048 kernel, so the run epilogue is the same code with k1 in place of the lane number.
+// A tile is FW S sequences = FW S / C whole frames (the host checks that C divides FW S).
+template <typename T, int S> struct encs_tail {
+  int lo[FRAD_NBANDS + 1];
+  double inv_ns[FRAD_NBANDS + 1];
+  double thr[FW][S][FRAD_NBANDS + 1];
+  float4 bp[FW][S][FRAD_NBANDS + 1];
+  T part[FW][S][64];
+};
+
+template <typename T, int PROFILE, int R1>
+__global__ void __launch_bounds__(FW * 32, (sizeof(T) == 8) ? 3 : FRAD_MINB)
+encs_kernel(enc_params P, plan_dev pl, const typename vec2<T>::type* __restrict__ tw32, int force_exact) {
+  typedef typename vec2<T>::type V;
+  constexpr bool F32 = sizeof(T) == 4;
+  constexpr int NN = 64 * R1, MM = 32 * R1, S = 32 / R1, SPC = FW * S;
+  constexpr int SEQ_T = 68 * R1;                       // T slots of one sequence in the padded spectrum layout
+  typedef encs_tail<T, S> TAIL;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  V* seq_all = (V*)smem_raw;
+  TAIL* tail = (TAIL*)(smem_raw + (size_t)FW * ESEQ * sizeof(V));
+  const int C = P.C;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int k1 = lane % R1, sl = lane / R1;
+  const int fpt = SPC / C;                             // whole frames per tile
+  const int ntiles = (P.B + fpt - 1) / fpt;
+  const V* cfh = (const V*)pl.cfh;
+  const V* dfh = (const V*)pl.dfh;
+  const bool p0_words = (PROFILE == 0) && F32 && P.bits == 32;
+  const bool vec_in = F32 && P.pcm_dtype == FRAD_F32 && C == 2 && (((uintptr_t)P.pcm) % 16) == 0 && ((P.hop * 2) % 4) == 0;
+
+  int bfirst = 0;
+  uint32_t fl_lo = 0, fl_hi = 0;
+  if (PROFILE != 0) {
+    if (tid <= FRAD_NBANDS) { const int e = P.bt->edge[tid]; tail->lo[tid] = (e < NN) ? e : NN; }
+    __syncthreads();
+    if (tid < FRAD_NBANDS) {
+      const int n = tail->lo[tid + 1] - tail->lo[tid];
+      tail->inv_ns[tid] = (n > 0) ? 1.0 / ((double)n * P.scale) : 0.0;
+    }
+#pragma unroll 1
+    for (int b = 1; b < FRAD_NBANDS; b++) {
+      const int d = tail->lo[b] - 64 * k1;
+      if (d <= 0) bfirst = b;
+      else if (d < 64 && tail->lo[b] < NN) { if (d < 32) fl_lo |= 1u << d; else fl_hi |= 1u << (d - 32); }
+    }
+  }
+  auto flag = [&](int j) -> bool { return ((j < 32 ? (fl_lo >> j) : (fl_hi >> (j - 32))) & 1u) != 0; };
+  // T-slot of sample n inside the z layout of sequence slot sq of its warp (Makhoul order, see zword)
+  auto zslot = [&](int n, int sq) -> int {
+    const int nn = (n & 1) ? (2 * NN - 1 - n) : n;
+    const int m = nn >> 2;
+    return 2 * (33 * R1 * sq + m + (m >> 5)) + ((nn >> 1) & 1);
+  };
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int b0 = tile * fpt;
+    const int nf = min(fpt, P.B - b0);
+    const int nseq = nf * C;
+    __syncthreads();
+    // ---- staging: the tile's frames in memory order (frame, sample, channel) ----
+    if (vec_in) {
+      for (int e4 = tid; e4 < nf * (NN / 2); e4 += FW * 32) {           // 16 bytes = samples n, n + 1 of both channels
+        const int f = e4 / (NN / 2), n = 2 * (e4 - f * (NN / 2));
+        const uint4 x = ldg_stream((const uint4*)((const float*)P.pcm + ((size_t)(b0 + f) * P.hop + n) * 2));
+        const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int q = 2 * f + (j & 1);
+          ((uint32_t*)(seq_all + (size_t)(q / S) * ESEQ))[zslot(n + (j >> 1), q % S)] = xs[j];
+        }
+      }
+    } else {
+      for (int e = tid; e < nf * NN * C; e += FW * 32) {
+        const int f = e / (NN * C), r = e - f * NN * C; int n, c; split_c(r, C, n, c);
+        const int q = f * C + c;
+        ((T*)(seq_all + (size_t)(q / S) * ESEQ))[zslot(n, q % S)] = load_pcm<T>(P.pcm, P.pcm_dtype, ((int64_t)(b0 + f) * P.hop + n) * C + c);
+      }
+    }
+    __syncthreads();
+    if (w * S < nseq) {
+      const int q_me = w * S + sl;                       // my sequence slot in the tile
+      const bool live = q_me < nseq;                     // lanes of slots beyond the batch compute on stale data and store nothing global
+      const int f_me = q_me / C, c_me = q_me - f_me * C, b_me = b0 + f_me;
+      V* buf = seq_all + (size_t)w * ESEQ;
+      T* X = (T*)buf;
+      T* Xs = X + SEQ_T * sl;                            // my sequence's spectrum
+      V v[32];
+#pragma unroll
+      for (int i = 0; i < 32; i++) v[i] = buf[lane + 33 * i];
+      __syncwarp();
+      fft_multi_warp<T, false, R1>(v, buf, lane, tw32);
+      __syncwarp();
+      // ---- pairwise real-FFT split + DCT twiddle: (k, M-k) -> X[k], X[N-k], X[M-k], X[M+k], k = k1 + R1 o ----
+      const int partner = sl * R1 + ((R1 - k1) % R1);
+      const bool swap_out = p0_words && !P.le;
+      T mx = T(0);
+      auto put = [&](int k, T val) {
+        if (PROFILE == 0) {
+          mx = fmax(mx, fabs(val));
+          if constexpr (F32) { if (swap_out) val = __uint_as_float(__byte_perm(__float_as_uint(val), 0, 0x0123)); }
+        }
+        Xs[xpos(k)] = val;
+      };
+      const T r2 = (T)FRAD_RSQRT2;
+      V cf_lane = mk2<T>(T(0), T(0)), df_lane = cf_lane;
+      if constexpr (!F32) { cf_lane = __ldg(cfh + k1); df_lane = __ldg(dfh + k1); }
+#pragma unroll
+      for (int o = 0; o < 16; o++) {
+        const V snd = (k1 == 0) ? v[(32 - o) & 31] : v[31 - o];
+        V zm;
+        zm.x = shfl_t<T>(snd.x, partner);
+        zm.y = -shfl_t<T>(snd.y, partner);
+        const int k = k1 + R1 * o;
+        const bool first = (o == 0) && (k1 == 0);
+        const V A = cadd(v[o], zm), D = csub(v[o], zm);
+        const V Bv = mk2<T>(D.y, -D.x);
+        V ck, dk;
+        if constexpr (F32) { ck = __ldg(cfh + k); dk = __ldg(dfh + k); }
+        else {   // cf[k1 + R1 o] = cf[k1] e^{-i pi o / 128}, df likewise with another e^{-i pi o / 32}: the same constants as for N = 2048
+          const V g = mk2<T>((T)g128_cos(o), (T)(-g128_sin(o)));
+          const V g2 = mk2<T>((T)g32_cos(o), (T)(-g32_sin(o)));
+          ck = cmul(cf_lane, g);
+          dk = cmul(cmul(df_lane, g), g2);
+        }
+        const V Pk = cmul(ck, A), Qk = cmul(dk, Bv);
+        const V y = cadd(Pk, Qk), t = csub(Pk, Qk);
+        put(k, y.x);
+        if (!first) put(NN - k, -y.y);
+        put(MM - k, (t.x - t.y) * r2);
+        if (!first) put(MM + k, (t.x + t.y) * r2);
+      }
+      if (k1 == 0) {                                       // self-paired bin k = M / 2 (and N - M / 2)
+        const V zk = v[16], zm = cconj(v[16]);
+        const V A = cadd(zk, zm), D = csub(zk, zm);
+        const V Bv = mk2<T>(D.y, -D.x);
+        const V y = cadd(cmul(__ldg(cfh + MM / 2), A), cmul(__ldg(dfh + MM / 2), Bv));
+        put(MM / 2, y.x);
+        put(NN - MM / 2, -y.y);
+      }
+      if (PROFILE == 0) {
+        if (P.peak) {
+#pragma unroll
+          for (int s = 1; s < R1; s <<= 1) mx = fmax(mx, (T)__shfl_xor_sync(0xffffffffu, mx, s));     // over the R1 lanes of my sequence
+          if (k1 == 0 && live) atomicMax((unsigned long long*)&P.peak[b_me], (unsigned long long)__double_as_longlong((double)mx));
+        }
+      } else {
+        __syncwarp();
+        const T* run = X + 68 * lane;
+        {
+          T* slot = tail->part[w][sl] + k1 + bfirst;
+          T acc = T(0);
+#pragma unroll
+          for (int i = 0; i < 16; i++) {
+            T xe[4];
+            if constexpr (F32) { const float4 t = ((const float4*)run)[i]; xe[0] = t.x; xe[1] = t.y; xe[2] = t.z; xe[3] = t.w; }
+            else {
+              const double2 t0 = ((const double2*)run)[2 * i], t1 = ((const double2*)run)[2 * i + 1];
+              xe[0] = t0.x; xe[1] = t0.y; xe[2] = t1.x; xe[3] = t1.y;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              const int j = 4 * i + e;
+              if (j > 0 && flag(j)) { *slot = acc; slot++; acc = T(0); }
+              acc = fma(xe[e], xe[e], acc);
+            }
+          }
+          *slot = acc;
+        }
+        __syncwarp();
+        const T scalef = (T)P.scale;
+        const float inv_log_base_f = (float)(1.0 / 0.30685281944005469058);
+        // thresholds of the warp's sequences, one after the other: band = lane
+#pragma unroll 1
+        for (int s2 = 0; s2 < S; s2++) {
+          const int q2 = w * S + s2;
+          if (q2 >= nseq) break;                           // warp-uniform
+          const int f2 = q2 / C, c2 = q2 - f2 * C, b2 = b0 + f2;
+          T tot = T(0);
+          int cnt = 1;
+          if (lane < FRAD_NBANDS) {
+            const int blo = tail->lo[lane], bhi = tail->lo[lane + 1];
+            cnt = bhi - blo;
+            if (bhi > blo) {
+              const T* row = tail->part[w][s2] + lane;
+              for (int l = blo >> 6; l <= (bhi - 1) >> 6; l++) tot += row[l];
+            }
+            tot *= scalef * scalef;
+          }
+          const unsigned empty = __ballot_sync(0xffffffffu, cnt <= 0);
+          const int first_empty = empty ? (__ffs(empty) - 1) : 32;
+          double thr = 0.0;
+          if (lane < FRAD_NBANDS && lane < first_empty) {
+            double level;
+            if constexpr (F32) level = (double)powf(sqrtf(tot / (float)cnt), 0.8f);
+            else level = pow(sqrt(tot / (double)cnt), 0.8);
+            thr = fmax(level, P.bt->ath[lane]) * P.loss;
+          }
+          if (lane <= FRAD_NBANDS) tail->thr[w][s2][lane] = thr;
+          if (lane < FRAD_NBANDS) {
+            int tqi = 0;
+            bool exact = false;
+            if (thr > 1.0) {
+              const float lv = logf((float)thr) * inv_log_base_f;
+              const float df = lv * cbrtf(lv);
+              const float rf = rintf(df);
+              exact = !(fabsf(fabsf(df - rf) - 0.5f) > 1.0e-3f * (1.0f + df) && df < 1.0e6f);
+              tqi = (int)rf;
+            }
+            if (exact) tqi = tq_exact_r(thr, P.bt->log_base);
+            P.tq[((size_t)b2 * FRAD_NBANDS + lane) * C + c2] = tqi;
+          }
+          const double thr_next = __shfl_down_sync(0xffffffffu, thr, 1);
+          if (lane <= FRAD_NBANDS) {
+            float4 bpv = make_float4(1.0e30f, 1.0e30f, -1.0f, 2.0f * NN);
+            if (lane < FRAD_NBANDS - 1 && cnt > 0) {
+              const double ins = tail->inv_ns[lane];
+              bpv = make_float4((float)(thr * ins), (float)(thr_next * ins), (float)tail->lo[lane], (float)tail->lo[lane + 1]);
+            }
+            tail->bp[w][s2][lane] = bpv;
+          }
+        }
+        __syncwarp();
+        {
+          const float4* bpp = tail->bp[w][sl] + bfirst;
+          float4 bpv = *bpp;
+          const float kb = (float)(64 * k1);
+          int4* qrun = (int4*)((int*)X + qpos<T>(64 * lane));
+#pragma unroll 1
+          for (int g = 0; g < 8; g++) {
+            int ms[8];
+            bool allok = true;
+            T xt[8];
+            if constexpr (F32) {
+              const float4 xa = ((const float4*)run)[2 * g], xb = ((const float4*)run)[2 * g + 1];
+              xt[0] = xa.x; xt[1] = xa.y; xt[2] = xa.z; xt[3] = xa.w; xt[4] = xb.x; xt[5] = xb.y; xt[6] = xb.z; xt[7] = xb.w;
+            } else {
+#pragma unroll
+              for (int u2 = 0; u2 < 4; u2++) { const double2 t = ((const double2*)run)[4 * g + u2]; xt[2 * u2] = t.x; xt[2 * u2 + 1] = t.y; }
+            }
+            float xs[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) xs[u] = (float)xt[u];
+            const uint32_t fb = ((g < 4) ? (fl_lo >> (8 * g)) : (fl_hi >> (8 * g - 32))) & (g == 0 ? 0xfeu : 0xffu);
+            const float kg = kb + (float)(8 * g);
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+              if ((fb >> u) & 1u) { bpp++; bpv = *bpp; }
+              const float kf = kg + (float)u;
+              const float x = xs[u];
+              const float dv = fmaf(kf - bpv.z, bpv.y, (bpv.w - kf) * bpv.x);
+              float rc, s, vv;
+              asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(dv));
+              const float y = fabsf(x) * rc;
+              asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(y));
+              asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(vv) : "f"(y * s));
+              const float big = copysignf(vv, x) + 12582912.0f;
+              const float r = big - 12582912.0f;
+              allok = allok && (fmaf(1.0e-6f, vv, fabsf(fabsf(vv) - fabsf(r))) < 0.4999999f);
+              ms[u] = __float_as_int(big) - 0x4B400000;
+            }
+            if (!allok || force_exact) {
+#pragma unroll
+              for (int u = 0; u < 8; u++) {
+                const int j = 8 * g + u;
+                const unsigned long long fl = ((unsigned long long)fl_hi << 32) | fl_lo;
+                const int bn = bfirst + __popcll(fl & ((j >= 63) ? ~0ull : ((2ull << j) - 1ull)));
+                bool redo = force_exact != 0;
+                if (!redo) {
+                  const float4 bq = tail->bp[w][sl][bn];
+                  const float kf = kg + (float)u;
+                  const float dv = fmaf(kf - bq.z, bq.y, (bq.w - kf) * bq.x);
+                  float rc, s, vv;
+                  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(dv));
+                  const float y = fabsf(xs[u]) * rc;
+                  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(y));
+                  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(vv) : "f"(y * s));
+                  const float r = (vv + 12582912.0f) - 12582912.0f;
+                  redo = !(fmaf(1.0e-6f, vv, fabsf(vv - r)) < 0.4999999f);
+                }
+                if (redo && bn != FRAD_NBANDS - 1) {
+                  const int lo = tail->lo[bn], n = tail->lo[bn + 1] - lo;
+                  const double t0 = tail->thr[w][sl][bn], t1 = tail->thr[w][sl][bn + 1];
+                  ms[u] = quant_exact_r((double)xt[u], 64 * k1 + j - lo, t0, (t1 - t0) / (double)n, P.scale);
+                }
+              }
+            }
+            qrun[2 * g] = make_int4(ms[0], ms[1], ms[2], ms[3]);
+            qrun[2 * g + 1] = make_int4(ms[4], ms[5], ms[6], ms[7]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // ---- cooperative store: value e = k*C + c of frame f <- sequence slot f*C + c, four consecutive values per thread ----
+    const bool words = (PROFILE != 0) || p0_words;
+    for (int e4 = tid; e4 < nf * (NN * C / 4); e4 += FW * 32) {
+      const int f = e4 / (NN * C / 4), vi = 4 * (e4 - f * (NN * C / 4));      // first of four consecutive values of frame f
+      uint32_t ow[4];
+      T ov[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        int k, c; split_c(vi + j, C, k, c); const int q = f * C + c;
+        if (words) {
+          const uint32_t* base = (const uint32_t*)(seq_all + (size_t)(q / S) * ESEQ) + (size_t)(q % S) * SEQ_T * (sizeof(T) / 4);
+          ow[j] = base[(PROFILE == 0) ? xpos(k) : qpos<T>(k)];
+        } else {
+          ov[j] = ((const T*)(seq_all + (size_t)(q / S) * ESEQ))[(size_t)(q % S) * SEQ_T + xpos(k)];
+        }
+      }
+      if (words) {
+        uint32_t* dst = (PROFILE == 0) ? (uint32_t*)(P.payload + (size_t)(b0 + f) * P.payload_stride) : (uint32_t*)(P.q + (size_t)(b0 + f) * NN * C);
+        *(uint4*)(dst + vi) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+      } else if constexpr (PROFILE == 0) {
+        uint8_t* frame = P.payload + (size_t)(b0 + f) * P.payload_stride;
+        p0_store4<T>(frame + (P.bits == 12 ? (size_t)vi * 3 / 2 : (size_t)vi * (size_t)(P.bits >> 3)), ov, P.bits, P.le != 0);
+      }
+    }
+  }
+}
+
 }  // namespace
 
 #define ENCR_DISPATCH(TT, PROF, CT)                                                                          \
@@ -595,6 +922,43 @@ bool frad_fast2048_encode_ok(const enc_params& P, int prec) {
   } else if (((uintptr_t)P.q % 16) != 0) return false;
   if (P.pcm_dtype == FRAD_F32 && prec == FRAD_PREC_F32 && ((((uintptr_t)P.pcm) % 16) != 0 || ((P.hop * P.C) % 4) != 0)) return false;
   return true;
+}
+
+#define ENCS_DISPATCH(TT, PROF, RR)                                                                          \
+  do {                                                                                                       \
+    auto k = encs_kernel<TT, PROF, RR>;                                                                      \
+    const int fpt = FW * (32 / RR) / P.C;                                                                    \
+    int grid;                                                                                                \
+    const size_t smem = (size_t)FW * ESEQ * sizeof(vec2<TT>::type) + ((PROF == 0) ? 16 : sizeof(encs_tail<TT, 32 / RR>)); \
+    int rc = launch_cfg(ctx, k, smem, (P.B + fpt - 1) / fpt, &grid);                                         \
+    if (rc) return rc;                                                                                       \
+    k<<<grid, FW * 32, smem, ctx->stream>>>(P, plan_view(pl), (const vec2<TT>::type*)pl->tw32, force_exact); \
+  } while (0)
+#define ENCS_BY_R(TT, PROF)                                                                             \
+  do {                                                                                                  \
+    if (P.N == 1024) ENCS_DISPATCH(TT, PROF, 16); else if (P.N == 512) ENCS_DISPATCH(TT, PROF, 8);      \
+    else if (P.N == 256) ENCS_DISPATCH(TT, PROF, 4); else ENCS_DISPATCH(TT, PROF, 2);                 \
+  } while (0)
+
+// N = 1024, 512, 256: S = 2, 4, 8 sequences per warp, FW S sequences per tile; whole frames per tile
+bool frad_fast_small_encode_ok(const enc_params& P, int prec) {
+  if (P.N != 1024 && P.N != 512 && P.N != 256 && P.N != 128) return false;
+  if (prec != FRAD_PREC_F32 && prec != FRAD_PREC_F64) return false;
+  const int spc = FW * (2048 / P.N);
+  if (P.C < 1 || P.C > spc || (spc % P.C) != 0) return false;
+  if (((size_t)P.N * P.C) % 4) return false;
+  if (P.profile == 2) return false;                           // profile 2 keeps the generic path at these sizes
+  if (P.profile == 0) {
+    if ((P.payload_stride % 16) != 0 || ((uintptr_t)P.payload % 16) != 0) return false;
+  } else if (((uintptr_t)P.q % 16) != 0) return false;
+  return true;
+}
+
+int frad_launch_encode_small(frad_ctx* ctx, const enc_params& P, const frad_plan* pl, int prec, int force_exact) {
+  if (prec == FRAD_PREC_F32) { if (P.profile == 0) ENCS_BY_R(float, 0); else ENCS_BY_R(float, 1); }
+  else { if (P.profile == 0) ENCS_BY_R(double, 0); else ENCS_BY_R(double, 1); }
+  FRAD_LAUNCH_CHECK(ctx);
+  return FRAD_OK;
 }
 
 int frad_launch_encode_2048r(frad_ctx* ctx, const enc_params& P, const frad_plan* pl, int prec, int force_exact) {

@@ -126,6 +126,32 @@ __device__ __forceinline__ void fft32_perm(V* v) {
   for (int k1 = 0; k1 < 4; k1++) fft8_perm<T, INV>(v + 8 * k1);
 }
 
+// 16-point DFT in place (4 x 4); position P of the output holds frequency index perm16(P)
+__host__ __device__ constexpr int perm16(int P) { return (P >> 2) + 4 * (P & 3); }
+template <typename T, bool INV, typename V>
+__device__ __forceinline__ void fft16_perm(V* v) {
+#pragma unroll
+  for (int n2 = 0; n2 < 4; n2++) {
+    fft4_inplace<T, INV>(v[n2], v[n2 + 4], v[n2 + 8], v[n2 + 12]);
+#pragma unroll
+    for (int k1 = 1; k1 < 4; k1++) v[4 * k1 + n2] = mul_w32<T, INV>(v[4 * k1 + n2], 2 * n2 * k1);   // W16^(n2 k1)
+  }
+#pragma unroll
+  for (int k1 = 0; k1 < 4; k1++) fft4_inplace<T, INV>(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);
+}
+// R-point DFT in place for R in {2, 4, 8, 16, 32}; position p of the output holds frequency index perm_r<R>(p)
+template <int R> __host__ __device__ constexpr int perm_r(int p) {
+  return (R == 32) ? perm32(p) : (R == 16) ? perm16(p) : (R == 8) ? perm8(p) : p;
+}
+template <typename T, bool INV, int R, typename V>
+__device__ __forceinline__ void fft_r_perm(V* v) {
+  if constexpr (R == 32) fft32_perm<T, INV>(v);
+  else if constexpr (R == 16) fft16_perm<T, INV>(v);
+  else if constexpr (R == 8) fft8_perm<T, INV>(v);
+  else if constexpr (R == 4) fft4_inplace<T, INV>(v[0], v[1], v[2], v[3]);
+  else { const V a = v[0], b = v[1]; v[0] = cadd(a, b); v[1] = csub(a, b); }
+}
+
 // padded complex index inside a per-warp exchange buffer: one pad element per 32
 __device__ __forceinline__ int padc(int a) { return a + (a >> 5); }
 
@@ -174,4 +200,94 @@ __device__ __forceinline__ void fft1024_warp(typename vec2<T>::type* v, typename
   for (int o = 0; o < 32; o++) t[o] = v[inv32(o)];
 #pragma unroll
   for (int o = 0; o < 32; o++) v[o] = t[o];
+}
+
+// Warp-level FFTs of S = 32 / R1 sequences of M = 32 R1 points each (R1 = 32: fft1024_warp).
+// In: v[s R1 + i] = z_s[lane + 32 i].  Out: lane L = s R1 + k1 holds v[o] = Z_s[k1 + R1 o].
+// M = 32 R1 with input index l + 32 i and output index k1 + R1 o:  Z[k] = sum_l w_32^(l o) w_M^(l k1) sum_i z[l + 32 i] w_R1^(i k1):
+// an R1-point DFT per lane and sequence, the cross twiddles w_M^(l k1) = tw32[l][L] (a 32 x 32 table per frame length), then
+// the 32-point DFT over l after the transposing exchange.
+template <typename T, bool INV, int R1>
+__device__ __forceinline__ void fft_multi_warp(typename vec2<T>::type* v, typename vec2<T>::type* buf, int lane,
+                                               const typename vec2<T>::type* __restrict__ tw32,
+                                               const typename vec2<T>::type* wlane = nullptr) {
+  typedef typename vec2<T>::type V;
+  if constexpr (R1 == 32) { fft1024_warp<T, INV>(v, buf, lane, tw32, wlane); return; }
+  constexpr int S = 32 / R1;
+#pragma unroll
+  for (int s = 0; s < S; s++) fft_r_perm<T, INV, R1>(v + s * R1);
+#pragma unroll
+  for (int P = 0; P < 32; P++) buf[33 * lane + (P / R1) * R1 + perm_r<R1>(P % R1)] = v[P];
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 32; i++) v[i] = buf[lane + 33 * i];
+  __syncwarp();
+  if constexpr (sizeof(T) == 8) {
+    V b = wlane ? *wlane : __ldg(&tw32[32 + lane]);
+    if (INV) b.y = -b.y;
+    const V b2 = cmul(b, b), b4 = cmul(b2, b2);
+    V w0 = b, w1 = b2, w2 = cmul(b2, b), w3 = b4;
+#pragma unroll
+    for (int i = 1; i < 32; i += 4) {
+      v[i] = cmul(v[i], w0);
+      if (i + 1 < 32) v[i + 1] = cmul(v[i + 1], w1);
+      if (i + 2 < 32) v[i + 2] = cmul(v[i + 2], w2);
+      if (i + 3 < 32) v[i + 3] = cmul(v[i + 3], w3);
+      if (i + 4 < 32) { w0 = cmul(w0, b4); w1 = cmul(w1, b4); w2 = cmul(w2, b4); w3 = cmul(w3, b4); }
+    }
+  } else {
+#pragma unroll
+    for (int i = 1; i < 32; i++) {
+      V w = __ldg(&tw32[i * 32 + lane]);
+      if (INV) w.y = -w.y;
+      v[i] = cmul(v[i], w);
+    }
+  }
+  fft32_perm<T, INV>(v);
+  V t[32];
+#pragma unroll
+  for (int o = 0; o < 32; o++) t[o] = v[inv32(o)];
+#pragma unroll
+  for (int o = 0; o < 32; o++) v[o] = t[o];
+}
+
+// Inverse counterpart for the small frames: the mirror image of fft_multi_warp.
+// In: lane L = s R1 + k1 holds v[o] = Z_s[k1 + R1 o].  Out: v[s R1 + p] = z_s[lane + 32 perm_r<R1>(p)] (unnormalised inverse).
+// z[n2 + 32 n1] = sum_k1 w_R1^(-k1 n1) w_M^(-k1 n2) sum_o Z[k1 + R1 o] w_32^(-o n2): the 32-point DFT over o in registers, the
+// cross twiddles conj(tw32[n2][L]), the transposing exchange, then an R1-point DFT per sequence.
+template <typename T, int R1>
+__device__ __forceinline__ void ifft_multi_warp(typename vec2<T>::type* v, typename vec2<T>::type* buf, int lane,
+                                                const typename vec2<T>::type* __restrict__ tw32) {
+  typedef typename vec2<T>::type V;
+  constexpr int S = 32 / R1;
+  fft32_perm<T, true>(v);                                  // position P holds n2 = perm32(P)
+  if constexpr (sizeof(T) == 8) {
+    V b = __ldg(&tw32[32 + lane]);                          // w_M^(k1); conjugated for the inverse
+    b.y = -b.y;
+    const V b2 = cmul(b, b), b4 = cmul(b2, b2);
+    V w0 = b, w1 = b2, w2 = cmul(b2, b), w3 = b4;            // w^1 .. w^4
+#pragma unroll
+    for (int i = 1; i < 32; i += 4) {
+      v[inv32(i)] = cmul(v[inv32(i)], w0);
+      if (i + 1 < 32) v[inv32(i + 1)] = cmul(v[inv32(i + 1)], w1);
+      if (i + 2 < 32) v[inv32(i + 2)] = cmul(v[inv32(i + 2)], w2);
+      if (i + 3 < 32) v[inv32(i + 3)] = cmul(v[inv32(i + 3)], w3);
+      if (i + 4 < 32) { w0 = cmul(w0, b4); w1 = cmul(w1, b4); w2 = cmul(w2, b4); w3 = cmul(w3, b4); }
+    }
+  } else {
+#pragma unroll
+    for (int i = 1; i < 32; i++) {
+      V w = __ldg(&tw32[i * 32 + lane]);
+      w.y = -w.y;
+      v[inv32(i)] = cmul(v[inv32(i)], w);
+    }
+  }
+#pragma unroll
+  for (int P = 0; P < 32; P++) buf[lane + 33 * perm32(P)] = v[P];
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 32; i++) v[i] = buf[i + 33 * lane];  // new lane = n2, register i = old lane (s, k1)
+  __syncwarp();
+#pragma unroll
+  for (int s = 0; s < S; s++) fft_r_perm<T, true, R1>(v + s * R1);
 }

@@ -79,7 +79,8 @@ static bool build_tables(frad_ctx* ctx, frad_plan* p) {
   }
   p->cf = upload_cpx<T>(ctx, re, im);
   p->df = upload_cpx<T>(ctx, re2, im2);
-  if (N == 2048) {
+  const bool warp_fft = (N == 2048 || N == 1024 || N == 512 || N == 256 || N == 128);   // frame lengths of the warp-FFT kernels: N = 64 R1
+  if (warp_fft) {
     for (int k = 0; k <= M; k++) { re[k] /= 2; im[k] /= 2; re2[k] /= 2; im2[k] /= 2; }
     p->cfh = upload_cpx<T>(ctx, re, im);
     p->dfh = upload_cpx<T>(ctx, re2, im2);
@@ -91,9 +92,11 @@ static bool build_tables(frad_ctx* ctx, frad_plan* p) {
   }
   p->ci = upload_cpx<T>(ctx, re, im);
   p->ei = upload_cpx<T>(ctx, re2, im2);
-  if (N == 2048) {
+  if (warp_fft) {
+    // cross twiddles of the warp FFT, [l][L] = exp(-2 pi i l (L mod R1) / M), R1 = M / 32 (fft32.cuh: fft_multi_warp)
+    const int R1 = M / 32;
     re.resize(1024); im.resize(1024);
-    for (int i = 0; i < 32; i++) for (int l = 0; l < 32; l++) unit_root(-2LL * i * l, 1024, &re[i * 32 + l], &im[i * 32 + l]);
+    for (int i = 0; i < 32; i++) for (int l = 0; l < 32; l++) unit_root(-2LL * i * (l % R1), M, &re[i * 32 + l], &im[i * 32 + l]);
     p->tw32 = upload_cpx<T>(ctx, re, im);
     if (!p->tw32) return false;
   }
@@ -704,7 +707,11 @@ static int frad_launch_encode_2048(frad_ctx* ctx, const enc_params& P, const fra
 }
 int frad_launch_decode_2048(frad_ctx* ctx, const dec_params& P, const frad_plan* pl, int prec);
 bool frad_fast2048_encode_ok(const enc_params& P, int prec);
+bool frad_fast_small_encode_ok(const enc_params& P, int prec);                                                       // enc2048.cu
+int frad_launch_encode_small(frad_ctx* ctx, const enc_params& P, const frad_plan* pl, int prec, int force_exact);
 bool frad_fast2048_decode_ok(const dec_params& P, int prec);
+bool frad_fast_small_decode_ok(const dec_params& P, int prec);                                                       // decs.cu
+int frad_launch_decode_small(frad_ctx* ctx, const dec_params& P, const frad_plan* pl, int prec);
 
 static int launch_encode(frad_ctx* ctx, enc_params& P, int prec) {
   if (P.B <= 0) return FRAD_OK;
@@ -727,6 +734,10 @@ static int launch_encode(frad_ctx* ctx, enc_params& P, int prec) {
     return FRAD_OK;
   }
 #ifdef FRAD_HAVE_FAST2048
+  if (!ctx->opt_force_generic && frad_fast_small_encode_ok(P, prec)) {
+    P.fast_ok = 2;
+    return frad_launch_encode_small(ctx, P, pl, prec, ctx->opt_exact_quant);
+  }
   if (!ctx->opt_force_generic && frad_fast2048_encode_ok(P, prec)) {
     P.fast_ok = 2;                                   // tells the caller that 12-bit payloads are already nibble-packed
     if (P.profile != 2) return frad_launch_encode_2048(ctx, P, pl, prec, ctx->opt_exact_quant);
@@ -813,6 +824,7 @@ static int launch_decode(frad_ctx* ctx, dec_params& P, int prec) {
     return FRAD_OK;
   }
 #ifdef FRAD_HAVE_FAST2048
+  if (!ctx->opt_force_generic && frad_fast_small_decode_ok(P, prec)) return frad_launch_decode_small(ctx, P, pl, prec);
   if (!ctx->opt_force_generic && frad_fast2048_decode_ok(P, prec)) return frad_launch_decode_2048(ctx, P, pl, prec);
 #endif
   launch_cfg cfg;
@@ -907,7 +919,7 @@ static int lossless_decode_dev(frad_ctx* ctx, int profile, const uint8_t* payloa
   P.payload = payload; P.payload_stride = payload_stride; P.pcm = pcm; P.pcm_dtype = pcm_dtype;
   P.fast_ok = 1;
   const size_t nvals = (size_t)N * C;
-  const bool fast12 = profile == 0 && !ctx->opt_force_generic && frad_fast2048_decode_ok(P, prec);   // unpacks the nibbles itself
+  const bool fast12 = profile == 0 && !ctx->opt_force_generic && (frad_fast2048_decode_ok(P, prec) || frad_fast_small_decode_ok(P, prec));   // unpacks the nibbles itself
   if (bits == 12 && B > 0 && !fast12) {
     uint16_t* hs = (uint16_t*)frad_scratch(ctx, 1, nvals * (size_t)B * sizeof(uint16_t));
     if (!hs) return FRAD_E_NOMEM;

@@ -572,3 +572,59 @@ def test_fast2048_encoder_every_sample_format_and_depth(ctx, dtype):
         finally:
             ctx.set_option(_abi.OPT_EXACT_QUANT, 0)
         assert np.array_equal(q, q2) and np.array_equal(tq, tq2)
+
+
+@pytest.mark.parametrize("n", [128, 256, 512, 1024])
+@pytest.mark.parametrize("c", [1, 2, 8])
+def test_small_frame_warp_kernels_match_generic_path_and_oracle(ctx, n, c):
+    """Round 2: N = 256 / 512 / 1024 (fourier/profiles.py:14-23) run on the warp-FFT kernels with 8 / 4 / 2 sequences per warp
+    (enc2048.cu: encs_kernel, decs.cu).  A/B against the generic shared-memory kernels and spot checks against the oracle."""
+    from frad_python_b200 import _abi
+    srate = {128: 8000, 256: 11025, 512: 24000, 1024: 44100}[n]
+    pcm = O.synth_pcm(n * 37 / 48000 + 0.01, 48000, c, seed=60 + n + c)[: n * 37]
+    hop = n - n // 16
+    nb0, nb1 = len(pcm) // n, (len(pcm) - n) // hop + 1
+    s16 = np.clip(np.round(pcm.astype(np.float64) * 32768), -32768, 32767).astype(np.int16)
+    res = {}
+    for mode in (0, 1):
+        ctx.set_option(_abi.OPT_FORCE_GENERIC, mode)
+        try:
+            pay, peak, _ = ctx.p0_encode(pcm, nb0, n, n, 32, False)
+            pay16, _, _ = ctx.p0_encode(pcm, nb0, n, n, 16, True)
+            pay64, _, _ = ctx.p0_encode(s16, nb0, n, n, 64, False)               # f64 arithmetic
+            q, tq, _ = ctx.p1_encode(pcm, nb1, n, hop, 16, srate, LOSS0)
+            q64, tq64, _ = ctx.p1_encode(s16, nb1, n, hop, 16, srate, LOSS0)
+            res[mode] = (pay, peak, pay16, pay64, q, tq, q64, tq64)
+        finally:
+            ctx.set_option(_abi.OPT_FORCE_GENERIC, 0)
+    a, b = res[0], res[1]
+    assert np.max(np.abs(values(a[0].tobytes(), 32, False) - values(b[0].tobytes(), 32, False))) <= TOL_F32
+    assert np.max(np.abs(a[1] - b[1])) <= 1e-6
+    assert np.max(np.abs(values(a[2].tobytes(), 16, True) - values(b[2].tobytes(), 16, True))) <= 2.0 ** -10
+    assert np.max(np.abs(values(a[3].tobytes(), 64, False) - values(b[3].tobytes(), 64, False))) <= TOL_F64 * 50
+    for qa, qb, ta, tb in ((a[4], b[4], a[5], b[5]), (a[6], b[6], a[7], b[7])):
+        assert np.max(np.abs(qa - qb)) <= 1 and np.mean(qa != qb) <= 1e-4 + 2.0 / qa.size and np.max(np.abs(ta - tb)) <= 1
+    # oracle: first and last frame
+    for i in (0, nb1 - 1):
+        oq, otq, *_ = O.p1_analogue_ints(pcm[i * hop:i * hop + n], 16, srate, LOSS0)
+        assert np.max(np.abs(a[4][i] - oq)) <= 1 and np.mean(a[4][i] != oq) <= 2e-3 and np.max(np.abs(a[5][i] - otq)) <= 1
+    want = values(O.p0_analogue(pcm[:n], 32, srate, False)[0], 32, False)
+    assert np.max(np.abs(values(a[0][0].tobytes(), 32, False) - want)) <= TOL_F32
+    # decode of identical inputs: fast vs generic, f64 and f32 arithmetic, several output formats and depths
+    outs = {}
+    for mode in (0, 1):
+        ctx.set_option(_abi.OPT_FORCE_GENERIC, mode)
+        try:
+            outs[mode] = (ctx.p0_decode(a[0], nb0, n, c, 32, False), ctx.p0_decode(a[2], nb0, n, c, 16, True),
+                          ctx.p0_decode(a[3], nb0, n, c, 64, False), ctx.p1_decode(a[4], a[5], None, nb1, n, c, 16, srate),
+                          ctx.p1_decode(a[4], a[5], None, nb1, n, c, 16, srate, prec=_abi.PREC_F32),
+                          ctx.p1_decode(a[4], a[5], None, nb1, n, c, 16, srate, out_dtype=np.int16))
+        finally:
+            ctx.set_option(_abi.OPT_FORCE_GENERIC, 0)
+    for j in (0, 1, 2, 3):
+        assert np.max(np.abs(outs[0][j] - outs[1][j])) <= 1e-13, j
+    assert np.max(np.abs(outs[0][4] - outs[1][3])) <= 2.0 ** -15                 # f32 arithmetic: <= 1 LSB at 16 bit
+    assert np.max(np.abs(outs[0][5].astype(int) - outs[1][5].astype(int))) <= 1
+    i = nb1 // 2
+    assert np.max(np.abs(outs[0][3][i] - O.p1_digital_ints(a[4][i], a[5][i], 16, c, srate, n))) <= 1e-12
+    assert np.max(np.abs(outs[0][0][1] - O.p0_digital(a[0][1].tobytes(), 3, c, False))) <= 1e-13

@@ -48,7 +48,10 @@ def pcm_dev(frames, n, hop, ch, dtype=np.float32):
 
 def transforms(limit=None):
     for (n, hop, ch, frames, tag) in ((2048, 2048, 2, 15000, "S48 N=2048 C=2"), (2048, 2048, 8, 4000, "S96 N=2048 C=8"),
-                                       (2048, 2048, 1, 30000, "mono N=2048"), (1024, 1024, 2, 30000, "N=1024 generic"),
+                                       (2048, 2048, 1, 30000, "mono N=2048"), (1024, 1024, 2, 30000, "N=1024 warp-FFT, 2 sequences per warp"),
+                                       (512, 512, 2, 60000, "N=512 warp-FFT, 4 sequences per warp"),
+                                       (256, 256, 2, 120000, "N=256 warp-FFT, 8 sequences per warp"),
+                                       (128, 128, 2, 240000, "N=128 warp-FFT, 16 sequences per warp"),
                                        (4096, 4096, 2, 7500, "N=4096 generic"), (1280, 1280, 2, 24000, "N=1280 generic"),
                                        (2000, 2000, 2, 15000, "N=2000 generic (lossless size)"))[:limit]:
         d_pcm, _ = pcm_dev(frames, n, hop, ch)
@@ -65,7 +68,7 @@ def transforms(limit=None):
                   ncoef * 8, f"p4 encode f32->be32 [{tag}]")
             timed(lambda: ctx.check(L.frad_p4_decode_dev(ctx.handle, d_pay.ptr, n * ch * 4, frames, n, ch, 32, 0, d_out.ptr, _abi.F64)),
                   ncoef * 12, f"p4 decode be32->f64 [{tag}]")
-        if n in (2048, 1024, 4096, 1280):
+        if n in (2048, 1024, 512, 256, 128, 4096, 1280):
             d_q = ctx.dev(ncoef * 4); d_tq = ctx.dev(frames * 27 * ch * 4)
             timed(lambda: ctx.check(L.frad_p1_encode_dev(ctx.handle, d_pcm.ptr, _abi.F32, hop, frames, n, ch, 16, 48000, 0.5526315789473684, 0, d_q.ptr, d_tq.ptr, None)),
                   ncoef * 8, f"p1 encode f32->int32 [{tag}]")
