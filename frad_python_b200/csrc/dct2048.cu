@@ -324,8 +324,10 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
               if constexpr (sizeof(T) == 8) {
                 const double2 r0 = make_double2(__hiloint2double((int)w0.y, (int)w0.x), __hiloint2double((int)w0.w, (int)w0.z));
                 const double2 r1 = make_double2(__hiloint2double((int)w1.y, (int)w1.x), __hiloint2double((int)w1.w, (int)w1.z));
-                const double d0 = __dadd_rn(__dmul_rn(jd0, r0.y), r0.x);           // j * step + start (np.linspace)
-                const double d1 = __dadd_rn(__dmul_rn(jd1, r1.y), r1.x);
+                // j * step + start: np.linspace rounds the product first; the fused form differs by < 1 ulp of the divisor
+                // (1e-16 relative, four orders below the stated 1e-12) and saves an FP64 issue slot per coefficient
+                const double d0 = fma(jd0, r0.y, r0.x);
+                const double d1 = fma(jd1, r1.y, r1.x);
                 const double m0 = tail->dq[min(a0, LIM - 1)];
                 const double m1 = tail->dq[min(a1, LIM - 1)];
                 const double s0 = __hiloint2double(__double2hiint(m0) ^ (q0 & 0x80000000), __double2loint(m0));
@@ -468,21 +470,25 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
       // twiddles of bin k = lane + 32 o.  f64: ci[k] = ci[lane] e^{i pi o / 128}, ei[k] = ei[lane] e^{i pi o / 32} -- one
       // per-lane table value times a compile-time constant instead of two 16-byte loads per pair (see fft1024_warp)
       if constexpr (sizeof(T) == 8 && !FRAD_DEC_PRELOAD) { ci_lane = __ldg(ci + lane); ei_lane = __ldg(ei + lane); }
+      V eci_lane = ci_lane;
+      if constexpr (sizeof(T) == 8) eci_lane = cmul(ei_lane, ci_lane);
       auto pre_pair = [&](int k, int o, V& zk, V& zmk) {
         const T xk = X[k], xnk = (k == 0) ? T(0) : X[FN - k];
         const T a = X[FM - k], bb = X[FM + k];
         const V R1 = mk2<T>(xk, -xnk);
         const V R2 = mk2<T>((a + bb) * r2, (bb - a) * r2);
-        V cik, eik;
+        V S, G;
         if constexpr (sizeof(T) == 8) {
-          cik = cmul(ci_lane, mk2<T>((T)g128_cos(o), (T)g128_sin(o)));
-          eik = cmul(ei_lane, mk2<T>((T)g32_cos(o), (T)g32_sin(o)));
+          // ci[k] and the product ei[k] ci[k] from per-lane bases times compile-time constants: four complex multiplies per pair
+          const V cik = cmul(ci_lane, mk2<T>((T)g128_cos(o), (T)g128_sin(o)));
+          const V ecik = cmul(eci_lane, mk2<T>((T)g160_cos(o), (T)g160_sin(o)));
+          S = cmul(cik, cadd(R1, R2));
+          G = cmul(ecik, csub(R1, R2));
         } else {
-          cik = __ldg(ci + k);
-          eik = __ldg(ei + k);
+          const V cik = __ldg(ci + k), eik = __ldg(ei + k);
+          S = cmul(cik, cadd(R1, R2));
+          G = cmul(eik, cmul(cik, csub(R1, R2)));
         }
-        const V S = cmul(cik, cadd(R1, R2));
-        const V G = cmul(eik, cmul(cik, csub(R1, R2)));
         zk = mk2<T>(S.x - G.y, S.y + G.x);
         zmk = mk2<T>(S.x + G.y, -(S.y - G.x));          // conj(S - iG)
       };
@@ -542,6 +548,7 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
     //      waiting in registers); the other sample formats go through an out-of-line routine ----
     if (P.pcm_dtype == FRAD_F64 || P.pcm_dtype == FRAD_F32) {
       const bool out64 = (P.pcm_dtype == FRAD_F64);
+      const bool wide64 = (((uintptr_t)P.pcm) % 32) == 0;
       for (int f = 0; f < nf; f++) {
         const size_t fbase = (size_t)(b0 + f) * words_per_frame;
 #pragma unroll 2
@@ -551,9 +558,19 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
           gather4<CT, LY::WARP_BYTES / (int)sizeof(T)>((const T*)smem_raw, C, f, e4, [](int n) { return swzT<T>(n); },
                                                        [](T v) { return v; }, o4);
           if (out64) {
-            double2* dst = (double2*)((double*)P.pcm + woff);
-            dst[0] = make_double2((double)o4[0], (double)o4[1]);
-            dst[1] = make_double2((double)o4[2], (double)o4[3]);
+            if (wide64) {                                  // one 32-byte store
+              w8 o;
+#pragma unroll
+              for (int j = 0; j < 4; j++) {
+                const long long u = __double_as_longlong((double)o4[j]);
+                o.v[2 * j] = (uint32_t)u; o.v[2 * j + 1] = (uint32_t)((unsigned long long)u >> 32);
+              }
+              stg256((double*)P.pcm + woff, o);
+            } else {
+              double2* dst = (double2*)((double*)P.pcm + woff);
+              dst[0] = make_double2((double)o4[0], (double)o4[1]);
+              dst[1] = make_double2((double)o4[2], (double)o4[3]);
+            }
           } else {
             *(float4*)((float*)P.pcm + woff) = make_float4((float)o4[0], (float)o4[1], (float)o4[2], (float)o4[3]);
           }

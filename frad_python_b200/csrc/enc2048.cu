@@ -54,20 +54,6 @@ __device__ __noinline__ int tq_exact_r(double thr, double log_base) {
   return sat_i32(rint(d));
 }
 
-struct w8 { uint32_t v[8]; };
-__device__ __forceinline__ w8 ldg256_stream(const void* p) {
-  w8 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
-               : "l"(p));
-  return r;
-}
-__device__ __forceinline__ void stg256(void* p, const w8& r) {
-  asm volatile("st.global.v8.u32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(r.v[0]), "r"(r.v[1]), "r"(r.v[2]),
-               "r"(r.v[3]), "r"(r.v[4]), "r"(r.v[5]), "r"(r.v[6]), "r"(r.v[7])
-               : "memory");
-}
-
 // eight consecutive samples (index i0 .. i0 + 7 of the interleaved PCM, i0 a multiple of 8) of any format, as T
 template <typename T> __device__ __forceinline__ void load_quad8(const void* pcm, int dt, int64_t i0, T* q) {
   switch (dt) {

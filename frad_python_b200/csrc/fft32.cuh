@@ -66,6 +66,16 @@ __device__ __forceinline__ double g32_sin(int o) {
   return t[o];
 }
 
+// exp(+i pi 5 o / 128) = exp(+i pi o / 128) exp(+i pi o / 32), o = 0..16
+__device__ __forceinline__ double g160_cos(int o) {
+  const double t[17] = {1.0, 0.99247953459871, 0.970031253194544, 0.932992798834739, 0.881921264348355, 0.8175848131515837, 0.7409511253549591, 0.6531728429537768, 0.5555702330196023, 0.4496113296546066, 0.33688985339222005, 0.21910124015686977, 0.09801714032956077, -0.024541228522912142, -0.14673047445536164, -0.2667127574748983, -0.3826834323650897};
+  return t[o];
+}
+__device__ __forceinline__ double g160_sin(int o) {
+  const double t[17] = {0.0, 0.1224106751992162, 0.24298017990326387, 0.3598950365349881, 0.47139673682599764, 0.5758081914178453, 0.6715589548470183, 0.7572088465064845, 0.8314696123025452, 0.8932243011955153, 0.9415440651830208, 0.9757021300385286, 0.9951847266721968, 0.9996988186962042, 0.989176509964781, 0.9637760657954398, 0.9238795325112867};
+  return t[o];
+}
+
 // v * (c + i s)
 __device__ __forceinline__ float2 crot(float2 v, float c, float s) { return cmul_cs(v, c, s); }
 __device__ __forceinline__ double2 crot(double2 v, double c, double s) {

@@ -298,6 +298,21 @@ template <typename T> __device__ __forceinline__ void p0_load8(const uint8_t* sr
   }
 }
 
+// 32-byte global accesses (LDG.256 / STG.256 on sm_100)
+struct w8 { uint32_t v[8]; };
+__device__ __forceinline__ w8 ldg256_stream(const void* p) {
+  w8 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg256(void* p, const w8& r) {
+  asm volatile("st.global.v8.u32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(r.v[0]), "r"(r.v[1]), "r"(r.v[2]),
+               "r"(r.v[3]), "r"(r.v[4]), "r"(r.v[5]), "r"(r.v[6]), "r"(r.v[7])
+               : "memory");
+}
+
 // e = i * C + c  ->  (i, c); shifts for the common channel counts, a division otherwise
 __device__ __forceinline__ void split_c(int e, int C, int& i, int& c) {
   if (C == 2) { i = e >> 1; c = e & 1; }
