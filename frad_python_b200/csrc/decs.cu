@@ -277,9 +277,19 @@ decs_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restrict_
       }
       const size_t woff = (size_t)(b0 + f) * NN * C + vi;
       if (P.pcm_dtype == FRAD_F64) {
-        double2* dst = (double2*)((double*)P.pcm + woff);
-        dst[0] = make_double2((double)o4[0], (double)o4[1]);
-        dst[1] = make_double2((double)o4[2], (double)o4[3]);
+        if ((((uintptr_t)P.pcm) % 32) == 0) {               // one 32-byte store
+          w8 o;
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const long long u = __double_as_longlong((double)o4[j]);
+            o.v[2 * j] = (uint32_t)u; o.v[2 * j + 1] = (uint32_t)((unsigned long long)u >> 32);
+          }
+          stg256((double*)P.pcm + woff, o);
+        } else {
+          double2* dst = (double2*)((double*)P.pcm + woff);
+          dst[0] = make_double2((double)o4[0], (double)o4[1]);
+          dst[1] = make_double2((double)o4[2], (double)o4[3]);
+        }
       } else if (P.pcm_dtype == FRAD_F32) {
         *(float4*)((float*)P.pcm + woff) = make_float4((float)o4[0], (float)o4[1], (float)o4[2], (float)o4[3]);
       } else {
