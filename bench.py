@@ -478,7 +478,7 @@ def main():
         traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
     except Exception:
         pass
-    k_enc = {"kernel": "enc2048_kernel<1,2> (f32 forward DCT + masking thresholds + quantiser -> int32)",
+    k_enc = {"kernel": "enc2048r_kernel<float,1,2> (f32 forward DCT + masking thresholds + quantiser -> int32)",
              "bytes": ncoef * 8.0, "ms": enc_ms}
     k_dec = {"kernel": "dec2048_kernel<double,1,2> (dequantiser + f64 inverse DCT, f64 PCM out; reference precision)",
              "bytes": ncoef * 12.0, "ms": dec_ms}
@@ -524,7 +524,7 @@ def main():
     }
     # profile 0 of the same clip shape (rank 0's timings; f32 PCM -> 32-bit big-endian coefficients -> f64 PCM)
     nval0 = B0 * N * CH
-    p0k = [{"kernel": "enc2048_kernel<0,2> (f32 forward DCT -> BE f32 payload + peak)", "bytes": nval0 * 8.0, "ms": p0_enc_ms},
+    p0k = [{"kernel": "enc2048r_kernel<float,0,2> (f32 forward DCT -> BE f32 payload + peak)", "bytes": nval0 * 8.0, "ms": p0_enc_ms},
            {"kernel": "dec2048_kernel<double,0,2> (unpack + f64 inverse DCT -> f64 PCM; reference precision)", "bytes": nval0 * 12.0,
             "ms": p0_dec_ms},
            {"kernel": "dec2048_kernel<float,0,2> (f32 inverse, f64 PCM out; <= 1 LSB at 16 bit)", "bytes": nval0 * 12.0,

@@ -39,6 +39,7 @@ class Encoder:
         self.srate = 0
         self.overlap_fragment = np.array([])
         self._frag_raw = None
+        self._frag_in_buffer = False
         self.pcm_format = ff_format_to_numpy_type(pcm_format)
         self.loss_level = 0.5
         self.init = False
@@ -126,6 +127,12 @@ class Encoder:
                                                  self.ctx, self.precision)
         return self._emit(pays, depth, ch, sr, fsizes, None, flush_each)
 
+    def _drop_buffered_fragment(self, bps: int):
+        frag = self.overlap_fragment
+        k = (len(frag) if frag.ndim == 2 else 0) * bps
+        self.buffer = self.buffer[k:]
+        self._frag_in_buffer = False
+
     def inner(self, stream: bytes, flush: bool) -> EncodeResult:
         self.buffer += stream
         ret, samples = [], 0
@@ -134,37 +141,51 @@ class Encoder:
         bps = self.pcm_format.itemsize * self.channels
 
         # ---- steady state: every complete frame in one batch --------------------------------
+        # The samples a lossy frame shares with the next one (encoder.py:46-50) are kept at the front of the byte buffer
+        # (`_frag_in_buffer`) as well as in `overlap_fragment`: the next batch then reads its frames straight out of the
+        # buffer -- a view, no concatenation of fragment and new PCM.
         n = self._frame_len()
         olap = self._overlap_len(n)
         frag = self.overlap_fragment
         frag_len = len(frag) if frag.ndim == 2 else 0
-        if n > 0 and frag_len in (0, olap) and bps > 0:
+        if self._frag_in_buffer and frag_len != olap:
+            self._drop_buffered_fragment(bps)
+        inbuf = frag_len if self._frag_in_buffer else 0
+        if n > 0 and frag_len in (0, olap) and bps > 0 and (frag_len == 0 or self._frag_in_buffer or self._frag_raw is not None
+                                                             or self.pcm_format.kind == "f"):
             hop = n - olap
-            avail = len(self.buffer) // bps
+            avail = len(self.buffer) // bps - inbuf              # samples not yet part of any frame
             first_need = n - frag_len
             if avail >= first_need:
                 nframes = 1 + (avail - first_need) // hop
                 used = first_need + (nframes - 1) * hop
-                mv = memoryview(self.buffer)                  # views, not slices: a 32 MiB piece is copied once, not four times
-                raw = np.frombuffer(mv[:used * bps], self.pcm_format).reshape(-1, self.channels)
-                self.buffer = bytes(mv[used * bps:])
-                # native-order integers stay raw (the device scales them like to_f64, pcmformat.py:34-47); a carried fragment is
-                # kept in the same raw form beside its float-domain twin, which the per-frame state machine below uses
-                fr_raw = self._frag_raw
-                raw_ok = frag_len == 0 or (fr_raw is not None and fr_raw.dtype == raw.dtype and len(fr_raw) == frag_len)
-                pcm = self._float_domain(raw, keep_native_ints=raw_ok)
-                if frag_len:
+                mv = memoryview(self.buffer)
+                raw = np.frombuffer(mv[:(inbuf + used) * bps], self.pcm_format).reshape(-1, self.channels)
+                pcm = self._float_domain(raw, keep_native_ints=True)
+                if frag_len and not inbuf:                    # fragment left by the per-frame state machine below: prepend once
                     whole = np.empty((frag_len + len(pcm), self.channels), pcm.dtype)
-                    whole[:frag_len] = fr_raw if (raw_ok and pcm.dtype == raw.dtype) else frag
+                    whole[:frag_len] = self._frag_raw if (self._frag_raw is not None and self._frag_raw.dtype == pcm.dtype) else frag
                     whole[frag_len:] = pcm
                     pcm = whole
                 ret.append(self._encode_frames(pcm, nframes, n, hop, [n] * nframes))
                 samples += used
                 if olap:
-                    self._frag_raw = np.array(pcm[nframes * hop:(nframes - 1) * hop + n])
+                    self.buffer = bytes(mv[(inbuf + used - olap) * bps:])       # the shared samples stay in front
+                    self._frag_in_buffer = True
+                    self._frag_raw = np.array(pcm[len(pcm) - olap:])
                     self.overlap_fragment = self._float_domain(self._frag_raw)
                 else:
+                    self.buffer = bytes(mv[(inbuf + used) * bps:])
+                    self._frag_in_buffer = False
                     self._frag_raw, self.overlap_fragment = None, np.array([])
+        if self._frag_in_buffer:
+            # the state machine below works from overlap_fragment; it only has something to do at flush time (or when it can
+            # form a frame, which the batch above has just ruled out) -- otherwise the fragment stays in the buffer
+            fl = len(self.overlap_fragment) if self.overlap_fragment.ndim == 2 else 0
+            need = (self._frame_len() - min(fl, self._frame_len())) * bps
+            if not flush and len(self.buffer) - fl * bps < need:
+                return EncodeResult(b"".join(ret), samples)
+            self._drop_buffered_fragment(bps)
 
         # ---- remainder: the reference's own per-frame state machine (flush / odd states) -----------
         while True:

@@ -5,6 +5,15 @@ import numpy as np
 from oracle import frad_oracle as O
 
 
+def _float_domain(pcm):
+    """What the device does with integer PCM: to_f64 (backend/pcmformat.py:34-47); floats keep their precision."""
+    dt = pcm.dtype
+    if dt.kind == "f":
+        return pcm
+    x = pcm.astype(np.float64) / float(2 ** (8 * dt.itemsize - 1))
+    return x - 1.0 if dt.kind == "u" else x
+
+
 class OracleCtx:
     """Implements the byte-side calls the batched Repairer / Decoder make (crc_many, rs_encode_many, rs_decode_many)."""
 
@@ -23,6 +32,7 @@ class OracleCtx:
     # ---- transform side (what Encoder / Decoder call on the batched routes), oracle arithmetic per frame ------------------
     def p0_encode(self, pcm, nframes, n, hop, bits, little_endian, prec=0, want_crc=True, profile=0):
         fn = O.p4_analogue if profile == 4 else O.p0_analogue
+        pcm = _float_domain(pcm)
         pays, peak = [], np.zeros(nframes)
         for i in range(nframes):
             fr = pcm[i * hop:i * hop + n]
@@ -43,6 +53,7 @@ class OracleCtx:
 
     def p1_encode_raw(self, pcm, nframes, n, hop, bits, srate, loss_level, prec=0, profile=1):
         import struct
+        pcm = _float_domain(pcm)
         parts = []
         for i in range(nframes):
             fr = pcm[i * hop:i * hop + n]

@@ -275,3 +275,46 @@ def test_native_batch_framing_matches_zlib_and_the_header_mirror(g_streams):
     mixed = g_streams["p0_b32"].tobytes()[:2 * (32 + 16384)] + s
     n, prm, *_ , nxt = _abi.asfh_scan(mixed, 0)
     assert n == 2 and nxt == 2 * (32 + 16384) and int(prm[0]) == 0
+
+
+@pytest.mark.parametrize("chunk", [32768, 1 << 22, 5000])
+def test_codec_objects_reproduce_the_reference_streams_with_oracle_arithmetic(g_streams, chunk):
+    """Host logic of the batched Encoder / Decoder / Repairer (frame cutting, overlap carry kept in the byte buffer, native
+    header writer and header walk, flush markers) with the oracle standing in for the device: the byte streams and the PCM
+    of the unmodified reference (tests/golden/streams.npz) come out bit for bit, for any chunking of the input."""
+    import frad_python_b200 as F
+    from stubctx import OracleCtx
+    loss0 = 1.25 ** 0 / 19 + 0.5
+    pcm = g_streams["pcm"]
+
+    def encode(profile, bits, ecc=False, le=False, ov=16, src=pcm, fmt="f32le", fsize=2048):
+        enc = F.Encoder(profile, 48000, 2, bits, fsize, fmt, ctx=OracleCtx())
+        enc.set_ecc(ecc, (96, 24)); enc.set_little_endian(le); enc.set_overlap_ratio(ov); enc.set_loss_level(loss0)
+        raw, out = src.tobytes(), b""
+        for i in range(0, len(raw), chunk):
+            out += enc.process(raw[i:i + chunk]).buf
+        return out + enc.flush().buf
+
+    assert encode(1, 16) == g_streams["p1"].tobytes()
+    assert encode(2, 16) == g_streams["p2"].tobytes()
+    assert encode(1, 16, ecc=True) == g_streams["p1_ecc"].tobytes()
+    assert encode(1, 16, ov=0) == g_streams["p1_noov"].tobytes()
+    assert encode(0, 32) == g_streams["p0_b32"].tobytes()
+    assert encode(0, 16, ecc=True, le=True) == g_streams["p0_b16_le_ecc"].tobytes()
+    assert encode(0, 24, src=g_streams["pcm_s16"], fmt="s16le", fsize=1000) == g_streams["p0_s16_b24"].tobytes()
+
+    def decode(name, fix=False):
+        dec = F.Decoder(fix, ctx=OracleCtx())
+        s, out = g_streams[name].tobytes(), []
+        for i in range(0, len(s), chunk):
+            r = dec.process(s[i:i + chunk])
+            if r.pcm.size:
+                out.append(r.pcm)
+        r = dec.flush()
+        if r.pcm.size:
+            out.append(r.pcm)
+        return np.concatenate(out)
+
+    for name, fix in (("p1", False), ("p2", False), ("p0_b32", False), ("p1_ecc", True), ("p1_ecc_bad", True), ("p0_b16_le_ecc_bad", True)):
+        got, want = decode(name, fix), g_streams[name + "_dec"]
+        assert got.shape == want.shape and np.max(np.abs(got - want)) <= 1e-13, name

@@ -13,6 +13,8 @@ frames = int(sys.argv[1]) if len(sys.argv) > 1 else 3000
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 mode = sys.argv[3] if len(sys.argv) > 3 else "p1"
 N, HOP, CH = 2048, 1920, 2
+if mode == "p1n1024":
+    N, HOP = 1024, 960
 L = _abi.lib()
 ctx = Context(0)
 tile = synth_pcm(2.0, 48000, CH, 1)
@@ -37,7 +39,7 @@ for _ in range(reps):
             d_lpc = ctx.dev(frames * 13 * CH * 4)
         ctx.check(L.frad_p1_encode_dev(ctx.handle, d_pcm.ptr, _abi.F32, HOP, frames, N, CH, 16, 48000, 0.5526315789473684, 0, d_q.ptr, d_tq.ptr, d_lpc.ptr))
         ctx.check(L.frad_p1_decode_dev(ctx.handle, d_q.ptr, d_tq.ptr, d_lpc.ptr, frames, N, CH, 16, 48000, _abi.PREC_F64, d_out.ptr, _abi.F64))
-    elif mode == "p1":
+    elif mode in ("p1", "p1n1024"):
         ctx.check(L.frad_p1_encode_dev(ctx.handle, d_pcm.ptr, _abi.F32, HOP, frames, N, CH, 16, 48000, 0.5526315789473684, 0, d_q.ptr, d_tq.ptr, None))
         ctx.check(L.frad_p1_decode_dev(ctx.handle, d_q.ptr, d_tq.ptr, None, frames, N, CH, 16, 48000, _abi.PREC_F64, d_out.ptr, _abi.F64))
         ctx.check(L.frad_p1_decode_dev(ctx.handle, d_q.ptr, d_tq.ptr, None, frames, N, CH, 16, 48000, _abi.PREC_F32, d_out.ptr, _abi.F64))
