@@ -789,95 +789,6 @@ int frad_ensure_dq64(frad_ctx* ctx) {
   return FRAD_OK;
 }
 
-// The same with coalesced memory traffic (round 2).  One thread per sequence reads and writes with a stride of C words per
-// bin and a whole frame between neighbouring threads: every 32-byte sector moved carries 8 (read) or 16 (write) useful
-// bytes, and the kernel was bound by that, not by the recurrence.  Here a CTA takes FPC = 128 / C whole frames (FPC C
-// sequences); per block of TNS_BLK bins all 128 threads fetch the frames' words in memory order (TNS_BLK C words = one or
-// two full lines per frame), dequantise them into shared memory, the sequence threads run their filter steps in place,
-// and the block leaves again in memory order.  Next block's integers are requested before the filter steps run.
-constexpr int TNS_BLK = 16;
-__global__ void __launch_bounds__(128) tns_synth_tiled_kernel(const int32_t* __restrict__ q, const int32_t* __restrict__ lpc, int B, int N,
-                                                               int C, double inv_scale, const double* __restrict__ dq64, int dq_len,
-                                                               double* __restrict__ spec) {
-  __shared__ double xs[TNS_BLK][130];                    // [bin of the block][sequence of the CTA], pitch 130: conflict-free both ways
-  const int tid = threadIdx.x;
-  const int fpc = 128 / C, sq = fpc * C;                 // frames / sequences per CTA
-  const int b0 = blockIdx.x * fpc;
-  const int nfr = min(fpc, B - b0);
-  const int nsq = nfr * C;
-  const int per = TNS_BLK * C;                           // words of one frame in a block
-  // my sequence (threads >= nsq only help with the copies)
-  const bool mine = tid < nsq;
-  const int fb = tid / C, c = tid - fb * C, b = b0 + fb;
-  double a[FRAD_LPC_LEN];
-  int any = 0;
-#pragma unroll
-  for (int i = 0; i < FRAD_LPC_LEN; i++) {
-    const int v = mine ? lpc[((size_t)b * FRAD_LPC_LEN + i) * C + c] : 0;
-    any |= (v != 0);
-    a[i] = (i == 0) ? 1.0 : (double)v / 15.0;                          // dequantise_lpc, p2tools.py:49-55
-  }
-  double z[FRAD_LPC_LEN - 1];
-#pragma unroll
-  for (int i = 0; i < FRAD_LPC_LEN - 1; i++) z[i] = 0.0;
-  double mx = 0.0;
-  bool bad = false;
-  int qreg[TNS_BLK];                                     // item i = tid + 128 r of the next block: frame i / per, word i % per
-  auto fetch = [&](int n0) {
-#pragma unroll
-    for (int r = 0; r < TNS_BLK; r++) {
-      const int i = tid + 128 * r, f = i / per, wd = i - f * per;
-      qreg[r] = (f < nfr && n0 + wd / C < N) ? __ldg(q + ((size_t)(b0 + f) * N + n0) * C + wd) : 0;
-    }
-  };
-  fetch(0);
-  for (int n0 = 0; n0 < N; n0 += TNS_BLK) {
-    // dequantise the fetched block into shared memory: sign(q) |q|^(4/3) / 2^(bits-1) (profile2.py:80)
-#pragma unroll
-    for (int r = 0; r < TNS_BLK; r++) {
-      const int i = tid + 128 * r, f = i / per, wd = i - f * per;
-      const int n = wd / C, cc = wd - n * C;
-      const int qv = qreg[r];
-      const uint32_t qa = (qv < 0) ? 0u - (uint32_t)qv : (uint32_t)qv;
-      double mag = __ldg(dq64 + min(qa, (uint32_t)(dq_len - 1))) * inv_scale;
-      if (qa >= (uint32_t)dq_len) mag = pow((double)qa, 1.0 / 0.75) * inv_scale;
-      if (f < fpc) xs[n][f * C + cc] = (qv < 0) ? -mag : mag;
-    }
-    __syncthreads();
-    if (n0 + TNS_BLK < N) fetch(n0 + TNS_BLK);           // in flight while the filter steps run
-    if (mine) {
-#pragma unroll
-      for (int j = 0; j < TNS_BLK; j++) {
-        const double xn = xs[j][tid];
-        const double yn = __dadd_rn(z[0], xn);
-        // SciPy also adds b[i] x[n] with b[i] = 0 to every state; x[n] is finite here, so those terms are +-0 and could only
-        // flip the sign of a state that is exactly zero -- left out.  All-zero LPC integers make this the identity.
-#pragma unroll
-        for (int i = 0; i < FRAD_LPC_LEN - 2; i++) z[i] = __dsub_rn(z[i + 1], __dmul_rn(yn, a[i + 1]));
-        z[FRAD_LPC_LEN - 2] = -__dmul_rn(yn, a[FRAD_LPC_LEN - 1]);
-        xs[j][tid] = yn;
-        bad |= !isfinite(yn);
-        mx = fmax(mx, fabs(yn));
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < TNS_BLK; r++) {
-      const int i = tid + 128 * r, f = i / per, wd = i - f * per;
-      const int n = wd / C, cc = wd - n * C;
-      if (f < nfr && n0 + n < N) spec[((size_t)(b0 + f) * N + n0) * C + wd] = xs[n][f * C + cc];
-    }
-    __syncthreads();
-  }
-  // rejected synthesis (p2tools.py:101-105): the sequence keeps its unfiltered coefficients
-  if (mine && any && (bad || mx > 1e6)) {
-    const int32_t* qs = q + (size_t)b * N * C + c;
-    double* out = spec + (size_t)b * N * C + c;
-    for (int n = 0; n < N; n++) out[(size_t)n * C] = dequant_slow(__ldg(qs + (size_t)n * C), dq64, dq_len, inv_scale);
-  }
-  (void)sq;
-}
-
 // profile 2: dequantiser + TNS synthesis of the whole batch into ctx scratch slot 4; sets P.spec
 static int run_tns_synthesis(frad_ctx* ctx, dec_params& P) {
   int rc = frad_ensure_dq64(ctx);
@@ -885,14 +796,10 @@ static int run_tns_synthesis(frad_ctx* ctx, dec_params& P) {
   double* spec = (double*)frad_scratch(ctx, 4, sizeof(double) * (size_t)P.B * P.N * P.C);
   if (!spec) return FRAD_E_NOMEM;
   const int nseq = P.B * P.C;
-  if (P.C <= 128 && (P.N % TNS_BLK) == 0 && !getenv("FRAD_TNS_SYNTH_OLD")) {
-    const int fpc = 128 / P.C;
-    tns_synth_tiled_kernel<<<(P.B + fpc - 1) / fpc, 128, 0, ctx->stream>>>(P.q, P.lpc, P.B, P.N, P.C, 1.0 / P.scale,
-                                                                         (const double*)ctx->dequant_table, FRAD_DQ_LEN, spec);
-  } else {
-    tns_synth_kernel<<<(nseq + 127) / 128, 128, 0, ctx->stream>>>(P.q, P.lpc, P.B, P.N, P.C, 1.0 / P.scale, (const double*)ctx->dequant_table,
-                                                                FRAD_DQ_LEN, spec);
-  }
+  // (A variant that stages TNS_BLK-bin blocks through shared memory for fully coalesced traffic was measured in round 2:
+  //  1.01 ms against 0.72 ms for the pair of decode kernels -- the recurrence is latency-bound, not sector-bound; not kept.)
+  tns_synth_kernel<<<(nseq + 127) / 128, 128, 0, ctx->stream>>>(P.q, P.lpc, P.B, P.N, P.C, 1.0 / P.scale, (const double*)ctx->dequant_table,
+                                                              FRAD_DQ_LEN, spec);
   FRAD_LAUNCH_CHECK(ctx);
   P.spec = spec;
   return FRAD_OK;
