@@ -194,12 +194,16 @@ def test_product_never_touches_the_oracle():
     assert len(uses) == 2 and all(any(0 < u - c < 600 for c in cpu_legs) for u in uses)
 
 
-def test_committed_bench_lines_follow_the_contract():
-    """profiles/r1_bench_line*.json are what bench.py printed on B200: the keys of the bench contract are all there."""
+@pytest.mark.parametrize("rnd", ["r1", "r2"])
+def test_committed_bench_lines_follow_the_contract(rnd):
+    """profiles/r?_bench_line*.json are what bench.py printed on B200: the keys of the bench contract are all there."""
     import json
     import os
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    d = json.load(open(os.path.join(root, "profiles", "r1_bench_line.json")))
+
+    def last_line(name):
+        return json.loads(open(os.path.join(root, "profiles", name)).read().strip().splitlines()[-1])
+    d = last_line(f"{rnd}_bench_line.json")
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
               "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
         assert k in d, k
@@ -213,12 +217,17 @@ def test_committed_bench_lines_follow_the_contract():
     c = d["cpu_baseline"]
     assert {"value", "unit", "cores", "kind", "sample"} <= set(c) and c["kind"] in ("port", "reference") and c["cores"] == 1
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"]) and d["gpu_launches"] > 0
-    ref = json.load(open(os.path.join(root, "profiles", "r1_bench_reference_line.json")))
+    ref = last_line(f"{rnd}_bench_reference_line.json")
     assert ref["impl"] == "reference" and ref["metric"] == d["metric"] and ref["unit"] == d["unit"]
     assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["cpu_baseline"]["value"] == ref["value"]
     for n in (2, 4, 8):
-        m = json.load(open(os.path.join(root, "profiles", f"r1_bench_line_{n}gpu.json")))
+        m = last_line(f"{rnd}_bench_line_{n}gpu.json")
         assert m["n_gpus"] == n and m["value"] > 0.9 * n * d["value"] * 0.9
+        if rnd == "r2":                                    # strong leg: one stream over n GPUs, identical to one GPU
+            for prof in ("p0", "p1"):
+                leg = m["strong"][prof]
+                assert leg["identical_to_one_gpu"] is True and len(leg["frames_per_rank"]) == n
+                assert sum(leg["frames_per_rank"]) == leg["frames"]
 
 
 def test_native_batch_framing_matches_zlib_and_the_header_mirror(g_streams):
