@@ -362,10 +362,11 @@ def main():
 
     e2e_step()
     barrier()
-    e2e_steps = max(2, min(args.steps, 5))
+    e2e_steps = max(2, min(args.steps, 20))     # the K steps of the contract (capped at 20: 8.4 ms each)
     ctx.event(5)
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+    e2e_serial_steps = min(e2e_steps, 5)
+    for _ in range(e2e_serial_steps):
         e2e_step()
     ctx.event(6)
     barrier()
@@ -503,7 +504,7 @@ def main():
                 "path": "frad_p1_encode_raw + frad_p1_decode_raw (pinned host buffers, f32 PCM out), two contexts: step i is "
                         "decoded while step i + 1 is encoded (both PCIe directions busy); wall clock over all steps incl. "
                         "pipeline fill and drain",
-                "serial": {"value": world * nscal / (e2e_serial_ms / e2e_steps * 1e-3) / 1e6, "unit": "MSamples/s",
+                "serial": {"value": world * nscal / (e2e_serial_ms / e2e_serial_steps * 1e-3) / 1e6, "unit": "MSamples/s",
                            "path": "the same two calls back to back on one context (encode, then decode)"},
                 "int32_f64_path": {"value": world * nscal / (e2e_int_ms * 1e-3) / 1e6, "unit": "MSamples/s",
                                    "h2d_bytes_per_step": int(h_pcm.nbytes + h_q.nbytes + h_tq.nbytes),

@@ -1,7 +1,10 @@
 // Host-pointer entry points: copy in, run the *_dev path, copy out, synchronise.
 // These are what a ctypes / cgo / JNI binding of the reference's per-frame seams would call.
+#include <cstdio>
 #include <cstdlib>
+#include <ctime>
 #include <sched.h>
+#include <vector>
 #include "common.cuh"
 
 static uint32_t host_max_len(const uint32_t* len, uint32_t ulen, int B) {
@@ -59,10 +62,19 @@ static inline cudaError_t wait_event(cudaEvent_t e) {
   }
 }
 
+// FRAD_TRACE=1: every pipelined call prints one line per chunk to stderr -- host submit times and device completion times
+// of its input copy, kernels and output copy, in ms since the call started (CLOCK_MONOTONIC of the start included, so
+// the lines of two contexts can be laid side by side).  Diagnostics only: the events then carry time stamps.
+static const int kTrace = env_int("FRAD_TRACE", 0, 0);
+static inline double mono_ms() {
+  timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+  return 1e3 * (double)ts.tv_sec + 1e-6 * (double)ts.tv_nsec;
+}
 struct pipeline {
   frad_ctx* ctx; int nchunks; int chunk;
   cudaEvent_t* in_done; cudaEvent_t* k_done; cudaEvent_t* aux; cudaEvent_t* out_done;     // one event of each kind per chunk
-  cudaEvent_t fin;
+  cudaEvent_t fin, fence;
+  double t0; std::vector<double> h_in, h_run, h_out;                                       // trace: host submit times
 };
 
 int pipeline_begin(frad_ctx* ctx, int B, pipeline* p) {
@@ -71,7 +83,7 @@ int pipeline_begin(frad_ctx* ctx, int B, pipeline* p) {
   p->nchunks = (B + p->chunk - 1) / p->chunk;
   while ((int)ctx->pipe_events.size() < 4 * p->nchunks + 2) {
     cudaEvent_t e;
-    FRAD_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming | (kWait == 2 ? cudaEventBlockingSync : 0)));
+    FRAD_CUDA(ctx, cudaEventCreateWithFlags(&e, (kTrace ? 0 : cudaEventDisableTiming) | (kWait == 2 ? cudaEventBlockingSync : 0)));
     ctx->pipe_events.push_back(e);
   }
   p->in_done = ctx->pipe_events.data();
@@ -81,6 +93,11 @@ int pipeline_begin(frad_ctx* ctx, int B, pipeline* p) {
   p->fin = ctx->pipe_events[2 * p->nchunks + 1];
   // the copy streams must not run ahead of work already queued on the main stream (buffer reuse)
   cudaEvent_t fence = ctx->pipe_events[2 * p->nchunks];
+  p->fence = fence;
+  if (kTrace) {
+    p->t0 = mono_ms();
+    p->h_in.assign(p->nchunks, 0.0); p->h_run.assign(p->nchunks, 0.0); p->h_out.assign(p->nchunks, 0.0);
+  }
   FRAD_CUDA(ctx, cudaEventRecord(fence, ctx->stream));
   FRAD_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, fence, 0));
   FRAD_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, fence, 0));
@@ -128,6 +145,7 @@ int pipeline_run_inner(pipeline& p, int B, NEED need, H2D h2d, RUN run, D2H d2h,
       const int i = submitted_in;
       if (i >= kDepth) FRAD_CUDA(ctx, wait_event(p.in_done[i - kDepth]));
       const int f0 = i * p.chunk, f1 = (f0 + p.chunk < B) ? f0 + p.chunk : B;
+      if (kTrace) p.h_in[i] = mono_ms() - p.t0;
       int r = h2d(i, f0, f1, ctx->s_in);
       if (r) return r;
       FRAD_CUDA(ctx, cudaEventRecord(p.in_done[i], ctx->s_in));
@@ -138,6 +156,7 @@ int pipeline_run_inner(pipeline& p, int B, NEED need, H2D h2d, RUN run, D2H d2h,
     const int f0 = i * p.chunk, f1 = (f0 + p.chunk < B) ? f0 + p.chunk : B;
     FRAD_CUDA(ctx, wait_event(p.k_done[i]));
     if (i >= kDepth) FRAD_CUDA(ctx, wait_event(p.out_done[i - kDepth]));
+    if (kTrace) p.h_out[i] = mono_ms() - p.t0;
     int r = d2h(f0, f1, ctx->s_out);
     if (r) return r;
     FRAD_CUDA(ctx, cudaEventRecord(p.out_done[i], ctx->s_out));
@@ -148,6 +167,7 @@ int pipeline_run_inner(pipeline& p, int B, NEED need, H2D h2d, RUN run, D2H d2h,
     const int last = need(i);
     if ((rc = queue_in_upto(last))) return rc;
     FRAD_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, p.in_done[last], 0));    // s_in is in order: covers every earlier chunk
+    if (kTrace) p.h_run[i] = mono_ms() - p.t0;
     if ((rc = run(f0, f1))) return rc;
     FRAD_CUDA(ctx, cudaEventRecord(p.k_done[i], ctx->stream));
     if (i + 1 < p.nchunks && (rc = queue_in_upto(need(i + 1)))) return rc;   // next input while these kernels run
@@ -157,6 +177,17 @@ int pipeline_run_inner(pipeline& p, int B, NEED need, H2D h2d, RUN run, D2H d2h,
   if ((rc = fin(ctx->s_out))) return rc;
   FRAD_CUDA(ctx, cudaEventRecord(p.fin, ctx->s_out));      // the kernels of every chunk precede its output copy
   FRAD_CUDA(ctx, wait_event(p.fin));
+  if (kTrace) {
+    const double t1 = mono_ms() - p.t0;
+    for (int i = 0; i < p.nchunks; i++) {
+      float a = 0, k = 0, o = 0;
+      cudaEventElapsedTime(&a, p.fence, p.in_done[i]);
+      cudaEventElapsedTime(&k, p.fence, p.k_done[i]);
+      cudaEventElapsedTime(&o, p.fence, p.out_done[i]);
+      fprintf(stderr, "{\"trace\": \"%p\", \"t0\": %.3f, \"chunk\": %d, \"h_in\": %.3f, \"in_done\": %.3f, \"h_run\": %.3f, \"k_done\": %.3f, "
+                      "\"h_out\": %.3f, \"out_done\": %.3f, \"end\": %.3f}\n", (void*)ctx, p.t0, i, p.h_in[i], a, p.h_run[i], k, p.h_out[i], o, t1);
+    }
+  }
   return FRAD_OK;
 }
 template <class NEED, class H2D, class RUN, class D2H, class FIN = no_fin>

@@ -11,6 +11,8 @@ import json
 import os
 import sys
 
+os.environ.setdefault("NCCL_DEBUG", "WARN")      # no version banner on stdout: the output is one JSON line
+
 import torch
 import torch.distributed as dist
 
