@@ -363,23 +363,120 @@ __global__ void __launch_bounds__(256) seq_decode_direct_kernel(dec_params P, pl
   }
 }
 
-// Profile-2 encode, second step after the N = 2048 transform kernel: one CTA of FRAD_TNS_THREADS threads per (frame,
-// channel) sequence.  Reads the spectrum (float bits left in the q array, [B][N][C]) and the sequence's thresholds
-// ([B][C][28] doubles), forms the masked spectrum X / div in f64 (profile2.py:28-31), runs the TNS analysis on it
-// (p2tools.py:72-95) and quantises the residual -- or the masked spectrum where TNS is rejected -- in place
-// (profile2.py:34-46).  Same device routines as the generic path's epilogue; the CTA is smaller (the per-thread partial
-// sums group differently, i.e. the last bits of the f64 reductions differ, the LPC integers do not).
-#ifndef FRAD_TNS_THREADS
-#define FRAD_TNS_THREADS 128         // measured: 1.75 ms with 256 threads (3 CTAs/SM), 1.49 ms with 128 (6 CTAs/SM, limited by shared memory)
+// Profile-2 encode, second step after the N = 2048 transform kernel (which leaves the spectrum as float bits in the q array,
+// [B][N][C], and the sequence's thresholds in [B][C][28] doubles).  Round 2: three kernels instead of one.
+//
+//   tns_stats_kernel   one CTA of 128 threads per (frame, channel) sequence: masked spectrum X / div in f64
+//                      (profile2.py:28-31), the sums of lpc_cond (p2tools.py:108-111) and, where the condition holds, the 13
+//                      windowed autocorrelation lags of the mean-removed unit-norm signal (p2tools.py:8-15)
+//   tns_lpc_kernel     one THREAD per sequence: Levinson-Durbin + 4-bit LPC quantiser (p2tools.py:17-34, 82-88).  In the
+//                      one-kernel version this serial recursion ran on thread 0 while 127 threads waited at a barrier (12 % of
+//                      the kernel's stall samples); here 30 000 of them run side by side
+//   tns_apply_kernel   one CTA per sequence again: masked spectrum recomputed from the same operands (bit-identical), FIR
+//                      residual lfilter(lpc_deq, [1], x), the finite / 1e6 check and the prediction gain (p2tools.py:57-70, 89-95),
+//                      then the quantiser over the residual -- or the masked spectrum where TNS is rejected (profile2.py:34-46)
+//
+// Thread t owns the 16 consecutive bins [16 t, 16 t + 16) in registers; the only values that cross threads are the 12-bin halos
+// of the two sliding windows (autocorrelation looks ahead, the FIR looks back), fetched once from shared memory -- the first
+// version re-read every operand of both passes from shared memory (13 loads per bin and pass, 415 instructions per bin).
+// Shared-memory rows are padded by one slot per 16 (`tpad`), so per-thread runs of 4- and 8-byte values are conflict-free;
+// global I/O stays coalesced through a staging row.  Re-reading the spectrum costs 245 MB of HBM traffic (0.04 ms); keeping
+// the two passes in separate kernels halves the live registers of each.  The block sums group differently from the generic
+// path's (last bits of the f64 reductions), the LPC integers and the per-output operation order of the FIR (lfilter's) do not.
+#define FRAD_TNS_THREADS 128
+#define FRAD_TNS_BPT 16
+#ifndef FRAD_TNS_MINB_STATS
+#define FRAD_TNS_MINB_STATS 4
 #endif
-__global__ void __launch_bounds__(FRAD_TNS_THREADS, 768 / FRAD_TNS_THREADS) tns_encode_kernel(enc_params P, const double* __restrict__ thr_in) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  band_work* bw = (band_work*)smem_raw;
-  double* masked = (double*)(smem_raw + ((sizeof(band_work) + 15) & ~(size_t)15));
-  double* work = masked + P.N;
-  uint8_t* bidx = (uint8_t*)(work + P.N);               // band of every bin (same for all sequences): 255 = past the ramps
-  const int t = threadIdx.x, N = P.N, C = P.C;
-  const int nseq = P.B * C;
+#ifndef FRAD_TNS_MINB_APPLY
+#define FRAD_TNS_MINB_APPLY 4
+#endif
+#define FRAD_TNS_ROW (2048 + 2048 / 16)
+__device__ __forceinline__ int tpad(int k) { return k + (k >> 4); }
+
+// block reductions of the 4-warp TNS CTAs: block_sum / block_max / block_sum_multi of profiles.cuh (same additions in the same
+// order) with the warp count a compile-time constant
+// Sums K (a power of two <= 16) values over the warp with K - 1 + (5 - log2 K) exchanges instead of 5 K: every step halves the
+// values a lane still carries (the lane keeps the half its bit of the lane number selects and adds the partner's copy of it).
+// On return v[0] of lane l is the warp total of value wrs_index<K>(l); every total sits in 32 / K lanes.
+template <int K> __device__ __forceinline__ int wrs_index(int lane) {
+  int idx = 0;
+#pragma unroll
+  for (int n = K, o = 16; n > 1; n >>= 1, o >>= 1) idx |= (lane & o) ? (n >> 1) : 0;
+  return idx;
+}
+template <int K>
+__device__ __forceinline__ void warp_reduce_scatter(double (&v)[K], int lane) {
+  int o = 16;
+#pragma unroll
+  for (int n = K; n > 1; n >>= 1, o >>= 1) {
+    const int half = n >> 1;
+    const bool upper = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < half; i++) {
+      const double send = upper ? v[i] : v[i + half];
+      const double keep = upper ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+#pragma unroll
+  for (; o > 0; o >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+}
+template <int K>
+__device__ __forceinline__ void tns_sum_multi(double (&v)[K], double* red /* K * 32 doubles */) {
+  constexpr int NW = FRAD_TNS_THREADS / 32;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  warp_reduce_scatter<K>(v, lane);
+  __syncthreads();
+  if ((lane & (32 / K - 1)) == 0) red[wrs_index<K>(lane) * 32 + w] = v[0];
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < K; j++) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < NW; i++) t += red[j * 32 + i];
+    v[j] = t;
+  }
+}
+__device__ __forceinline__ double tns_sum(double v, double* red) { double a[1] = {v}; tns_sum_multi<1>(a, red); return a[0]; }
+__device__ __forceinline__ double tns_max(double v, double* red) {
+  constexpr int NW = FRAD_TNS_THREADS / 32;
+  v = warp_max(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = red[0];
+#pragma unroll
+  for (int i = 1; i < NW; i++) t = fmax(t, red[i]);
+  return t;
+}
+
+// quant075 (profiles.cuh) with approximate square roots (<= 1 ulp each: 3e-7 relative in total, inside the 1e-6 guard) and the
+// f64 formula next to a rounding tie out of line -- the inlined slow path made the unrolled quantiser loop miss the instruction cache
+__device__ __noinline__ double tns_div(double a, double b) { return a / b; }
+__device__ __noinline__ int32_t quant075_slow(double y) { return sat_i32(rint(copysign(pow075(fabs(y)), y))); }
+__device__ __forceinline__ int32_t quant075_fast(double y) {
+  const float af = (float)fabs(y);
+  float s1, v;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s1) : "f"(af));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(v) : "f"(af * s1));
+  const float r = rintf(v);
+  if (fabsf(fabsf(v - r) - 0.5f) > 1.0e-6f * v + 1.0e-7f && v < 4.0e6f) { const int m = (int)r; return (y < 0.0) ? -m : m; }
+  return quant075_slow(y);
+}
+
+struct tns_ctl {                   // per-sequence hand-over between the three kernels
+  double r[FRAD_LPC_LEN];          // stats -> lpc: windowed lags
+  double sx;                       // stats -> apply: sum of the masked spectrum
+  int aq[FRAD_LPC_LEN];            // lpc -> apply: quantised coefficients (aq[0] unused)
+  int cond;                        // stats: lpc_cond holds and the lags are valid
+  int flag;                        // lpc: coefficients accepted
+  int pad_;
+};
+
+// band of every bin (same for all sequences; 255 = past the ramps) + clipped band starts; one call per CTA
+__device__ __forceinline__ void tns_cta_setup(const enc_params& P, band_work* bw, uint8_t* bidx) {
+  const int t = threadIdx.x, N = P.N;
   if (t <= FRAD_NBANDS) { const int e = P.bt->edge[t]; bw->lo[t] = (e < N) ? e : N; }
   __syncthreads();
   for (int k = t; k < N; k += blockDim.x) {
@@ -388,39 +485,302 @@ __global__ void __launch_bounds__(FRAD_TNS_THREADS, 768 / FRAD_TNS_THREADS) tns_
     for (int sh = 16; sh > 0; sh >>= 1) { if (b + sh <= FRAD_NBANDS - 2 && bw->lo[b + sh] <= k) b += sh; }
     bidx[k] = (k >= bw->lo[FRAD_NBANDS - 1]) ? 255 : (uint8_t)b;     // exactly ramp_value's search
   }
+}
+
+// pulls the sequence this CTA takes after `s` towards L2
+__device__ __forceinline__ void tns_prefetch_next(const enc_params& P, int s, int nseq) {
+  const int s2 = s + gridDim.x;
+  if (s2 < nseq && (s2 / P.C) != (s / P.C)) {
+    const char* nxt = (const char*)(P.q + (size_t)(s2 / P.C) * P.N * P.C);
+    const size_t bytes = (size_t)P.N * P.C * 4;
+    for (size_t o = (size_t)threadIdx.x * 128; o < bytes; o += (size_t)blockDim.x * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + o));
+  }
+}
+
+// masked spectrum of the own block (profile2.py:28-31); with SUMS also this thread's share of
+// sum log(|x| + 1e-10) (f32 first), sum |x|, sum x^2, sum x.  Contains barriers: every thread of the CTA calls it.
+template <bool SUMS>
+__device__ __forceinline__ void tns_masked_own(const enc_params& P, const double* __restrict__ thr_in, band_work* bw, const uint8_t* bidx,
+                                               int32_t* stage, int s, double (&x)[FRAD_TNS_BPT], double (&s4)[4]) {
+  constexpr int BPT = FRAD_TNS_BPT;
+  const int t = threadIdx.x, N = P.N, C = P.C;
+  const int b = s / C, c = s - b * C;
+  const int own = (BPT + 1) * t;                         // tpad(16 t)
+  __syncthreads();                                       // the previous sequence's staging row and band parameters are free
+  const int32_t* qrow = P.q + (size_t)b * N * C + c;
+  {
+    const int32_t* qp = qrow + (size_t)t * C;
+    const size_t qstep = (size_t)FRAD_TNS_THREADS * C;
+    int32_t* sp = stage + tpad(t);                       // tpad(t + 128 j) = tpad(t) + 136 j
+#pragma unroll
+    for (int j = 0; j < BPT; j++) sp[(FRAD_TNS_THREADS + FRAD_TNS_THREADS / 16) * j] = __ldg(qp + qstep * j);
+  }
+  if (t <= FRAD_NBANDS) bw->thr[t] = thr_in[(size_t)s * (FRAD_NBANDS + 1) + t];
+  __syncthreads();
+  ramp_setup(bw, P.bt, N);
+  __syncthreads();
+  const uint4 bq = *(const uint4*)(bidx + BPT * t);
+  const uint32_t bwd[4] = {bq.x, bq.y, bq.z, bq.w};
+  int cur = -1, lo = 0; double step = 0.0, thr0 = 0.0;
+  float slf = 0.0f;
+#pragma unroll
+  for (int i = 0; i < BPT; i++) {
+    const int bnd = (int)((bwd[i >> 2] >> (8 * (i & 3))) & 255u);
+    if (bnd != cur) { cur = bnd; if (bnd != 255) { lo = bw->lo[bnd]; step = bw->step[bnd]; thr0 = bw->thr[bnd]; } }
+    const double xv = (double)__int_as_float(stage[own + i]);
+    const double div = (bnd == 255) ? 0.0 : __dadd_rn(__dmul_rn((double)(BPT * t + i - lo), step), thr0);
+    const double v = (div == 0.0) ? 0.0 : xv / div;
+    x[i] = v;
+    if (SUMS) {
+      const double m = fabs(v);
+      // log2 from the SFU (absolute error 2^-22): the sum only feeds the flatness test, which is re-done in f64 inside +-1e-3
+      slf += __log2f((float)(m + 1e-10)); s4[1] += m; s4[2] += v * v; s4[3] += v;
+    }
+  }
+  if (SUMS) s4[0] = (double)slf * 0.69314718055994530942;
+}
+
+__global__ void __launch_bounds__(FRAD_TNS_THREADS, FRAD_TNS_MINB_STATS)
+tns_stats_kernel(enc_params P, const double* __restrict__ thr_in, tns_ctl* __restrict__ ctl, double* __restrict__ xbuf) {
+  constexpr int BPT = FRAD_TNS_BPT, L = FRAD_LPC_LEN, H = FRAD_LPC_LEN - 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  band_work* bw = (band_work*)smem_raw;
+  double* ws = (double*)(smem_raw + ((sizeof(band_work) + 15) & ~(size_t)15));     // normalised signal (autocorrelation halos)
+  int32_t* stage = (int32_t*)ws;                                                   // input staging row (before ws is live)
+  uint8_t* bidx = (uint8_t*)(ws + FRAD_TNS_ROW);
+  const int t = threadIdx.x, N = P.N;
+  const int nseq = P.B * P.C;
+  const int own = (BPT + 1) * t;
+  tns_cta_setup(P, bw, bidx);
   for (int s = blockIdx.x; s < nseq; s += gridDim.x) {
-    const int b = s / C, c = s - b * C;
-    {   // the frame of this CTA's next sequence: towards L2 now, read at the top of the next iteration
-      const int s2 = s + gridDim.x;
-      if (s2 < nseq) {
-        const char* nxt = (const char*)(P.q + (size_t)(s2 / C) * N * C);
-        const size_t bytes = (size_t)N * C * 4;
-        for (size_t o = (size_t)t * 128; o < bytes; o += (size_t)blockDim.x * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + o));
+    tns_prefetch_next(P, s, nseq);
+    double x[BPT];
+    double s4[4] = {0.0, 0.0, 0.0, 0.0};
+    tns_masked_own<true>(P, thr_in, bw, bidx, stage, s, x, s4);
+    {                                                    // hand the masked spectrum to tns_apply_kernel: 128 contiguous bytes per thread
+      double2* xo = (double2*)(xbuf + (size_t)s * N + BPT * t);
+#pragma unroll
+      for (int i = 0; i < BPT / 2; i++) xo[i] = make_double2(x[2 * i], x[2 * i + 1]);
+    }
+    tns_sum_multi<4>(s4, bw->redm);                      // (its barriers also retire the staging row)
+    const double sa = s4[1], se = s4[2], sx = s4[3];
+    const double arith = sa / N;
+    double flat = exp(s4[0] / N) / (arith + 1e-10);
+    if (!(fabs(flat - 0.5) > 1e-3)) {                    // too close to call (or NaN): exact f64 sum of logs, same for every thread
+      double sl = 0.0;
+#pragma unroll
+      for (int i = 0; i < BPT; i++) sl += log(fabs(x[i]) + 1e-10);
+      sl = tns_sum(sl, bw->redm);
+      flat = exp(sl / N) / (arith + 1e-10);
+    }
+    const bool cond = (flat < 0.5) && !(se < 1e-10);     // uniform over the CTA: every thread holds the same sums
+    if (cond) {
+      // ---- autocorrelation of the mean-removed, unit-norm signal (p2tools.py:8-15) ----
+      const double mean = sx / N;
+      double sg[BPT + H];
+      double ss = 0.0;
+#pragma unroll
+      for (int i = 0; i < BPT; i++) { sg[i] = x[i] - mean; ss += sg[i] * sg[i]; }
+      ss = tns_sum(ss, bw->redm);
+      const double nrm = sqrt(ss);
+      if (nrm > 1e-6) {
+        // x / nrm with one division per thread: q0 = x r, q = q0 + (x - q0 nrm) r with r = RN(1 / nrm) is the correctly
+        // rounded quotient (Markstein), except possibly when the significand of nrm is all ones -- that case divides
+        const double rinv = 1.0 / nrm;
+        const bool plain = ((unsigned long long)__double_as_longlong(nrm) & 0xFFFFFFFFFFFFFull) == 0xFFFFFFFFFFFFFull;
+        if (!plain) {
+#pragma unroll
+          for (int i = 0; i < BPT; i++) {
+            const double w = sg[i];
+            const double q0 = w * rinv;
+            sg[i] = fma(fma(-q0, nrm, w), rinv, q0);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < BPT; i++) sg[i] = tns_div(sg[i], nrm);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < BPT; i++) ws[own + i] = sg[i];
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < H; j++) sg[BPT + j] = (t + 1 < FRAD_TNS_THREADS) ? ws[own + (BPT + 1) + j] : 0.0;   // next block's first 12
+      double acc[L];
+#pragma unroll
+      for (int l = 0; l < L; l++) acc[l] = 0.0;
+#pragma unroll
+      for (int i = 0; i < BPT; i++) {
+#pragma unroll
+        for (int l = 0; l < L; l++) acc[l] += sg[i] * sg[i + l];
+      }
+      // warp totals to shared memory (16 slots, 13 used); thread l adds up lag l, applies the lag window (p2tools.py:14) and
+      // hands it over
+      const int w = t >> 5, nw = FRAD_TNS_THREADS >> 5;
+      {
+        double a16[16];
+#pragma unroll
+        for (int l = 0; l < 16; l++) a16[l] = (l < L) ? acc[l] : 0.0;
+        warp_reduce_scatter<16>(a16, t & 31);
+        const int idx = wrs_index<16>(t & 31);
+        if ((t & 1) == 0 && idx < L) bw->redm[idx * 32 + w] = a16[0];
+      }
+      __syncthreads();
+      if (t < L) {
+        double v = 0.0;
+        for (int i = 0; i < nw; i++) v += bw->redm[t * 32 + i];
+        const double wl = 0.01 * t;
+        ctl[s].r[t] = v * exp(-0.5 * (wl * wl));
       }
     }
-    __syncthreads();
-    if (t <= FRAD_NBANDS) {
-      const int e = P.bt->edge[t];
-      bw->lo[t] = (e < N) ? e : N;
-      bw->thr[t] = thr_in[(size_t)s * (FRAD_NBANDS + 1) + t];
+    if (t == 0) { ctl[s].sx = sx; ctl[s].cond = cond ? 1 : 0; }
+  }
+}
+
+// Levinson-Durbin + 4-bit LPC quantiser (p2tools.py:17-34, 82-88) on the windowed lags; one thread per sequence.
+__global__ void __launch_bounds__(64) tns_lpc_kernel(tns_ctl* __restrict__ ctl, int nseq) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nseq) return;
+  int flag = 0;
+  int aqv[FRAD_LPC_LEN];
+#pragma unroll
+  for (int j = 0; j < FRAD_LPC_LEN; j++) aqv[j] = 0;
+  if (ctl[s].cond) {
+    double r[FRAD_LPC_LEN];
+#pragma unroll
+    for (int l = 0; l < FRAD_LPC_LEN; l++) r[l] = ctl[s].r[l];
+    double a[FRAD_LPC_LEN];
+#pragma unroll
+    for (int i = 0; i < FRAD_LPC_LEN; i++) a[i] = 0.0;
+    a[0] = 1.0;
+    double err = r[0];
+    bool go = err > 1e-10;
+    levinson_step<1>(a, r, err, go); levinson_step<2>(a, r, err, go); levinson_step<3>(a, r, err, go);
+    levinson_step<4>(a, r, err, go); levinson_step<5>(a, r, err, go); levinson_step<6>(a, r, err, go);
+    levinson_step<7>(a, r, err, go); levinson_step<8>(a, r, err, go); levinson_step<9>(a, r, err, go);
+    levinson_step<10>(a, r, err, go); levinson_step<11>(a, r, err, go); levinson_step<12>(a, r, err, go);
+    double prod[FRAD_LPC_LEN];
+#pragma unroll
+    for (int j = 0; j < FRAD_LPC_LEN - 1; j++) prod[j] = fabs(a[j + 1]);
+    prod[FRAD_LPC_LEN - 1] = 0.0;
+    const bool ok = !(np_sum_small_t<FRAD_LPC_LEN - 1>(prod) < 0.01);
+    int any = 0;
+#pragma unroll
+    for (int j = 1; j < FRAD_LPC_LEN; j++) {
+      double v = a[j] * 15.0;
+      v = fmin(fmax(v, -15.0), 14.0);
+      aqv[j] = (int)rint(v);
+      any |= (aqv[j] != 0);
     }
-    __syncthreads();
-    ramp_setup(bw, P.bt, N);
+    flag = (ok && any) ? 1 : 0;
+  }
+#pragma unroll
+  for (int j = 0; j < FRAD_LPC_LEN; j++) ctl[s].aq[j] = flag ? aqv[j] : 0;
+  ctl[s].flag = flag;
+}
+
+__global__ void __launch_bounds__(FRAD_TNS_THREADS, FRAD_TNS_MINB_APPLY)
+tns_apply_kernel(enc_params P, const tns_ctl* __restrict__ ctl, const double* __restrict__ xbuf) {
+  constexpr int BPT = FRAD_TNS_BPT, L = FRAD_LPC_LEN, H = FRAD_LPC_LEN - 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  band_work* bw = (band_work*)smem_raw;
+  double* xs = (double*)(smem_raw + ((sizeof(band_work) + 15) & ~(size_t)15));     // masked spectrum, padded rows (FIR halos)
+  int32_t* stage = (int32_t*)(xs + FRAD_TNS_ROW);                                  // output staging row
+  const int t = threadIdx.x, N = P.N, C = P.C;
+  const int nseq = P.B * C;
+  const int own = (BPT + 1) * t;
+  for (int s = blockIdx.x; s < nseq; s += gridDim.x) {
+    const int b = s / C, c = s - b * C;
+    double x[BPT];
+    {
+      const double2* xi = (const double2*)(xbuf + (size_t)s * N + BPT * t);
+#pragma unroll
+      for (int i = 0; i < BPT / 2; i++) { const double2 v = __ldg(xi + i); x[2 * i] = v.x; x[2 * i + 1] = v.y; }
+    }
+    if (s + gridDim.x < nseq) {                          // pull this CTA's next sequence towards L2 (one 128-byte line per thread)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(xbuf + (size_t)(s + gridDim.x) * N + BPT * t));
+      if (t == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(ctl + s + gridDim.x));
+    }
+    __syncthreads();                                     // the previous sequence's rows and coefficients are free
+    bool accept = ctl[s].flag != 0;                      // uniform over the CTA
+    int aq_t = 0;
+    double y[BPT];
+    if (accept) {
+      if (t < L) { aq_t = ctl[s].aq[t]; bw->a[t] = (t == 0) ? 1.0 : (double)aq_t / 15.0; }     // dequantise_lpc, p2tools.py:49-55
+      const double sx = ctl[s].sx;
+#pragma unroll
+      for (int i = 0; i < BPT; i++) xs[own + i] = x[i];
+      __syncthreads();
+      // ---- FIR residual, lfilter(lpc_deq, [1], x): b0 x[n] + (b1 x[n-1] + (... + b12 x[n-12])), tap by tap over the block ----
+      double xh[H + BPT];                                // xh[H + i] = x[i], xh[0 .. H) = the previous block's last 12 bins
+#pragma unroll
+      for (int j = 0; j < H; j++) xh[j] = (t > 0) ? xs[own - (BPT + 1) + (BPT - H) + j] : 0.0;
+#pragma unroll
+      for (int i = 0; i < BPT; i++) xh[H + i] = x[i];
+      if (t > 0) {                                       // all taps present
+        const double c12 = bw->a[L - 1];
+#pragma unroll
+        for (int i = 0; i < BPT; i++) y[i] = __dmul_rn(c12, xh[i]);
+#pragma unroll
+        for (int k = L - 2; k >= 0; k--) {
+          const double ck = bw->a[k];
+#pragma unroll
+          for (int i = 0; i < BPT; i++) y[i] = __dadd_rn(y[i], __dmul_rn(ck, xh[H + i - k]));
+        }
+      } else {                                           // the first bins of the sequence: only the taps that exist (lfilter's start-up)
+#pragma unroll
+        for (int i = 0; i < BPT; i++) {
+          double a12 = 0.0;
+          bool first = true;
+#pragma unroll
+          for (int k = L - 1; k >= 1; k--) {
+            if (i - k >= 0) {
+              const double pp = __dmul_rn(bw->a[k], xh[H + i - k]);
+              a12 = first ? pp : __dadd_rn(a12, pp);
+              first = false;
+            }
+          }
+          const double p0 = __dmul_rn(bw->a[0], xh[H + i]);
+          y[i] = first ? p0 : __dadd_rn(a12, p0);
+        }
+      }
+      double mxv = 0.0;
+      double s2[2] = {0.0, 0.0};                         // count of non-finite outputs, sum of the residual
+#pragma unroll
+      for (int i = 0; i < BPT; i++) {
+        if (!isfinite(y[i])) s2[0] = 1.0;
+        mxv = fmax(mxv, fabs(y[i]));
+        s2[1] += y[i];
+      }
+      mxv = tns_max(mxv, bw->red);
+      tns_sum_multi<2>(s2, bw->redm);
+      const double sr = s2[1];
+      accept = !(s2[0] > 0.0 || mxv > 1e6);
+      // prediction gain (p2tools.py:57-70)
+      const double mo = sx / N, mr = sr / N;
+      double e2[2] = {0.0, 0.0};
+#pragma unroll
+      for (int i = 0; i < BPT; i++) {
+        const double d0 = x[i] - mo, d1 = y[i] - mr;
+        e2[0] += d0 * d0; e2[1] += d1 * d1;
+      }
+      tns_sum_multi<2>(e2, bw->redm);
+      const double eo = e2[0], er = e2[1];
+      double gain = 0.0;
+      if (!(eo < 1e-10 || er < 1e-10 || er >= eo)) gain = 20.0 * log10(eo / er);
+      if (gain < 0.030102999566398118) accept = false;    // log10(2) / 10
+    }
+    // ---- quantise the residual (or the masked spectrum) and store through the staging row ----
+#pragma unroll
+    for (int i = 0; i < BPT; i++) stage[own + i] = quant075_fast((accept ? y[i] : x[i]) * P.scale);
+    if (t < L) P.lpc[((size_t)b * L + t) * C + c] = accept ? aq_t : 0;
     __syncthreads();
     int32_t* qrow = P.q + (size_t)b * N * C + c;
-    for (int k = t; k < N; k += blockDim.x) {
-      const double x = (double)__int_as_float(qrow[(size_t)k * C]);
-      const int bnd = bidx[k];
-      const double div = (bnd == 255) ? 0.0 : __dadd_rn(__dmul_rn((double)(k - bw->lo[bnd]), bw->step[bnd]), bw->thr[bnd]);
-      masked[k] = (div == 0.0) ? 0.0 : x / div;
-    }
-    __syncthreads();
-    tns_analysis_block(masked, work, N, bw);
-    const double* src = bw->flag ? work : masked;
-    if (t < FRAD_LPC_LEN) P.lpc[((size_t)b * FRAD_LPC_LEN + t) * C + c] = bw->aq[t];
-    for (int k = t; k < N; k += blockDim.x) {
-      const double y = src[k] * P.scale;
-      qrow[(size_t)k * C] = quant075(y);
+    {
+      int32_t* qp = qrow + (size_t)t * C;
+      const size_t qstep = (size_t)FRAD_TNS_THREADS * C;
+      const int32_t* sp = stage + tpad(t);
+#pragma unroll
+      for (int j = 0; j < BPT; j++) qp[qstep * j] = sp[(FRAD_TNS_THREADS + FRAD_TNS_THREADS / 16) * j];
     }
   }
 }
@@ -741,19 +1101,34 @@ static int launch_encode(frad_ctx* ctx, enc_params& P, int prec) {
   if (!ctx->opt_force_generic && frad_fast2048_encode_ok(P, prec)) {
     P.fast_ok = 2;                                   // tells the caller that 12-bit payloads are already nibble-packed
     if (P.profile != 2) return frad_launch_encode_2048(ctx, P, pl, prec, ctx->opt_exact_quant);
-    // profile 2: transform + thresholds, then the TNS kernel (one CTA per sequence, masked spectrum and residual in smem)
-    double* thr = (double*)frad_scratch(ctx, 4, sizeof(double) * (size_t)nseq * (FRAD_NBANDS + 1));
-    if (!thr) return FRAD_E_NOMEM;
+    // profile 2: transform + thresholds, then the three TNS kernels (statistics + lags, Levinson per sequence, residual + quantiser)
+    const size_t thr_bytes = (sizeof(double) * (size_t)nseq * (FRAD_NBANDS + 1) + 15) & ~(size_t)15;
+    const size_t ctl_bytes = (sizeof(tns_ctl) * (size_t)nseq + 15) & ~(size_t)15;
+    char* sc = (char*)frad_scratch(ctx, 4, thr_bytes + ctl_bytes + sizeof(double) * (size_t)nseq * P.N);
+    if (!sc) return FRAD_E_NOMEM;
+    double* thr = (double*)sc;
+    tns_ctl* ctl = (tns_ctl*)(sc + thr_bytes);
+    double* xbuf = (double*)(sc + thr_bytes + ctl_bytes);       // masked spectrum [sequence][N] f64, stats -> apply
     P.tns_scratch = thr;
     int rc = frad_launch_encode_2048(ctx, P, pl, prec, ctx->opt_exact_quant);
     if (rc) return rc;
-    const size_t smem = ((sizeof(band_work) + 15) & ~(size_t)15) + 2 * (size_t)P.N * sizeof(double) + (size_t)P.N;
-    FRAD_CUDA(ctx, cudaFuncSetAttribute(tns_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t head = (sizeof(band_work) + 15) & ~(size_t)15;
+    const size_t smem_stats = head + (size_t)FRAD_TNS_ROW * sizeof(double) + (size_t)P.N;
+    const size_t smem_apply = head + (size_t)FRAD_TNS_ROW * (sizeof(double) + sizeof(int32_t));
+    FRAD_CUDA(ctx, cudaFuncSetAttribute(tns_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_stats));
+    FRAD_CUDA(ctx, cudaFuncSetAttribute(tns_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_apply));
     int per_sm = 1;
-    FRAD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tns_encode_kernel, FRAD_TNS_THREADS, smem));
+    FRAD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tns_stats_kernel, FRAD_TNS_THREADS, smem_stats));
     if (per_sm < 1) per_sm = 1;
     int grid = per_sm * ctx->sm_count; if (grid > nseq) grid = nseq;
-    tns_encode_kernel<<<grid, FRAD_TNS_THREADS, smem, ctx->stream>>>(P, thr);
+    tns_stats_kernel<<<grid, FRAD_TNS_THREADS, smem_stats, ctx->stream>>>(P, thr, ctl, xbuf);
+    FRAD_LAUNCH_CHECK(ctx);
+    tns_lpc_kernel<<<(nseq + 63) / 64, 64, 0, ctx->stream>>>(ctl, nseq);
+    FRAD_LAUNCH_CHECK(ctx);
+    FRAD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tns_apply_kernel, FRAD_TNS_THREADS, smem_apply));
+    if (per_sm < 1) per_sm = 1;
+    grid = per_sm * ctx->sm_count; if (grid > nseq) grid = nseq;
+    tns_apply_kernel<<<grid, FRAD_TNS_THREADS, smem_apply, ctx->stream>>>(P, ctl, xbuf);
     FRAD_LAUNCH_CHECK(ctx);
     return FRAD_OK;
   }

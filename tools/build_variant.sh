@@ -11,5 +11,5 @@ src=${VARIANT_SRC:-dct2048}
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-O2,-Wall -DFRAD_HAVE_FAST2048 "$@" \
   -c $src.cu -o build/var_$name/$src.o 2> build/var_$name/ptxas.log || { cat build/var_$name/ptxas.log; exit 1; }
 objs=$(ls build/*.o | grep -v "/$src.o")
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../lib/variants/$name.so $objs build/var_$name/$src.o -lcudart
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../lib/variants/$name.so $objs build/var_$name/$src.o -lcudart -lz -lpthread
 echo built ../lib/variants/$name.so
