@@ -22,10 +22,13 @@
 
 namespace {
 
+#ifndef GE_MINB
+#define GE_MINB 3
+#endif
 constexpr int GE_THREADS = 256;
 constexpr int GE_VPT = 16;                                  // values per thread and chunk
 constexpr int GE_CHUNK = GE_THREADS * GE_VPT;               // 4096 values
-constexpr int GE_WORDS = (GE_CHUNK * 35 + 31) / 32 + 2;     // bit buffer of one chunk (+ carried partial word)
+constexpr int GE_WORDS = (GE_CHUNK * 35 + 31) / 32 + 3;     // bit buffer of one chunk (+ carried partial word)
 
 struct ge_smem {
   uint32_t bits[GE_WORDS];
@@ -61,40 +64,76 @@ __device__ __forceinline__ uint32_t block_exscan(uint32_t v, ge_smem* sm, uint32
   return base + inc - v;
 }
 
-// code of one value: w (the bits) and its length in bits
-__device__ __forceinline__ void code_of(int32_t v, int k, uint64_t* w, int* len) {
-  const uint64_t a = (v < 0) ? (uint64_t)(-(int64_t)v) : (uint64_t)v;
-  const uint64_t u = (v > 0) ? 2 * a - 1 : 2 * a;
-  const uint64_t x = u + (1ull << k);
-  const int nb = 64 - __clzll((long long)x);
-  *w = x;
-  *len = 2 * nb - (k + 1);
+// this thread's 16 consecutive values [i0, i0 + 16) of the stream (0 beyond n): four 16-byte loads where the row allows them
+__device__ __forceinline__ void load_vals(const int32_t* __restrict__ v, int n, int i0, int32_t (&val)[GE_VPT]) {
+  if (i0 + GE_VPT <= n && (((uintptr_t)(v + i0)) & 15) == 0) {
+    const int4* p = (const int4*)(v + i0);
+#pragma unroll
+    for (int j = 0; j < GE_VPT / 4; j++) { const int4 x = __ldg(p + j); val[4 * j] = x.x; val[4 * j + 1] = x.y; val[4 * j + 2] = x.z; val[4 * j + 3] = x.w; }
+  } else {
+#pragma unroll
+    for (int j = 0; j < GE_VPT; j++) val[j] = (i0 + j < n) ? __ldg(v + i0 + j) : 0;
+  }
+}
+
+// Bytes [skip, nbytes) of the big-endian bit buffer to o[skip .. nbytes); o is 4-byte aligned: whole words are byte-swapped and
+// stored as words, the (at most 3 + 3) bytes in front of and behind them one by one.
+__device__ __forceinline__ void flush_bits(const uint32_t* __restrict__ bits, uint8_t* __restrict__ o, uint32_t skip, uint32_t nbytes) {
+  const uint32_t w0 = (skip + 3) >> 2, w1 = nbytes >> 2;
+  uint32_t* ow = (uint32_t*)o;
+  for (uint32_t w = w0 + threadIdx.x; w < w1; w += GE_THREADS) ow[w] = __byte_perm(bits[w], 0, 0x0123);
+  if (threadIdx.x < 8) {
+    const uint32_t j = threadIdx.x & 3;
+    uint32_t b; bool ok;
+    if (threadIdx.x < 4) { b = j; ok = (b >= skip) && (b < min(4 * w0, nbytes)); }                  // in front of the first whole word
+    else { b = 4 * w1 + j; ok = (w1 >= w0) && (b >= skip) && (b < nbytes); }                         // behind the last one
+    if (ok) o[b] = (uint8_t)(bits[b >> 2] >> (24 - 8 * (b & 3)));
+  }
 }
 
 // Encodes the stream v[0..n) to dst (k byte + bits); returns the byte length.  All threads of the CTA take part.
-__device__ uint32_t encode_stream(const int32_t* __restrict__ v, int n, uint8_t* __restrict__ dst, ge_smem* sm) {
+// Round 2: the values are loaded once and stay in registers between the maximum and the code pass (streams of up to one chunk,
+// i.e. every stream of the N <= 2048 stereo frames); code lengths are k + 1 or k + 3, so a thread's bit count is a population
+// count; only the words a chunk can reach are cleared; the bit buffer is laid out relative to the 4-byte aligned address below
+// dst + 1, so that it leaves as byte-swapped words instead of single bytes.
+__device__ __noinline__ uint32_t encode_stream(const int32_t* __restrict__ v, int n, uint8_t* __restrict__ dst, ge_smem* sm) {
   const int tid = threadIdx.x;
   if (n <= 0) { if (tid == 0) dst[0] = 0; return 1; }
+  const bool single = (n <= GE_CHUNK);
+  int32_t val[GE_VPT];
   uint32_t mx = 0;
-  for (int i = tid; i < n; i += GE_THREADS) { const int32_t x = v[i]; mx = max(mx, (uint32_t)((x < 0) ? -(int64_t)x : (int64_t)x)); }
+  if (single) {
+    load_vals(v, n, tid * GE_VPT, val);
+#pragma unroll
+    for (int j = 0; j < GE_VPT; j++) mx = max(mx, (uint32_t)((val[j] < 0) ? -(int64_t)val[j] : (int64_t)val[j]));
+  } else {
+    for (int i = tid; i < n; i += GE_THREADS) { const int32_t x = v[i]; mx = max(mx, (uint32_t)((x < 0) ? -(int64_t)x : (int64_t)x)); }
+  }
   mx = block_max(mx, sm);
   const int k = (mx <= 1) ? 0 : 32 - __clz((int)(mx - 1));
   if (tid == 0) dst[0] = (uint8_t)k;
   uint8_t* out = dst + 1;
-  uint64_t bitpos = 0;                                        // bits already flushed to `out` (multiple of 32) + carried bits
-  uint32_t carry = 0;                                         // bits of the partial word kept in sm->bits[0]
+  const uint32_t mis = (uint32_t)((uintptr_t)out & 3);         // the buffer's byte 0 is out - mis
+  uint8_t* obase = out - mis;
+  uint64_t flushed = 0;                                        // buffer bytes already written (a multiple of 4)
+  uint32_t carry = 8 * mis;                                    // bits of sm->bits[0] in front of this chunk's codes
+  uint32_t skip = mis;                                         // bytes at the front of the buffer that are not ours (first chunk)
   for (int c0 = 0; c0 < n; c0 += GE_CHUNK) {
-    for (int i = tid; i < GE_WORDS; i += GE_THREADS) if (i > 0 || c0 == 0) sm->bits[i] = 0;
+    const int nv = min(GE_CHUNK, n - c0);
+    const uint32_t reach = (carry + (uint32_t)nv * (uint32_t)(k + 3) + 31) / 32 + 1;
+    for (uint32_t i = tid; i < reach; i += GE_THREADS) if (i > 0 || c0 == 0) sm->bits[i] = 0;
     // this thread's values: [c0 + 16 tid, +16)
     const int i0 = c0 + tid * GE_VPT;
-    uint64_t w[GE_VPT];
-    int len[GE_VPT];
-    uint32_t mine = 0;
+    if (!single) load_vals(v, n, i0, val);
+    const int cnt = max(0, min(GE_VPT, n - i0));
+    uint32_t longmask = 0;                                     // codes of k + 3 bits: u >= 2^k
 #pragma unroll
     for (int j = 0; j < GE_VPT; j++) {
-      if (i0 + j < n) code_of(v[i0 + j], k, &w[j], &len[j]); else { w[j] = 0; len[j] = 0; }
-      mine += (uint32_t)len[j];
+      const uint64_t a = (val[j] < 0) ? (uint64_t)(-(int64_t)val[j]) : (uint64_t)val[j];
+      const uint64_t u = (val[j] > 0) ? 2 * a - 1 : 2 * a;
+      if (j < cnt && (u >> k) != 0) longmask |= 1u << j;
     }
+    const uint32_t mine = (uint32_t)cnt * (uint32_t)(k + 1) + 2u * (uint32_t)__popc(longmask);
     uint32_t chunk_bits;
     const uint32_t start = carry + block_exscan(mine, sm, &chunk_bits);     // bit offset inside sm->bits
     // (block_exscan's barriers also order the zeroing above before the writes below)
@@ -110,31 +149,36 @@ __device__ uint32_t encode_stream(const int32_t* __restrict__ v, int n, uint8_t*
       };
 #pragma unroll
       for (int j = 0; j < GE_VPT; j++) {
-        int l = len[j];
-        if (l > 32) { acc = (acc << (l - 16)) | (w[j] >> 16); nacc += l - 16; if (nacc >= 32) emit(); w[j] &= 0xFFFFu; l = 16; }
-        if (l) { acc = (acc << l) | w[j]; nacc += l; if (nacc >= 32) emit(); }
+        if (j < cnt) {
+          const uint64_t a = (val[j] < 0) ? (uint64_t)(-(int64_t)val[j]) : (uint64_t)val[j];
+          const uint64_t u = (val[j] > 0) ? 2 * a - 1 : 2 * a;
+          uint64_t w = u + (1ull << k);
+          int l = ((longmask >> j) & 1u) ? k + 3 : k + 1;
+          if (l > 32) { acc = (acc << (l - 16)) | (w >> 16); nacc += l - 16; if (nacc >= 32) emit(); w &= 0xFFFFu; l = 16; }
+          acc = (acc << l) | w; nacc += l; if (nacc >= 32) emit();
+        }
       }
       if (nacc > 0) atomicOr(&sm->bits[wi], (uint32_t)(acc << (32 - nacc)));
     }
     __syncthreads();
-    // flush the complete words (big-endian byte order) and keep the partial one for the next chunk
+    // flush the complete words and keep the partial one for the next chunk
     const uint32_t filled = carry + chunk_bits;
     const bool last = (c0 + GE_CHUNK >= n);
     const uint32_t nbytes = last ? (filled + 7) / 8 : (filled / 32) * 4;
-    uint8_t* o = out + (bitpos >> 3);
-    for (uint32_t b = tid; b < nbytes; b += GE_THREADS) o[b] = (uint8_t)(sm->bits[b >> 2] >> (24 - 8 * (b & 3)));
-    if (last) return 1 + (uint32_t)(bitpos >> 3) + nbytes;
+    flush_bits(sm->bits, obase + flushed, skip, nbytes);
+    if (last) return 1 + (uint32_t)(flushed + nbytes - mis);
     const uint32_t keep = sm->bits[filled / 32];
     __syncthreads();
     if (tid == 0) sm->bits[0] = keep;
-    bitpos += (filled / 32) * 32;
+    flushed += (filled / 32) * 4;
     carry = filled & 31;
+    skip = 0;
     __syncthreads();
   }
   return 0;   // not reached
 }
 
-__global__ void __launch_bounds__(GE_THREADS) p1_pack_kernel(const int32_t* __restrict__ q, const int32_t* __restrict__ tq,
+__global__ void __launch_bounds__(GE_THREADS, GE_MINB) p1_pack_kernel(const int32_t* __restrict__ q, const int32_t* __restrict__ tq,
                                                              const int32_t* __restrict__ lpc, int B, int nq, int ntq, int nlpc,
                                                              uint8_t* __restrict__ raw, size_t stride, uint32_t* __restrict__ raw_len) {
   __shared__ ge_smem sm;
@@ -273,6 +317,41 @@ __device__ __forceinline__ lane_chain run_chain(const stream_view& sv, uint32_t 
     bw.win = ((uint64_t)(bw.word() << off)) << 32;
     bw.navail = 32 - off;
     const int64_t bias = (int64_t)1 << sv.k;
+    auto put = [&](int32_t v) {                                // value number r.count of this chain
+      const int at = obase + r.count;
+      if (at < cap) {
+        const int slot = at & 3;
+        if (slot == 3 && filled == 3 && vec) { *(int4*)(out + at - 3) = make_int4(v0, v1, v2, v); filled = 0; }
+        else if (slot == 3) {                                  // group started in the middle (or unaligned row): scalar stores
+          if (filled >= 3) out[at - 3] = v0;
+          if (filled >= 2) out[at - 2] = v1;
+          if (filled >= 1) out[at - 1] = v2;
+          out[at] = v; filled = 0;
+        } else { v0 = v1; v1 = v2; v2 = v; filled++; }         // v2 is the most recent value
+      }
+    };
+    // Fast walk (round 2).  What a conforming encoder writes is a '1' followed by k bits or '01' followed by k + 1 bits (k is
+    // derived from the maximum, see the header), so away from the end of the stream a code is classified by its two leading
+    // bits and its length is k + 1 or k + 3 -- for k <= 29 at most 32 bits, i.e. one refill and one shift per code.  Two leading
+    // zeros, the last 64 bits of the stream and k >= 30 go through the general loop below, which accepts everything the
+    // reference's parser accepts; both loops classify a code the same way, so where the walk stops makes no difference.
+    if (sv.k <= 29 && sv.nbits > 64) {
+      const uint32_t lim = min(seg_hi, sv.nbits - 64);
+      const int l1 = sv.k + 1, l3 = sv.k + 3;
+      while (pos < lim) {
+        bw.refill();                                           // navail in (32, 64]
+        const uint32_t top = (uint32_t)(bw.win >> 62);
+        if (top == 0) break;
+        const int l = (top & 2u) ? l1 : l3;
+        if (WRITE) {
+          const int32_t nv = (int32_t)((uint32_t)(bw.win >> (64 - l)) - (uint32_t)bias);      // < 2^(k+2) <= 2^31
+          put((nv & 1) ? ((nv + 1) >> 1) : -(nv >> 1));
+        }
+        bw.win <<= l; bw.navail -= l;
+        pos += (uint32_t)l;
+        r.count++;
+      }
+    }
     while (pos < seg_hi) {
       bw.refill();
       const uint32_t remaining = sv.nbits - pos;
@@ -304,18 +383,7 @@ __device__ __forceinline__ lane_chain run_chain(const stream_view& sv, uint32_t 
       if (WRITE) {
         const int64_t nv = (int64_t)x - bias;
         const int64_t val = (nv & 1) ? ((nv + 1) >> 1) : -(nv >> 1);
-        const int32_t v = (int32_t)max((int64_t)-2147483647 - 1, min((int64_t)2147483647, val));
-        const int at = obase + r.count;
-        if (at < cap) {
-          const int slot = at & 3;
-          if (slot == 3 && filled == 3 && vec) { *(int4*)(out + at - 3) = make_int4(v0, v1, v2, v); filled = 0; }
-          else if (slot == 3) {                                // group started in the middle (or unaligned row): scalar stores
-            if (filled >= 3) out[at - 3] = v0;
-            if (filled >= 2) out[at - 2] = v1;
-            if (filled >= 1) out[at - 1] = v2;
-            out[at] = v; filled = 0;
-          } else { v0 = v1; v1 = v2; v2 = v; filled++; }       // v2 is the most recent value
-        }
+        put((int32_t)max((int64_t)-2147483647 - 1, min((int64_t)2147483647, val)));
       }
       r.count++;
     }
