@@ -264,14 +264,28 @@ __global__ void __launch_bounds__(128) compact_kernel(const uint8_t* __restrict_
 // ---- decode ---------------------------------------------------------------------------------------------
 struct bit_window {
   const uint32_t* w; uint32_t wi, nwords, last_mask;
+  uint32_t nxt;                                                // word wi, already fetched: the load is one refill ahead of its use
   uint64_t win; int navail;
-  __device__ __forceinline__ uint32_t word() {
+  __device__ __forceinline__ uint32_t fetch(uint32_t i) const {
     uint32_t x = 0;
-    if (wi < nwords) {
-      x = __byte_perm(__ldg(w + wi), 0, 0x0123);
-      if (wi == nwords - 1) x &= last_mask;
+    if (i < nwords) {
+      x = __byte_perm(__ldg(w + i), 0, 0x0123);
+      if (i == nwords - 1) x &= last_mask;
     }
+    return x;
+  }
+  __device__ __forceinline__ void start(uint32_t abs_bit) {    // window at absolute bit abs_bit of the word array
+    wi = abs_bit >> 5;
+    const int off = (int)(abs_bit & 31);
+    win = ((uint64_t)(fetch(wi) << off)) << 32;
+    navail = 32 - off;
     wi++;
+    nxt = fetch(wi);
+  }
+  __device__ __forceinline__ uint32_t word() {
+    const uint32_t x = nxt;
+    wi++;
+    nxt = fetch(wi);
     return x;
   }
   __device__ __forceinline__ void refill() {                   // navail <= 32 -> navail in (32, 64]
@@ -311,11 +325,7 @@ __device__ __forceinline__ lane_chain run_chain(const stream_view& sv, uint32_t 
   if (pos < seg_hi) {
     bit_window bw;
     bw.w = sv.w; bw.nwords = sv.nwords; bw.last_mask = sv.last_mask;
-    const uint32_t abs0 = (uint32_t)sv.skip + pos;
-    bw.wi = abs0 >> 5;
-    const int off = (int)(abs0 & 31);
-    bw.win = ((uint64_t)(bw.word() << off)) << 32;
-    bw.navail = 32 - off;
+    bw.start((uint32_t)sv.skip + pos);
     const int64_t bias = (int64_t)1 << sv.k;
     auto put = [&](int32_t v) {                                // value number r.count of this chain
       const int at = obase + r.count;
@@ -335,13 +345,12 @@ __device__ __forceinline__ lane_chain run_chain(const stream_view& sv, uint32_t 
     // bits and its length is k + 1 or k + 3 -- for k <= 29 at most 32 bits, i.e. one refill and one shift per code.  Two leading
     // zeros, the last 64 bits of the stream and k >= 30 go through the general loop below, which accepts everything the
     // reference's parser accepts; both loops classify a code the same way, so where the walk stops makes no difference.
-    if (sv.k <= 29 && sv.nbits > 64) {
-      const uint32_t lim = min(seg_hi, sv.nbits - 64);
-      const int l1 = sv.k + 1, l3 = sv.k + 3;
-      while (pos < lim) {
-        bw.refill();                                           // navail in (32, 64]
-        const uint32_t top = (uint32_t)(bw.win >> 62);
-        if (top == 0) break;
+    const uint32_t lim = (sv.k <= 29 && sv.nbits > 64) ? min(seg_hi, sv.nbits - 64) : 0;
+    const int l1 = sv.k + 1, l3 = sv.k + 3;
+    while (pos < seg_hi) {
+      bw.refill();                                             // navail in (32, 64]
+      const uint32_t top = (uint32_t)(bw.win >> 62);
+      if (top != 0 && pos < lim) {
         const int l = (top & 2u) ? l1 : l3;
         if (WRITE) {
           const int32_t nv = (int32_t)((uint32_t)(bw.win >> (64 - l)) - (uint32_t)bias);      // < 2^(k+2) <= 2^31
@@ -350,10 +359,8 @@ __device__ __forceinline__ lane_chain run_chain(const stream_view& sv, uint32_t 
         bw.win <<= l; bw.navail -= l;
         pos += (uint32_t)l;
         r.count++;
+        continue;
       }
-    }
-    while (pos < seg_hi) {
-      bw.refill();
       const uint32_t remaining = sv.nbits - pos;
       if (bw.win == 0) {                                       // only padding left, or > 32 zeros in front of a code
         if (remaining > (uint32_t)bw.navail) r.bad = 1;
