@@ -185,6 +185,7 @@ class Context:
         self.handle = h
         self.device = device
         self._pinned = []
+        self._registered = {}          # address -> nbytes of caller-owned memory page-locked through register()
 
     # -- plumbing ---------------------------------------------------------------------------
     def close(self):
@@ -192,6 +193,9 @@ class Context:
             for p in self._pinned:
                 lib().frad_host_free(self.handle, p)
             self._pinned = []
+            for addr in list(self._registered):          # memory must not outlive its registration: a freed, still page-locked
+                lib().frad_host_unregister(self.handle, addr)      # range that malloc hands out again fails in cudaMemcpyAsync
+            self._registered = {}
             lib().frad_ctx_destroy(self.handle)
             self.handle = None
 
@@ -236,8 +240,11 @@ class Context:
     def register(self, arr: np.ndarray):
         """Page-lock an existing host array (a shared-memory mapping, say) for asynchronous copies; undo with unregister."""
         self.check(lib().frad_host_register(self.handle, arr.ctypes.data, arr.nbytes))
+        self._registered[arr.ctypes.data] = arr.nbytes
 
     def unregister(self, arr: np.ndarray):
+        if self._registered.pop(arr.ctypes.data, None) is None:
+            return                                       # not ours, or already undone by close()
         self.check(lib().frad_host_unregister(self.handle, arr.ctypes.data))
 
     def dev(self, nbytes: int) -> DeviceBuffer:

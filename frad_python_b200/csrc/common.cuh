@@ -45,10 +45,21 @@ static inline int frad_fail(frad_ctx* ctx, int code, const char* what, const cha
   return code;
 }
 
+// Table uploads (once per table, never on the timed path).  A cudaMemcpy from pageable memory may return as soon as the source
+// has been staged: the DMA itself is ordered on the legacy stream, which the library's non-blocking streams do not wait for.
+// A kernel launched right after the first use of a table could read it before it had arrived (seen as a rare wrong
+// Reed-Solomon word in the first test run on a cold box), so the device is synchronised before the table is published.
+static inline cudaError_t frad_upload(void* d, const void* h, size_t n) {
+  cudaError_t e = cudaMemcpy(d, h, n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  return e;
+}
+
 #define FRAD_CUDA(ctx, call)                                                      \
   do {                                                                            \
     cudaError_t _e = (call);                                                      \
-    if (_e != cudaSuccess) return frad_fail((ctx), FRAD_E_CUDA, #call, cudaGetErrorString(_e)); \
+    if (_e != cudaSuccess) { cudaGetLastError(); /* reported here: a later launch check must not see it again */ \
+      return frad_fail((ctx), FRAD_E_CUDA, #call, cudaGetErrorString(_e)); }        \
   } while (0)
 
 #define FRAD_LAUNCH_CHECK(ctx)                                                    \

@@ -212,7 +212,7 @@ int ensure_tables(frad_ctx* ctx) {
   build_tables(0xA001u, 16, &h->t16);
   void* d = nullptr;
   cudaError_t e = cudaMalloc(&d, sizeof(crc_tables_all));
-  if (e == cudaSuccess) e = cudaMemcpy(d, h, sizeof(crc_tables_all), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = frad_upload(d, h, sizeof(crc_tables_all));
   delete h;
   if (e != cudaSuccess) { cudaGetLastError(); if (d) cudaFree(d); return frad_fail(ctx, FRAD_E_NOMEM, "crc table upload failed"); }
   ctx->crc_tables = d;

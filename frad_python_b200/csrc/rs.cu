@@ -61,7 +61,7 @@ const rs_table* get_table(frad_ctx* ctx, int csize) {
     }
   }
   void* d = nullptr;
-  if (cudaMalloc(&d, bytes) != cudaSuccess || cudaMemcpy(d, h.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+  if (cudaMalloc(&d, bytes) != cudaSuccess || frad_upload(d, h.data(), bytes) != cudaSuccess) {
     cudaGetLastError();
     frad_fail(ctx, FRAD_E_NOMEM, "rs table upload failed");
     return nullptr;

@@ -36,7 +36,7 @@ static void* upload_cpx(frad_ctx* ctx, const std::vector<long double>& re, const
   void* d = nullptr;
   if (cudaMalloc(&d, 2 * n * sizeof(T)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
   // tables are uploaded synchronously once per (N, precision); not on the timed path
-  if (cudaMemcpy(d, h.data(), 2 * n * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return nullptr; }
+  if (frad_upload(d, h.data(), 2 * n * sizeof(T)) != cudaSuccess) { cudaFree(d); return nullptr; }
   return d;
 }
 
@@ -115,7 +115,7 @@ frad_plan* frad_get_plan(frad_ctx* ctx, int N, int prec) {
     std::vector<double> h((size_t)4 * N);
     for (long long q = 0; q < 4LL * N; q++) { long double c, s; unit_root(q, 2LL * N, &c, &s); h[q] = (double)c; }
     if (cudaMalloc(&p->ct, h.size() * sizeof(double)) != cudaSuccess ||
-        cudaMemcpy(p->ct, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) ok = false;
+        frad_upload(p->ct, h.data(), h.size() * sizeof(double)) != cudaSuccess) ok = false;
   } else {
     ok = (prec == FRAD_PREC_F32) ? build_tables<float>(ctx, p) : build_tables<double>(ctx, p);
   }
@@ -799,8 +799,9 @@ __device__ __noinline__ double dequant_slow(int qv, const double* __restrict__ d
 __global__ void __launch_bounds__(128) tns_synth_kernel(const int32_t* __restrict__ q, const int32_t* __restrict__ lpc, int B, int N, int C,
                                                          double inv_scale, const double* __restrict__ dq64, int dq_len,
                                                          double* __restrict__ spec) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= B * C) return;
+  const int s0 = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = s0 < B * C;                                        // (no early return: the warp works together at the end)
+  const int s = live ? s0 : B * C - 1;
   const int b = s / C, c = s - b * C;
   const int32_t* qs = q + (size_t)b * N * C + c;
   double* out = spec + (size_t)b * N * C + c;
@@ -812,14 +813,8 @@ __global__ void __launch_bounds__(128) tns_synth_kernel(const int32_t* __restric
     any |= (v != 0);
     a[i] = (i == 0) ? 1.0 : (double)v / 15.0;                          // dequantise_lpc, p2tools.py:49-55
   }
-  auto coef = [&](int n) -> double {                                   // sign(q) |q|^(4/3) / 2^(bits-1), profile2.py:80
-    const int qv = __ldg(qs + (size_t)n * C);
-    const uint32_t qa = (qv < 0) ? 0u - (uint32_t)qv : (uint32_t)qv;
-    const double mag = ((qa < (uint32_t)dq_len) ? __ldg(dq64 + qa) : pow((double)qa, 1.0 / 0.75)) * inv_scale;
-    return (qv < 0) ? -mag : mag;
-  };
   bool ok = false;
-  if (any) {
+  if (any && live) {
     double z[FRAD_LPC_LEN - 1];
 #pragma unroll
     for (int i = 0; i < FRAD_LPC_LEN - 1; i++) z[i] = 0.0;
@@ -875,8 +870,20 @@ __global__ void __launch_bounds__(128) tns_synth_kernel(const int32_t* __restric
     }
     ok = !(bad || mx > 1e6);
   }
-  if (!ok) {
-    for (int n = 0; n < N; n++) out[(size_t)n * C] = coef(n);
+  // Sequences without TNS (all-zero LPC) or with a rejected synthesis keep their dequantised coefficients
+  // (sign(q) |q|^(4/3) / 2^(bits-1), profile2.py:80).  The warp takes them one after the other with all 32 lanes along the
+  // bins: as a per-thread loop this path was a serial chain of dependent loads that the whole (diverged) warp waited for --
+  // 43 % of the kernel's stall samples in the capture of the first version.
+  unsigned todo = __ballot_sync(0xffffffffu, live && !ok);
+  const int lane = threadIdx.x & 31;
+  while (todo) {
+    const int l = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const int sl = __shfl_sync(0xffffffffu, s, l);
+    const int bl = sl / C, cl = sl - bl * C;
+    const int32_t* ql = q + (size_t)bl * N * C + cl;
+    double* ol = spec + (size_t)bl * N * C + cl;
+    for (int n = lane; n < N; n += 32) ol[(size_t)n * C] = dequant_slow(__ldg(ql + (size_t)n * C), dq64, dq_len, inv_scale);
   }
 }
 
@@ -1156,7 +1163,7 @@ int frad_ensure_dq64(frad_ctx* ctx) {
   for (int i = 0; i < FRAD_DQ_LEN; i++) h[i] = pow((double)i, 1.0 / 0.75);
   void* d = nullptr;
   if (cudaMalloc(&d, sizeof(double) * FRAD_DQ_LEN) != cudaSuccess ||
-      cudaMemcpy(d, h.data(), sizeof(double) * FRAD_DQ_LEN, cudaMemcpyHostToDevice) != cudaSuccess) {
+      frad_upload(d, h.data(), sizeof(double) * FRAD_DQ_LEN) != cudaSuccess) {
     cudaGetLastError();
     return frad_fail(ctx, FRAD_E_NOMEM, "dequantiser table upload failed");
   }
@@ -1173,7 +1180,7 @@ static int run_tns_synthesis(frad_ctx* ctx, dec_params& P) {
   const int nseq = P.B * P.C;
   // (A variant that stages TNS_BLK-bin blocks through shared memory for fully coalesced traffic was measured in round 2:
   //  1.01 ms against 0.72 ms for the pair of decode kernels -- the recurrence is latency-bound, not sector-bound; not kept.)
-  tns_synth_kernel<<<(nseq + 127) / 128, 128, 0, ctx->stream>>>(P.q, P.lpc, P.B, P.N, P.C, 1.0 / P.scale, (const double*)ctx->dequant_table,
+  tns_synth_kernel<<<(nseq + 31) / 32, 32, 0, ctx->stream>>>(P.q, P.lpc, P.B, P.N, P.C, 1.0 / P.scale, (const double*)ctx->dequant_table,
                                                               FRAD_DQ_LEN, spec);
   FRAD_LAUNCH_CHECK(ctx);
   P.spec = spec;
@@ -1367,7 +1374,7 @@ static const band_table* get_band_table(frad_ctx* ctx, int N, int srate) {
   }
   void* d = nullptr;
   if (cudaMalloc(&d, sizeof(band_table)) != cudaSuccess ||
-      cudaMemcpy(d, &h, sizeof(band_table), cudaMemcpyHostToDevice) != cudaSuccess) {
+      frad_upload(d, &h, sizeof(band_table)) != cudaSuccess) {
     cudaGetLastError();
     frad_fail(ctx, FRAD_E_NOMEM, "band table allocation failed");
     return nullptr;

@@ -33,6 +33,7 @@ class Encoder:
         self.precision = precision
         self.asfh = ASFH()
         self.buffer = b""
+        self._arena = None                 # persistent staging area of the batched route (see _gather)
         self.bit_depth = 0
         self.channels = 0
         self.fsize = 0
@@ -133,8 +134,39 @@ class Encoder:
         self.buffer = self.buffer[k:]
         self._frag_in_buffer = False
 
+    ARENA_MIN = 1 << 20
+
+    def _gather(self, stream: bytes):
+        """Pending bytes + `stream` as one contiguous buffer.  MB-sized feeds are copied into a persistent arena instead of a
+        fresh ``bytes`` object per call: a new 32 MB allocation is mostly page faults (13 ms per call measured, a quarter of
+        configs[1]'s encode time).  The arena is ordinary pageable memory -- page-locking it was tried and dropped: the gain was
+        a few ms per call, and a registration that outlives its memory is a hazard for every later copy of the process."""
+        total = len(self.buffer) + len(stream)
+        if total < self.ARENA_MIN or not self.init:
+            self.buffer += stream
+            return self.buffer
+        arena = self._arena
+        if arena is None or arena.nbytes < total:
+            # headroom for what the next call carries over (overlap samples, an incomplete frame)
+            arena = self._arena = np.empty(max(total + (4 << 20), 2 * (arena.nbytes if arena is not None else 0)), np.uint8)
+        k = len(self.buffer)
+        if k:
+            arena[:k] = np.frombuffer(self.buffer, np.uint8)
+        if len(stream):
+            arena[k:total] = np.frombuffer(stream, np.uint8)
+        self.buffer = b""                                         # owned by the arena until inner() hands the rest back
+        return memoryview(arena)[:total]
+
     def inner(self, stream: bytes, flush: bool) -> EncodeResult:
-        self.buffer += stream
+        buf = self._gather(stream)
+        try:
+            return self._inner(buf, flush)
+        finally:
+            if isinstance(self.buffer, memoryview):               # what the batch left over goes back to a bytes object
+                self.buffer = bytes(self.buffer)
+
+    def _inner(self, buf, flush: bool) -> EncodeResult:
+        self.buffer = buf
         ret, samples = [], 0
         if not self.init:
             return EncodeResult(b"", 0)

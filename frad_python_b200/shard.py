@@ -149,6 +149,7 @@ class ShardedEncoder(Encoder):
         for g in range(shards):
             w = copy.copy(self)                              # shares settings, owns its header object and context
             w.asfh, w.ctx = _clone_asfh(self.asfh), self.ctxs[g]
+            w._arena = None                                  # the staging arena stays with the owner
             workers.append(w)
 
         def work(g):
