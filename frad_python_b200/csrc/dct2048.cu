@@ -250,32 +250,46 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
     __syncthreads();                                        // previous tile stored, ramp tables visible
     if (!EARLY) request_tile(tile);
     if constexpr (PROFILE == 2) {
-      // ---- profile 2: the spectrum arrives dequantised and TNS-synthesised (tns_synth_kernel) as f64 [B][N][C];
+      // ---- profile 2: the spectrum arrives dequantised and TNS-synthesised (tns_synth_kernel) as f64, four sequences per sector;
       //      what is left of profile2.py:85-91 is the ramp multiplication ----
       constexpr int STRIDE_T = LY::WARP_BYTES / (int)sizeof(T);
       T* seq_base = (T*)smem_raw;
       const int Cg = (CT == 4) ? 4 : C, c0 = (CT == 4) ? 4 * grp : 0;
+      auto ramp_mul = [&](double v, int sq, int k) -> T {
+        const int bnd = tail->bidx[k];
+        if constexpr (sizeof(T) == 8) {
+          const double2 rp = tail->rp[sq][bnd];
+          return v * __dadd_rn(__dmul_rn((double)(k - tail->lo[bnd]), rp.y), rp.x);        // j * step + start
+        } else {
+          const float4 bpv = tail->bp[sq][bnd];
+          const float kf = (float)k;
+          return (float)v * fmaf(kf - bpv.z, bpv.y, (bpv.w - kf) * bpv.x);
+        }
+      };
+      if constexpr (CT == 1 || CT == 2 || CT == 4) {
+        // the tile's four sequences are one group of tns_synth_kernel's layout (their first index is a multiple of four):
+        // 64 KiB in one run, a thread takes two sequences of a bin with one 16-byte load
+        const int s4 = (CT == 4) ? b0 * C + 4 * grp : b0 * C;
+        const double2* base = (const double2*)(P.spec + (size_t)(s4 >> 2) * FN * 4);
+#pragma unroll 4
+        for (int idx = tid; idx < FN * 2; idx += FW * 32) {
+          const int k = idx >> 1, h = idx & 1;
+          const double2 v2 = __ldg(base + idx);
+          seq_base[(size_t)(2 * h) * STRIDE_T + k] = ramp_mul(v2.x, 2 * h, k);
+          seq_base[(size_t)(2 * h + 1) * STRIDE_T + k] = ramp_mul(v2.y, 2 * h + 1, k);
+        }
+      } else {
       for (int f = 0; f < nf; f++) {
-        const double* src = P.spec + (size_t)(b0 + f) * FN * C + c0;
+        const int s_first = (b0 + f) * C + c0;                // layout of tns_synth_kernel: spec[((s >> 2) N + k) 4 + (s & 3)]
 #pragma unroll 4
         for (int idx = tid; idx < FN * Cg; idx += FW * 32) {
-          int k, cc;
-          if (CT == 1) { k = idx; cc = 0; } else if (CT == 2) { k = idx >> 1; cc = idx & 1; }
-          else if (CT == 4) { k = idx >> 2; cc = idx & 3; } else { k = idx / C; cc = idx - k * C; }
-          const double v = __ldg(src + (size_t)k * C + cc);
-          const int sq = (CT == 4) ? cc : f * C + cc;
-          const int bnd = tail->bidx[k];
-          T val;
-          if constexpr (sizeof(T) == 8) {
-            const double2 rp = tail->rp[sq][bnd];
-            val = v * __dadd_rn(__dmul_rn((double)(k - tail->lo[bnd]), rp.y), rp.x);      // j * step + start
-          } else {
-            const float4 bpv = tail->bp[sq][bnd];
-            const float kf = (float)k;
-            val = (float)v * fmaf(kf - bpv.z, bpv.y, (bpv.w - kf) * bpv.x);
-          }
-          seq_base[(size_t)sq * STRIDE_T + k] = val;
+          const int k = idx / C, cc = idx - k * C;
+          const int sg = s_first + cc;
+          const double v = __ldg(P.spec + ((size_t)(sg >> 2) * FN + k) * 4 + (sg & 3));
+          const int sq = f * C + cc;
+          seq_base[(size_t)sq * STRIDE_T + k] = ramp_mul(v, sq, k);
         }
+      }
       }
     } else if constexpr (PAIR) {
       // ---- stereo profile-1 staging: thread `tid` converts the bin pairs p = tid + 128 i of all four sequences ----
@@ -452,7 +466,13 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
         const int nnf = min(tm.fpc, P.B - nb0);
         const char* base = (PROFILE == 0) ? (const char*)(P.payload + (size_t)nb0 * P.payload_stride)
                                           : (const char*)(P.q + (size_t)nb0 * words_per_frame);
-        const size_t bytes = (PROFILE == 0) ? (size_t)nnf * P.payload_stride : (size_t)nnf * words_per_frame * 4;
+        size_t bytes = (PROFILE == 0) ? (size_t)nnf * P.payload_stride : (size_t)nnf * words_per_frame * 4;
+        if constexpr (PROFILE == 2 && (CT == 1 || CT == 2 || CT == 4)) {      // the tile's group of tns_synth_kernel's layout: 64 KiB
+          const int ngrp = (CT == 4) ? nt - nb0 * tm.groups : 0;
+          const int ns4 = (CT == 4) ? nb0 * C + 4 * ngrp : nb0 * C;
+          base = (const char*)(P.spec + (size_t)(ns4 >> 2) * FN * 4);
+          bytes = (size_t)FN * 4 * sizeof(double);
+        }
         for (size_t o = (size_t)tid * 128; o < bytes; o += (size_t)FW * 32 * 128)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(base + o));
       }

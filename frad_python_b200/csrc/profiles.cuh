@@ -517,6 +517,7 @@ __device__ void p1_prologue(const dec_params& P, T* X, int N, int b, int c, band
   }
   // profile 2: the dequantiser and the all-pole TNS synthesis (profile2.py:80-85, p2tools.py:97-106) have already run for
   // every sequence of the batch (tns_synth_kernel, one thread per sequence); only the ramp is left
-  const double* src = P.spec + (size_t)b * N * C + c;
-  for (int k = t; k < N; k += blockDim.x) X[k] = (T)(src[(size_t)k * C] * ramp_value(bw, k));
+  const int sq = b * C + c;                                           // layout of tns_synth_kernel: bin k of four sequences per sector
+  const double* src = P.spec + (size_t)(sq >> 2) * N * 4 + (sq & 3);
+  for (int k = t; k < N; k += blockDim.x) X[k] = (T)(src[(size_t)k * 4] * ramp_value(bw, k));
 }

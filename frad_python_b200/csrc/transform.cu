@@ -791,20 +791,75 @@ __device__ __noinline__ double dequant_slow(int qv, const double* __restrict__ d
   return (qv < 0) ? -mag : mag;
 }
 
-// Profile-2 decode, first step (profile2.py:80-85): dequantise the coefficients of every (frame, channel) sequence and run
-// the all-pole TNS synthesis lfilter([1], lpc / 15, x) over them (p2tools.py:97-106) -- a recurrence along the bins, so
-// the parallelism is across sequences: one thread per sequence, filter state in registers, SciPy's transposed direct
-// form II order of operations.  A sequence whose LPC integers are all zero, or whose output is not finite / exceeds 1e6,
-// keeps its unfiltered coefficients.  q, spec: [B][N][C]; lpc: [B][13][C]; dq64: |q|^(4/3) for |q| < 4096 (host libm).
-__global__ void __launch_bounds__(128) tns_synth_kernel(const int32_t* __restrict__ q, const int32_t* __restrict__ lpc, int B, int N, int C,
-                                                         double inv_scale, const double* __restrict__ dq64, int dq_len,
-                                                         double* __restrict__ spec) {
-  const int s0 = blockIdx.x * blockDim.x + threadIdx.x;
+// Profile-2 decode, first steps (profile2.py:80-85): dequantise the coefficients of every (frame, channel) sequence
+// (sign(q) |q|^(4/3) / 2^(bits-1)) and run the all-pole TNS synthesis lfilter([1], lpc / 15, x) over them (p2tools.py:97-106).
+//
+// The synthesis is a recurrence along the bins, so its parallelism is across sequences: one thread per sequence, filter
+// state in registers, SciPy's transposed direct form II order of operations.  Round 2, second version: the two steps are
+// separate kernels and meet in a layout made for the recurrence,
+//     spec[((s >> 2) N + n) 4 + (s & 3)],   s = frame * C + channel,
+// i.e. bin n of four neighbouring sequences is one 32-byte sector -- the four sequences are exactly one tile of the N = 2048
+// inverse-transform kernel, which therefore reads its 64 KiB as one contiguous run.  tns_dequant_kernel is a plain pass
+// (every bin in parallel, table look-ups off anybody's critical path); tns_synth_kernel then loads x[n] and stores y[n] as
+// whole sectors (eight per warp request) -- the first version gathered 4-byte integers at a 16 KiB stride, chained a table
+// look-up behind each of them and scattered 8-byte results over half-used sectors.  (With all 32 sequences of a warp in one
+// 256-byte line the recurrence is faster still, 0.196 ms, but the transform kernel then reads 16 bytes out of every line:
+// 0.27 -> 0.45 ms, measured.)  A sequence whose LPC integers are all zero needs nothing (its coefficients are already in
+// place); one whose output is not finite / exceeds 1e6 is dequantised again.
+// q: [B][N][C]; lpc: [B][13][C]; dq64: |q|^(4/3) for |q| < 4096 (host libm).
+__device__ __forceinline__ size_t spec_index(int s, int n, int N) { return ((size_t)(s >> 2) * N + n) * 4 + (s & 3); }
+
+// One thread per (group of four sequences, bin): 32 bytes out.  Stereo: the group is two frames, an 8-byte load from each.
+// The four table look-ups are issued without a branch between them; magnitudes beyond the table (rare) are redone afterwards.
+__global__ void __launch_bounds__(256) tns_dequant_kernel(const int32_t* __restrict__ q, int B, int N, int C, double inv_scale,
+                                                          const double* __restrict__ dq64, int dq_len, double* __restrict__ spec) {
+  const int nseq = B * C;
+  const long long total = (long long)((nseq + 3) / 4) * N;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const int g = (int)((unsigned long long)e / (unsigned)N), n = (int)(e - (long long)g * N);
+    int qv[4];
+    if (C == 2) {
+      const int b = 2 * g;
+      const int2 q0 = __ldg((const int2*)(q + ((size_t)b * N + n) * 2));
+      const int2 q1 = (b + 1 < B) ? __ldg((const int2*)(q + ((size_t)(b + 1) * N + n) * 2)) : make_int2(0, 0);
+      qv[0] = q0.x; qv[1] = q0.y; qv[2] = q1.x; qv[3] = q1.y;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int sq = 4 * g + j;
+        const int b = sq / C, c = sq - b * C;
+        qv[j] = (sq < nseq) ? __ldg(q + ((size_t)b * N + n) * C + c) : 0;
+      }
+    }
+    double v[4];
+    uint32_t big = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint32_t qa = (qv[j] < 0) ? 0u - (uint32_t)qv[j] : (uint32_t)qv[j];
+      big |= qa;
+      const double mag = __ldg(dq64 + min(qa, (uint32_t)(dq_len - 1))) * inv_scale;
+      v[j] = (qv[j] < 0) ? -mag : mag;
+    }
+    if (big >= (uint32_t)dq_len) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) v[j] = dequant_slow(qv[j], dq64, dq_len, inv_scale);
+    }
+    double2* o = (double2*)(spec + (size_t)e * 4);
+    o[0] = make_double2(v[0], v[1]);
+    o[1] = make_double2(v[2], v[3]);
+  }
+}
+
+__global__ void __launch_bounds__(32) tns_synth_kernel(const int32_t* __restrict__ q, const int32_t* __restrict__ lpc, int B, int N, int C,
+                                                        double inv_scale, const double* __restrict__ dq64, int dq_len,
+                                                        double* __restrict__ spec) {
+  const int lane = threadIdx.x;
+  const int s0 = blockIdx.x * 32 + lane;
   const bool live = s0 < B * C;                                        // (no early return: the warp works together at the end)
   const int s = live ? s0 : B * C - 1;
   const int b = s / C, c = s - b * C;
-  const int32_t* qs = q + (size_t)b * N * C + c;
-  double* out = spec + (size_t)b * N * C + c;
+  double* col = spec + (size_t)(s0 >> 2) * N * 4 + (s0 & 3);           // bin n of this thread's sequence: col[4 n]
   double a[FRAD_LPC_LEN];
   int any = 0;
 #pragma unroll
@@ -813,54 +868,38 @@ __global__ void __launch_bounds__(128) tns_synth_kernel(const int32_t* __restric
     any |= (v != 0);
     a[i] = (i == 0) ? 1.0 : (double)v / 15.0;                          // dequantise_lpc, p2tools.py:49-55
   }
-  bool ok = false;
-  if (any && live) {
+  const bool run = any && live;
+  bool bad = false;
+  double mx = 0.0;
+  if (__any_sync(0xffffffffu, run)) {
+    // Lanes without TNS walk along with a = (1, 0, ..., 0): y = x, stored over itself -- cheaper than diverging the warp.
+    if (!run) {
+#pragma unroll
+      for (int i = 1; i < FRAD_LPC_LEN; i++) a[i] = 0.0;
+    }
     double z[FRAD_LPC_LEN - 1];
 #pragma unroll
     for (int i = 0; i < FRAD_LPC_LEN - 1; i++) z[i] = 0.0;
-    double mx = 0.0;
-    bool bad = false;
-    // The recurrence is serial along n; the loads are not.  Two blocks ahead of the filter: the integers of block k + 2 are
-    // requested and block k + 1 is dequantised (table look-ups) before the filter steps of block k run, so both dependent
-    // memory accesses per bin are off the critical path.
+    // The recurrence is serial along n; the loads are not: the block after the current one is in flight while it runs.
     constexpr int BLK = 16;
-    auto fetch = [&](int n0, int (&qv)[BLK]) {
-#pragma unroll
-      for (int j = 0; j < BLK; j++) qv[j] = (n0 + j < N) ? __ldg(qs + (size_t)(n0 + j) * C) : 0;
-    };
-    auto dequant = [&](int n0, const int (&qv)[BLK], double (&xv)[BLK]) {
-      uint32_t big = 0;
-#pragma unroll
-      for (int j = 0; j < BLK; j++) {                                  // table look-ups without branches in between
-        const uint32_t qa = (qv[j] < 0) ? 0u - (uint32_t)qv[j] : (uint32_t)qv[j];
-        big |= qa;
-        const double mag = __ldg(dq64 + min(qa, (uint32_t)(dq_len - 1))) * inv_scale;
-        xv[j] = (qv[j] < 0) ? -mag : mag;
-      }
-      if (big >= (uint32_t)dq_len) {                                   // rare: magnitudes beyond the table
-#pragma unroll
-        for (int j = 0; j < BLK; j++) xv[j] = dequant_slow(qv[j], dq64, dq_len, inv_scale);   // (static indices: xv stays in registers)
-      }
-    };
-    int qnext[BLK];
     double xcur[BLK], xnext[BLK];
-    fetch(0, qnext);
-    dequant(0, qnext, xcur);
-    fetch(BLK, qnext);
+    auto fetch = [&](int n0, double (&xv)[BLK]) {
+#pragma unroll
+      for (int j = 0; j < BLK; j++) xv[j] = (n0 + j < N) ? col[(size_t)(n0 + j) * 4] : 0.0;
+    };
+    fetch(0, xcur);
     for (int n0 = 0; n0 < N; n0 += BLK) {
-      dequant(n0 + BLK, qnext, xnext);
-      fetch(n0 + 2 * BLK, qnext);
+      fetch(n0 + BLK, xnext);
 #pragma unroll
       for (int j = 0; j < BLK; j++) {
         if (n0 + j < N) {
-          const double xn = xcur[j];
-          const double yn = __dadd_rn(z[0], xn);
+          const double yn = __dadd_rn(z[0], xcur[j]);
           // SciPy also adds b[i] x[n] with b[i] = 0 to every state; x[n] is finite here (|q| < 2^31), so those terms are
           // +-0 and could only flip the sign of a state that is exactly zero -- left out (half of the arithmetic)
 #pragma unroll
           for (int i = 0; i < FRAD_LPC_LEN - 2; i++) z[i] = __dsub_rn(z[i + 1], __dmul_rn(yn, a[i + 1]));
           z[FRAD_LPC_LEN - 2] = -__dmul_rn(yn, a[FRAD_LPC_LEN - 1]);
-          out[(size_t)(n0 + j) * C] = yn;
+          col[(size_t)(n0 + j) * 4] = yn;
           bad |= !isfinite(yn);
           mx = fmax(mx, fabs(yn));
         }
@@ -868,22 +907,17 @@ __global__ void __launch_bounds__(128) tns_synth_kernel(const int32_t* __restric
 #pragma unroll
       for (int j = 0; j < BLK; j++) xcur[j] = xnext[j];
     }
-    ok = !(bad || mx > 1e6);
   }
-  // Sequences without TNS (all-zero LPC) or with a rejected synthesis keep their dequantised coefficients
-  // (sign(q) |q|^(4/3) / 2^(bits-1), profile2.py:80).  The warp takes them one after the other with all 32 lanes along the
-  // bins: as a per-thread loop this path was a serial chain of dependent loads that the whole (diverged) warp waited for --
-  // 43 % of the kernel's stall samples in the capture of the first version.
-  unsigned todo = __ballot_sync(0xffffffffu, live && !ok);
-  const int lane = threadIdx.x & 31;
+  // a rejected synthesis keeps the unfiltered coefficients: the warp dequantises those sequences again, lanes along the bins
+  unsigned todo = __ballot_sync(0xffffffffu, run && (bad || mx > 1e6));
   while (todo) {
     const int l = __ffs(todo) - 1;
     todo &= todo - 1;
     const int sl = __shfl_sync(0xffffffffu, s, l);
     const int bl = sl / C, cl = sl - bl * C;
     const int32_t* ql = q + (size_t)bl * N * C + cl;
-    double* ol = spec + (size_t)bl * N * C + cl;
-    for (int n = lane; n < N; n += 32) ol[(size_t)n * C] = dequant_slow(__ldg(ql + (size_t)n * C), dq64, dq_len, inv_scale);
+    double* ol = spec + (size_t)(sl >> 2) * N * 4 + (sl & 3);
+    for (int n = lane; n < N; n += 32) ol[(size_t)n * 4] = dequant_slow(__ldg(ql + (size_t)n * C), dq64, dq_len, inv_scale);
   }
 }
 
@@ -1175,13 +1209,19 @@ int frad_ensure_dq64(frad_ctx* ctx) {
 static int run_tns_synthesis(frad_ctx* ctx, dec_params& P) {
   int rc = frad_ensure_dq64(ctx);
   if (rc) return rc;
-  double* spec = (double*)frad_scratch(ctx, 4, sizeof(double) * (size_t)P.B * P.N * P.C);
-  if (!spec) return FRAD_E_NOMEM;
   const int nseq = P.B * P.C;
-  // (A variant that stages TNS_BLK-bin blocks through shared memory for fully coalesced traffic was measured in round 2:
-  //  1.01 ms against 0.72 ms for the pair of decode kernels -- the recurrence is latency-bound, not sector-bound; not kept.)
-  tns_synth_kernel<<<(nseq + 31) / 32, 32, 0, ctx->stream>>>(P.q, P.lpc, P.B, P.N, P.C, 1.0 / P.scale, (const double*)ctx->dequant_table,
-                                                              FRAD_DQ_LEN, spec);
+  const int nwarps = (nseq + 31) / 32;
+  double* spec = (double*)frad_scratch(ctx, 4, sizeof(double) * (size_t)nwarps * 32 * P.N);        // layout: spec_index()
+  if (!spec) return FRAD_E_NOMEM;
+  // (A variant that stages TNS_BLK-bin blocks through shared memory inside the recurrence was measured in round 2:
+  //  1.01 ms against 0.72 ms for the pair of decode kernels; not kept.)
+  const long long want = ((long long)nwarps * 8 * P.N + 255) / 256;
+  const long long cap = (long long)ctx->sm_count * 16;
+  tns_dequant_kernel<<<(int)(want < cap ? want : cap), 256, 0, ctx->stream>>>(P.q, P.B, P.N, P.C, 1.0 / P.scale,
+                                                                             (const double*)ctx->dequant_table, FRAD_DQ_LEN, spec);
+  FRAD_LAUNCH_CHECK(ctx);
+  tns_synth_kernel<<<nwarps, 32, 0, ctx->stream>>>(P.q, P.lpc, P.B, P.N, P.C, 1.0 / P.scale, (const double*)ctx->dequant_table,
+                                                   FRAD_DQ_LEN, spec);
   FRAD_LAUNCH_CHECK(ctx);
   P.spec = spec;
   return FRAD_OK;
