@@ -264,32 +264,35 @@ __global__ void __launch_bounds__(128) compact_kernel(const uint8_t* __restrict_
 // ---- decode ---------------------------------------------------------------------------------------------
 struct bit_window {
   const uint32_t* w; uint32_t wi, nwords, last_mask;
-  uint32_t nxt;                                                // word wi, already fetched: the load is one refill ahead of its use
+  uint32_t nxt;                                                // word wi as loaded (0 beyond the end): the load is issued one refill
+                                                               // ahead of its use, byte order and end mask are applied at the use
   uint64_t win; int navail;
-  __device__ __forceinline__ uint32_t fetch(uint32_t i) const {
-    uint32_t x = 0;
-    if (i < nwords) {
-      x = __byte_perm(__ldg(w + i), 0, 0x0123);
-      if (i == nwords - 1) x &= last_mask;
-    }
+  __device__ __forceinline__ uint32_t load(uint32_t i) const { return (i < nwords) ? __ldg(w + i) : 0u; }
+  __device__ __forceinline__ uint32_t cook(uint32_t raw, uint32_t i) const {
+    uint32_t x = __byte_perm(raw, 0, 0x0123);
+    if (i == nwords - 1) x &= last_mask;
     return x;
   }
   __device__ __forceinline__ void start(uint32_t abs_bit) {    // window at absolute bit abs_bit of the word array
     wi = abs_bit >> 5;
     const int off = (int)(abs_bit & 31);
-    win = ((uint64_t)(fetch(wi) << off)) << 32;
+    win = ((uint64_t)(cook(load(wi), wi) << off)) << 32;
     navail = 32 - off;
     wi++;
-    nxt = fetch(wi);
-  }
-  __device__ __forceinline__ uint32_t word() {
-    const uint32_t x = nxt;
-    wi++;
-    nxt = fetch(wi);
-    return x;
+    nxt = load(wi);
   }
   __device__ __forceinline__ void refill() {                   // navail <= 32 -> navail in (32, 64]
-    if (navail <= 32) { win |= (uint64_t)word() << (32 - navail); navail += 32; }
+    if (navail <= 32) {
+      win |= (uint64_t)cook(nxt, wi) << (32 - navail); navail += 32;
+      wi++; nxt = load(wi);
+    }
+  }
+  // the same where the word taken lies wholly inside the stream (callers: at least 64 bits of stream after the window start)
+  __device__ __forceinline__ void refill_inside() {
+    if (navail <= 32) {
+      win |= (uint64_t)__byte_perm(nxt, 0, 0x0123) << (32 - navail); navail += 32;
+      wi++; nxt = load(wi);
+    }
   }
   __device__ __forceinline__ void drop(int n) { win = (n >= 64) ? 0 : (win << n); navail -= n; }
 };
@@ -348,9 +351,10 @@ __device__ __forceinline__ lane_chain run_chain(const stream_view& sv, uint32_t 
     const uint32_t lim = (sv.k <= 29 && sv.nbits > 64) ? min(seg_hi, sv.nbits - 64) : 0;
     const int l1 = sv.k + 1, l3 = sv.k + 3;
     while (pos < seg_hi) {
-      bw.refill();                                             // navail in (32, 64]
+      const bool inside = pos < lim;
+      if (inside) bw.refill_inside(); else bw.refill();        // navail in (32, 64]
       const uint32_t top = (uint32_t)(bw.win >> 62);
-      if (top != 0 && pos < lim) {
+      if (top != 0 && inside) {
         const int l = (top & 2u) ? l1 : l3;
         if (WRITE) {
           const int32_t nv = (int32_t)((uint32_t)(bw.win >> (64 - l)) - (uint32_t)bias);      // < 2^(k+2) <= 2^31
