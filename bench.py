@@ -550,6 +550,30 @@ def main():
                                                      "with tools/pcie_probe.py on a box of this pool)"}
     except Exception:
         pass
+    # ---- the byte compressor of the frame payloads (profile1.py:50,59): host work by design (north_star), timed apart ----
+    if not args.no_cpu and world == 1:
+        try:
+            nb_off = np.array(h_off, np.uint64)
+            raw_np = np.array(h_raw[:int(nb_off[B])])
+            _abi.deflate_frames(raw_np, nb_off)                                    # warm-up: thread pool, allocations
+            t0 = time.perf_counter()
+            z, zoff = _abi.deflate_frames(raw_np, nb_off)
+            t_def = time.perf_counter() - t0
+            zlen = (zoff[1:] - zoff[:-1]).astype(np.uint32)
+            slot = int(np.max(nb_off[1:] - nb_off[:-1]))
+            _abi.inflate_frames(z, zoff[:-1], zlen, slot)
+            t0 = time.perf_counter()
+            back, boff = _abi.inflate_frames(z, zoff[:-1], zlen, slot)
+            t_inf = time.perf_counter() - t0
+            line["host_deflate"] = {
+                "what": "raw deflate / inflate (libz, zlib.compress(x, wbits=-15) parameters: byte-identical to the reference) of "
+                        "the step's 15 000 frame payloads on the host thread pool; NOT part of value or e2e",
+                "threads": os.cpu_count(), "deflate_ms": 1e3 * t_def, "inflate_ms": 1e3 * t_inf,
+                "deflate_MSamples_per_s": B * HOP * CH / t_def / 1e6, "inflate_MSamples_per_s": B * HOP * CH / t_inf / 1e6,
+                "payload_bytes": int(nb_off[B]), "deflated_bytes": int(zoff[B]),
+                "roundtrip_identical": bool(int(boff[B]) == int(nb_off[B]) and np.array_equal(back[:int(boff[B])], raw_np))}
+        except Exception as e:                                                     # never lose the contract line over this leg
+            line["host_deflate"] = {"error": repr(e)}
     if not args.no_cpu and world == 1:
         nsample = 1000
         frames = [pcm_host[i * HOP:i * HOP + N] for i in range(nsample)]

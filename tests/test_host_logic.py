@@ -286,8 +286,8 @@ def test_native_batch_framing_matches_zlib_and_the_header_mirror(g_streams):
     assert n == 2 and nxt == 2 * (32 + 16384) and int(prm[0]) == 0
 
 
-@pytest.mark.parametrize("chunk", [32768, 1 << 22, 5000])
-def test_codec_objects_reproduce_the_reference_streams_with_oracle_arithmetic(g_streams, chunk):
+@pytest.mark.parametrize("chunk", [32768, 1 << 22, 5000, -32768])
+def test_codec_objects_reproduce_the_reference_streams_with_oracle_arithmetic(g_streams, chunk, monkeypatch):
     """Host logic of the batched Encoder / Decoder / Repairer (frame cutting, overlap carry kept in the byte buffer, native
     header writer and header walk, flush markers) with the oracle standing in for the device: the byte streams and the PCM
     of the unmodified reference (tests/golden/streams.npz) come out bit for bit, for any chunking of the input."""
@@ -295,6 +295,9 @@ def test_codec_objects_reproduce_the_reference_streams_with_oracle_arithmetic(g_
     from stubctx import OracleCtx
     loss0 = 1.25 ** 0 / 19 + 0.5
     pcm = g_streams["pcm"]
+    if chunk < 0:                      # the Encoder's persistent staging arena (MB-sized feeds) on these small streams
+        chunk = -chunk
+        monkeypatch.setattr(F.Encoder, "ARENA_MIN", 4096)
 
     def encode(profile, bits, ecc=False, le=False, ov=16, src=pcm, fmt="f32le", fsize=2048):
         enc = F.Encoder(profile, 48000, 2, bits, fsize, fmt, ctx=OracleCtx())
