@@ -25,43 +25,59 @@ namespace {
 #ifndef GE_MINB
 #define GE_MINB 3
 #endif
-constexpr int GE_THREADS = 256;
 constexpr int GE_VPT = 16;                                  // values per thread and chunk
-constexpr int GE_CHUNK = GE_THREADS * GE_VPT;               // 4096 values
-constexpr int GE_WORDS = (GE_CHUNK * 35 + 31) / 32 + 3;     // bit buffer of one chunk (+ carried partial word)
+constexpr int GE_WARPS = 8;                                 // frames per CTA (one warp each)
 
-struct ge_smem {
-  uint32_t bits[GE_WORDS];
-  uint32_t warp_tot[GE_THREADS / 32];
-  uint32_t red[GE_THREADS / 32];
+// The coder is written once for a group of NT cooperating threads: NT = 32, a warp per frame (round 2: no block barrier
+// anywhere, eight independent frames per CTA -- the CTA-per-frame form spent 32 % of its stall samples at barriers between its
+// max / scan / emit / flush phases with three CTAs per SM to hide them), or NT = 256, the CTA-per-frame form.
+template <int NT> struct ge_smem_t {
+  static constexpr int CHUNK = NT * GE_VPT;                   // values per chunk
+  static constexpr int WORDS = (CHUNK * 35 + 31) / 32 + 3;    // bit buffer of one chunk (+ carried partial word)
+  uint32_t bits[WORDS];
+  uint32_t warp_tot[NT / 32];
+  uint32_t red[NT / 32];
 };
 
-__device__ __forceinline__ uint32_t block_max(uint32_t v, ge_smem* sm) {
+template <int NT> __device__ __forceinline__ int ge_tid() { return (NT == 32) ? (int)(threadIdx.x & 31) : (int)threadIdx.x; }
+template <int NT> __device__ __forceinline__ void ge_sync() { if (NT == 32) __syncwarp(); else __syncthreads(); }
+
+template <int NT> __device__ __forceinline__ uint32_t group_max(uint32_t v, ge_smem_t<NT>* sm) {
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, s));
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) sm->red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  uint32_t r = 0;
+  if constexpr (NT == 32) return v;
+  else {
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm->red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    uint32_t r = 0;
 #pragma unroll
-  for (int i = 0; i < GE_THREADS / 32; i++) r = max(r, sm->red[i]);
-  return r;
+    for (int i = 0; i < NT / 32; i++) r = max(r, sm->red[i]);
+    return r;
+  }
 }
 
-// exclusive prefix of `v` over the CTA; *total receives the CTA sum
-__device__ __forceinline__ uint32_t block_exscan(uint32_t v, ge_smem* sm, uint32_t* total) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+// exclusive prefix of `v` over the group; *total receives the group sum.  Its barriers also order what precedes it.
+template <int NT> __device__ __forceinline__ uint32_t group_exscan(uint32_t v, ge_smem_t<NT>* sm, uint32_t* total) {
+  const int lane = threadIdx.x & 31;
   uint32_t inc = v;
 #pragma unroll
   for (int s = 1; s < 32; s <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, s); if (lane >= s) inc += t; }
-  __syncthreads();
-  if (lane == 31) sm->warp_tot[w] = inc;
-  __syncthreads();
-  uint32_t base = 0, tot = 0;
+  if constexpr (NT == 32) {
+    *total = __shfl_sync(0xffffffffu, inc, 31);
+    __syncwarp();
+    return inc - v;
+  } else {
+    const int w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 31) sm->warp_tot[w] = inc;
+    __syncthreads();
+    uint32_t base = 0, tot = 0;
 #pragma unroll
-  for (int i = 0; i < GE_THREADS / 32; i++) { const uint32_t t = sm->warp_tot[i]; if (i < w) base += t; tot += t; }
-  *total = tot;
-  return base + inc - v;
+    for (int i = 0; i < NT / 32; i++) { const uint32_t t = sm->warp_tot[i]; if (i < w) base += t; tot += t; }
+    *total = tot;
+    return base + inc - v;
+  }
 }
 
 // this thread's 16 consecutive values [i0, i0 + 16) of the stream (0 beyond n): four 16-byte loads where the row allows them
@@ -78,38 +94,51 @@ __device__ __forceinline__ void load_vals(const int32_t* __restrict__ v, int n, 
 
 // Bytes [skip, nbytes) of the big-endian bit buffer to o[skip .. nbytes); o is 4-byte aligned: whole words are byte-swapped and
 // stored as words, the (at most 3 + 3) bytes in front of and behind them one by one.
+template <int NT>
 __device__ __forceinline__ void flush_bits(const uint32_t* __restrict__ bits, uint8_t* __restrict__ o, uint32_t skip, uint32_t nbytes) {
   const uint32_t w0 = (skip + 3) >> 2, w1 = nbytes >> 2;
+  const uint32_t tid = (uint32_t)ge_tid<NT>();
   uint32_t* ow = (uint32_t*)o;
-  for (uint32_t w = w0 + threadIdx.x; w < w1; w += GE_THREADS) ow[w] = __byte_perm(bits[w], 0, 0x0123);
-  if (threadIdx.x < 8) {
-    const uint32_t j = threadIdx.x & 3;
+  for (uint32_t w = w0 + tid; w < w1; w += NT) ow[w] = __byte_perm(bits[w], 0, 0x0123);
+  if (tid < 8) {
+    const uint32_t j = tid & 3;
     uint32_t b; bool ok;
-    if (threadIdx.x < 4) { b = j; ok = (b >= skip) && (b < min(4 * w0, nbytes)); }                  // in front of the first whole word
+    if (tid < 4) { b = j; ok = (b >= skip) && (b < min(4 * w0, nbytes)); }                          // in front of the first whole word
     else { b = 4 * w1 + j; ok = (w1 >= w0) && (b >= skip) && (b < nbytes); }                         // behind the last one
     if (ok) o[b] = (uint8_t)(bits[b >> 2] >> (24 - 8 * (b & 3)));
   }
 }
 
-// Encodes the stream v[0..n) to dst (k byte + bits); returns the byte length.  All threads of the CTA take part.
-// Round 2: the values are loaded once and stay in registers between the maximum and the code pass (streams of up to one chunk,
-// i.e. every stream of the N <= 2048 stereo frames); code lengths are k + 1 or k + 3, so a thread's bit count is a population
-// count; only the words a chunk can reach are cleared; the bit buffer is laid out relative to the 4-byte aligned address below
-// dst + 1, so that it leaves as byte-swapped words instead of single bytes.
-__device__ __noinline__ uint32_t encode_stream(const int32_t* __restrict__ v, int n, uint8_t* __restrict__ dst, ge_smem* sm) {
-  const int tid = threadIdx.x;
+// Encodes the stream v[0..n) to dst (k byte + bits); returns the byte length.  All NT threads of the group take part.
+// The values of a stream of up to one chunk are loaded once and stay in registers between the maximum and the code pass;
+// code lengths are k + 1 or k + 3, so a thread's bit count is a population count; only the words a chunk can reach are
+// cleared; the bit buffer is laid out relative to the 4-byte aligned address below dst + 1, so that it leaves as
+// byte-swapped words instead of single bytes.
+template <int NT>
+__device__ __noinline__ uint32_t encode_stream(const int32_t* __restrict__ v, int n, uint8_t* __restrict__ dst, ge_smem_t<NT>* sm) {
+  constexpr int CHUNK = ge_smem_t<NT>::CHUNK;
+  const int tid = ge_tid<NT>();
   if (n <= 0) { if (tid == 0) dst[0] = 0; return 1; }
-  const bool single = (n <= GE_CHUNK);
+  const bool single = (n <= CHUNK);
   int32_t val[GE_VPT];
   uint32_t mx = 0;
   if (single) {
     load_vals(v, n, tid * GE_VPT, val);
 #pragma unroll
     for (int j = 0; j < GE_VPT; j++) mx = max(mx, (uint32_t)((val[j] < 0) ? -(int64_t)val[j] : (int64_t)val[j]));
+  } else if ((((uintptr_t)v) & 15) == 0) {
+    const int4* v4 = (const int4*)v;
+    for (int i = tid; i < (n >> 2); i += NT) {
+      const int4 x = __ldg(v4 + i);
+      const uint32_t a0 = (uint32_t)((x.x < 0) ? -(int64_t)x.x : (int64_t)x.x), a1 = (uint32_t)((x.y < 0) ? -(int64_t)x.y : (int64_t)x.y);
+      const uint32_t a2 = (uint32_t)((x.z < 0) ? -(int64_t)x.z : (int64_t)x.z), a3 = (uint32_t)((x.w < 0) ? -(int64_t)x.w : (int64_t)x.w);
+      mx = max(max(mx, max(a0, a1)), max(a2, a3));
+    }
+    for (int i = (n & ~3) + tid; i < n; i += NT) { const int32_t x = v[i]; mx = max(mx, (uint32_t)((x < 0) ? -(int64_t)x : (int64_t)x)); }
   } else {
-    for (int i = tid; i < n; i += GE_THREADS) { const int32_t x = v[i]; mx = max(mx, (uint32_t)((x < 0) ? -(int64_t)x : (int64_t)x)); }
+    for (int i = tid; i < n; i += NT) { const int32_t x = v[i]; mx = max(mx, (uint32_t)((x < 0) ? -(int64_t)x : (int64_t)x)); }
   }
-  mx = block_max(mx, sm);
+  mx = group_max<NT>(mx, sm);
   const int k = (mx <= 1) ? 0 : 32 - __clz((int)(mx - 1));
   if (tid == 0) dst[0] = (uint8_t)k;
   uint8_t* out = dst + 1;
@@ -118,10 +147,10 @@ __device__ __noinline__ uint32_t encode_stream(const int32_t* __restrict__ v, in
   uint64_t flushed = 0;                                        // buffer bytes already written (a multiple of 4)
   uint32_t carry = 8 * mis;                                    // bits of sm->bits[0] in front of this chunk's codes
   uint32_t skip = mis;                                         // bytes at the front of the buffer that are not ours (first chunk)
-  for (int c0 = 0; c0 < n; c0 += GE_CHUNK) {
-    const int nv = min(GE_CHUNK, n - c0);
+  for (int c0 = 0; c0 < n; c0 += CHUNK) {
+    const int nv = min(CHUNK, n - c0);
     const uint32_t reach = (carry + (uint32_t)nv * (uint32_t)(k + 3) + 31) / 32 + 1;
-    for (uint32_t i = tid; i < reach; i += GE_THREADS) if (i > 0 || c0 == 0) sm->bits[i] = 0;
+    for (uint32_t i = tid; i < reach; i += NT) if (i > 0 || c0 == 0) sm->bits[i] = 0;
     // this thread's values: [c0 + 16 tid, +16)
     const int i0 = c0 + tid * GE_VPT;
     if (!single) load_vals(v, n, i0, val);
@@ -135,8 +164,8 @@ __device__ __noinline__ uint32_t encode_stream(const int32_t* __restrict__ v, in
     }
     const uint32_t mine = (uint32_t)cnt * (uint32_t)(k + 1) + 2u * (uint32_t)__popc(longmask);
     uint32_t chunk_bits;
-    const uint32_t start = carry + block_exscan(mine, sm, &chunk_bits);     // bit offset inside sm->bits
-    // (block_exscan's barriers also order the zeroing above before the writes below)
+    const uint32_t start = carry + group_exscan<NT>(mine, sm, &chunk_bits);   // bit offset inside sm->bits
+    // (group_exscan's barriers also order the zeroing above before the writes below)
     if (mine) {
       uint32_t wi = start >> 5;
       int nacc = (int)(start & 31);                           // bits of word wi that belong to the threads before
@@ -160,46 +189,51 @@ __device__ __noinline__ uint32_t encode_stream(const int32_t* __restrict__ v, in
       }
       if (nacc > 0) atomicOr(&sm->bits[wi], (uint32_t)(acc << (32 - nacc)));
     }
-    __syncthreads();
+    ge_sync<NT>();
     // flush the complete words and keep the partial one for the next chunk
     const uint32_t filled = carry + chunk_bits;
-    const bool last = (c0 + GE_CHUNK >= n);
+    const bool last = (c0 + CHUNK >= n);
     const uint32_t nbytes = last ? (filled + 7) / 8 : (filled / 32) * 4;
-    flush_bits(sm->bits, obase + flushed, skip, nbytes);
+    flush_bits<NT>(sm->bits, obase + flushed, skip, nbytes);
     if (last) return 1 + (uint32_t)(flushed + nbytes - mis);
     const uint32_t keep = sm->bits[filled / 32];
-    __syncthreads();
+    ge_sync<NT>();
     if (tid == 0) sm->bits[0] = keep;
     flushed += (filled / 32) * 4;
     carry = filled & 31;
     skip = 0;
-    __syncthreads();
+    ge_sync<NT>();
   }
   return 0;   // not reached
 }
 
-__global__ void __launch_bounds__(GE_THREADS, GE_MINB) p1_pack_kernel(const int32_t* __restrict__ q, const int32_t* __restrict__ tq,
-                                                             const int32_t* __restrict__ lpc, int B, int nq, int ntq, int nlpc,
-                                                             uint8_t* __restrict__ raw, size_t stride, uint32_t* __restrict__ raw_len) {
-  __shared__ ge_smem sm;
-  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+// One group of NT threads per frame: NT = 32, eight frames per CTA (the bulk kernel); NT = 256, one frame per CTA.
+template <int NT>
+__global__ void __launch_bounds__(256, GE_MINB) p1_pack_kernel(const int32_t* __restrict__ q, const int32_t* __restrict__ tq,
+                                                               const int32_t* __restrict__ lpc, int B, int nq, int ntq, int nlpc,
+                                                               uint8_t* __restrict__ raw, size_t stride, uint32_t* __restrict__ raw_len) {
+  constexpr int GROUPS = 256 / NT;
+  __shared__ ge_smem_t<NT> sm_all[GROUPS];
+  ge_smem_t<NT>* sm = &sm_all[(NT == 32) ? (threadIdx.x >> 5) : 0];
+  const int tid = ge_tid<NT>();
+  for (int b = blockIdx.x * GROUPS + ((NT == 32) ? (int)(threadIdx.x >> 5) : 0); b < B; b += gridDim.x * GROUPS) {
     uint8_t* out = raw + (size_t)b * stride;
     uint32_t pos = 0;
     if (lpc) {                                                 // profile2.py:51  >H len || gol(lpc)
-      const uint32_t L = encode_stream(lpc + (size_t)b * nlpc, nlpc, out + 2, &sm);
-      if (threadIdx.x == 0) { out[0] = (uint8_t)(L >> 8); out[1] = (uint8_t)L; }
+      const uint32_t L = encode_stream<NT>(lpc + (size_t)b * nlpc, nlpc, out + 2, sm);
+      if (tid == 0) { out[0] = (uint8_t)(L >> 8); out[1] = (uint8_t)L; }
       pos = 2 + L;
-      __syncthreads();
+      ge_sync<NT>();
     }
     {                                                          // profile1.py:45  >I len || gol(thresholds)
-      const uint32_t L = encode_stream(tq + (size_t)b * ntq, ntq, out + pos + 4, &sm);
-      if (threadIdx.x == 0) { out[pos] = (uint8_t)(L >> 24); out[pos + 1] = (uint8_t)(L >> 16); out[pos + 2] = (uint8_t)(L >> 8); out[pos + 3] = (uint8_t)L; }
+      const uint32_t L = encode_stream<NT>(tq + (size_t)b * ntq, ntq, out + pos + 4, sm);
+      if (tid == 0) { out[pos] = (uint8_t)(L >> 24); out[pos + 1] = (uint8_t)(L >> 16); out[pos + 2] = (uint8_t)(L >> 8); out[pos + 3] = (uint8_t)L; }
       pos += 4 + L;
-      __syncthreads();
+      ge_sync<NT>();
     }
-    pos += encode_stream(q + (size_t)b * nq, nq, out + pos, &sm);
-    if (threadIdx.x == 0) raw_len[b] = pos;
-    __syncthreads();
+    pos += encode_stream<NT>(q + (size_t)b * nq, nq, out + pos, sm);
+    if (tid == 0) raw_len[b] = pos;
+    ge_sync<NT>();
   }
 }
 
@@ -594,8 +628,16 @@ extern "C" int frad_p1_pack_dev(frad_ctx* ctx, const int32_t* q, const int32_t* 
     return frad_fail(ctx, FRAD_E_ARG, "frad_p1_pack_dev: bad argument (raw_stride must be >= frad_p1_raw_bound)");
   if (B == 0) return FRAD_OK;
   FRAD_CUDA(ctx, cudaSetDevice(ctx->device));
-  const int grid = B < ctx->sm_count * 8 ? B : ctx->sm_count * 8;
-  p1_pack_kernel<<<grid, GE_THREADS, 0, ctx->stream>>>(q, tq, lpc, B, N * C, FRAD_NBANDS * C, FRAD_LPC_LEN * C, raw, raw_stride, raw_len);
+  // a warp per frame (eight frames per CTA); FRAD_PACK_CTA=1 forces the CTA-per-frame form
+  static const char* force = getenv("FRAD_PACK_CTA");
+  if (force && force[0] == '1') {
+    const int grid = B < ctx->sm_count * 8 ? B : ctx->sm_count * 8;
+    p1_pack_kernel<256><<<grid, 256, 0, ctx->stream>>>(q, tq, lpc, B, N * C, FRAD_NBANDS * C, FRAD_LPC_LEN * C, raw, raw_stride, raw_len);
+  } else {
+    const int want = (B + GE_WARPS - 1) / GE_WARPS;
+    const int grid = want < ctx->sm_count * 8 ? want : ctx->sm_count * 8;
+    p1_pack_kernel<32><<<grid, 256, 0, ctx->stream>>>(q, tq, lpc, B, N * C, FRAD_NBANDS * C, FRAD_LPC_LEN * C, raw, raw_stride, raw_len);
+  }
   FRAD_LAUNCH_CHECK(ctx);
   return FRAD_OK;
 }
