@@ -11,6 +11,7 @@
 #include "../../include/fradb200.h"
 
 #define FRAD_MAX_RADIX_PASSES 20
+#define FRAD_MAX_FRAME 28672          // largest compact frame length (fourier/profiles.py:14-23)
 #define FRAD_NEVENTS 64
 
 struct frad_plan;  // transform plan, see plan.cuh

@@ -17,6 +17,8 @@ struct band_table {
   // decoded thresholds (e/2)^(sign(t) |t|^0.75) for the threshold integers |t| <= FRAD_THR_TAB (profile1.py:66), computed
   // on the host with libm's pow exactly in the reference's order; larger |t| are evaluated on the device
   double thr_pow[2 * 255 + 1];
+  // ramp band of every bin (what ramp_value's search returns; 255 from the start of the last band on), host-built
+  uint8_t bidx[FRAD_MAX_FRAME];
 };
 #define FRAD_THR_TAB 255
 __device__ __forceinline__ double decode_threshold(const band_table* bt, int t) {
@@ -55,7 +57,8 @@ struct dec_params {
   double scale; const band_table* bt; const int32_t* q; const int32_t* tq; const int32_t* lpc;
   void* pcm; int pcm_dtype;
   void* gscratch; double* tns_scratch;
-  const double* spec;          // profile 2: dequantised spectrum after TNS synthesis, [B][N][C] (tns_synth_kernel)
+  const double* spec;          // profile 2: dequantised spectrum after TNS synthesis (tns_synth_kernel's layout)
+  const double* dq64; int dq_len;   // |q|^(4/3) for |q| < dq_len (host libm), generic-size decode kernels
 };
 
 // ---- block reductions (all threads get the result) ---------------------------------------------
@@ -167,6 +170,21 @@ __device__ __forceinline__ void ramp_setup(band_work* bw, const band_table* bt, 
   if (t < FRAD_NBANDS - 1) {
     const int n = bw->lo[t + 1] - bw->lo[t];
     bw->step[t] = (n > 0) ? (bw->thr[t + 1] - bw->thr[t]) / (double)n : 0.0;
+  }
+}
+
+// f(k, divisor) for every bin k of the sequence (a flat, unrollable loop over the CTA's threads): what ramp_value(bw, k)
+// returns, with the band of the bin read from the host-built table instead of a binary search per bin (12-15 % of the generic
+// kernels' instructions in the round-2 capture).  (Striding through band after band was measured first: 27 short loops per
+// thread whose loads do not overlap -- slower than the search.)
+template <typename F>
+__device__ __forceinline__ void for_each_bin_ramp(const band_work* bw, const band_table* bt, int N, F f) {
+  const int t = threadIdx.x, nt = blockDim.x;
+#pragma unroll 4
+  for (int k = t; k < N; k += nt) {
+    const int bnd = __ldg(&bt->bidx[k]);
+    const double div = (bnd == 255) ? 0.0 : __dadd_rn(__dmul_rn((double)(k - bw->lo[bnd]), bw->step[bnd]), bw->thr[bnd]);
+    f(k, div);
   }
 }
 
@@ -467,28 +485,22 @@ __device__ void p1_epilogue(const enc_params& P, const T* X, int N, int b, int c
   __syncthreads();
   int32_t* qrow = P.q + (size_t)b * N * C;
   if (P.profile == 1) {
-    for (int k = t; k < N; k += blockDim.x) {
-      const double div = ramp_value(bw, k);
-      double y = (div == 0.0) ? 0.0 : ((double)X[k] / div) * P.scale;
-      const double m = pow075(fabs(y));
-      qrow[(size_t)k * C + c] = sat_i32(rint(copysign(m, y)));
-    }
+    for_each_bin_ramp(bw, bt, N, [&](int k, double div) {
+      const double y = (div == 0.0) ? 0.0 : ((double)X[k] / div) * P.scale;
+      qrow[(size_t)k * C + c] = quant075(y);               // f32 first, the f64 formula next to a rounding tie
+    });
     return;
   }
   // profile 2: TNS over the masked spectrum (profile2.py:32)
   double* masked = P.tns_scratch + (size_t)cta * 2 * N;
   double* work = masked + N;
-  for (int k = t; k < N; k += blockDim.x) {
-    const double div = ramp_value(bw, k);
-    masked[k] = (div == 0.0) ? 0.0 : (double)X[k] / div;
-  }
+  for_each_bin_ramp(bw, bt, N, [&](int k, double div) { masked[k] = (div == 0.0) ? 0.0 : (double)X[k] / div; });
   __syncthreads();
   tns_analysis_block(masked, work, N, bw);
   const double* src = bw->flag ? work : masked;
   if (t < FRAD_LPC_LEN) P.lpc[((size_t)b * FRAD_LPC_LEN + t) * C + c] = bw->aq[t];
   for (int k = t; k < N; k += blockDim.x) {
-    const double y = src[k] * P.scale;
-    qrow[(size_t)k * C + c] = sat_i32(rint(copysign(pow075(fabs(y)), y)));
+    qrow[(size_t)k * C + c] = quant075(src[k] * P.scale);
   }
 }
 
@@ -508,16 +520,20 @@ __device__ void p1_prologue(const dec_params& P, T* X, int N, int b, int c, band
   __syncthreads();
   const int32_t* qrow = P.q + (size_t)b * N * C;
   if (P.profile == 1) {
-    for (int k = t; k < N; k += blockDim.x) {
-      const double qv = (double)qrow[(size_t)k * C + c];
-      const double coef = copysign(pow(fabs(qv), 1.0 / 0.75), qv) / P.scale;    // profile1.py:65
-      X[k] = (T)(coef * ramp_value(bw, k));
-    }
+    // profile1.py:65: sign(q) |q|^(4/3) / 2^(bits-1); the magnitudes come from the host-computed table (libm's pow, like the
+    // reference) -- the in-line pow() was 40 % of this kernel's instructions
+    for_each_bin_ramp(bw, bt, N, [&](int k, double div) {
+      const int qi = qrow[(size_t)k * C + c];
+      const uint32_t qa = (qi < 0) ? 0u - (uint32_t)qi : (uint32_t)qi;
+      const double mag = (P.dq64 && qa < (uint32_t)P.dq_len) ? __ldg(P.dq64 + qa) : pow((double)qa, 1.0 / 0.75);
+      const double coef = ((qi < 0) ? -mag : mag) / P.scale;
+      X[k] = (T)(coef * div);
+    });
     return;
   }
   // profile 2: the dequantiser and the all-pole TNS synthesis (profile2.py:80-85, p2tools.py:97-106) have already run for
   // every sequence of the batch (tns_synth_kernel, one thread per sequence); only the ramp is left
   const int sq = b * C + c;                                           // layout of tns_synth_kernel: bin k of four sequences per sector
   const double* src = P.spec + (size_t)(sq >> 2) * N * 4 + (sq & 3);
-  for (int k = t; k < N; k += blockDim.x) X[k] = (T)(src[(size_t)k * 4] * ramp_value(bw, k));
+  for_each_bin_ramp(bw, bt, N, [&](int k, double div) { X[k] = (T)(src[(size_t)k * 4] * div); });
 }

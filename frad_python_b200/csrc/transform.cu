@@ -138,8 +138,9 @@ __device__ __forceinline__ void fft_pass(const typename vec2<T>::type* __restric
   typedef typename vec2<T>::type V;
   const int L = M / R;
   const int tstep = M / (Ns * R);
+  const bool ns_pow2 = (Ns & (Ns - 1)) == 0;           // always, until an odd radix has run (odd radices come last)
   for (int j = threadIdx.x; j < L; j += blockDim.x) {
-    const int k = j % Ns;
+    const int k = ns_pow2 ? (j & (Ns - 1)) : (j % Ns);
     V v[R];
 #pragma unroll
     for (int i = 0; i < R; i++) v[i] = in[j + i * L];
@@ -1236,6 +1237,11 @@ static int launch_decode(frad_ctx* ctx, dec_params& P, int prec) {
     int rc = run_tns_synthesis(ctx, P);
     if (rc) return rc;
   }
+  if (P.profile == 1 || P.profile == 2) {                    // the generic prologue's dequantiser table
+    int rc = frad_ensure_dq64(ctx);
+    if (rc) return rc;
+    P.dq64 = (const double*)ctx->dequant_table; P.dq_len = FRAD_DQ_LEN;
+  }
   if (pl->direct) {
     int grid = 4 * ctx->sm_count; if (grid > nseq) grid = nseq;
     size_t need = (size_t)grid * P.N * sizeof(double);
@@ -1392,7 +1398,8 @@ static const band_table* get_band_table(frad_ctx* ctx, int N, int srate) {
   if (it != ctx->band_tables.end()) return (const band_table*)it->second;
   static const double hz[28] = {0, 200, 400, 600, 800, 1000, 1200, 1400, 1600, 2000, 2400, 2800, 3200, 4000, 4800, 5600,
                                 6800, 8000, 9600, 12000, 15600, 20000, 24000, 28800, 34400, 40800, 48000, 4294967295.0};
-  band_table h;
+  std::vector<band_table> hv(1);                           // (28 KiB: not on the stack)
+  band_table& h = hv[0];
   for (int i = 0; i < 28; i++) {
     // p1tools.py:16  round(dlen/(srate/2)*Hz), half-to-even
     double v = (double)N / ((double)srate / 2.0) * hz[i];
@@ -1411,6 +1418,15 @@ static const band_table* get_band_table(frad_ctx* ctx, int N, int srate) {
   for (int t = -FRAD_THR_TAB; t <= FRAD_THR_TAB; t++) {
     const double v = (double)t;      // np.power(np.e / 2, sign(t) * |t| ** 0.75), profile1.py:66
     h.thr_pow[t + FRAD_THR_TAB] = pow(M_E / 2.0, copysign(pow(fabs(v), 0.75), v));
+  }
+  {   // ramp band of every bin: ramp_value's search over the clipped band starts (profiles.cuh)
+    int lo[FRAD_NBANDS + 1];
+    for (int i = 0; i <= FRAD_NBANDS; i++) lo[i] = (h.edge[i] < N) ? h.edge[i] : N;
+    for (int k = 0; k < FRAD_MAX_FRAME; k++) {
+      int b = 0;
+      for (int s2 = 16; s2 > 0; s2 >>= 1) { if (b + s2 <= FRAD_NBANDS - 2 && lo[b + s2] <= k) b += s2; }
+      h.bidx[k] = (k >= N || k >= lo[FRAD_NBANDS - 1]) ? 255 : (uint8_t)b;
+    }
   }
   void* d = nullptr;
   if (cudaMalloc(&d, sizeof(band_table)) != cudaSuccess ||

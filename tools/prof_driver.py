@@ -15,6 +15,8 @@ mode = sys.argv[3] if len(sys.argv) > 3 else "p1"
 N, HOP, CH = 2048, 1920, 2
 if mode == "p1n1024":
     N, HOP = 1024, 960
+if mode.startswith("p1n") and mode != "p1n1024":            # any other frame length, e.g. p1n4096 / p1n1280 (generic kernels)
+    N = int(mode[3:]); HOP = N - N // 16
 L = _abi.lib()
 ctx = Context(0)
 tile = synth_pcm(2.0, 48000, CH, 1)
@@ -39,7 +41,7 @@ for _ in range(reps):
             d_lpc = ctx.dev(frames * 13 * CH * 4)
         ctx.check(L.frad_p1_encode_dev(ctx.handle, d_pcm.ptr, _abi.F32, HOP, frames, N, CH, 16, 48000, 0.5526315789473684, 0, d_q.ptr, d_tq.ptr, d_lpc.ptr))
         ctx.check(L.frad_p1_decode_dev(ctx.handle, d_q.ptr, d_tq.ptr, d_lpc.ptr, frames, N, CH, 16, 48000, _abi.PREC_F64, d_out.ptr, _abi.F64))
-    elif mode in ("p1", "p1n1024"):
+    elif mode == "p1" or mode.startswith("p1n"):
         ctx.check(L.frad_p1_encode_dev(ctx.handle, d_pcm.ptr, _abi.F32, HOP, frames, N, CH, 16, 48000, 0.5526315789473684, 0, d_q.ptr, d_tq.ptr, None))
         ctx.check(L.frad_p1_decode_dev(ctx.handle, d_q.ptr, d_tq.ptr, None, frames, N, CH, 16, 48000, _abi.PREC_F64, d_out.ptr, _abi.F64))
         ctx.check(L.frad_p1_decode_dev(ctx.handle, d_q.ptr, d_tq.ptr, None, frames, N, CH, 16, 48000, _abi.PREC_F32, d_out.ptr, _abi.F64))
