@@ -57,6 +57,24 @@ template <typename T, bool INV> struct small_dft<T, 4, INV> {
     v[1] = cadd(d02, d13); v[3] = csub(d02, d13);
   }
 };
+// radix 8 = two radix-4 butterflies over the even / odd inputs and one twiddled radix-2 stage (W8^k = e^{-+ 2 pi i k / 8})
+template <typename T, bool INV> struct small_dft<T, 8, INV> {
+  typedef typename vec2<T>::type V;
+  static __device__ __forceinline__ void run(V* v) {
+    V e[4] = {v[0], v[2], v[4], v[6]}, o[4] = {v[1], v[3], v[5], v[7]};
+    small_dft<T, 4, INV>::run(e);
+    small_dft<T, 4, INV>::run(o);
+    const T h = (T)0.70710678118654752440;
+    // forward: W8 = (1 - i)/sqrt2, W8^2 = -i, W8^3 = (-1 - i)/sqrt2; the inverse conjugates
+    const V o1 = INV ? mk2<T>((o[1].x - o[1].y) * h, (o[1].x + o[1].y) * h) : mk2<T>((o[1].x + o[1].y) * h, (o[1].y - o[1].x) * h);
+    const V o2 = mul_mi<INV>(o[2]);
+    const V o3 = INV ? mk2<T>(-(o[3].x + o[3].y) * h, (o[3].x - o[3].y) * h) : mk2<T>((o[3].y - o[3].x) * h, -(o[3].x + o[3].y) * h);
+    v[0] = cadd(e[0], o[0]); v[4] = csub(e[0], o[0]);
+    v[1] = cadd(e[1], o1);   v[5] = csub(e[1], o1);
+    v[2] = cadd(e[2], o2);   v[6] = csub(e[2], o2);
+    v[3] = cadd(e[3], o3);   v[7] = csub(e[3], o3);
+  }
+};
 template <int R> struct odd_roots;
 template <> struct odd_roots<3> {
   static __device__ __forceinline__ double c(int i) { const double t[3] = {1.0, -0.5, -0.5}; return t[i]; }
