@@ -1,6 +1,7 @@
 // Shared host/device plumbing for libfradb200 (context, error handling, plan cache).
 #pragma once
-#define FRAD_DQ_LEN 4096            // entries of the global |q|^(4/3) table (frad_ensure_dq64)
+#define FRAD_DQ_LEN 65536           // entries of the global |q|^(4/3) table (frad_ensure_dq64): 512 KiB, L2-resident.  Loud low bins of
+                                    // a 16-bit stream reach five digits, and one such lane sends its whole warp through pow()
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>

@@ -522,11 +522,12 @@ __device__ void p1_prologue(const dec_params& P, T* X, int N, int b, int c, band
   if (P.profile == 1) {
     // profile1.py:65: sign(q) |q|^(4/3) / 2^(bits-1); the magnitudes come from the host-computed table (libm's pow, like the
     // reference) -- the in-line pow() was 40 % of this kernel's instructions
+    const double inv_scale = 1.0 / P.scale;                   // a power of two: the product is the quotient, bit for bit
     for_each_bin_ramp(bw, bt, N, [&](int k, double div) {
       const int qi = qrow[(size_t)k * C + c];
       const uint32_t qa = (qi < 0) ? 0u - (uint32_t)qi : (uint32_t)qi;
       const double mag = (P.dq64 && qa < (uint32_t)P.dq_len) ? __ldg(P.dq64 + qa) : pow((double)qa, 1.0 / 0.75);
-      const double coef = ((qi < 0) ? -mag : mag) / P.scale;
+      const double coef = ((qi < 0) ? -mag : mag) * inv_scale;
       X[k] = (T)(coef * div);
     });
     return;
