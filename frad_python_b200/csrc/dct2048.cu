@@ -275,8 +275,22 @@ dec2048_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restri
         for (int idx = tid; idx < FN * 2; idx += FW * 32) {
           const int k = idx >> 1, h = idx & 1;
           const double2 v2 = __ldg(base + idx);
-          seq_base[(size_t)(2 * h) * STRIDE_T + k] = ramp_mul(v2.x, 2 * h, k);
-          seq_base[(size_t)(2 * h + 1) * STRIDE_T + k] = ramp_mul(v2.y, 2 * h + 1, k);
+          // both sequences share the bin: one band look-up, both products formed before either is stored
+          const int bnd = tail->bidx[k];
+          T r0, r1;
+          if constexpr (sizeof(T) == 8) {
+            const double jd = (double)(k - tail->lo[bnd]);
+            const double2 p0 = tail->rp[2 * h][bnd], p1 = tail->rp[2 * h + 1][bnd];
+            r0 = v2.x * __dadd_rn(__dmul_rn(jd, p0.y), p0.x);                              // j * step + start
+            r1 = v2.y * __dadd_rn(__dmul_rn(jd, p1.y), p1.x);
+          } else {
+            const float4 b0v = tail->bp[2 * h][bnd], b1v = tail->bp[2 * h + 1][bnd];
+            const float kf = (float)k;
+            r0 = (float)v2.x * fmaf(kf - b0v.z, b0v.y, (b0v.w - kf) * b0v.x);
+            r1 = (float)v2.y * fmaf(kf - b1v.z, b1v.y, (b1v.w - kf) * b1v.x);
+          }
+          seq_base[(size_t)(2 * h) * STRIDE_T + k] = r0;
+          seq_base[(size_t)(2 * h + 1) * STRIDE_T + k] = r1;
         }
       } else {
       for (int f = 0; f < nf; f++) {
