@@ -705,13 +705,17 @@ tns_apply_kernel(enc_params P, const tns_ctl* __restrict__ ctl, const double* __
       asm volatile("prefetch.global.L2 [%0];" ::"l"(xbuf + (size_t)(s + gridDim.x) * N + BPT * t));
       if (t == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(ctl + s + gridDim.x));
     }
+    // the sequence's hand-over record is requested together with its spectrum, ahead of the barrier (three dependent loads
+    // behind it were 11 % of the kernel's stall samples)
+    const int flag_s = ctl[s].flag;
+    const int aq_ld = (t < L) ? ctl[s].aq[t] : 0;
+    const double sx = ctl[s].sx;
     __syncthreads();                                     // the previous sequence's rows and coefficients are free
-    bool accept = ctl[s].flag != 0;                      // uniform over the CTA
+    bool accept = flag_s != 0;                           // uniform over the CTA
     int aq_t = 0;
     double y[BPT];
     if (accept) {
-      if (t < L) { aq_t = ctl[s].aq[t]; bw->a[t] = (t == 0) ? 1.0 : (double)aq_t / 15.0; }     // dequantise_lpc, p2tools.py:49-55
-      const double sx = ctl[s].sx;
+      if (t < L) { aq_t = aq_ld; bw->a[t] = (t == 0) ? 1.0 : (double)aq_t / 15.0; }            // dequantise_lpc, p2tools.py:49-55
 #pragma unroll
       for (int i = 0; i < BPT; i++) xs[own + i] = x[i];
       __syncthreads();
