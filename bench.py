@@ -379,13 +379,17 @@ def main():
     # the PCM from pinned memory and its own D2H of the decoded PCM; the payload goes through one of two pinned slots.
     import queue
     ctx_b = Context(local)
-    h_raw2 = [h_raw, ctx.pinned((raw_cap,), np.uint8)]
-    h_off2 = [h_off, ctx.pinned((B + 1,), np.uint64)]
+    h_raw2 = [h_raw, ctx.pinned((raw_cap,), np.uint8), ctx.pinned((raw_cap,), np.uint8)]
+    h_off2 = [h_off, ctx.pinned((B + 1,), np.uint64), ctx.pinned((B + 1,), np.uint64)]
     h_out_b = ctx_b.pinned((B, N, CH), np.float32)
     h_st_b = ctx_b.pinned((B,), np.int32)
     ready, free_slots, errs = queue.Queue(), queue.Queue(), []
-    for sl in (0, 1):
+    for sl in (0, 1, 2):
         free_slots.put(sl)
+    # Both calls of a pair start when the encoder has delivered a step and take equally long, so their pipeline fill (H2D
+    # only) and drain (D2H only) phases coincide and both directions idle together.  The decoder is therefore started a
+    # fraction of a step late once; with three payload slots the offset persists.  FRAD_E2E_STAGGER_MS=0 switches it off.
+    stagger_s = float(os.environ.get("FRAD_E2E_STAGGER_MS", "4")) * 1e-3
 
     def enc_worker(nsteps):
         try:
@@ -399,10 +403,12 @@ def main():
 
     def dec_worker(nsteps):
         try:
-            for _ in range(nsteps):
+            for it in range(nsteps):
                 sl = ready.get()
                 if sl is None:
                     return
+                if it == 0 and stagger_s > 0:
+                    time.sleep(stagger_s)
                 ctx_b.check(L.frad_p1_decode_raw(ctx_b.handle, h_raw2[sl].ctypes.data, h_off2[sl].ctypes.data, B, N, CH, BITS,
                                                  SRATE, _abi.PREC_REF, 1, h_out_b.ctypes.data, _abi.F32, h_st_b.ctypes.data))
                 free_slots.put(sl)
