@@ -8,6 +8,8 @@
 //              says so (f64: highest group first, so the 8-byte values never overwrite integers that are still to be read)
 //   transform  pairwise pre-processing (k, M-k) as in dct2048.cu, then fft32.cuh: ifft_multi_warp
 //   store      time samples through a rotated staging layout, then cooperative 16-byte stores of the interleaved PCM
+// R1 = 3, 5, 6, 7, 10, 12, 14, 20, 24, 28 (N = 192 ... 1792, the 160 / 192 / 224 families): S = floor(32 / R1) sequences per warp and the
+// mixed-radix last pass of fftmix.cuh; the lanes at and above S R1 own no sequence before the exchange (see enc2048.cu).
 // Reference lines: fourier/profile0.py:46-69; fourier/profile1.py:54-77; fourier/tools/p1tools.py:35-44.
 #include "tile2048.cuh"
 
@@ -39,6 +41,7 @@ decs_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restrict_
   constexpr bool F32 = sizeof(T) == 4;
   constexpr int NN = 64 * R1, MM = 32 * R1, S = 32 / R1, SPC = FW * S;
   constexpr int SEQ_T = 68 * R1;
+  constexpr int RS = S * R1;                          // lanes that own a sequence before the exchange (32 for the powers of two)
   constexpr int DQN = F32 ? 1024 : 256;
   typedef decs_tail<T, S> TAIL;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -46,7 +49,8 @@ decs_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restrict_
   TAIL* tail = (TAIL*)(smem_raw + (size_t)FW * DSEQ * sizeof(V));
   const int C = P.C;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int k1 = lane % R1, sl = lane / R1;
+  const int k1 = lane % R1, sl = (RS == 32) ? lane / R1 : min(lane / R1, S - 1);
+  const bool act = (RS == 32) || lane < RS;
   const int fpt = SPC / C;
   const int ntiles = (P.B + fpt - 1) / fpt;
   const V* ci = (const V*)pl.ci;
@@ -145,6 +149,7 @@ decs_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restrict_
       T* Xs = X + SEQ_T * sl;
       // ---- the lane's run, converted in place: 32-bit words -> spectrum values of type T ----
       if (PROFILE != 0 || p0_words) {
+        if (act) {
         const int* qrun = (const int*)X + qposd<T>(64 * lane);
         T* xrun = X + 68 * lane;
         int bnd = bfirst;
@@ -206,6 +211,7 @@ decs_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restrict_
             for (int u2 = 0; u2 < 4; u2++) ((double2*)xrun)[4 * g + u2] = make_double2(out[2 * u2], out[2 * u2 + 1]);
           }
         }
+        }
         __syncwarp();
       }
       // ---- pairwise pre-processing: R1 = X[k] - i X[N-k], R2 = (X[M-k] + i X[M+k]) e^{-i pi/4},
@@ -256,7 +262,7 @@ decs_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restrict_
       // ---- undo the Makhoul reordering into the time-domain staging: register s R1 + p holds z_s[m], m = lane + 32 perm_r(p);
       //      m < M/2: samples 4m, 4m + 2;  m >= M/2: samples 2N - 1 - 4m, 2N - 3 - 4m ----
 #pragma unroll
-      for (int i = 0; i < 32; i++) {
+      for (int i = 0; i < RS; i++) {
         const int s = i / R1, m = lane + 32 * perm_r<R1>(i % R1);
         T* ts = X + SEQ_T * s;
         const int na = (m < MM / 2) ? 4 * m : 2 * NN - 1 - 4 * m;
@@ -302,19 +308,6 @@ decs_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restrict_
 
 }  // namespace
 
-bool frad_fast_small_decode_ok(const dec_params& P, int prec) {
-  (void)prec;
-  if (P.N != 1024 && P.N != 512 && P.N != 256 && P.N != 128) return false;
-  const int spc = FW * (2048 / P.N);
-  if (P.C < 1 || P.C > spc || (spc % P.C) != 0) return false;
-  if (((size_t)P.N * P.C) % 8) return false;
-  if (P.profile == 2 || P.profile == 4) return false;
-  if (P.profile == 0 && ((P.payload_stride % 16) != 0 || ((uintptr_t)P.payload % 16) != 0)) return false;
-  if (P.profile == 1 && ((uintptr_t)P.q % 16) != 0) return false;
-  if (((uintptr_t)P.pcm % 16) != 0) return false;
-  return true;
-}
-
 #define DECS_DISPATCH(TT, PROF, RR)                                                                          \
   do {                                                                                                       \
     auto k = decs_kernel<TT, PROF, RR>;                                                                      \
@@ -325,17 +318,66 @@ bool frad_fast_small_decode_ok(const dec_params& P, int prec) {
     if (rc) return rc;                                                                                       \
     k<<<grid, FW * 32, smem, ctx->stream>>>(P, plan_view(pl), (const vec2<TT>::type*)pl->tw32, (const double*)ctx->dequant_table); \
   } while (0)
+
+#ifdef FRAD_TU_MIXED
+// ---- translation units decm32.cu / decm64.cu: the mixed-radix frame lengths, one arithmetic type each ----
+#define DECM_BY_R(TT, PROF)                                                                             \
+  do {                                                                                                  \
+    switch (P.N / 64) {                                                                                 \
+      case 3: DECS_DISPATCH(TT, PROF, 3); break;    case 5: DECS_DISPATCH(TT, PROF, 5); break;          \
+      case 6: DECS_DISPATCH(TT, PROF, 6); break;    case 7: DECS_DISPATCH(TT, PROF, 7); break;          \
+      case 10: DECS_DISPATCH(TT, PROF, 10); break;  case 12: DECS_DISPATCH(TT, PROF, 12); break;        \
+      case 14: DECS_DISPATCH(TT, PROF, 14); break;  case 20: DECS_DISPATCH(TT, PROF, 20); break;        \
+      case 24: DECS_DISPATCH(TT, PROF, 24); break;  case 28: DECS_DISPATCH(TT, PROF, 28); break;        \
+      default: return frad_fail(ctx, FRAD_E_ARG, "mixed-radix decoder: frame length");                  \
+    }                                                                                                   \
+  } while (0)
+#if FRAD_TU_MIXED == 32
+int frad_launch_decode_mixed_f32(frad_ctx* ctx, const dec_params& P, const frad_plan* pl) {
+  if (P.profile == 0) DECM_BY_R(float, 0); else DECM_BY_R(float, 1);
+  FRAD_LAUNCH_CHECK(ctx);
+  return FRAD_OK;
+}
+#else
+int frad_launch_decode_mixed_f64(frad_ctx* ctx, const dec_params& P, const frad_plan* pl) {
+  if (P.profile == 0) DECM_BY_R(double, 0); else DECM_BY_R(double, 1);
+  FRAD_LAUNCH_CHECK(ctx);
+  return FRAD_OK;
+}
+#endif
+#else   // !FRAD_TU_MIXED
+
+bool frad_fast_small_decode_ok(const dec_params& P, int prec) {
+  (void)prec;
+  const int r1 = frad_warp_r1(P.N);
+  if (!r1) return false;
+  const int spc = FW * (32 / r1);
+  if (P.C < 1 || P.C > spc || (spc % P.C) != 0) return false;
+  if (((size_t)P.N * P.C) % 8) return false;
+  if (P.profile == 2 || P.profile == 4) return false;
+  if (P.profile == 0 && ((P.payload_stride % 16) != 0 || ((uintptr_t)P.payload % 16) != 0)) return false;
+  if (P.profile == 1 && ((uintptr_t)P.q % 16) != 0) return false;
+  if (((uintptr_t)P.pcm % 16) != 0) return false;
+  return true;
+}
+
 #define DECS_BY_R(TT, PROF)                                                                             \
   do {                                                                                                  \
     if (P.N == 1024) DECS_DISPATCH(TT, PROF, 16); else if (P.N == 512) DECS_DISPATCH(TT, PROF, 8);      \
     else if (P.N == 256) DECS_DISPATCH(TT, PROF, 4); else DECS_DISPATCH(TT, PROF, 2);                 \
   } while (0)
 
+int frad_launch_decode_mixed_f32(frad_ctx* ctx, const dec_params& P, const frad_plan* pl);   // decm32.cu
+int frad_launch_decode_mixed_f64(frad_ctx* ctx, const dec_params& P, const frad_plan* pl);   // decm64.cu
+
 int frad_launch_decode_small(frad_ctx* ctx, const dec_params& P, const frad_plan* pl, int prec) {
   int rc = frad_ensure_dq64(ctx);
   if (rc) return rc;
+  if (frad_warp_r1_mixed(frad_warp_r1(P.N)))
+    return (prec == FRAD_PREC_F32) ? frad_launch_decode_mixed_f32(ctx, P, pl) : frad_launch_decode_mixed_f64(ctx, P, pl);
   if (prec == FRAD_PREC_F32) { if (P.profile == 0) DECS_BY_R(float, 0); else DECS_BY_R(float, 1); }
   else { if (P.profile == 0) DECS_BY_R(double, 0); else DECS_BY_R(double, 1); }
   FRAD_LAUNCH_CHECK(ctx);
   return FRAD_OK;
 }
+#endif  // FRAD_TU_MIXED

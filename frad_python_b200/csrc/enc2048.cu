@@ -559,6 +559,11 @@ enc2048r_kernel(enc_params P, plan_dev pl, const typename vec2<T>::type* __restr
 // 64 contiguous bins [64 k1, 64 k1 + 64) of its sequence -- which in the padded layout start at word 68 L of the warp buffer,
 // exactly as in the N = 2048 kernel, so the run epilogue is the same code with k1 in place of the lane number.
 // A tile is FW S sequences = FW S / C whole frames (the host checks that C divides FW S).
+//
+// R1 = 3, 5, 6, 7, 10, 12, 14, 20, 24, 28 (N = 192 ... 1792: the 160 / 192 / 224 families of the compact table): the same kernel with
+// the mixed-radix first pass of fftmix.cuh and S = floor(32 / R1) sequences per warp.  S R1 < 32 then: the lanes at and above
+// S R1 have no sequence after the exchange -- they run along on the last sequence's addresses (every shuffle keeps its full
+// mask) and store nothing.
 template <typename T, int S> struct encs_tail {
   int lo[FRAD_NBANDS + 1];
   double inv_ns[FRAD_NBANDS + 1];
@@ -573,6 +578,7 @@ encs_kernel(enc_params P, plan_dev pl, const typename vec2<T>::type* __restrict_
   typedef typename vec2<T>::type V;
   constexpr bool F32 = sizeof(T) == 4;
   constexpr int NN = 64 * R1, MM = 32 * R1, S = 32 / R1, SPC = FW * S;
+  constexpr int RS = S * R1;                           // lanes that own a sequence after the exchange (32 for the powers of two)
   constexpr int SEQ_T = 68 * R1;                       // T slots of one sequence in the padded spectrum layout
   typedef encs_tail<T, S> TAIL;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -580,7 +586,8 @@ encs_kernel(enc_params P, plan_dev pl, const typename vec2<T>::type* __restrict_
   TAIL* tail = (TAIL*)(smem_raw + (size_t)FW * ESEQ * sizeof(V));
   const int C = P.C;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int k1 = lane % R1, sl = lane / R1;
+  const int k1 = lane % R1, sl = (RS == 32) ? lane / R1 : min(lane / R1, S - 1);
+  const bool act = (RS == 32) || lane < RS;
   const int fpt = SPC / C;                             // whole frames per tile
   const int ntiles = (P.B + fpt - 1) / fpt;
   const V* cfh = (const V*)pl.cfh;
@@ -639,7 +646,7 @@ encs_kernel(enc_params P, plan_dev pl, const typename vec2<T>::type* __restrict_
     __syncthreads();
     if (w * S < nseq) {
       const int q_me = w * S + sl;                       // my sequence slot in the tile
-      const bool live = q_me < nseq;                     // lanes of slots beyond the batch compute on stale data and store nothing global
+      const bool live = act && q_me < nseq;              // lanes of slots beyond the batch compute on stale data and store nothing global
       const int f_me = q_me / C, c_me = q_me - f_me * C, b_me = b0 + f_me;
       V* buf = seq_all + (size_t)w * ESEQ;
       T* X = (T*)buf;
@@ -655,6 +662,7 @@ encs_kernel(enc_params P, plan_dev pl, const typename vec2<T>::type* __restrict_
       const bool swap_out = p0_words && !P.le;
       T mx = T(0);
       auto put = [&](int k, T val) {
+        if (!act) return;
         if (PROFILE == 0) {
           mx = fmax(mx, fabs(val));
           if constexpr (F32) { if (swap_out) val = __uint_as_float(__byte_perm(__float_as_uint(val), 0, 0x0123)); }
@@ -699,14 +707,20 @@ encs_kernel(enc_params P, plan_dev pl, const typename vec2<T>::type* __restrict_
       }
       if (PROFILE == 0) {
         if (P.peak) {
+          if constexpr ((R1 & (R1 - 1)) == 0) {
 #pragma unroll
-          for (int s = 1; s < R1; s <<= 1) mx = fmax(mx, (T)__shfl_xor_sync(0xffffffffu, mx, s));     // over the R1 lanes of my sequence
+            for (int s = 1; s < R1; s <<= 1) mx = fmax(mx, (T)__shfl_xor_sync(0xffffffffu, mx, s));   // over the R1 lanes of my sequence
+          } else {
+            const T mine = mx;
+#pragma unroll
+            for (int s = 1; s < R1; s++) mx = fmax(mx, shfl_t<T>(mine, sl * R1 + (k1 + s) % R1));
+          }
           if (k1 == 0 && live) atomicMax((unsigned long long*)&P.peak[b_me], (unsigned long long)__double_as_longlong((double)mx));
         }
       } else {
         __syncwarp();
         const T* run = X + 68 * lane;
-        {
+        if (act) {
           T* slot = tail->part[w][sl] + k1 + bfirst;
           T acc = T(0);
 #pragma unroll
@@ -780,7 +794,7 @@ encs_kernel(enc_params P, plan_dev pl, const typename vec2<T>::type* __restrict_
           }
         }
         __syncwarp();
-        {
+        if (act) {
           const float4* bpp = tail->bp[w][sl] + bfirst;
           float4 bpv = *bpp;
           const float kb = (float)(64 * k1);
@@ -880,6 +894,46 @@ encs_kernel(enc_params P, plan_dev pl, const typename vec2<T>::type* __restrict_
 
 }  // namespace
 
+#define ENCS_DISPATCH(TT, PROF, RR)                                                                          \
+  do {                                                                                                       \
+    auto k = encs_kernel<TT, PROF, RR>;                                                                      \
+    const int fpt = FW * (32 / RR) / P.C;                                                                    \
+    int grid;                                                                                                \
+    const size_t smem = (size_t)FW * ESEQ * sizeof(vec2<TT>::type) + ((PROF == 0) ? 16 : sizeof(encs_tail<TT, 32 / RR>)); \
+    int rc = launch_cfg(ctx, k, smem, (P.B + fpt - 1) / fpt, &grid);                                         \
+    if (rc) return rc;                                                                                       \
+    k<<<grid, FW * 32, smem, ctx->stream>>>(P, plan_view(pl), (const vec2<TT>::type*)pl->tw32, force_exact); \
+  } while (0)
+
+#ifdef FRAD_TU_MIXED
+// ---- translation units encm32.cu / encm64.cu: the mixed-radix frame lengths (N = 64 R1, R1 as in fftmix.cuh), one arithmetic
+//      type each, so that their twenty kernels compile beside this file's ----
+#define ENCM_BY_R(TT, PROF)                                                                             \
+  do {                                                                                                  \
+    switch (P.N / 64) {                                                                                 \
+      case 3: ENCS_DISPATCH(TT, PROF, 3); break;    case 5: ENCS_DISPATCH(TT, PROF, 5); break;          \
+      case 6: ENCS_DISPATCH(TT, PROF, 6); break;    case 7: ENCS_DISPATCH(TT, PROF, 7); break;          \
+      case 10: ENCS_DISPATCH(TT, PROF, 10); break;  case 12: ENCS_DISPATCH(TT, PROF, 12); break;        \
+      case 14: ENCS_DISPATCH(TT, PROF, 14); break;  case 20: ENCS_DISPATCH(TT, PROF, 20); break;        \
+      case 24: ENCS_DISPATCH(TT, PROF, 24); break;  case 28: ENCS_DISPATCH(TT, PROF, 28); break;        \
+      default: return frad_fail(ctx, FRAD_E_ARG, "mixed-radix encoder: frame length");                  \
+    }                                                                                                   \
+  } while (0)
+#if FRAD_TU_MIXED == 32
+int frad_launch_encode_mixed_f32(frad_ctx* ctx, const enc_params& P, const frad_plan* pl, int force_exact) {
+  if (P.profile == 0) ENCM_BY_R(float, 0); else ENCM_BY_R(float, 1);
+  FRAD_LAUNCH_CHECK(ctx);
+  return FRAD_OK;
+}
+#else
+int frad_launch_encode_mixed_f64(frad_ctx* ctx, const enc_params& P, const frad_plan* pl, int force_exact) {
+  if (P.profile == 0) ENCM_BY_R(double, 0); else ENCM_BY_R(double, 1);
+  FRAD_LAUNCH_CHECK(ctx);
+  return FRAD_OK;
+}
+#endif
+#else   // !FRAD_TU_MIXED
+
 #define ENCR_DISPATCH(TT, PROF, CT)                                                                          \
   do {                                                                                                       \
     auto k = enc2048r_kernel<TT, PROF, CT>;                                                                  \
@@ -910,27 +964,18 @@ bool frad_fast2048_encode_ok(const enc_params& P, int prec) {
   return true;
 }
 
-#define ENCS_DISPATCH(TT, PROF, RR)                                                                          \
-  do {                                                                                                       \
-    auto k = encs_kernel<TT, PROF, RR>;                                                                      \
-    const int fpt = FW * (32 / RR) / P.C;                                                                    \
-    int grid;                                                                                                \
-    const size_t smem = (size_t)FW * ESEQ * sizeof(vec2<TT>::type) + ((PROF == 0) ? 16 : sizeof(encs_tail<TT, 32 / RR>)); \
-    int rc = launch_cfg(ctx, k, smem, (P.B + fpt - 1) / fpt, &grid);                                         \
-    if (rc) return rc;                                                                                       \
-    k<<<grid, FW * 32, smem, ctx->stream>>>(P, plan_view(pl), (const vec2<TT>::type*)pl->tw32, force_exact); \
-  } while (0)
 #define ENCS_BY_R(TT, PROF)                                                                             \
   do {                                                                                                  \
     if (P.N == 1024) ENCS_DISPATCH(TT, PROF, 16); else if (P.N == 512) ENCS_DISPATCH(TT, PROF, 8);      \
     else if (P.N == 256) ENCS_DISPATCH(TT, PROF, 4); else ENCS_DISPATCH(TT, PROF, 2);                 \
   } while (0)
 
-// N = 1024, 512, 256: S = 2, 4, 8 sequences per warp, FW S sequences per tile; whole frames per tile
+// N = 64 R1 < 2048 (frad_warp_r1): S = floor(32 / R1) sequences per warp, FW S sequences per tile; whole frames per tile
 bool frad_fast_small_encode_ok(const enc_params& P, int prec) {
-  if (P.N != 1024 && P.N != 512 && P.N != 256 && P.N != 128) return false;
+  const int r1 = frad_warp_r1(P.N);
+  if (!r1) return false;
   if (prec != FRAD_PREC_F32 && prec != FRAD_PREC_F64) return false;
-  const int spc = FW * (2048 / P.N);
+  const int spc = FW * (32 / r1);
   if (P.C < 1 || P.C > spc || (spc % P.C) != 0) return false;
   if (((size_t)P.N * P.C) % 4) return false;
   if (P.profile == 2) return false;                           // profile 2 keeps the generic path at these sizes
@@ -940,7 +985,12 @@ bool frad_fast_small_encode_ok(const enc_params& P, int prec) {
   return true;
 }
 
+int frad_launch_encode_mixed_f32(frad_ctx* ctx, const enc_params& P, const frad_plan* pl, int force_exact);   // encm32.cu
+int frad_launch_encode_mixed_f64(frad_ctx* ctx, const enc_params& P, const frad_plan* pl, int force_exact);   // encm64.cu
+
 int frad_launch_encode_small(frad_ctx* ctx, const enc_params& P, const frad_plan* pl, int prec, int force_exact) {
+  if (frad_warp_r1_mixed(frad_warp_r1(P.N)))
+    return (prec == FRAD_PREC_F32) ? frad_launch_encode_mixed_f32(ctx, P, pl, force_exact) : frad_launch_encode_mixed_f64(ctx, P, pl, force_exact);
   if (prec == FRAD_PREC_F32) { if (P.profile == 0) ENCS_BY_R(float, 0); else ENCS_BY_R(float, 1); }
   else { if (P.profile == 0) ENCS_BY_R(double, 0); else ENCS_BY_R(double, 1); }
   FRAD_LAUNCH_CHECK(ctx);
@@ -960,3 +1010,4 @@ int frad_launch_encode_2048r(frad_ctx* ctx, const enc_params& P, const frad_plan
   FRAD_LAUNCH_CHECK(ctx);
   return FRAD_OK;
 }
+#endif  // FRAD_TU_MIXED

@@ -98,6 +98,8 @@ __device__ __forceinline__ V mul_w32(V v, int t) {
   return crot(v, c, s);
 }
 
+#include "fftmix.cuh"
+
 template <typename T, bool INV, typename V>
 __device__ __forceinline__ void fft4_inplace(V& a, V& b, V& c, V& d) {
   V s0 = cadd(a, c), s1 = csub(a, c), s2 = cadd(b, d), s3 = mul_mi<INV>(csub(b, d));
@@ -151,11 +153,12 @@ __device__ __forceinline__ void fft16_perm(V* v) {
 }
 // R-point DFT in place for R in {2, 4, 8, 16, 32}; position p of the output holds frequency index perm_r<R>(p)
 template <int R> __host__ __device__ constexpr int perm_r(int p) {
-  return (R == 32) ? perm32(p) : (R == 16) ? perm16(p) : (R == 8) ? perm8(p) : p;
+  return mix_radix<R>() ? mix_perm<R>(p) : (R == 32) ? perm32(p) : (R == 16) ? perm16(p) : (R == 8) ? perm8(p) : p;
 }
 template <typename T, bool INV, int R, typename V>
 __device__ __forceinline__ void fft_r_perm(V* v) {
-  if constexpr (R == 32) fft32_perm<T, INV>(v);
+  if constexpr (mix_radix<R>()) mix_fft<T, INV, R>(v);
+  else if constexpr (R == 32) fft32_perm<T, INV>(v);
   else if constexpr (R == 16) fft16_perm<T, INV>(v);
   else if constexpr (R == 8) fft8_perm<T, INV>(v);
   else if constexpr (R == 4) fft4_inplace<T, INV>(v[0], v[1], v[2], v[3]);
@@ -223,11 +226,11 @@ __device__ __forceinline__ void fft_multi_warp(typename vec2<T>::type* v, typena
                                                const typename vec2<T>::type* wlane = nullptr) {
   typedef typename vec2<T>::type V;
   if constexpr (R1 == 32) { fft1024_warp<T, INV>(v, buf, lane, tw32, wlane); return; }
-  constexpr int S = 32 / R1;
+  constexpr int S = 32 / R1;                             // R1 not a power of two: S R1 < 32 registers (then lanes) carry data
 #pragma unroll
   for (int s = 0; s < S; s++) fft_r_perm<T, INV, R1>(v + s * R1);
 #pragma unroll
-  for (int P = 0; P < 32; P++) buf[33 * lane + (P / R1) * R1 + perm_r<R1>(P % R1)] = v[P];
+  for (int P = 0; P < S * R1; P++) buf[33 * lane + (P / R1) * R1 + perm_r<R1>(P % R1)] = v[P];
   __syncwarp();
 #pragma unroll
   for (int i = 0; i < 32; i++) v[i] = buf[lane + 33 * i];

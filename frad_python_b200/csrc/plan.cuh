@@ -19,8 +19,8 @@ struct frad_plan {
   int npass = 0;
   int radix[FRAD_MAX_RADIX_PASSES] = {};
   void *tw = nullptr, *cf = nullptr, *df = nullptr, *ci = nullptr, *ei = nullptr;
-  void *cfh = nullptr, *dfh = nullptr;  // N == 2048 only: cf / 2, df / 2 (pairwise post-processing)
-  void* tw32 = nullptr;  // N == 2048 only: [i][lane] = exp(-2 pi i * i * lane / 1024) for the 32 x 32 warp FFT
+  void *cfh = nullptr, *dfh = nullptr;  // warp-FFT lengths (N == 2048, frad_warp_r1) only: cf / 2, df / 2 (pairwise post-processing)
+  void* tw32 = nullptr;  // warp-FFT lengths only: [i][lane] = exp(-2 pi i * i * (lane mod R1) / M), R1 = M / 32 (N == 2048: lane)
   double* ct = nullptr;
 };
 
@@ -39,6 +39,18 @@ static inline plan_dev plan_view(const frad_plan* p) {
   d.tw = p->tw; d.cf = p->cf; d.df = p->df; d.ci = p->ci; d.ei = p->ei; d.ct = p->ct; d.cfh = p->cfh; d.dfh = p->dfh;
   return d;
 }
+
+// Frame lengths N = 64 R1 < 2048 of the multi-sequence warp-FFT kernels (enc2048.cu: encs_kernel, decs.cu): R1 a power of two
+// (N = 128 ... 1024) or one of fftmix.cuh's mixed radices (N = 192 ... 1792).  Returns R1, or 0 for every other length.
+static inline int frad_warp_r1(int N) {
+  if (N <= 0 || (N % 64) != 0) return 0;
+  switch (N / 64) {
+    case 2: case 4: case 8: case 16:
+    case 3: case 5: case 6: case 7: case 10: case 12: case 14: case 20: case 24: case 28: return N / 64;
+    default: return 0;
+  }
+}
+static inline bool frad_warp_r1_mixed(int r1) { return r1 != 0 && (r1 & (r1 - 1)) != 0; }
 
 // returns nullptr on failure (ctx->err set)
 frad_plan* frad_get_plan(frad_ctx* ctx, int N, int prec);

@@ -80,7 +80,7 @@ static bool build_tables(frad_ctx* ctx, frad_plan* p) {
   }
   p->cf = upload_cpx<T>(ctx, re, im);
   p->df = upload_cpx<T>(ctx, re2, im2);
-  const bool warp_fft = (N == 2048 || N == 1024 || N == 512 || N == 256 || N == 128);   // frame lengths of the warp-FFT kernels: N = 64 R1
+  const bool warp_fft = (N == 2048 || frad_warp_r1(N) != 0);   // frame lengths of the warp-FFT kernels: N = 64 R1
   if (warp_fft) {
     for (int k = 0; k <= M; k++) { re[k] /= 2; im[k] /= 2; re2[k] /= 2; im2[k] /= 2; }
     p->cfh = upload_cpx<T>(ctx, re, im);

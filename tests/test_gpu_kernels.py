@@ -574,13 +574,16 @@ def test_fast2048_encoder_every_sample_format_and_depth(ctx, dtype):
         assert np.array_equal(q, q2) and np.array_equal(tq, tq2)
 
 
-@pytest.mark.parametrize("n", [128, 256, 512, 1024])
+@pytest.mark.parametrize("n", [128, 256, 512, 1024, 192, 320, 384, 448, 640, 768, 896, 1280, 1536, 1792])
 @pytest.mark.parametrize("c", [1, 2, 8])
 def test_small_frame_warp_kernels_match_generic_path_and_oracle(ctx, n, c):
-    """Round 2: N = 256 / 512 / 1024 (fourier/profiles.py:14-23) run on the warp-FFT kernels with 8 / 4 / 2 sequences per warp
-    (enc2048.cu: encs_kernel, decs.cu).  A/B against the generic shared-memory kernels and spot checks against the oracle."""
+    """Round 2: N = 64 R1 < 2048 (fourier/profiles.py:14-23) run on the warp-FFT kernels with floor(32 / R1) sequences per warp
+    (enc2048.cu: encs_kernel, decs.cu): R1 = 2 ... 16 and the mixed radices 3, 5, 6, 7, 10, 12, 14, 20, 24, 28 of the 160 / 192 / 224
+    families (fftmix.cuh).  A/B against the generic shared-memory kernels and spot checks against the oracle.  (Channel counts
+    that do not divide the sequences of a tile stay on the generic kernels: both sides of the A/B are then the same.)"""
     from frad_python_b200 import _abi
-    srate = {128: 8000, 256: 11025, 512: 24000, 1024: 44100}[n]
+    srate = {128: 8000, 256: 11025, 512: 24000, 1024: 44100, 192: 8000, 320: 12000, 384: 16000, 448: 22050, 640: 32000,
+             768: 44100, 896: 48000, 1280: 64000, 1536: 88200, 1792: 96000}[n]
     pcm = O.synth_pcm(n * 37 / 48000 + 0.01, 48000, c, seed=60 + n + c)[: n * 37]
     hop = n - n // 16
     nb0, nb1 = len(pcm) // n, (len(pcm) - n) // hop + 1

@@ -46,14 +46,24 @@ def pcm_dev(frames, n, hop, ch, dtype=np.float32):
     return d, pcm
 
 
-def transforms(limit=None):
+def transforms(limit=None, only=None):
     for (n, hop, ch, frames, tag) in ((2048, 2048, 2, 15000, "S48 N=2048 C=2"), (2048, 2048, 8, 4000, "S96 N=2048 C=8"),
                                        (2048, 2048, 1, 30000, "mono N=2048"), (1024, 1024, 2, 30000, "N=1024 warp-FFT, 2 sequences per warp"),
                                        (512, 512, 2, 60000, "N=512 warp-FFT, 4 sequences per warp"),
                                        (256, 256, 2, 120000, "N=256 warp-FFT, 8 sequences per warp"),
                                        (128, 128, 2, 240000, "N=128 warp-FFT, 16 sequences per warp"),
-                                       (4096, 4096, 2, 7500, "N=4096 generic"), (1280, 1280, 2, 24000, "N=1280 generic"),
+                                       (4096, 4096, 2, 7500, "N=4096 generic"), (1280, 1280, 2, 24000, "N=1280 warp-FFT, mixed radix 20"),
+                                       (1792, 1792, 2, 17142, "N=1792 warp-FFT, mixed radix 28"), (1536, 1536, 2, 20000, "N=1536 warp-FFT, mixed radix 24"),
+                                       (896, 896, 2, 34284, "N=896 warp-FFT, mixed radix 14, 2 sequences per warp"),
+                                       (768, 768, 2, 40000, "N=768 warp-FFT, mixed radix 12, 2 sequences per warp"),
+                                       (640, 640, 2, 48000, "N=640 warp-FFT, mixed radix 10, 3 sequences per warp"),
+                                       (448, 448, 2, 68568, "N=448 warp-FFT, mixed radix 7, 4 sequences per warp"),
+                                       (384, 384, 2, 80000, "N=384 warp-FFT, mixed radix 6, 5 sequences per warp"),
+                                       (320, 320, 2, 96000, "N=320 warp-FFT, mixed radix 5, 6 sequences per warp"),
+                                       (192, 192, 2, 160000, "N=192 warp-FFT, mixed radix 3, 10 sequences per warp"),
                                        (2000, 2000, 2, 15000, "N=2000 generic (lossless size)"))[:limit]:
+        if only and only not in tag:
+            continue
         d_pcm, _ = pcm_dev(frames, n, hop, ch)
         ncoef = frames * n * ch
         d_pay = ctx.dev(ncoef * 4); d_peak = ctx.dev(frames * 8); d_out = ctx.dev(ncoef * 8)
@@ -68,7 +78,7 @@ def transforms(limit=None):
                   ncoef * 8, f"p4 encode f32->be32 [{tag}]")
             timed(lambda: ctx.check(L.frad_p4_decode_dev(ctx.handle, d_pay.ptr, n * ch * 4, frames, n, ch, 32, 0, d_out.ptr, _abi.F64)),
                   ncoef * 12, f"p4 decode be32->f64 [{tag}]")
-        if n in (2048, 1024, 512, 256, 128, 4096, 1280):
+        if n in (2048, 1024, 512, 256, 128, 4096) or "mixed radix" in tag:
             d_q = ctx.dev(ncoef * 4); d_tq = ctx.dev(frames * 27 * ch * 4)
             timed(lambda: ctx.check(L.frad_p1_encode_dev(ctx.handle, d_pcm.ptr, _abi.F32, hop, frames, n, ch, 16, 48000, 0.5526315789473684, 0, d_q.ptr, d_tq.ptr, None)),
                   ncoef * 8, f"p1 encode f32->int32 [{tag}]")
@@ -168,6 +178,12 @@ if __name__ == "__main__":
         transforms()
     if which == "quick":                      # the three N = 2048 shapes only
         transforms(3)
+    if which == "mixed":                      # the mixed-radix frame lengths, then the same rows on the generic kernels
+        transforms(only="mixed radix")
+        ctx.set_option(_abi.OPT_FORCE_GENERIC, 1)
+        print(json.dumps({"note": "the same rows with FRAD_OPT_FORCE_GENERIC (shared-memory Stockham kernels)"}), flush=True)
+        transforms(only="mixed radix")
+        ctx.set_option(_abi.OPT_FORCE_GENERIC, 0)
     if which in ("all", "formats"):
         formats()
     if which in ("all", "bytes"):
