@@ -23,11 +23,17 @@ template <typename T> __device__ __forceinline__ int qposd(int k) {
 }
 __device__ __forceinline__ int tpos(int n) { return n + (n >> 5); }     // time-domain staging: one pad slot per 32 samples
 
-template <typename T, int S> struct decs_tail {
+// per-CTA tables behind the sequence buffers.  Each arithmetic type keeps only its own ramp form: with both, the f64 kernel at
+// S <= 2 (N >= 768) was 2.6 KB over three CTAs per SM
+template <typename T, int S> struct decs_tail {       // f32
   int lo[FRAD_NBANDS + 1];
-  double2 rp[FW][S][FRAD_NBANDS + 1];                 // per band: start, step of np.linspace (f64) / t0 / n, t1 / n as floats in .x (f32)
-  float4 bp[FW][S][FRAD_NBANDS + 1];
-  T dq[(sizeof(T) == 8) ? 256 : 1024];                // |q|^(4/3) / scale for small |q|
+  float4 bp[FW][S][FRAD_NBANDS + 1];                  // per band: t0 / n, t1 / n, lo, hi
+  T dq[1024];                                         // |q|^(4/3) / scale for small |q|
+};
+template <int S> struct decs_tail<double, S> {        // f64: exact np.linspace ramp
+  int lo[FRAD_NBANDS + 1];
+  double2 rp[FW][S][FRAD_NBANDS + 1];                 // per band: start, step
+  double dq[256];
 };
 
 __device__ __noinline__ double dequant_big_s(const double* __restrict__ dq64, int qa) {
