@@ -37,6 +37,9 @@ __device__ __forceinline__ float2 cmul_cs(float2 a, float c, float s) {
   return __ffma2_rn(make_float2(-a.y, a.x), make_float2(s, s), __fmul2_rn(a, make_float2(c, c)));
 }
 __device__ __forceinline__ float2 cscale(float2 a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
+// acc + v * c (c real): one FFMA2 for float2
+__device__ __forceinline__ float2 caxpy(float2 acc, float2 v, float c) { return __ffma2_rn(v, make_float2(c, c), acc); }
+__device__ __forceinline__ double2 caxpy(double2 acc, double2 v, double c) { acc.x = fma(v.x, c, acc.x); acc.y = fma(v.y, c, acc.y); return acc; }
 
 // ---- small DFTs, natural order in place; forward kernel exp(-2 pi i pq/R), inverse conjugated ----
 template <typename T, int R, bool INV> struct small_dft;
@@ -115,8 +118,8 @@ template <typename T, int R, bool INV> struct small_dft {
       for (int q = 1; q <= H; q++) {
         const T cc = (T)odd_roots<R>::c((p * q) % R);
         const T ss = (T)odd_roots<R>::s((p * q) % R);
-        a.x += cc * sp[q - 1].x; a.y += cc * sp[q - 1].y;
-        b.x += ss * sm[q - 1].x; b.y += ss * sm[q - 1].y;
+        a = caxpy(a, sp[q - 1], cc);
+        b = caxpy(b, sm[q - 1], ss);
       }
       // forward: y[p] = a - i b ; y[R-p] = a + i b   (inverse swaps)
       V mib = mul_mi<INV>(b);

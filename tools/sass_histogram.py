@@ -17,7 +17,10 @@ WANT = [("enc2048r_kernelIfLi1ELi2E", "enc2048r_kernel<float, 1, 2>   p1 encode,
         ("dec2048_kernelIfLi1ELi2E", "dec2048_kernel<float, 1, 2>    p1 decode, f32"),
         ("dec2048_kernelIdLi0ELi2E", "dec2048_kernel<double, 0, 2>   p0 decode, f64"),
         ("encs_kernelIfLi1ELi16E", "encs_kernel<float, 1, 16>      p1 encode, N = 1024 (2 sequences per warp)"),
-        ("decs_kernelIdLi1ELi16E", "decs_kernel<double, 1, 16>     p1 decode, N = 1024, f64")]
+        ("decs_kernelIdLi1ELi16E", "decs_kernel<double, 1, 16>     p1 decode, N = 1024, f64"),
+        ("encs_kernelIfLi1ELi20E", "encs_kernel<float, 1, 20>      p1 encode, N = 1280 (mixed radix 5 x 4, one sequence per warp)"),
+        ("decs_kernelIfLi1ELi20E", "decs_kernel<float, 1, 20>      p1 decode, N = 1280, f32"),
+        ("encs_kernelIfLi1ELi7E", "encs_kernel<float, 1, 7>       p1 encode, N = 448 (radix 7, four sequences per warp)")]
 names = subprocess.run(["cuobjdump", "-elf", LIB], capture_output=True, text=True).stdout
 syms = sorted(set(re.findall(r"_ZN[0-9A-Za-z_]+", names)))
 for key, title in WANT:
