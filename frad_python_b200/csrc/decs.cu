@@ -87,7 +87,22 @@ decs_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restrict_
     const int nseq = nf * C;
     __syncthreads();
     // ---- staging: the tile's frames in memory order; word of (frame f, bin k, channel c) -> sequence slot f C + c ----
-    if (PROFILE != 0 || p0_words) {
+    if ((PROFILE != 0 || p0_words) && C == 2) {
+      // stereo: a 16-byte vector is bins k0, k0 + 1 of both channels -- two 8-byte stores, every divisor a compile-time constant
+      constexpr int VPF = NN / 2;
+      for (int e4 = tid; e4 < nf * VPF; e4 += FW * 32) {
+        const int f = e4 / VPF, k0 = 2 * (e4 - f * VPF);
+        const uint32_t* src = (PROFILE == 0) ? (const uint32_t*)(P.payload + (size_t)(b0 + f) * P.payload_stride)
+                                             : (const uint32_t*)(P.q + (size_t)(b0 + f) * NN * 2);
+        const uint4 x = ldg_stream((const uint4*)(src + 2 * k0));
+        const int q0 = 2 * f, q1 = q0 + 1;
+        uint32_t* bq0 = (uint32_t*)(seq_all + (size_t)(q0 / S) * DSEQ) + (size_t)(q0 % S) * SEQ_T * (sizeof(T) / 4);
+        uint32_t* bq1 = (uint32_t*)(seq_all + (size_t)(q1 / S) * DSEQ) + (size_t)(q1 % S) * SEQ_T * (sizeof(T) / 4);
+        const int pk = qposd<T>(k0);                       // even, and bin k0 + 1 is the next word
+        *(uint2*)(bq0 + pk) = make_uint2(x.x, x.z);
+        *(uint2*)(bq1 + pk) = make_uint2(x.y, x.w);
+      }
+    } else if (PROFILE != 0 || p0_words) {
       for (int e4 = tid; e4 < nf * (NN * C / 4); e4 += FW * 32) {
         const int f = e4 / (NN * C / 4), vi = 4 * (e4 - f * (NN * C / 4));
         const uint32_t* src = (PROFILE == 0) ? (const uint32_t*)(P.payload + (size_t)(b0 + f) * P.payload_stride)
@@ -279,13 +294,24 @@ decs_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restrict_
     }
     __syncthreads();
     // ---- cooperative, coalesced store of PCM [n][c] ----
-    for (int e4 = tid; e4 < nf * (NN * C / 4); e4 += FW * 32) {
-      const int f = e4 / (NN * C / 4), vi = 4 * (e4 - f * (NN * C / 4));
+    const int vpf = (C == 2) ? NN / 2 : NN * C / 4;         // 16-byte output vectors per frame
+    for (int e4 = tid; e4 < nf * vpf; e4 += FW * 32) {
+      int f, vi;
       T o4[4];
+      if (C == 2) {                                          // samples n0, n0 + 1 of both channels; constant divisors
+        f = e4 / (NN / 2); vi = 4 * (e4 - f * (NN / 2));
+        const int q0 = 2 * f, q1 = q0 + 1;
+        const T* t0 = (const T*)(seq_all + (size_t)(q0 / S) * DSEQ) + (size_t)(q0 % S) * SEQ_T;
+        const T* t1 = (const T*)(seq_all + (size_t)(q1 / S) * DSEQ) + (size_t)(q1 % S) * SEQ_T;
+        const int pn = tpos(vi >> 1);                        // n0 is even: n0 + 1 lies in the same group of 32
+        o4[0] = t0[pn]; o4[1] = t1[pn]; o4[2] = t0[pn + 1]; o4[3] = t1[pn + 1];
+      } else {
+        f = e4 / vpf; vi = 4 * (e4 - f * vpf);
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        int n, c; split_c(vi + j, C, n, c); const int q = f * C + c;
-        o4[j] = ((const T*)(seq_all + (size_t)(q / S) * DSEQ))[(size_t)(q % S) * SEQ_T + tpos(n)];
+        for (int j = 0; j < 4; j++) {
+          int n, c; split_c(vi + j, C, n, c); const int q = f * C + c;
+          o4[j] = ((const T*)(seq_all + (size_t)(q / S) * DSEQ))[(size_t)(q % S) * SEQ_T + tpos(n)];
+        }
       }
       const size_t woff = (size_t)(b0 + f) * NN * C + vi;
       if (P.pcm_dtype == FRAD_F64) {

@@ -867,10 +867,21 @@ encs_kernel(enc_params P, plan_dev pl, const typename vec2<T>::type* __restrict_
     __syncthreads();
     // ---- cooperative store: value e = k*C + c of frame f <- sequence slot f*C + c, four consecutive values per thread ----
     const bool words = (PROFILE != 0) || p0_words;
-    for (int e4 = tid; e4 < nf * (NN * C / 4); e4 += FW * 32) {
-      const int f = e4 / (NN * C / 4), vi = 4 * (e4 - f * (NN * C / 4));      // first of four consecutive values of frame f
+    const int vpf = (C == 2) ? NN / 2 : NN * C / 4;        // 16-byte output vectors per frame
+    for (int e4 = tid; e4 < nf * vpf; e4 += FW * 32) {
+      int f, vi;                                           // vi: first of four consecutive values of frame f
       uint32_t ow[4];
       T ov[4];
+      if (C == 2 && words) {                               // bins k0, k0 + 1 of both channels: two 8-byte loads, constant divisors
+        f = e4 / (NN / 2); vi = 4 * (e4 - f * (NN / 2));
+        const int q0 = 2 * f, q1 = q0 + 1, k0 = vi >> 1;
+        const uint32_t* bq0 = (const uint32_t*)(seq_all + (size_t)(q0 / S) * ESEQ) + (size_t)(q0 % S) * SEQ_T * (sizeof(T) / 4);
+        const uint32_t* bq1 = (const uint32_t*)(seq_all + (size_t)(q1 / S) * ESEQ) + (size_t)(q1 % S) * SEQ_T * (sizeof(T) / 4);
+        const int pk = (PROFILE == 0) ? xpos(k0) : qpos<T>(k0);
+        const uint2 a = *(const uint2*)(bq0 + pk), bb = *(const uint2*)(bq1 + pk);
+        ow[0] = a.x; ow[1] = bb.x; ow[2] = a.y; ow[3] = bb.y;
+      } else {
+      f = e4 / vpf; vi = 4 * (e4 - f * vpf);
 #pragma unroll
       for (int j = 0; j < 4; j++) {
         int k, c; split_c(vi + j, C, k, c); const int q = f * C + c;
@@ -880,6 +891,7 @@ encs_kernel(enc_params P, plan_dev pl, const typename vec2<T>::type* __restrict_
         } else {
           ov[j] = ((const T*)(seq_all + (size_t)(q / S) * ESEQ))[(size_t)(q % S) * SEQ_T + xpos(k)];
         }
+      }
       }
       if (words) {
         uint32_t* dst = (PROFILE == 0) ? (uint32_t*)(P.payload + (size_t)(b0 + f) * P.payload_stride) : (uint32_t*)(P.q + (size_t)(b0 + f) * NN * C);
