@@ -102,6 +102,17 @@ decs_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restrict_
         *(uint2*)(bq0 + pk) = make_uint2(x.x, x.z);
         *(uint2*)(bq1 + pk) = make_uint2(x.y, x.w);
       }
+    } else if ((PROFILE != 0 || p0_words) && C == 1) {
+      // mono: a 16-byte vector is four consecutive bins of one sequence (their words stay together in the padded layouts)
+      constexpr int VPF = NN / 4;
+      for (int e4 = tid; e4 < nf * VPF; e4 += FW * 32) {
+        const int f = e4 / VPF, k0 = 4 * (e4 - f * VPF);
+        const uint32_t* src = (PROFILE == 0) ? (const uint32_t*)(P.payload + (size_t)(b0 + f) * P.payload_stride)
+                                             : (const uint32_t*)(P.q + (size_t)(b0 + f) * NN);
+        const uint4 x = ldg_stream((const uint4*)(src + k0));
+        uint32_t* bq = (uint32_t*)(seq_all + (size_t)(f / S) * DSEQ) + (size_t)(f % S) * SEQ_T * (sizeof(T) / 4);
+        *(uint4*)(bq + qposd<T>(k0)) = x;
+      }
     } else if (PROFILE != 0 || p0_words) {
       for (int e4 = tid; e4 < nf * (NN * C / 4); e4 += FW * 32) {
         const int f = e4 / (NN * C / 4), vi = 4 * (e4 - f * (NN * C / 4));
@@ -294,7 +305,7 @@ decs_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restrict_
     }
     __syncthreads();
     // ---- cooperative, coalesced store of PCM [n][c] ----
-    const int vpf = (C == 2) ? NN / 2 : NN * C / 4;         // 16-byte output vectors per frame
+    const int vpf = (C == 2) ? NN / 2 : (C == 1) ? NN / 4 : NN * C / 4;         // 16-byte output vectors per frame
     for (int e4 = tid; e4 < nf * vpf; e4 += FW * 32) {
       int f, vi;
       T o4[4];
@@ -305,6 +316,10 @@ decs_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restrict_
         const T* t1 = (const T*)(seq_all + (size_t)(q1 / S) * DSEQ) + (size_t)(q1 % S) * SEQ_T;
         const int pn = tpos(vi >> 1);                        // n0 is even: n0 + 1 lies in the same group of 32
         o4[0] = t0[pn]; o4[1] = t1[pn]; o4[2] = t0[pn + 1]; o4[3] = t1[pn + 1];
+      } else if (C == 1) {                                   // four consecutive samples of one sequence (same group of 32)
+        f = e4 / (NN / 4); vi = 4 * (e4 - f * (NN / 4));
+        const T* t0 = (const T*)(seq_all + (size_t)(f / S) * DSEQ) + (size_t)(f % S) * SEQ_T + tpos(vi);
+        o4[0] = t0[0]; o4[1] = t0[1]; o4[2] = t0[2]; o4[3] = t0[3];
       } else {
         f = e4 / vpf; vi = 4 * (e4 - f * vpf);
 #pragma unroll

@@ -629,12 +629,11 @@ encs_kernel(enc_params P, plan_dev pl, const typename vec2<T>::type* __restrict_
       for (int e4 = tid; e4 < nf * (NN / 2); e4 += FW * 32) {           // 16 bytes = samples n, n + 1 of both channels
         const int f = e4 / (NN / 2), n = 2 * (e4 - f * (NN / 2));
         const uint4 x = ldg_stream((const uint4*)((const float*)P.pcm + ((size_t)(b0 + f) * P.hop + n) * 2));
-        const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int q = 2 * f + (j & 1);
-          ((uint32_t*)(seq_all + (size_t)(q / S) * ESEQ))[zslot(n + (j >> 1), q % S)] = xs[j];
-        }
+        const int q0 = 2 * f, q1 = q0 + 1;
+        uint32_t* bq0 = (uint32_t*)(seq_all + (size_t)(q0 / S) * ESEQ) + 2 * 33 * R1 * (q0 % S);
+        uint32_t* bq1 = (uint32_t*)(seq_all + (size_t)(q1 / S) * ESEQ) + 2 * 33 * R1 * (q1 % S);
+        const int z0 = zslot(n, 0), z1 = zslot(n + 1, 0);              // the slot inside a sequence is the same for both channels
+        bq0[z0] = x.x; bq1[z0] = x.y; bq0[z1] = x.z; bq1[z1] = x.w;
       }
     } else {
       for (int e = tid; e < nf * NN * C; e += FW * 32) {
@@ -867,7 +866,7 @@ encs_kernel(enc_params P, plan_dev pl, const typename vec2<T>::type* __restrict_
     __syncthreads();
     // ---- cooperative store: value e = k*C + c of frame f <- sequence slot f*C + c, four consecutive values per thread ----
     const bool words = (PROFILE != 0) || p0_words;
-    const int vpf = (C == 2) ? NN / 2 : NN * C / 4;        // 16-byte output vectors per frame
+    const int vpf = (C == 2) ? NN / 2 : (C == 1) ? NN / 4 : NN * C / 4;        // 16-byte output vectors per frame
     for (int e4 = tid; e4 < nf * vpf; e4 += FW * 32) {
       int f, vi;                                           // vi: first of four consecutive values of frame f
       uint32_t ow[4];
@@ -880,6 +879,11 @@ encs_kernel(enc_params P, plan_dev pl, const typename vec2<T>::type* __restrict_
         const int pk = (PROFILE == 0) ? xpos(k0) : qpos<T>(k0);
         const uint2 a = *(const uint2*)(bq0 + pk), bb = *(const uint2*)(bq1 + pk);
         ow[0] = a.x; ow[1] = bb.x; ow[2] = a.y; ow[3] = bb.y;
+      } else if (C == 1 && words) {                        // mono: four consecutive bins, one 16-byte load
+        f = e4 / (NN / 4); vi = 4 * (e4 - f * (NN / 4));
+        const uint32_t* bq = (const uint32_t*)(seq_all + (size_t)(f / S) * ESEQ) + (size_t)(f % S) * SEQ_T * (sizeof(T) / 4);
+        const uint4 a = *(const uint4*)(bq + ((PROFILE == 0) ? xpos(vi) : qpos<T>(vi)));
+        ow[0] = a.x; ow[1] = a.y; ow[2] = a.z; ow[3] = a.w;
       } else {
       f = e4 / vpf; vi = 4 * (e4 - f * vpf);
 #pragma unroll
