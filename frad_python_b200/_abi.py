@@ -77,6 +77,7 @@ def lib():
             "frad_memset_dev": (i32, [vp, vp, i32, sz]),
             "frad_event_record": (i32, [vp, i32]),
             "frad_event_elapsed_ms": (i32, [vp, i32, i32, C.POINTER(C.c_float)]),
+            "frad_frame_length_class": (i32, [i32]),
             "frad_p0_payload_bytes": (sz, [i32, i32, i32]),
             "frad_p0_encode_dev": (i32, [vp, vp, i32, i64, i32, i32, i32, i32, i32, i32, vp, sz, vp]),
             "frad_p0_decode_dev": (i32, [vp, vp, sz, i32, i32, i32, i32, i32, i32, vp, i32]),
@@ -132,7 +133,7 @@ def lib():
 EXPORTS = [
     "frad_ctx_create", "frad_ctx_destroy", "frad_last_error", "frad_sync", "frad_stream", "frad_device_count",
     "frad_device_pci_bus_id",
-    "frad_sm_count", "frad_kernel_launches", "frad_set_option", "frad_host_alloc", "frad_host_free", "frad_host_register", "frad_host_unregister", "frad_dev_alloc", "frad_dev_free",
+    "frad_sm_count", "frad_kernel_launches", "frad_set_option", "frad_frame_length_class", "frad_host_alloc", "frad_host_free", "frad_host_register", "frad_host_unregister", "frad_dev_alloc", "frad_dev_free",
     "frad_h2d", "frad_d2h", "frad_memset_dev", "frad_event_record", "frad_event_elapsed_ms",
     "frad_p0_payload_bytes", "frad_p0_encode_dev", "frad_p0_decode_dev", "frad_p0_encode", "frad_p0_decode",
     "frad_p4_encode_dev", "frad_p4_decode_dev", "frad_p4_encode", "frad_p4_decode",

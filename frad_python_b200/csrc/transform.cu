@@ -1305,6 +1305,14 @@ static int launch_decode(frad_ctx* ctx, dec_params& P, int prec) {
 // ------------------------------------------------------------------------------------------------
 static bool p0_bits_ok(int bits) { return bits == 12 || bits == 16 || bits == 24 || bits == 32 || bits == 48 || bits == 64; }
 
+extern "C" int frad_frame_length_class(int N) {
+#ifdef FRAD_HAVE_FAST2048
+  if (N == 2048) return 2;
+  if (frad_warp_r1(N)) return 1;
+#endif
+  return 0;
+}
+
 extern "C" size_t frad_p0_payload_bytes(int N, int C, int bits) {
   size_t nv = (size_t)N * (size_t)C;
   if (bits == 12) return (nv * 3 + 1) / 2;

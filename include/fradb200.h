@@ -74,9 +74,16 @@ int  frad_sm_count(frad_ctx* ctx);
 uint64_t frad_kernel_launches(frad_ctx* ctx);    /* kernels launched through this ctx so far */
 
 /* test / diagnostic switches (default 0): results must not depend on them beyond the stated tolerances */
-enum { FRAD_OPT_FORCE_GENERIC = 1,   /* bypass the N = 2048 fast kernels */
+enum { FRAD_OPT_FORCE_GENERIC = 1,   /* bypass the warp-FFT kernels (N = 2048 and the other N = 64 R1 lengths): generic kernels only */
        FRAD_OPT_EXACT_QUANT = 2 };   /* profile-1 quantiser: always evaluate the f64 formula */
 int  frad_set_option(frad_ctx* ctx, int option, int value);
+
+/* Which transform kernels a frame length runs on (needs no context or device): 2 = the N = 2048 kernels (the reference's default
+ * frame, src/tools/cli.py:26), 1 = the multi-sequence warp-FFT kernels (N = 64 R1 < 2048 with R1 a power of two or one of 3, 5, 6,
+ * 7, 10, 12, 14, 20, 24, 28: fourteen of the compact sizes of fourier/profiles.py:14-23), 0 = the generic shared-memory kernels
+ * (every other length the reference accepts: same results, lower throughput).  Channel counts that do not divide a tile of
+ * class 1, profile 2 at class 1 and misaligned buffers also take the generic kernels. */
+int  frad_frame_length_class(int N);
 
 void* frad_host_alloc(frad_ctx* ctx, size_t bytes);   /* pinned host memory, NULL on failure */
 void  frad_host_free(frad_ctx* ctx, void* p);

@@ -24,6 +24,21 @@ def test_library_exports_every_declared_symbol():
     assert declared <= set(_abi.EXPORTS) | {"frad_ctx"}, sorted(declared - set(_abi.EXPORTS))
 
 
+def test_frame_length_classes_cover_the_compact_table():
+    """frad_frame_length_class (no device needed): the default frame on its own kernels, fourteen of the fifteen other compact
+    sizes below it of fourier/profiles.py:14-23 on the multi-sequence warp kernels, everything else generic."""
+    from frad_python_b200 import _abi
+    from frad_python_b200.fourier.profiles import compact
+    L = _abi.lib()
+    cls = {n: L.frad_frame_length_class(n) for n in compact.SAMPLES}
+    assert cls[2048] == 2
+    warp = sorted(n for n, c in cls.items() if c == 1)
+    assert warp == [128, 192, 256, 320, 384, 448, 512, 640, 768, 896, 1024, 1280, 1536, 1792]
+    assert sorted(n for n, c in cls.items() if c == 0) == [160, 224] + [n for n in compact.SAMPLES if n > 2048]
+    for n in (0, -64, 2000, 2047, 64, 1088, 4096, 1 << 20):        # not N = 64 R1 with a supported R1
+        assert L.frad_frame_length_class(n) == 0, n
+
+
 def test_no_cpu_fallback_without_gpu():
     import torch
     if torch.cuda.is_available():
