@@ -1,4 +1,4 @@
-// Decoder for the frame lengths N = 64 R1 < 2048 (R1 = 16, 8, 4: N = 1024, 512, 256 of fourier/profiles.py:14-23): S = 32 / R1
+// Decoder for the frame lengths N = 64 R1 < 2048 (R1 = 16, 8, 4, 2: N = 1024 ... 128 of fourier/profiles.py:14-23; the mixed radices below): S = 32 / R1
 // sequences per warp, the mirror image of enc2048.cu's small-frame encoder.
 //
 //   staging    the tile's 32-bit words (quantised ints / profile-0 values) are copied to shared memory in memory order

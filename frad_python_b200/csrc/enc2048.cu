@@ -553,7 +553,7 @@ enc2048r_kernel(enc_params P, plan_dev pl, const typename vec2<T>::type* __restr
 
 
 // ------------------------------------------------------------------------------------------------------------------------
-// Frame lengths N = 64 R1 < 2048 (R1 = 16, 8, 4: N = 1024, 512, 256 of the compact table, fourier/profiles.py:14-23): the same
+// Frame lengths N = 64 R1 < 2048 (R1 = 16, 8, 4, 2: N = 1024 ... 128 of the compact table, fourier/profiles.py:14-23; mixed radices below): the same
 // kernel with S = 32 / R1 sequences per warp.  Lane L = s R1 + k1 of a warp works on sequence s: in the first FFT pass it
 // transforms R1 points, after the exchange it holds Z_s[k1 + R1 o] (fft32.cuh: fft_multi_warp), and in the epilogue it owns the
 // 64 contiguous bins [64 k1, 64 k1 + 64) of its sequence -- which in the padded layout start at word 68 L of the warp buffer,
