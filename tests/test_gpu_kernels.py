@@ -633,6 +633,37 @@ def test_small_frame_warp_kernels_match_generic_path_and_oracle(ctx, n, c):
     assert np.max(np.abs(outs[0][0][1] - O.p0_digital(a[0][1].tobytes(), 3, c, False))) <= 1e-13
 
 
+@pytest.mark.parametrize("n,c", [(512, 2), (640, 2), (1792, 1), (448, 2), (1280, 4)])
+def test_small_frame_warp_kernels_every_profile0_depth(ctx, n, c):
+    """The small-frame warp kernels pack and unpack all six profile-0 depths themselves (profile0.py:28-42, 51-66), both byte
+    orders: A/B against the generic kernels on identical input, decode of identical payloads."""
+    from frad_python_b200 import _abi
+    pcm = O.synth_pcm(n * 21 / 48000 + 0.01, 48000, c, seed=90 + n + c)[: n * 21]
+    nb = len(pcm) // n
+    for bits in (12, 16, 24, 32, 48, 64):
+        for le in (False, True):
+            if bits == 12 and le:
+                continue                                  # 12-bit values are always big-endian nibbles
+            fast, pk_f, _ = ctx.p0_encode(pcm, nb, n, n, bits, le)
+            ctx.set_option(_abi.OPT_FORCE_GENERIC, 1)
+            try:
+                gen, pk_g, _ = ctx.p0_encode(pcm, nb, n, n, bits, le)
+                d_gen = ctx.p0_decode(fast, nb, n, c, bits, le)
+            finally:
+                ctx.set_option(_abi.OPT_FORCE_GENERIC, 0)
+            assert fast.shape == gen.shape, (bits, le)
+            vf, vg = values(fast.tobytes(), bits, le), values(gen.tobytes(), bits, le)
+            ulp = {12: 2.0 ** -7, 16: 2.0 ** -10, 24: 2.0 ** -15, 32: 2.0 ** -23, 48: 2.0 ** -36, 64: 2.0 ** -52}[bits]
+            assert np.max(np.abs(vf - vg)) <= TOL_F32 + ulp * np.max(np.abs(vg)), (bits, le)
+            assert np.max(np.abs(pk_f - pk_g)) <= 1e-6
+            d_fast = ctx.p0_decode(fast, nb, n, c, bits, le)
+            d_f32 = ctx.p0_decode(fast, nb, n, c, bits, le, prec=_abi.PREC_F32)
+            assert np.max(np.abs(d_fast - d_gen)) <= 1e-13 and np.max(np.abs(d_f32 - d_gen)) <= 2.0 ** -15, (bits, le)
+    want = values(O.p0_analogue(pcm[:n], 24, 48000, False)[0], 24, False)
+    got = values(ctx.p0_encode(pcm, nb, n, n, 24, False)[0][0].tobytes(), 24, False)
+    assert np.max(np.abs(got - want)) <= TOL_F32 + 2.0 ** -15 * np.max(np.abs(want))
+
+
 def test_rs_results_repeat_under_interleaved_calls(ctx):
     """Every repetition of the Reed-Solomon calls -- interleaved with transform, bit-coder and CRC calls on the same context,
     first use of each code's table included -- reproduces the first result.  (Round 2 found a first-use race of the device
