@@ -626,14 +626,32 @@ encs_kernel(enc_params P, plan_dev pl, const typename vec2<T>::type* __restrict_
     __syncthreads();
     // ---- staging: the tile's frames in memory order (frame, sample, channel) ----
     if (vec_in) {
-      for (int e4 = tid; e4 < nf * (NN / 2); e4 += FW * 32) {           // 16 bytes = samples n, n + 1 of both channels
-        const int f = e4 / (NN / 2), n = 2 * (e4 - f * (NN / 2));
-        const uint4 x = ldg_stream((const uint4*)((const float*)P.pcm + ((size_t)(b0 + f) * P.hop + n) * 2));
-        const int q0 = 2 * f, q1 = q0 + 1;
-        uint32_t* bq0 = (uint32_t*)(seq_all + (size_t)(q0 / S) * ESEQ) + 2 * 33 * R1 * (q0 % S);
-        uint32_t* bq1 = (uint32_t*)(seq_all + (size_t)(q1 / S) * ESEQ) + 2 * 33 * R1 * (q1 % S);
-        const int z0 = zslot(n, 0), z1 = zslot(n + 1, 0);              // the slot inside a sequence is the same for both channels
-        bq0[z0] = x.x; bq1[z0] = x.y; bq0[z1] = x.z; bq1[z1] = x.w;
+      // 16 bytes = samples n, n + 1 of both channels.  S >= 3 (N <= 640): four vectors per thread are requested before the first
+      // is scattered (p0 encode at N = 640: 0.245 -> 0.182 ms); measured slower by 4-7 % at S <= 2, and in the decoder everywhere
+      constexpr int UB = (S >= 3) ? 4 : 1;
+      const int total = nf * (NN / 2);
+      for (int e0 = tid; e0 < total; e0 += FW * 32 * UB) {
+        uint4 x[UB];
+#pragma unroll
+        for (int u = 0; u < UB; u++) {
+          const int e4 = e0 + u * FW * 32;
+          if (e4 < total) {
+            const int f = e4 / (NN / 2), n = 2 * (e4 - f * (NN / 2));
+            x[u] = ldg_stream((const uint4*)((const float*)P.pcm + ((size_t)(b0 + f) * P.hop + n) * 2));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UB; u++) {
+          const int e4 = e0 + u * FW * 32;
+          if (e4 < total) {
+            const int f = e4 / (NN / 2), n = 2 * (e4 - f * (NN / 2));
+            const int q0 = 2 * f, q1 = q0 + 1;
+            uint32_t* bq0 = (uint32_t*)(seq_all + (size_t)(q0 / S) * ESEQ) + 2 * 33 * R1 * (q0 % S);
+            uint32_t* bq1 = (uint32_t*)(seq_all + (size_t)(q1 / S) * ESEQ) + 2 * 33 * R1 * (q1 % S);
+            const int z0 = zslot(n, 0), z1 = zslot(n + 1, 0);          // the slot inside a sequence is the same for both channels
+            bq0[z0] = x[u].x; bq1[z0] = x[u].y; bq0[z1] = x[u].z; bq1[z1] = x[u].w;
+          }
+        }
       }
     } else {
       for (int e = tid; e < nf * NN * C; e += FW * 32) {
