@@ -174,6 +174,22 @@ decs_kernel(dec_params P, plan_dev pl, const typename vec2<T>::type* __restrict_
       }
     }
     __syncthreads();
+    {   // pull the next tile of this CTA towards L2 while the current one is transformed (its staging loads are one per iteration)
+      const int nt = tile + gridDim.x;
+      if (nt < ntiles) {
+        const int nb0 = nt * fpt, nnf = min(fpt, P.B - nb0);
+        const char* base;
+        size_t bytes;
+        if (PROFILE == 0) {
+          base = (const char*)(P.payload + (size_t)nb0 * P.payload_stride);
+          bytes = (size_t)(nnf - 1) * P.payload_stride + (size_t)NN * C * P.bits / 8;
+        } else {
+          base = (const char*)(P.q + (size_t)nb0 * NN * C);
+          bytes = (size_t)nnf * NN * C * 4;
+        }
+        for (size_t o = (size_t)tid * 128; o < bytes; o += (size_t)FW * 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + o));
+      }
+    }
     if (w * S < nseq) {
       const int q_me = w * S + sl;
       V* buf = seq_all + (size_t)w * DSEQ;

@@ -661,6 +661,16 @@ encs_kernel(enc_params P, plan_dev pl, const typename vec2<T>::type* __restrict_
       }
     }
     __syncthreads();
+    {   // pull the next tile of this CTA towards L2 while the current one is transformed
+      const int nt = tile + gridDim.x;
+      if (nt < ntiles) {
+        const int nb0 = nt * fpt, nnf = min(fpt, P.B - nb0);
+        const size_t es = (size_t)pcm_size(P.pcm_dtype);
+        const char* base = (const char*)P.pcm + (size_t)nb0 * P.hop * C * es;
+        const size_t bytes = ((size_t)(nnf - 1) * P.hop + NN) * C * es;
+        for (size_t o = (size_t)tid * 128; o < bytes; o += (size_t)FW * 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + o));
+      }
+    }
     if (w * S < nseq) {
       const int q_me = w * S + sl;                       // my sequence slot in the tile
       const bool live = act && q_me < nseq;              // lanes of slots beyond the batch compute on stale data and store nothing global
