@@ -314,6 +314,15 @@ __global__ void __launch_bounds__(MAXT) seq_encode_kernel(enc_params P, plan_dev
   const int nseq = P.B * P.C;
   for (int s = blockIdx.x; s < nseq; s += gridDim.x) {
     const int b = s / P.C, c = s % P.C;
+    {   // pull the frame of this CTA's next sequence towards L2 (its samples are fetched one scalar load at a time)
+      const int s2 = s + gridDim.x;
+      if (s2 < nseq && (s2 / P.C) != b) {
+        const size_t es = (size_t)pcm_size(P.pcm_dtype);
+        const char* nxt = (const char*)P.pcm + (size_t)(s2 / P.C) * P.hop * P.C * es;
+        const size_t bytes = (size_t)pl.N * P.C * es;
+        for (size_t o = (size_t)threadIdx.x * 128; o < bytes; o += (size_t)blockDim.x * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + o));
+      }
+    }
     T* X = forward_sequence<T>(P, pl, b, c, bufA, bufB);
     if (P.profile == 0) p0_epilogue<T>(P, X, pl.N, b, c, bw);
     else p1_epilogue<T>(P, X, pl.N, b, c, bw, blockIdx.x);
@@ -346,6 +355,15 @@ __global__ void __launch_bounds__(MAXT) seq_decode_kernel(dec_params P, plan_dev
   const int nseq = P.B * P.C;
   for (int s = blockIdx.x; s < nseq; s += gridDim.x) {
     const int b = s / P.C, c = s % P.C;
+    {   // pull the coded frame of this CTA's next sequence towards L2
+      const int s2 = s + gridDim.x;
+      if (s2 < nseq && (s2 / P.C) != b) {
+        const char* nxt = (P.profile == 0) ? (const char*)(P.payload + (size_t)(s2 / P.C) * P.payload_stride)
+                                           : (const char*)(P.q + (size_t)(s2 / P.C) * pl.N * P.C);
+        const size_t bytes = (P.profile == 0) ? (size_t)pl.N * P.C * P.bits / 8 : (size_t)pl.N * P.C * 4;
+        for (size_t o = (size_t)threadIdx.x * 128; o < bytes; o += (size_t)blockDim.x * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + o));
+      }
+    }
     T* X = (T*)bufA;
     if (P.profile == 0) p0_prologue<T>(P, X, pl.N, b, c);
     else p1_prologue<T>(P, X, pl.N, b, c, bw, blockIdx.x);
