@@ -68,52 +68,61 @@ class ASFH:
         head += encode_css_prf1(max(self.channels, 1), self.srate, self.fsize, True)
         return head + b"\x00"
 
+    # ---- parsing: length first, fields second --------------------------------------------------------------------------
+    # The header's length follows from its own prefix: 9 bytes tell the profile and the ECC flag, a compact header's 12 tell a
+    # force-flush marker (nothing follows), and an all-ones size field appends a 64-bit size.  `read` tops the buffer up to what
+    # the prefix asks for, asks again, and decodes every field in one pass once the length is final.
+    _WIDE_SIZE = b"\xff\xff\xff\xff"
+
+    def _span(self):
+        """(bytes this header needs as far as the buffered prefix can tell, True when that is the whole header)"""
+        have = self.buffer
+        if len(have) < 9:
+            return 9, False
+        if (have[8] >> 5) in COMPACT:
+            if len(have) < 12:
+                return 12, False
+            if have[10] & 1:                                   # force-flush bit of the css word
+                return 12, True
+            base = 16 if (have[8] >> 4) & 1 else 12
+        else:
+            base = 32
+        return base + (8 if have[4:8] == self._WIDE_SIZE else 0), True
+
     def fill_buffer(self, buffer: bytes, target_size: int):
+        """Tops the header buffer up to target_size bytes from `buffer`; returns (reached, rest of `buffer`)."""
+        take = max(target_size - len(self.buffer), 0)
+        self.buffer += buffer[:take]
         if len(self.buffer) < target_size:
-            need = target_size - len(self.buffer)
-            self.buffer += buffer[:need]
-            buffer = buffer[need:]
-            if len(self.buffer) < target_size:
-                return False, buffer
+            return False, buffer[take:]
         self.header_bytes = target_size
-        return True, buffer
+        return True, buffer[take:]
 
     def read(self, buffer: bytes):
-        ok, buffer = self.fill_buffer(buffer, 9)
-        if not ok:
-            return "Incomplete", buffer
-        self.frmbytes = struct.unpack(">I", self.buffer[4:8])[0]
-        self.profile, self.ecc, self.endian, self.bit_depth_index = decode_pfb(self.buffer[8:9])
-        if self.profile in COMPACT:
-            ok, buffer = self.fill_buffer(buffer, 12)
-            if not ok:
+        final = False
+        while not final:
+            want, final = self._span()
+            reached, buffer = self.fill_buffer(buffer, want)
+            if not reached:
                 return "Incomplete", buffer
-            self.channels, self.srate, self.fsize, flush = decode_css_prf1(self.buffer[9:11])
+            final = final and self._span() == (want, True)     # a longer prefix may ask for more
+        head = self.buffer
+        self.profile, self.ecc, self.endian, self.bit_depth_index = decode_pfb(head[8:9])
+        self.frmbytes = struct.unpack_from(">I", head, 4)[0]
+        if self.profile in COMPACT:
+            self.channels, self.srate, self.fsize, flush = decode_css_prf1(head[9:11])
             if flush:
                 return "ForceFlush", buffer
-            self.overlap_ratio = self.buffer[11]
-            if self.overlap_ratio != 0:
-                self.overlap_ratio += 1
+            self.overlap_ratio = head[11] + 1 if head[11] else 0
             if self.ecc:
-                ok, buffer = self.fill_buffer(buffer, 16)
-                if not ok:
-                    return "Incomplete", buffer
-                self.ecc_dsize, self.ecc_codesize = self.buffer[12], self.buffer[13]
-                self.crc = self.buffer[14:16]
+                self.ecc_dsize, self.ecc_codesize, self.crc = head[12], head[13], head[14:16]
         else:
-            ok, buffer = self.fill_buffer(buffer, 32)
-            if not ok:
-                return "Incomplete", buffer
-            self.channels = self.buffer[9] + 1
-            self.ecc_dsize, self.ecc_codesize = self.buffer[10], self.buffer[11]
-            self.srate = struct.unpack(">I", self.buffer[12:16])[0]
-            self.fsize = struct.unpack(">I", self.buffer[24:28])[0]
-            self.crc = self.buffer[28:32]
-        if self.frmbytes == 0xFFFFFFFF:
-            ok, buffer = self.fill_buffer(buffer, self.header_bytes + 8)
-            if not ok:
-                return "Incomplete", buffer
-            self.frmbytes = struct.unpack(">Q", self.buffer[-8:])[0]
+            chm1, self.ecc_dsize, self.ecc_codesize, self.srate = struct.unpack_from(">BBBI", head, 9)
+            self.channels = chm1 + 1
+            self.fsize = struct.unpack_from(">I", head, 24)[0]
+            self.crc = head[28:32]
+        if head[4:8] == self._WIDE_SIZE:
+            self.frmbytes = struct.unpack_from(">Q", head, self.header_bytes - 8)[0]
         self.all_set = True
         return "Complete", buffer
 

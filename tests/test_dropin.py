@@ -233,3 +233,56 @@ def test_repairer_force_flush_streams_on_the_device(g_streams):
             if not piece and rp.is_empty():
                 break
         assert out + rp.flush() == _with_flush_markers_of(g_streams["p1_ecc"].tobytes(), s)
+
+
+def test_frame_header_parser_matches_the_reference_on_any_chunking(reference_libfrad):
+    """tools/asfh.py parses length-first (its own design); the reference's ASFH.read (libfrad/tools/asfh.py) is incremental.
+    Same status, same unread remainder and same buffer after every call, same fields on Complete / ForceFlush -- every profile,
+    ECC on / off, the 64-bit size extension, force-flush markers, fed whole, byte by byte and in random pieces."""
+    import random
+    import struct
+    from frad_python_b200.tools.asfh import ASFH as Mine, encode_pfb, encode_css_prf1
+    Ref = reference_libfrad.tools.asfh.ASFH
+    rng = random.Random(7)
+    fields = ["frmbytes", "profile", "ecc", "endian", "bit_depth_index", "channels", "srate", "fsize", "ecc_dsize", "ecc_codesize",
+              "overlap_ratio", "crc", "header_bytes", "all_set", "buffer"]
+    sign = b"\xff\xd0\xd2\x97"
+    heads = []
+    for prof in (0, 1, 2, 4):
+        for ecc in (False, True):
+            for wide in (False, True):
+                size = 0xFFFFFFFF if wide else rng.randrange(1, 1 << 20)
+                h = sign + struct.pack(">I", size) + encode_pfb(prof, ecc, rng.random() < 0.5, rng.randrange(7))
+                if prof in (1, 2):
+                    h += encode_css_prf1(rng.randrange(1, 9), rng.choice([8000, 44100, 48000, 96000]), rng.choice([128, 1280, 2048, 28672]), False)
+                    h += bytes([rng.randrange(0, 255)])
+                    if ecc:
+                        h += bytes([rng.randrange(1, 255), rng.randrange(1, 255)]) + rng.randbytes(2)
+                else:
+                    h += (bytes([rng.randrange(0, 8), rng.randrange(1, 255), rng.randrange(1, 255)]) + struct.pack(">I", rng.randrange(1, 200000))
+                          + rng.randbytes(8) + struct.pack(">I", rng.randrange(1, 100000)) + rng.randbytes(4))
+                if wide:
+                    h += struct.pack(">Q", rng.randrange(1 << 33, 1 << 40))
+                heads.append(h)
+        if prof in (1, 2):
+            heads.append(sign + b"\x00" * 4 + encode_pfb(prof, rng.random() < 0.5, False, 3) + encode_css_prf1(2, 48000, 2048, True) + b"\x00")
+            heads.append(sign + b"\xff" * 4 + encode_pfb(prof, True, False, 3) + encode_css_prf1(2, 48000, 2048, True) + b"\x07")
+    calls = 0
+    for h in heads:
+        for trial in range(25):
+            data = h + rng.randbytes(rng.randrange(0, 20))
+            cuts = sorted(rng.sample(range(len(data) + 1), rng.randrange(0, 6)))
+            pieces = [data[a:b] for a, b in zip([0] + cuts, cuts + [len(data)])]
+            if trial == 0:
+                pieces = [data[i:i + 1] for i in range(len(data))]
+            a, b = Mine(), Ref()
+            for pc in pieces:
+                ra, rest_a = a.read(pc)
+                rb, rest_b = b.read(pc)
+                assert (ra, rest_a) == (rb, rest_b), (h.hex(), pc)
+                for f in (fields if ra != "Incomplete" else ["buffer", "all_set"]):
+                    assert getattr(a, f) == getattr(b, f), (f, h.hex(), ra)
+                calls += 1
+                if ra != "Incomplete":
+                    break
+    assert calls > 1000
