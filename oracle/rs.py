@@ -18,10 +18,15 @@ SURVEY.md F4 -- so this file restates its *published* algorithm):
 Any bounded-distance decoder gives identical bytes: success iff a codeword of the
 shortened code lies within floor(nsym/2) byte errors of the received word.
 
-PARITY UNPINNED by the reference (it has no RS vectors).  Pinned here by two public
-known-answer vectors (tests/test_oracle_rs.py): the QR-code example
+PARITY UNPINNED by the reference (it has no RS vectors).  Pinned here by public material
+(tests/test_oracle_golden.py): two known-answer vectors -- the QR-code example
 ``40 d2 75 47 76 17 32 06 27 26 96 c6 c6 96 70 ec`` -> parity
-``bc 2a 90 13 6b af ef fd 4b e0`` and ``RSCodec(10).encode(b'hello world')``.
+``bc 2a 90 13 6b af ef fd 4b e0`` and ``RSCodec(10).encode(b'hello world')`` --, the
+QR version 1-M "HELLO WORLD" codewords, the generator polynomials of the QR specification's
+tables (same field, alpha and fcr) against which the encoder is checked by an independent
+schoolbook division, and the decoder's bounded-distance limits.  The GPU encoder is checked
+by the code's definition as well (every word vanishes at alpha^0 .. alpha^(nsym-1)):
+tests/test_gpu_kernels.py::test_rs_encode_is_the_code_by_definition.
 """
 from __future__ import annotations
 
