@@ -121,6 +121,66 @@ def test_rs_correction_limits():
         R.correct_word(bytes(w), 24)
 
 
+def _gen_exponent_free(nsym: int):
+    """g(x) = prod (x - alpha^i), i = 0 .. nsym - 1, highest degree first, by plain polynomial multiplication."""
+    g = [1]
+    for i in range(nsym):
+        a = alpha_pow(i)
+        g = [x ^ gf_mul_plain(y, a) for x, y in zip(g + [0], [0] + g)]
+    return g
+
+
+def _parity_plain(msg: bytes, g) -> bytes:
+    nsym = len(g) - 1
+    rem = list(msg) + [0] * nsym
+    for i in range(len(msg)):
+        c = rem[i]
+        if c:
+            for j in range(1, nsym + 1):
+                rem[i + j] ^= gf_mul_plain(g[j], c)
+    return bytes(rem[len(msg):])
+
+
+def test_rs_decoder_is_the_bounded_distance_decoder_exhaustively_on_single_error_codes():
+    """What reedsolo's decoder does with any word (ecc.py:20-22: data of the codeword within nsym // 2 errors, ReedSolomonError
+    when there is none -- miscorrections included), decided by brute force for t = 1 codes: every word at Hamming distance <= 1 is
+    tried as a codeword by schoolbook division.  Independent of oracle/rs.py (no shared tables, no syndromes); covers shortened
+    words, where an error located in the absent prefix must be a failure, and odd nsym."""
+    rng = np.random.default_rng(11)
+    for nsym, k in ((2, 1), (2, 3), (3, 2), (3, 6), (2, 40), (3, 120)):
+        g = _gen_exponent_free(nsym)
+        assert [int(c) for c in R.generator_poly(nsym)] == g
+        n = k + nsym
+        # the remainder is linear in the data: parity(d + e u_pos) = parity(d) + e parity(u_pos)
+        unit = [_parity_plain(bytes([0] * pos + [1] + [0] * (k - pos - 1)), g) for pos in range(k)]
+        tally = {"ok": 0, "fail": 0, "miscorrect": 0}
+        for trial in range(60 if n < 50 else 25):
+            msg = rng.integers(0, 256, k, dtype=np.uint8).tobytes()
+            w = bytearray(msg + _parity_plain(msg, g))
+            ne = int(rng.integers(0, 4))
+            for pos in rng.choice(n, size=min(ne, n), replace=False):
+                w[pos] ^= int(rng.integers(1, 256))
+            # brute force: the codewords within distance 1 of w (at most one exists: minimum distance nsym + 1 >= 3)
+            diff = bytes(a ^ b for a, b in zip(_parity_plain(bytes(w[:k]), g), w[k:]))
+            near = []
+            if not any(diff) or sum(x != 0 for x in diff) == 1:          # a codeword, or one wrong parity byte
+                near.append(bytes(w[:k]))
+            for pos in range(k):                                         # one wrong data byte: every error value
+                for e in range(1, 256):
+                    if all(gf_mul_plain(e, u) == x for u, x in zip(unit[pos], diff)):
+                        near.append(bytes(w[:pos]) + bytes([w[pos] ^ e]) + bytes(w[pos + 1:k]))
+            assert len(near) <= 1
+            if near:
+                got, _ = R.correct_word(bytes(w), nsym)
+                assert got == near[0]
+                tally["ok" if near[0] == msg else "miscorrect"] += 1
+            else:
+                with pytest.raises(R.ReedSolomonError):
+                    R.correct_word(bytes(w), nsym)
+                tally["fail"] += 1
+        assert tally["ok"] and tally["fail"], (nsym, k, tally)
+
+
 def test_crc_golden(g_crc):
     for n in (0, 1, 9, 255, 4096, 20488):
         b = g_crc[f"crc_in_{n}"].tobytes()
