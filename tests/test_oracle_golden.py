@@ -181,6 +181,58 @@ def test_rs_decoder_is_the_bounded_distance_decoder_exhaustively_on_single_error
         assert tally["ok"] and tally["fail"], (nsym, k, tally)
 
 
+def test_rs_decoder_is_the_bounded_distance_decoder_exhaustively_on_double_error_codes():
+    """The same decision for t = 2 (nsym 4 and 5): every error pattern of weight <= 2 over the n positions of the (shortened)
+    word is tried, vectorised over the two error values with a multiplication table built here from gf_mul_plain."""
+    mul = np.array([[gf_mul_plain(a, b) for b in range(256)] for a in range(256)], np.uint8)
+    rng = np.random.default_rng(12)
+    ev = np.arange(1, 256)
+    for nsym, k in ((4, 1), (4, 3), (5, 5), (4, 24), (5, 40)):
+        g = _gen_exponent_free(nsym)
+        assert [int(c) for c in R.generator_poly(nsym)] == g
+        n = k + nsym
+        # col[j]: what a unit error at word position j adds to (parity of the received data) xor (received parity)
+        col = [np.frombuffer(_parity_plain(bytes([0] * pos + [1] + [0] * (k - pos - 1)), g), np.uint8) for pos in range(k)]
+        col += [np.eye(nsym, dtype=np.uint8)[i] for i in range(nsym)]
+        scaled = [mul[ev][:, c] for c in col]                                # [255, nsym]: e * col[j] for every error value
+        tally = {"ok": 0, "fail": 0, "miscorrect": 0}
+        for trial in range(40 if n < 20 else 10):
+            msg = rng.integers(0, 256, k, dtype=np.uint8).tobytes()
+            w = bytearray(msg + _parity_plain(msg, g))
+            ne = int(rng.integers(0, 6))
+            for pos in rng.choice(n, size=min(ne, n), replace=False):
+                w[pos] ^= int(rng.integers(1, 256))
+            diff = np.frombuffer(bytes(a ^ b for a, b in zip(_parity_plain(bytes(w[:k]), g), w[k:])), np.uint8)
+            near = set()
+
+            def fixed(errs):
+                d = bytearray(w[:k])
+                for j, e in errs:
+                    if j < k:
+                        d[j] ^= int(e)
+                return bytes(d)
+
+            if not diff.any():
+                near.add(bytes(w[:k]))
+            for j in range(n):
+                for i in np.nonzero((scaled[j] == diff).all(axis=1))[0]:
+                    near.add(fixed([(j, ev[i])]))
+                for j2 in range(j + 1, n):
+                    hit = ((scaled[j][:, None, :] ^ scaled[j2][None, :, :]) == diff).all(axis=2)
+                    for i, i2 in zip(*np.nonzero(hit)):
+                        near.add(fixed([(j, ev[i]), (j2, ev[i2])]))
+            assert len(near) <= 1                                            # minimum distance nsym + 1 >= 5
+            if near:
+                got, _ = R.correct_word(bytes(w), nsym)
+                assert got == next(iter(near))
+                tally["ok" if got == msg else "miscorrect"] += 1
+            else:
+                with pytest.raises(R.ReedSolomonError):
+                    R.correct_word(bytes(w), nsym)
+                tally["fail"] += 1
+        assert tally["ok"] and tally["fail"], (nsym, k, tally)
+
+
 def test_crc_golden(g_crc):
     for n in (0, 1, 9, 255, 4096, 20488):
         b = g_crc[f"crc_in_{n}"].tobytes()
