@@ -183,8 +183,10 @@ class Encoder:
         if self._frag_in_buffer and frag_len != olap:
             self._drop_buffered_fragment(bps)
         inbuf = frag_len if self._frag_in_buffer else 0
-        if n > 0 and frag_len in (0, olap) and bps > 0 and (frag_len == 0 or self._frag_in_buffer or self._frag_raw is not None
-                                                             or self.pcm_format.kind == "f"):
+        # Not at flush time: the reference then ends every frame it still finds with a force-flush header and shares no samples
+        # between them (encoder.py:41-44,105) -- whole frames are only left over after set_profile shrank the frame size.
+        if not flush and n > 0 and frag_len in (0, olap) and bps > 0 and (frag_len == 0 or self._frag_in_buffer
+                                                                          or self._frag_raw is not None or self.pcm_format.kind == "f"):
             hop = n - olap
             avail = len(self.buffer) // bps - inbuf              # samples not yet part of any frame
             first_need = n - frag_len

@@ -399,3 +399,100 @@ def test_decoder_state_machine_matches_the_reference_on_mangled_streams(referenc
                 assert np.max(np.abs(g - w)) <= 1e-12, trial
         cases += 1
     assert cases >= trial // 2, (cases, crashed)
+
+
+def test_encoder_state_machine_matches_the_reference_on_random_sessions(reference_libfrad):
+    """Differential test of the batched Encoder's host logic (frame cutting, overlap carry, compact frame lengths, flush and
+    force-flush markers, ECC framing, sample formats, setters called in mid-stream) against the unmodified reference Encoder
+    (libfrad/encoder.py:54-113,157-215): random sessions, the same calls on both, every returned buffer and sample count
+    equal.  The oracle stands in for the device (its integers are the reference's, tests/test_oracle_golden.py)."""
+    import random
+    import frad_python_b200 as F
+    ref = reference_libfrad
+    if 2 not in ref.fourier.AVAILABLE:
+        ref.fourier.AVAILABLE.append(2)                                   # SURVEY F3; the list object is shared with libfrad.encoder
+    rng = random.Random(int(os.environ.get("FRAD_FUZZ_SEED", "5")))
+    nrng = np.random.default_rng(9)
+    compact_sizes = list(ref.fourier.profiles.compact.SAMPLES)
+    fmts = ["f32le", "f32le", "f64be", "s16le", "s32le", "u8", "f32be", "s16be", "f64le", "s8", "u16le"]
+    sessions = torn = 0
+    for trial in range(int(os.environ.get("FRAD_FUZZ_TRIALS", "40"))):
+        prof = rng.choice([0, 1, 1, 2, 4])
+        ch = rng.choice([1, 2, 2, 3])
+        srate = rng.choice([48000, 44100, 8000, 96000]) if prof in (1, 2) else rng.choice([48000, 11111, 192000])
+        bits = rng.choice([b for b in ref.BIT_DEPTHS[prof] if b])
+        fsize = rng.choice([128, 160, 333, 500, 1000, 1024]) if prof in (1, 2) else rng.choice([1, 17, 333, 1000])
+        fmt = rng.choice(fmts)
+        dt = ref.ff_format_to_numpy_type(fmt)
+        total = rng.randrange(0, 6 * fsize + 50)
+        x = O.synth_pcm(max(total, 1) / srate + 0.001, srate, ch, seed=trial)[:total]
+        if dt.kind == "f":
+            raw = x.astype(dt).tobytes()
+        elif dt.kind == "i":
+            raw = np.clip(np.round(x * 2.0 ** (8 * dt.itemsize - 1)), -2.0 ** (8 * dt.itemsize - 1), 2.0 ** (8 * dt.itemsize - 1) - 1).astype(dt).tobytes()
+        else:
+            raw = np.clip(np.round((x + 1) * 2.0 ** (8 * dt.itemsize - 1)), 0, 2.0 ** (8 * dt.itemsize) - 1).astype(dt).tobytes()
+        raw += rng.randbytes(rng.choice([0, 0, 0, 0, 0, 1, 3]))          # now and then a torn last sample
+        a = ref.Encoder(prof, srate, ch, bits, fsize, fmt)
+        b = F.Encoder(prof, srate, ch, bits, fsize, fmt, ctx=OracleCtx())
+        for e in (a, b):
+            e.set_ecc(rng.random() < 0.3 if e is a else a.asfh.ecc, (96, 24))
+        ov = rng.choice([0, 1, 2, 3, 16, 16, 255])
+        le = rng.random() < 0.5
+        loss = rng.choice([LOSS0, 0.125, 2.0])
+        for e in (a, b):
+            e.set_overlap_ratio(ov); e.set_little_endian(le); e.set_loss_level(loss)
+        chunk = rng.choice([32768, 1000, 77, 1 << 20])
+        pos, abandoned = 0, False
+        while pos < len(raw):
+            piece = raw[pos:pos + chunk]; pos += len(piece)
+            try:
+                ra = a.process(piece)
+            except ValueError:                                            # after a channel change: bytes that are no whole rows
+                abandoned = True
+                break
+            rb = b.process(piece)
+            assert (ra.samples, ra.buf) == (rb.samples, rb.buf), (trial, "process", pos)
+            if rng.random() < 0.15:                                       # a setter in mid-stream, same call on both
+                kind = rng.randrange(5)
+                if kind == 4:                                             # another channel count / sample rate: the setter flushes
+                    ch = rng.choice([1, 2, 3])
+                    srate = rng.choice([48000, 44100, 8000, 96000]) if prof in (1, 2) else rng.choice([48000, 11111, 192000])
+                    try:
+                        sa = a.set_profile(prof, srate, ch, bits, fsize)
+                    except ValueError:                                    # rows of the old channel count torn (encoder.py:84)
+                        abandoned = True
+                        break
+                    sb = b.set_profile(prof, srate, ch, bits, fsize)
+                    assert (sa.samples, sa.buf) == (sb.samples, sb.buf), (trial, "set_profile with flush")
+                elif kind == 0:
+                    nov = rng.choice([0, 2, 8, 16])
+                    a.set_overlap_ratio(nov); b.set_overlap_ratio(nov)
+                elif kind == 1:
+                    on, pair = rng.random() < 0.5, rng.choice([(96, 24), (128, 20), (10, 7)])
+                    a.set_ecc(on, pair); b.set_ecc(on, pair)
+                elif kind == 2:
+                    nf = rng.choice([128, 256, 500]) if prof in (1, 2) else rng.choice([64, 999])
+                    nb = rng.choice([v for v in ref.BIT_DEPTHS[prof] if v])
+                    sa, sb = a.set_profile(prof, srate, ch, nb, nf), b.set_profile(prof, srate, ch, nb, nf)
+                    assert type(sa) is type(sb) or (hasattr(sa, "buf") and hasattr(sb, "buf"))
+                    if hasattr(sa, "buf"):
+                        assert (sa.samples, sa.buf) == (sb.samples, sb.buf), (trial, "set_profile")
+                else:
+                    nl = rng.choice([0.125, 0.7, 5.0])
+                    a.set_loss_level(nl); b.set_loss_level(nl)
+        if abandoned:
+            torn += 1
+            continue
+        try:
+            ra = a.flush()
+        except ValueError:                                                # a torn last sample or row: np.frombuffer / reshape raise
+            torn += 1                                                     # (encoder.py:84); the mirror encodes the whole rows and
+            assert b.flush().buf.endswith(b.asfh.force_flush())           # drops the torn one
+            continue
+        rb = b.flush()
+        assert (ra.samples, ra.buf) == (rb.samples, rb.buf), (trial, "flush", prof, ch, srate, bits, fsize, fmt, total, ov, chunk)
+        ra, rb = a.flush(), b.flush()                                     # a second flush: markers only
+        assert (ra.samples, ra.buf) == (rb.samples, rb.buf), (trial, "flush twice")
+        sessions += 1
+    assert sessions >= trial // 2 and sessions + torn == trial + 1, (sessions, torn)
