@@ -496,3 +496,55 @@ def test_encoder_state_machine_matches_the_reference_on_random_sessions(referenc
         assert (ra.samples, ra.buf) == (rb.samples, rb.buf), (trial, "flush twice")
         sessions += 1
     assert sessions >= trial // 2 and sessions + torn == trial + 1, (sessions, torn)
+
+
+def test_repairer_state_machine_matches_the_reference_on_mangled_streams(reference_libfrad, g_streams):
+    """The batched Repairer against the unmodified reference Repairer (libfrad/repairer.py:28-80) under the application's
+    loop, on streams without force-flush headers (the reference never gets past one: ADVICE r1, repairer.py:66): junk between
+    frames is passed through, frames dropped / repeated / cut short, damaged ECC frames repaired, any ECC ratio out."""
+    import random
+    import frad_python_b200 as F
+    rng = random.Random(int(os.environ.get("FRAD_FUZZ_SEED", "8")))
+    sign = O.FRM_SIGN
+
+    def frames_of(s):
+        cuts, i = [], s.find(sign)
+        while i != -1:
+            cuts.append(i)
+            i = s.find(sign, i + 4)
+        return [f for f in (s[a:b] for a, b in zip(cuts, cuts[1:] + [len(s)])) if len(f) != 12]      # force-flush headers out
+
+    base = [frames_of(g_streams[k].tobytes())[:6] for k in ("p1", "p1_ecc", "p1_ecc_bad", "p2")]          # the RS oracle is slow
+    base += [frames_of(g_streams[k].tobytes())[:2] for k in ("p0_b32", "p0_b16_le_ecc_bad")]
+
+    def loop(rp, s, chunk):
+        out, pos, calls = b"", 0, 0
+        while True:
+            piece = s[pos:pos + chunk]; pos += len(piece)
+            if not piece and rp.is_empty():
+                break
+            out += rp.process(piece); calls += 1
+            assert calls < 5000
+        return out + rp.flush()
+
+    for trial in range(int(os.environ.get("FRAD_FUZZ_TRIALS", "16"))):
+        fr = list(rng.choice(base))
+        kind = rng.randrange(5)
+        if kind == 0:
+            fr = [f for f in fr if rng.random() > 0.2]
+        elif kind == 1:
+            fr = [f for g in fr for f in [g] * rng.choice([1, 1, 2])]
+        s = b""
+        for f in fr:
+            if kind == 2 and rng.random() < 0.3:
+                s += rng.choice([rng.randbytes(rng.randrange(1, 30)), sign[:rng.randrange(1, 4)]])
+            s += f
+        if kind == 3 and len(s) > 1:
+            s = s[:rng.randrange(1, len(s))]
+        if kind == 4:
+            s = rng.randbytes(rng.randrange(0, 50)) + s + sign[:rng.randrange(0, 4)]
+        ratio = rng.choice([(96, 24), (128, 20), (10, 7), (200, 55)])
+        chunk = rng.choice([32768, 1000, 97, 1 << 20])
+        want = loop(reference_libfrad.Repairer(ratio), s, chunk)
+        got = loop(F.Repairer(ratio, ctx=OracleCtx()), s, chunk)
+        assert got == want, (trial, kind, ratio, chunk, len(got), len(want))
