@@ -548,3 +548,59 @@ def test_repairer_state_machine_matches_the_reference_on_mangled_streams(referen
         want = loop(reference_libfrad.Repairer(ratio), s, chunk)
         got = loop(F.Repairer(ratio, ctx=OracleCtx()), s, chunk)
         assert got == want, (trial, kind, ratio, chunk, len(got), len(want))
+
+
+def test_per_frame_seams_match_the_reference_functions_with_oracle_arithmetic(reference_libfrad):
+    """The level-1 seams (fourier.profileN.analogue / digital, tools.ecc, the checksums) with the oracle standing in for the
+    device, against the reference's own functions on random frames: any frame length (padding to the compact table), sample
+    rates that are not in the table, loss levels below the floor and negative, every depth, both byte orders, f32 / f64 input.
+    Host-side argument handling of the seams; payload bytes identical, decoded PCM within 1e-12."""
+    import random
+    from frad_python_b200 import fourier as MF, common as MC
+    from frad_python_b200.tools import ecc as MECC
+    ref = reference_libfrad
+    rng = random.Random(int(os.environ.get("FRAD_FUZZ_SEED", "2")))
+    ctx = OracleCtx()
+    for trial in range(int(os.environ.get("FRAD_FUZZ_TRIALS", "60"))):
+        prof = rng.choice([0, 1, 2, 4])
+        ch = rng.choice([1, 2, 3, 5])
+        le = rng.random() < 0.5
+        dt = rng.choice([np.float32, np.float64])
+        if prof in (1, 2):
+            n = rng.choice([1, 100, 128, 129, 777, 1024, 1500, 2048])
+            srate = rng.choice([48000, 44100, 8000, 50000, 7000, 96000])
+            bits = rng.choice([8, 12, 16, 24, 32, 48, 64])
+            loss = rng.choice([LOSS0, 0.01, -2.0, 0.125, 7.5])
+            x = O.synth_pcm(n / 48000 + 0.001, 48000, ch, seed=trial)[:n].astype(dt)
+            rm, mm = (ref.fourier.profile1, MF.profile1) if prof == 1 else (ref.fourier.profile2, MF.profile2)
+            want = rm.analogue(x.copy(), bits, srate, loss)
+            got = mm.analogue(x.copy(), bits, srate, loss, ctx=ctx)
+            assert tuple(got) == tuple(want), (trial, prof, n, ch, srate, bits, loss)
+            frad, fb, c, sr = want
+            for fsize in (ref.fourier.profiles.compact.get_samples_min_ge(n),):      # what the header carries (asfh.py:11-17)
+                w = rm.digital(frad, fb, c, sr, fsize)
+                g = mm.digital(frad, fb, c, sr, fsize, ctx=ctx)
+                assert g.shape == w.shape and g.dtype == w.dtype and np.max(np.abs(g - w), initial=0) <= 1e-12, (trial, fsize)
+            w = rm.digital(b"not deflate", fb, c, sr, 256)            # inflate failure: silence (profile1.py:59-60)
+            g = mm.digital(b"not deflate", fb, c, sr, 256, ctx=ctx)
+            assert g.shape == w.shape and not g.any() and not w.any()
+        else:
+            n = rng.choice([1, 2, 17, 333, 1000, 2048])
+            bits = rng.choice([12, 16, 24, 32, 48, 64])
+            srate = rng.choice([48000, 12345])
+            x = O.synth_pcm(n / 48000 + 0.001, 48000, ch, seed=trial)[:n].astype(dt)
+            rm, mm = (ref.fourier.profile0, MF.profile0) if prof == 0 else (ref.fourier.profile4, MF.profile4)
+            want = rm.analogue(x.copy(), bits, srate, le)
+            got = mm.analogue(x.copy(), bits, srate, le, ctx=ctx)
+            assert tuple(got) == tuple(want), (trial, prof, n, ch, bits, le)
+            frad, fb, c, sr = want
+            w = rm.digital(frad, fb, c, le)
+            g = mm.digital(frad, fb, c, le, ctx=ctx)
+            assert g.shape == w.shape and g.dtype == w.dtype and np.max(np.abs(g - w), initial=0) <= 1e-12, (trial, prof)
+        blob = rng.randbytes(rng.choice([0, 1, 95, 96, 97, 500]))
+        ds, cs = rng.choice([(96, 24), (128, 20), (10, 7), (1, 2)])
+        enc = ref.tools.ecc.encode(blob, ds, cs)
+        assert MECC.encode(blob, ds, cs, ctx=ctx) == enc
+        for repair in (False, True):
+            assert MECC.decode(enc, ds, cs, repair, ctx=ctx) == ref.tools.ecc.decode(enc, ds, cs, repair) == blob
+        assert MC.crc16_ansi(blob, ctx=ctx) == ref.common.crc16_ansi(blob)
