@@ -614,3 +614,55 @@ def test_per_frame_seams_match_the_reference_functions_with_oracle_arithmetic(re
         for repair in (False, True):
             assert MECC.decode(enc, ds, cs, repair, ctx=ctx) == ref.tools.ecc.decode(enc, ds, cs, repair) == blob
         assert MC.crc16_ansi(blob, ctx=ctx) == ref.common.crc16_ansi(blob)
+
+
+def test_encoder_validators_and_setters_answer_like_the_reference(reference_libfrad, capsys):
+    """verify_* / set_* / get_* (libfrad/encoder.py:115-215): the same return values and error strings for legal and illegal
+    arguments, the same stderr text from set_ecc, the same state afterwards."""
+    import itertools
+    import frad_python_b200 as F
+    ref = reference_libfrad
+    if 2 not in ref.fourier.AVAILABLE:
+        ref.fourier.AVAILABLE.insert(2, 2)                               # the experimental profile switched on (SURVEY F3)
+    RE, ME = ref.Encoder, F.Encoder
+
+    def ans(fn, *args):
+        try:
+            return fn(*args)
+        except Exception as e:                                            # e.g. a sample rate above the table: min() of nothing
+            return ("raises", type(e).__name__)
+
+    for prof in (0, 1, 2, 3, 4, 7):
+        assert ME.verify_profile(prof) == RE.verify_profile(prof)
+    for prof, v in itertools.product((0, 1, 2, 4), (0, 1, 8, 12, 16, 20, 24, 32, 48, 64, 4000, 44100, 48000, 50000, 96000, 200000,
+                                                     2 ** 20, 2 ** 32)):
+        assert ans(ME.verify_srate, prof, v) == ans(RE.verify_srate, prof, v)
+        assert ans(ME.verify_channels, prof, v) == ans(RE.verify_channels, prof, v)
+        assert ans(ME.verify_bit_depth, prof, v) == ans(RE.verify_bit_depth, prof, v)
+        assert ans(ME.verify_frame_size, prof, v) == ans(RE.verify_frame_size, prof, v)
+
+    def state(e):
+        a = e.asfh
+        return (e.get_profile(), e.get_srate(), e.get_channels(), e.get_bit_depth(), e.get_frame_size(), e.loss_level, e.init,
+                a.ecc, a.ecc_dsize, a.ecc_codesize, a.endian, a.overlap_ratio)
+
+    def same(x, y):
+        if hasattr(x, "buf") or hasattr(y, "buf"):
+            return (x.buf, x.samples) == (y.buf, y.samples)
+        return x == y
+
+    a, b = RE(1, 48000, 2, 16, 2048, "f32le"), ME(1, 48000, 2, 16, 2048, "f32le", ctx=OracleCtx())
+    calls = [("set_profile", (9, 48000, 2, 16, 2048)), ("set_profile", (1, 50000, 2, 16, 2048)), ("set_profile", (1, 48000, 0, 16, 2048)),
+             ("set_profile", (1, 48000, 2, 20, 2048)), ("set_profile", (1, 48000, 2, 16, 10 ** 6)), ("set_profile", (0, 12345, 3, 24, 777)),
+             ("set_srate", (0,)), ("set_srate", (22050,)), ("set_srate", (10 ** 6,)), ("set_channels", (0,)), ("set_channels", (5,)), ("set_frame_size", (0,)),
+             ("set_frame_size", (4096,)), ("set_frame_size", (2 ** 31,)), ("set_bit_depth", (0,)), ("set_bit_depth", (13,)), ("set_bit_depth", (64,)),
+             ("set_ecc", (True, (0, 24))), ("set_ecc", (True, (200, 100))), ("set_ecc", (False, (128, 20))), ("set_little_endian", (True,)),
+             ("set_loss_level", (-3.0,)), ("set_loss_level", (0.0,)), ("set_overlap_ratio", (1,)), ("set_overlap_ratio", (0,)),
+             ("set_overlap_ratio", (1000,)), ("set_profile", (2, 44100, 1, 8, 128))]
+    for name, args in calls:
+        capsys.readouterr()
+        ra = ans(getattr(a, name), *args)
+        ea = capsys.readouterr().err
+        rb = ans(getattr(b, name), *args)
+        eb = capsys.readouterr().err
+        assert same(ra, rb) and ea == eb and state(a) == state(b), (name, args, ra, rb, state(a), state(b))
