@@ -666,3 +666,59 @@ def test_encoder_validators_and_setters_answer_like_the_reference(reference_libf
         rb = ans(getattr(b, name), *args)
         eb = capsys.readouterr().err
         assert same(ra, rb) and ea == eb and state(a) == state(b), (name, args, ra, rb, state(a), state(b))
+
+
+def test_unmodified_reference_objects_run_on_the_patched_seams(reference_libfrad, g_streams, monkeypatch):
+    """The level-1 drop-in end to end on the build box: install.patch_reference swaps the seams, then the reference's OWN
+    Encoder / Decoder / Repairer (untouched code: encoder.py:54-113, decoder.py:48-104, repairer.py:28-73) run on them and
+    must reproduce the streams and the PCM the unpatched reference wrote into tests/golden/streams.npz.  The oracle stands in
+    for the device behind the seams' default context (no GPU here); every argument the reference passes -- float64 frames,
+    padded or ragged, bytes, header checksums -- goes through the replacement functions."""
+    import frad_python_b200 as F
+    from frad_python_b200 import install
+    ctx = OracleCtx()
+    for mod in (F.common, F.fourier.profile0, F.fourier.profile1, F.fourier.profile2, F.tools.ecc):
+        monkeypatch.setattr(mod, "default_context", lambda: ctx)
+    lf = reference_libfrad
+    install.patch_reference(lf)
+    try:
+        assert lf.fourier.profile1.analogue is F.fourier.profile1.analogue
+        pcm = g_streams["pcm"]
+
+        def encode(profile, bits, ecc=False, le=False, ov=16, src=pcm, fmt="f32le", fsize=2048):
+            enc = lf.Encoder(profile, 48000, 2, bits, fsize, fmt)
+            enc.set_ecc(ecc, (96, 24)); enc.set_little_endian(le); enc.set_overlap_ratio(ov); enc.set_loss_level(LOSS0)
+            raw, out = src.tobytes(), b""
+            for i in range(0, len(raw), 32768):
+                out += enc.process(raw[i:i + 32768]).buf
+            return out + enc.flush().buf
+
+        assert encode(1, 16) == g_streams["p1"].tobytes()
+        assert encode(2, 16) == g_streams["p2"].tobytes()
+        assert encode(1, 16, ecc=True) == g_streams["p1_ecc"].tobytes()
+        assert encode(0, 32) == g_streams["p0_b32"].tobytes()
+        assert encode(0, 16, ecc=True, le=True) == g_streams["p0_b16_le_ecc"].tobytes()
+        assert encode(0, 24, src=g_streams["pcm_s16"], fmt="s16le", fsize=1000) == g_streams["p0_s16_b24"].tobytes()
+
+        def decode(name, fix=False):
+            dec = lf.Decoder(fix)
+            s, out = g_streams[name].tobytes(), []
+            for i in range(0, len(s), 32768):
+                r = dec.process(s[i:i + 32768])
+                if r.pcm.size:
+                    out.append(r.pcm)
+            r = dec.flush()
+            if r.pcm.size:
+                out.append(r.pcm)
+            return np.concatenate(out)
+
+        for name, fix in (("p1", False), ("p2", False), ("p0_b32", False), ("p1_ecc", True), ("p1_ecc_bad", True),
+                          ("p0_b16_le_ecc_bad", True)):
+            got, want = decode(name, fix), g_streams[name + "_dec"]
+            assert got.shape == want.shape and np.max(np.abs(got - want)) <= 1e-13, name
+
+        rp = lf.Repairer((96, 24))
+        s = g_streams["p0_b32"].tobytes()
+        assert rp.process(s) + rp.flush() == g_streams["p0_b32_rep"].tobytes()
+    finally:
+        install.unpatch_reference()
