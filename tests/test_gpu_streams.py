@@ -299,3 +299,63 @@ def test_profile4_streams_byte_exact(F, g_p4):
     # the decoder can hand out the file's own sample format
     got = run_decoder(F, g["s_b32"].tobytes(), pcm_format="<i2")
     assert np.array_equal(got, O.pcm_from_f64(g["s_b32_dec"], "<i2"))
+
+
+def test_profile4_random_sessions_on_the_device_match_the_oracle_backed_mirror(F):
+    """Random Encoder sessions of the PCM-archive profile (no transform: every byte is exact) on the device against the same
+    sessions with the oracle behind the mirror -- which tests/test_dropin.py ties to the unmodified reference Encoder call by
+    call: sample formats incl. big-endian ones, channel counts, depths (with the overflow bump of raw big-endian integers),
+    ECC ratios, chunkings, setters in mid-stream.  Then both Decoders on the stream, with and without repair."""
+    import random
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from stubctx import OracleCtx
+    rng = random.Random(17)
+    fmts = ["f32le", "f64le", "s16le", "s32le", "u8", "f32be", "f64be", "s16be", "s32be", "s8", "u16le", "f16le"]
+    for trial in range(24):
+        ch = rng.choice([1, 2, 3, 8])
+        srate = rng.choice([48000, 11111, 192000])
+        bits = rng.choice([12, 16, 24, 32, 48, 64])
+        fsize = rng.choice([1, 17, 333, 1000, 2048, 4096])
+        fmt = rng.choice(fmts)
+        a = F.Encoder(4, srate, ch, bits, fsize, fmt, ctx=OracleCtx())
+        b = F.Encoder(4, srate, ch, bits, fsize, fmt)
+        dt = a.pcm_format
+        total = rng.randrange(0, 9 * fsize + 50)
+        x = O.synth_pcm(max(total, 1) / srate + 0.001, srate, ch, seed=100 + trial)[:total]
+        if dt.kind == "f":
+            raw = x.astype(dt).tobytes()
+        elif dt.kind == "i":
+            raw = np.clip(np.round(x * 2.0 ** (8 * dt.itemsize - 1)), -2.0 ** (8 * dt.itemsize - 1), 2.0 ** (8 * dt.itemsize - 1) - 1).astype(dt).tobytes()
+        else:
+            raw = np.clip(np.round((x + 1) * 2.0 ** (8 * dt.itemsize - 1)), 0, 2.0 ** (8 * dt.itemsize) - 1).astype(dt).tobytes()
+        ecc, pair, le = rng.random() < 0.5, rng.choice([(96, 24), (128, 20), (10, 7)]), rng.random() < 0.5
+        for e in (a, b):
+            e.set_ecc(ecc, pair); e.set_little_endian(le)
+        chunk = rng.choice([32768, 1000, 1 << 20])
+        pos, sa, sb = 0, b"", b""
+        while pos < len(raw):
+            piece = raw[pos:pos + chunk]; pos += len(piece)
+            ra, rb = a.process(piece), b.process(piece)
+            assert (ra.samples, ra.buf) == (rb.samples, rb.buf), (trial, fmt, ch, bits, fsize, "process", pos)
+            sa += ra.buf; sb += rb.buf
+            if rng.random() < 0.2:
+                kind = rng.randrange(3)
+                if kind == 0:
+                    on, pr = rng.random() < 0.5, rng.choice([(96, 24), (200, 55), (1, 2)])
+                    a.set_ecc(on, pr); b.set_ecc(on, pr)
+                elif kind == 1:
+                    nb, nf = rng.choice([12, 16, 24, 32, 48, 64]), rng.choice([64, 999, 2048])
+                    ra, rb = a.set_profile(4, srate, ch, nb, nf), b.set_profile(4, srate, ch, nb, nf)
+                    assert (ra.samples, ra.buf) == (rb.samples, rb.buf), (trial, "set_profile")
+                else:
+                    le = not le
+                    a.set_little_endian(le); b.set_little_endian(le)
+        ra, rb = a.flush(), b.flush()
+        assert (ra.samples, ra.buf) == (rb.samples, rb.buf), (trial, fmt, ch, bits, fsize, "flush")
+        sa += ra.buf
+        for fix in (False, True):
+            want = run_decoder(F, sa, fix, chunk, ctx=OracleCtx()) if len(sa) > 24 and total else None
+            if want is not None:
+                got = run_decoder(F, sa, fix, chunk)
+                assert got.shape == want.shape and np.array_equal(got, want), (trial, fmt, ch, bits, fsize, fix)
