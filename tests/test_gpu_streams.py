@@ -359,3 +359,67 @@ def test_profile4_random_sessions_on_the_device_match_the_oracle_backed_mirror(F
             if want is not None:
                 got = run_decoder(F, sa, fix, chunk)
                 assert got.shape == want.shape and np.array_equal(got, want), (trial, fmt, ch, bits, fsize, fix)
+
+
+def test_repairer_on_the_device_matches_the_oracle_backed_mirror_on_mangled_streams(F, g_streams):
+    """The batched Repairer with the device's CRC / Reed-Solomon kernels against the same object with the oracle behind it
+    (tied to the unmodified reference Repairer in tests/test_dropin.py) under the application's loop: junk between frames,
+    frames dropped / repeated / cut short, damaged ECC frames (correctable and not), force-flush headers, any output ratio,
+    random extra corruption of payload bytes.  Bytes identical."""
+    import random
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from stubctx import OracleCtx
+    rng = random.Random(23)
+    sign = O.FRM_SIGN
+
+    def frames_of(s):
+        cuts, i = [], s.find(sign)
+        while i != -1:
+            cuts.append(i)
+            i = s.find(sign, i + 4)
+        return [s[a:b] for a, b in zip(cuts, cuts[1:] + [len(s)])]
+
+    base = [frames_of(g_streams[k].tobytes()) for k in ("p1", "p1_ecc", "p1_ecc_bad", "p2")]
+    base += [frames_of(g_streams[k].tobytes())[:3] for k in ("p0_b32", "p0_b16_le_ecc_bad")]
+
+    def loop(rp, s, chunk):
+        out, pos, calls = b"", 0, 0
+        while True:
+            piece = s[pos:pos + chunk]; pos += len(piece)
+            if not piece and rp.is_empty():
+                break
+            out += rp.process(piece); calls += 1
+            assert calls < 5000
+        return out + rp.flush()
+
+    for trial in range(20):
+        fr = list(rng.choice(base))
+        kind = rng.randrange(6)
+        if kind == 0:
+            fr = [f for f in fr if rng.random() > 0.2]
+        elif kind == 1:
+            fr = [f for g in fr for f in [g] * rng.choice([1, 1, 2])]
+        elif kind == 5:                                                   # more damage: a few payload bytes of some frames
+            out = []
+            for f in fr:
+                f = bytearray(f)
+                if len(f) > 64 and rng.random() < 0.5:
+                    for _ in range(rng.randrange(1, 30)):
+                        f[rng.randrange(40, len(f))] ^= rng.randrange(1, 256)
+                out.append(bytes(f))
+            fr = out
+        s = b""
+        for f in fr:
+            if kind == 2 and rng.random() < 0.3:
+                s += rng.choice([rng.randbytes(rng.randrange(1, 30)), sign[:rng.randrange(1, 4)]])
+            s += f
+        if kind == 3 and len(s) > 1:
+            s = s[:rng.randrange(1, len(s))]
+        if kind == 4:
+            s = rng.randbytes(rng.randrange(0, 50)) + s + sign[:rng.randrange(0, 4)]
+        ratio = rng.choice([(96, 24), (128, 20), (10, 7), (200, 55)])
+        chunk = rng.choice([32768, 1000, 1 << 20])
+        want = loop(F.Repairer(ratio, ctx=OracleCtx()), s, chunk)
+        got = loop(F.Repairer(ratio), s, chunk)
+        assert got == want, (trial, kind, ratio, chunk, len(got), len(want))
