@@ -423,3 +423,100 @@ def test_repairer_on_the_device_matches_the_oracle_backed_mirror_on_mangled_stre
         want = loop(F.Repairer(ratio, ctx=OracleCtx()), s, chunk)
         got = loop(F.Repairer(ratio), s, chunk)
         assert got == want, (trial, kind, ratio, chunk, len(got), len(want))
+
+
+def test_decoder_on_the_device_matches_the_oracle_backed_mirror_on_mangled_streams(F, g_streams):
+    """The batched Decoder on the device (fused parse / dequantise / inverse / cross-fade route, run splitting, per-frame
+    fall-backs, ECC repair, output sample formats) against the same object with the oracle behind it -- tied to the unmodified
+    reference Decoder in tests/test_dropin.py -- on spliced, mangled and truncated streams of several shapes under the reference
+    application's read loop.  f64 PCM within 2e-12; integer formats within one step on at most 0.1 % of the samples."""
+    import random
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from stubctx import OracleCtx
+    rng = random.Random(29)
+    sign = O.FRM_SIGN
+
+    def make(profile, bits, srate, ch, fsize, ov, secs=0.12, ecc=False):
+        pcm = O.synth_pcm(secs, srate, ch, seed=profile * 10 + ch)
+        enc = F.Encoder(profile, srate, ch, bits, fsize, "f32le", ctx=OracleCtx())
+        enc.set_ecc(ecc, (96, 24)); enc.set_overlap_ratio(ov); enc.set_loss_level(LOSS0)
+        return enc.process(pcm.astype(np.float32).tobytes()).buf + enc.flush().buf
+
+    base = {
+        "p1": g_streams["p1"].tobytes(), "p2": g_streams["p2"].tobytes(), "p0": g_streams["p0_b32"].tobytes()[:5 * (32 + 16384)],
+        "p1_ecc_bad": g_streams["p1_ecc_bad"].tobytes(), "p1_noov": g_streams["p1_noov"].tobytes(),
+        "p1_mono_44k": make(1, 16, 44100, 1, 1280, 8), "p0_mono_8k": make(0, 16, 8000, 1, 333, 0, 0.5),
+        "p4_3ch": make(4, 24, 48000, 3, 700, 0), "p2_96k": make(2, 16, 96000, 2, 512, 2, 0.05),
+    }
+
+    def frames_of(s):
+        cuts, i = [], s.find(sign)
+        while i != -1:
+            cuts.append(i)
+            i = s.find(sign, i + 4)
+        return [s[a:b] for a, b in zip(cuts, cuts[1:] + [len(s)])]
+
+    def mangle(s):
+        fr = frames_of(s)
+        kind = rng.randrange(6)
+        if kind == 0:
+            out = b""
+            for f in fr:
+                if rng.random() < 0.3:
+                    out += rng.choice([rng.randbytes(rng.randrange(1, 40)), sign[:rng.randrange(1, 4)], b"\xff" * 5])
+                out += f
+            return out
+        if kind == 1 and len(fr) > 3:
+            return b"".join(f for f in fr if rng.random() > 0.25)
+        if kind == 2 and len(fr) > 1:
+            return b"".join(f * rng.choice([1, 1, 2, 3]) for f in fr)
+        if kind == 3:
+            return s[:rng.randrange(1, len(s))]
+        if kind == 4:
+            return rng.randbytes(rng.randrange(0, 100)) + s + sign[:rng.randrange(0, 4)]
+        return s
+
+    def app_loop(dec, stream, chunk):
+        out, pos, calls = [], 0, 0
+        while True:
+            piece = stream[pos:pos + chunk]; pos += len(piece)
+            if not piece and dec.is_empty():
+                break
+            r = dec.process(piece); calls += 1
+            assert calls < 5000
+            if getattr(r.pcm, "ndim", 1) == 2 and len(r.pcm):
+                out.append(np.asarray(r.pcm))
+        r = dec.flush()
+        if getattr(r.pcm, "ndim", 1) == 2 and len(r.pcm):
+            out.append(np.asarray(r.pcm))
+        return out
+
+    names, compared = sorted(base), 0
+    for trial in range(30):
+        picked = [rng.choice(names) for _ in range(rng.choice([1, 1, 2, 3]))]
+        stream = b"".join(mangle(base[k]) for k in picked)
+        chunk = rng.choice([32768, 4096, 1000, 1 << 20])
+        fix = rng.random() < 0.4 or "p1_ecc_bad" in picked               # damaged frames are repaired or silenced, never parsed
+        fmt = rng.choice([None, None, "<i2", "<f4", "u1", ">i4", ">f8"])
+        kw = {} if fmt is None else {"pcm_format": np.dtype(fmt)}
+        try:
+            want = app_loop(F.Decoder(fix, ctx=OracleCtx(), **kw), stream, chunk)
+        except (ValueError, IndexError):                                  # two channel counts in one result, a damaged header
+            want = None
+        try:
+            got = app_loop(F.Decoder(fix, **kw), stream, chunk)
+        except (ValueError, IndexError):
+            assert want is None, trial
+            continue
+        assert want is not None, trial
+        assert [g.shape for g in got] == [w.shape for w in want] and [g.dtype for g in got] == [w.dtype for w in want], trial
+        for g, w in zip(got, want):
+            g, w = g.astype(np.float64), w.astype(np.float64)
+            if fmt is None or np.dtype(fmt).kind == "f":
+                scale = max(1.0, float(np.max(np.abs(w), initial=0)))
+                assert np.max(np.abs(g - w), initial=0) <= (2e-12 if fmt != "<f4" else 1e-6) * scale, (trial, fmt)
+            else:
+                assert np.max(np.abs(g - w), initial=0) <= 1 and np.mean(g != w) <= 1e-3, (trial, fmt)
+        compared += 1
+    assert compared >= 15
