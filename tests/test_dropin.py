@@ -6,6 +6,7 @@ like libfrad drives an Encoder -> Decoder round of one frame through the patched
 libfrad/encoder.py:96-104 and decoder.py:63-74 call them (attribute lookup at call time).
 CPU part also covers the Repairer's host logic on streams that end in ForceFlush headers (oracle-backed stub context)."""
 import inspect
+import struct
 import os
 import sys
 import types
@@ -318,7 +319,8 @@ def _app_loop(dec, stream: bytes, chunk: int):
     return out
 
 
-def test_decoder_state_machine_matches_the_reference_on_mangled_streams(reference_libfrad, g_streams):
+@pytest.mark.parametrize("sharded", [False, True])
+def test_decoder_state_machine_matches_the_reference_on_mangled_streams(reference_libfrad, g_streams, sharded):
     """Differential test of the batched Decoder's host logic (frame sync, header walk, runs, critical-info changes, force
     flush, truncation, cross-fade carry) against the unmodified reference Decoder (libfrad/decoder.py:48-110), both driven by
     the reference application's loop.  Streams: the reference-made golden streams, streams of other shapes made by the Encoder
@@ -372,7 +374,7 @@ def test_decoder_state_machine_matches_the_reference_on_mangled_streams(referenc
         return s
 
     names = sorted(base)
-    cases = crashed = 0
+    cases = crashed = nshard = 0
     for trial in range(int(os.environ.get("FRAD_FUZZ_TRIALS", "48"))):
         parts = [mangle(base[rng.choice(names)]) for _ in range(rng.choice([1, 1, 2, 3]))]
         stream = b"".join(parts)
@@ -380,7 +382,7 @@ def test_decoder_state_machine_matches_the_reference_on_mangled_streams(referenc
         fix = rng.random() < 0.3
         try:
             want = _app_loop(reference_libfrad.Decoder(fix), stream, chunk)
-        except (ValueError, IndexError):  # the reference's DecodeResult cannot join an empty flush (1-D) to frames (decoder.py:13,
+        except (ValueError, IndexError, struct.error):  # (struct.error: a payload cut short by the mangling, p1tools.py:63) the reference's DecodeResult cannot join an empty flush (1-D) to frames (decoder.py:13,
             want = None                 # :99-100), nor frames of two channel counts (its info aliases its asfh after the first
             crashed += 1                # header, decoder.py:93, so no critical-info change is ever reported), and its overlap()
                                         # indexes a fragment of fewer channels out of bounds (decoder.py:37)
@@ -392,8 +394,14 @@ def test_decoder_state_machine_matches_the_reference_on_mangled_streams(referenc
             with np.errstate(all="ignore"):
                 want = [(reference_libfrad.from_f64(w, dt).astype(dt).astype(np.float64), sh, sr) for w, sh, sr in want]
         try:
-            got = _app_loop(F.Decoder(fix, ctx=OracleCtx(), pcm_format=None if fmt is None else
-                                      reference_libfrad.ff_format_to_numpy_type(fmt)), stream, chunk)
+            pf = None if fmt is None else reference_libfrad.ff_format_to_numpy_type(fmt)
+            if sharded:                 # the same object cut by frame range over three contexts, runs of >= 2 frames
+                from frad_python_b200.shard import ShardedDecoder
+                dec = ShardedDecoder(fix, ctxs=[OracleCtx() for _ in range(3)], min_frames_per_shard=1, pcm_format=pf)
+            else:
+                dec = F.Decoder(fix, ctx=OracleCtx(), pcm_format=pf)
+            got = _app_loop(dec, stream, chunk)
+            nshard += getattr(dec, "sharded_batches", 0)
         except (ValueError, IndexError):
             assert want is None, trial  # the mirror only fails where the reference does (two channel counts in one result, a
                                         # sample-rate index beyond the table in a damaged header: tools/asfh.py:29)
@@ -408,10 +416,11 @@ def test_decoder_state_machine_matches_the_reference_on_mangled_streams(referenc
                 bad = np.abs(g - w) > (1e-6 if fmt == "f32le" else tol)  # side of an integer for values 1e-13 apart
                 assert not bad.any() and (fmt is None or fmt[0] == "f" or np.mean(g != w) < 1e-3), (trial, fmt)
         cases += 1
-    assert cases >= trial // 2, (cases, crashed)
+    assert cases >= trial // 2 and (nshard > 0) == sharded, (cases, crashed, nshard)
 
 
-def test_encoder_state_machine_matches_the_reference_on_random_sessions(reference_libfrad):
+@pytest.mark.parametrize("sharded", [False, True])
+def test_encoder_state_machine_matches_the_reference_on_random_sessions(reference_libfrad, sharded):
     """Differential test of the batched Encoder's host logic (frame cutting, overlap carry, compact frame lengths, flush and
     force-flush markers, ECC framing, sample formats, setters called in mid-stream) against the unmodified reference Encoder
     (libfrad/encoder.py:54-113,157-215): random sessions, the same calls on both, every returned buffer and sample count
@@ -425,7 +434,7 @@ def test_encoder_state_machine_matches_the_reference_on_random_sessions(referenc
     nrng = np.random.default_rng(9)
     compact_sizes = list(ref.fourier.profiles.compact.SAMPLES)
     fmts = ["f32le", "f32le", "f64be", "s16le", "s32le", "u8", "f32be", "s16be", "f64le", "s8", "u16le"]
-    sessions = torn = 0
+    sessions = torn = nshard = 0
     for trial in range(int(os.environ.get("FRAD_FUZZ_TRIALS", "40"))):
         prof = rng.choice([0, 1, 1, 2, 4])
         ch = rng.choice([1, 2, 2, 3])
@@ -444,7 +453,11 @@ def test_encoder_state_machine_matches_the_reference_on_random_sessions(referenc
             raw = np.clip(np.round((x + 1) * 2.0 ** (8 * dt.itemsize - 1)), 0, 2.0 ** (8 * dt.itemsize) - 1).astype(dt).tobytes()
         raw += rng.randbytes(rng.choice([0, 0, 0, 0, 0, 1, 3]))          # now and then a torn last sample
         a = ref.Encoder(prof, srate, ch, bits, fsize, fmt)
-        b = F.Encoder(prof, srate, ch, bits, fsize, fmt, ctx=OracleCtx())
+        if sharded:                     # the same object cut by frame range over three contexts
+            from frad_python_b200.shard import ShardedEncoder
+            b = ShardedEncoder(prof, srate, ch, bits, fsize, fmt, ctxs=[OracleCtx() for _ in range(3)], min_frames_per_shard=1)
+        else:
+            b = F.Encoder(prof, srate, ch, bits, fsize, fmt, ctx=OracleCtx())
         for e in (a, b):
             e.set_ecc(rng.random() < 0.3 if e is a else a.asfh.ecc, (96, 24))
         ov = rng.choice([0, 1, 2, 3, 16, 16, 255])
@@ -505,7 +518,8 @@ def test_encoder_state_machine_matches_the_reference_on_random_sessions(referenc
         ra, rb = a.flush(), b.flush()                                     # a second flush: markers only
         assert (ra.samples, ra.buf) == (rb.samples, rb.buf), (trial, "flush twice")
         sessions += 1
-    assert sessions >= trial // 2 and sessions + torn == trial + 1, (sessions, torn)
+        nshard += getattr(b, "sharded_batches", 0)
+    assert sessions >= trial // 2 and sessions + torn == trial + 1 and (nshard > 0) == sharded, (sessions, torn, nshard)
 
 
 def test_repairer_state_machine_matches_the_reference_on_mangled_streams(reference_libfrad, g_streams):
