@@ -193,6 +193,7 @@ class ShardedDecoder(Decoder):
         else:
             regular = regular and not have
         if not regular:
+            self.last_shards = 1
             return Decoder._decode_run(self, run)
         self.last_shards = shards
         self.sharded_batches += 1
