@@ -355,7 +355,15 @@ def test_decoder_state_machine_matches_the_reference_on_mangled_streams(referenc
 
     def mangle(s):
         fr = frames_of(s)
-        kind = rng.randrange(6)
+        kind = rng.randrange(7)
+        if kind == 6:                                                    # a damaged header: one bit of the frame length, of the
+            out = b""                                                    # profile / ECC / byte order / depth byte or of byte 11
+            for f in fr:                                                 # (overlap ratio; an ECC size in lossless headers).  The
+                if rng.random() < 0.25 and len(f) > 12:                  # channel / rate / frame-size fields stay: a lossy frame
+                    f = bytearray(f)                                     # with fewer threshold integers than its header promises
+                    f[rng.choice([4, 5, 6, 7, 8, 11])] ^= 1 << rng.randrange(8)   # is dequantised differently
+                out += bytes(f)
+            return out
         if kind == 0:                                                    # junk between frames
             out = b""
             for f in fr:
