@@ -441,7 +441,7 @@ def test_encoder_state_machine_matches_the_reference_on_random_sessions(referenc
     rng = random.Random(int(os.environ.get("FRAD_FUZZ_SEED", "5")))
     nrng = np.random.default_rng(9)
     compact_sizes = list(ref.fourier.profiles.compact.SAMPLES)
-    fmts = ["f32le", "f32le", "f64be", "s16le", "s32le", "u8", "f32be", "s16be", "f64le", "s8", "u16le"]
+    fmts = ["f32le", "f32le", "f64be", "s16le", "s32le", "u8", "f32be", "s16be", "f64le", "s8", "u16le", "s32be", "u64le", "s64be", "f16le"]
     sessions = torn = nshard = 0
     for trial in range(int(os.environ.get("FRAD_FUZZ_TRIALS", "40"))):
         prof = rng.choice([0, 1, 1, 2, 4])
